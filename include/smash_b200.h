@@ -1,0 +1,164 @@
+/* include/smash_b200.h -- C ABI of libsmash_b200.so (hand-written sm_100a CUDA behind it).
+ *
+ * The reference (yamrom/smash-paper) has no plugin/FFI interface; its boundary is the `mummer`
+ * process + the `<ref>.bin/` index files + `mapout/*.txt`, and inside the process the seam
+ * `Aligner::run -> longSA::MAM|MEM(Aligner&) -> Aligner::process_match` (query.cpp:322-329,
+ * 436-438).  Every entry point below names the reference interface it replaces.  Plain
+ * pointers and sizes only; all calls return 0 on success or a negative smash_status, with the
+ * message available from smash_last_error().  There is NO CPU fallback: every compute call
+ * fails with SMASH_ERR_CUDA when no sm_100 device / driver is present.
+ *
+ * Threading: one smash_ctx per GPU, calls on one ctx are serialised by the caller; different
+ * ctxs (different GPUs / processes) are independent.  The index object is immutable.
+ */
+#ifndef SMASH_B200_H_
+#define SMASH_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  SMASH_OK = 0,
+  SMASH_ERR_ARG = -1,      /* bad argument */
+  SMASH_ERR_IO = -2,       /* index file missing / malformed (paa::Error in fasta.cpp:103-119, longSA.cpp:115-125) */
+  SMASH_ERR_CUDA = -3,     /* CUDA failure or no device */
+  SMASH_ERR_NOMEM = -4,
+  SMASH_ERR_STATE = -5,    /* call order (e.g. bins not loaded) */
+  SMASH_ERR_DATA = -6      /* input the reference itself rejects (e.g. mappability_tag.cpp:107-113) */
+} smash_status;
+
+typedef struct smash_index smash_index;   /* host view of <fa>.bin/ (mmap) or of caller arrays */
+typedef struct smash_ctx smash_ctx;       /* one GPU: index in HBM + batch buffers + tail state */
+
+/* match_t (longSA.h:78-92) */
+typedef struct { uint64_t ref, query, len; } smash_match;
+
+enum { SMASH_MODE_MUM = 0, SMASH_MODE_MAM = 1, SMASH_MODE_MEM = 2 };   /* mum_t, query.h:126 */
+
+const char *smash_last_error(void);
+/* Number of usable sm_100 devices (0 without a driver/GPU). */
+int smash_device_count(void);
+
+/* ---- index: replaces Sequence::Sequence load branch (fasta.cpp:106-137) and the longSA load
+ * branch (longSA.cpp:112-136, util.cpp:100-125).  File names and formats unchanged:
+ * <fa>.bin/rc{r}.ref.bin, .ref.seq.bin, rc{r}.i{4|8}.index.bin, .sa.bin, .isa.bin, .lcp.vec.bin,
+ * .lcp.m.bin (+ optional map.bin).  The FASTA itself is only stat()ed for the size guard. */
+int smash_index_open(const char *ref_fasta, int rcref, smash_index **out);
+/* Same object from caller-owned arrays (no files): text N bytes; sa/isa N*w bytes (isa may be
+ * NULL: only MEM mode and mappability generation need it); lcp_vec N bytes; lcp_m n_m 16-byte
+ * items {u64 idx; u64 val}.  Pointers must stay valid until smash_index_close. */
+int smash_index_from_arrays(const uint8_t *text, uint64_t N, const void *sa, const void *isa, int w,
+                            const uint8_t *lcp_vec, const void *lcp_m, uint64_t n_m,
+                            uint64_t n_descr, const uint64_t *startpos, const uint64_t *sizes,
+                            const char *const *descr, int rcref, smash_index **out);
+void smash_index_close(smash_index *ix);
+uint64_t smash_index_text_len(const smash_index *ix);
+int smash_index_int_width(const smash_index *ix);
+/* Sequence::sam_header() (fasta.cpp:243-252); returns bytes needed. */
+size_t smash_index_sam_header(const smash_index *ix, char *buf, size_t cap);
+
+/* ---- context: replaces Pairs/Pair/Aligner construction (query.cpp:471-475, 537-563) */
+typedef struct {
+  int device;            /* CUDA ordinal */
+  int mode;              /* SMASH_MODE_MAM (default, -mumreference) or SMASH_MODE_MEM (-maxmatch) */
+  uint32_t min_len;      /* -l, default 20 (query.h:129) */
+  int nomap;             /* -nomap */
+  int nucleotides_only;  /* -n (query.cpp:131-138) */
+  int tag_mappability;   /* append mappability_tag's L<i>/R<i> tags to every record (needs map.bin) */
+  uint64_t max_batch_reads;   /* capacity hint, 0 = default */
+  int seed_k;            /* 0 = auto; k-mer length of the derived seed table (<=16) */
+} smash_params;
+void smash_params_default(smash_params *p);
+
+int smash_ctx_create(const smash_index *ix, const smash_params *p, smash_ctx **out);
+void smash_ctx_destroy(smash_ctx *ctx);
+/* map.bin (longSA::show_mappability output, longSA.cpp:612-690; 2 junk bytes + 2 bytes/base) for
+ * the L/R tags and the smashMEM excess-mappability filter.  body = file contents after the two
+ * junk bytes.  Without it smash_map_batch still works (untagged SAM), the tail does not. */
+int smash_ctx_load_mappability(smash_ctx *ctx, const uint8_t *body, uint64_t n_bytes);
+/* Build map.bin's body on the GPU from SA/ISA/LCP (needs isa). Copies to host if body != NULL. */
+int smash_ctx_build_mappability(smash_ctx *ctx, uint8_t *body, uint64_t cap_bytes);
+
+/* ---- one batch of reads = what QueryReader::run hands to Pair::run (query.cpp:614-687, 481-520).
+ * Reads 2k and 2k+1 are mates-by-arrival; n_reads must be even except for the last batch.
+ * names: SAM column 1 without the :0/:1 suffix; read_flag: 0/65/129 as Aligner::reset derives it
+ * (query.cpp:185-201); seq: original-case bases; qual; opt: "\tTAG:..." for every extra field. */
+typedef struct {
+  uint64_t n_reads;
+  const uint8_t *names;  const int64_t *name_off;   /* n_reads+1 */
+  const uint8_t *seq;    const uint8_t *qual;  const int64_t *seq_off;
+  const uint8_t *opt;    const int64_t *opt_off;    /* may be NULL */
+  const uint16_t *read_flag;
+  uint64_t first_pair_ordinal;   /* global index of the batch's first pair (dedupe order) */
+} smash_batch;
+
+typedef struct {
+  uint64_t n_reads, n_matches, n_records, sam_bytes;
+  /* Pointers into ctx-owned PINNED host memory, valid until the next smash_map_batch on this
+   * ctx.  sam = record lines in input order (read 0's records in HI order, read 1's, ...). */
+  const char *sam;
+  const int64_t *match_off;       /* n_reads+1; NULL unless want_matches */
+  const smash_match *matches;
+  float gpu_ms;                   /* device time of this batch's kernels (CUDA events) */
+} smash_result;
+
+enum { SMASH_WANT_SAM = 1, SMASH_WANT_MATCHES = 2, SMASH_WANT_TAIL = 4 };
+
+/* Pinned host memory for batches (cudaHostAlloc): buffers handed to smash_map_batch /
+ * smash_submit from here are copied with true asynchronous DMA. */
+void *smash_host_alloc(size_t bytes);
+void smash_host_free(void *p);
+
+/* Host buffers in, host buffers out: H2D copy, search, records, SAM text, (tail accumulation),
+ * D2H copy.  Replaces Aligner::run + set_mate + print_matches for the whole batch. */
+int smash_map_batch(smash_ctx *ctx, const smash_batch *b, int want, smash_result *res);
+
+/* Double-buffered form of smash_map_batch: a ctx owns SMASH_N_SLOTS independent slots (device
+ * buffers + pinned result buffers + stream).  submit() enqueues H2D + kernels + D2H on the slot's
+ * stream and returns; wait() blocks until that slot's result is in host memory.  The batch's
+ * host buffers must stay valid until wait(). */
+#define SMASH_N_SLOTS 2
+int smash_submit(smash_ctx *ctx, int slot, const smash_batch *b, int want);
+int smash_wait(smash_ctx *ctx, int slot, smash_result *res);
+
+/* Device-resident variant used to time the kernels alone: upload once, run many times. */
+int smash_batch_upload(smash_ctx *ctx, const smash_batch *b);
+int smash_map_resident(smash_ctx *ctx, int want, smash_result *res);  /* no H2D/D2H; res->sam NULL */
+/* Copy the resident run's SAM text to host (for checks). */
+int smash_fetch_sam(smash_ctx *ctx, const char **sam, uint64_t *n_bytes);
+
+/* ---- tail: smashMEM.py filter (smashMEM.py:84-92,193-228 with "0 0 10000 4") + awk/perl chromosome
+ * filter (smash_mapping.sh:29) + varbin.py (varbin.py:6-118).  Bins are bins.txt column 3
+ * (start_abspos, ascending); chrom_* describe chrom_sizes.txt (names matched against the index's
+ * forward sequence names).  Counting is done when smash_tail_finish is called. */
+int smash_tail_configure(smash_ctx *ctx, const int64_t *bin_starts, uint64_t n_bins,
+                         const char *const *chrom_names, const int64_t *chrom_offsets,
+                         uint64_t n_chroms, int64_t hit_window, int32_t min_excess);
+typedef struct {
+  uint64_t total_reads, dups_removed, reads_kept;   /* varbin stats line (varbin.py:104-114) */
+  uint64_t n_dupe_pairs, n_non_dupe_pairs;          /* smashMEM.py:230 trailer */
+  uint64_t n_positions;                             /* lines of <id>.positions.txt */
+} smash_tail_stats;
+/* counts: n_bins int64 (this rank's counts; the caller allreduces across GPUs).  If
+ * counts_device != NULL the counts are also left in that device buffer (for NCCL). */
+int smash_tail_finish(smash_ctx *ctx, int64_t *counts, void *counts_device, smash_tail_stats *st);
+/* positions.txt rows produced so far by smash_tail_finish: chromosome index (into the forward
+ * sequences) and 0-based position, in output order. */
+int smash_tail_positions(smash_ctx *ctx, const int32_t **chrom, const int64_t **pos, uint64_t *n);
+/* Cross-rank fix-ups (read-sharded multi-GPU): opaque per-rank summary to all-gather. */
+int smash_tail_reset(smash_ctx *ctx);
+
+/* ---- counters for bench.py: kernels launched by this library since ctx creation */
+uint64_t smash_ctx_launch_count(const smash_ctx *ctx);
+/* Bytes of HBM held by the index on this ctx (text, SA, LCP, seed table, ...). */
+uint64_t smash_ctx_index_bytes(const smash_ctx *ctx);
+/* Raw CUDA stream (cudaStream_t) the ctx launches on, for external event timing. */
+void *smash_ctx_stream(const smash_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMASH_B200_H_ */

@@ -1,0 +1,293 @@
+"""ctypes binding of libsmash_b200.so (include/smash_b200.h) -- the product path.
+
+No CPU fallback: if the library is missing, or no sm_100 GPU is present, constructing a
+`Context` raises.  The oracle is never imported from here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsmash_b200.so")
+MODE_MUM, MODE_MAM, MODE_MEM = 0, 1, 2
+WANT_SAM, WANT_MATCHES, WANT_TAIL = 1, 2, 4
+N_SLOTS = 2
+
+
+class SmashError(RuntimeError):
+    pass
+
+
+class _Params(C.Structure):
+    _fields_ = [("device", C.c_int), ("mode", C.c_int), ("min_len", C.c_uint32), ("nomap", C.c_int),
+                ("nucleotides_only", C.c_int), ("tag_mappability", C.c_int),
+                ("max_batch_reads", C.c_uint64), ("seed_k", C.c_int)]
+
+
+class _Batch(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("names", C.c_void_p), ("name_off", C.c_void_p),
+                ("seq", C.c_void_p), ("qual", C.c_void_p), ("seq_off", C.c_void_p),
+                ("opt", C.c_void_p), ("opt_off", C.c_void_p), ("read_flag", C.c_void_p),
+                ("first_pair_ordinal", C.c_uint64)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_matches", C.c_uint64), ("n_records", C.c_uint64),
+                ("sam_bytes", C.c_uint64), ("sam", C.c_void_p), ("match_off", C.c_void_p),
+                ("matches", C.c_void_p), ("gpu_ms", C.c_float)]
+
+
+class _TailStats(C.Structure):
+    _fields_ = [("total_reads", C.c_uint64), ("dups_removed", C.c_uint64), ("reads_kept", C.c_uint64),
+                ("n_dupe_pairs", C.c_uint64), ("n_non_dupe_pairs", C.c_uint64), ("n_positions", C.c_uint64)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load libsmash_b200.so; fails loudly when it has not been built (see __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SmashError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.smash_last_error.restype = C.c_char_p
+    L.smash_index_text_len.restype = C.c_uint64
+    L.smash_index_sam_header.restype = C.c_size_t
+    L.smash_ctx_launch_count.restype = C.c_uint64
+    L.smash_ctx_index_bytes.restype = C.c_uint64
+    L.smash_ctx_stream.restype = C.c_void_p
+    L.smash_host_alloc.restype = C.c_void_p
+    L.smash_host_alloc.argtypes = [C.c_size_t]
+    L.smash_host_free.argtypes = [C.c_void_p]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise SmashError(f"libsmash_b200 error {rc}: {load_library().smash_last_error().decode(errors='replace')}")
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+def device_count():
+    return int(load_library().smash_device_count())
+
+
+def read_flags_from_sam_flags(flags, names=None, name_off=None):
+    """QueryReader::run + Aligner::reset (query.cpp:643-644, 185-201) -> 0 / 65 / 129."""
+    fl = np.asarray(flags).astype(np.uint16)
+    return np.where(fl & 64, 65, np.where(fl & 128, 129, 0)).astype(np.uint16)
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc memory (so H2D copies of batches are true async DMA)."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * self.dtype.itemsize
+        self._p = load_library().smash_host_alloc(max(n, 16))
+        if not self._p:
+            raise SmashError("cudaHostAlloc failed")
+        buf = (C.c_uint8 * max(n, 16)).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            load_library().smash_host_free(C.c_void_p(self._p))
+            self._p = None
+
+
+class Index:
+    """The reference's `<fa>.bin/` index (Sequence + longSA load branches)."""
+
+    def __init__(self, handle, keep=None):
+        self.h = handle
+        self._keep = keep
+
+    @staticmethod
+    def open(fasta, rcref=True):
+        L = load_library()
+        h = C.c_void_p()
+        _check(L.smash_index_open(str(fasta).encode(), int(bool(rcref)), C.byref(h)))
+        return Index(h)
+
+    @staticmethod
+    def from_arrays(text, sa, isa, lcp_vec, lcp_m_raw, startpos, sizes, descr, rcref=True):
+        L = load_library()
+        h = C.c_void_p()
+        startpos = np.ascontiguousarray(startpos, dtype=np.uint64)
+        sizes = np.ascontiguousarray(sizes, dtype=np.uint64)
+        d = (C.c_char_p * len(descr))(*[x.encode() for x in descr])
+        n_m = 0 if lcp_m_raw is None else lcp_m_raw.size // 16
+        _check(L.smash_index_from_arrays(_ptr(text), C.c_uint64(len(text)), _ptr(sa), _ptr(isa) if isa is not None else None,
+                                         int(sa.dtype.itemsize), _ptr(lcp_vec), _ptr(lcp_m_raw) if n_m else None,
+                                         C.c_uint64(n_m), C.c_uint64(len(descr)), _ptr(startpos), _ptr(sizes), d,
+                                         int(bool(rcref)), C.byref(h)))
+        return Index(h, keep=(text, sa, isa, lcp_vec, lcp_m_raw, startpos, sizes, d))
+
+    @property
+    def text_len(self):
+        return int(load_library().smash_index_text_len(self.h))
+
+    def sam_header(self):
+        L = load_library()
+        n = L.smash_index_sam_header(self.h, None, C.c_size_t(0))
+        buf = C.create_string_buffer(n)
+        L.smash_index_sam_header(self.h, buf, C.c_size_t(n))
+        return buf.raw[:n]
+
+    def close(self):
+        if self.h:
+            load_library().smash_index_close(self.h)
+            self.h = None
+
+
+class Result:
+    def __init__(self, r: _Result, want):
+        self.n_reads = int(r.n_reads)
+        self.sam_bytes = int(r.sam_bytes)
+        self.gpu_ms = float(r.gpu_ms)
+        self.sam = None
+        self.match_off = None
+        self.matches = None
+        if (want & WANT_SAM) and r.sam:
+            self.sam = C.string_at(r.sam, self.sam_bytes)
+        if (want & WANT_MATCHES) and r.match_off:
+            n = self.n_reads
+            self.match_off = np.ctypeslib.as_array(C.cast(r.match_off, C.POINTER(C.c_int64)), shape=(n + 1,)).copy()
+            m = int(self.match_off[-1])
+            self.matches = (np.ctypeslib.as_array(C.cast(r.matches, C.POINTER(C.c_uint64)), shape=(max(m, 1) * 3,))
+                            [:3 * m].reshape(-1, 3).copy())
+
+
+class Context:
+    """One GPU: index in HBM + batch slots (Pairs/Pair/Aligner of the reference)."""
+
+    def __init__(self, index: Index, device=0, mode=MODE_MAM, min_len=20, nomap=True,
+                 nucleotides_only=False, tag_mappability=False, seed_k=0):
+        L = load_library()
+        if L.smash_device_count() <= 0:
+            raise SmashError("no sm_100 CUDA device: libsmash_b200 has no CPU fallback")
+        p = _Params()
+        L.smash_params_default(C.byref(p))
+        p.device, p.mode, p.min_len, p.nomap = device, mode, min_len, int(nomap)
+        p.nucleotides_only, p.tag_mappability, p.seed_k = int(nucleotides_only), int(tag_mappability), seed_k
+        self.h = C.c_void_p()
+        self.index = index
+        _check(L.smash_ctx_create(index.h, C.byref(p), C.byref(self.h)))
+        self._inflight = {}
+
+    def close(self):
+        if self.h:
+            load_library().smash_ctx_destroy(self.h)
+            self.h = None
+
+    # -- mappability -----------------------------------------------------------------------
+    def load_mappability(self, body: np.ndarray):
+        body = np.ascontiguousarray(body, dtype=np.uint8)
+        _check(load_library().smash_ctx_load_mappability(self.h, _ptr(body), C.c_uint64(body.size)))
+
+    def load_mappability_file(self, path):
+        self.load_mappability(np.fromfile(path, dtype=np.uint8)[2:])     # 2 junk bytes (longSA.cpp:606-617)
+
+    def build_mappability(self, total_forward_bases):
+        out = np.empty(2 * int(total_forward_bases), dtype=np.uint8)
+        _check(load_library().smash_ctx_build_mappability(self.h, _ptr(out), C.c_uint64(out.size)))
+        return out
+
+    # -- batches ---------------------------------------------------------------------------
+    @staticmethod
+    def _cbatch(batch, read_flag, first_pair=0):
+        b = _Batch(batch.n, _ptr(batch.names), _ptr(batch.name_off), _ptr(batch.seq), _ptr(batch.qual),
+                   _ptr(batch.seq_off), _ptr(batch.opt) if batch.opt.size else None,
+                   _ptr(batch.opt_off) if batch.opt.size else None, _ptr(read_flag), first_pair)
+        return b
+
+    def map_batch(self, batch, want=WANT_SAM, first_pair=0, read_flag=None):
+        rf = read_flags_from_sam_flags(batch.flags) if read_flag is None else read_flag
+        b = self._cbatch(batch, rf, first_pair)
+        r = _Result()
+        _check(load_library().smash_map_batch(self.h, C.byref(b), want, C.byref(r)))
+        return Result(r, want)
+
+    def submit(self, slot, batch, want=WANT_SAM, first_pair=0, read_flag=None):
+        rf = read_flags_from_sam_flags(batch.flags) if read_flag is None else read_flag
+        b = self._cbatch(batch, rf, first_pair)
+        self._inflight[slot] = (batch, rf, b, want)
+        _check(load_library().smash_submit(self.h, slot, C.byref(b), want))
+
+    def wait(self, slot, copy=True):
+        r = _Result()
+        _check(load_library().smash_wait(self.h, slot, C.byref(r)))
+        want = self._inflight.pop(slot)[3]
+        if not copy:
+            return r
+        return Result(r, want)
+
+    def upload(self, batch, read_flag=None):
+        rf = read_flags_from_sam_flags(batch.flags) if read_flag is None else read_flag
+        b = self._cbatch(batch, rf)
+        self._resident = (batch, rf)
+        _check(load_library().smash_batch_upload(self.h, C.byref(b)))
+
+    def map_resident(self, want=WANT_SAM):
+        r = _Result()
+        _check(load_library().smash_map_resident(self.h, want, C.byref(r)))
+        return r
+
+    def fetch_sam(self):
+        p = C.c_void_p()
+        n = C.c_uint64()
+        _check(load_library().smash_fetch_sam(self.h, C.byref(p), C.byref(n)))
+        return C.string_at(p, n.value)
+
+    # -- tail ------------------------------------------------------------------------------
+    def tail_configure(self, bin_starts, chrom_names, chrom_offsets, hit_window=10000, min_excess=4):
+        bs = np.ascontiguousarray(bin_starts, dtype=np.int64)
+        co = np.ascontiguousarray(chrom_offsets, dtype=np.int64)
+        names = (C.c_char_p * len(chrom_names))(*[c.encode() for c in chrom_names])
+        self.n_bins = len(bs)
+        _check(load_library().smash_tail_configure(self.h, _ptr(bs), C.c_uint64(len(bs)), names, _ptr(co),
+                                                   C.c_uint64(len(co)), C.c_int64(hit_window), C.c_int32(min_excess)))
+
+    def tail_finish(self, counts_device_ptr=None):
+        counts = np.zeros(self.n_bins, dtype=np.int64)
+        st = _TailStats()
+        _check(load_library().smash_tail_finish(self.h, _ptr(counts), C.c_void_p(counts_device_ptr) if counts_device_ptr else None,
+                                                C.byref(st)))
+        return counts, {k: int(getattr(st, k)) for k, _ in _TailStats._fields_}
+
+    def tail_positions(self):
+        c, p, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        _check(load_library().smash_tail_positions(self.h, C.byref(c), C.byref(p), C.byref(n)))
+        m = n.value
+        if not m:
+            return np.zeros(0, np.int32), np.zeros(0, np.int64)
+        return (np.ctypeslib.as_array(C.cast(c, C.POINTER(C.c_int32)), shape=(m,)).copy(),
+                np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int64)), shape=(m,)).copy())
+
+    def tail_reset(self):
+        _check(load_library().smash_tail_reset(self.h))
+
+    @property
+    def launches(self):
+        return int(load_library().smash_ctx_launch_count(self.h))
+
+    @property
+    def index_bytes(self):
+        return int(load_library().smash_ctx_index_bytes(self.h))
+
+    @property
+    def stream(self):
+        return load_library().smash_ctx_stream(self.h)

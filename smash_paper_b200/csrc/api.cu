@@ -1,0 +1,658 @@
+// api.cu -- host side of the C ABI (include/smash_b200.h): index files -> HBM, batch slots,
+// stream plumbing.  No compute happens here and there is no CPU fallback: without a CUDA device
+// every entry point that would compute returns SMASH_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/smash_b200.h"
+#include "kernels.cuh"
+#include "tail.cuh"
+
+using namespace smash;
+
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char *fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+  return code;
+}
+#define CU(call)                                                                        \
+  do { cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) return fail(SMASH_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" const char *smash_last_error(void) { return g_err; }
+
+extern "C" int smash_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major >= 10) ++ok;
+  }
+  return ok;
+}
+
+// ------------------------------------------------------------------ index (host view)
+
+struct Mapping { void *p = nullptr; size_t n = 0; };
+static int map_file(const std::string &path, size_t expect, Mapping *m) {
+  int fd = open(path.c_str(), O_RDONLY);
+  if (fd < 0) return fail(SMASH_ERR_IO, "could not open input %s for reading", path.c_str());
+  struct stat st; fstat(fd, &st);
+  if (expect != (size_t)-1 && (size_t)st.st_size != expect) {
+    close(fd);
+    return fail(SMASH_ERR_IO, "%s has %zu bytes, expected %zu", path.c_str(), (size_t)st.st_size, expect);
+  }
+  m->n = (size_t)st.st_size;
+  if (m->n) {
+    m->p = mmap(nullptr, m->n, PROT_READ, MAP_SHARED, fd, 0);
+    if (m->p == MAP_FAILED) { close(fd); m->p = nullptr; return fail(SMASH_ERR_IO, "Memory mapping error for %s", path.c_str()); }
+  }
+  close(fd);
+  return 0;
+}
+
+struct smash_index {
+  uint64_t N = 0; int w = 4; int rcref = 1; uint64_t fasta_size = 0;
+  const uint8_t *text = nullptr; const void *sa = nullptr; const void *isa = nullptr;
+  const uint8_t *lcp = nullptr; const uint8_t *lcp_m_raw = nullptr; uint64_t n_m = 0;
+  std::vector<uint64_t> startpos, sizes; std::vector<std::string> descr;
+  std::vector<Mapping> maps;
+  std::string fasta;
+};
+
+static bool read_u64(FILE *f, uint64_t *v) { return fread(v, 8, 1, f) == 1; }
+
+extern "C" int smash_index_open(const char *ref_fasta, int rcref, smash_index **out) {
+  if (!ref_fasta || !out) return fail(SMASH_ERR_ARG, "null argument");
+  smash_index *ix = new smash_index();
+  ix->rcref = rcref ? 1 : 0; ix->fasta = ref_fasta;
+  struct stat st;
+  if (stat(ref_fasta, &st) != 0) { delete ix; return fail(SMASH_ERR_IO, "unable to open %s", ref_fasta); }
+  ix->fasta_size = (uint64_t)st.st_size;
+  const std::string base = std::string(ref_fasta) + ".bin/rc" + (rcref ? "1" : "0");
+  FILE *f = fopen((base + ".ref.bin").c_str(), "rb");
+  if (!f) { delete ix; return fail(SMASH_ERR_IO, "could not open reference bin file %s.ref.bin for reading (run the index build first)", base.c_str()); }
+  uint64_t saved = 0, nd = 0;
+  bool ok = read_u64(f, &saved) && read_u64(f, &ix->N) && read_u64(f, &nd);
+  if (ok && saved != ix->fasta_size) {
+    fclose(f); delete ix;
+    return fail(SMASH_ERR_IO, "reference fasta size has changed\nmaybe the reference has changed?\nIf so, you will need to delete the current reference to proceed");
+  }
+  for (uint64_t i = 0; ok && i < nd; ++i) {
+    uint64_t sp, sz, sl;
+    ok = read_u64(f, &sp) && read_u64(f, &sz) && read_u64(f, &sl);
+    if (!ok || sl > 1u << 20) { ok = false; break; }
+    std::string d(sl, '\0');
+    if (sl && fread(&d[0], 1, sl, f) != sl) { ok = false; break; }
+    ix->startpos.push_back(sp); ix->sizes.push_back(sz); ix->descr.push_back(d);
+  }
+  fclose(f);
+  if (!ok) { delete ix; return fail(SMASH_ERR_IO, "problem reading %s.ref.bin", base.c_str()); }
+  // int width: the reference picks the binary (mummer / mummer-long) from the FASTA size
+  // (mummer.cpp:156-183); we take whichever index the build left behind.
+  std::string ib;
+  if (access((base + ".i4.index.bin").c_str(), R_OK) == 0) { ix->w = 4; ib = base + ".i4.index"; }
+  else if (access((base + ".i8.index.bin").c_str(), R_OK) == 0) { ix->w = 8; ib = base + ".i8.index"; }
+  else { delete ix; return fail(SMASH_ERR_IO, "could not open index %s.i{4,8}.index.bin for reading", base.c_str()); }
+  uint64_t hdr[6];
+  f = fopen((ib + ".bin").c_str(), "rb");
+  if (!f || fread(hdr, 8, 6, f) != 6) { if (f) fclose(f); delete ix; return fail(SMASH_ERR_IO, "problem reading 48 elements at index header"); }
+  fclose(f);
+  if (hdr[0] != ix->fasta_size) {
+    delete ix;
+    return fail(SMASH_ERR_IO, "saved fasta size used for index does notmatch current fasta size\nmaybe the reference has changed?\nyou may need to delete the current index to proceed");
+  }
+  if (hdr[3] != ix->N || hdr[4] != ix->N) { delete ix; return fail(SMASH_ERR_IO, "index size %llu does not match reference length %llu", (unsigned long long)hdr[3], (unsigned long long)ix->N); }
+  ix->n_m = hdr[5];
+  Mapping m;
+  int rc;
+  if ((rc = map_file(base + ".ref.seq.bin", ix->N, &m))) { delete ix; return rc; }
+  ix->text = (const uint8_t *)m.p; ix->maps.push_back(m);
+  if ((rc = map_file(ib + ".sa.bin", ix->N * ix->w, &m))) { smash_index_close(ix); return rc; }
+  ix->sa = m.p; ix->maps.push_back(m);
+  if (access((ib + ".isa.bin").c_str(), R_OK) == 0) {
+    if ((rc = map_file(ib + ".isa.bin", ix->N * ix->w, &m))) { smash_index_close(ix); return rc; }
+    ix->isa = m.p; ix->maps.push_back(m);
+  }
+  if ((rc = map_file(ib + ".lcp.vec.bin", ix->N, &m))) { smash_index_close(ix); return rc; }
+  ix->lcp = (const uint8_t *)m.p; ix->maps.push_back(m);
+  if ((rc = map_file(ib + ".lcp.m.bin", ix->n_m * 16, &m))) { smash_index_close(ix); return rc; }
+  ix->lcp_m_raw = (const uint8_t *)m.p; ix->maps.push_back(m);
+  *out = ix;
+  return 0;
+}
+
+extern "C" int smash_index_from_arrays(const uint8_t *text, uint64_t N, const void *sa, const void *isa, int w,
+                                       const uint8_t *lcp_vec, const void *lcp_m, uint64_t n_m,
+                                       uint64_t n_descr, const uint64_t *startpos, const uint64_t *sizes,
+                                       const char *const *descr, int rcref, smash_index **out) {
+  if (!text || !sa || !lcp_vec || !out || (w != 4 && w != 8) || !n_descr) return fail(SMASH_ERR_ARG, "bad index arrays");
+  smash_index *ix = new smash_index();
+  ix->N = N; ix->w = w; ix->rcref = rcref ? 1 : 0; ix->text = text; ix->sa = sa; ix->isa = isa;
+  ix->lcp = lcp_vec; ix->lcp_m_raw = (const uint8_t *)lcp_m; ix->n_m = n_m;
+  for (uint64_t i = 0; i < n_descr; ++i) { ix->startpos.push_back(startpos[i]); ix->sizes.push_back(sizes[i]); ix->descr.push_back(descr[i]); }
+  *out = ix;
+  return 0;
+}
+
+extern "C" void smash_index_close(smash_index *ix) {
+  if (!ix) return;
+  for (auto &m : ix->maps) if (m.p && m.n) munmap(m.p, m.n);
+  delete ix;
+}
+extern "C" uint64_t smash_index_text_len(const smash_index *ix) { return ix ? ix->N : 0; }
+extern "C" int smash_index_int_width(const smash_index *ix) { return ix ? ix->w : 0; }
+
+extern "C" size_t smash_index_sam_header(const smash_index *ix, char *buf, size_t cap) {
+  std::string s = "@HD\tVN:1.0\tSO:unsorted\n";                 // fasta.cpp:243-252
+  for (size_t c = 0; c < ix->sizes.size(); c += ix->rcref ? 2 : 1)
+    s += "@SQ\tSN:" + ix->descr[c] + "\tLN:" + std::to_string(ix->sizes[c]) + "\n";
+  s += "@PG\tID:longMEM\tPN:longMEM\tVN:0.5\n";
+  if (buf && cap) { size_t n = s.size() < cap ? s.size() : cap; memcpy(buf, s.data(), n); }
+  return s.size();
+}
+
+// ------------------------------------------------------------------ context
+
+template <class T> struct DBuf {        // growable device buffer
+  T *p = nullptr; size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    size_t want = n + n / 4 + 64;
+    cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+    if (e != cudaSuccess) { cap = 0; return fail(SMASH_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e)); }
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <class T> struct HBuf {        // growable pinned host buffer
+  T *p = nullptr; size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    size_t want = n + n / 4 + 64;
+    cudaError_t e = cudaHostAlloc((void **)&p, want * sizeof(T), cudaHostAllocDefault);
+    if (e != cudaSuccess) { cap = 0; return fail(SMASH_ERR_NOMEM, "cudaHostAlloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e)); }
+    cap = want;
+    return 0;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Slot {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // batch on device
+  DBuf<uint8_t> names, seq, qual, opt;
+  DBuf<int64_t> name_off, seq_off, opt_off;
+  DBuf<uint16_t> read_flag;
+  BatchDev bd{};
+  // work
+  int cap = 0;
+  DBuf<Match> match_slots; DBuf<uint32_t> match_cnt; DBuf<Item> item_slots; DBuf<Rec> rec_slots;
+  DBuf<ReadSum> sums; DBuf<uint32_t> read_bytes; DBuf<uint64_t> out_off; DBuf<uint64_t> blk_sums;
+  DBuf<char> sam; DBuf<uint32_t> flags;
+  DBuf<int64_t> csr_off; DBuf<uint64_t> csr_triples;
+  // results on host
+  HBuf<char> h_sam; HBuf<int64_t> h_csr_off; HBuf<smash_match> h_matches; HBuf<uint64_t> h_small;
+  // in flight
+  bool busy = false; int want = 0; uint64_t n_reads = 0; uint64_t first_pair = 0;
+  uint64_t sam_bytes = 0, n_matches = 0, n_records = 0;
+};
+
+struct smash_ctx {
+  const smash_index *hix = nullptr;
+  smash_params prm{};
+  int device = 0;
+  DevIndex dix{};
+  SearchParams sp{};
+  // index storage
+  uint8_t *text_alloc = nullptr; void *sa = nullptr; void *isa = nullptr; uint8_t *lcp = nullptr;
+  LcpItem *lcp_m = nullptr; uint8_t *uniq = nullptr; void *seed = nullptr; uint64_t *startpos = nullptr;
+  uint64_t *sizes = nullptr; char *descr = nullptr; int *descr_off = nullptr; uint32_t *alpha = nullptr;
+  uint8_t *mapbody = nullptr; uint32_t *chrom_off32 = nullptr;
+  uint64_t index_bytes = 0;
+  uint64_t launches = 0;
+  Slot slot[SMASH_N_SLOTS];
+  TailState tail;
+};
+
+static int dmalloc(void **p, size_t bytes, uint64_t *acct) {
+  cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+  if (e != cudaSuccess) return fail(SMASH_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+  if (acct) *acct += bytes;
+  return 0;
+}
+
+extern "C" void smash_params_default(smash_params *p) {
+  memset(p, 0, sizeof *p);
+  p->device = 0; p->mode = SMASH_MODE_MAM; p->min_len = 20; p->nomap = 0; p->nucleotides_only = 0;
+  p->tag_mappability = 0; p->max_batch_reads = 0; p->seed_k = 0;
+}
+
+extern "C" void *smash_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+extern "C" void smash_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+static void set_search_params(smash_ctx *c) {
+  SearchParams &sp = c->sp;
+  sp.L = c->prm.min_len < 2 ? 2u : c->prm.min_len;
+  sp.k = c->dix.seed_k < (int)sp.L ? c->dix.seed_k : (int)sp.L;
+  sp.s = (int)sp.L - sp.k + 1;
+  sp.nucleotides_only = c->prm.nucleotides_only;
+  sp.nomap = c->prm.nomap;
+  sp.tag_mappability = c->prm.tag_mappability;
+  // the anchor path enumerates seed buckets: only sensible when a k-mer of that length is rare
+  const double expect = (double)c->dix.N / pow(4.0, (double)sp.k);
+  sp.fast_ok = expect <= 16.0;
+}
+
+extern "C" int smash_ctx_create(const smash_index *ix, const smash_params *p, smash_ctx **out) {
+  if (!ix || !p || !out) return fail(SMASH_ERR_ARG, "null argument");
+  if (smash_device_count() <= 0) return fail(SMASH_ERR_CUDA, "no sm_100 CUDA device available (this library has no CPU fallback)");
+  if (p->mode != SMASH_MODE_MAM && p->mode != SMASH_MODE_MEM) return fail(SMASH_ERR_ARG, "mode %d not supported (MAM or MEM)", p->mode);
+  if (p->mode == SMASH_MODE_MEM && !ix->isa) return fail(SMASH_ERR_ARG, "MEM mode needs the .isa.bin array");
+  CU(cudaSetDevice(p->device));
+  smash_ctx *c = new smash_ctx();
+  c->hix = ix; c->prm = *p; c->device = p->device;
+  const uint64_t N = ix->N; const int w = ix->w;
+  int rc = 0;
+  cudaStream_t st = nullptr;
+#define CK(x) do { if ((rc = (x))) { smash_ctx_destroy(c); return rc; } } while (0)
+#define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { smash_ctx_destroy(c); return fail(SMASH_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
+  for (int s = 0; s < SMASH_N_SLOTS; ++s) {
+    CUC(cudaStreamCreateWithFlags(&c->slot[s].st, cudaStreamNonBlocking));
+    CUC(cudaEventCreate(&c->slot[s].ev0)); CUC(cudaEventCreate(&c->slot[s].ev1));
+  }
+  st = c->slot[0].st;
+  CK(dmalloc((void **)&c->text_alloc, N + 2 * TEXT_PAD, &c->index_bytes));
+  CUC(cudaMemsetAsync(c->text_alloc, 0, N + 2 * TEXT_PAD, st));
+  CUC(cudaMemcpyAsync(c->text_alloc + TEXT_PAD, ix->text, N, cudaMemcpyHostToDevice, st));
+  CK(dmalloc(&c->sa, N * w, &c->index_bytes));
+  CUC(cudaMemcpyAsync(c->sa, ix->sa, N * w, cudaMemcpyHostToDevice, st));
+  if (ix->isa && (p->mode == SMASH_MODE_MEM)) {
+    CK(dmalloc(&c->isa, N * w, &c->index_bytes));
+    CUC(cudaMemcpyAsync(c->isa, ix->isa, N * w, cudaMemcpyHostToDevice, st));
+  }
+  CK(dmalloc((void **)&c->lcp, N, &c->index_bytes));
+  CUC(cudaMemcpyAsync(c->lcp, ix->lcp, N, cudaMemcpyHostToDevice, st));
+  {
+    // .lcp.m.bin items are {u64 idx; ANINT val; pad}: widen val so the device sees one layout
+    std::vector<LcpItem> m(ix->n_m);
+    for (uint64_t i = 0; i < ix->n_m; ++i) {
+      const uint8_t *r = ix->lcp_m_raw + 16 * i;
+      memcpy(&m[i].idx, r, 8);
+      if (w == 4) { uint32_t v; memcpy(&v, r + 8, 4); m[i].val = v; } else memcpy(&m[i].val, r + 8, 8);
+    }
+    CK(dmalloc((void **)&c->lcp_m, sizeof(LcpItem) * (ix->n_m + 1), &c->index_bytes));
+    if (ix->n_m) CUC(cudaMemcpy(c->lcp_m, m.data(), sizeof(LcpItem) * ix->n_m, cudaMemcpyHostToDevice));
+  }
+  const int nd = (int)ix->descr.size();
+  CK(dmalloc((void **)&c->startpos, 8 * nd, &c->index_bytes));
+  CK(dmalloc((void **)&c->sizes, 8 * nd, &c->index_bytes));
+  CUC(cudaMemcpy(c->startpos, ix->startpos.data(), 8 * nd, cudaMemcpyHostToDevice));
+  CUC(cudaMemcpy(c->sizes, ix->sizes.data(), 8 * nd, cudaMemcpyHostToDevice));
+  {
+    std::string blob; std::vector<int> off(nd + 1, 0);
+    for (int i = 0; i < nd; ++i) { off[i] = (int)blob.size(); blob += ix->descr[i]; }
+    off[nd] = (int)blob.size();
+    CK(dmalloc((void **)&c->descr, blob.size() + 1, &c->index_bytes));
+    CK(dmalloc((void **)&c->descr_off, 4 * (nd + 1), &c->index_bytes));
+    CUC(cudaMemcpy(c->descr, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    CUC(cudaMemcpy(c->descr_off, off.data(), 4 * (nd + 1), cudaMemcpyHostToDevice));
+    // mappability_tag's 32-bit offsets over all @SQ (chromosomes.h:29-66)
+    std::vector<uint32_t> o32((nd + 1) / (ix->rcref ? 2 : 1) + 1, 0);
+    uint32_t acc = 0; int k = 0;
+    for (int i = 0; i < nd; i += ix->rcref ? 2 : 1) { o32[k++] = acc; acc += (uint32_t)ix->sizes[i]; }
+    CK(dmalloc((void **)&c->chrom_off32, 4 * o32.size(), &c->index_bytes));
+    CUC(cudaMemcpy(c->chrom_off32, o32.data(), 4 * o32.size(), cudaMemcpyHostToDevice));
+  }
+  CK(dmalloc((void **)&c->alpha, 32, nullptr));
+  DevIndex &d = c->dix;
+  d.text = c->text_alloc + TEXT_PAD; d.N = N; d.sa = c->sa; d.isa = c->isa; d.w = w; d.lcp = c->lcp;
+  d.lcp_m = c->lcp_m; d.n_m = ix->n_m; d.startpos = c->startpos; d.sizes = c->sizes; d.n_descr = nd;
+  d.rcref = ix->rcref; d.descr = c->descr; d.descr_off = c->descr_off;
+  d.logN = (uint64_t)ceil(log((double)N) / log(2.0));          // longSA.cpp:97
+  d.mapbody = nullptr; d.map_bytes = 0; d.chrom_off32 = c->chrom_off32;
+  // derived: alphabet bitmap, shortest-unique-length bytes, k-mer seed table
+  c->launches += launch_alpha(d.text, N, c->alpha, st);
+  CUC(cudaMemcpyAsync(d.alpha, c->alpha, 32, cudaMemcpyDeviceToHost, st));
+  CK(dmalloc((void **)&c->uniq, N, &c->index_bytes));
+  c->launches += launch_uniq_build(d, c->uniq, st);
+  d.uniq = c->uniq;
+  int k = p->seed_k;
+  if (k <= 0) { k = (int)ceil(log((double)N) / log(4.0)) + 1; }
+  if (k > 16) k = 16;
+  if (k < 4) k = 4;
+  d.seed_k = k; d.seed_w = N < 0xffffffffull ? 4 : 8;
+  CK(dmalloc(&c->seed, ((1ull << (2 * k)) + 1) * d.seed_w, &c->index_bytes));
+  c->launches += launch_seed_build(d, c->seed, k, d.seed_w, st);
+  d.seed = c->seed;
+  CUC(cudaStreamSynchronize(st));
+  CUC(cudaGetLastError());
+  set_search_params(c);
+  tail_init(&c->tail);
+#undef CK
+#undef CUC
+  *out = c;
+  return 0;
+}
+
+static void slot_release(Slot &s) {
+  s.names.release(); s.seq.release(); s.qual.release(); s.opt.release(); s.name_off.release();
+  s.seq_off.release(); s.opt_off.release(); s.read_flag.release(); s.match_slots.release();
+  s.match_cnt.release(); s.item_slots.release(); s.rec_slots.release(); s.sums.release();
+  s.read_bytes.release(); s.out_off.release(); s.blk_sums.release(); s.sam.release(); s.flags.release();
+  s.csr_off.release(); s.csr_triples.release(); s.h_sam.release(); s.h_csr_off.release();
+  s.h_matches.release(); s.h_small.release();
+  if (s.ev0) cudaEventDestroy(s.ev0);
+  if (s.ev1) cudaEventDestroy(s.ev1);
+  if (s.st) cudaStreamDestroy(s.st);
+}
+
+extern "C" void smash_ctx_destroy(smash_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (int s = 0; s < SMASH_N_SLOTS; ++s) slot_release(c->slot[s]);
+  tail_release(&c->tail);
+  void *ptrs[] = {c->text_alloc, c->sa, c->isa, c->lcp, c->lcp_m, c->uniq, c->seed, c->startpos, c->sizes,
+                  c->descr, c->descr_off, c->alpha, c->mapbody, c->chrom_off32};
+  for (void *p : ptrs) if (p) cudaFree(p);
+  delete c;
+}
+
+extern "C" int smash_ctx_load_mappability(smash_ctx *c, const uint8_t *body, uint64_t n) {
+  if (!c || !body) return fail(SMASH_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (c->mapbody) { cudaFree(c->mapbody); c->mapbody = nullptr; }
+  int rc = dmalloc((void **)&c->mapbody, n, &c->index_bytes);
+  if (rc) return rc;
+  CU(cudaMemcpy(c->mapbody, body, n, cudaMemcpyHostToDevice));
+  c->dix.mapbody = c->mapbody; c->dix.map_bytes = n;
+  return 0;
+}
+
+extern "C" int smash_ctx_build_mappability(smash_ctx *c, uint8_t *body, uint64_t cap) {
+  if (!c) return fail(SMASH_ERR_ARG, "null argument");
+  if (!c->hix->isa) return fail(SMASH_ERR_STATE, "mappability needs the .isa.bin array");
+  if (!c->hix->rcref) return fail(SMASH_ERR_ARG, "-mappability requires -rcref");   // mummer.cpp:145
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->slot[0].st;
+  uint64_t total = 0;
+  for (size_t i = 0; i < c->hix->sizes.size(); i += 2) total += 2 * c->hix->sizes[i];
+  bool temp_isa = false;
+  if (!c->isa) {
+    int rc = dmalloc(&c->isa, c->dix.N * c->dix.w, nullptr); if (rc) return rc;
+    CU(cudaMemcpy(c->isa, c->hix->isa, c->dix.N * c->dix.w, cudaMemcpyHostToDevice));
+    c->dix.isa = c->isa; temp_isa = true;
+  }
+  if (c->mapbody) { cudaFree(c->mapbody); c->mapbody = nullptr; }
+  int rc = dmalloc((void **)&c->mapbody, total, &c->index_bytes);
+  if (rc) return rc;
+  c->launches += launch_mappability(c->dix, nullptr, c->mapbody, st);
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  if (temp_isa && c->prm.mode != SMASH_MODE_MEM) { cudaFree(c->isa); c->isa = nullptr; c->dix.isa = nullptr; }
+  c->dix.mapbody = c->mapbody; c->dix.map_bytes = total;
+  if (body) {
+    if (cap < total) return fail(SMASH_ERR_ARG, "mappability buffer too small: need %llu bytes", (unsigned long long)total);
+    CU(cudaMemcpy(body, c->mapbody, total, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ batches
+
+static int slot_prepare(smash_ctx *c, Slot &s, const smash_batch *b, bool copy) {
+  const uint64_t n = b->n_reads;
+  const size_t name_bytes = n ? (size_t)b->name_off[n] : 0, seq_bytes = n ? (size_t)b->seq_off[n] : 0;
+  const size_t opt_bytes = (b->opt && n) ? (size_t)b->opt_off[n] : 0;
+  int rc;
+  if ((rc = s.names.ensure(name_bytes + 16)) || (rc = s.seq.ensure(seq_bytes + 16)) || (rc = s.qual.ensure(seq_bytes + 16)) ||
+      (rc = s.name_off.ensure(n + 1)) || (rc = s.seq_off.ensure(n + 1)) || (rc = s.read_flag.ensure(n + 1)))
+    return rc;
+  if (opt_bytes && ((rc = s.opt.ensure(opt_bytes + 16)) || (rc = s.opt_off.ensure(n + 1)))) return rc;
+  if (s.cap == 0) s.cap = 24;
+  if ((rc = s.match_slots.ensure(n * s.cap)) || (rc = s.match_cnt.ensure(n + 1)) || (rc = s.item_slots.ensure(n * s.cap)) ||
+      (rc = s.rec_slots.ensure(n * s.cap)) || (rc = s.sums.ensure(n + 2)) || (rc = s.read_bytes.ensure(n + 1)) ||
+      (rc = s.out_off.ensure(n + 2)) || (rc = s.blk_sums.ensure(n / 2048 + 8)) || (rc = s.flags.ensure(N_FLAGS)) ||
+      (rc = s.h_small.ensure(16)))
+    return rc;
+  if (copy && n) {
+    CU(cudaMemcpyAsync(s.names.p, b->names, name_bytes, cudaMemcpyHostToDevice, s.st));
+    CU(cudaMemcpyAsync(s.seq.p, b->seq, seq_bytes, cudaMemcpyHostToDevice, s.st));
+    CU(cudaMemcpyAsync(s.qual.p, b->qual, seq_bytes, cudaMemcpyHostToDevice, s.st));
+    CU(cudaMemcpyAsync(s.name_off.p, b->name_off, 8 * (n + 1), cudaMemcpyHostToDevice, s.st));
+    CU(cudaMemcpyAsync(s.seq_off.p, b->seq_off, 8 * (n + 1), cudaMemcpyHostToDevice, s.st));
+    CU(cudaMemcpyAsync(s.read_flag.p, b->read_flag, 2 * n, cudaMemcpyHostToDevice, s.st));
+    if (opt_bytes) {
+      CU(cudaMemcpyAsync(s.opt.p, b->opt, opt_bytes, cudaMemcpyHostToDevice, s.st));
+      CU(cudaMemcpyAsync(s.opt_off.p, b->opt_off, 8 * (n + 1), cudaMemcpyHostToDevice, s.st));
+    }
+  }
+  s.bd.n_reads = n; s.bd.names = s.names.p; s.bd.name_off = s.name_off.p; s.bd.seq = s.seq.p; s.bd.qual = s.qual.p;
+  s.bd.seq_off = s.seq_off.p; s.bd.opt = opt_bytes ? s.opt.p : nullptr; s.bd.opt_off = opt_bytes ? s.opt_off.p : nullptr;
+  s.bd.read_flag = s.read_flag.p;
+  s.n_reads = n; s.first_pair = b->first_pair_ordinal;
+  return 0;
+}
+
+static WorkDev work_of(Slot &s) {
+  WorkDev w{};
+  w.cap = s.cap; w.match_slots = s.match_slots.p; w.match_cnt = s.match_cnt.p; w.item_slots = s.item_slots.p;
+  w.rec_slots = s.rec_slots.p; w.sums = s.sums.p; w.read_bytes = s.read_bytes.p; w.out_off = s.out_off.p;
+  w.blk_sums = s.blk_sums.p; w.sam = s.sam.p; w.sam_cap = s.sam.cap; w.flags = s.flags.p;
+  return w;
+}
+
+// search -> records -> sizes/scan -> (sync for the byte total) -> emit [-> D2H].
+// The only host synchronisation inside is the 8-byte read of the SAM size.
+static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
+  const uint64_t n = s.n_reads;
+  s.sam_bytes = 0; s.n_matches = 0; s.n_records = 0; s.want = want;
+  if (!n) return 0;
+  for (int attempt = 0;; ++attempt) {
+    WorkDev w = work_of(s);
+    CU(cudaMemsetAsync(s.flags.p, 0, sizeof(uint32_t) * N_FLAGS, s.st));
+    CU(cudaEventRecord(s.ev0, s.st));
+    int nl;
+    if (c->prm.mode == SMASH_MODE_MEM) nl = launch_mem_search(c->dix, s.bd, w, c->sp, s.st);
+    else nl = launch_mam_search(c->dix, s.bd, w, c->sp, s.st);
+    if (nl < 0) return fail(SMASH_ERR_STATE, "MEM mode kernel not available in this build");
+    c->launches += nl;
+    c->launches += launch_records(c->dix, s.bd, w, c->sp, s.st);
+    c->launches += launch_sizes_scan(c->dix, s.bd, w, c->sp, s.st);
+    CU(cudaMemcpyAsync(s.h_small.p, s.out_off.p + n, 8, cudaMemcpyDeviceToHost, s.st));
+    CU(cudaMemcpyAsync(s.h_small.p + 1, s.flags.p, sizeof(uint32_t) * N_FLAGS, cudaMemcpyDeviceToHost, s.st));
+    CU(cudaStreamSynchronize(s.st));
+    const uint32_t *fl = (const uint32_t *)(s.h_small.p + 1);
+    if (fl[FLAG_LONGREAD]) return fail(SMASH_ERR_ARG, "%u reads longer than %d bases are not supported by this build", fl[FLAG_LONGREAD], MAXQ_FAST);
+    if (fl[FLAG_OVERFLOW]) {
+      const uint32_t need = fl[FLAG_MAXCNT];
+      if (need > (uint32_t)STAGE_CAP || attempt > 3)
+        return fail(SMASH_ERR_DATA, "a read produced %u matches; this build keeps at most %d per read", need, STAGE_CAP);
+      s.cap = (int)need + 8 > STAGE_CAP ? STAGE_CAP : (int)need + 8;
+      int rc;
+      if ((rc = s.match_slots.ensure(n * s.cap)) || (rc = s.item_slots.ensure(n * s.cap)) || (rc = s.rec_slots.ensure(n * s.cap))) return rc;
+      continue;                                              // rerun the batch with wider slots
+    }
+    if (fl[FLAG_MAPERR] && ((want & SMASH_WANT_TAIL) || c->prm.tag_mappability))
+      return fail(SMASH_ERR_DATA, "left/right mappability too big for %u records (mappability_tag.cpp:107-113 throws here)", fl[FLAG_MAPERR]);
+    break;
+  }
+  s.sam_bytes = s.h_small.p[0];
+  if (want & SMASH_WANT_SAM) {
+    int rc;
+    if ((rc = s.sam.ensure(s.sam_bytes + 64))) return rc;
+    WorkDev w = work_of(s);
+    c->launches += launch_emit(c->dix, s.bd, w, c->sp, s.st);
+    if (to_host) {
+      if ((rc = s.h_sam.ensure(s.sam_bytes + 64))) return rc;
+      CU(cudaMemcpyAsync(s.h_sam.p, s.sam.p, s.sam_bytes, cudaMemcpyDeviceToHost, s.st));
+    }
+  }
+  if (want & SMASH_WANT_MATCHES) {
+    int rc;
+    if ((rc = s.csr_off.ensure(n + 2))) return rc;
+    if ((rc = s.csr_triples.ensure(3 * n * (size_t)s.cap + 8))) return rc;
+    WorkDev w = work_of(s);
+    c->launches += launch_match_csr(s.bd, w, s.csr_off.p, s.csr_triples.p, s.blk_sums.p, s.st);
+    if ((rc = s.h_csr_off.ensure(n + 2)) || (rc = s.h_matches.ensure(n * (size_t)s.cap + 8))) return rc;
+    CU(cudaMemcpyAsync(s.h_csr_off.p, s.csr_off.p, 8 * (n + 1), cudaMemcpyDeviceToHost, s.st));
+    CU(cudaMemcpyAsync(s.h_matches.p, s.csr_triples.p, 24 * n * (size_t)s.cap, cudaMemcpyDeviceToHost, s.st));
+  }
+  if (want & SMASH_WANT_TAIL) {
+    int rc = tail_accumulate(&c->tail, c->dix, s.bd, work_of(s), s.first_pair, s.st, &c->launches);
+    if (rc) return fail(rc, "tail: %s", tail_error());
+  }
+  CU(cudaEventRecord(s.ev1, s.st));
+  return 0;
+}
+
+static int slot_finish(smash_ctx *, Slot &s, smash_result *res) {
+  CU(cudaStreamSynchronize(s.st));
+  CU(cudaGetLastError());
+  if (res) {
+    memset(res, 0, sizeof *res);
+    res->n_reads = s.n_reads; res->sam_bytes = s.sam_bytes;
+    if (s.n_reads) { float ms = 0; cudaEventElapsedTime(&ms, s.ev0, s.ev1); res->gpu_ms = ms; }
+    if ((s.want & SMASH_WANT_SAM) && s.h_sam.p) res->sam = s.h_sam.p;
+    if ((s.want & SMASH_WANT_MATCHES) && s.n_reads) {
+      res->match_off = s.h_csr_off.p; res->matches = s.h_matches.p;
+      res->n_matches = (uint64_t)s.h_csr_off.p[s.n_reads];
+    }
+  }
+  s.busy = false;
+  return 0;
+}
+
+extern "C" int smash_submit(smash_ctx *c, int slot, const smash_batch *b, int want) {
+  if (!c || !b || slot < 0 || slot >= SMASH_N_SLOTS) return fail(SMASH_ERR_ARG, "bad argument");
+  Slot &s = c->slot[slot];
+  if (s.busy) return fail(SMASH_ERR_STATE, "slot %d still has a batch in flight", slot);
+  CU(cudaSetDevice(c->device));
+  int rc = slot_prepare(c, s, b, true);
+  if (rc) return rc;
+  rc = slot_run(c, s, want, true);
+  if (rc) return rc;
+  s.busy = true;
+  return 0;
+}
+extern "C" int smash_wait(smash_ctx *c, int slot, smash_result *res) {
+  if (!c || slot < 0 || slot >= SMASH_N_SLOTS) return fail(SMASH_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  return slot_finish(c, c->slot[slot], res);
+}
+extern "C" int smash_map_batch(smash_ctx *c, const smash_batch *b, int want, smash_result *res) {
+  int rc = smash_submit(c, 0, b, want);
+  if (rc) return rc;
+  return smash_wait(c, 0, res);
+}
+
+extern "C" int smash_batch_upload(smash_ctx *c, const smash_batch *b) {
+  if (!c || !b) return fail(SMASH_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  Slot &s = c->slot[0];
+  int rc = slot_prepare(c, s, b, true);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(s.st));
+  return 0;
+}
+extern "C" int smash_map_resident(smash_ctx *c, int want, smash_result *res) {
+  if (!c) return fail(SMASH_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  Slot &s = c->slot[0];
+  int rc = slot_run(c, s, want & ~SMASH_WANT_MATCHES, false);
+  if (rc) return rc;
+  rc = slot_finish(c, s, res);
+  if (res) res->sam = nullptr;
+  return rc;
+}
+extern "C" int smash_fetch_sam(smash_ctx *c, const char **sam, uint64_t *n_bytes) {
+  if (!c || !sam || !n_bytes) return fail(SMASH_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  Slot &s = c->slot[0];
+  int rc = s.h_sam.ensure(s.sam_bytes + 64);
+  if (rc) return rc;
+  CU(cudaMemcpy(s.h_sam.p, s.sam.p, s.sam_bytes, cudaMemcpyDeviceToHost));
+  *sam = s.h_sam.p; *n_bytes = s.sam_bytes;
+  return 0;
+}
+
+// ------------------------------------------------------------------ tail + misc
+
+extern "C" int smash_tail_configure(smash_ctx *c, const int64_t *bin_starts, uint64_t n_bins,
+                                    const char *const *chrom_names, const int64_t *chrom_offsets,
+                                    uint64_t n_chroms, int64_t hit_window, int32_t min_excess) {
+  if (!c || !bin_starts || !n_bins) return fail(SMASH_ERR_ARG, "bad argument");
+  if (!c->dix.mapbody) return fail(SMASH_ERR_STATE, "the tail needs map.bin (smash_ctx_load_mappability / smash_ctx_build_mappability)");
+  CU(cudaSetDevice(c->device));
+  // per forward chromosome: passes /^chr(\d+|[XY])$/ (smash_mapping.sh:29) and is listed in
+  // chrom_sizes.txt without '_' / chrM (varbin.py:38-49) -> its absolute offset, else -1
+  std::vector<int64_t> off;
+  const int step = c->hix->rcref ? 2 : 1;
+  for (size_t i = 0; i < c->hix->descr.size(); i += step) {
+    const std::string &nm = c->hix->descr[i];
+    int64_t o = -1;
+    bool re = nm.size() > 3 && nm.compare(0, 3, "chr") == 0;
+    if (re) {
+      const std::string t = nm.substr(3);
+      bool digits = !t.empty();
+      for (char ch : t) digits = digits && ch >= '0' && ch <= '9';
+      re = digits || t == "X" || t == "Y";
+    }
+    if (re && nm.find('_') == std::string::npos && nm != "chrM")
+      for (uint64_t k = 0; k < n_chroms; ++k)
+        if (nm == chrom_names[k]) { o = chrom_offsets[k]; break; }
+    off.push_back(o);
+  }
+  int rc = tail_configure(&c->tail, bin_starts, n_bins, off.data(), off.size(), hit_window, min_excess);
+  if (rc) return fail(rc, "tail: %s", tail_error());
+  return 0;
+}
+extern "C" int smash_tail_finish(smash_ctx *c, int64_t *counts, void *counts_device, smash_tail_stats *st) {
+  if (!c) return fail(SMASH_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  for (int s = 0; s < SMASH_N_SLOTS; ++s) CU(cudaStreamSynchronize(c->slot[s].st));
+  int rc = tail_finish(&c->tail, counts, (int64_t *)counts_device, st, c->slot[0].st, &c->launches);
+  if (rc) return fail(rc, "tail: %s", tail_error());
+  return 0;
+}
+extern "C" int smash_tail_positions(smash_ctx *c, const int32_t **chrom, const int64_t **pos, uint64_t *n) {
+  if (!c || !chrom || !pos || !n) return fail(SMASH_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  int rc = tail_positions(&c->tail, chrom, pos, n);
+  if (rc) return fail(rc, "tail: %s", tail_error());
+  return 0;
+}
+extern "C" int smash_tail_reset(smash_ctx *c) {
+  if (!c) return fail(SMASH_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  tail_reset(&c->tail);
+  return 0;
+}
+
+extern "C" uint64_t smash_ctx_launch_count(const smash_ctx *c) { return c ? c->launches : 0; }
+extern "C" uint64_t smash_ctx_index_bytes(const smash_ctx *c) { return c ? c->index_bytes : 0; }
+extern "C" void *smash_ctx_stream(const smash_ctx *c) { return c ? (void *)c->slot[0].st : nullptr; }

@@ -1,0 +1,256 @@
+// core.cuh -- data layout in HBM and the per-lane building blocks of the kernels.
+//
+// Everything here is `__host__ __device__` so that tests/emul (a host-side lane-by-lane
+// emulation used only by the CPU test-suite to debug logic without a GPU) can run exactly the
+// same functions the kernels run.  The product never executes these on the host.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define HD __host__ __device__ __forceinline__
+#define HDN __host__ __device__
+#else
+#define HD inline
+#define HDN
+#endif
+
+namespace smash {
+
+constexpr int TEXT_PAD = 64;        // zero bytes before text[0] and after text[N-1]
+constexpr int MAXQ_FAST = 1024;     // reads longer than this take the global-memory path
+constexpr int P_FRONT = 16;         // bytes of 0xFE before the staged read
+constexpr int P_BACK = 16;          // bytes of 0xFF after it
+constexpr int BIG_BUCKET = 48;      // seed buckets larger than this use the exact per-start search
+constexpr int STAGE_CAP = 64;       // matches staged in shared memory per read before spilling
+
+struct LcpItem { uint64_t idx, val; };          // .lcp.m.bin item (longSA.h:19-28), val widened
+
+// The reference's index as it lives in HBM (+ the structures derived from it at load time).
+struct DevIndex {
+  const uint8_t *text;       // N bytes (rc1.ref.seq.bin), TEXT_PAD zero bytes either side
+  uint64_t N;
+  const void *sa;            // N * w
+  const void *isa;           // N * w or null (only MEM mode / mappability build need it)
+  int w;                     // 4 or 8 (size.h:9-22)
+  const uint8_t *lcp;        // N bytes, 255 => look in lcp_m (longSA.h:34-39)
+  const LcpItem *lcp_m;
+  uint64_t n_m;
+  // derived at load (file surface unchanged):
+  const uint8_t *uniq;       // U[pos] = min(255, max(LCP[ISA[pos]], LCP[ISA[pos]+1]) + 1): shortest unique length
+  const void *seed;          // S[x] = #suffixes < k-mer x (monotone, 4^k + 1 entries)
+  int seed_k;
+  int seed_w;                // 4 or 8 bytes per entry
+  uint32_t alpha[8];         // bitmap of byte values present in text
+  // Sequence metadata (fasta.h:24-42)
+  const uint64_t *startpos;  // n_descr
+  const uint64_t *sizes;
+  int n_descr;
+  int rcref;
+  const char *descr;         // concatenated names
+  const int *descr_off;      // n_descr + 1
+  uint64_t logN;             // ceil(log2 N) as longSA.cpp:97 computes it
+  // mappability (map.bin body) + 32-bit chromosome offsets of mappability_tag (chromosomes.h:109)
+  const uint8_t *mapbody;
+  uint64_t map_bytes;
+  const uint32_t *chrom_off32;   // per forward chromosome
+};
+
+HD uint64_t sa_at(const DevIndex &ix, uint64_t i) {
+  return ix.w == 4 ? (uint64_t)((const uint32_t *)ix.sa)[i] : ((const uint64_t *)ix.sa)[i];
+}
+HD uint64_t isa_at(const DevIndex &ix, uint64_t i) {
+  return ix.w == 4 ? (uint64_t)((const uint32_t *)ix.isa)[i] : ((const uint64_t *)ix.isa)[i];
+}
+HD uint64_t seed_at(const DevIndex &ix, uint64_t x) {
+  return ix.seed_w == 4 ? (uint64_t)((const uint32_t *)ix.seed)[x] : ((const uint64_t *)ix.seed)[x];
+}
+// vec_uchar::operator[] (longSA.h:34-39)
+HD uint64_t lcp_at(const DevIndex &ix, uint64_t i) {
+  uint8_t v = ix.lcp[i];
+  if (v != 255) return v;
+  uint64_t lo = 0, hi = ix.n_m;
+  while (lo < hi) {
+    uint64_t mid = lo + ((hi - lo) >> 1);
+    if (ix.lcp_m[mid].idx < i) lo = mid + 1; else hi = mid;
+  }
+  return ix.lcp_m[lo].val;
+}
+
+// Unaligned little-endian 8-byte load from the padded text (pos may be in [-TEXT_PAD, N+TEXT_PAD-8]).
+HD uint64_t text8(const uint8_t *T, int64_t pos) {
+#if defined(__CUDA_ARCH__)
+  const uint64_t *a = reinterpret_cast<const uint64_t *>(T + (pos & ~(int64_t)7));
+  const unsigned sh = (unsigned)(pos & 7) * 8u;
+  uint64_t lo = __ldg(a);
+  if (sh == 0) return lo;
+  uint64_t hi = __ldg(a + 1);
+  return (lo >> sh) | (hi << (64u - sh));
+#else
+  uint64_t v; memcpy(&v, T + pos, 8); return v;
+#endif
+}
+// Same for the staged read (shared memory on the device). P points at read[0]; the buffer has
+// P_FRONT bytes before and P_BACK after, so pos in [-8, q+8) is fine.
+HD uint64_t read8(const uint8_t *P, int pos) {
+#if defined(__CUDA_ARCH__)
+  const uint8_t *b = P + pos;
+  const uint32_t *a = reinterpret_cast<const uint32_t *>(b - ((uintptr_t)b & 3));
+  const unsigned sh = (unsigned)((uintptr_t)b & 3) * 8u;
+  uint32_t w0 = a[0], w1 = a[1], w2 = a[2];
+  uint64_t lo = ((uint64_t)w1 << 32) | w0;
+  if (sh == 0) return lo;
+  return (lo >> sh) | ((uint64_t)w2 << (64u - sh));
+#else
+  uint64_t v; memcpy(&v, P + pos, 8); return v;
+#endif
+}
+
+HD int ctz64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)v) - 1;
+#else
+  return __builtin_ctzll(v);
+#endif
+}
+HD int clz64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)v);
+#else
+  return __builtin_clzll(v);
+#endif
+}
+
+// a,c,g,t -> 0..3 (lexicographic), anything else -> 4
+HD int base_code(uint8_t c) {
+  return c == 'a' ? 0 : c == 'c' ? 1 : c == 'g' ? 2 : c == 't' ? 3 : 4;
+}
+HD bool in_alpha(const DevIndex &ix, uint8_t c) { return (ix.alpha[c >> 5] >> (c & 31)) & 1u; }
+
+// NewQuery::extend (query.cpp:125-144): tolower, and with -n everything but acgt becomes '~'.
+HD uint8_t query_char(uint8_t c, int nucleotides_only) {
+  if (c >= 'A' && c <= 'Z') c = (uint8_t)(c + 32);
+  if (nucleotides_only && c != 'a' && c != 'c' && c != 'g' && c != 't') c = '~';
+  return c;
+}
+
+// Number of leading equal bytes of text[tpos..] and read[ppos..], at most `limit`.
+HD int match_right(const uint8_t *T, int64_t tpos, const uint8_t *P, int ppos, int limit) {
+  int m = 0;
+  while (m < limit) {
+    uint64_t d = text8(T, tpos + m) ^ read8(P, ppos + m);
+    if (d) { m += ctz64(d) >> 3; break; }
+    m += 8;
+  }
+  return m < limit ? m : limit;
+}
+// Number of equal bytes going left from text[tpos-1], read[ppos-1], at most `limit`.
+HD int match_left(const uint8_t *T, int64_t tpos, const uint8_t *P, int ppos, int limit) {
+  int m = 0;
+  while (m < limit) {
+    uint64_t d = text8(T, tpos - m - 8) ^ read8(P, ppos - m - 8);
+    if (d) { m += clz64(d) >> 3; break; }
+    m += 8;
+  }
+  return m < limit ? m : limit;
+}
+
+struct Match { uint64_t ref; uint32_t qpos, len; };     // 16 bytes in HBM
+
+// Is text[r .. r+len) unique in the text?  U answers in one byte unless it saturated.
+HD bool is_unique(const DevIndex &ix, uint64_t r, uint32_t len, uint64_t sa_index_if_known,
+                  bool have_sa_index) {
+  uint8_t u = ix.uniq[r];
+  if (u != 255) return len >= u;
+  if (len < 255) return false;
+  // saturated: need the exact LCP values around the suffix (overflow table, longSA.h:34-39)
+  uint64_t i;
+  if (have_sa_index) i = sa_index_if_known;
+  else if (ix.isa) i = isa_at(ix, r);
+  else return false;   // caller must supply the SA index when ISA is absent
+  uint64_t a = lcp_at(ix, i);
+  uint64_t b = (i + 1 < ix.N) ? lcp_at(ix, i + 1) : 0;
+  return a < len && b < len;
+}
+
+// Exact answer for ONE start p: longest prefix of P[p..q) in the text by
+// binary search over the suffix array (optionally inside the seed bucket), its uniqueness and
+// left-maximality.  Returns true and fills m when (p) is a reportable MAM.
+HD bool exact_start(const DevIndex &ix, const uint8_t *P, int q, int p, uint32_t L, Match *m) {
+  if (q - p < (int)L) return false;
+  const uint8_t *T = ix.text;
+  uint64_t lo = 0, hi = ix.N;
+  int kk = ix.seed_k < (int)L ? ix.seed_k : (int)L;
+  if (kk > q - p) kk = q - p;
+  if (kk > 0 && ix.seed) {
+    uint64_t code = 0; bool ok = true;
+    for (int j = 0; j < kk; ++j) { int b = base_code(P[p + j]); if (b > 3) { ok = false; break; } code = (code << 2) | (uint64_t)b; }
+    if (ok) {
+      int sh = 2 * (ix.seed_k - kk);
+      lo = seed_at(ix, code << sh);
+      hi = seed_at(ix, (code + 1) << sh);
+    }
+  }
+  if (lo >= hi) return false;
+  // insertion point of P[p..] in [lo,hi): l/r are exclusive virtual bounds with lcp 0
+  int64_t l = (int64_t)lo - 1, r = (int64_t)hi;
+  int llcp = 0, rlcp = 0;
+  const int rem = q - p;
+  while (r - l > 1) {
+    int64_t mid = l + ((r - l) >> 1);
+    uint64_t s = sa_at(ix, (uint64_t)mid);
+    int h = llcp < rlcp ? llcp : rlcp;
+    int lc = h + match_right(T, (int64_t)s + h, P, p + h, rem - h);
+    bool greater;   // P[p..] > suffix ?
+    if (lc == rem) greater = false;
+    else greater = P[p + lc] > ((s + (uint64_t)lc < ix.N) ? T[s + lc] : 0);
+    if (greater) { l = mid; llcp = lc; } else { r = mid; rlcp = lc; }
+  }
+  int best = llcp > rlcp ? llcp : rlcp;
+  if (best < (int)L || best < 2) return false;
+  if (llcp == rlcp) return false;                    // two suffixes share the longest match
+  uint64_t idx = (uint64_t)(llcp > rlcp ? l : r);
+  uint64_t ref = sa_at(ix, idx);
+  if (!is_unique(ix, ref, (uint32_t)best, idx, true)) return false;
+  if (!(p == 0 || ref == 0 || P[p - 1] != T[ref - 1])) return false;   // is_leftmaximal, longSA.cpp:540-546
+  m->ref = ref; m->qpos = (uint32_t)p; m->len = (uint32_t)best;
+  return true;
+}
+
+// Fast path for one anchor x = a*s (see DESIGN.md "mam_search"): every reportable match whose
+// start lies in (x-s, x] contains P[x..x+k); enumerate the seed bucket, extend each candidate
+// along its diagonal in the text and keep those that are long enough and unique.
+// Returns the number of matches appended to out (<= cap), or -1 if the anchor needs the exact path.
+HD int anchor_candidates(const DevIndex &ix, const uint8_t *P, int q, int x, int s, int k,
+                         uint32_t L, Match *out, int cap) {
+  uint64_t code = 0;
+  for (int j = 0; j < k; ++j) {
+    int b = base_code(P[x + j]);
+    if (b > 3) return 0;            // caller guarantees such a char is not in the text alphabet
+    code = (code << 2) | (uint64_t)b;
+  }
+  const int sh = 2 * (ix.seed_k - k);
+  const uint64_t lo = seed_at(ix, code << sh), hi = seed_at(ix, (code + 1) << sh);
+  if (hi - lo > (uint64_t)BIG_BUCKET) return -1;
+  const uint8_t *T = ix.text;
+  int n = 0;
+  for (uint64_t i = lo; i < hi; ++i) {
+    const uint64_t c = sa_at(ix, i);
+    const int right = match_right(T, (int64_t)c, P, x, q - x);
+    if (right < k) continue;        // bucket is a superset: suffixes between two k-mers
+    // the 0xFE pad before the read and the zero pad before the text stop this at either start
+    const int left = match_left(T, (int64_t)c, P, x, s);
+    if (left >= s) continue;        // start <= x-s: an earlier anchor owns this diagonal
+    const uint32_t len = (uint32_t)(left + right);
+    if (len < L || len < 2) continue;
+    const uint64_t ref = c - (uint64_t)left;
+    uint8_t u = ix.uniq[ref];
+    if (u == 255 && len >= 255) return -1;
+    if (len < u) continue;
+    if (n < cap) { out[n].ref = ref; out[n].qpos = (uint32_t)(x - left); out[n].len = len; }
+    ++n;
+  }
+  return n;
+}
+
+}  // namespace smash

@@ -1,0 +1,553 @@
+// kernels.cu -- hand-written sm_100a kernels of the SMASH hot path and their launchers.
+//
+//   k_uniq_build / k_seed_build / k_alpha   index-derived structures, once per context
+//   k_mam_search     K1: maximal almost-unique matches (longSA::MAM, longSA.cpp:503-546)
+//   k_records        K3: resolve + merge + CIGAR items + XE + HI order (query.cpp:68-97, 231-320)
+//   k_sizes + scan   K4a: exact SAM bytes per read and their exclusive prefix sum
+//   k_emit           K4b: SAM text (print_matches, query.cpp:331-415) at the scanned offsets
+//
+// One warp owns one read in every per-read kernel; the read is staged once in shared memory.
+// All kernels are grid-stride over reads with a grid sized from the SM count.
+#include "kernels.cuh"
+
+namespace smash {
+
+constexpr int WARPS = 8;
+constexpr int THREADS = WARPS * 32;
+constexpr int PBUF = P_FRONT + MAXQ_FAST + P_BACK;
+constexpr int SCR_CAP = 64;       // alignments per read the shared-memory scratch holds
+constexpr int LANE_CAP = 4;
+constexpr int LINE_BUF = 1024;
+
+static int g_sm_count = 0;
+static int sm_count() {
+  if (!g_sm_count) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+static int grid_for_warps(uint64_t n_items, int ctas_per_sm) {
+  uint64_t need = (n_items + WARPS - 1) / WARPS;
+  uint64_t cap = (uint64_t)sm_count() * (uint64_t)ctas_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// ------------------------------------------------------------------ derived index structures
+
+__global__ void k_alpha(const uint8_t *__restrict__ text, uint64_t N, uint32_t *alpha8) {
+  __shared__ uint32_t bm[8];
+  if (threadIdx.x < 8) bm[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint8_t c = text[i];
+    loc[c >> 5] |= 1u << (c & 31);
+  }
+  for (int j = 0; j < 8; ++j) if (loc[j]) atomicOr(&bm[j], loc[j]);
+  __syncthreads();
+  if (threadIdx.x < 8 && bm[threadIdx.x]) atomicOr(&alpha8[threadIdx.x], bm[threadIdx.x]);
+}
+
+// U[SA[i]] = min(255, max(LCP[i], LCP[i+1]) + 1): shortest unique prefix length of the suffix.
+__global__ void k_uniq_build(DevIndex ix, uint8_t *__restrict__ uniq) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ix.N; i += (uint64_t)gridDim.x * blockDim.x) {
+    int a = ix.lcp[i];
+    int b = (i + 1 < ix.N) ? ix.lcp[i + 1] : 0;
+    int m = a > b ? a : b;
+    uniq[sa_at(ix, i)] = (uint8_t)(m >= 254 ? 255 : m + 1);
+  }
+}
+
+// f(i) = number of k-mers (as strings over a<c<g<t) that are <= suffix SA[i]; monotone in i.
+__device__ __forceinline__ uint64_t kmers_le_suffix(const DevIndex &ix, uint64_t i, int k) {
+  const uint64_t s = sa_at(ix, i);
+  uint64_t code = 0;
+  for (int j = 0; j < k; ++j) {
+    const uint64_t p = s + (uint64_t)j;
+    const uint8_t ch = p < ix.N ? ix.text[p] : 0;
+    const int b = base_code(ch);
+    if (b <= 3) { code = (code << 2) | (uint64_t)b; continue; }
+    // non-acgt byte: how many of a,c,g,t sort below it (ASCII order)
+    const uint64_t below = ch < 'a' ? 0 : ch < 'c' ? 1 : ch < 'g' ? 2 : ch < 't' ? 3 : 4;
+    return ((code << 2) + below) << (2 * (k - j - 1));
+  }
+  return code + 1;
+}
+// S[x] = first SA index whose suffix is >= k-mer x  (= number of suffixes < x), x in [0, 4^k].
+template <typename SeedT>
+__global__ void k_seed_build(DevIndex ix, SeedT *__restrict__ seed, int k) {
+  const uint64_t total = ix.N + 1;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t prev = i ? kmers_le_suffix(ix, i - 1, k) : 0;
+    const uint64_t cur = i < ix.N ? kmers_le_suffix(ix, i, k) : ((1ull << (2 * k)) + 1);
+    for (uint64_t x = prev; x < cur; ++x) seed[x] = (SeedT)i;
+  }
+}
+
+int launch_alpha(const uint8_t *text, uint64_t N, uint32_t *alpha8, cudaStream_t st) {
+  cudaMemsetAsync(alpha8, 0, 32, st);
+  k_alpha<<<sm_count() * 4, 256, 0, st>>>(text, N, alpha8);
+  return 1;
+}
+int launch_uniq_build(const DevIndex &ix, uint8_t *uniq, cudaStream_t st) {
+  k_uniq_build<<<sm_count() * 8, 256, 0, st>>>(ix, uniq);
+  return 1;
+}
+int launch_seed_build(const DevIndex &ix, void *seed, int k, int seed_w, cudaStream_t st) {
+  if (seed_w == 4) k_seed_build<uint32_t><<<sm_count() * 8, 256, 0, st>>>(ix, (uint32_t *)seed, k);
+  else k_seed_build<uint64_t><<<sm_count() * 8, 256, 0, st>>>(ix, (uint64_t *)seed, k);
+  return 1;
+}
+
+// ------------------------------------------------------------------ read staging
+
+// Warp-cooperative: lower-case the read into shared memory (with the pads core.cuh relies on)
+// and report whether it holds a non-acgt byte that also occurs in the text (=> exact path).
+__device__ __forceinline__ bool stage_read(const DevIndex &ix, const uint8_t *__restrict__ seq, int q,
+                                           int nucleotides_only, uint8_t *pbuf, int lane) {
+  uint8_t *P = pbuf + P_FRONT;
+  bool odd = false;
+  for (int j = lane; j < q; j += 32) {
+    const uint8_t c = query_char(seq[j], nucleotides_only);
+    P[j] = c;
+    if (base_code(c) > 3 && in_alpha(ix, c)) odd = true;
+  }
+  if (lane < P_FRONT) pbuf[lane] = 0xFE;
+  if (lane < P_BACK) P[q + lane] = 0xFF;
+  __syncwarp();
+  return __any_sync(0xffffffffu, odd);
+}
+
+// ------------------------------------------------------------------ K1: MAM search
+
+struct SearchSmem {
+  uint8_t pbuf[WARPS][PBUF];
+  Match stage[WARPS][STAGE_CAP];
+  int nstage[WARPS];
+};
+
+__device__ __forceinline__ void stage_push(SearchSmem &sm, int warp, const Match &m) {
+  const int slot = atomicAdd(&sm.nstage[warp], 1);
+  if (slot < STAGE_CAP) sm.stage[warp][slot] = m;
+}
+
+__global__ void __launch_bounds__(THREADS)
+k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
+  __shared__ __align__(16) SearchSmem sm;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
+  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
+    const int64_t so = b.seq_off[read];
+    const int q = (int)(b.seq_off[read + 1] - so);
+    if (lane == 0) sm.nstage[warp] = 0;
+    if (q > MAXQ_FAST) {
+      if (lane == 0) { atomicAdd(&w.flags[FLAG_LONGREAD], 1u); w.match_cnt[read] = 0; }
+      __syncwarp();
+      continue;
+    }
+    const bool odd = stage_read(ix, b.seq + so, q, sp.nucleotides_only, sm.pbuf[warp], lane);
+    const uint8_t *P = sm.pbuf[warp] + P_FRONT;
+    const int L = (int)sp.L;
+    if (q >= L) {
+      if (!odd && sp.fast_ok) {
+        const int s = sp.s, k = sp.k;
+        const int n_anchor = (q - L + s - 1) / s + 1;        // anchors x = a*s cover starts 0..q-L
+        for (int a0 = 0; a0 < n_anchor; a0 += 32) {
+          const int a = a0 + lane;
+          int r = 0;
+          Match loc[LANE_CAP];
+          if (a < n_anchor) {
+            r = anchor_candidates(ix, P, q, a * s, s, k, sp.L, loc, LANE_CAP);
+            if (r > LANE_CAP) r = -1;
+            for (int i = 0; i < r; ++i) stage_push(sm, warp, loc[i]);
+          }
+          unsigned slow = __ballot_sync(0xffffffffu, r < 0);
+          while (slow) {                                     // exact per-start search for that window
+            const int la = __ffs((int)slow) - 1; slow &= slow - 1;
+            const int x = (a0 + la) * s;
+            const int p_lo = x - s + 1 > 0 ? x - s + 1 : 0;
+            for (int p = p_lo + lane; p <= x; p += 32) {
+              Match m;
+              if (exact_start(ix, P, q, p, sp.L, &m)) stage_push(sm, warp, m);
+            }
+          }
+        }
+      } else {
+        for (int p = lane; p + L <= q; p += 32) {
+          Match m;
+          if (exact_start(ix, P, q, p, sp.L, &m)) stage_push(sm, warp, m);
+        }
+      }
+    }
+    __syncwarp();
+    const int n = sm.nstage[warp];
+    const int ns = n < STAGE_CAP ? n : STAGE_CAP;
+    // ordered emission: rank by query offset (distinct per match in MAM mode)
+    Match *dst = w.match_slots + read * (uint64_t)w.cap;
+    for (int e = lane; e < ns; e += 32) {
+      const Match me = sm.stage[warp][e];
+      int rank = 0;
+      for (int f = 0; f < ns; ++f) rank += sm.stage[warp][f].qpos < me.qpos;
+      if (rank < w.cap) dst[rank] = me;
+    }
+    if (lane == 0) {
+      w.match_cnt[read] = (uint32_t)n;
+      if (n > w.cap || n > STAGE_CAP) atomicAdd(&w.flags[FLAG_OVERFLOW], 1u);
+      atomicMax(&w.flags[FLAG_MAXCNT], (uint32_t)n);
+    }
+    __syncwarp();
+  }
+}
+
+int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
+  if (!b.n_reads) return 0;
+  k_mam_search<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p);
+  return 1;
+}
+
+// ------------------------------------------------------------------ K3: records
+
+struct RecSmem {
+  uint8_t pbuf[WARPS][PBUF];
+  Aln aln[WARPS][SCR_CAP];
+  uint16_t ord[WARPS][SCR_CAP];
+  int nrec[WARPS];
+};
+
+__global__ void __launch_bounds__(THREADS)
+k_records(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
+  __shared__ __align__(16) RecSmem sm;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
+  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
+    const int64_t so = b.seq_off[read];
+    const int q = (int)(b.seq_off[read + 1] - so);
+    int n_in = (int)w.match_cnt[read];
+    if (n_in > w.cap) n_in = w.cap;
+    if (n_in > SCR_CAP) n_in = SCR_CAP;
+    const int qs = q > MAXQ_FAST ? 0 : q;
+    stage_read(ix, b.seq + so, qs, sp.nucleotides_only, sm.pbuf[warp], lane);
+    const uint8_t *P = sm.pbuf[warp] + P_FRONT;
+    Item *items = w.item_slots + read * (uint64_t)w.cap;
+    Rec *recs = w.rec_slots + read * (uint64_t)w.cap;
+    if (lane == 0) {
+      sm.nrec[warp] = build_records(ix, w.match_slots + read * (uint64_t)w.cap, n_in, q, sp.nomap,
+                                    sm.aln[warp], sm.ord[warp], items, recs, &w.sums[read]);
+    }
+    __syncwarp();
+    const int n_rec = sm.nrec[warp];
+    const bool unmapped = w.sums[read].unmapped;
+    if (!unmapped) {
+      for (int r = 0; r < n_rec; ++r) {                    // XE: all lanes, 8 read bytes each
+        const int64_t rcpos = recs[r].rcpos;
+        int cnt = 0;
+        for (int j0 = lane * 8; j0 < q; j0 += 256) cnt += xe_word(ix, P, q, rcpos, j0);
+        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) recs[r].xe = (uint16_t)cnt;
+      }
+      if (ix.mapbody) {                                    // L0/R0 + the tagger's range check
+        for (int r = lane; r < n_rec; r += 32) {
+          bool ok = true; int L0 = 0, R0 = 0;
+          for (int u = 0; u < recs[r].item_cnt; ++u) {
+            const Item it = items[recs[r].item_begin + u];
+            int L, R;
+            ok = map_lr(ix, recs[r].si >> 1, recs[r].pos, it.prefix, it.len, &L, &R) && ok;
+            if (u == 0) { L0 = L; R0 = R; }
+          }
+          recs[r].L0 = (uint8_t)L0; recs[r].R0 = (uint8_t)R0;
+          if (!ok) {
+            // mappability_tag.cpp:107-113 throws unless the chromosome is _gl000*/chrM
+            const char *nm = ix.descr + ix.descr_off[recs[r].si];
+            const int nl = ix.descr_off[recs[r].si + 1] - ix.descr_off[recs[r].si];
+            bool small = false;
+            for (int i = 0; i + 4 <= nl; ++i) if (nm[i] == 'c' && nm[i + 1] == 'h' && nm[i + 2] == 'r' && nm[i + 3] == 'M') small = true;
+            for (int i = 0; i + 6 <= nl; ++i) if (nm[i] == '_' && nm[i + 1] == 'g' && nm[i + 2] == 'l' && nm[i + 3] == '0' && nm[i + 4] == '0' && nm[i + 5] == '0') small = true;
+            if (!small) atomicAdd(&w.flags[FLAG_MAPERR], 1u);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+int launch_records(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
+  if (!b.n_reads) return 0;
+  k_records<<<grid_for_warps(b.n_reads, 6), THREADS, 0, st>>>(ix, b, w, p);
+  return 1;
+}
+
+// ------------------------------------------------------------------ K4a: sizes + scan
+
+// flag + mate view of one read (set_mate, query.cpp:421-434)
+__device__ __forceinline__ void read_mate(const BatchDev &b, const WorkDev &w, uint64_t read,
+                                          uint16_t *flag, MateView *mv) {
+  const ReadSum me = w.sums[read];
+  const uint16_t mine = (uint16_t)(b.read_flag[read] | (me.unmapped ? 4 : 0));
+  const uint64_t other = read ^ 1ull;
+  if (other < b.n_reads) {
+    const ReadSum ot = w.sums[other];
+    const uint16_t of = (uint16_t)(b.read_flag[other] | (ot.unmapped ? 4 : 0));
+    mate_view(mine, me, of, &ot, (read & 1ull) == 0, mv, flag);
+  } else {
+    mate_view(mine, me, 0, nullptr, true, mv, flag);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS)
+k_sizes(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
+  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
+    const ReadSum me = w.sums[read];
+    const int n_rec = me.n_rec;
+    uint32_t bytes = 0;
+    if (n_rec) {
+      uint16_t flag; MateView mv;
+      read_mate(b, w, read, &flag, &mv);
+      const int q = (int)(b.seq_off[read + 1] - b.seq_off[read]);
+      const int name_len = (int)(b.name_off[read + 1] - b.name_off[read]);
+      const int opt_len = b.opt ? (int)(b.opt_off[read + 1] - b.opt_off[read]) : 0;
+      const Item *items = w.item_slots + read * (uint64_t)w.cap;
+      const Rec *recs = w.rec_slots + read * (uint64_t)w.cap;
+      for (int r = lane; r < n_rec; r += 32) {             // one lane per record
+        CountSink cs;
+        put_head(cs, ix, (const char *)nullptr, name_len, flag, me.unmapped, recs[r], r, items, mv);
+        put_tags(cs, ix, me.unmapped, recs, r, n_rec, items);
+        if (sp.tag_mappability && !me.unmapped) put_lr_tags(cs, ix, recs[r], items);
+        bytes += cs.n + 2u * (uint32_t)q + 1u /*tab between SEQ and QUAL*/ + (uint32_t)opt_len + 1u /*\n*/;
+      }
+    }
+    for (int o = 16; o; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
+    if (lane == 0) w.read_bytes[read] = bytes;
+  }
+}
+
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_BLOCK = 256;
+constexpr int SCAN_TILE = SCAN_ITEMS * SCAN_BLOCK;
+
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t *total) {
+  __shared__ uint64_t wsum[SCAN_BLOCK / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t inc = v;
+  for (int o = 1; o < 32; o <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t s = lane < SCAN_BLOCK / 32 ? wsum[lane] : 0, si = s;
+    for (int o = 1; o < 32; o <<= 1) { uint64_t t = __shfl_up_sync(0xffffffffu, si, o); if (lane >= o) si += t; }
+    if (lane < SCAN_BLOCK / 32) wsum[lane] = si - s;
+    if (lane == 31) *total = si;
+  }
+  __syncthreads();
+  const uint64_t r = wsum[warp] + inc - v;
+  __syncthreads();
+  return r;
+}
+
+__global__ void k_scan_tiles(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ blk) {
+  __shared__ uint64_t tot;
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint64_t s = 0;
+  for (int i = 0; i < SCAN_ITEMS; ++i) if (base + i < n) s += in[base + i];
+  block_exclusive_scan(s, &tot);
+  if (threadIdx.x == 0) blk[blockIdx.x] = tot;
+}
+__global__ void k_scan_top(uint64_t *blk, uint64_t n_blk) {
+  __shared__ uint64_t tot;
+  __shared__ uint64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint64_t b0 = 0; b0 < n_blk; b0 += SCAN_BLOCK) {
+    const uint64_t i = b0 + threadIdx.x;
+    const uint64_t v = i < n_blk ? blk[i] : 0;
+    const uint64_t ex = block_exclusive_scan(v, &tot);
+    if (i < n_blk) blk[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) blk[n_blk] = carry;
+}
+__global__ void k_scan_apply(const uint32_t *__restrict__ in, uint64_t n, const uint64_t *__restrict__ blk,
+                             uint64_t *__restrict__ out) {
+  __shared__ uint64_t tot;
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS]; uint64_t s = 0;
+  for (int i = 0; i < SCAN_ITEMS; ++i) { v[i] = base + i < n ? in[base + i] : 0; s += v[i]; }
+  uint64_t ex = block_exclusive_scan(s, &tot) + blk[blockIdx.x];
+  for (int i = 0; i < SCAN_ITEMS; ++i) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = blk[gridDim.x];
+}
+static int exclusive_scan_u32(const uint32_t *in, uint64_t n, uint64_t *blk, uint64_t *out, cudaStream_t st) {
+  const uint64_t n_blk = (n + SCAN_TILE - 1) / SCAN_TILE;
+  k_scan_tiles<<<(unsigned)n_blk, SCAN_BLOCK, 0, st>>>(in, n, blk);
+  k_scan_top<<<1, SCAN_BLOCK, 0, st>>>(blk, n_blk);
+  k_scan_apply<<<(unsigned)n_blk, SCAN_BLOCK, 0, st>>>(in, n, blk, out);
+  return 3;
+}
+
+int launch_sizes_scan(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
+  if (!b.n_reads) return 0;
+  k_sizes<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p);
+  return 1 + exclusive_scan_u32(w.read_bytes, b.n_reads, w.blk_sums, w.out_off, st);
+}
+
+// ------------------------------------------------------------------ K4b: emit
+
+struct EmitSmem { char line[WARPS][LINE_BUF]; };
+
+// all lanes: copy n bytes from shared/global src to global dst
+__device__ __forceinline__ void warp_copy(char *__restrict__ dst, const char *__restrict__ src, int n, int lane) {
+  for (int i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(THREADS)
+k_emit(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
+  __shared__ EmitSmem sm;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
+  char *line = sm.line[warp];
+  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
+    const ReadSum me = w.sums[read];
+    const int n_rec = me.n_rec;
+    if (!n_rec) continue;
+    uint16_t flag; MateView mv;
+    read_mate(b, w, read, &flag, &mv);
+    const int64_t so = b.seq_off[read];
+    const int q = (int)(b.seq_off[read + 1] - so);
+    const char *name = (const char *)b.names + b.name_off[read];
+    const int name_len = (int)(b.name_off[read + 1] - b.name_off[read]);
+    const char *opt = b.opt ? (const char *)b.opt + b.opt_off[read] : nullptr;
+    const int opt_len = b.opt ? (int)(b.opt_off[read + 1] - b.opt_off[read]) : 0;
+    const Item *items = w.item_slots + read * (uint64_t)w.cap;
+    const Rec *recs = w.rec_slots + read * (uint64_t)w.cap;
+    const uint8_t *seq = b.seq + so, *qual = b.qual + so;
+    char *out = w.sam + w.out_off[read];
+    for (int r = 0; r < n_rec; ++r) {
+      // --- columns 1-9: name copied by the warp, the rest composed by lane 0 in shared memory
+      warp_copy(out, name, name_len, lane);
+      out += name_len;
+      int n = 0;
+      if (lane == 0) {
+        CountSink cs; put_head(cs, ix, (const char *)nullptr, 0, flag, me.unmapped, recs[r], r, items, mv);
+        n = (int)cs.n;
+        if (n <= LINE_BUF) { BufSink bs{line}; put_head(bs, ix, (const char *)nullptr, 0, flag, me.unmapped, recs[r], r, items, mv); }
+        else { BufSink bs{out}; put_head(bs, ix, (const char *)nullptr, 0, flag, me.unmapped, recs[r], r, items, mv); }
+      }
+      n = __shfl_sync(0xffffffffu, n, 0);
+      if (n <= LINE_BUF) warp_copy(out, line, n, lane);
+      out += n;
+      // --- SEQ \t QUAL (reverse-complemented / reversed for a reverse-strand record)
+      if (recs[r].rc && !me.unmapped) {
+        for (int j = lane; j < q; j += 32) { out[j] = (char)comp_char(seq[q - 1 - j]); out[q + 1 + j] = (char)qual[q - 1 - j]; }
+      } else {
+        for (int j = lane; j < q; j += 32) { out[j] = (char)seq[j]; out[q + 1 + j] = (char)qual[j]; }
+      }
+      if (lane == 0) out[q] = '\t';
+      out += 2 * q + 1;
+      __syncwarp();
+      // --- tags
+      if (lane == 0) {
+        CountSink cs; put_tags(cs, ix, me.unmapped, recs, r, n_rec, items);
+        n = (int)cs.n;
+        if (n <= LINE_BUF) { BufSink bs{line}; put_tags(bs, ix, me.unmapped, recs, r, n_rec, items); }
+        else { BufSink bs{out}; put_tags(bs, ix, me.unmapped, recs, r, n_rec, items); }
+      }
+      n = __shfl_sync(0xffffffffu, n, 0);
+      if (n <= LINE_BUF) warp_copy(out, line, n, lane);
+      out += n;
+      if (opt_len) { warp_copy(out, opt, opt_len, lane); out += opt_len; }
+      __syncwarp();
+      if (sp.tag_mappability && !me.unmapped) {
+        if (lane == 0) { BufSink bs{line}; put_lr_tags(bs, ix, recs[r], items); n = (int)bs.n; }
+        n = __shfl_sync(0xffffffffu, n, 0);
+        warp_copy(out, line, n, lane);
+        out += n;
+        __syncwarp();
+      }
+      if (lane == 0) *out = '\n';
+      out += 1;
+    }
+  }
+}
+
+int launch_emit(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
+  if (!b.n_reads) return 0;
+  k_emit<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p);
+  return 1;
+}
+
+// ------------------------------------------------------------------ matches -> CSR for the host
+
+__global__ void k_match_copy(BatchDev b, WorkDev w, const uint64_t *__restrict__ off, uint64_t *__restrict__ triples) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
+  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
+    const uint32_t n = w.match_cnt[read];
+    const Match *src = w.match_slots + read * (uint64_t)w.cap;
+    uint64_t *dst = triples + 3 * off[read];
+    for (uint32_t i = lane; i < n && i < (uint32_t)w.cap; i += 32) {
+      dst[3 * i] = src[i].ref; dst[3 * i + 1] = src[i].qpos; dst[3 * i + 2] = src[i].len;
+    }
+  }
+}
+int launch_match_csr(const BatchDev &b, const WorkDev &w, int64_t *off, uint64_t *triples, uint64_t *scratch, cudaStream_t st) {
+  if (!b.n_reads) return 0;
+  int n = exclusive_scan_u32(w.match_cnt, b.n_reads, scratch, (uint64_t *)off, st);
+  k_match_copy<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(b, w, (const uint64_t *)off, triples);
+  return n + 1;
+}
+
+// ------------------------------------------------------------------ map.bin on the GPU
+
+// longSA::show, bin=true (longSA.cpp:612-690): two bytes per forward base.  The reference fills an
+// N-entry vector in SA order and then edits single entries; every entry is visited once, so the
+// result is a pure function of (SA, ISA, LCP) that is evaluated here per base, with no scratch.
+__device__ __forceinline__ uint64_t min_unique_len(const DevIndex &ix, uint64_t sa_index) {
+  const uint64_t a = lcp_at(ix, sa_index);
+  const uint64_t b = sa_index + 1 < ix.N ? lcp_at(ix, sa_index + 1) : 0;
+  return (a > b ? a : b) + 1;
+}
+__global__ void k_mappability(DevIndex ix, int chrom, uint64_t out_base, uint8_t *__restrict__ body) {
+  const uint64_t start = ix.startpos[chrom], size = ix.sizes[chrom];
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t r = min_unique_len(ix, isa_at(ix, start + i));
+    uint64_t l = min_unique_len(ix, isa_at(ix, start + 2 * size - i));
+    if (r + i >= size) r = 0;
+    if (l >= i) l = 0;
+    body[out_base + 2 * i] = (uint8_t)(l < 255 ? l : 255);
+    body[out_base + 2 * i + 1] = (uint8_t)(r < 255 ? r : 255);
+  }
+}
+int launch_mappability(const DevIndex &ix, uint64_t *, uint8_t *body, cudaStream_t st) {
+  // host-side loop over forward chromosomes; startpos/sizes are read on the device
+  int launches = 0;
+  uint64_t base = 0;
+  uint64_t *h_sizes = new uint64_t[ix.n_descr];
+  cudaMemcpyAsync(h_sizes, ix.sizes, sizeof(uint64_t) * ix.n_descr, cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  for (int c = 0; c < ix.n_descr; c += 2) {
+    k_mappability<<<sm_count() * 8, 256, 0, st>>>(ix, c, base, body);
+    base += 2 * h_sizes[c];
+    ++launches;
+  }
+  delete[] h_sizes;
+  return launches;
+}
+
+int launch_mem_search(const DevIndex &, const BatchDev &, const WorkDev &, const SearchParams &, cudaStream_t) {
+  return -1;   // K2 lands in mem_search.cu
+}
+
+}  // namespace smash
+
+namespace smash {
+int exclusive_scan_u32_public(const uint32_t *in, uint64_t n, uint64_t *blk, uint64_t *out, cudaStream_t st) {
+  return exclusive_scan_u32(in, n, blk, out, st);
+}
+}  // namespace smash

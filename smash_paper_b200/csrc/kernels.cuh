@@ -1,0 +1,57 @@
+// kernels.cuh -- device-side views shared by kernels.cu (kernels + launchers) and api.cu (host).
+#pragma once
+#include <cuda_runtime.h>
+#include "core.cuh"
+#include "records.cuh"
+
+namespace smash {
+
+struct BatchDev {
+  uint64_t n_reads;
+  const uint8_t *names; const int64_t *name_off;
+  const uint8_t *seq; const uint8_t *qual; const int64_t *seq_off;
+  const uint8_t *opt; const int64_t *opt_off;      // opt may be null
+  const uint16_t *read_flag;
+};
+
+enum { FLAG_OVERFLOW = 0, FLAG_MAPERR = 1, FLAG_LONGREAD = 2, FLAG_MAXCNT = 3, N_FLAGS = 8 };
+
+struct WorkDev {
+  int cap;                     // slots per read (matches / items / records)
+  Match *match_slots;          // n_reads * cap
+  uint32_t *match_cnt;         // n_reads (true count, may exceed cap => overflow flag)
+  Item *item_slots;            // n_reads * cap
+  Rec *rec_slots;              // n_reads * cap
+  ReadSum *sums;               // n_reads
+  uint32_t *read_bytes;        // n_reads: SAM bytes of the read's records
+  uint64_t *out_off;           // n_reads + 1 (exclusive scan of read_bytes)
+  uint64_t *blk_sums;          // scan scratch
+  char *sam;                   // output text
+  uint64_t sam_cap;
+  uint32_t *flags;             // N_FLAGS counters
+};
+
+struct SearchParams {
+  uint32_t L;                  // effective min_len = max(min_len, 2)
+  int k;                       // seed length used = min(seed_k, L)
+  int s;                       // anchor stride = L - k + 1
+  int nucleotides_only;
+  int nomap;
+  int tag_mappability;
+  int fast_ok;                 // 0 => every read takes the exact per-start path
+};
+
+// launchers (all asynchronous on `st`); each returns the number of kernels it launched
+int launch_uniq_build(const DevIndex &ix, uint8_t *uniq, cudaStream_t st);
+int launch_seed_build(const DevIndex &ix, void *seed, int k, int seed_w, cudaStream_t st);
+int launch_alpha(const uint8_t *text, uint64_t N, uint32_t *alpha8, cudaStream_t st);
+int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
+int launch_mem_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
+int launch_records(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
+int launch_sizes_scan(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
+int launch_emit(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
+// matches -> CSR (offsets int64[n+1] + smash_match-compatible {u64 ref, u64 query, u64 len})
+int launch_match_csr(const BatchDev &b, const WorkDev &w, int64_t *off, uint64_t *triples, uint64_t *scratch, cudaStream_t st);
+int launch_mappability(const DevIndex &ix, uint64_t *min_len_scratch, uint8_t *body, cudaStream_t st);
+
+}  // namespace smash

@@ -1,0 +1,400 @@
+// records.cuh -- per-read record construction (Alignment::resolve + prepare_matches + set_nomap,
+// query.cpp:68-97, 231-320) and SAM line formatting (print_matches, query.cpp:331-415) as
+// lane-serial building blocks.  See DESIGN.md "records" / "sam_emit".
+#pragma once
+#include "core.cuh"
+
+namespace smash {
+
+// One alignment while a read is being processed (scratch, shared memory).
+struct Aln {
+  int64_t rcpos, pos;
+  uint32_t si;
+  uint16_t prefix, len, suffix, qpos;      // qpos may be lowered by the merge (query.cpp:283)
+  uint16_t xm, xu;                         // n_matches, n_unique_bases (moved along the group)
+  uint8_t rc, last;                        // last: this alignment carries its group's record
+  uint16_t first_item, last_item;          // group's first/last position in merge order
+};
+
+// One printed record in HBM (records of a read are stored in HI order => prev/next implicit).
+struct Rec {
+  int64_t pos;           // 0-based position on chromosome si
+  int64_t rcpos;         // text position of read offset 0 on the matched strand (for XE)
+  uint32_t si;           // even seq_index (forward copy)
+  uint16_t item_begin, item_cnt;   // CIGAR items (merge order) in the read's item slots
+  uint16_t xu, xe, qlen, suffix;   // qlen = read length minus soft clips (pysam qlen)
+  uint8_t rc, L0, R0, flags;       // L0/R0: mappability_tag values of the first '=' block
+};
+struct Item { uint16_t prefix, len; };
+
+// Per-read summary (what the mate and the size/emit kernels need).
+struct ReadSum {
+  int64_t best_pos;
+  uint32_t best_si;
+  uint16_t n_rec;        // records to print (1 for an unmapped placeholder)
+  uint8_t has_best;      // best_alignment != nullptr
+  uint8_t unmapped;      // placeholder present (read_flag |= 4)
+};
+
+// ---- libstdc++ std::sort on an index array (bits/stl_algo.h), needed because to_print has real
+// ties in MEM mode: threshold 16, median-of-3 to first, unguarded
+// partition, heap sort when the depth limit is hit, final insertion sort.
+template <class Less>
+struct StdSort {
+  uint16_t *v; Less lt;
+  HDN void linear_insert(int last) {
+    uint16_t val = v[last]; int next = last - 1;
+    while (lt(val, v[next])) { v[last] = v[next]; last = next; --next; }
+    v[last] = val;
+  }
+  HDN void insertion(int first, int last) {
+    if (first == last) return;
+    for (int i = first + 1; i != last; ++i) {
+      if (lt(v[i], v[first])) {
+        uint16_t val = v[i];
+        for (int j = i; j > first; --j) v[j] = v[j - 1];
+        v[first] = val;
+      } else linear_insert(i);
+    }
+  }
+  HDN void push_heap(int first, int hole, int top, uint16_t val) {
+    int parent = (hole - 1) / 2;
+    while (hole > top && lt(v[first + parent], val)) {
+      v[first + hole] = v[first + parent]; hole = parent; parent = (hole - 1) / 2;
+    }
+    v[first + hole] = val;
+  }
+  HDN void adjust_heap(int first, int hole, int len, uint16_t val) {
+    const int top = hole; int child = hole;
+    while (child < (len - 1) / 2) {
+      child = 2 * (child + 1);
+      if (lt(v[first + child], v[first + child - 1])) child--;
+      v[first + hole] = v[first + child]; hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+      child = 2 * (child + 1);
+      v[first + hole] = v[first + child - 1]; hole = child - 1;
+    }
+    push_heap(first, hole, top, val);
+  }
+  HDN void heap_sort(int first, int last) {
+    int len = last - first;
+    if (len >= 2)
+      for (int parent = (len - 2) / 2;; --parent) { adjust_heap(first, parent, len, v[first + parent]); if (parent == 0) break; }
+    while (last - first > 1) {
+      --last; uint16_t val = v[last]; v[last] = v[first];
+      adjust_heap(first, 0, last - first, val);
+    }
+  }
+  HDN void swp(int a, int b) { uint16_t t = v[a]; v[a] = v[b]; v[b] = t; }
+  HDN void median_to_first(int res, int a, int b, int c) {
+    if (lt(v[a], v[b])) {
+      if (lt(v[b], v[c])) swp(res, b); else if (lt(v[a], v[c])) swp(res, c); else swp(res, a);
+    } else if (lt(v[a], v[c])) swp(res, a);
+    else if (lt(v[b], v[c])) swp(res, c);
+    else swp(res, b);
+  }
+  HDN int partition(int first, int last, int pivot) {
+    for (;;) {
+      while (lt(v[first], v[pivot])) ++first;
+      --last;
+      while (lt(v[pivot], v[last])) --last;
+      if (!(first < last)) return first;
+      swp(first, last); ++first;
+    }
+  }
+  HDN void run(int n) {
+    if (n <= 0) return;
+    if (n > 16) {
+      // __introsort_loop with an explicit stack (the recursion is on the right part)
+      int lg = 0; for (int k = n; k > 1; k >>= 1) ++lg;
+      int stk_first[40], stk_last[40], stk_depth[40], sp = 0;
+      stk_first[0] = 0; stk_last[0] = n; stk_depth[0] = 2 * lg; sp = 1;
+      while (sp) {
+        --sp; int first = stk_first[sp], last = stk_last[sp], depth = stk_depth[sp];
+        while (last - first > 16) {
+          if (depth == 0) { heap_sort(first, last); break; }
+          --depth;
+          int mid = first + (last - first) / 2;
+          median_to_first(first, first + 1, mid, last - 1);
+          int cut = partition(first + 1, last, first);
+          if (sp < 40) { stk_first[sp] = cut; stk_last[sp] = last; stk_depth[sp] = depth; ++sp; }
+          last = cut;
+        }
+      }
+      insertion(0, 16);
+      for (int i = 16; i != n; ++i) linear_insert(i);
+    } else insertion(0, n);
+  }
+};
+// NOTE on the explicit stack: libstdc++ recurses on [cut,last) FIRST and then continues with
+// [first,cut).  The two halves are disjoint, so processing order does not change the result.
+
+struct LessMerge {   // to_merge, query.cpp:203-219
+  const Aln *a;
+  HDN bool operator()(uint16_t x, uint16_t y) const {
+    const Aln &p = a[x], &q = a[y];
+    if (p.rc != q.rc) return p.rc < q.rc;
+    if (p.si != q.si) return p.si < q.si;
+    if (p.pos != q.pos) return p.pos < q.pos;
+    return p.prefix < q.prefix;
+  }
+};
+struct LessPrint {   // to_print, query.cpp:221-229
+  const Aln *a;
+  HDN bool operator()(uint16_t x, uint16_t y) const {
+    const Aln &p = a[x], &q = a[y];
+    if (p.qpos == q.qpos) return p.rc < q.rc;
+    return p.qpos < q.qpos;
+  }
+};
+
+// Alignment::resolve (query.cpp:68-97)
+HD void resolve_match(const DevIndex &ix, const Match &m, int q, Aln *a) {
+  int lo = 0, hi = ix.n_descr;                       // upper_bound(startpos, ref)
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (ix.startpos[mid] <= m.ref) lo = mid + 1; else hi = mid; }
+  uint32_t si = (uint32_t)(lo - 1);
+  a->rcpos = (int64_t)m.ref - (int64_t)m.qpos;
+  a->pos = a->rcpos - (int64_t)ix.startpos[si];
+  const uint32_t extra = (uint32_t)q - m.len - m.qpos;
+  if (ix.rcref && (si & 1u)) {
+    si -= 1;
+    a->pos = (int64_t)ix.sizes[si] - a->pos - (int64_t)q;
+    a->prefix = (uint16_t)extra; a->suffix = (uint16_t)m.qpos; a->rc = 1;
+  } else {
+    a->prefix = (uint16_t)m.qpos; a->suffix = (uint16_t)extra; a->rc = 0;
+  }
+  a->si = si; a->qpos = (uint16_t)m.qpos; a->len = (uint16_t)m.len;
+  a->xm = 0; a->xu = 0; a->last = 0; a->first_item = 0; a->last_item = 0;
+}
+
+// prepare_matches (query.cpp:231-306) + set_nomap (308-320), lane-serial.
+//   aln[n_in] scratch, ord[n_in] scratch; writes items[] (merge order), recs[] (HI order), sum.
+// Returns the number of records (0 if the read prints nothing).
+HDN inline int build_records(const DevIndex &ix, const Match *matches, int n_in, int q, int nomap,
+                             Aln *aln, uint16_t *ord, Item *items, Rec *recs, ReadSum *sum) {
+  int n = 0;
+  for (int i = 0; i < n_in; ++i) {
+    Aln a; resolve_match(ix, matches[i], q, &a);
+    if (a.pos < 0) continue;                          // query.cpp:239-246
+    aln[n] = a; ord[n] = (uint16_t)n; ++n;
+  }
+  sum->has_best = 0; sum->unmapped = 0; sum->best_pos = 0; sum->best_si = 0; sum->n_rec = 0;
+  int n_rec = 0;
+  if (n) {
+    StdSort<LessMerge> s1{ord, LessMerge{aln}}; s1.run(n);
+    int group_first = 0;
+    for (int i = 0; i < n; ++i) {
+      Aln &a = aln[ord[i]];
+      items[i].prefix = a.prefix; items[i].len = a.len;
+      a.xm += 1; a.xu += a.len;
+      const bool end = (i + 1 == n) || aln[ord[i + 1]].pos != a.pos || aln[ord[i + 1]].si != a.si ||
+                       aln[ord[i + 1]].rc != a.rc;
+      if (end) {
+        a.last = 1; a.first_item = (uint16_t)group_first; a.last_item = (uint16_t)i; group_first = i + 1;
+      } else {
+        Aln &na = aln[ord[i + 1]];
+        na.qpos = a.qpos < na.qpos ? a.qpos : na.qpos;
+        na.xm = a.xm; a.xm = 0;                       // ::swap + zero (query.cpp:284-287)
+        na.xu = a.xu; a.xu = 0;
+      }
+    }
+    StdSort<LessPrint> s2{ord, LessPrint{aln}}; s2.run(n);
+    const Aln &b = aln[ord[0]];
+    sum->has_best = 1; sum->best_si = b.si; sum->best_pos = b.pos;
+    for (int i = 0; i < n; ++i) {
+      const Aln &a = aln[ord[i]];
+      if (!a.last) continue;
+      Rec r;
+      const int last_item = a.last_item;
+      r.pos = a.pos; r.rcpos = a.rcpos; r.si = a.si; r.rc = a.rc;
+      r.item_begin = a.first_item; r.item_cnt = (uint16_t)(last_item - a.first_item + 1);
+      r.xu = a.xu; r.xe = 0;
+      const int lead = items[a.first_item].prefix;
+      const int endq = items[last_item].prefix + items[last_item].len;
+      r.suffix = (uint16_t)(q - endq);
+      r.qlen = (uint16_t)(endq - lead);
+      r.L0 = 0; r.R0 = 0; r.flags = 0;
+      recs[n_rec++] = r;
+    }
+  }
+  if (n_rec == 0 && nomap) {                          // set_nomap
+    sum->unmapped = 1; n_rec = 1;
+    Rec r; r.pos = 0; r.rcpos = 0; r.si = 0; r.rc = 0; r.item_begin = 0; r.item_cnt = 0;
+    r.xu = 0; r.xe = 0; r.qlen = 0; r.suffix = 0; r.L0 = 0; r.R0 = 0; r.flags = 0;
+    recs[0] = r;
+  }
+  sum->n_rec = (uint16_t)n_rec;
+  return n_rec;
+}
+
+// XE contribution of read bytes [j0, j0+8) of one record (query.cpp:270-274).
+HD int xe_word(const DevIndex &ix, const uint8_t *P, int q, int64_t rcpos, int j0) {
+  int cnt = 0;
+  const int64_t rp = rcpos + j0;
+  if (rp >= 0 && rp + 8 <= (int64_t)ix.N && j0 + 8 <= q) {
+    uint64_t d = text8(ix.text, rp) ^ read8(P, j0);
+    // count zero bytes of d
+    uint64_t t = (d & 0x7f7f7f7f7f7f7f7fULL) + 0x7f7f7f7f7f7f7f7fULL;
+    t = ~(t | d | 0x7f7f7f7f7f7f7f7fULL);
+#if defined(__CUDA_ARCH__)
+    cnt = __popcll(t);
+#else
+    cnt = __builtin_popcountll(t);
+#endif
+  } else {
+    for (int j = j0; j < j0 + 8 && j < q; ++j) {
+      const int64_t p = rcpos + j;
+      if (p >= 0 && p < (int64_t)ix.N && ix.text[p] == P[j]) ++cnt;
+    }
+  }
+  return cnt;
+}
+
+// mappability_tag.cpp:93-121 for one '=' block: abs = off32[chr] + POS (32-bit), block at read
+// offset `off` of length `cnt`.  Returns false where the reference throws.
+HD bool map_lr(const DevIndex &ix, uint32_t chrom, int64_t pos0, uint32_t off, uint32_t cnt,
+               int *L, int *R) {
+  const uint32_t abspos = ix.chrom_off32[chrom] + (uint32_t)(pos0 + 1);
+  const uint32_t li = abspos + off + cnt - 1u, ri = abspos + off - 1u;
+  const uint64_t lb = 2ull * li, rb = 2ull * ri + 1ull;
+  const int lm = lb < ix.map_bytes ? ix.mapbody[lb] : 0;
+  const int rm = rb < ix.map_bytes ? ix.mapbody[rb] : 0;
+  *L = lm ? lm - 1 : 255;
+  *R = rm ? rm : 255;
+  return !((uint32_t)*L > cnt || (uint32_t)*R > cnt);
+}
+
+// ---- SAM text --------------------------------------------------------------------------------
+struct CountSink {
+  uint32_t n = 0;
+  HDN void ch(char) { ++n; }
+  HDN void put(const char *, int len) { n += (uint32_t)len; }
+};
+struct BufSink {
+  char *p; uint32_t n = 0;
+  HDN void ch(char c) { p[n++] = c; }
+  HDN void put(const char *s, int len) { for (int i = 0; i < len; ++i) p[n + i] = s[i]; n += (uint32_t)len; }
+};
+template <class S> HDN inline void put_u64(S &s, uint64_t v) {
+  char t[20]; int n = 0;
+  do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  while (n) s.ch(t[--n]);
+}
+template <class S> HDN inline void put_i64(S &s, int64_t v) {
+  if (v < 0) { s.ch('-'); put_u64(s, (uint64_t)(-v)); } else put_u64(s, (uint64_t)v);
+}
+template <class S> HDN inline void put_lit(S &s, const char *lit) { int n = 0; while (lit[n]) ++n; s.put(lit, n); }
+template <class S> HDN inline void put_descr(S &s, const DevIndex &ix, uint32_t si) {
+  s.put(ix.descr + ix.descr_off[si], ix.descr_off[si + 1] - ix.descr_off[si]);
+}
+// CIGAR of a record (query.cpp:260-268): [<prefix>S] len= [<gap>M len=]... [<suffix>S]
+template <class S> HDN inline void put_cigar(S &s, const Rec &r, const Item *items) {
+  if (r.item_cnt == 0) { s.ch('*'); return; }
+  uint32_t last_end = 0;
+  for (int i = 0; i < r.item_cnt; ++i) {
+    const Item it = items[r.item_begin + i];
+    if (it.prefix) { put_u64(s, it.prefix - last_end); s.ch(last_end ? 'M' : 'S'); }
+    put_u64(s, it.len); s.ch('=');
+    last_end = (uint32_t)it.prefix + it.len;
+  }
+  if (r.suffix) { put_u64(s, r.suffix); s.ch('S'); }
+}
+
+struct MateView { uint8_t has; uint32_t si; int64_t pos; };
+
+// set_mate (query.cpp:421-434) seen from one read: which (chr,pos) goes into RNEXT/PNEXT (and,
+// for a placeholder, RNAME/POS), and whether flag 8 is added.
+HD void mate_view(uint16_t my_flag, const ReadSum &me, uint16_t other_flag, const ReadSum *other,
+                  bool is_first_of_pair, MateView *mv, uint16_t *flag_out) {
+  mv->has = 0; mv->si = 0; mv->pos = 0; *flag_out = my_flag;
+  if (!other) return;
+  const uint16_t f1 = is_first_of_pair ? my_flag : other_flag;
+  const uint16_t f2 = is_first_of_pair ? other_flag : my_flag;
+  if (!((f1 & 64) && (f2 & 128))) return;              // has_mate (query.cpp:417-419)
+  if (!(me.n_rec && other->n_rec)) return;
+  if (other->has_best) { mv->has = 1; mv->si = other->best_si; mv->pos = other->best_pos; }
+  else {
+    *flag_out = (uint16_t)(my_flag | 8);
+    if (me.has_best) { mv->has = 1; mv->si = me.best_si; mv->pos = me.best_pos; }
+  }
+}
+
+// Columns 1-9 (up to and including the tab before SEQ).
+template <class S>
+HDN inline void put_head(S &s, const DevIndex &ix, const char *name, int name_len, uint16_t flag,
+                         bool unmapped, const Rec &r, int hi, const Item *items, const MateView &mv) {
+  s.put(name, name_len); s.ch('\t');
+  if (unmapped) {
+    put_u64(s, flag); s.ch('\t');
+    if (mv.has) { put_descr(s, ix, mv.si); s.ch('\t'); put_i64(s, mv.pos + 1); } else put_lit(s, "*\t0");
+    put_lit(s, "\t0\t*");
+  } else {
+    put_u64(s, (uint64_t)(flag | (r.rc ? 16 : 0) | (hi ? 256 : 0))); s.ch('\t');
+    put_descr(s, ix, r.si); s.ch('\t'); put_i64(s, r.pos + 1); put_lit(s, "\t50\t");
+    put_cigar(s, r, items);
+  }
+  if (mv.has) { s.ch('\t'); put_descr(s, ix, mv.si); s.ch('\t'); put_i64(s, mv.pos + 1); put_lit(s, "\t0\t"); }
+  else put_lit(s, "\t*\t0\t0\t");
+}
+// Everything after QUAL up to (not including) the optional fields / L,R tags / newline.
+template <class S>
+HDN inline void put_tags(S &s, const DevIndex &ix, bool unmapped, const Rec *recs, int hi, int n_rec,
+                         const Item *items) {
+  const Rec &r = recs[hi];
+  if (!unmapped) {
+    put_lit(s, "\tXM:i:"); put_u64(s, r.item_cnt);
+    put_lit(s, "\tXU:i:"); put_u64(s, r.xu);
+    put_lit(s, "\tXE:i:"); put_u64(s, r.xe);
+    put_lit(s, "\tXS:A:"); s.ch(r.rc ? '-' : '+');
+    put_lit(s, "\tNH:i:"); put_u64(s, (uint64_t)n_rec);
+    put_lit(s, "\tHI:i:"); put_u64(s, (uint64_t)hi);
+    if (hi > 0) {
+      const Rec &p = recs[hi - 1];
+      put_lit(s, "\tcc:Z:"); put_descr(s, ix, p.si);
+      put_lit(s, "\tcp:i:"); put_i64(s, p.pos + 1);
+      put_lit(s, "\txo:A:"); s.ch(p.rc == r.rc ? '=' : '!');
+      put_lit(s, "\txc:Z:"); put_cigar(s, p, items);
+    }
+    if (hi + 1 < n_rec) {
+      const Rec &x = recs[hi + 1];
+      put_lit(s, "\tCC:Z:"); put_descr(s, ix, x.si);
+      put_lit(s, "\tCP:i:"); put_i64(s, x.pos + 1);
+      put_lit(s, "\tXO:A:"); s.ch(x.rc == r.rc ? '=' : '!');
+      put_lit(s, "\tXC:Z:"); put_cigar(s, x, items);
+    }
+  } else {
+    put_lit(s, "\tXM:i:0\tNH:i:0");
+  }
+}
+// mappability_tag's appended tags (after the optional fields): \tL<u>:i:x\tR<u>:i:y for u < 10.
+template <class S>
+HDN inline bool put_lr_tags(S &s, const DevIndex &ix, const Rec &r, const Item *items) {
+  bool ok = true;
+  for (int u = 0; u < r.item_cnt; ++u) {
+    const Item it = items[r.item_begin + u];
+    int L, R;
+    const bool fine = map_lr(ix, r.si >> 1, r.pos, it.prefix, it.len, &L, &R);
+    if (u < 10) {
+      put_lit(s, "\tL"); s.ch((char)('0' + u)); put_lit(s, ":i:"); put_u64(s, (uint64_t)L);
+      put_lit(s, "\tR"); s.ch((char)('0' + u)); put_lit(s, ":i:"); put_u64(s, (uint64_t)R);
+    }
+    ok = ok && fine;
+  }
+  return ok;
+}
+
+// reverse_complement (fasta.cpp:26-61) for one character
+HD uint8_t comp_char(uint8_t c) {
+  switch (c) {
+    case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
+    case 'r': return 'y'; case 'y': return 'r'; case 'm': return 'k'; case 'k': return 'm';
+    case 'b': return 'v'; case 'd': return 'h'; case 'h': return 'd'; case 'v': return 'b';
+    case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
+    case 'R': return 'Y'; case 'Y': return 'R'; case 'M': return 'K'; case 'K': return 'M';
+    case 'B': return 'V'; case 'D': return 'H'; case 'H': return 'D'; case 'V': return 'B';
+    default: return c;
+  }
+}
+
+}  // namespace smash

@@ -1,0 +1,371 @@
+// tail.cu -- K7 smash_filter (smashMEM.py:84-92, 193-228 with argv "0 0 10000 4") and
+// K8 varbin_hist (varbin.py:34-93) on the GPU.
+//
+// Per batch (tail_accumulate): one thread per read pair applies the excess-mappability filter
+// and the read-2-near-read-1 window, and appends the pair's kept hits (tid,pos in HI order, r1
+// then r2) plus a 128-bit fingerprint of the dupe key to HBM-resident arrays.
+// At the end (tail_finish): first-wins duplicate removal through an open-addressing table keyed
+// by the fingerprint with an exact comparison of the hit lists, ordered compaction of the
+// surviving hits into the positions list (prefix scan => the reference's output order), the
+// chromosome filters, varbin's adjacent-duplicate rule and the bin histogram
+// (shared-memory privatised when the bins fit in one SM's shared memory).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "tail.cuh"
+
+namespace smash {
+
+static thread_local char t_err[512] = "";
+const char *tail_error() { return t_err; }
+static int tfail(int code, const char *fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(t_err, sizeof t_err, fmt, ap); va_end(ap);
+  return code;
+}
+#define TCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return tfail(SMASH_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+template <class T> int DGrow<T>::reserve(size_t n, size_t used, cudaStream_t st) {
+  if (n <= cap) return 0;
+  size_t want = cap * 2 > n ? cap * 2 : n + n / 8 + 1024;
+  T *np = nullptr;
+  cudaError_t e = cudaMalloc((void **)&np, want * sizeof(T));
+  if (e != cudaSuccess) return tfail(SMASH_ERR_NOMEM, "cudaMalloc(%zu): %s", want * sizeof(T), cudaGetErrorString(e));
+  if (p && used) {
+    TCU(cudaMemcpyAsync(np, p, used * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    TCU(cudaStreamSynchronize(st));
+  }
+  if (p) cudaFree(p);
+  p = np; cap = want;
+  return 0;
+}
+template struct DGrow<uint32_t>;
+template struct DGrow<uint64_t>;
+
+void tail_init(TailState *) {}
+void tail_reset(TailState *t) { t->n_pairs = 0; t->n_hits = 0; t->n_positions = 0; }
+void tail_release(TailState *t) {
+  t->pair_nhits.release(); t->pair_fp.release(); t->pair_hit_off.release(); t->hits.release();
+  void *d[] = {t->bin_starts, t->chrom_off, t->batch_cnt, t->batch_off, t->blk, t->counts, t->pos_chrom, t->pos_pos};
+  for (void *p : d) if (p) cudaFree(p);
+  if (t->h_pos_chrom) cudaFreeHost(t->h_pos_chrom);
+  if (t->h_pos_pos) cudaFreeHost(t->h_pos_pos);
+  *t = TailState();
+}
+
+int tail_configure(TailState *t, const int64_t *bin_starts, uint64_t n_bins, const int64_t *chrom_off,
+                   uint64_t n_chrom, int64_t hit_window, int32_t min_excess) {
+  if (t->bin_starts) cudaFree(t->bin_starts);
+  if (t->chrom_off) cudaFree(t->chrom_off);
+  if (t->counts) cudaFree(t->counts);
+  t->bin_starts = nullptr; t->chrom_off = nullptr; t->counts = nullptr;
+  TCU(cudaMalloc((void **)&t->bin_starts, 8 * n_bins));
+  TCU(cudaMalloc((void **)&t->chrom_off, 8 * (n_chrom + 1)));
+  TCU(cudaMalloc((void **)&t->counts, 8 * n_bins));
+  TCU(cudaMemcpy(t->bin_starts, bin_starts, 8 * n_bins, cudaMemcpyHostToDevice));
+  TCU(cudaMemcpy(t->chrom_off, chrom_off, 8 * n_chrom, cudaMemcpyHostToDevice));
+  t->n_bins = n_bins; t->n_chrom = n_chrom; t->hit_window = hit_window; t->min_excess = min_excess;
+  t->configured = true;
+  tail_reset(t);
+  return 0;
+}
+
+// ------------------------------------------------------------------ per batch
+
+struct PairParams { int64_t hit_window; int32_t min_excess; };
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ULL; x ^= x >> 27; x *= 0x94d049bb133111ebULL; x ^= x >> 31;
+  return x;
+}
+// smashMEM.py:84-92: mapped and qlen - max(L0,R0) >= minExcessMappability
+__device__ __forceinline__ bool rec_passes(const Rec &r, int32_t min_excess) {
+  const int mm = r.L0 > r.R0 ? r.L0 : r.R0;
+  return (int)r.qlen - mm >= min_excess;
+}
+// Visit the kept hits of pair (2p, 2p+1) in output order; f(tid, pos).
+template <class F>
+__device__ __forceinline__ void for_kept_hits(const BatchDev &b, const WorkDev &w, uint64_t p, const PairParams &pp, F f) {
+  const uint64_t ra = 2 * p, rb = 2 * p + 1;
+  const ReadSum sa = w.sums[ra];
+  const Rec *reca = w.rec_slots + ra * (uint64_t)w.cap;
+  const int na = sa.unmapped ? 0 : sa.n_rec;
+  for (int i = 0; i < na; ++i)
+    if (rec_passes(reca[i], pp.min_excess)) f((uint32_t)(reca[i].si >> 1), reca[i].pos);
+  if (rb >= b.n_reads) return;
+  const ReadSum sb = w.sums[rb];
+  const Rec *recb = w.rec_slots + rb * (uint64_t)w.cap;
+  const int nb = sb.unmapped ? 0 : sb.n_rec;
+  for (int j = 0; j < nb; ++j) {
+    if (!rec_passes(recb[j], pp.min_excess)) continue;
+    bool near = false;                                       // smashMEM.py:193-208
+    for (int i = 0; i < na && !near; ++i) {
+      if (!rec_passes(reca[i], pp.min_excess)) continue;
+      if (reca[i].si != recb[j].si) continue;
+      int64_t d = reca[i].pos - recb[j].pos; if (d < 0) d = -d;
+      near = d < pp.hit_window;
+    }
+    if (!near) f((uint32_t)(recb[j].si >> 1), recb[j].pos);
+  }
+}
+
+__global__ void k_pair_count(BatchDev b, WorkDev w, PairParams pp, uint64_t n_pairs, uint32_t *__restrict__ cnt) {
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t n = 0;
+    for_kept_hits(b, w, p, pp, [&](uint32_t, int64_t) { ++n; });
+    cnt[p] = n;
+  }
+}
+__global__ void k_pair_write(BatchDev b, WorkDev w, PairParams pp, uint64_t n_pairs, const uint64_t *__restrict__ off,
+                             uint64_t pair_base, uint64_t hit_base, uint32_t *__restrict__ pair_nhits,
+                             uint64_t *__restrict__ pair_fp, uint64_t *__restrict__ pair_hit_off, uint64_t *__restrict__ hits) {
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t o = hit_base + off[p];
+    const uint64_t o0 = o;
+    uint64_t h1 = 0x243f6a8885a308d3ULL, h2 = 0x13198a2e03707344ULL;
+    for_kept_hits(b, w, p, pp, [&](uint32_t tid, int64_t pos) {
+      const uint64_t v = ((uint64_t)tid << 40) | (uint64_t)pos;
+      hits[o++] = v;
+      h1 = mix64(h1 ^ v) + 0x9e3779b97f4a7c15ULL;
+      h2 = mix64((h2 + v) * 0xff51afd7ed558ccdULL) ^ (h2 >> 29);
+    });
+    pair_nhits[pair_base + p] = (uint32_t)(o - o0);
+    pair_hit_off[pair_base + p] = o0;
+    pair_fp[2 * (pair_base + p)] = h1; pair_fp[2 * (pair_base + p) + 1] = h2;
+  }
+}
+
+// exclusive scan helper lives in kernels.cu
+int exclusive_scan_u32_public(const uint32_t *in, uint64_t n, uint64_t *blk, uint64_t *out, cudaStream_t st);
+
+int tail_accumulate(TailState *t, const DevIndex &ix, const BatchDev &b, const WorkDev &w,
+                    uint64_t /*first_pair*/, cudaStream_t st, uint64_t *launches) {
+  if (!t->configured) return tfail(SMASH_ERR_STATE, "smash_tail_configure has not been called");
+  if (!ix.mapbody) return tfail(SMASH_ERR_STATE, "map.bin not loaded");
+  const uint64_t n_pairs = (b.n_reads + 1) / 2;
+  if (!n_pairs) return 0;
+  if (n_pairs + 2 > t->batch_cap) {
+    if (t->batch_cnt) cudaFree(t->batch_cnt);
+    if (t->batch_off) cudaFree(t->batch_off);
+    if (t->blk) cudaFree(t->blk);
+    t->batch_cap = n_pairs + n_pairs / 4 + 1024;
+    TCU(cudaMalloc((void **)&t->batch_cnt, 4 * t->batch_cap));
+    TCU(cudaMalloc((void **)&t->batch_off, 8 * (t->batch_cap + 1)));
+    TCU(cudaMalloc((void **)&t->blk, 8 * (t->batch_cap / 2048 + 8)));
+  }
+  PairParams pp{t->hit_window, t->min_excess};
+  const int grid = (int)((n_pairs + 255) / 256 < 148 * 8 ? (n_pairs + 255) / 256 : 148 * 8);
+  k_pair_count<<<grid, 256, 0, st>>>(b, w, pp, n_pairs, t->batch_cnt);
+  *launches += 1 + exclusive_scan_u32_public(t->batch_cnt, n_pairs, t->blk, t->batch_off, st);
+  uint64_t total = 0;
+  TCU(cudaMemcpyAsync(&total, t->batch_off + n_pairs, 8, cudaMemcpyDeviceToHost, st));
+  TCU(cudaStreamSynchronize(st));
+  int rc;
+  if ((rc = t->pair_nhits.reserve(t->n_pairs + n_pairs, t->n_pairs, st)) ||
+      (rc = t->pair_fp.reserve(2 * (t->n_pairs + n_pairs), 2 * t->n_pairs, st)) ||
+      (rc = t->pair_hit_off.reserve(t->n_pairs + n_pairs, t->n_pairs, st)) ||
+      (rc = t->hits.reserve(t->n_hits + total + 1, t->n_hits, st)))
+    return rc;
+  k_pair_write<<<grid, 256, 0, st>>>(b, w, pp, n_pairs, t->batch_off, t->n_pairs, t->n_hits, t->pair_nhits.p,
+                                     t->pair_fp.p, t->pair_hit_off.p, t->hits.p);
+  *launches += 1;
+  TCU(cudaGetLastError());
+  t->n_pairs += n_pairs; t->n_hits += total;
+  return 0;
+}
+
+// ------------------------------------------------------------------ finish
+
+constexpr uint64_t EMPTY_KEY = 0xffffffffffffffffULL;
+
+__global__ void k_dd_insert(const uint32_t *__restrict__ nhits, const uint64_t *__restrict__ fp, uint64_t n_pairs,
+                            uint64_t seed, uint64_t *keys, uint32_t *minidx, uint64_t mask, uint32_t *__restrict__ slot_of) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (!nhits[i]) continue;
+    uint64_t h = mix64(fp[2 * i] ^ mix64(fp[2 * i + 1] + seed));
+    if (h == EMPTY_KEY) h = 0;
+    uint64_t s = h & mask;
+    for (;;) {
+      const uint64_t prev = atomicCAS((unsigned long long *)&keys[s], (unsigned long long)EMPTY_KEY, (unsigned long long)h);
+      if (prev == EMPTY_KEY || prev == h) break;
+      s = (s + 1) & mask;
+    }
+    atomicMin(&minidx[s], (uint32_t)i);
+    slot_of[i] = (uint32_t)s;
+  }
+}
+// keep[i] = 1 first occurrence of its key, 0 empty or duplicate (smashMEM.py:217-228)
+__global__ void k_dd_resolve(const uint32_t *__restrict__ nhits, const uint64_t *__restrict__ hit_off,
+                             const uint64_t *__restrict__ hits, uint64_t n_pairs, const uint32_t *__restrict__ minidx,
+                             const uint32_t *__restrict__ slot_of, uint8_t *__restrict__ keep, uint64_t *stats /*[0]=dupes,[1]=nondupes,[2]=unresolved*/) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t n = nhits[i];
+    if (!n) { keep[i] = 0; continue; }
+    const uint32_t j = minidx[slot_of[i]];
+    if (j == (uint32_t)i) { keep[i] = 1; atomicAdd((unsigned long long *)&stats[1], 1ull); continue; }
+    bool same = nhits[j] == n;
+    for (uint32_t k = 0; same && k < n; ++k) same = hits[hit_off[j] + k] == hits[hit_off[i] + k];
+    if (same) { keep[i] = 0; atomicAdd((unsigned long long *)&stats[0], 1ull); }
+    else { keep[i] = 0; atomicAdd((unsigned long long *)&stats[2], 1ull); }
+  }
+}
+// per surviving pair: how many hits pass the regex (positions.txt) / varbin's chromosome filters
+__global__ void k_pair_out_count(const uint32_t *__restrict__ nhits, const uint64_t *__restrict__ hit_off,
+                                 const uint64_t *__restrict__ hits, const uint8_t *__restrict__ keep, uint64_t n_pairs,
+                                 const int64_t *__restrict__ chrom_off, uint32_t *__restrict__ c_pos, uint32_t *__restrict__ c_bin) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t a = 0, bct = 0;
+    if (keep[i]) {
+      for (uint32_t k = 0; k < nhits[i]; ++k) {
+        const int64_t o = chrom_off[hits[hit_off[i] + k] >> 40];
+        a += o != -1; bct += o >= 0;
+      }
+    }
+    c_pos[i] = a; c_bin[i] = bct;
+  }
+}
+__global__ void k_pair_out_write(const uint32_t *__restrict__ nhits, const uint64_t *__restrict__ hit_off,
+                                 const uint64_t *__restrict__ hits, const uint8_t *__restrict__ keep, uint64_t n_pairs,
+                                 const int64_t *__restrict__ chrom_off, const uint64_t *__restrict__ o_pos,
+                                 const uint64_t *__restrict__ o_bin, int32_t *__restrict__ pos_chrom, int64_t *__restrict__ pos_pos,
+                                 int64_t *__restrict__ f_pos, int64_t *__restrict__ f_abs) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (!keep[i]) continue;
+    uint64_t a = o_pos[i], bq = o_bin[i];
+    for (uint32_t k = 0; k < nhits[i]; ++k) {
+      const uint64_t v = hits[hit_off[i] + k];
+      const int64_t pos = (int64_t)(v & ((1ull << 40) - 1));
+      const int64_t o = chrom_off[v >> 40];
+      if (o != -1) { pos_chrom[a] = (int32_t)(v >> 40); pos_pos[a] = pos; ++a; }
+      if (o >= 0) { f_pos[bq] = pos; f_abs[bq] = pos + o; ++bq; }
+    }
+  }
+}
+
+__device__ __forceinline__ uint64_t bin_of(const int64_t *__restrict__ starts, uint64_t n_bins, int64_t abspos) {
+  uint64_t lo = 0, hi = n_bins;                              // bisect.bisect (right) - 1, varbin.py:89-92
+  while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (starts[mid] <= abspos) lo = mid + 1; else hi = mid; }
+  return lo ? lo - 1 : n_bins - 1;                           // python's counts[-1]
+}
+// varbin.py:56-58: a line whose position string equals the previous kept line's is a duplicate
+__global__ void k_varbin_global(const int64_t *__restrict__ f_pos, const int64_t *__restrict__ f_abs, uint64_t n,
+                                const int64_t *__restrict__ starts, uint64_t n_bins, unsigned long long *counts,
+                                unsigned long long *stats /*[3]=dups*/) {
+  unsigned long long dups = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (i && f_pos[i] == f_pos[i - 1]) { ++dups; continue; }
+    atomicAdd(&counts[bin_of(starts, n_bins, f_abs[i])], 1ull);
+  }
+  if (dups) atomicAdd(&stats[3], dups);
+}
+__global__ void k_varbin_smem(const int64_t *__restrict__ f_pos, const int64_t *__restrict__ f_abs, uint64_t n,
+                              const int64_t *__restrict__ starts, uint64_t n_bins, unsigned long long *counts,
+                              unsigned long long *stats) {
+  extern __shared__ uint32_t hist[];
+  for (uint64_t k = threadIdx.x; k < n_bins; k += blockDim.x) hist[k] = 0;
+  __syncthreads();
+  unsigned long long dups = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (i && f_pos[i] == f_pos[i - 1]) { ++dups; continue; }
+    atomicAdd(&hist[bin_of(starts, n_bins, f_abs[i])], 1u);
+  }
+  if (dups) atomicAdd(&stats[3], dups);
+  __syncthreads();
+  for (uint64_t k = threadIdx.x; k < n_bins; k += blockDim.x) if (hist[k]) atomicAdd(&counts[k], (unsigned long long)hist[k]);
+}
+
+int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smash_tail_stats *stats,
+                cudaStream_t st, uint64_t *launches) {
+  if (!t->configured) return tfail(SMASH_ERR_STATE, "smash_tail_configure has not been called");
+  const uint64_t P = t->n_pairs;
+  TCU(cudaMemsetAsync(t->counts, 0, 8 * t->n_bins, st));
+  smash_tail_stats s{};
+  uint64_t h_stats[4] = {0, 0, 0, 0};
+  uint64_t n_pos = 0, n_f = 0;
+  if (P) {
+    if (P >= 0xffffffffull) return tfail(SMASH_ERR_ARG, "too many pairs for one tail pass");
+    uint64_t tsize = 1024; while (tsize < 2 * P) tsize <<= 1;
+    uint64_t *keys = nullptr, *d_stats = nullptr, *o_pos = nullptr, *o_bin = nullptr, *blk = nullptr;
+    uint32_t *minidx = nullptr, *slot_of = nullptr, *c_pos = nullptr, *c_bin = nullptr; uint8_t *keep = nullptr;
+    int64_t *f_pos = nullptr, *f_abs = nullptr;
+    TCU(cudaMalloc((void **)&keys, 8 * tsize)); TCU(cudaMalloc((void **)&minidx, 4 * tsize));
+    TCU(cudaMalloc((void **)&slot_of, 4 * P)); TCU(cudaMalloc((void **)&keep, P)); TCU(cudaMalloc((void **)&d_stats, 32));
+    TCU(cudaMalloc((void **)&c_pos, 4 * P)); TCU(cudaMalloc((void **)&c_bin, 4 * P));
+    TCU(cudaMalloc((void **)&o_pos, 8 * (P + 1))); TCU(cudaMalloc((void **)&o_bin, 8 * (P + 1)));
+    TCU(cudaMalloc((void **)&blk, 8 * (P / 2048 + 8)));
+    const int grid = (int)((P + 255) / 256 < 148 * 8 ? (P + 255) / 256 : 148 * 8);
+    for (uint64_t seed = 1;; ++seed) {
+      TCU(cudaMemsetAsync(keys, 0xff, 8 * tsize, st)); TCU(cudaMemsetAsync(minidx, 0xff, 4 * tsize, st));
+      TCU(cudaMemsetAsync(d_stats, 0, 32, st));
+      k_dd_insert<<<grid, 256, 0, st>>>(t->pair_nhits.p, t->pair_fp.p, P, seed * 0x9e3779b97f4a7c15ULL, keys, minidx, tsize - 1, slot_of);
+      k_dd_resolve<<<grid, 256, 0, st>>>(t->pair_nhits.p, t->pair_hit_off.p, t->hits.p, P, minidx, slot_of, keep, d_stats);
+      *launches += 2;
+      TCU(cudaMemcpyAsync(h_stats, d_stats, 32, cudaMemcpyDeviceToHost, st));
+      TCU(cudaStreamSynchronize(st));
+      if (h_stats[2] == 0) break;                            // a 64-bit table-key collision: re-key
+      if (seed > 8) return tfail(SMASH_ERR_DATA, "duplicate-key table could not be resolved");
+    }
+    k_pair_out_count<<<grid, 256, 0, st>>>(t->pair_nhits.p, t->pair_hit_off.p, t->hits.p, keep, P, t->chrom_off, c_pos, c_bin);
+    *launches += 1 + exclusive_scan_u32_public(c_pos, P, blk, o_pos, st);
+    *launches += exclusive_scan_u32_public(c_bin, P, blk, o_bin, st);
+    TCU(cudaMemcpyAsync(&n_pos, o_pos + P, 8, cudaMemcpyDeviceToHost, st));
+    TCU(cudaMemcpyAsync(&n_f, o_bin + P, 8, cudaMemcpyDeviceToHost, st));
+    TCU(cudaStreamSynchronize(st));
+    if (n_pos + 1 > t->pos_cap) {
+      if (t->pos_chrom) cudaFree(t->pos_chrom);
+      if (t->pos_pos) cudaFree(t->pos_pos);
+      t->pos_cap = n_pos + 1024;
+      TCU(cudaMalloc((void **)&t->pos_chrom, 4 * t->pos_cap)); TCU(cudaMalloc((void **)&t->pos_pos, 8 * t->pos_cap));
+    }
+    TCU(cudaMalloc((void **)&f_pos, 8 * (n_f + 1))); TCU(cudaMalloc((void **)&f_abs, 8 * (n_f + 1)));
+    k_pair_out_write<<<grid, 256, 0, st>>>(t->pair_nhits.p, t->pair_hit_off.p, t->hits.p, keep, P, t->chrom_off, o_pos, o_bin,
+                                           t->pos_chrom, t->pos_pos, f_pos, f_abs);
+    *launches += 1;
+    if (n_f) {
+      const size_t smem = 4 * t->n_bins;
+      const int vgrid = (int)((n_f + 255) / 256 < 148 * 2 ? (n_f + 255) / 256 : 148 * 2);
+      if (smem <= 200 * 1024 && n_f >= 16 * t->n_bins) {
+        TCU(cudaFuncSetAttribute(k_varbin_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int g = vgrid < 148 ? vgrid : 148;
+        k_varbin_smem<<<g, 1024, smem, st>>>(f_pos, f_abs, n_f, t->bin_starts, t->n_bins, (unsigned long long *)t->counts, (unsigned long long *)d_stats);
+      } else {
+        k_varbin_global<<<vgrid, 256, 0, st>>>(f_pos, f_abs, n_f, t->bin_starts, t->n_bins, (unsigned long long *)t->counts, (unsigned long long *)d_stats);
+      }
+      *launches += 1;
+    }
+    TCU(cudaMemcpyAsync(h_stats, d_stats, 32, cudaMemcpyDeviceToHost, st));
+    TCU(cudaStreamSynchronize(st));
+    TCU(cudaGetLastError());
+    void *fr[] = {keys, minidx, slot_of, keep, d_stats, c_pos, c_bin, o_pos, o_bin, blk, f_pos, f_abs};
+    for (void *p : fr) cudaFree(p);
+  }
+  t->n_positions = n_pos;
+  s.n_dupe_pairs = h_stats[0]; s.n_non_dupe_pairs = h_stats[1];
+  s.n_positions = n_pos; s.total_reads = n_f; s.dups_removed = h_stats[3]; s.reads_kept = n_f - h_stats[3];
+  if (counts_device) TCU(cudaMemcpyAsync(counts_device, t->counts, 8 * t->n_bins, cudaMemcpyDeviceToDevice, st));
+  if (counts_host) TCU(cudaMemcpyAsync(counts_host, t->counts, 8 * t->n_bins, cudaMemcpyDeviceToHost, st));
+  TCU(cudaStreamSynchronize(st));
+  if (stats) *stats = s;
+  return 0;
+}
+
+int tail_positions(TailState *t, const int32_t **chrom, const int64_t **pos, uint64_t *n) {
+  const uint64_t m = t->n_positions;
+  if (m + 1 > t->h_pos_cap) {
+    if (t->h_pos_chrom) cudaFreeHost(t->h_pos_chrom);
+    if (t->h_pos_pos) cudaFreeHost(t->h_pos_pos);
+    t->h_pos_cap = m + 1024;
+    TCU(cudaHostAlloc((void **)&t->h_pos_chrom, 4 * t->h_pos_cap, cudaHostAllocDefault));
+    TCU(cudaHostAlloc((void **)&t->h_pos_pos, 8 * t->h_pos_cap, cudaHostAllocDefault));
+  }
+  if (m) {
+    TCU(cudaMemcpy(t->h_pos_chrom, t->pos_chrom, 4 * m, cudaMemcpyDeviceToHost));
+    TCU(cudaMemcpy(t->h_pos_pos, t->pos_pos, 8 * m, cudaMemcpyDeviceToHost));
+  }
+  *chrom = t->h_pos_chrom; *pos = t->h_pos_pos; *n = m;
+  return 0;
+}
+
+}  // namespace smash

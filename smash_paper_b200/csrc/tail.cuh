@@ -1,0 +1,47 @@
+// tail.cuh -- device state of the smashMEM.py filter + varbin.py counting (K7/K8).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/smash_b200.h"
+#include "kernels.cuh"
+
+namespace smash {
+
+template <class T> struct DGrow {       // growable device array that keeps its contents
+  T *p = nullptr; size_t cap = 0;
+  int reserve(size_t n, size_t used, cudaStream_t st);
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct TailState {
+  bool configured = false;
+  // configuration
+  int64_t *bin_starts = nullptr; uint64_t n_bins = 0;
+  int64_t *chrom_off = nullptr; uint64_t n_chrom = 0;   // >=0 abs offset, -1 filtered by the regex, -2 by varbin
+  int64_t hit_window = 10000; int32_t min_excess = 4;
+  // accumulated over batches (pair index = order of submission)
+  uint64_t n_pairs = 0, n_hits = 0;
+  DGrow<uint32_t> pair_nhits;       // kept hits of the pair (0 => pair never reaches the dupe set)
+  DGrow<uint64_t> pair_fp;          // 2 per pair: 128-bit fingerprint of the dupe key
+  DGrow<uint64_t> pair_hit_off;     // first hit of the pair in `hits`
+  DGrow<uint64_t> hits;             // tid << 40 | 0-based pos, r1 hits in HI order then r2 hits
+  // scratch
+  uint32_t *batch_cnt = nullptr; uint64_t *batch_off = nullptr; uint64_t *blk = nullptr; size_t batch_cap = 0;
+  // results of finish
+  int64_t *counts = nullptr;        // n_bins
+  int32_t *pos_chrom = nullptr; int64_t *pos_pos = nullptr; uint64_t n_positions = 0; size_t pos_cap = 0;
+  int32_t *h_pos_chrom = nullptr; int64_t *h_pos_pos = nullptr; size_t h_pos_cap = 0;
+};
+
+void tail_init(TailState *t);
+void tail_release(TailState *t);
+void tail_reset(TailState *t);
+const char *tail_error();
+int tail_configure(TailState *t, const int64_t *bin_starts, uint64_t n_bins, const int64_t *chrom_off,
+                   uint64_t n_chrom, int64_t hit_window, int32_t min_excess);
+int tail_accumulate(TailState *t, const DevIndex &ix, const BatchDev &b, const WorkDev &w,
+                    uint64_t first_pair, cudaStream_t st, uint64_t *launches);
+int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smash_tail_stats *stats,
+                cudaStream_t st, uint64_t *launches);
+int tail_positions(TailState *t, const int32_t **chrom, const int64_t **pos, uint64_t *n);
+
+}  // namespace smash
