@@ -74,6 +74,18 @@ typedef struct {
 void smash_params_default(smash_params *p);
 
 int smash_ctx_create(const smash_index *ix, const smash_params *p, smash_ctx **out);
+/* Same context, but the index is BUILT on the GPU from the text (replaces the longSA build branch,
+ * longSA.cpp:137-176: qsufsort + Kasai) and stays in HBM.  text = Sequence layout (fasta.cpp:151-203).
+ * keep_isa: keep the inverse suffix array resident (needed for MEM mode, mappability, saving).
+ * chunk_cap: suffixes sorted per pass (0 = default), bounds the builder's scratch memory. */
+int smash_ctx_create_from_text(const uint8_t *text, uint64_t N, uint64_t n_descr, const uint64_t *startpos,
+                               const uint64_t *sizes, const char *const *descr, int rcref, int w,
+                               int keep_isa, uint64_t chunk_cap, const smash_params *p, smash_ctx **out);
+/* Copy the index arrays out of HBM (any pointer may be NULL); lcp_m gets n_m .lcp.m.bin items. */
+int smash_ctx_copy_index(smash_ctx *ctx, void *sa, void *isa, uint8_t *lcp_vec, void *lcp_m, uint64_t *n_m);
+/* Write <ref_fasta>.bin/rc{r}.* (and map.bin) in the reference's formats (fasta.cpp:215-236,
+ * longSA.cpp:179-190): what `mummer -rcref <fa> dummy` leaves behind (index_setup.sh:19,22). */
+int smash_ctx_save_index(smash_ctx *ctx, const char *ref_fasta, int with_mappability);
 void smash_ctx_destroy(smash_ctx *ctx);
 /* map.bin (longSA::show_mappability output, longSA.cpp:612-690; 2 junk bytes + 2 bytes/base) for
  * the L/R tags and the smashMEM excess-mappability filter.  body = file contents after the two

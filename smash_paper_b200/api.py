@@ -188,6 +188,48 @@ class Context:
         _check(L.smash_ctx_create(index.h, C.byref(p), C.byref(self.h)))
         self._inflight = {}
 
+    @classmethod
+    def from_text(cls, text, startpos, sizes, descr, rcref=True, w=None, keep_isa=True, chunk_cap=0,
+                  device=0, mode=MODE_MAM, min_len=20, nomap=True, nucleotides_only=False,
+                  tag_mappability=False, seed_k=0):
+        """Build the index ON THE GPU from the Sequence text (longSA build branch) and keep it in HBM."""
+        L = load_library()
+        if L.smash_device_count() <= 0:
+            raise SmashError("no sm_100 CUDA device: libsmash_b200 has no CPU fallback")
+        p = _Params()
+        L.smash_params_default(C.byref(p))
+        p.device, p.mode, p.min_len, p.nomap = device, mode, min_len, int(nomap)
+        p.nucleotides_only, p.tag_mappability, p.seed_k = int(nucleotides_only), int(tag_mappability), seed_k
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        sp = np.ascontiguousarray(startpos, dtype=np.uint64)
+        sz = np.ascontiguousarray(sizes, dtype=np.uint64)
+        d = (C.c_char_p * len(descr))(*[x.encode() for x in descr])
+        if w is None:
+            w = 4 if len(text) < 0xFFFFFFFF - 100000 else 8          # mummer.cpp:156-183
+        self = cls.__new__(cls)
+        self.h = C.c_void_p()
+        self.index = None
+        self._inflight = {}
+        self.N, self.w, self.sizes = len(text), w, sz
+        _check(L.smash_ctx_create_from_text(_ptr(text), C.c_uint64(len(text)), C.c_uint64(len(descr)), _ptr(sp),
+                                            _ptr(sz), d, int(bool(rcref)), int(w), int(bool(keep_isa)),
+                                            C.c_uint64(chunk_cap), C.byref(p), C.byref(self.h)))
+        return self
+
+    def copy_index(self, N, w, want_isa=True):
+        dt = np.uint32 if w == 4 else np.uint64
+        sa = np.empty(N, dtype=dt)
+        isa = np.empty(N, dtype=dt) if want_isa else None
+        vec = np.empty(N, dtype=np.uint8)
+        nm = C.c_uint64()
+        _check(load_library().smash_ctx_copy_index(self.h, _ptr(sa), _ptr(isa) if want_isa else None, _ptr(vec), None, C.byref(nm)))
+        m = np.zeros(16 * max(nm.value, 1), dtype=np.uint8)
+        _check(load_library().smash_ctx_copy_index(self.h, None, None, None, _ptr(m), None))
+        return sa, isa, vec, m[:16 * nm.value]
+
+    def save_index(self, fasta, with_mappability=False):
+        _check(load_library().smash_ctx_save_index(self.h, str(fasta).encode(), int(with_mappability)))
+
     def close(self):
         if self.h:
             load_library().smash_ctx_destroy(self.h)

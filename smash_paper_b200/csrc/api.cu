@@ -18,6 +18,7 @@
 #include "../../include/smash_b200.h"
 #include "kernels.cuh"
 #include "tail.cuh"
+#include "sabuild.cuh"
 
 using namespace smash;
 
@@ -228,6 +229,8 @@ struct smash_ctx {
   LcpItem *lcp_m = nullptr; uint8_t *uniq = nullptr; void *seed = nullptr; uint64_t *startpos = nullptr;
   uint64_t *sizes = nullptr; char *descr = nullptr; int *descr_off = nullptr; uint32_t *alpha = nullptr;
   uint8_t *mapbody = nullptr; uint32_t *chrom_off32 = nullptr;
+  uint64_t n_m = 0;
+  smash_index *own_index = nullptr;
   uint64_t index_bytes = 0;
   uint64_t launches = 0;
   Slot slot[SMASH_N_SLOTS];
@@ -267,46 +270,28 @@ static void set_search_params(smash_ctx *c) {
   sp.fast_ok = expect <= 16.0;
 }
 
-extern "C" int smash_ctx_create(const smash_index *ix, const smash_params *p, smash_ctx **out) {
-  if (!ix || !p || !out) return fail(SMASH_ERR_ARG, "null argument");
-  if (smash_device_count() <= 0) return fail(SMASH_ERR_CUDA, "no sm_100 CUDA device available (this library has no CPU fallback)");
-  if (p->mode != SMASH_MODE_MAM && p->mode != SMASH_MODE_MEM) return fail(SMASH_ERR_ARG, "mode %d not supported (MAM or MEM)", p->mode);
-  if (p->mode == SMASH_MODE_MEM && !ix->isa) return fail(SMASH_ERR_ARG, "MEM mode needs the .isa.bin array");
-  CU(cudaSetDevice(p->device));
-  smash_ctx *c = new smash_ctx();
-  c->hix = ix; c->prm = *p; c->device = p->device;
-  const uint64_t N = ix->N; const int w = ix->w;
-  int rc = 0;
-  cudaStream_t st = nullptr;
 #define CK(x) do { if ((rc = (x))) { smash_ctx_destroy(c); return rc; } } while (0)
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { smash_ctx_destroy(c); return fail(SMASH_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
+
+static int ctx_begin(const smash_params *p, smash_ctx **out) {
+  if (smash_device_count() <= 0) return fail(SMASH_ERR_CUDA, "no sm_100 CUDA device available (this library has no CPU fallback)");
+  if (p->mode != SMASH_MODE_MAM && p->mode != SMASH_MODE_MEM) return fail(SMASH_ERR_ARG, "mode %d not supported (MAM or MEM)", p->mode);
+  CU(cudaSetDevice(p->device));
+  smash_ctx *c = new smash_ctx();
+  c->prm = *p; c->device = p->device;
   for (int s = 0; s < SMASH_N_SLOTS; ++s) {
     CUC(cudaStreamCreateWithFlags(&c->slot[s].st, cudaStreamNonBlocking));
     CUC(cudaEventCreate(&c->slot[s].ev0)); CUC(cudaEventCreate(&c->slot[s].ev1));
   }
-  st = c->slot[0].st;
-  CK(dmalloc((void **)&c->text_alloc, N + 2 * TEXT_PAD, &c->index_bytes));
-  CUC(cudaMemsetAsync(c->text_alloc, 0, N + 2 * TEXT_PAD, st));
-  CUC(cudaMemcpyAsync(c->text_alloc + TEXT_PAD, ix->text, N, cudaMemcpyHostToDevice, st));
-  CK(dmalloc(&c->sa, N * w, &c->index_bytes));
-  CUC(cudaMemcpyAsync(c->sa, ix->sa, N * w, cudaMemcpyHostToDevice, st));
-  if (ix->isa && (p->mode == SMASH_MODE_MEM)) {
-    CK(dmalloc(&c->isa, N * w, &c->index_bytes));
-    CUC(cudaMemcpyAsync(c->isa, ix->isa, N * w, cudaMemcpyHostToDevice, st));
-  }
-  CK(dmalloc((void **)&c->lcp, N, &c->index_bytes));
-  CUC(cudaMemcpyAsync(c->lcp, ix->lcp, N, cudaMemcpyHostToDevice, st));
-  {
-    // .lcp.m.bin items are {u64 idx; ANINT val; pad}: widen val so the device sees one layout
-    std::vector<LcpItem> m(ix->n_m);
-    for (uint64_t i = 0; i < ix->n_m; ++i) {
-      const uint8_t *r = ix->lcp_m_raw + 16 * i;
-      memcpy(&m[i].idx, r, 8);
-      if (w == 4) { uint32_t v; memcpy(&v, r + 8, 4); m[i].val = v; } else memcpy(&m[i].val, r + 8, 8);
-    }
-    CK(dmalloc((void **)&c->lcp_m, sizeof(LcpItem) * (ix->n_m + 1), &c->index_bytes));
-    if (ix->n_m) CUC(cudaMemcpy(c->lcp_m, m.data(), sizeof(LcpItem) * ix->n_m, cudaMemcpyHostToDevice));
-  }
+  *out = c;
+  return 0;
+}
+
+// metadata + derived structures once text/sa/(isa)/lcp/lcp_m are in HBM
+static int ctx_finish(smash_ctx *c, const smash_index *ix) {
+  int rc = 0;
+  cudaStream_t st = c->slot[0].st;
+  const uint64_t N = ix->N;
   const int nd = (int)ix->descr.size();
   CK(dmalloc((void **)&c->startpos, 8 * nd, &c->index_bytes));
   CK(dmalloc((void **)&c->sizes, 8 * nd, &c->index_bytes));
@@ -329,8 +314,8 @@ extern "C" int smash_ctx_create(const smash_index *ix, const smash_params *p, sm
   }
   CK(dmalloc((void **)&c->alpha, 32, nullptr));
   DevIndex &d = c->dix;
-  d.text = c->text_alloc + TEXT_PAD; d.N = N; d.sa = c->sa; d.isa = c->isa; d.w = w; d.lcp = c->lcp;
-  d.lcp_m = c->lcp_m; d.n_m = ix->n_m; d.startpos = c->startpos; d.sizes = c->sizes; d.n_descr = nd;
+  d.text = c->text_alloc + TEXT_PAD; d.N = N; d.sa = c->sa; d.isa = c->isa; d.w = ix->w; d.lcp = c->lcp;
+  d.lcp_m = c->lcp_m; d.n_m = c->n_m; d.startpos = c->startpos; d.sizes = c->sizes; d.n_descr = nd;
   d.rcref = ix->rcref; d.descr = c->descr; d.descr_off = c->descr_off;
   d.logN = (uint64_t)ceil(log((double)N) / log(2.0));          // longSA.cpp:97
   d.mapbody = nullptr; d.map_bytes = 0; d.chrom_off32 = c->chrom_off32;
@@ -340,7 +325,7 @@ extern "C" int smash_ctx_create(const smash_index *ix, const smash_params *p, sm
   CK(dmalloc((void **)&c->uniq, N, &c->index_bytes));
   c->launches += launch_uniq_build(d, c->uniq, st);
   d.uniq = c->uniq;
-  int k = p->seed_k;
+  int k = c->prm.seed_k;
   if (k <= 0) { k = (int)ceil(log((double)N) / log(4.0)) + 1; }
   if (k > 16) k = 16;
   if (k < 4) k = 4;
@@ -352,9 +337,171 @@ extern "C" int smash_ctx_create(const smash_index *ix, const smash_params *p, sm
   CUC(cudaGetLastError());
   set_search_params(c);
   tail_init(&c->tail);
+  return 0;
+}
+
+extern "C" int smash_ctx_create(const smash_index *ix, const smash_params *p, smash_ctx **out) {
+  if (!ix || !p || !out) return fail(SMASH_ERR_ARG, "null argument");
+  if (!ix->text || !ix->sa) return fail(SMASH_ERR_ARG, "index has no host arrays");
+  if (p->mode == SMASH_MODE_MEM && !ix->isa) return fail(SMASH_ERR_ARG, "MEM mode needs the .isa.bin array");
+  smash_ctx *c = nullptr;
+  int rc = ctx_begin(p, &c);
+  if (rc) return rc;
+  c->hix = ix;
+  const uint64_t N = ix->N; const int w = ix->w;
+  cudaStream_t st = c->slot[0].st;
+  CK(dmalloc((void **)&c->text_alloc, N + 2 * TEXT_PAD, &c->index_bytes));
+  CUC(cudaMemsetAsync(c->text_alloc, 0, N + 2 * TEXT_PAD, st));
+  CUC(cudaMemcpyAsync(c->text_alloc + TEXT_PAD, ix->text, N, cudaMemcpyHostToDevice, st));
+  CK(dmalloc(&c->sa, N * w, &c->index_bytes));
+  CUC(cudaMemcpyAsync(c->sa, ix->sa, N * w, cudaMemcpyHostToDevice, st));
+  if (ix->isa && (p->mode == SMASH_MODE_MEM)) {
+    CK(dmalloc(&c->isa, N * w, &c->index_bytes));
+    CUC(cudaMemcpyAsync(c->isa, ix->isa, N * w, cudaMemcpyHostToDevice, st));
+  }
+  CK(dmalloc((void **)&c->lcp, N, &c->index_bytes));
+  CUC(cudaMemcpyAsync(c->lcp, ix->lcp, N, cudaMemcpyHostToDevice, st));
+  {
+    // .lcp.m.bin items are {u64 idx; ANINT val; pad}: widen val so the device sees one layout
+    std::vector<LcpItem> m(ix->n_m);
+    for (uint64_t i = 0; i < ix->n_m; ++i) {
+      const uint8_t *r = ix->lcp_m_raw + 16 * i;
+      memcpy(&m[i].idx, r, 8);
+      if (w == 4) { uint32_t v; memcpy(&v, r + 8, 4); m[i].val = v; } else memcpy(&m[i].val, r + 8, 8);
+    }
+    CK(dmalloc((void **)&c->lcp_m, sizeof(LcpItem) * (ix->n_m + 1), &c->index_bytes));
+    if (ix->n_m) CUC(cudaMemcpy(c->lcp_m, m.data(), sizeof(LcpItem) * ix->n_m, cudaMemcpyHostToDevice));
+    c->n_m = ix->n_m;
+  }
+  if ((rc = ctx_finish(c, ix))) return rc;
+  *out = c;
+  return 0;
+}
+
+// Index construction on the GPU (replaces the longSA build branch, longSA.cpp:137-176): the text
+// is uploaded, SA/ISA/LCP are built in HBM and stay there; nothing is copied back unless
+// smash_ctx_save_index / smash_ctx_copy_index is called.
+extern "C" int smash_ctx_create_from_text(const uint8_t *text, uint64_t N, uint64_t n_descr, const uint64_t *startpos,
+                                          const uint64_t *sizes, const char *const *descr, int rcref, int w,
+                                          int keep_isa, uint64_t chunk_cap, const smash_params *p, smash_ctx **out) {
+  if (!text || !N || !n_descr || !startpos || !sizes || !descr || !p || !out || (w != 4 && w != 8))
+    return fail(SMASH_ERR_ARG, "bad argument");
+  if (w == 4 && N >= 0xffffffffull) return fail(SMASH_ERR_ARG, "text too long for 4-byte index integers");
+  smash_ctx *c = nullptr;
+  int rc = ctx_begin(p, &c);
+  if (rc) return rc;
+  smash_index *ix = new smash_index();
+  ix->N = N; ix->w = w; ix->rcref = rcref ? 1 : 0;
+  for (uint64_t i = 0; i < n_descr; ++i) { ix->startpos.push_back(startpos[i]); ix->sizes.push_back(sizes[i]); ix->descr.push_back(descr[i]); }
+  c->hix = ix; c->own_index = ix;
+  cudaStream_t st = c->slot[0].st;
+  CK(dmalloc((void **)&c->text_alloc, N + 2 * TEXT_PAD, &c->index_bytes));
+  CUC(cudaMemsetAsync(c->text_alloc, 0, N + 2 * TEXT_PAD, st));
+  CUC(cudaMemcpyAsync(c->text_alloc + TEXT_PAD, text, N, cudaMemcpyHostToDevice, st));
+  CK(dmalloc(&c->sa, N * w, &c->index_bytes));
+  if (keep_isa || p->mode == SMASH_MODE_MEM) CK(dmalloc(&c->isa, N * w, &c->index_bytes));
+  CK(dmalloc((void **)&c->lcp, N, &c->index_bytes));
+  char err[256] = "";
+  rc = build_index_device(c->text_alloc + TEXT_PAD, N, w, c->sa, c->isa, c->lcp, &c->lcp_m, &c->n_m, chunk_cap, st, err, &c->launches);
+  if (rc) { smash_ctx_destroy(c); return fail(rc == -3 ? SMASH_ERR_CUDA : SMASH_ERR_DATA, "index build: %s", err); }
+  c->index_bytes += sizeof(LcpItem) * (c->n_m + 1);
+  if ((rc = ctx_finish(c, ix))) return rc;
+  *out = c;
+  return 0;
+}
 #undef CK
 #undef CUC
-  *out = c;
+
+// Copy the index arrays from HBM to caller buffers (any pointer may be NULL).  lcp_m receives
+// n_m 16-byte items in the .lcp.m.bin layout {u64 idx; ANINT val; zero pad}.
+extern "C" int smash_ctx_copy_index(smash_ctx *c, void *sa, void *isa, uint8_t *lcp_vec, void *lcp_m, uint64_t *n_m) {
+  if (!c) return fail(SMASH_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  const uint64_t N = c->dix.N; const int w = c->dix.w;
+  if (sa) CU(cudaMemcpy(sa, c->sa, N * w, cudaMemcpyDeviceToHost));
+  if (isa) { if (!c->isa) return fail(SMASH_ERR_STATE, "ISA is not resident"); CU(cudaMemcpy(isa, c->isa, N * w, cudaMemcpyDeviceToHost)); }
+  if (lcp_vec) CU(cudaMemcpy(lcp_vec, c->lcp, N, cudaMemcpyDeviceToHost));
+  if (n_m) *n_m = c->n_m;
+  if (lcp_m && c->n_m) {
+    std::vector<LcpItem> m(c->n_m);
+    CU(cudaMemcpy(m.data(), c->lcp_m, sizeof(LcpItem) * c->n_m, cudaMemcpyDeviceToHost));
+    uint8_t *o = (uint8_t *)lcp_m;
+    for (uint64_t i = 0; i < c->n_m; ++i) {
+      memset(o + 16 * i, 0, 16); memcpy(o + 16 * i, &m[i].idx, 8);
+      if (w == 4) { uint32_t v = (uint32_t)m[i].val; memcpy(o + 16 * i + 8, &v, 4); } else memcpy(o + 16 * i + 8, &m[i].val, 8);
+    }
+  }
+  return 0;
+}
+
+static int write_file(const std::string &path, const void *p, size_t n) {
+  FILE *f = fopen(path.c_str(), "wb");
+  if (!f) return fail(SMASH_ERR_IO, "could not open output %s for writing", path.c_str());
+  const bool ok = n == 0 || fwrite(p, 1, n, f) == n;
+  if (fclose(f) != 0 || !ok) return fail(SMASH_ERR_IO, "problem writing %zu bytes at %s", n, path.c_str());
+  return 0;
+}
+static int write_device_file(const std::string &path, const void *dptr, size_t n) {
+  FILE *f = fopen(path.c_str(), "wb");
+  if (!f) return fail(SMASH_ERR_IO, "could not open output %s for writing", path.c_str());
+  const size_t CH = 256u << 20;
+  void *h = nullptr;
+  if (cudaHostAlloc(&h, CH, cudaHostAllocDefault) != cudaSuccess) { fclose(f); return fail(SMASH_ERR_NOMEM, "cudaHostAlloc"); }
+  int rc = 0;
+  for (size_t o = 0; o < n && !rc; o += CH) {
+    const size_t m = n - o < CH ? n - o : CH;
+    if (cudaMemcpy(h, (const uint8_t *)dptr + o, m, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(SMASH_ERR_CUDA, "D2H copy failed");
+    else if (fwrite(h, 1, m, f) != m) rc = fail(SMASH_ERR_IO, "problem writing %s", path.c_str());
+  }
+  cudaFreeHost(h);
+  if (fclose(f) != 0 && !rc) rc = fail(SMASH_ERR_IO, "problem closing %s", path.c_str());
+  return rc;
+}
+// Write <fa>.bin/rc{r}.* exactly as the reference's build branch does (fasta.cpp:215-236,
+// longSA.cpp:179-190) from the arrays in HBM.  Needs ISA resident.
+extern "C" int smash_ctx_save_index(smash_ctx *c, const char *ref_fasta, int with_mappability) {
+  if (!c || !ref_fasta) return fail(SMASH_ERR_ARG, "null argument");
+  if (!c->isa) return fail(SMASH_ERR_STATE, "ISA is not resident (create the context with keep_isa)");
+  CU(cudaSetDevice(c->device));
+  struct stat st;
+  if (stat(ref_fasta, &st) != 0) return fail(SMASH_ERR_IO, "unable to open %s", ref_fasta);
+  const uint64_t fasta_size = (uint64_t)st.st_size;
+  const smash_index *ix = c->hix;
+  const std::string dir = std::string(ref_fasta) + ".bin";
+  mkdir(dir.c_str(), 0755);
+  const std::string base = dir + "/rc" + (ix->rcref ? "1" : "0");
+  std::string ref;
+  auto put64 = [&](uint64_t v) { ref.append((const char *)&v, 8); };
+  put64(fasta_size); put64(ix->N); put64(ix->descr.size());
+  uint64_t maxd = 0;
+  for (size_t i = 0; i < ix->descr.size(); ++i) {
+    put64(ix->startpos[i]); put64(ix->sizes[i]); put64(ix->descr[i].size()); ref += ix->descr[i];
+    if (ix->descr[i].size() > maxd) maxd = ix->descr[i].size();
+  }
+  put64(maxd);
+  int rc;
+  if ((rc = write_file(base + ".ref.bin", ref.data(), ref.size()))) return rc;
+  if ((rc = write_device_file(base + ".ref.seq.bin", c->text_alloc + TEXT_PAD, ix->N))) return rc;
+  const std::string ib = base + ".i" + std::to_string(ix->w) + ".index";
+  const uint64_t hdr[6] = {fasta_size, c->dix.logN, ix->N - 1, ix->N, ix->N, c->n_m};
+  if ((rc = write_file(ib + ".bin", hdr, 48))) return rc;
+  if ((rc = write_device_file(ib + ".sa.bin", c->sa, ix->N * ix->w))) return rc;
+  if ((rc = write_device_file(ib + ".isa.bin", c->isa, ix->N * ix->w))) return rc;
+  if ((rc = write_device_file(ib + ".lcp.vec.bin", c->lcp, ix->N))) return rc;
+  std::vector<uint8_t> m(16 * c->n_m);
+  if ((rc = smash_ctx_copy_index(c, nullptr, nullptr, nullptr, m.data(), nullptr))) return rc;
+  if ((rc = write_file(ib + ".lcp.m.bin", m.data(), m.size()))) return rc;
+  if (with_mappability) {
+    if (!c->mapbody) return fail(SMASH_ERR_STATE, "mappability has not been built");
+    FILE *f = fopen((dir + "/map.bin").c_str(), "wb");
+    if (!f) return fail(SMASH_ERR_IO, "could not open outfile %s/map.bin for writing", dir.c_str());
+    fputc(0, f); fputc(0, f); fclose(f);          // the reference writes two junk bytes first (longSA.cpp:606-617)
+    std::vector<uint8_t> body(c->dix.map_bytes);
+    CU(cudaMemcpy(body.data(), c->mapbody, body.size(), cudaMemcpyDeviceToHost));
+    f = fopen((dir + "/map.bin").c_str(), "ab");
+    if (!f || fwrite(body.data(), 1, body.size(), f) != body.size()) { if (f) fclose(f); return fail(SMASH_ERR_IO, "problem writing map.bin"); }
+    fclose(f);
+  }
   return 0;
 }
 
@@ -379,6 +526,7 @@ extern "C" void smash_ctx_destroy(smash_ctx *c) {
   void *ptrs[] = {c->text_alloc, c->sa, c->isa, c->lcp, c->lcp_m, c->uniq, c->seed, c->startpos, c->sizes,
                   c->descr, c->descr_off, c->alpha, c->mapbody, c->chrom_off32};
   for (void *p : ptrs) if (p) cudaFree(p);
+  if (c->own_index) delete c->own_index;
   delete c;
 }
 
@@ -395,7 +543,7 @@ extern "C" int smash_ctx_load_mappability(smash_ctx *c, const uint8_t *body, uin
 
 extern "C" int smash_ctx_build_mappability(smash_ctx *c, uint8_t *body, uint64_t cap) {
   if (!c) return fail(SMASH_ERR_ARG, "null argument");
-  if (!c->hix->isa) return fail(SMASH_ERR_STATE, "mappability needs the .isa.bin array");
+  if (!c->hix->isa && !c->isa) return fail(SMASH_ERR_STATE, "mappability needs the .isa.bin array");
   if (!c->hix->rcref) return fail(SMASH_ERR_ARG, "-mappability requires -rcref");   // mummer.cpp:145
   CU(cudaSetDevice(c->device));
   cudaStream_t st = c->slot[0].st;

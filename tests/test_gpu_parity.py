@@ -107,3 +107,86 @@ def test_double_buffered_submit(case, gpu):
     ctx.submit(0, case["reads"]); ctx.submit(1, case["reads"])
     a = ctx.wait(0); b = ctx.wait(1)
     assert a.sam == sam and b.sam == sam
+
+
+def _lcpm_raw(oix):
+    raw = np.zeros((len(oix.lcp_m), 16), dtype=np.uint8)
+    if len(oix.lcp_m):
+        raw[:, :8] = oix.lcp_m["idx"].astype("<u8").view(np.uint8).reshape(-1, 8)
+        raw[:, 8:] = oix.lcp_m["val"].astype("<u8").view(np.uint8).reshape(-1, 8)
+        if oix.w == 4:
+            raw[:, 12:] = 0
+    return raw.reshape(-1)
+
+
+@pytest.mark.parametrize("chunk_cap", [0, 30000])
+def test_gpu_index_build_matches_canonical_arrays(case, chunk_cap):
+    """SA/ISA/LCP built on the GPU == the arrays of the index files (canonical functions of the text)."""
+    from smash_paper_b200 import api
+    oix = case["oix"]
+    ctx = api.Context.from_text(oix.text, oix.startpos, oix.sizes, oix.descr, w=4, chunk_cap=chunk_cap)
+    try:
+        sa, isa, vec, m = ctx.copy_index(oix.N, 4)
+        assert np.array_equal(sa, oix.sa)
+        assert np.array_equal(isa, oix.isa)
+        assert np.array_equal(vec, oix.lcp_vec)
+        assert np.array_equal(m, _lcpm_raw(oix))
+        assert ctx.map_batch(case["reads"]).sam == oix.map_batch(case["reads"], min_len=20, n_threads=4)
+    finally:
+        ctx.close()
+
+
+def test_gpu_index_files_equal_reference_files(case, workdir):
+    """smash_ctx_save_index writes byte-identical <fa>.bin/ files (incl. map.bin body)."""
+    import filecmp, shutil
+    from smash_paper_b200 import api
+    oix = case["oix"]
+    d = os.path.join(workdir, "saved")
+    os.makedirs(d, exist_ok=True)
+    fa = os.path.join(d, "ref.fa")
+    shutil.copy(case["fa"], fa)
+    ctx = api.Context.from_text(oix.text, oix.startpos, oix.sizes, oix.descr, w=4)
+    try:
+        ctx.build_mappability(int(oix.sizes[::2].sum()))
+        ctx.save_index(fa, with_mappability=True)
+    finally:
+        ctx.close()
+    for f in ["rc1.ref.bin", "rc1.ref.seq.bin", "rc1.i4.index.bin", "rc1.i4.index.sa.bin", "rc1.i4.index.isa.bin",
+              "rc1.i4.index.lcp.vec.bin", "rc1.i4.index.lcp.m.bin"]:
+        assert filecmp.cmp(os.path.join(fa + ".bin", f), os.path.join(case["fa"] + ".bin", f), shallow=False), f
+    a = np.fromfile(fa + ".bin/map.bin", dtype=np.uint8)[2:]
+    assert np.array_equal(a, case["body"])
+
+
+@pytest.mark.skipif(not O.have_reference(), reason="oracle/_ref not built")
+def test_against_unmodified_reference_binary(workdir):
+    """End to end against the real `mummer` (oracle/_ref) at 2 x 1 Mb: index files, map.bin, SAM lines."""
+    from smash_paper_b200 import api, synth
+    d = os.path.join(workdir, "vs_ref")
+    os.makedirs(d, exist_ok=True)
+    ref = synth.make_reference([("chr1", 1000000), ("chr2", 800000)], seed=5, n_families=30, n_long=3)
+    fa = os.path.join(d, "ref.fa")
+    synth.write_fasta(ref, fa)
+    reads = synth.make_reads(ref, 5000, seed=6)
+    synth.write_sam(reads, os.path.join(d, "reads.sam"))
+    O.ref_build_index(fa)
+    hdr, lines = O.ref_map(fa, os.path.join(d, "reads.sam"), d, threads=4)
+    ix = api.Index.open(fa)
+    ctx = api.Context(ix, min_len=20, nomap=True)
+    try:
+        assert ix.sam_header() == hdr
+        res = ctx.map_batch(reads)
+        assert sorted(res.sam.splitlines(keepends=True)) == lines
+        body = ctx.build_mappability(ref.total)
+        assert np.array_equal(body, np.fromfile(fa + ".bin/map.bin", dtype=np.uint8)[2:])
+    finally:
+        ctx.close(); ix.close()
+    # and the GPU-built index equals the reference-built files
+    oix = O.Index.load(fa)
+    ctx = api.Context.from_text(oix.text, oix.startpos, oix.sizes, oix.descr, w=4)
+    try:
+        sa, isa, vec, m = ctx.copy_index(oix.N, 4)
+        assert np.array_equal(sa, oix.sa) and np.array_equal(isa, oix.isa) and np.array_equal(vec, oix.lcp_vec)
+        assert np.array_equal(m, _lcpm_raw(oix))
+    finally:
+        ctx.close()
