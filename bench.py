@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s mapped (MAM search + SAM records) and binned (smashMEM filter + varbin) on
+N B200s, next to the reference's CPU path on the box's own host cores.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config1|config2] [--impl ours|reference]
+
+One "step" = one batch of synthetic reads through the whole hot path.  Prints ONE JSON line
+(rank 0).  `value` = whole-job reads/s with the batch resident in HBM (CUDA events);
+`e2e` = the same through smash_submit/smash_wait with pinned HOST buffers, H2D and D2H copies of
+every step inside the timed region.  See DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from smash_paper_b200 import sequence, synth  # noqa: E402
+
+METRIC = "reads_per_s_mapped_and_binned"
+UNIT = "reads/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[0]: 5 x 10 Mb random reference with planted repeats, 150 bp reads, l=20, 50 kb bins
+    "config1": dict(chroms=[(f"chr{i + 1}", 10_000_000) for i in range(5)], read_len=150, min_len=20,
+                    bin_width=50_000, families=200, chunk_cap=0,
+                    # bytes the REFERENCE algorithm touches per read (w=4)
+                    ref_alg_bytes_per_read=7800.0),
+    # configs[1]: hg19-shaped 24 chromosomes (3.1 Gb), 8-byte index
+    "config2": dict(chroms=synth.HG19_SIZES, read_len=150, min_len=20, bin_width=None, families=2000,
+                    chunk_cap=400_000_000, ref_alg_bytes_per_read=14100.0),
+    # tiny, for CI
+    "tiny": dict(chroms=[("chr1", 300_000), ("chr2", 200_000)], read_len=150, min_len=20, bin_width=5000,
+                 families=10, chunk_cap=0, ref_alg_bytes_per_read=7800.0),
+}
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu):
+        self.gpu = gpu
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        self.path = tempfile.mktemp(suffix=".csv")
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def make_reference(wl, seed=1):
+    t0 = time.time()
+    ref = synth.make_reference(wl["chroms"], seed=seed, n_families=wl["families"])
+    log(f"reference: {len(ref.names)} chromosomes, {ref.total} bp in {time.time() - t0:.1f}s")
+    return ref
+
+
+def make_bins(wl, ref, workdir):
+    """bins: start_abspos column.  config2 uses the reference's own sample_bins/50000/bins.txt
+    (committed copy under tests/golden/, hg19 offsets); the others fixed-width bins."""
+    if wl["bin_width"] is None:
+        path = os.path.join(ROOT, "tests", "golden", "sample_bins_50000_bins.txt")
+        starts = np.array([int(line.split("\t")[2]) for line in open(path)], dtype=np.int64)
+        return starts
+    path = os.path.join(workdir, "bins.txt")
+    synth.write_fixed_bins(ref, path, wl["bin_width"])
+    return np.array([int(line.split("\t")[2]) for line in open(path)], dtype=np.int64)
+
+
+def pinned_batch(api, batch):
+    """Copy a synth.ReadBatch into cudaHostAlloc memory."""
+    out, keep = {}, []
+    for k in ("names", "name_off", "seq", "qual", "seq_off", "flags", "opt", "opt_off"):
+        a = getattr(batch, k)
+        p = api.PinnedArray(a.shape, a.dtype)
+        p.array[...] = a
+        out[k] = p.array
+        keep.append(p)
+    b = synth.ReadBatch(**out)
+    b._pinned = keep
+    return b
+
+
+# ------------------------------------------------------------------------------------------ ours
+
+def run_ours(args, wl, rank, world):
+    import torch
+    from smash_paper_b200 import api
+    dev = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    workdir = tempfile.mkdtemp(prefix="smash_bench_")
+    ref = make_reference(wl)
+    names, seqs = ref.names, ref.seqs
+    t0 = time.time()
+    text, startpos, sizes, descr = sequence.text_from_chromosomes(names, seqs, rcref=True)
+    log(f"text: N={len(text)} in {time.time() - t0:.1f}s")
+    t0 = time.time()
+    ctx = api.Context.from_text(text, startpos, sizes, descr, keep_isa=True, chunk_cap=wl["chunk_cap"], device=dev,
+                                min_len=wl["min_len"], nomap=True, tag_mappability=True)
+    t_index = time.time() - t0
+    t0 = time.time()
+    ctx.build_mappability_device(ref.total)
+    t_map = time.time() - t0
+    log(f"index built on GPU in {t_index:.1f}s, map.bin in {t_map:.1f}s, {ctx.index_bytes / 1e9:.2f} GB in HBM")
+    starts = make_bins(wl, ref, workdir)
+    offs = ref.offsets()
+    ctx.tail_configure(starts, names, offs)
+    genome = ref.concat()
+
+    B = args.batch_reads
+    n_batches = args.warmup + args.steps
+    pairs_per_batch = B // 2
+    batches = []
+    t0 = time.time()
+    for i in range(n_batches):
+        first = (rank * n_batches + i) * pairs_per_batch
+        b = synth.make_reads_fast(genome, pairs_per_batch, read_len=wl["read_len"], seed=1000, first_pair=first)
+        batches.append(pinned_batch(api, b))
+    log(f"{n_batches} batches x {B} reads generated in {time.time() - t0:.1f}s")
+    del genome
+    want = api.WANT_SAM | api.WANT_TAIL
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident: inputs in HBM before the timed region of every step
+    for i in range(args.warmup):
+        ctx.upload(batches[i]); ctx.map_resident(want)
+    ctx.tail_reset(); ctx.stage_ms(reset=True)
+    counts_t = torch.zeros(len(starts), dtype=torch.int64, device=f"cuda:{dev}")
+    sampler = ClockSampler(dev)
+    barrier()
+    sampler.start()
+    launches0 = ctx.launches
+    dev_ms = 0.0
+    sam_bytes = 0
+    for i in range(args.steps):
+        ctx.upload(batches[args.warmup + i])            # untimed: H2D, then the step runs on resident data
+        r = ctx.map_resident(want)
+        dev_ms += r.gpu_ms
+        sam_bytes += r.sam_bytes
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    counts, stats = ctx.tail_finish(counts_t.data_ptr())
+    if dist:
+        dist.all_reduce(counts_t)                        # the one collective of the path: per-bin counts
+    ev1.record()
+    torch.cuda.synchronize()
+    dev_ms += ev0.elapsed_time(ev1)
+    stage = ctx.stage_ms()
+    launches = ctx.launches - launches0
+    clocks = sampler.stop()
+    t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=f"cuda:{dev}")
+    if dist:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t_ms.item())
+    total_reads = B * args.steps * world
+    value = total_reads / (dev_ms_max / 1e3)
+
+    # ---------------- end to end: pinned host batches in, SAM bytes + counts back on the host
+    ctx.tail_reset()
+    for i in range(max(api.N_SLOTS, min(2 * api.N_SLOTS, args.warmup))):   # warm every slot (buffers, pinned results)
+        ctx.submit(i % api.N_SLOTS, batches[i % len(batches)], want=want)
+        ctx.wait(i % api.N_SLOTS, copy=False)
+    ctx.tail_reset()
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for i in range(args.steps):
+        slot = i % api.N_SLOTS
+        if i >= api.N_SLOTS:
+            r = ctx.wait(slot, copy=False); d2h += int(r.sam_bytes)
+        b = batches[args.warmup + i]
+        ctx.submit(slot, b, want=want, first_pair=i * pairs_per_batch)
+        h2d += b.names.nbytes + b.name_off.nbytes + b.seq.nbytes + b.qual.nbytes + b.seq_off.nbytes + 2 * b.n
+    for i in range(max(0, args.steps - api.N_SLOTS), args.steps):
+        r = ctx.wait(i % api.N_SLOTS, copy=False); d2h += int(r.sam_bytes)
+    counts2, stats2 = ctx.tail_finish(counts_t.data_ptr())
+    if dist:
+        dist.all_reduce(counts_t)
+    host_counts = counts_t.cpu()
+    d2h += host_counts.numel() * 8
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{dev}")
+    if dist:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = total_reads / float(t_e.item())
+
+    out = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        search_ms = stage["search"] / args.steps
+        # algorithmic bytes of OUR search kernel per read (DESIGN.md "mam_search roofline"):
+        # anchors * (8 B seed pair) + candidates * (w B SA + ~2 text words + 1 B U) + q read bytes
+        alg_bytes = ours_alg_bytes_per_read(wl, len(text), ctx)
+        achieved = B * alg_bytes / (search_ms / 1e3) / 1e9 if search_ms > 0 else 0.0
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload_desc, "reads_per_step_per_gpu": B, "read_len": wl["read_len"],
+                       "min_len": wl["min_len"], "text_len": int(len(text)), "n_bins": int(len(starts)),
+                       "index": "built on GPU, replicated per GPU", "sharding": f"reads x{world}, 1 allreduce of bin counts",
+                       "l2": "inputs (index touches, 1.7 KB/read SAM) far larger than L2; distinct batch per step",
+                       "timing": "sum of per-step CUDA-event durations with the batch resident + tail_finish/allreduce; max over ranks"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // max(args.steps, 1),
+                    "d2h_bytes_per_step": d2h // max(args.steps, 1)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "kernel": "k_mam_search", "kernel_ms": search_ms, "alg_bytes_per_read": alg_bytes,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                         "ref_alg_bytes_per_read": wl["ref_alg_bytes_per_read"],
+                         "achieved_on_ref_alg_bytes": B * wl["ref_alg_bytes_per_read"] / (search_ms / 1e3) / 1e9 if search_ms > 0 else None},
+            "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+            "sam_bytes_per_read": sam_bytes / max(B * args.steps, 1),
+            "tail": stats, "index_build_s": t_index, "mappability_build_s": t_map,
+            "index_hbm_gb": ctx.index_bytes / 1e9,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                out["cpu_baseline"] = cpu_baseline(args, wl, ref, ctx, workdir, sample_pairs=args.cpu_sample_pairs, steps=1)
+            except Exception as e:  # noqa: BLE001 -- the baseline must never break the bench line
+                out["cpu_baseline"] = {"error": str(e)[:300]}
+    ctx.close()
+    shutil.rmtree(workdir, ignore_errors=True)
+    if dist:
+        dist.destroy_process_group()
+    return out
+
+
+def ours_alg_bytes_per_read(wl, N, ctx):
+    """Element-granular bytes our anchor search must touch per read (stated in DESIGN.md)."""
+    import math
+    w = 4 if N < 0xFFFFFFFF - 100000 else 8
+    L, q = wl["min_len"], wl["read_len"]
+    k = min(16, max(4, math.ceil(math.log(N) / math.log(4.0)) + 1), L)
+    s = L - k + 1
+    anchors = (q - L + s - 1) // s + 1
+    cand_per_anchor = N / 4.0 ** k + 0.25        # chance hits + the true locus for ~1/4 of the anchors
+    seed_w = 4 if N < 0xFFFFFFFF else 8
+    per_cand = w + 2 * 16 + 1                    # SA entry + two 16-byte text windows (left/right) + U byte
+    return q + anchors * (2 * seed_w + cand_per_anchor * per_cand)
+
+
+# ------------------------------------------------------------------------------------- reference
+
+def cpu_baseline(args, wl, ref, ctx, workdir, sample_pairs, steps):
+    """The UNMODIFIED reference (oracle/_ref/mummer[-long]) on the host cores, bounded sample.
+    ctx: a GPU context whose index is saved in the reference's file format (byte-identical files,
+    tests/test_gpu_parity.py) or None -> the reference builds its own index."""
+    from oracle import oracle as O
+    if not O.have_reference():
+        raise RuntimeError("oracle/_ref not built")
+    cores = os.cpu_count() or 2
+    fa = os.path.join(workdir, "ref.fa")
+    t0 = time.time()
+    synth.write_fasta(ref, fa)
+    long_ints = (2 * ref.total + 2 * len(ref.names)) >= 0xFFFFFFFF - 100000
+    if ctx is not None:
+        ctx.save_index(fa, with_mappability=False)
+        built = "gpu builder (files byte-identical to the reference's, see tests)"
+    else:
+        O.ref_build_index(fa, long_ints=long_ints, mappability=False)
+        built = "reference's own qsufsort build"
+    log(f"reference index files ready in {time.time() - t0:.1f}s ({built})")
+    exe = os.path.join(O.REF_BIN, "mummer-long" if long_ints else "mummer")
+    empty = os.path.join(workdir, "empty.sam")
+    open(empty, "w").close()
+
+    def run(sam):
+        shutil.rmtree(os.path.join(workdir, "mapout"), ignore_errors=True)
+        t = time.perf_counter()
+        subprocess.run([exe, "-rcref", "-qthreads", str(max(2, cores)), "-nomap", "-samin", "-samout", fa, sam],
+                       cwd=workdir, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        return time.perf_counter() - t
+
+    genome = ref.concat()
+    run(empty)                                   # page the index in
+    startup = min(run(empty), run(empty))
+    vals = []
+    for s in range(steps):
+        b = synth.make_reads_fast(genome, sample_pairs, read_len=wl["read_len"], seed=1000, first_pair=500_000_000 + s * sample_pairs)
+        sam = os.path.join(workdir, f"sample{s}.sam")
+        synth.write_sam(b, sam)
+        wall = run(sam)
+        vals.append(2 * sample_pairs / max(wall - startup, 1e-6))
+        log(f"reference step {s}: {2 * sample_pairs} reads wall {wall:.2f}s startup {startup:.2f}s -> {vals[-1]:.0f} reads/s")
+        os.unlink(sam)
+    return {"value": float(np.mean(vals)), "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"{2 * sample_pairs} reads/step x {steps} through oracle/_ref/{os.path.basename(exe)} -rcref -qthreads {max(2, cores)} "
+                      f"-nomap -samin -samout; wall minus a zero-read run ({startup:.2f}s index mmap + buffer init); "
+                      f"mapping+SAM only (mappability_tag/smashMEM/varbin stages not included)",
+            "index": built, "per_step": vals}
+
+
+def run_reference(args, wl, rank, world):
+    if rank != 0:
+        return None
+    workdir = tempfile.mkdtemp(prefix="smash_ref_")
+    ref = make_reference(wl)
+    ctx = None
+    N = 2 * ref.total + 2 * len(ref.names)
+    if N > 400_000_000:
+        # the reference's own index build would take hours here: use the GPU builder's files
+        from smash_paper_b200 import api
+        text, startpos, sizes, descr = sequence.text_from_chromosomes(ref.names, ref.seqs, rcref=True)
+        ctx = api.Context.from_text(text, startpos, sizes, descr, keep_isa=True, chunk_cap=wl["chunk_cap"])
+        del text
+    try:
+        cb = cpu_baseline(args, wl, ref, ctx, workdir, sample_pairs=args.cpu_sample_pairs, steps=args.warmup + args.steps)
+    finally:
+        if ctx is not None:
+            ctx.close()
+        shutil.rmtree(workdir, ignore_errors=True)
+    vals = cb["per_step"][args.warmup:] or cb["per_step"]
+    v = float(np.mean(vals))
+    cb["value"] = v
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * 2 * args.cpu_sample_pairs / v, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload_desc, "read_len": wl["read_len"], "min_len": wl["min_len"],
+                       "reads_per_step": 2 * args.cpu_sample_pairs},
+            "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("SMASH_BENCH_WORKLOAD", "config1"), choices=sorted(WORKLOADS))
+    ap.add_argument("--batch-reads", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=150_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.workload == "tiny":
+        args.batch_reads = min(args.batch_reads, 20000)
+        args.cpu_sample_pairs = min(args.cpu_sample_pairs, 5000)
+    total_bp = sum(s for _, s in wl["chroms"])
+    args.workload_desc = (f"{args.workload}: synthetic {len(wl['chroms'])}-chromosome {total_bp / 1e6:.0f} Mb reference "
+                          f"(planted repeats, N-padded ends), {wl['read_len']} bp chimeric SMASH reads, min MEM {wl['min_len']}, "
+                          f"MAM mode (production flags -rcref -nomap -samin -samout), mappability filter + 50k-style bins")
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        out = run_reference(args, wl, rank, world)
+    else:
+        out = run_ours(args, wl, rank, world)
+    if rank == 0 and out is not None:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

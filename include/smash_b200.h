@@ -165,6 +165,9 @@ int smash_tail_reset(smash_ctx *ctx);
 
 /* ---- counters for bench.py: kernels launched by this library since ctx creation */
 uint64_t smash_ctx_launch_count(const smash_ctx *ctx);
+/* Device milliseconds accumulated per stage since the last reset, measured with CUDA events on the
+ * launching stream: [0] search, [1] records, [2] sizes+scan, [3] emit, [4] match CSR, [5] tail. */
+void smash_ctx_stage_ms(smash_ctx *ctx, double *out8, int reset);
 /* Bytes of HBM held by the index on this ctx (text, SA, LCP, seed table, ...). */
 uint64_t smash_ctx_index_bytes(const smash_ctx *ctx);
 /* Raw CUDA stream (cudaStream_t) the ctx launches on, for external event timing. */

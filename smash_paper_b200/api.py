@@ -227,6 +227,10 @@ class Context:
         _check(load_library().smash_ctx_copy_index(self.h, None, None, None, _ptr(m), None))
         return sa, isa, vec, m[:16 * nm.value]
 
+    def build_mappability_device(self, total_forward_bases=None):
+        """map.bin body built and kept in HBM only (no host copy)."""
+        _check(load_library().smash_ctx_build_mappability(self.h, None, C.c_uint64(0)))
+
     def save_index(self, fasta, with_mappability=False):
         _check(load_library().smash_ctx_save_index(self.h, str(fasta).encode(), int(with_mappability)))
 
@@ -321,6 +325,11 @@ class Context:
 
     def tail_reset(self):
         _check(load_library().smash_tail_reset(self.h))
+
+    def stage_ms(self, reset=False):
+        out = (C.c_double * 8)()
+        load_library().smash_ctx_stage_ms(self.h, out, int(reset))
+        return dict(zip(["search", "records", "sizes_scan", "emit", "match_csr", "tail"], list(out)[:6]))
 
     @property
     def launches(self):

@@ -200,6 +200,8 @@ template <class T> struct HBuf {        // growable pinned host buffer
 struct Slot {
   cudaStream_t st = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries
+  int n_evs = 0; int ev_stage[8];
   // batch on device
   DBuf<uint8_t> names, seq, qual, opt;
   DBuf<int64_t> name_off, seq_off, opt_off;
@@ -208,7 +210,7 @@ struct Slot {
   // work
   int cap = 0;
   DBuf<Match> match_slots; DBuf<uint32_t> match_cnt; DBuf<Item> item_slots; DBuf<Rec> rec_slots;
-  DBuf<ReadSum> sums; DBuf<uint32_t> read_bytes; DBuf<uint64_t> out_off; DBuf<uint64_t> blk_sums;
+  DBuf<ReadSum> sums; DBuf<uint32_t> nrec; DBuf<uint64_t> rec_base; DBuf<uint32_t> rec_read; DBuf<uint32_t> read_bytes; DBuf<uint64_t> out_off; DBuf<uint64_t> blk_sums;
   DBuf<char> sam; DBuf<uint32_t> flags;
   DBuf<int64_t> csr_off; DBuf<uint64_t> csr_triples;
   // results on host
@@ -233,6 +235,7 @@ struct smash_ctx {
   smash_index *own_index = nullptr;
   uint64_t index_bytes = 0;
   uint64_t launches = 0;
+  double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // search, records, sizes+scan, emit, csr, tail
   Slot slot[SMASH_N_SLOTS];
   TailState tail;
 };
@@ -282,6 +285,7 @@ static int ctx_begin(const smash_params *p, smash_ctx **out) {
   for (int s = 0; s < SMASH_N_SLOTS; ++s) {
     CUC(cudaStreamCreateWithFlags(&c->slot[s].st, cudaStreamNonBlocking));
     CUC(cudaEventCreate(&c->slot[s].ev0)); CUC(cudaEventCreate(&c->slot[s].ev1));
+    for (int e = 0; e < 8; ++e) CUC(cudaEventCreate(&c->slot[s].evs[e]));
   }
   *out = c;
   return 0;
@@ -509,11 +513,12 @@ static void slot_release(Slot &s) {
   s.names.release(); s.seq.release(); s.qual.release(); s.opt.release(); s.name_off.release();
   s.seq_off.release(); s.opt_off.release(); s.read_flag.release(); s.match_slots.release();
   s.match_cnt.release(); s.item_slots.release(); s.rec_slots.release(); s.sums.release();
-  s.read_bytes.release(); s.out_off.release(); s.blk_sums.release(); s.sam.release(); s.flags.release();
+  s.nrec.release(); s.rec_base.release(); s.rec_read.release(); s.read_bytes.release(); s.out_off.release(); s.blk_sums.release(); s.sam.release(); s.flags.release();
   s.csr_off.release(); s.csr_triples.release(); s.h_sam.release(); s.h_csr_off.release();
   s.h_matches.release(); s.h_small.release();
   if (s.ev0) cudaEventDestroy(s.ev0);
   if (s.ev1) cudaEventDestroy(s.ev1);
+  for (int e = 0; e < 8; ++e) if (s.evs[e]) cudaEventDestroy(s.evs[e]);
   if (s.st) cudaStreamDestroy(s.st);
 }
 
@@ -583,9 +588,10 @@ static int slot_prepare(smash_ctx *c, Slot &s, const smash_batch *b, bool copy) 
   if (opt_bytes && ((rc = s.opt.ensure(opt_bytes + 16)) || (rc = s.opt_off.ensure(n + 1)))) return rc;
   if (s.cap == 0) s.cap = 24;
   if ((rc = s.match_slots.ensure(n * s.cap)) || (rc = s.match_cnt.ensure(n + 1)) || (rc = s.item_slots.ensure(n * s.cap)) ||
-      (rc = s.rec_slots.ensure(n * s.cap)) || (rc = s.sums.ensure(n + 2)) || (rc = s.read_bytes.ensure(n + 1)) ||
+      (rc = s.rec_slots.ensure(n * s.cap)) || (rc = s.sums.ensure(n + 2)) || (rc = s.nrec.ensure(n + 1)) ||
+      (rc = s.rec_base.ensure(n + 2)) || (rc = s.rec_read.ensure(n * s.cap + 1)) || (rc = s.read_bytes.ensure(n + 1)) ||
       (rc = s.out_off.ensure(n + 2)) || (rc = s.blk_sums.ensure(n / 2048 + 8)) || (rc = s.flags.ensure(N_FLAGS)) ||
-      (rc = s.h_small.ensure(16)))
+      (rc = s.h_small.ensure(32)))
     return rc;
   if (copy && n) {
     CU(cudaMemcpyAsync(s.names.p, b->names, name_bytes, cudaMemcpyHostToDevice, s.st));
@@ -609,11 +615,12 @@ static int slot_prepare(smash_ctx *c, Slot &s, const smash_batch *b, bool copy) 
 static WorkDev work_of(Slot &s) {
   WorkDev w{};
   w.cap = s.cap; w.match_slots = s.match_slots.p; w.match_cnt = s.match_cnt.p; w.item_slots = s.item_slots.p;
-  w.rec_slots = s.rec_slots.p; w.sums = s.sums.p; w.read_bytes = s.read_bytes.p; w.out_off = s.out_off.p;
+  w.rec_slots = s.rec_slots.p; w.sums = s.sums.p; w.nrec = s.nrec.p; w.rec_base = s.rec_base.p; w.rec_read = s.rec_read.p; w.read_bytes = s.read_bytes.p; w.out_off = s.out_off.p;
   w.blk_sums = s.blk_sums.p; w.sam = s.sam.p; w.sam_cap = s.sam.cap; w.flags = s.flags.p;
   return w;
 }
 
+#define MARK(stage) do { if (s.n_evs < 8) { CU(cudaEventRecord(s.evs[s.n_evs], s.st)); s.ev_stage[s.n_evs++] = (stage); } } while (0)
 // search -> records -> sizes/scan -> (sync for the byte total) -> emit [-> D2H].
 // The only host synchronisation inside is the 8-byte read of the SAM size.
 static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
@@ -624,14 +631,19 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
     WorkDev w = work_of(s);
     CU(cudaMemsetAsync(s.flags.p, 0, sizeof(uint32_t) * N_FLAGS, s.st));
     CU(cudaEventRecord(s.ev0, s.st));
+    s.n_evs = 0;
     int nl;
     if (c->prm.mode == SMASH_MODE_MEM) nl = launch_mem_search(c->dix, s.bd, w, c->sp, s.st);
     else nl = launch_mam_search(c->dix, s.bd, w, c->sp, s.st);
     if (nl < 0) return fail(SMASH_ERR_STATE, "MEM mode kernel not available in this build");
     c->launches += nl;
+    MARK(0);
     c->launches += launch_records(c->dix, s.bd, w, c->sp, s.st);
+    MARK(1);
     c->launches += launch_sizes_scan(c->dix, s.bd, w, c->sp, s.st);
+    MARK(2);
     CU(cudaMemcpyAsync(s.h_small.p, s.out_off.p + n, 8, cudaMemcpyDeviceToHost, s.st));
+    CU(cudaMemcpyAsync(s.h_small.p + 8, s.rec_base.p + n, 8, cudaMemcpyDeviceToHost, s.st));
     CU(cudaMemcpyAsync(s.h_small.p + 1, s.flags.p, sizeof(uint32_t) * N_FLAGS, cudaMemcpyDeviceToHost, s.st));
     CU(cudaStreamSynchronize(s.st));
     const uint32_t *fl = (const uint32_t *)(s.h_small.p + 1);
@@ -642,7 +654,8 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
         return fail(SMASH_ERR_DATA, "a read produced %u matches; this build keeps at most %d per read", need, STAGE_CAP);
       s.cap = (int)need + 8 > STAGE_CAP ? STAGE_CAP : (int)need + 8;
       int rc;
-      if ((rc = s.match_slots.ensure(n * s.cap)) || (rc = s.item_slots.ensure(n * s.cap)) || (rc = s.rec_slots.ensure(n * s.cap))) return rc;
+      if ((rc = s.match_slots.ensure(n * s.cap)) || (rc = s.item_slots.ensure(n * s.cap)) || (rc = s.rec_slots.ensure(n * s.cap)) ||
+          (rc = s.rec_read.ensure(n * s.cap + 1))) return rc;
       continue;                                              // rerun the batch with wider slots
     }
     if (fl[FLAG_MAPERR] && ((want & SMASH_WANT_TAIL) || c->prm.tag_mappability))
@@ -650,11 +663,13 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
     break;
   }
   s.sam_bytes = s.h_small.p[0];
+  s.n_records = s.h_small.p[8];
   if (want & SMASH_WANT_SAM) {
     int rc;
     if ((rc = s.sam.ensure(s.sam_bytes + 64))) return rc;
     WorkDev w = work_of(s);
-    c->launches += launch_emit(c->dix, s.bd, w, c->sp, s.st);
+    c->launches += launch_emit(c->dix, s.bd, w, c->sp, s.st, s.n_records);
+    MARK(3);
     if (to_host) {
       if ((rc = s.h_sam.ensure(s.sam_bytes + 64))) return rc;
       CU(cudaMemcpyAsync(s.h_sam.p, s.sam.p, s.sam_bytes, cudaMemcpyDeviceToHost, s.st));
@@ -666,24 +681,31 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
     if ((rc = s.csr_triples.ensure(3 * n * (size_t)s.cap + 8))) return rc;
     WorkDev w = work_of(s);
     c->launches += launch_match_csr(s.bd, w, s.csr_off.p, s.csr_triples.p, s.blk_sums.p, s.st);
+    MARK(4);
     if ((rc = s.h_csr_off.ensure(n + 2)) || (rc = s.h_matches.ensure(n * (size_t)s.cap + 8))) return rc;
     CU(cudaMemcpyAsync(s.h_csr_off.p, s.csr_off.p, 8 * (n + 1), cudaMemcpyDeviceToHost, s.st));
     CU(cudaMemcpyAsync(s.h_matches.p, s.csr_triples.p, 24 * n * (size_t)s.cap, cudaMemcpyDeviceToHost, s.st));
   }
   if (want & SMASH_WANT_TAIL) {
-    int rc = tail_accumulate(&c->tail, c->dix, s.bd, work_of(s), s.first_pair, s.st, &c->launches);
+    int rc = tail_accumulate(&c->tail, c->dix, s.bd, work_of(s), s.n_records, s.st, &c->launches);
     if (rc) return fail(rc, "tail: %s", tail_error());
+    MARK(5);
   }
   CU(cudaEventRecord(s.ev1, s.st));
   return 0;
 }
 
-static int slot_finish(smash_ctx *, Slot &s, smash_result *res) {
+static int slot_finish(smash_ctx *c, Slot &s, smash_result *res) {
   CU(cudaStreamSynchronize(s.st));
   CU(cudaGetLastError());
+  if (s.n_reads) {
+    cudaEvent_t prev = s.ev0;
+    for (int e = 0; e < s.n_evs; ++e) { float ms = 0; if (cudaEventElapsedTime(&ms, prev, s.evs[e]) == cudaSuccess) c->stage_ms[s.ev_stage[e]] += ms; prev = s.evs[e]; }
+    s.n_evs = 0;
+  }
   if (res) {
     memset(res, 0, sizeof *res);
-    res->n_reads = s.n_reads; res->sam_bytes = s.sam_bytes;
+    res->n_reads = s.n_reads; res->sam_bytes = s.sam_bytes; res->n_records = s.n_records;
     if (s.n_reads) { float ms = 0; cudaEventElapsedTime(&ms, s.ev0, s.ev1); res->gpu_ms = ms; }
     if ((s.want & SMASH_WANT_SAM) && s.h_sam.p) res->sam = s.h_sam.p;
     if ((s.want & SMASH_WANT_MATCHES) && s.n_reads) {
@@ -802,5 +824,10 @@ extern "C" int smash_tail_reset(smash_ctx *c) {
 }
 
 extern "C" uint64_t smash_ctx_launch_count(const smash_ctx *c) { return c ? c->launches : 0; }
+extern "C" void smash_ctx_stage_ms(smash_ctx *c, double *out, int reset) {
+  if (!c) return;
+  if (out) for (int i = 0; i < 8; ++i) out[i] = c->stage_ms[i];
+  if (reset) for (int i = 0; i < 8; ++i) c->stage_ms[i] = 0;
+}
 extern "C" uint64_t smash_ctx_index_bytes(const smash_ctx *c) { return c ? c->index_bytes : 0; }
 extern "C" void *smash_ctx_stream(const smash_ctx *c) { return c ? (void *)c->slot[0].st : nullptr; }

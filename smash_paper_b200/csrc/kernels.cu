@@ -239,6 +239,7 @@ k_records(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     }
     __syncwarp();
     const int n_rec = sm.nrec[warp];
+    if (lane == 0) w.nrec[read] = (uint32_t)n_rec;
     const bool unmapped = w.sums[read].unmapped;
     if (!unmapped) {
       for (int r = 0; r < n_rec; ++r) {                    // XE: all lanes, 8 read bytes each
@@ -274,10 +275,11 @@ k_records(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
   }
 }
 
+static int exclusive_scan_u32(const uint32_t *in, uint64_t n, uint64_t *blk, uint64_t *out, cudaStream_t st);
 int launch_records(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
   if (!b.n_reads) return 0;
   k_records<<<grid_for_warps(b.n_reads, 6), THREADS, 0, st>>>(ix, b, w, p);
-  return 1;
+  return 1 + exclusive_scan_u32(w.nrec, b.n_reads, w.blk_sums, w.rec_base, st);
 }
 
 // ------------------------------------------------------------------ K4a: sizes + scan
@@ -312,13 +314,17 @@ k_sizes(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
       const int name_len = (int)(b.name_off[read + 1] - b.name_off[read]);
       const int opt_len = b.opt ? (int)(b.opt_off[read + 1] - b.opt_off[read]) : 0;
       const Item *items = w.item_slots + read * (uint64_t)w.cap;
-      const Rec *recs = w.rec_slots + read * (uint64_t)w.cap;
+      Rec *recs = w.rec_slots + read * (uint64_t)w.cap;
+      const uint64_t fbase = w.rec_base[read];
       for (int r = lane; r < n_rec; r += 32) {             // one lane per record
         CountSink cs;
         put_head(cs, ix, (const char *)nullptr, name_len, flag, me.unmapped, recs[r], r, items, mv);
         put_tags(cs, ix, me.unmapped, recs, r, n_rec, items);
         if (sp.tag_mappability && !me.unmapped) put_lr_tags(cs, ix, recs[r], items);
-        bytes += cs.n + 2u * (uint32_t)q + 1u /*tab between SEQ and QUAL*/ + (uint32_t)opt_len + 1u /*\n*/;
+        const uint32_t nb = cs.n + 2u * (uint32_t)q + 1u /*tab between SEQ and QUAL*/ + (uint32_t)opt_len + 1u /*\n*/;
+        recs[r].bytes = nb;
+        w.rec_read[fbase + r] = (uint32_t)read;
+        bytes += nb;
       }
     }
     for (int o = 16; o; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
@@ -398,87 +404,111 @@ int launch_sizes_scan(const DevIndex &ix, const BatchDev &b, const WorkDev &w, c
 }
 
 // ------------------------------------------------------------------ K4b: emit
+//
+// Flat over records: a warp takes 32 consecutive records (any reads).  Phase 1, one lane per
+// record: the variable text (columns 2-9, the tags, the L/R tags) is formatted into the lane's
+// private shared-memory buffers -- 32 records are formatted at once instead of one.  Phase 2, the
+// whole warp per record: name, head, SEQ, QUAL, tags, optional fields, L/R tags and the newline
+// are streamed to the line's place in the output with coalesced byte copies.
+constexpr int EWARPS = 4;
+constexpr int HEAD_CAP = 128;
+constexpr int TAIL_CAP = 416;
 
-struct EmitSmem { char line[WARPS][LINE_BUF]; };
+struct EmitRec {           // what phase 2 needs, one per lane, exchanged with shuffles
+  unsigned long long out, name, seq, qual, opt;
+  int name_len, q, opt_len, head_len, tags_len, lr_len, rc, slow;
+};
 
-// all lanes: copy n bytes from shared/global src to global dst
-__device__ __forceinline__ void warp_copy(char *__restrict__ dst, const char *__restrict__ src, int n, int lane) {
-  for (int i = lane; i < n; i += 32) dst[i] = src[i];
-}
-
-__global__ void __launch_bounds__(THREADS)
-k_emit(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
-  __shared__ EmitSmem sm;
+__global__ void __launch_bounds__(EWARPS * 32)
+k_emit(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp, uint64_t n_records) {
+  extern __shared__ __align__(16) char esm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
-  char *line = sm.line[warp];
-  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
-    const ReadSum me = w.sums[read];
-    const int n_rec = me.n_rec;
-    if (!n_rec) continue;
-    uint16_t flag; MateView mv;
-    read_mate(b, w, read, &flag, &mv);
-    const int64_t so = b.seq_off[read];
-    const int q = (int)(b.seq_off[read + 1] - so);
-    const char *name = (const char *)b.names + b.name_off[read];
-    const int name_len = (int)(b.name_off[read + 1] - b.name_off[read]);
-    const char *opt = b.opt ? (const char *)b.opt + b.opt_off[read] : nullptr;
-    const int opt_len = b.opt ? (int)(b.opt_off[read + 1] - b.opt_off[read]) : 0;
-    const Item *items = w.item_slots + read * (uint64_t)w.cap;
-    const Rec *recs = w.rec_slots + read * (uint64_t)w.cap;
-    const uint8_t *seq = b.seq + so, *qual = b.qual + so;
-    char *out = w.sam + w.out_off[read];
-    for (int r = 0; r < n_rec; ++r) {
-      // --- columns 1-9: name copied by the warp, the rest composed by lane 0 in shared memory
-      warp_copy(out, name, name_len, lane);
-      out += name_len;
-      int n = 0;
-      if (lane == 0) {
-        CountSink cs; put_head(cs, ix, (const char *)nullptr, 0, flag, me.unmapped, recs[r], r, items, mv);
-        n = (int)cs.n;
-        if (n <= LINE_BUF) { BufSink bs{line}; put_head(bs, ix, (const char *)nullptr, 0, flag, me.unmapped, recs[r], r, items, mv); }
-        else { BufSink bs{out}; put_head(bs, ix, (const char *)nullptr, 0, flag, me.unmapped, recs[r], r, items, mv); }
+  char *hbuf = esm + (size_t)warp * 32 * (HEAD_CAP + TAIL_CAP);
+  char *tbuf = hbuf + 32 * HEAD_CAP;
+  const uint64_t warps_total = (uint64_t)gridDim.x * EWARPS;
+  for (uint64_t f0 = ((uint64_t)blockIdx.x * EWARPS + warp) * 32; f0 < n_records; f0 += warps_total * 32) {
+    const uint64_t f = f0 + lane;
+    EmitRec e; memset(&e, 0, sizeof e);
+    if (f < n_records) {
+      const uint64_t read = w.rec_read[f];
+      const int hi = (int)(f - w.rec_base[read]);
+      const ReadSum me = w.sums[read];
+      uint16_t flag; MateView mv;
+      read_mate(b, w, read, &flag, &mv);
+      const int64_t so = b.seq_off[read];
+      const Item *items = w.item_slots + read * (uint64_t)w.cap;
+      const Rec *recs = w.rec_slots + read * (uint64_t)w.cap;
+      uint64_t off = w.out_off[read];
+      for (int r = 0; r < hi; ++r) off += recs[r].bytes;
+      e.out = (unsigned long long)(w.sam + off);
+      e.name = (unsigned long long)(b.names + b.name_off[read]);
+      e.name_len = (int)(b.name_off[read + 1] - b.name_off[read]);
+      e.seq = (unsigned long long)(b.seq + so); e.qual = (unsigned long long)(b.qual + so);
+      e.q = (int)(b.seq_off[read + 1] - so);
+      e.opt = b.opt ? (unsigned long long)(b.opt + b.opt_off[read]) : 0ull;
+      e.opt_len = b.opt ? (int)(b.opt_off[read + 1] - b.opt_off[read]) : 0;
+      e.rc = recs[hi].rc && !me.unmapped;
+      CapSink hs{hbuf + lane * HEAD_CAP, (uint32_t)HEAD_CAP};
+      put_head(hs, ix, (const char *)nullptr, 0, flag, me.unmapped, recs[hi], hi, items, mv);
+      e.head_len = (int)hs.n;
+      CapSink ts{tbuf + lane * TAIL_CAP, (uint32_t)TAIL_CAP};
+      put_tags(ts, ix, me.unmapped, recs, hi, me.n_rec, items);
+      e.tags_len = (int)ts.n;
+      if (sp.tag_mappability && !me.unmapped) { put_lr_tags(ts, ix, recs[hi], items); e.lr_len = (int)ts.n - e.tags_len; }
+      if (hs.n > (uint32_t)HEAD_CAP || ts.n > (uint32_t)TAIL_CAP) {
+        // rare: very long CIGARs / names -> this lane writes its variable text straight to HBM
+        e.slow = 1;
+        char *o = (char *)e.out + e.name_len;
+        BufSink h2{o}; put_head(h2, ix, (const char *)nullptr, 0, flag, me.unmapped, recs[hi], hi, items, mv);
+        o += h2.n + 2 * e.q + 1;
+        BufSink t2{o}; put_tags(t2, ix, me.unmapped, recs, hi, me.n_rec, items);
+        if (sp.tag_mappability && !me.unmapped) { BufSink l2{o + t2.n + e.opt_len}; put_lr_tags(l2, ix, recs[hi], items); }
       }
-      n = __shfl_sync(0xffffffffu, n, 0);
-      if (n <= LINE_BUF) warp_copy(out, line, n, lane);
-      out += n;
-      // --- SEQ \t QUAL (reverse-complemented / reversed for a reverse-strand record)
-      if (recs[r].rc && !me.unmapped) {
+    }
+    __syncwarp();
+    const int n_here = (int)(n_records - f0 < 32 ? n_records - f0 : 32);
+    for (int r = 0; r < n_here; ++r) {
+      char *out = (char *)__shfl_sync(0xffffffffu, e.out, r);
+      const char *name = (const char *)__shfl_sync(0xffffffffu, e.name, r);
+      const uint8_t *seq = (const uint8_t *)__shfl_sync(0xffffffffu, e.seq, r);
+      const uint8_t *qual = (const uint8_t *)__shfl_sync(0xffffffffu, e.qual, r);
+      const char *opt = (const char *)__shfl_sync(0xffffffffu, e.opt, r);
+      const int name_len = __shfl_sync(0xffffffffu, e.name_len, r), q = __shfl_sync(0xffffffffu, e.q, r);
+      const int opt_len = __shfl_sync(0xffffffffu, e.opt_len, r), head_len = __shfl_sync(0xffffffffu, e.head_len, r);
+      const int tags_len = __shfl_sync(0xffffffffu, e.tags_len, r), lr_len = __shfl_sync(0xffffffffu, e.lr_len, r);
+      const int rc = __shfl_sync(0xffffffffu, e.rc, r), slow = __shfl_sync(0xffffffffu, e.slow, r);
+      for (int i = lane; i < name_len; i += 32) out[i] = name[i];
+      out += name_len;
+      if (!slow) { const char *h = hbuf + r * HEAD_CAP; for (int i = lane; i < head_len; i += 32) out[i] = h[i]; }
+      out += head_len;
+      if (rc) {
         for (int j = lane; j < q; j += 32) { out[j] = (char)comp_char(seq[q - 1 - j]); out[q + 1 + j] = (char)qual[q - 1 - j]; }
       } else {
         for (int j = lane; j < q; j += 32) { out[j] = (char)seq[j]; out[q + 1 + j] = (char)qual[j]; }
       }
       if (lane == 0) out[q] = '\t';
       out += 2 * q + 1;
-      __syncwarp();
-      // --- tags
-      if (lane == 0) {
-        CountSink cs; put_tags(cs, ix, me.unmapped, recs, r, n_rec, items);
-        n = (int)cs.n;
-        if (n <= LINE_BUF) { BufSink bs{line}; put_tags(bs, ix, me.unmapped, recs, r, n_rec, items); }
-        else { BufSink bs{out}; put_tags(bs, ix, me.unmapped, recs, r, n_rec, items); }
-      }
-      n = __shfl_sync(0xffffffffu, n, 0);
-      if (n <= LINE_BUF) warp_copy(out, line, n, lane);
-      out += n;
-      if (opt_len) { warp_copy(out, opt, opt_len, lane); out += opt_len; }
-      __syncwarp();
-      if (sp.tag_mappability && !me.unmapped) {
-        if (lane == 0) { BufSink bs{line}; put_lr_tags(bs, ix, recs[r], items); n = (int)bs.n; }
-        n = __shfl_sync(0xffffffffu, n, 0);
-        warp_copy(out, line, n, lane);
-        out += n;
-        __syncwarp();
-      }
+      const char *t = tbuf + r * TAIL_CAP;
+      if (!slow) for (int i = lane; i < tags_len; i += 32) out[i] = t[i];
+      out += tags_len;
+      for (int i = lane; i < opt_len; i += 32) out[i] = opt[i];
+      out += opt_len;
+      if (!slow) for (int i = lane; i < lr_len; i += 32) out[i] = t[tags_len + i];
+      out += lr_len;
       if (lane == 0) *out = '\n';
-      out += 1;
     }
+    __syncwarp();
   }
 }
 
-int launch_emit(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
-  if (!b.n_reads) return 0;
-  k_emit<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p);
+int launch_emit(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st, uint64_t n_records) {
+  if (!b.n_reads || !n_records) return 0;
+  const size_t smem = (size_t)EWARPS * 32 * (HEAD_CAP + TAIL_CAP);
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  uint64_t need = (n_records + 32 * EWARPS - 1) / (32 * EWARPS);
+  uint64_t cap = (uint64_t)sm_count() * 3;
+  k_emit<<<(unsigned)(need < cap ? need : cap), EWARPS * 32, smem, st>>>(ix, b, w, p, n_records);
   return 1;
 }
 

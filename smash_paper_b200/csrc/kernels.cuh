@@ -23,6 +23,9 @@ struct WorkDev {
   Item *item_slots;            // n_reads * cap
   Rec *rec_slots;              // n_reads * cap
   ReadSum *sums;               // n_reads
+  uint32_t *nrec;              // n_reads: records printed for the read
+  uint64_t *rec_base;          // n_reads + 1: exclusive scan of nrec (flat record index)
+  uint32_t *rec_read;          // per flat record: its read
   uint32_t *read_bytes;        // n_reads: SAM bytes of the read's records
   uint64_t *out_off;           // n_reads + 1 (exclusive scan of read_bytes)
   uint64_t *blk_sums;          // scan scratch
@@ -49,7 +52,7 @@ int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, c
 int launch_mem_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
 int launch_records(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
 int launch_sizes_scan(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
-int launch_emit(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
+int launch_emit(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st, uint64_t n_records);
 // matches -> CSR (offsets int64[n+1] + smash_match-compatible {u64 ref, u64 query, u64 len})
 int launch_match_csr(const BatchDev &b, const WorkDev &w, int64_t *off, uint64_t *triples, uint64_t *scratch, cudaStream_t st);
 int launch_mappability(const DevIndex &ix, uint64_t *min_len_scratch, uint8_t *body, cudaStream_t st);

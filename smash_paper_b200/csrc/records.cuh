@@ -24,6 +24,7 @@ struct Rec {
   uint16_t item_begin, item_cnt;   // CIGAR items (merge order) in the read's item slots
   uint16_t xu, xe, qlen, suffix;   // qlen = read length minus soft clips (pysam qlen)
   uint8_t rc, L0, R0, flags;       // L0/R0: mappability_tag values of the first '=' block
+  uint32_t bytes;                  // length of this record's SAM line (set by k_sizes)
 };
 struct Item { uint16_t prefix, len; };
 
@@ -214,14 +215,14 @@ HDN inline int build_records(const DevIndex &ix, const Match *matches, int n_in,
       const int endq = items[last_item].prefix + items[last_item].len;
       r.suffix = (uint16_t)(q - endq);
       r.qlen = (uint16_t)(endq - lead);
-      r.L0 = 0; r.R0 = 0; r.flags = 0;
+      r.L0 = 0; r.R0 = 0; r.flags = 0; r.bytes = 0;
       recs[n_rec++] = r;
     }
   }
   if (n_rec == 0 && nomap) {                          // set_nomap
     sum->unmapped = 1; n_rec = 1;
     Rec r; r.pos = 0; r.rcpos = 0; r.si = 0; r.rc = 0; r.item_begin = 0; r.item_cnt = 0;
-    r.xu = 0; r.xe = 0; r.qlen = 0; r.suffix = 0; r.L0 = 0; r.R0 = 0; r.flags = 0;
+    r.xu = 0; r.xe = 0; r.qlen = 0; r.suffix = 0; r.L0 = 0; r.R0 = 0; r.flags = 0; r.bytes = 0;
     recs[0] = r;
   }
   sum->n_rec = (uint16_t)n_rec;
@@ -276,9 +277,19 @@ struct BufSink {
   HDN void ch(char c) { p[n++] = c; }
   HDN void put(const char *s, int len) { for (int i = 0; i < len; ++i) p[n + i] = s[i]; n += (uint32_t)len; }
 };
+struct CapSink {
+  char *p; uint32_t cap; uint32_t n = 0;
+  HDN void ch(char c) { if (n < cap) p[n] = c; ++n; }
+  HDN void put(const char *s, int len) { for (int i = 0; i < len; ++i) { if (n < cap) p[n] = s[i]; ++n; } }
+};
 template <class S> HDN inline void put_u64(S &s, uint64_t v) {
   char t[20]; int n = 0;
-  do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  if (v <= 0xffffffffull) {                // 32-bit divide-by-constant: a multiply and a shift
+    uint32_t x = (uint32_t)v;
+    do { const uint32_t d = x / 10u; t[n++] = (char)('0' + (x - d * 10u)); x = d; } while (x);
+  } else {
+    do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  }
   while (n) s.ch(t[--n]);
 }
 template <class S> HDN inline void put_i64(S &s, int64_t v) {

@@ -45,13 +45,14 @@ template struct DGrow<uint32_t>;
 template struct DGrow<uint64_t>;
 
 void tail_init(TailState *) {}
-void tail_reset(TailState *t) { t->n_pairs = 0; t->n_hits = 0; t->n_positions = 0; }
+void tail_reset(TailState *t) { t->n_pairs = 0; t->n_hits_bound = 0; t->n_positions = 0; if (t->d_nhits) cudaMemset(t->d_nhits, 0, 8); }
 void tail_release(TailState *t) {
   t->pair_nhits.release(); t->pair_fp.release(); t->pair_hit_off.release(); t->hits.release();
-  void *d[] = {t->bin_starts, t->chrom_off, t->batch_cnt, t->batch_off, t->blk, t->counts, t->pos_chrom, t->pos_pos};
+  void *d[] = {t->bin_starts, t->chrom_off, t->batch_cnt, t->batch_off, t->blk, t->counts, t->pos_chrom, t->pos_pos, t->d_nhits};
   for (void *p : d) if (p) cudaFree(p);
   if (t->h_pos_chrom) cudaFreeHost(t->h_pos_chrom);
   if (t->h_pos_pos) cudaFreeHost(t->h_pos_pos);
+  if (t->last_ev) cudaEventDestroy(t->last_ev);
   *t = TailState();
 }
 
@@ -119,10 +120,10 @@ __global__ void k_pair_count(BatchDev b, WorkDev w, PairParams pp, uint64_t n_pa
   }
 }
 __global__ void k_pair_write(BatchDev b, WorkDev w, PairParams pp, uint64_t n_pairs, const uint64_t *__restrict__ off,
-                             uint64_t pair_base, uint64_t hit_base, uint32_t *__restrict__ pair_nhits,
+                             uint64_t pair_base, const uint64_t *__restrict__ hit_base_p, uint32_t *__restrict__ pair_nhits,
                              uint64_t *__restrict__ pair_fp, uint64_t *__restrict__ pair_hit_off, uint64_t *__restrict__ hits) {
   for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (uint64_t)gridDim.x * blockDim.x) {
-    uint64_t o = hit_base + off[p];
+    uint64_t o = *hit_base_p + off[p];
     const uint64_t o0 = o;
     uint64_t h1 = 0x243f6a8885a308d3ULL, h2 = 0x13198a2e03707344ULL;
     for_kept_hits(b, w, p, pp, [&](uint32_t tid, int64_t pos) {
@@ -140,12 +141,20 @@ __global__ void k_pair_write(BatchDev b, WorkDev w, PairParams pp, uint64_t n_pa
 // exclusive scan helper lives in kernels.cu
 int exclusive_scan_u32_public(const uint32_t *in, uint64_t n, uint64_t *blk, uint64_t *out, cudaStream_t st);
 
+__global__ void k_bump(uint64_t *total, const uint64_t *batch_total) { *total += *batch_total; }
+
+// No host synchronisation here: the running hit total lives on the device (t->d_nhits) and the
+// host only keeps an upper bound (every kept hit is one of the batch's records) for capacity.
 int tail_accumulate(TailState *t, const DevIndex &ix, const BatchDev &b, const WorkDev &w,
-                    uint64_t /*first_pair*/, cudaStream_t st, uint64_t *launches) {
+                    uint64_t n_records_bound, cudaStream_t st, uint64_t *launches) {
   if (!t->configured) return tfail(SMASH_ERR_STATE, "smash_tail_configure has not been called");
   if (!ix.mapbody) return tfail(SMASH_ERR_STATE, "map.bin not loaded");
   const uint64_t n_pairs = (b.n_reads + 1) / 2;
   if (!n_pairs) return 0;
+  if (!t->d_nhits) { TCU(cudaMalloc((void **)&t->d_nhits, 8)); TCU(cudaMemset(t->d_nhits, 0, 8)); }
+  if (!t->last_ev) TCU(cudaEventCreateWithFlags(&t->last_ev, cudaEventDisableTiming));
+  // batches come from SMASH_N_SLOTS streams: chain the appends so they never overlap
+  if (t->ev_recorded) TCU(cudaStreamWaitEvent(st, t->last_ev, 0));
   if (n_pairs + 2 > t->batch_cap) {
     if (t->batch_cnt) cudaFree(t->batch_cnt);
     if (t->batch_off) cudaFree(t->batch_off);
@@ -155,24 +164,25 @@ int tail_accumulate(TailState *t, const DevIndex &ix, const BatchDev &b, const W
     TCU(cudaMalloc((void **)&t->batch_off, 8 * (t->batch_cap + 1)));
     TCU(cudaMalloc((void **)&t->blk, 8 * (t->batch_cap / 2048 + 8)));
   }
+  int rc;
+  if (t->ev_recorded && (t->n_pairs + n_pairs > t->pair_nhits.cap || t->n_hits_bound + n_records_bound + 1 > t->hits.cap))
+    TCU(cudaEventSynchronize(t->last_ev));          // growing: the previous append must have landed
+  const size_t want_pairs = t->pair_nhits.cap ? t->n_pairs + n_pairs : 8 * n_pairs;      // first batch: room for 8
+  const size_t want_hits = t->hits.cap ? t->n_hits_bound + n_records_bound + 1 : 8 * (n_records_bound + 1);
+  if ((rc = t->pair_nhits.reserve(want_pairs, t->n_pairs, st)) || (rc = t->pair_fp.reserve(2 * want_pairs, 2 * t->n_pairs, st)) ||
+      (rc = t->pair_hit_off.reserve(want_pairs, t->n_pairs, st)) || (rc = t->hits.reserve(want_hits, t->n_hits_bound, st)))
+    return rc;
   PairParams pp{t->hit_window, t->min_excess};
   const int grid = (int)((n_pairs + 255) / 256 < 148 * 8 ? (n_pairs + 255) / 256 : 148 * 8);
   k_pair_count<<<grid, 256, 0, st>>>(b, w, pp, n_pairs, t->batch_cnt);
   *launches += 1 + exclusive_scan_u32_public(t->batch_cnt, n_pairs, t->blk, t->batch_off, st);
-  uint64_t total = 0;
-  TCU(cudaMemcpyAsync(&total, t->batch_off + n_pairs, 8, cudaMemcpyDeviceToHost, st));
-  TCU(cudaStreamSynchronize(st));
-  int rc;
-  if ((rc = t->pair_nhits.reserve(t->n_pairs + n_pairs, t->n_pairs, st)) ||
-      (rc = t->pair_fp.reserve(2 * (t->n_pairs + n_pairs), 2 * t->n_pairs, st)) ||
-      (rc = t->pair_hit_off.reserve(t->n_pairs + n_pairs, t->n_pairs, st)) ||
-      (rc = t->hits.reserve(t->n_hits + total + 1, t->n_hits, st)))
-    return rc;
-  k_pair_write<<<grid, 256, 0, st>>>(b, w, pp, n_pairs, t->batch_off, t->n_pairs, t->n_hits, t->pair_nhits.p,
+  k_pair_write<<<grid, 256, 0, st>>>(b, w, pp, n_pairs, t->batch_off, t->n_pairs, t->d_nhits, t->pair_nhits.p,
                                      t->pair_fp.p, t->pair_hit_off.p, t->hits.p);
-  *launches += 1;
+  k_bump<<<1, 1, 0, st>>>(t->d_nhits, t->batch_off + n_pairs);
+  *launches += 2;
   TCU(cudaGetLastError());
-  t->n_pairs += n_pairs; t->n_hits += total;
+  TCU(cudaEventRecord(t->last_ev, st)); t->ev_recorded = true;
+  t->n_pairs += n_pairs; t->n_hits_bound += n_records_bound;
   return 0;
 }
 

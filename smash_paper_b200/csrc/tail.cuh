@@ -19,7 +19,9 @@ struct TailState {
   int64_t *chrom_off = nullptr; uint64_t n_chrom = 0;   // >=0 abs offset, -1 filtered by the regex, -2 by varbin
   int64_t hit_window = 10000; int32_t min_excess = 4;
   // accumulated over batches (pair index = order of submission)
-  uint64_t n_pairs = 0, n_hits = 0;
+  uint64_t n_pairs = 0, n_hits_bound = 0;   // hits: host-side upper bound, exact total in *d_nhits
+  uint64_t *d_nhits = nullptr;
+  cudaEvent_t last_ev = nullptr; bool ev_recorded = false;
   DGrow<uint32_t> pair_nhits;       // kept hits of the pair (0 => pair never reaches the dupe set)
   DGrow<uint64_t> pair_fp;          // 2 per pair: 128-bit fingerprint of the dupe key
   DGrow<uint64_t> pair_hit_off;     // first hit of the pair in `hits`
@@ -39,7 +41,7 @@ const char *tail_error();
 int tail_configure(TailState *t, const int64_t *bin_starts, uint64_t n_bins, const int64_t *chrom_off,
                    uint64_t n_chrom, int64_t hit_window, int32_t min_excess);
 int tail_accumulate(TailState *t, const DevIndex &ix, const BatchDev &b, const WorkDev &w,
-                    uint64_t first_pair, cudaStream_t st, uint64_t *launches);
+                    uint64_t n_records_bound, cudaStream_t st, uint64_t *launches);
 int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smash_tail_stats *stats,
                 cudaStream_t st, uint64_t *launches);
 int tail_positions(TailState *t, const int32_t **chrom, const int64_t **pos, uint64_t *n);

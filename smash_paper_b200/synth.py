@@ -238,6 +238,52 @@ def make_reads(ref: Reference, n_pairs, read_len=150, seed=2, frag_min=3, frag_m
         flags=flags, opt=np.zeros(0, dtype=np.uint8), opt_off=np.zeros(n + 1, dtype=np.int64))
 
 
+_FAST = None
+
+
+def _fast_lib():
+    """smash_paper_b200/host/synth_reads.c compiled on first use (gcc, in-tree .so)."""
+    global _FAST
+    if _FAST is None:
+        import ctypes
+        import subprocess
+        here = os.path.dirname(os.path.abspath(__file__))
+        src = os.path.join(here, "host", "synth_reads.c")
+        so = os.path.join(here, "host", "libsynth_reads.so")
+        if not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
+            subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-pthread", "-o", so, src])
+        _FAST = ctypes.CDLL(so)
+    return _FAST
+
+
+def make_reads_fast(genome, n_pairs, read_len=150, seed=2, frag_min=3, frag_max=8, sub_rate=0.0075,
+                    z_rate=0.01, random_frac=0.02, dup_frac=0.002, first_pair=0, n_threads=None):
+    """Same recipe as make_reads, generated by host/synth_reads.c (~100x faster; a different but
+    equally deterministic random stream: every read is a function of (seed, global pair index))."""
+    import ctypes as C
+    n = 2 * n_pairs
+    q = read_len
+    seq = np.empty(n * q, dtype=np.uint8)
+    qual = np.empty(n * q, dtype=np.uint8)
+    genome = np.ascontiguousarray(genome, dtype=np.uint8)
+    _fast_lib().synth_reads(genome.ctypes.data_as(C.c_void_p), C.c_uint64(len(genome)), C.c_uint64(seed),
+                            C.c_uint64(first_pair), C.c_uint64(n_pairs), C.c_int(q), C.c_int(frag_min), C.c_int(frag_max),
+                            C.c_double(sub_rate), C.c_double(z_rate), C.c_double(random_frac), C.c_double(dup_frac),
+                            seq.ctypes.data_as(C.c_void_p), qual.ctypes.data_as(C.c_void_p),
+                            C.c_int(n_threads or min(16, os.cpu_count() or 1)))
+    ids = first_pair + np.arange(n_pairs, dtype=np.int64)
+    digits = np.empty((n_pairs, 10), dtype=np.uint8)
+    digits[:, 0] = ord("r")
+    v = ids.copy()
+    for k in range(9, 0, -1):
+        digits[:, k] = 48 + (v % 10)
+        v //= 10
+    name_blob = np.repeat(digits, 2, axis=0)
+    return ReadBatch(names=name_blob.reshape(-1), name_off=np.arange(n + 1, dtype=np.int64) * 10, seq=seq, qual=qual,
+                     seq_off=np.arange(n + 1, dtype=np.int64) * q, flags=np.tile(np.array([77, 141], dtype=np.uint16), n_pairs),
+                     opt=np.zeros(0, dtype=np.uint8), opt_off=np.zeros(n + 1, dtype=np.int64))
+
+
 def write_sam(batch: ReadBatch, path):
     """Unaligned SAM lines as fastqs_to_sam.cpp:80-93 prints them (flags 77/141)."""
     with open(path, "wb") as f:
