@@ -256,6 +256,9 @@ def read_flags(batch):
     """QueryReader::run + Aligner::reset (query.cpp:643-644, 185-201): name gets ':0'/':1' from
     flag 64/128, then a trailing ':0'/':1' is stripped into read_flag 65/129.  batch.names never
     carry the suffix, so only names that *themselves* end in :0/:1 need the strip quirk."""
+    pre = getattr(batch, "read_flag", None)
+    if pre is not None:
+        return np.ascontiguousarray(pre, dtype=np.uint16)
     fl = batch.flags.astype(np.uint16)
     rf = np.where(fl & 64, 65, np.where(fl & 128, 129, 0)).astype(np.uint16)
     return rf

@@ -89,6 +89,11 @@ def read_flags_from_sam_flags(flags, names=None, name_off=None):
     return np.where(fl & 64, 65, np.where(fl & 128, 129, 0)).astype(np.uint16)
 
 
+def _read_flag(batch):
+    rf = getattr(batch, "read_flag", None)
+    return np.ascontiguousarray(rf, dtype=np.uint16) if rf is not None else read_flags_from_sam_flags(batch.flags)
+
+
 class PinnedArray:
     """numpy view over cudaHostAlloc memory (so H2D copies of batches are true async DMA)."""
 
@@ -261,14 +266,14 @@ class Context:
         return b
 
     def map_batch(self, batch, want=WANT_SAM, first_pair=0, read_flag=None):
-        rf = read_flags_from_sam_flags(batch.flags) if read_flag is None else read_flag
+        rf = _read_flag(batch) if read_flag is None else read_flag
         b = self._cbatch(batch, rf, first_pair)
         r = _Result()
         _check(load_library().smash_map_batch(self.h, C.byref(b), want, C.byref(r)))
         return Result(r, want)
 
     def submit(self, slot, batch, want=WANT_SAM, first_pair=0, read_flag=None):
-        rf = read_flags_from_sam_flags(batch.flags) if read_flag is None else read_flag
+        rf = _read_flag(batch) if read_flag is None else read_flag
         b = self._cbatch(batch, rf, first_pair)
         self._inflight[slot] = (batch, rf, b, want)
         _check(load_library().smash_submit(self.h, slot, C.byref(b), want))
@@ -282,7 +287,7 @@ class Context:
         return Result(r, want)
 
     def upload(self, batch, read_flag=None):
-        rf = read_flags_from_sam_flags(batch.flags) if read_flag is None else read_flag
+        rf = _read_flag(batch) if read_flag is None else read_flag
         b = self._cbatch(batch, rf)
         self._resident = (batch, rf)
         _check(load_library().smash_batch_upload(self.h, C.byref(b)))

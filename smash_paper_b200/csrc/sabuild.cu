@@ -261,14 +261,30 @@ int build_index_device(const uint8_t *T, uint64_t N, int w, void *d_sa, void *d_
   if (w == 4) k_lcp<uint32_t><<<gridn(N), 256, 0, st>>>(T, N, (const uint32_t *)d_sa, d_lcp, big);
   else k_lcp<uint64_t><<<gridn(N), 256, 0, st>>>(T, N, (const uint64_t *)d_sa, d_lcp, big);
   SCU(cudaMalloc((void **)&bigidx, 8 * (N / 16 + 1024)));
-  // ordered compaction of the indices with LCP >= 255 (sorted by idx, as vec_uchar::init leaves them)
-  {
-    size_t tb = tbytes;
-    cudaError_t e = cub::DeviceSelect::Flagged(tmp, tb, cub::CountingInputIterator<uint64_t>(0), big, bigidx, d_cnt, N, st);
-    if (e != cudaSuccess) { snprintf(err, 256, "select: %s", cudaGetErrorString(e)); return -3; }
-  }
+  // ordered compaction of the indices with LCP >= 255 (sorted by idx, as vec_uchar::init leaves them);
+  // done in pieces of 2^30 so the item count always fits CUB's 32-bit fast path
   unsigned long long nm = 0;
-  SCU(cudaMemcpyAsync(&nm, d_cnt, 8, cudaMemcpyDeviceToHost, st)); SCU(cudaStreamSynchronize(st));
+  const uint64_t big_cap = N / 16 + 1024;
+  for (uint64_t o = 0; o < N; o += (1ull << 30)) {
+    const uint64_t cnt = N - o < (1ull << 30) ? N - o : (1ull << 30);
+    if (nm >= big_cap) break;
+    // worst case this piece could add cnt entries; stop cleanly if that would overflow
+    size_t tb = tbytes;
+    unsigned long long piece = 0;
+    uint64_t room = big_cap - nm;
+    if (room < cnt) {
+      // count first (cheap: flags only) to stay inside the buffer
+      cudaError_t e0 = cub::DeviceReduce::Sum(tmp, tb, big + o, d_cnt, (int)cnt, st);
+      if (e0 != cudaSuccess) { snprintf(err, 256, "reduce: %s", cudaGetErrorString(e0)); return -3; }
+      SCU(cudaMemcpyAsync(&piece, d_cnt, 8, cudaMemcpyDeviceToHost, st)); SCU(cudaStreamSynchronize(st));
+      if (piece > room) { nm = big_cap + 1; break; }
+      tb = tbytes;
+    }
+    cudaError_t e = cub::DeviceSelect::Flagged(tmp, tb, cub::CountingInputIterator<uint64_t>(o), big + o, bigidx + nm, d_cnt, (int)cnt, st);
+    if (e != cudaSuccess) { snprintf(err, 256, "select: %s", cudaGetErrorString(e)); return -3; }
+    SCU(cudaMemcpyAsync(&piece, d_cnt, 8, cudaMemcpyDeviceToHost, st)); SCU(cudaStreamSynchronize(st));
+    nm += piece;
+  }
   if (nm > N / 16 + 1024) { snprintf(err, 256, "LCP overflow table too large (%llu entries)", nm); return -6; }
   SCU(cudaMalloc((void **)d_lcpm, sizeof(LcpItem) * (nm + 1)));
   if (nm) {

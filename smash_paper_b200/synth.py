@@ -65,8 +65,12 @@ def make_reference(chrom_sizes, seed=1, n_pad=1000, n_families=200, family_len=3
     names = [n for n, _ in chrom_sizes]
     seqs = []
     for _, size in chrom_sizes:
-        s = _ACGT[rng.integers(0, 4, size=size, dtype=np.uint8)]
-        seqs.append(s)
+        # 4 bases per random byte (one PCG64 byte stream per chromosome)
+        raw = np.frombuffer(rng.bytes((size + 3) // 4), dtype=np.uint8)
+        s = np.empty(4 * len(raw), dtype=np.uint8)
+        for k in range(4):
+            s[k::4] = _ACGT[(raw >> (2 * k)) & 3]
+        seqs.append(s[:size].copy() if 4 * len(raw) != size else s)
     lens = np.array([len(s) for s in seqs])
 
     def plant(unit, copies):
