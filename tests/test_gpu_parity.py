@@ -190,3 +190,40 @@ def test_against_unmodified_reference_binary(workdir):
         assert np.array_equal(m, _lcpm_raw(oix))
     finally:
         ctx.close()
+
+
+# ---- golden vectors of the unmodified reference (tests/golden) through the CUDA path ----------
+from helpers import golden_lines, golden_variants, load_golden_case  # noqa: E402
+
+_GOLD_MAM = [(c, v) for c in ["case_basic", "case_adversarial"] for v in golden_variants(c) if v["mode"] == "mam"]
+
+
+@pytest.mark.parametrize("case_name,variant", _GOLD_MAM, ids=[f"{c}-{v['name']}" for c, v in _GOLD_MAM])
+def test_golden_mam_records(case_name, variant):
+    from smash_paper_b200 import api
+    g = load_golden_case(case_name)
+    hdr, lines = golden_lines(variant["path"])
+    oix = g["oix"]
+    ctx = api.Context.from_text(oix.text, oix.startpos, oix.sizes, oix.descr, w=4, min_len=variant["min_len"],
+                                nomap=True, nucleotides_only=variant["nuc"])
+    try:
+        res = ctx.map_batch(g["reads"])
+        assert sorted(res.sam.splitlines(keepends=True)) == lines                 # what the reference printed
+        assert res.sam == oix.map_batch(g["reads"], min_len=variant["min_len"], nucleotides_only=variant["nuc"], n_threads=4)
+    finally:
+        ctx.close()
+
+
+def test_golden_map_bin():
+    import gzip
+    from smash_paper_b200 import api
+    for case_name in ["case_basic", "case_adversarial"]:
+        g = load_golden_case(case_name)
+        oix = g["oix"]
+        ctx = api.Context.from_text(oix.text, oix.startpos, oix.sizes, oix.descr, w=4)
+        try:
+            body = ctx.build_mappability(int(oix.sizes[::2].sum()))
+            ref = np.frombuffer(gzip.open(os.path.join(g["dir"], "map.bin.gz")).read(), dtype=np.uint8)[2:]
+            assert np.array_equal(body, ref)
+        finally:
+            ctx.close()
