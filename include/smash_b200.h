@@ -160,7 +160,10 @@ int smash_tail_finish(smash_ctx *ctx, int64_t *counts, void *counts_device, smas
 /* positions.txt rows produced so far by smash_tail_finish: chromosome index (into the forward
  * sequences) and 0-based position, in output order. */
 int smash_tail_positions(smash_ctx *ctx, const int32_t **chrom, const int64_t **pos, uint64_t *n);
-/* Cross-rank fix-ups (read-sharded multi-GPU): opaque per-rank summary to all-gather. */
+/* Capacity hint (optional): pre-allocate the tail's HBM buffers for a run of max_pairs read pairs
+ * producing at most max_hits kept hits, so no allocation happens inside the run. */
+int smash_tail_reserve(smash_ctx *ctx, uint64_t max_pairs, uint64_t max_hits);
+/* Forget everything accumulated so far (buffers are kept). */
 int smash_tail_reset(smash_ctx *ctx);
 
 /* ---- counters for bench.py: kernels launched by this library since ctx creation */

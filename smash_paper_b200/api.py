@@ -328,6 +328,9 @@ class Context:
         return (np.ctypeslib.as_array(C.cast(c, C.POINTER(C.c_int32)), shape=(m,)).copy(),
                 np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int64)), shape=(m,)).copy())
 
+    def tail_reserve(self, max_pairs, max_hits):
+        _check(load_library().smash_tail_reserve(self.h, C.c_uint64(max_pairs), C.c_uint64(max_hits)))
+
     def tail_reset(self):
         _check(load_library().smash_tail_reset(self.h))
 

@@ -23,6 +23,10 @@
 using namespace smash;
 
 static thread_local char g_err[1024] = "";
+#include <chrono>
+static const bool g_dbg = getenv("SMASH_DEBUG_TIMING") != nullptr;
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define DBG_T(label, t0) do { if (g_dbg) fprintf(stderr, "[smash-dbg] %-28s %8.3f ms\n", label, now_ms() - (t0)); } while (0)
 static int fail(int code, const char *fmt, ...) {
   va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
   return code;
@@ -210,7 +214,7 @@ struct Slot {
   // work
   int cap = 0;
   DBuf<Match> match_slots; DBuf<uint32_t> match_cnt; DBuf<Item> item_slots; DBuf<Rec> rec_slots;
-  DBuf<ReadSum> sums; DBuf<uint32_t> nrec; DBuf<uint64_t> rec_base; DBuf<uint32_t> rec_read; DBuf<uint32_t> read_bytes; DBuf<uint64_t> out_off; DBuf<uint64_t> blk_sums;
+  DBuf<ReadSum> sums; DBuf<uint32_t> nrec; DBuf<uint64_t> rec_base; DBuf<uint32_t> rec_read; DBuf<uint32_t> rec_bytes; DBuf<uint64_t> rec_off; DBuf<uint64_t> sam_total; DBuf<uint64_t> blk_sums2; DBuf<uint64_t> blk_sums;
   DBuf<char> sam; DBuf<uint32_t> flags;
   DBuf<int64_t> csr_off; DBuf<uint64_t> csr_triples;
   // results on host
@@ -513,7 +517,7 @@ static void slot_release(Slot &s) {
   s.names.release(); s.seq.release(); s.qual.release(); s.opt.release(); s.name_off.release();
   s.seq_off.release(); s.opt_off.release(); s.read_flag.release(); s.match_slots.release();
   s.match_cnt.release(); s.item_slots.release(); s.rec_slots.release(); s.sums.release();
-  s.nrec.release(); s.rec_base.release(); s.rec_read.release(); s.read_bytes.release(); s.out_off.release(); s.blk_sums.release(); s.sam.release(); s.flags.release();
+  s.nrec.release(); s.rec_base.release(); s.rec_read.release(); s.rec_bytes.release(); s.rec_off.release(); s.sam_total.release(); s.blk_sums2.release(); s.blk_sums.release(); s.sam.release(); s.flags.release();
   s.csr_off.release(); s.csr_triples.release(); s.h_sam.release(); s.h_csr_off.release();
   s.h_matches.release(); s.h_small.release();
   if (s.ev0) cudaEventDestroy(s.ev0);
@@ -589,8 +593,9 @@ static int slot_prepare(smash_ctx *c, Slot &s, const smash_batch *b, bool copy) 
   if (s.cap == 0) s.cap = 24;
   if ((rc = s.match_slots.ensure(n * s.cap)) || (rc = s.match_cnt.ensure(n + 1)) || (rc = s.item_slots.ensure(n * s.cap)) ||
       (rc = s.rec_slots.ensure(n * s.cap)) || (rc = s.sums.ensure(n + 2)) || (rc = s.nrec.ensure(n + 1)) ||
-      (rc = s.rec_base.ensure(n + 2)) || (rc = s.rec_read.ensure(n * s.cap + 1)) || (rc = s.read_bytes.ensure(n + 1)) ||
-      (rc = s.out_off.ensure(n + 2)) || (rc = s.blk_sums.ensure(n / 2048 + 8)) || (rc = s.flags.ensure(N_FLAGS)) ||
+      (rc = s.rec_base.ensure(n + 2)) || (rc = s.rec_read.ensure(n * s.cap + 1)) || (rc = s.rec_bytes.ensure(n * s.cap + 1)) ||
+      (rc = s.rec_off.ensure(n * s.cap + 2)) || (rc = s.sam_total.ensure(2)) || (rc = s.blk_sums.ensure(n / 2048 + 8)) ||
+      (rc = s.blk_sums2.ensure(n * s.cap / 2048 + 8)) || (rc = s.flags.ensure(N_FLAGS)) ||
       (rc = s.h_small.ensure(32)))
     return rc;
   if (copy && n) {
@@ -615,7 +620,7 @@ static int slot_prepare(smash_ctx *c, Slot &s, const smash_batch *b, bool copy) 
 static WorkDev work_of(Slot &s) {
   WorkDev w{};
   w.cap = s.cap; w.match_slots = s.match_slots.p; w.match_cnt = s.match_cnt.p; w.item_slots = s.item_slots.p;
-  w.rec_slots = s.rec_slots.p; w.sums = s.sums.p; w.nrec = s.nrec.p; w.rec_base = s.rec_base.p; w.rec_read = s.rec_read.p; w.read_bytes = s.read_bytes.p; w.out_off = s.out_off.p;
+  w.rec_slots = s.rec_slots.p; w.sums = s.sums.p; w.nrec = s.nrec.p; w.rec_base = s.rec_base.p; w.rec_read = s.rec_read.p; w.rec_bytes = s.rec_bytes.p; w.rec_off = s.rec_off.p; w.sam_total = s.sam_total.p; w.blk_sums2 = s.blk_sums2.p;
   w.blk_sums = s.blk_sums.p; w.sam = s.sam.p; w.sam_cap = s.sam.cap; w.flags = s.flags.p;
   return w;
 }
@@ -642,10 +647,10 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
     MARK(1);
     c->launches += launch_sizes_scan(c->dix, s.bd, w, c->sp, s.st);
     MARK(2);
-    CU(cudaMemcpyAsync(s.h_small.p, s.out_off.p + n, 8, cudaMemcpyDeviceToHost, s.st));
+    CU(cudaMemcpyAsync(s.h_small.p, s.sam_total.p, 8, cudaMemcpyDeviceToHost, s.st));
     CU(cudaMemcpyAsync(s.h_small.p + 8, s.rec_base.p + n, 8, cudaMemcpyDeviceToHost, s.st));
     CU(cudaMemcpyAsync(s.h_small.p + 1, s.flags.p, sizeof(uint32_t) * N_FLAGS, cudaMemcpyDeviceToHost, s.st));
-    CU(cudaStreamSynchronize(s.st));
+    { const double ts = now_ms(); CU(cudaStreamSynchronize(s.st)); DBG_T("  run:sync for sizes", ts); }
     const uint32_t *fl = (const uint32_t *)(s.h_small.p + 1);
     if (fl[FLAG_LONGREAD]) return fail(SMASH_ERR_ARG, "%u reads longer than %d bases are not supported by this build", fl[FLAG_LONGREAD], MAXQ_FAST);
     if (fl[FLAG_OVERFLOW]) {
@@ -655,7 +660,8 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
       s.cap = (int)need + 8 > STAGE_CAP ? STAGE_CAP : (int)need + 8;
       int rc;
       if ((rc = s.match_slots.ensure(n * s.cap)) || (rc = s.item_slots.ensure(n * s.cap)) || (rc = s.rec_slots.ensure(n * s.cap)) ||
-          (rc = s.rec_read.ensure(n * s.cap + 1))) return rc;
+          (rc = s.rec_read.ensure(n * s.cap + 1)) || (rc = s.rec_bytes.ensure(n * s.cap + 1)) || (rc = s.rec_off.ensure(n * s.cap + 2)) ||
+          (rc = s.blk_sums2.ensure(n * s.cap / 2048 + 8))) return rc;
       continue;                                              // rerun the batch with wider slots
     }
     if (fl[FLAG_MAPERR] && ((want & SMASH_WANT_TAIL) || c->prm.tag_mappability))
@@ -687,7 +693,9 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
     CU(cudaMemcpyAsync(s.h_matches.p, s.csr_triples.p, 24 * n * (size_t)s.cap, cudaMemcpyDeviceToHost, s.st));
   }
   if (want & SMASH_WANT_TAIL) {
+    const double tt = now_ms();
     int rc = tail_accumulate(&c->tail, c->dix, s.bd, work_of(s), s.n_records, s.st, &c->launches);
+    DBG_T("  run:tail_accumulate", tt);
     if (rc) return fail(rc, "tail: %s", tail_error());
     MARK(5);
   }
@@ -722,9 +730,13 @@ extern "C" int smash_submit(smash_ctx *c, int slot, const smash_batch *b, int wa
   Slot &s = c->slot[slot];
   if (s.busy) return fail(SMASH_ERR_STATE, "slot %d still has a batch in flight", slot);
   CU(cudaSetDevice(c->device));
+  double t0 = now_ms();
   int rc = slot_prepare(c, s, b, true);
+  DBG_T("submit:prepare+h2d enqueue", t0);
   if (rc) return rc;
+  t0 = now_ms();
   rc = slot_run(c, s, want, true);
+  DBG_T("submit:run", t0);
   if (rc) return rc;
   s.busy = true;
   return 0;
@@ -732,7 +744,10 @@ extern "C" int smash_submit(smash_ctx *c, int slot, const smash_batch *b, int wa
 extern "C" int smash_wait(smash_ctx *c, int slot, smash_result *res) {
   if (!c || slot < 0 || slot >= SMASH_N_SLOTS) return fail(SMASH_ERR_ARG, "bad argument");
   CU(cudaSetDevice(c->device));
-  return slot_finish(c, c->slot[slot], res);
+  const double t0 = now_ms();
+  const int rc = slot_finish(c, c->slot[slot], res);
+  DBG_T("wait", t0);
+  return rc;
 }
 extern "C" int smash_map_batch(smash_ctx *c, const smash_batch *b, int want, smash_result *res) {
   int rc = smash_submit(c, 0, b, want);
@@ -805,7 +820,9 @@ extern "C" int smash_tail_finish(smash_ctx *c, int64_t *counts, void *counts_dev
   if (!c) return fail(SMASH_ERR_ARG, "null argument");
   CU(cudaSetDevice(c->device));
   for (int s = 0; s < SMASH_N_SLOTS; ++s) CU(cudaStreamSynchronize(c->slot[s].st));
+  const double tf = now_ms();
   int rc = tail_finish(&c->tail, counts, (int64_t *)counts_device, st, c->slot[0].st, &c->launches);
+  DBG_T("tail_finish", tf);
   if (rc) return fail(rc, "tail: %s", tail_error());
   return 0;
 }
@@ -813,6 +830,13 @@ extern "C" int smash_tail_positions(smash_ctx *c, const int32_t **chrom, const i
   if (!c || !chrom || !pos || !n) return fail(SMASH_ERR_ARG, "null argument");
   CU(cudaSetDevice(c->device));
   int rc = tail_positions(&c->tail, chrom, pos, n);
+  if (rc) return fail(rc, "tail: %s", tail_error());
+  return 0;
+}
+extern "C" int smash_tail_reserve(smash_ctx *c, uint64_t max_pairs, uint64_t max_hits) {
+  if (!c) return fail(SMASH_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  int rc = tail_reserve(&c->tail, max_pairs, max_hits, c->slot[0].st);
   if (rc) return fail(rc, "tail: %s", tail_error());
   return 0;
 }

@@ -209,77 +209,148 @@ int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, c
 }
 
 // ------------------------------------------------------------------ K3: records
+//
+// k_rec_build   one THREAD per read: resolve / erase / sort / merge / HI order (query.cpp:68-97,
+//               231-320) with the per-read scratch in thread-local arrays -- 32 reads advance per
+//               warp instead of one lane working while 31 wait.  (Reads with more than LOCAL_CAP
+//               matches only exist after a slot-capacity rerun; they take k_rec_build_serial.)
+// scan          nrec -> rec_base: every record gets a flat index
+// k_rec_xe      one warp per read, 8 lanes per record: XE (query.cpp:270-274) straight from the
+//               read and text words in HBM, L/R mappability of every '=' block, flat record -> read map
+constexpr int LOCAL_CAP = 24;
+
+__global__ void __launch_bounds__(128)
+k_rec_build(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
+  for (uint64_t read = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; read < b.n_reads; read += (uint64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(b.seq_off[read + 1] - b.seq_off[read]);
+    int n_in = (int)w.match_cnt[read];
+    if (n_in > w.cap) n_in = w.cap;
+    if (n_in > LOCAL_CAP) n_in = LOCAL_CAP;
+    Aln aln[LOCAL_CAP]; uint16_t ord[LOCAL_CAP];
+    ReadSum sum;
+    const int n_rec = build_records(ix, w.match_slots + read * (uint64_t)w.cap, n_in, q, sp.nomap, aln, ord,
+                                    w.item_slots + read * (uint64_t)w.cap, w.rec_slots + read * (uint64_t)w.cap, &sum);
+    w.sums[read] = sum;
+    w.nrec[read] = (uint32_t)n_rec;
+  }
+}
 
 struct RecSmem {
-  uint8_t pbuf[WARPS][PBUF];
   Aln aln[WARPS][SCR_CAP];
   uint16_t ord[WARPS][SCR_CAP];
-  int nrec[WARPS];
 };
-
 __global__ void __launch_bounds__(THREADS)
-k_records(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
+k_rec_build_serial(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
   __shared__ __align__(16) RecSmem sm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
   for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
-    const int64_t so = b.seq_off[read];
-    const int q = (int)(b.seq_off[read + 1] - so);
+    const int q = (int)(b.seq_off[read + 1] - b.seq_off[read]);
     int n_in = (int)w.match_cnt[read];
     if (n_in > w.cap) n_in = w.cap;
     if (n_in > SCR_CAP) n_in = SCR_CAP;
-    const int qs = q > MAXQ_FAST ? 0 : q;
-    stage_read(ix, b.seq + so, qs, sp.nucleotides_only, sm.pbuf[warp], lane);
-    const uint8_t *P = sm.pbuf[warp] + P_FRONT;
-    Item *items = w.item_slots + read * (uint64_t)w.cap;
-    Rec *recs = w.rec_slots + read * (uint64_t)w.cap;
     if (lane == 0) {
-      sm.nrec[warp] = build_records(ix, w.match_slots + read * (uint64_t)w.cap, n_in, q, sp.nomap,
-                                    sm.aln[warp], sm.ord[warp], items, recs, &w.sums[read]);
+      const int n_rec = build_records(ix, w.match_slots + read * (uint64_t)w.cap, n_in, q, sp.nomap, sm.aln[warp], sm.ord[warp],
+                                      w.item_slots + read * (uint64_t)w.cap, w.rec_slots + read * (uint64_t)w.cap, &w.sums[read]);
+      w.nrec[read] = (uint32_t)n_rec;
     }
     __syncwarp();
-    const int n_rec = sm.nrec[warp];
-    if (lane == 0) w.nrec[read] = (uint32_t)n_rec;
-    const bool unmapped = w.sums[read].unmapped;
-    if (!unmapped) {
-      for (int r = 0; r < n_rec; ++r) {                    // XE: all lanes, 8 read bytes each
+  }
+}
+
+// 8 bytes of the read at offset j (unaligned) with NewQuery::extend's tolower applied (A-Z only)
+__device__ __forceinline__ uint64_t read8_lower(const uint8_t *__restrict__ seq, int j) {
+  const uint8_t *p = seq + j;
+  const uint64_t *a = reinterpret_cast<const uint64_t *>(p - ((uintptr_t)p & 7));
+  const unsigned sh = (unsigned)((uintptr_t)p & 7) * 8u;
+  uint64_t x = __ldg(a);
+  if (sh) x = (x >> sh) | (__ldg(a + 1) << (64u - sh));
+  const uint64_t h = x & 0x7f7f7f7f7f7f7f7fULL;
+  const uint64_t ge_A = h + 0x3f3f3f3f3f3f3f3fULL, gt_Z = h + 0x2525252525252525ULL;
+  const uint64_t upper = ge_A & ~gt_Z & ~x & 0x8080808080808080ULL;
+  return x | (upper >> 2);
+}
+__device__ __forceinline__ int xe_word_g(const DevIndex &ix, const uint8_t *__restrict__ seq, int q, int64_t rcpos, int j0, int nuc) {
+  const int64_t rp = rcpos + j0;
+  if (!nuc && rp >= 0 && rp + 8 <= (int64_t)ix.N && j0 + 8 <= q) {
+    const uint64_t d = text8(ix.text, rp) ^ read8_lower(seq, j0);
+    uint64_t t = (d & 0x7f7f7f7f7f7f7f7fULL) + 0x7f7f7f7f7f7f7f7fULL;
+    t = ~(t | d | 0x7f7f7f7f7f7f7f7fULL);
+    return __popcll(t);
+  }
+  int cnt = 0;
+  for (int j = j0; j < j0 + 8 && j < q; ++j) {
+    const int64_t p = rcpos + j;
+    if (p >= 0 && p < (int64_t)ix.N && ix.text[p] == query_char(seq[j], nuc)) ++cnt;
+  }
+  return cnt;
+}
+
+__global__ void __launch_bounds__(THREADS)
+k_rec_xe(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane >> 3, sl = lane & 7;
+  const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
+  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
+    const int n_rec = (int)w.nrec[read];
+    if (!n_rec) continue;
+    const uint64_t fbase = w.rec_base[read];
+    for (int r = lane; r < n_rec; r += 32) w.rec_read[fbase + r] = (uint32_t)read;
+    if (w.sums[read].unmapped) continue;
+    const int64_t so = b.seq_off[read];
+    const int q = (int)(b.seq_off[read + 1] - so);
+    const uint8_t *seq = b.seq + so;
+    Item *items = w.item_slots + read * (uint64_t)w.cap;
+    Rec *recs = w.rec_slots + read * (uint64_t)w.cap;
+    for (int r0 = 0; r0 < n_rec; r0 += 4) {                 // 4 records per pass, 8 lanes each
+      const int r = r0 + sub;
+      int cnt = 0;
+      if (r < n_rec) {
         const int64_t rcpos = recs[r].rcpos;
-        int cnt = 0;
-        for (int j0 = lane * 8; j0 < q; j0 += 256) cnt += xe_word(ix, P, q, rcpos, j0);
-        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0) recs[r].xe = (uint16_t)cnt;
+        for (int j0 = sl * 8; j0 < q; j0 += 64) cnt += xe_word_g(ix, seq, q, rcpos, j0, sp.nucleotides_only);
       }
-      if (ix.mapbody) {                                    // L0/R0 + the tagger's range check
-        for (int r = lane; r < n_rec; r += 32) {
-          bool ok = true; int L0 = 0, R0 = 0;
-          for (int u = 0; u < recs[r].item_cnt; ++u) {
-            const Item it = items[recs[r].item_begin + u];
-            int L, R;
-            ok = map_lr(ix, recs[r].si >> 1, recs[r].pos, it.prefix, it.len, &L, &R) && ok;
-            if (u == 0) { L0 = L; R0 = R; }
-          }
-          recs[r].L0 = (uint8_t)L0; recs[r].R0 = (uint8_t)R0;
-          if (!ok) {
-            // mappability_tag.cpp:107-113 throws unless the chromosome is _gl000*/chrM
-            const char *nm = ix.descr + ix.descr_off[recs[r].si];
-            const int nl = ix.descr_off[recs[r].si + 1] - ix.descr_off[recs[r].si];
-            bool small = false;
-            for (int i = 0; i + 4 <= nl; ++i) if (nm[i] == 'c' && nm[i + 1] == 'h' && nm[i + 2] == 'r' && nm[i + 3] == 'M') small = true;
-            for (int i = 0; i + 6 <= nl; ++i) if (nm[i] == '_' && nm[i + 1] == 'g' && nm[i + 2] == 'l' && nm[i + 3] == '0' && nm[i + 4] == '0' && nm[i + 5] == '0') small = true;
-            if (!small) atomicAdd(&w.flags[FLAG_MAPERR], 1u);
-          }
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+      if (r < n_rec && sl == 0) recs[r].xe = (uint16_t)cnt;
+    }
+    if (ix.mapbody) {                                        // L0/R0 + the tagger's range check
+      for (int r = lane; r < n_rec; r += 32) {
+        bool ok = true; int L0 = 0, R0 = 0;
+        const Rec rr = recs[r];
+        for (int u = 0; u < rr.item_cnt; ++u) {
+          const Item it = items[rr.item_begin + u];
+          int L, R;
+          ok = map_lr(ix, rr.si >> 1, rr.pos, it.prefix, it.len, &L, &R) && ok;
+          if (u == 0) { L0 = L; R0 = R; }
+        }
+        recs[r].L0 = (uint8_t)L0; recs[r].R0 = (uint8_t)R0;
+        if (!ok) {
+          // mappability_tag.cpp:107-113 throws unless the chromosome is _gl000*/chrM
+          const char *nm = ix.descr + ix.descr_off[rr.si];
+          const int nl = ix.descr_off[rr.si + 1] - ix.descr_off[rr.si];
+          bool small = false;
+          for (int i = 0; i + 4 <= nl; ++i) if (nm[i] == 'c' && nm[i + 1] == 'h' && nm[i + 2] == 'r' && nm[i + 3] == 'M') small = true;
+          for (int i = 0; i + 6 <= nl; ++i) if (nm[i] == '_' && nm[i + 1] == 'g' && nm[i + 2] == 'l' && nm[i + 3] == '0' && nm[i + 4] == '0' && nm[i + 5] == '0') small = true;
+          if (!small) atomicAdd(&w.flags[FLAG_MAPERR], 1u);
         }
       }
     }
-    __syncwarp();
   }
 }
 
 static int exclusive_scan_u32(const uint32_t *in, uint64_t n, uint64_t *blk, uint64_t *out, cudaStream_t st);
 int launch_records(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
   if (!b.n_reads) return 0;
-  k_records<<<grid_for_warps(b.n_reads, 6), THREADS, 0, st>>>(ix, b, w, p);
-  return 1 + exclusive_scan_u32(w.nrec, b.n_reads, w.blk_sums, w.rec_base, st);
+  if (w.cap <= LOCAL_CAP) {
+    const uint64_t need = (b.n_reads + 127) / 128, cap = (uint64_t)sm_count() * 16;
+    k_rec_build<<<(unsigned)(need < cap ? need : cap), 128, 0, st>>>(ix, b, w, p);
+  } else {
+    k_rec_build_serial<<<grid_for_warps(b.n_reads, 6), THREADS, 0, st>>>(ix, b, w, p);
+  }
+  int n = 1 + exclusive_scan_u32(w.nrec, b.n_reads, w.blk_sums, w.rec_base, st);
+  k_rec_xe<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p);
+  return n + 1;
 }
 
 // ------------------------------------------------------------------ K4a: sizes + scan
@@ -299,36 +370,26 @@ __device__ __forceinline__ void read_mate(const BatchDev &b, const WorkDev &w, u
   }
 }
 
-__global__ void __launch_bounds__(THREADS)
+// One THREAD per record (flat index): exact byte length of its SAM line.
+__global__ void __launch_bounds__(128)
 k_sizes(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
-  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
+  const uint64_t n_records = w.rec_base[b.n_reads];
+  for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_records; f += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t read = w.rec_read[f];
+    const int r = (int)(f - w.rec_base[read]);
     const ReadSum me = w.sums[read];
-    const int n_rec = me.n_rec;
-    uint32_t bytes = 0;
-    if (n_rec) {
-      uint16_t flag; MateView mv;
-      read_mate(b, w, read, &flag, &mv);
-      const int q = (int)(b.seq_off[read + 1] - b.seq_off[read]);
-      const int name_len = (int)(b.name_off[read + 1] - b.name_off[read]);
-      const int opt_len = b.opt ? (int)(b.opt_off[read + 1] - b.opt_off[read]) : 0;
-      const Item *items = w.item_slots + read * (uint64_t)w.cap;
-      Rec *recs = w.rec_slots + read * (uint64_t)w.cap;
-      const uint64_t fbase = w.rec_base[read];
-      for (int r = lane; r < n_rec; r += 32) {             // one lane per record
-        CountSink cs;
-        put_head(cs, ix, (const char *)nullptr, name_len, flag, me.unmapped, recs[r], r, items, mv);
-        put_tags(cs, ix, me.unmapped, recs, r, n_rec, items);
-        if (sp.tag_mappability && !me.unmapped) put_lr_tags(cs, ix, recs[r], items);
-        const uint32_t nb = cs.n + 2u * (uint32_t)q + 1u /*tab between SEQ and QUAL*/ + (uint32_t)opt_len + 1u /*\n*/;
-        recs[r].bytes = nb;
-        w.rec_read[fbase + r] = (uint32_t)read;
-        bytes += nb;
-      }
-    }
-    for (int o = 16; o; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
-    if (lane == 0) w.read_bytes[read] = bytes;
+    uint16_t flag; MateView mv;
+    read_mate(b, w, read, &flag, &mv);
+    const int q = (int)(b.seq_off[read + 1] - b.seq_off[read]);
+    const int name_len = (int)(b.name_off[read + 1] - b.name_off[read]);
+    const int opt_len = b.opt ? (int)(b.opt_off[read + 1] - b.opt_off[read]) : 0;
+    const Item *items = w.item_slots + read * (uint64_t)w.cap;
+    const Rec *recs = w.rec_slots + read * (uint64_t)w.cap;
+    CountSink cs;
+    put_head(cs, ix, (const char *)nullptr, name_len, flag, me.unmapped, recs[r], r, items, mv);
+    put_tags(cs, ix, me.unmapped, recs, r, me.n_rec, items);
+    if (sp.tag_mappability && !me.unmapped) put_lr_tags(cs, ix, recs[r], items);
+    w.rec_bytes[f] = cs.n + 2u * (uint32_t)q + 1u /*tab between SEQ and QUAL*/ + (uint32_t)opt_len + 1u /*\n*/;
   }
 }
 
@@ -355,17 +416,19 @@ __device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t *t
   return r;
 }
 
-__global__ void k_scan_tiles(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ blk) {
+__global__ void k_scan_tiles(const uint32_t *__restrict__ in, uint64_t n, const uint64_t *__restrict__ n_dev, uint64_t *__restrict__ blk) {
   __shared__ uint64_t tot;
+  if (n_dev) { n = *n_dev; if ((uint64_t)blockIdx.x * SCAN_TILE >= n) return; }
   const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
   uint64_t s = 0;
   for (int i = 0; i < SCAN_ITEMS; ++i) if (base + i < n) s += in[base + i];
   block_exclusive_scan(s, &tot);
   if (threadIdx.x == 0) blk[blockIdx.x] = tot;
 }
-__global__ void k_scan_top(uint64_t *blk, uint64_t n_blk) {
+__global__ void k_scan_top(uint64_t *blk, uint64_t n_blk, const uint64_t *__restrict__ n_dev) {
   __shared__ uint64_t tot;
   __shared__ uint64_t carry;
+  if (n_dev) n_blk = (*n_dev + SCAN_TILE - 1) / SCAN_TILE;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   for (uint64_t b0 = 0; b0 < n_blk; b0 += SCAN_BLOCK) {
@@ -379,28 +442,45 @@ __global__ void k_scan_top(uint64_t *blk, uint64_t n_blk) {
   }
   if (threadIdx.x == 0) blk[n_blk] = carry;
 }
-__global__ void k_scan_apply(const uint32_t *__restrict__ in, uint64_t n, const uint64_t *__restrict__ blk,
-                             uint64_t *__restrict__ out) {
+__global__ void k_scan_apply(const uint32_t *__restrict__ in, uint64_t n, const uint64_t *__restrict__ n_dev,
+                             const uint64_t *__restrict__ blk, uint64_t *__restrict__ out, uint64_t *__restrict__ total_out) {
   __shared__ uint64_t tot;
+  uint64_t n_blk = gridDim.x;
+  if (n_dev) {
+    n = *n_dev; n_blk = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) { out[0] = 0; if (total_out) *total_out = 0; }
+    if (blockIdx.x >= n_blk) return;
+  }
   const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
   uint32_t v[SCAN_ITEMS]; uint64_t s = 0;
   for (int i = 0; i < SCAN_ITEMS; ++i) { v[i] = base + i < n ? in[base + i] : 0; s += v[i]; }
   uint64_t ex = block_exclusive_scan(s, &tot) + blk[blockIdx.x];
   for (int i = 0; i < SCAN_ITEMS; ++i) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = blk[gridDim.x];
+  if (blockIdx.x == n_blk - 1 && threadIdx.x == 0) { out[n] = blk[n_blk]; if (total_out) *total_out = blk[n_blk]; }
 }
 static int exclusive_scan_u32(const uint32_t *in, uint64_t n, uint64_t *blk, uint64_t *out, cudaStream_t st) {
   const uint64_t n_blk = (n + SCAN_TILE - 1) / SCAN_TILE;
-  k_scan_tiles<<<(unsigned)n_blk, SCAN_BLOCK, 0, st>>>(in, n, blk);
-  k_scan_top<<<1, SCAN_BLOCK, 0, st>>>(blk, n_blk);
-  k_scan_apply<<<(unsigned)n_blk, SCAN_BLOCK, 0, st>>>(in, n, blk, out);
+  k_scan_tiles<<<(unsigned)n_blk, SCAN_BLOCK, 0, st>>>(in, n, nullptr, blk);
+  k_scan_top<<<1, SCAN_BLOCK, 0, st>>>(blk, n_blk, nullptr);
+  k_scan_apply<<<(unsigned)n_blk, SCAN_BLOCK, 0, st>>>(in, n, nullptr, blk, out, nullptr);
+  return 3;
+}
+// same, but the element count lives in device memory (*n_dev <= n_bound): tiles past it exit at once
+static int exclusive_scan_u32_devn(const uint32_t *in, uint64_t n_bound, const uint64_t *n_dev, uint64_t *blk, uint64_t *out,
+                                   uint64_t *total_out, cudaStream_t st) {
+  const uint64_t n_blk = (n_bound + SCAN_TILE - 1) / SCAN_TILE;
+  k_scan_tiles<<<(unsigned)n_blk, SCAN_BLOCK, 0, st>>>(in, 0, n_dev, blk);
+  k_scan_top<<<1, SCAN_BLOCK, 0, st>>>(blk, 0, n_dev);
+  k_scan_apply<<<(unsigned)n_blk, SCAN_BLOCK, 0, st>>>(in, 0, n_dev, blk, out, total_out);
   return 3;
 }
 
 int launch_sizes_scan(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
   if (!b.n_reads) return 0;
-  k_sizes<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p);
-  return 1 + exclusive_scan_u32(w.read_bytes, b.n_reads, w.blk_sums, w.out_off, st);
+  k_sizes<<<sm_count() * 16, 128, 0, st>>>(ix, b, w, p);
+  // rec_off = exclusive scan of rec_bytes over the (device-side) record count; total -> sam_total[0]
+  return 1 + exclusive_scan_u32_devn(w.rec_bytes, b.n_reads * (uint64_t)w.cap, w.rec_base + b.n_reads, w.blk_sums2, w.rec_off,
+                                     w.sam_total, st);
 }
 
 // ------------------------------------------------------------------ K4b: emit
@@ -411,8 +491,8 @@ int launch_sizes_scan(const DevIndex &ix, const BatchDev &b, const WorkDev &w, c
 // whole warp per record: name, head, SEQ, QUAL, tags, optional fields, L/R tags and the newline
 // are streamed to the line's place in the output with coalesced byte copies.
 constexpr int EWARPS = 4;
-constexpr int HEAD_CAP = 128;
-constexpr int TAIL_CAP = 416;
+constexpr int HEAD_CAP = 96;
+constexpr int TAIL_CAP = 320;
 
 struct EmitRec {           // what phase 2 needs, one per lane, exchanged with shuffles
   unsigned long long out, name, seq, qual, opt;
@@ -438,9 +518,7 @@ k_emit(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp, uint64_t n_records) 
       const int64_t so = b.seq_off[read];
       const Item *items = w.item_slots + read * (uint64_t)w.cap;
       const Rec *recs = w.rec_slots + read * (uint64_t)w.cap;
-      uint64_t off = w.out_off[read];
-      for (int r = 0; r < hi; ++r) off += recs[r].bytes;
-      e.out = (unsigned long long)(w.sam + off);
+      e.out = (unsigned long long)(w.sam + w.rec_off[f]);
       e.name = (unsigned long long)(b.names + b.name_off[read]);
       e.name_len = (int)(b.name_off[read + 1] - b.name_off[read]);
       e.seq = (unsigned long long)(b.seq + so); e.qual = (unsigned long long)(b.qual + so);

@@ -26,9 +26,11 @@ struct WorkDev {
   uint32_t *nrec;              // n_reads: records printed for the read
   uint64_t *rec_base;          // n_reads + 1: exclusive scan of nrec (flat record index)
   uint32_t *rec_read;          // per flat record: its read
-  uint32_t *read_bytes;        // n_reads: SAM bytes of the read's records
-  uint64_t *out_off;           // n_reads + 1 (exclusive scan of read_bytes)
-  uint64_t *blk_sums;          // scan scratch
+  uint32_t *rec_bytes;         // per flat record: bytes of its SAM line
+  uint64_t *rec_off;           // per flat record (+1): exclusive scan of rec_bytes = offset in `sam`
+  uint64_t *sam_total;         // [0] = total SAM bytes of the batch
+  uint64_t *blk_sums;          // scan scratch (n_reads / 2048 + 8)
+  uint64_t *blk_sums2;         // scan scratch (n_reads * cap / 2048 + 8)
   char *sam;                   // output text
   uint64_t sam_cap;
   uint32_t *flags;             // N_FLAGS counters

@@ -16,6 +16,12 @@
 #include <vector>
 
 #include "tail.cuh"
+#include <chrono>
+#include <stdlib.h>
+static const bool t_dbg = getenv("SMASH_DEBUG_TIMING") != nullptr;
+static const bool t_dbg_sync = getenv("SMASH_DEBUG_TIMING") && atoi(getenv("SMASH_DEBUG_TIMING")) >= 2;
+static double t_now() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define TDBG(label) do { if (t_dbg) { if (t_dbg_sync) cudaStreamSynchronize(st); fprintf(stderr, "[smash-dbg]    finish:%-20s %8.3f ms\n", label, t_now() - tq); tq = t_now(); } } while (0)
 
 namespace smash {
 
@@ -42,12 +48,14 @@ template <class T> int DGrow<T>::reserve(size_t n, size_t used, cudaStream_t st)
   return 0;
 }
 template struct DGrow<uint32_t>;
+template struct DGrow<uint8_t>;
 template struct DGrow<uint64_t>;
 
 void tail_init(TailState *) {}
 void tail_reset(TailState *t) { t->n_pairs = 0; t->n_hits_bound = 0; t->n_positions = 0; if (t->d_nhits) cudaMemset(t->d_nhits, 0, 8); }
 void tail_release(TailState *t) {
   t->pair_nhits.release(); t->pair_fp.release(); t->pair_hit_off.release(); t->hits.release();
+  for (auto &b : t->scr) b.release();
   void *d[] = {t->bin_starts, t->chrom_off, t->batch_cnt, t->batch_off, t->blk, t->counts, t->pos_chrom, t->pos_pos, t->d_nhits};
   for (void *p : d) if (p) cudaFree(p);
   if (t->h_pos_chrom) cudaFreeHost(t->h_pos_chrom);
@@ -210,15 +218,23 @@ __global__ void k_dd_insert(const uint32_t *__restrict__ nhits, const uint64_t *
 __global__ void k_dd_resolve(const uint32_t *__restrict__ nhits, const uint64_t *__restrict__ hit_off,
                              const uint64_t *__restrict__ hits, uint64_t n_pairs, const uint32_t *__restrict__ minidx,
                              const uint32_t *__restrict__ slot_of, uint8_t *__restrict__ keep, uint64_t *stats /*[0]=dupes,[1]=nondupes,[2]=unresolved*/) {
+  unsigned dup = 0, non = 0, unres = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t n = nhits[i];
     if (!n) { keep[i] = 0; continue; }
     const uint32_t j = minidx[slot_of[i]];
-    if (j == (uint32_t)i) { keep[i] = 1; atomicAdd((unsigned long long *)&stats[1], 1ull); continue; }
+    if (j == (uint32_t)i) { keep[i] = 1; ++non; continue; }
     bool same = nhits[j] == n;
     for (uint32_t k = 0; same && k < n; ++k) same = hits[hit_off[j] + k] == hits[hit_off[i] + k];
-    if (same) { keep[i] = 0; atomicAdd((unsigned long long *)&stats[0], 1ull); }
-    else { keep[i] = 0; atomicAdd((unsigned long long *)&stats[2], 1ull); }
+    keep[i] = 0;
+    if (same) ++dup; else ++unres;
+  }
+  // one atomic per warp and counter instead of one per pair
+  dup = __reduce_add_sync(0xffffffffu, dup); non = __reduce_add_sync(0xffffffffu, non); unres = __reduce_add_sync(0xffffffffu, unres);
+  if ((threadIdx.x & 31) == 0) {
+    if (dup) atomicAdd((unsigned long long *)&stats[0], (unsigned long long)dup);
+    if (non) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)non);
+    if (unres) atomicAdd((unsigned long long *)&stats[2], (unsigned long long)unres);
   }
 }
 // per surviving pair: how many hits pass the regex (positions.txt) / varbin's chromosome filters
@@ -290,6 +306,7 @@ int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smas
                 cudaStream_t st, uint64_t *launches) {
   if (!t->configured) return tfail(SMASH_ERR_STATE, "smash_tail_configure has not been called");
   const uint64_t P = t->n_pairs;
+  double tq = t_now();
   TCU(cudaMemsetAsync(t->counts, 0, 8 * t->n_bins, st));
   smash_tail_stats s{};
   uint64_t h_stats[4] = {0, 0, 0, 0};
@@ -297,14 +314,20 @@ int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smas
   if (P) {
     if (P >= 0xffffffffull) return tfail(SMASH_ERR_ARG, "too many pairs for one tail pass");
     uint64_t tsize = 1024; while (tsize < 2 * P) tsize <<= 1;
-    uint64_t *keys = nullptr, *d_stats = nullptr, *o_pos = nullptr, *o_bin = nullptr, *blk = nullptr;
-    uint32_t *minidx = nullptr, *slot_of = nullptr, *c_pos = nullptr, *c_bin = nullptr; uint8_t *keep = nullptr;
+    // persistent scratch (grown on demand, never freed per call: cudaMalloc/cudaFree cost milliseconds)
+    int rcs;
+    if ((rcs = t->scr[0].reserve(8 * tsize, 0, st)) || (rcs = t->scr[1].reserve(4 * tsize, 0, st)) || (rcs = t->scr[2].reserve(4 * P, 0, st)) ||
+        (rcs = t->scr[3].reserve(P, 0, st)) || (rcs = t->scr[4].reserve(64, 0, st)) || (rcs = t->scr[5].reserve(4 * P, 0, st)) ||
+        (rcs = t->scr[6].reserve(4 * P, 0, st)) || (rcs = t->scr[7].reserve(8 * (P + 1), 0, st)) || (rcs = t->scr[8].reserve(8 * (P + 1), 0, st)) ||
+        (rcs = t->scr[9].reserve(8 * (P / 2048 + 8), 0, st)))
+      return rcs;
+    uint64_t *keys = (uint64_t *)t->scr[0].p, *d_stats = (uint64_t *)t->scr[4].p, *o_pos = (uint64_t *)t->scr[7].p,
+             *o_bin = (uint64_t *)t->scr[8].p, *blk = (uint64_t *)t->scr[9].p;
+    uint32_t *minidx = (uint32_t *)t->scr[1].p, *slot_of = (uint32_t *)t->scr[2].p, *c_pos = (uint32_t *)t->scr[5].p,
+             *c_bin = (uint32_t *)t->scr[6].p;
+    uint8_t *keep = (uint8_t *)t->scr[3].p;
     int64_t *f_pos = nullptr, *f_abs = nullptr;
-    TCU(cudaMalloc((void **)&keys, 8 * tsize)); TCU(cudaMalloc((void **)&minidx, 4 * tsize));
-    TCU(cudaMalloc((void **)&slot_of, 4 * P)); TCU(cudaMalloc((void **)&keep, P)); TCU(cudaMalloc((void **)&d_stats, 32));
-    TCU(cudaMalloc((void **)&c_pos, 4 * P)); TCU(cudaMalloc((void **)&c_bin, 4 * P));
-    TCU(cudaMalloc((void **)&o_pos, 8 * (P + 1))); TCU(cudaMalloc((void **)&o_bin, 8 * (P + 1)));
-    TCU(cudaMalloc((void **)&blk, 8 * (P / 2048 + 8)));
+    TDBG("mallocs");
     const int grid = (int)((P + 255) / 256 < 148 * 8 ? (P + 255) / 256 : 148 * 8);
     for (uint64_t seed = 1;; ++seed) {
       TCU(cudaMemsetAsync(keys, 0xff, 8 * tsize, st)); TCU(cudaMemsetAsync(minidx, 0xff, 4 * tsize, st));
@@ -317,6 +340,7 @@ int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smas
       if (h_stats[2] == 0) break;                            // a 64-bit table-key collision: re-key
       if (seed > 8) return tfail(SMASH_ERR_DATA, "duplicate-key table could not be resolved");
     }
+    TDBG("dedupe");
     k_pair_out_count<<<grid, 256, 0, st>>>(t->pair_nhits.p, t->pair_hit_off.p, t->hits.p, keep, P, t->chrom_off, c_pos, c_bin);
     *launches += 1 + exclusive_scan_u32_public(c_pos, P, blk, o_pos, st);
     *launches += exclusive_scan_u32_public(c_bin, P, blk, o_bin, st);
@@ -329,10 +353,13 @@ int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smas
       t->pos_cap = n_pos + 1024;
       TCU(cudaMalloc((void **)&t->pos_chrom, 4 * t->pos_cap)); TCU(cudaMalloc((void **)&t->pos_pos, 8 * t->pos_cap));
     }
-    TCU(cudaMalloc((void **)&f_pos, 8 * (n_f + 1))); TCU(cudaMalloc((void **)&f_abs, 8 * (n_f + 1)));
+    TDBG("out_count+scans");
+    if ((rcs = t->scr[10].reserve(8 * (n_f + 1), 0, st)) || (rcs = t->scr[11].reserve(8 * (n_f + 1), 0, st))) return rcs;
+    f_pos = (int64_t *)t->scr[10].p; f_abs = (int64_t *)t->scr[11].p;
     k_pair_out_write<<<grid, 256, 0, st>>>(t->pair_nhits.p, t->pair_hit_off.p, t->hits.p, keep, P, t->chrom_off, o_pos, o_bin,
                                            t->pos_chrom, t->pos_pos, f_pos, f_abs);
     *launches += 1;
+    TDBG("out_write");
     if (n_f) {
       const size_t smem = 4 * t->n_bins;
       const int vgrid = (int)((n_f + 255) / 256 < 148 * 2 ? (n_f + 255) / 256 : 148 * 2);
@@ -345,11 +372,11 @@ int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smas
       }
       *launches += 1;
     }
+    TDBG("varbin");
     TCU(cudaMemcpyAsync(h_stats, d_stats, 32, cudaMemcpyDeviceToHost, st));
     TCU(cudaStreamSynchronize(st));
     TCU(cudaGetLastError());
-    void *fr[] = {keys, minidx, slot_of, keep, d_stats, c_pos, c_bin, o_pos, o_bin, blk, f_pos, f_abs};
-    for (void *p : fr) cudaFree(p);
+    TDBG("frees");
   }
   t->n_positions = n_pos;
   s.n_dupe_pairs = h_stats[0]; s.n_non_dupe_pairs = h_stats[1];
@@ -358,6 +385,26 @@ int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smas
   if (counts_host) TCU(cudaMemcpyAsync(counts_host, t->counts, 8 * t->n_bins, cudaMemcpyDeviceToHost, st));
   TCU(cudaStreamSynchronize(st));
   if (stats) *stats = s;
+  return 0;
+}
+
+// Capacity hint: allocate everything tail_accumulate / tail_finish will need for `pairs` read pairs
+// and `hits` kept hits, so that no cudaMalloc/cudaFree happens later (they cost milliseconds each).
+int tail_reserve(TailState *t, uint64_t pairs, uint64_t hits, cudaStream_t st) {
+  int rc;
+  if ((rc = t->pair_nhits.reserve(pairs, t->n_pairs, st)) || (rc = t->pair_fp.reserve(2 * pairs, 2 * t->n_pairs, st)) ||
+      (rc = t->pair_hit_off.reserve(pairs, t->n_pairs, st)) || (rc = t->hits.reserve(hits + 1, t->n_hits_bound, st)))
+    return rc;
+  uint64_t tsize = 1024; while (tsize < 2 * pairs) tsize <<= 1;
+  const size_t want[12] = {8 * tsize, 4 * tsize, 4 * pairs, pairs, 64, 4 * pairs, 4 * pairs, 8 * (pairs + 1), 8 * (pairs + 1),
+                           8 * (pairs / 2048 + 8), 8 * (hits + 1), 8 * (hits + 1)};
+  for (int i = 0; i < 12; ++i) if ((rc = t->scr[i].reserve(want[i], 0, st))) return rc;
+  if (hits + 1 > t->pos_cap) {
+    if (t->pos_chrom) cudaFree(t->pos_chrom);
+    if (t->pos_pos) cudaFree(t->pos_pos);
+    t->pos_cap = hits + 1024;
+    TCU(cudaMalloc((void **)&t->pos_chrom, 4 * t->pos_cap)); TCU(cudaMalloc((void **)&t->pos_pos, 8 * t->pos_cap));
+  }
   return 0;
 }
 

@@ -27,6 +27,7 @@ struct TailState {
   DGrow<uint64_t> pair_hit_off;     // first hit of the pair in `hits`
   DGrow<uint64_t> hits;             // tid << 40 | 0-based pos, r1 hits in HI order then r2 hits
   // scratch
+  DGrow<uint8_t> scr[12];           // tail_finish work buffers (persistent)
   uint32_t *batch_cnt = nullptr; uint64_t *batch_off = nullptr; uint64_t *blk = nullptr; size_t batch_cap = 0;
   // results of finish
   int64_t *counts = nullptr;        // n_bins
@@ -44,6 +45,7 @@ int tail_accumulate(TailState *t, const DevIndex &ix, const BatchDev &b, const W
                     uint64_t n_records_bound, cudaStream_t st, uint64_t *launches);
 int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smash_tail_stats *stats,
                 cudaStream_t st, uint64_t *launches);
+int tail_reserve(TailState *t, uint64_t pairs, uint64_t hits, cudaStream_t st);
 int tail_positions(TailState *t, const int32_t **chrom, const int64_t **pos, uint64_t *n);
 
 }  // namespace smash
