@@ -79,6 +79,18 @@ def read_flag_of(batch):
     return np.where(fl & 64, 65, np.where(fl & 128, 129, 0)).astype(np.uint16)
 
 
+def slice_batch(b, lo, hi):
+    """Reads [lo,hi) of a batch (lo even keeps mates together)."""
+    def cut(blob, off):
+        return blob[off[lo]:off[hi]], (off[lo:hi + 1] - off[lo]).astype(np.int64)
+    nb, no = cut(b.names, b.name_off); sb, so = cut(b.seq, b.seq_off); qb, _ = cut(b.qual, b.seq_off)
+    ob, oo = cut(b.opt, b.opt_off) if b.opt.size else (b.opt, np.zeros(hi - lo + 1, dtype=np.int64))
+    out = ReadBatch(names=np.ascontiguousarray(nb), name_off=no, seq=np.ascontiguousarray(sb), qual=np.ascontiguousarray(qb),
+                    seq_off=so, flags=b.flags[lo:hi].copy(), opt=np.ascontiguousarray(ob), opt_off=oo)
+    out.read_flag = np.ascontiguousarray(read_flag_of(b)[lo:hi])
+    return out
+
+
 def write_mapout(header: bytes, sam: bytes, directory="mapout", tag="b200", seq=1):
     """mapout/mapout<id>.<k>.txt = header + records (query.cpp:453-463)."""
     os.makedirs(directory, exist_ok=True)
