@@ -24,7 +24,7 @@ struct Rec {
   uint16_t item_begin, item_cnt;   // CIGAR items (merge order) in the read's item slots
   uint16_t xu, xe, qlen, suffix;   // qlen = read length minus soft clips (pysam qlen)
   uint8_t rc, L0, R0, flags;       // L0/R0: mappability_tag values of the first '=' block
-  uint32_t bytes;                  // length of this record's SAM line (set by k_sizes)
+  uint16_t seq_off, lr_len;        // offset of the SEQ column in the line, length of the L/R tags (set by k_sizes)
 };
 struct Item { uint16_t prefix, len; };
 
@@ -215,14 +215,14 @@ HDN inline int build_records(const DevIndex &ix, const Match *matches, int n_in,
       const int endq = items[last_item].prefix + items[last_item].len;
       r.suffix = (uint16_t)(q - endq);
       r.qlen = (uint16_t)(endq - lead);
-      r.L0 = 0; r.R0 = 0; r.flags = 0; r.bytes = 0;
+      r.L0 = 0; r.R0 = 0; r.flags = 0; r.seq_off = 0; r.lr_len = 0;
       recs[n_rec++] = r;
     }
   }
   if (n_rec == 0 && nomap) {                          // set_nomap
     sum->unmapped = 1; n_rec = 1;
     Rec r; r.pos = 0; r.rcpos = 0; r.si = 0; r.rc = 0; r.item_begin = 0; r.item_cnt = 0;
-    r.xu = 0; r.xe = 0; r.qlen = 0; r.suffix = 0; r.L0 = 0; r.R0 = 0; r.flags = 0; r.bytes = 0;
+    r.xu = 0; r.xe = 0; r.qlen = 0; r.suffix = 0; r.L0 = 0; r.R0 = 0; r.flags = 0; r.seq_off = 0; r.lr_len = 0;
     recs[0] = r;
   }
   sum->n_rec = (uint16_t)n_rec;
