@@ -157,6 +157,23 @@ typedef struct {
 /* counts: n_bins int64 (this rank's counts; the caller allreduces across GPUs).  If
  * counts_device != NULL the counts are also left in that device buffer (for NCCL). */
 int smash_tail_finish(smash_ctx *ctx, int64_t *counts, void *counts_device, smash_tail_stats *st);
+/* ---- read-sharded multi-GPU tail (one context per rank; the host moves the small arrays with
+ * NCCL/gloo, see smash_paper_b200/multigpu.py).  Ranks hold contiguous ranges of pairs; rank r's pair
+ * i has the global ordinal ordinal_base + i.
+ *  1. smash_tail_export_keys: device array of {fp1, fp2, ordinal} (3 x u64) for this rank's pairs that
+ *     reach smashMEM's dupe set, sorted by ordinal.  The host all-gathers them.
+ *  2. smash_tail_phase_a with the concatenated keys of the LOWER ranks (device pointer): global
+ *     first-wins duplicate removal (smashMEM.py:217-228) + ordered compaction; returns the shard edge.
+ *  3. the host all-gathers the edges; smash_tail_phase_b gets the last filtered position of the
+ *     nearest lower rank that has one (varbin.py:56-58 compares with the previous kept line).
+ *  4. the host all-reduces the counts and the stats.
+ * smash_tail_finish == phase_a(no foreign keys) + phase_b(no predecessor). */
+typedef struct { uint64_t n_filtered; int64_t first_pos, last_pos; } smash_tail_edge;
+int smash_tail_export_keys(smash_ctx *ctx, uint64_t ordinal_base, const void **dev_keys, uint64_t *n_keys);
+int smash_tail_phase_a(smash_ctx *ctx, uint64_t ordinal_base, const void *foreign_keys_dev, uint64_t n_foreign,
+                       smash_tail_edge *edge);
+int smash_tail_phase_b(smash_ctx *ctx, int has_prev, int64_t prev_last_pos, int64_t *counts, void *counts_device,
+                       smash_tail_stats *st);
 /* positions.txt rows produced so far by smash_tail_finish: chromosome index (into the forward
  * sequences) and 0-based position, in output order. */
 int smash_tail_positions(smash_ctx *ctx, const int32_t **chrom, const int64_t **pos, uint64_t *n);
@@ -165,6 +182,10 @@ int smash_tail_positions(smash_ctx *ctx, const int32_t **chrom, const int64_t **
 int smash_tail_reserve(smash_ctx *ctx, uint64_t max_pairs, uint64_t max_hits);
 /* Forget everything accumulated so far (buffers are kept). */
 int smash_tail_reset(smash_ctx *ctx);
+
+/* cudaMemcpy(cudaMemcpyDefault): lets a host language move the small exchange arrays of the multi-GPU
+ * tail between library-owned device memory and its own (e.g. torch) tensors. */
+int smash_memcpy(void *dst, const void *src, size_t bytes);
 
 /* ---- counters for bench.py: kernels launched by this library since ctx creation */
 uint64_t smash_ctx_launch_count(const smash_ctx *ctx);

@@ -45,6 +45,10 @@ class _TailStats(C.Structure):
                 ("n_dupe_pairs", C.c_uint64), ("n_non_dupe_pairs", C.c_uint64), ("n_positions", C.c_uint64)]
 
 
+class _TailEdge(C.Structure):
+    _fields_ = [("n_filtered", C.c_uint64), ("first_pos", C.c_int64), ("last_pos", C.c_int64)]
+
+
 _lib = None
 
 
@@ -77,6 +81,11 @@ def _check(rc):
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+def memcpy(dst_ptr, src_ptr, nbytes):
+    """cudaMemcpyDefault between any two pointers (host or device)."""
+    _check(load_library().smash_memcpy(C.c_void_p(dst_ptr), C.c_void_p(src_ptr), C.c_size_t(nbytes)))
 
 
 def device_count():
@@ -327,6 +336,26 @@ class Context:
             return np.zeros(0, np.int32), np.zeros(0, np.int64)
         return (np.ctypeslib.as_array(C.cast(c, C.POINTER(C.c_int32)), shape=(m,)).copy(),
                 np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int64)), shape=(m,)).copy())
+
+    # -- read-sharded multi-GPU tail (see multigpu.py) -----------------------------------------
+    def tail_export_keys(self, ordinal_base):
+        """-> (device pointer, n): {fp1, fp2, ordinal} u64 triples of this rank's dupe-set pairs."""
+        ptr, n = C.c_void_p(), C.c_uint64()
+        _check(load_library().smash_tail_export_keys(self.h, C.c_uint64(ordinal_base), C.byref(ptr), C.byref(n)))
+        return ptr.value, int(n.value)
+
+    def tail_phase_a(self, ordinal_base, foreign_ptr=None, n_foreign=0):
+        e = _TailEdge()
+        _check(load_library().smash_tail_phase_a(self.h, C.c_uint64(ordinal_base), C.c_void_p(foreign_ptr) if n_foreign else None,
+                                                 C.c_uint64(n_foreign), C.byref(e)))
+        return int(e.n_filtered), int(e.first_pos), int(e.last_pos)
+
+    def tail_phase_b(self, has_prev=False, prev_last_pos=0, counts_device_ptr=None):
+        counts = np.zeros(self.n_bins, dtype=np.int64)
+        st = _TailStats()
+        _check(load_library().smash_tail_phase_b(self.h, int(bool(has_prev)), C.c_int64(prev_last_pos), _ptr(counts),
+                                                 C.c_void_p(counts_device_ptr) if counts_device_ptr else None, C.byref(st)))
+        return counts, {k: int(getattr(st, k)) for k, _ in _TailStats._fields_}
 
     def tail_reserve(self, max_pairs, max_hits):
         _check(load_library().smash_tail_reserve(self.h, C.c_uint64(max_pairs), C.c_uint64(max_hits)))

@@ -826,6 +826,33 @@ extern "C" int smash_tail_finish(smash_ctx *c, int64_t *counts, void *counts_dev
   if (rc) return fail(rc, "tail: %s", tail_error());
   return 0;
 }
+extern "C" int smash_tail_export_keys(smash_ctx *c, uint64_t ordinal_base, const void **dev_keys, uint64_t *n_keys) {
+  if (!c || !dev_keys || !n_keys) return fail(SMASH_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  for (int s = 0; s < SMASH_N_SLOTS; ++s) CU(cudaStreamSynchronize(c->slot[s].st));
+  const uint64_t *k = nullptr;
+  int rc = tail_export_keys(&c->tail, ordinal_base, &k, n_keys, c->slot[0].st, &c->launches);
+  if (rc) return fail(rc, "tail: %s", tail_error());
+  *dev_keys = k;
+  return 0;
+}
+extern "C" int smash_tail_phase_a(smash_ctx *c, uint64_t ordinal_base, const void *foreign_keys_dev, uint64_t n_foreign,
+                                  smash_tail_edge *edge) {
+  if (!c) return fail(SMASH_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  for (int s = 0; s < SMASH_N_SLOTS; ++s) CU(cudaStreamSynchronize(c->slot[s].st));
+  int rc = tail_phase_a(&c->tail, ordinal_base, (const uint64_t *)foreign_keys_dev, n_foreign, edge, c->slot[0].st, &c->launches);
+  if (rc) return fail(rc, "tail: %s", tail_error());
+  return 0;
+}
+extern "C" int smash_tail_phase_b(smash_ctx *c, int has_prev, int64_t prev_last_pos, int64_t *counts, void *counts_device,
+                                  smash_tail_stats *st) {
+  if (!c) return fail(SMASH_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  int rc = tail_phase_b(&c->tail, has_prev, prev_last_pos, counts, (int64_t *)counts_device, st, c->slot[0].st, &c->launches);
+  if (rc) return fail(rc, "tail: %s", tail_error());
+  return 0;
+}
 extern "C" int smash_tail_positions(smash_ctx *c, const int32_t **chrom, const int64_t **pos, uint64_t *n) {
   if (!c || !chrom || !pos || !n) return fail(SMASH_ERR_ARG, "null argument");
   CU(cudaSetDevice(c->device));
@@ -847,6 +874,11 @@ extern "C" int smash_tail_reset(smash_ctx *c) {
   return 0;
 }
 
+extern "C" int smash_memcpy(void *dst, const void *src, size_t bytes) {
+  if (!bytes) return 0;
+  CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));       // UVA: any of host/device on either side
+  return 0;
+}
 extern "C" uint64_t smash_ctx_launch_count(const smash_ctx *c) { return c ? c->launches : 0; }
 extern "C" void smash_ctx_stage_ms(smash_ctx *c, double *out, int reset) {
   if (!c) return;

@@ -56,6 +56,7 @@ void tail_reset(TailState *t) { t->n_pairs = 0; t->n_hits_bound = 0; t->n_positi
 void tail_release(TailState *t) {
   t->pair_nhits.release(); t->pair_fp.release(); t->pair_hit_off.release(); t->hits.release();
   for (auto &b : t->scr) b.release();
+  t->exp_keys.release();
   void *d[] = {t->bin_starts, t->chrom_off, t->batch_cnt, t->batch_off, t->blk, t->counts, t->pos_chrom, t->pos_pos, t->d_nhits};
   for (void *p : d) if (p) cudaFree(p);
   if (t->h_pos_chrom) cudaFreeHost(t->h_pos_chrom);
@@ -198,34 +199,57 @@ int tail_accumulate(TailState *t, const DevIndex &ix, const BatchDev &b, const W
 
 constexpr uint64_t EMPTY_KEY = 0xffffffffffffffffULL;
 
-__global__ void k_dd_insert(const uint32_t *__restrict__ nhits, const uint64_t *__restrict__ fp, uint64_t n_pairs,
-                            uint64_t seed, uint64_t *keys, uint32_t *minidx, uint64_t mask, uint32_t *__restrict__ slot_of) {
+// Table value = smallest GLOBAL pair ordinal with this key.  Local pair i has ordinal base + i;
+// foreign keys (other ranks' pairs, {fp1, fp2, ordinal} triples sorted by ordinal) are inserted too.
+__device__ __forceinline__ uint64_t table_key(uint64_t fp1, uint64_t fp2, uint64_t seed) {
+  uint64_t h = mix64(fp1 ^ mix64(fp2 + seed));
+  return h == EMPTY_KEY ? 0 : h;
+}
+__device__ __forceinline__ uint64_t table_claim(uint64_t *keys, uint64_t mask, uint64_t h) {
+  uint64_t s = h & mask;
+  for (;;) {
+    const uint64_t prev = atomicCAS((unsigned long long *)&keys[s], (unsigned long long)EMPTY_KEY, (unsigned long long)h);
+    if (prev == EMPTY_KEY || prev == h) return s;
+    s = (s + 1) & mask;
+  }
+}
+__global__ void k_dd_insert(const uint32_t *__restrict__ nhits, const uint64_t *__restrict__ fp, uint64_t n_pairs, uint64_t base,
+                            uint64_t seed, uint64_t *keys, unsigned long long *minord, uint64_t mask, uint32_t *__restrict__ slot_of) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t)gridDim.x * blockDim.x) {
     if (!nhits[i]) continue;
-    uint64_t h = mix64(fp[2 * i] ^ mix64(fp[2 * i + 1] + seed));
-    if (h == EMPTY_KEY) h = 0;
-    uint64_t s = h & mask;
-    for (;;) {
-      const uint64_t prev = atomicCAS((unsigned long long *)&keys[s], (unsigned long long)EMPTY_KEY, (unsigned long long)h);
-      if (prev == EMPTY_KEY || prev == h) break;
-      s = (s + 1) & mask;
-    }
-    atomicMin(&minidx[s], (uint32_t)i);
+    const uint64_t s = table_claim(keys, mask, table_key(fp[2 * i], fp[2 * i + 1], seed));
+    atomicMin(&minord[s], (unsigned long long)(base + i));
     slot_of[i] = (uint32_t)s;
   }
 }
+__global__ void k_dd_insert_foreign(const uint64_t *__restrict__ fk, uint64_t n, uint64_t seed, uint64_t *keys,
+                                    unsigned long long *minord, uint64_t mask) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t s = table_claim(keys, mask, table_key(fk[3 * i], fk[3 * i + 1], seed));
+    atomicMin(&minord[s], (unsigned long long)fk[3 * i + 2]);
+  }
+}
 // keep[i] = 1 first occurrence of its key, 0 empty or duplicate (smashMEM.py:217-228)
-__global__ void k_dd_resolve(const uint32_t *__restrict__ nhits, const uint64_t *__restrict__ hit_off,
-                             const uint64_t *__restrict__ hits, uint64_t n_pairs, const uint32_t *__restrict__ minidx,
-                             const uint32_t *__restrict__ slot_of, uint8_t *__restrict__ keep, uint64_t *stats /*[0]=dupes,[1]=nondupes,[2]=unresolved*/) {
+__global__ void k_dd_resolve(const uint32_t *__restrict__ nhits, const uint64_t *__restrict__ fp, const uint64_t *__restrict__ hit_off,
+                             const uint64_t *__restrict__ hits, uint64_t n_pairs, uint64_t base, const unsigned long long *__restrict__ minord,
+                             const uint32_t *__restrict__ slot_of, const uint64_t *__restrict__ fk, uint64_t n_foreign,
+                             uint8_t *__restrict__ keep, uint64_t *stats /*[0]=dupes,[1]=nondupes,[2]=unresolved*/) {
   unsigned dup = 0, non = 0, unres = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t n = nhits[i];
     if (!n) { keep[i] = 0; continue; }
-    const uint32_t j = minidx[slot_of[i]];
-    if (j == (uint32_t)i) { keep[i] = 1; ++non; continue; }
-    bool same = nhits[j] == n;
-    for (uint32_t k = 0; same && k < n; ++k) same = hits[hit_off[j] + k] == hits[hit_off[i] + k];
+    const uint64_t m = minord[slot_of[i]];
+    if (m == base + i) { keep[i] = 1; ++non; continue; }
+    bool same;
+    if (m >= base && m < base + n_pairs) {                   // an earlier pair of this rank: compare the hit lists
+      const uint64_t j = m - base;
+      same = nhits[j] == n;
+      for (uint32_t k = 0; same && k < n; ++k) same = hits[hit_off[j] + k] == hits[hit_off[i] + k];
+    } else {                                                 // another rank's pair: compare the 128-bit fingerprint
+      uint64_t lo = 0, hi = n_foreign;
+      while (lo < hi) { const uint64_t mid = (lo + hi) >> 1; if (fk[3 * mid + 2] < m) lo = mid + 1; else hi = mid; }
+      same = lo < n_foreign && fk[3 * lo + 2] == m && fk[3 * lo] == fp[2 * i] && fk[3 * lo + 1] == fp[2 * i + 1];
+    }
     keep[i] = 0;
     if (same) ++dup; else ++unres;
   }
@@ -236,6 +260,15 @@ __global__ void k_dd_resolve(const uint32_t *__restrict__ nhits, const uint64_t 
     if (non) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)non);
     if (unres) atomicAdd((unsigned long long *)&stats[2], (unsigned long long)unres);
   }
+}
+// {fp1, fp2, ordinal} of every non-empty pair, in pair order (=> sorted by ordinal)
+__global__ void k_export_flags(const uint32_t *__restrict__ nhits, uint64_t n, uint32_t *__restrict__ flag) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) flag[i] = nhits[i] != 0;
+}
+__global__ void k_export_keys(const uint32_t *__restrict__ nhits, const uint64_t *__restrict__ fp, const uint64_t *__restrict__ off,
+                              uint64_t n, uint64_t base, uint64_t *__restrict__ out) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    if (nhits[i]) { const uint64_t o = off[i]; out[3 * o] = fp[2 * i]; out[3 * o + 1] = fp[2 * i + 1]; out[3 * o + 2] = base + i; }
 }
 // per surviving pair: how many hits pass the regex (positions.txt) / varbin's chromosome filters
 __global__ void k_pair_out_count(const uint32_t *__restrict__ nhits, const uint64_t *__restrict__ hit_off,
@@ -278,23 +311,23 @@ __device__ __forceinline__ uint64_t bin_of(const int64_t *__restrict__ starts, u
 // varbin.py:56-58: a line whose position string equals the previous kept line's is a duplicate
 __global__ void k_varbin_global(const int64_t *__restrict__ f_pos, const int64_t *__restrict__ f_abs, uint64_t n,
                                 const int64_t *__restrict__ starts, uint64_t n_bins, unsigned long long *counts,
-                                unsigned long long *stats /*[3]=dups*/) {
+                                unsigned long long *stats /*[3]=dups*/, int has_prev, int64_t prev_pos) {
   unsigned long long dups = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    if (i && f_pos[i] == f_pos[i - 1]) { ++dups; continue; }
+    if (i ? f_pos[i] == f_pos[i - 1] : (has_prev && f_pos[0] == prev_pos)) { ++dups; continue; }
     atomicAdd(&counts[bin_of(starts, n_bins, f_abs[i])], 1ull);
   }
   if (dups) atomicAdd(&stats[3], dups);
 }
 __global__ void k_varbin_smem(const int64_t *__restrict__ f_pos, const int64_t *__restrict__ f_abs, uint64_t n,
                               const int64_t *__restrict__ starts, uint64_t n_bins, unsigned long long *counts,
-                              unsigned long long *stats) {
+                              unsigned long long *stats, int has_prev, int64_t prev_pos) {
   extern __shared__ uint32_t hist[];
   for (uint64_t k = threadIdx.x; k < n_bins; k += blockDim.x) hist[k] = 0;
   __syncthreads();
   unsigned long long dups = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    if (i && f_pos[i] == f_pos[i - 1]) { ++dups; continue; }
+    if (i ? f_pos[i] == f_pos[i - 1] : (has_prev && f_pos[0] == prev_pos)) { ++dups; continue; }
     atomicAdd(&hist[bin_of(starts, n_bins, f_abs[i])], 1u);
   }
   if (dups) atomicAdd(&stats[3], dups);
@@ -302,38 +335,40 @@ __global__ void k_varbin_smem(const int64_t *__restrict__ f_pos, const int64_t *
   for (uint64_t k = threadIdx.x; k < n_bins; k += blockDim.x) if (hist[k]) atomicAdd(&counts[k], (unsigned long long)hist[k]);
 }
 
-int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smash_tail_stats *stats,
-                cudaStream_t st, uint64_t *launches) {
+// Phase A: duplicate removal (local pairs + foreign keys), ordered compaction into the positions
+// list and the varbin-filtered list; reports the shard's edge (first/last filtered position).
+int tail_phase_a(TailState *t, uint64_t ordinal_base, const uint64_t *foreign_keys, uint64_t n_foreign,
+                 smash_tail_edge *edge, cudaStream_t st, uint64_t *launches) {
   if (!t->configured) return tfail(SMASH_ERR_STATE, "smash_tail_configure has not been called");
   const uint64_t P = t->n_pairs;
   double tq = t_now();
-  TCU(cudaMemsetAsync(t->counts, 0, 8 * t->n_bins, st));
-  smash_tail_stats s{};
   uint64_t h_stats[4] = {0, 0, 0, 0};
   uint64_t n_pos = 0, n_f = 0;
+  t->a_done = false;
   if (P) {
-    if (P >= 0xffffffffull) return tfail(SMASH_ERR_ARG, "too many pairs for one tail pass");
-    uint64_t tsize = 1024; while (tsize < 2 * P) tsize <<= 1;
+    uint64_t tsize = 1024; while (tsize < 2 * (P + n_foreign)) tsize <<= 1;
     // persistent scratch (grown on demand, never freed per call: cudaMalloc/cudaFree cost milliseconds)
     int rcs;
-    if ((rcs = t->scr[0].reserve(8 * tsize, 0, st)) || (rcs = t->scr[1].reserve(4 * tsize, 0, st)) || (rcs = t->scr[2].reserve(4 * P, 0, st)) ||
+    if ((rcs = t->scr[0].reserve(8 * tsize, 0, st)) || (rcs = t->scr[1].reserve(8 * tsize, 0, st)) || (rcs = t->scr[2].reserve(4 * P, 0, st)) ||
         (rcs = t->scr[3].reserve(P, 0, st)) || (rcs = t->scr[4].reserve(64, 0, st)) || (rcs = t->scr[5].reserve(4 * P, 0, st)) ||
         (rcs = t->scr[6].reserve(4 * P, 0, st)) || (rcs = t->scr[7].reserve(8 * (P + 1), 0, st)) || (rcs = t->scr[8].reserve(8 * (P + 1), 0, st)) ||
         (rcs = t->scr[9].reserve(8 * (P / 2048 + 8), 0, st)))
       return rcs;
     uint64_t *keys = (uint64_t *)t->scr[0].p, *d_stats = (uint64_t *)t->scr[4].p, *o_pos = (uint64_t *)t->scr[7].p,
              *o_bin = (uint64_t *)t->scr[8].p, *blk = (uint64_t *)t->scr[9].p;
-    uint32_t *minidx = (uint32_t *)t->scr[1].p, *slot_of = (uint32_t *)t->scr[2].p, *c_pos = (uint32_t *)t->scr[5].p,
-             *c_bin = (uint32_t *)t->scr[6].p;
+    unsigned long long *minord = (unsigned long long *)t->scr[1].p;
+    uint32_t *slot_of = (uint32_t *)t->scr[2].p, *c_pos = (uint32_t *)t->scr[5].p, *c_bin = (uint32_t *)t->scr[6].p;
     uint8_t *keep = (uint8_t *)t->scr[3].p;
-    int64_t *f_pos = nullptr, *f_abs = nullptr;
-    TDBG("mallocs");
+    TDBG("reserve");
     const int grid = (int)((P + 255) / 256 < 148 * 8 ? (P + 255) / 256 : 148 * 8);
     for (uint64_t seed = 1;; ++seed) {
-      TCU(cudaMemsetAsync(keys, 0xff, 8 * tsize, st)); TCU(cudaMemsetAsync(minidx, 0xff, 4 * tsize, st));
+      TCU(cudaMemsetAsync(keys, 0xff, 8 * tsize, st)); TCU(cudaMemsetAsync(minord, 0xff, 8 * tsize, st));
       TCU(cudaMemsetAsync(d_stats, 0, 32, st));
-      k_dd_insert<<<grid, 256, 0, st>>>(t->pair_nhits.p, t->pair_fp.p, P, seed * 0x9e3779b97f4a7c15ULL, keys, minidx, tsize - 1, slot_of);
-      k_dd_resolve<<<grid, 256, 0, st>>>(t->pair_nhits.p, t->pair_hit_off.p, t->hits.p, P, minidx, slot_of, keep, d_stats);
+      const uint64_t sd = seed * 0x9e3779b97f4a7c15ULL;
+      if (n_foreign) { k_dd_insert_foreign<<<grid, 256, 0, st>>>(foreign_keys, n_foreign, sd, keys, minord, tsize - 1); *launches += 1; }
+      k_dd_insert<<<grid, 256, 0, st>>>(t->pair_nhits.p, t->pair_fp.p, P, ordinal_base, sd, keys, minord, tsize - 1, slot_of);
+      k_dd_resolve<<<grid, 256, 0, st>>>(t->pair_nhits.p, t->pair_fp.p, t->pair_hit_off.p, t->hits.p, P, ordinal_base, minord, slot_of,
+                                         foreign_keys, n_foreign, keep, d_stats);
       *launches += 2;
       TCU(cudaMemcpyAsync(h_stats, d_stats, 32, cudaMemcpyDeviceToHost, st));
       TCU(cudaStreamSynchronize(st));
@@ -355,36 +390,96 @@ int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smas
     }
     TDBG("out_count+scans");
     if ((rcs = t->scr[10].reserve(8 * (n_f + 1), 0, st)) || (rcs = t->scr[11].reserve(8 * (n_f + 1), 0, st))) return rcs;
-    f_pos = (int64_t *)t->scr[10].p; f_abs = (int64_t *)t->scr[11].p;
+    int64_t *f_pos = (int64_t *)t->scr[10].p, *f_abs = (int64_t *)t->scr[11].p;
     k_pair_out_write<<<grid, 256, 0, st>>>(t->pair_nhits.p, t->pair_hit_off.p, t->hits.p, keep, P, t->chrom_off, o_pos, o_bin,
                                            t->pos_chrom, t->pos_pos, f_pos, f_abs);
     *launches += 1;
     TDBG("out_write");
-    if (n_f) {
-      const size_t smem = 4 * t->n_bins;
-      const int vgrid = (int)((n_f + 255) / 256 < 148 * 2 ? (n_f + 255) / 256 : 148 * 2);
-      if (smem <= 200 * 1024 && n_f >= 16 * t->n_bins) {
-        TCU(cudaFuncSetAttribute(k_varbin_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int g = vgrid < 148 ? vgrid : 148;
-        k_varbin_smem<<<g, 1024, smem, st>>>(f_pos, f_abs, n_f, t->bin_starts, t->n_bins, (unsigned long long *)t->counts, (unsigned long long *)d_stats);
-      } else {
-        k_varbin_global<<<vgrid, 256, 0, st>>>(f_pos, f_abs, n_f, t->bin_starts, t->n_bins, (unsigned long long *)t->counts, (unsigned long long *)d_stats);
-      }
-      *launches += 1;
+  }
+  t->n_positions = n_pos; t->n_f = n_f; t->a_dupes = h_stats[0]; t->a_non_dupes = h_stats[1];
+  smash_tail_edge e{}; e.n_filtered = n_f;
+  if (n_f) {
+    const int64_t *f_pos = (const int64_t *)t->scr[10].p;
+    TCU(cudaMemcpyAsync(&e.first_pos, f_pos, 8, cudaMemcpyDeviceToHost, st));
+    TCU(cudaMemcpyAsync(&e.last_pos, f_pos + (n_f - 1), 8, cudaMemcpyDeviceToHost, st));
+    TCU(cudaStreamSynchronize(st));
+  }
+  TCU(cudaGetLastError());
+  if (edge) *edge = e;
+  t->a_done = true;
+  return 0;
+}
+
+// Phase B: varbin's adjacent-duplicate rule (optionally seeded with the previous shard's last
+// filtered position) + bin histogram.
+int tail_phase_b(TailState *t, int has_prev, int64_t prev_last_pos, int64_t *counts_host, int64_t *counts_device,
+                 smash_tail_stats *stats, cudaStream_t st, uint64_t *launches) {
+  if (!t->a_done) return tfail(SMASH_ERR_STATE, "phase A has not run");
+  double tq = t_now();
+  TCU(cudaMemsetAsync(t->counts, 0, 8 * t->n_bins, st));
+  uint64_t h_stats[4] = {0, 0, 0, 0};
+  const uint64_t n_f = t->n_f;
+  if (n_f) {
+    int rcs;
+    if ((rcs = t->scr[4].reserve(64, 0, st))) return rcs;
+    uint64_t *d_stats = (uint64_t *)t->scr[4].p;
+    TCU(cudaMemsetAsync(d_stats, 0, 32, st));
+    const int64_t *f_pos = (const int64_t *)t->scr[10].p, *f_abs = (const int64_t *)t->scr[11].p;
+    const size_t smem = 4 * t->n_bins;
+    const int vgrid = (int)((n_f + 255) / 256 < 148 * 2 ? (n_f + 255) / 256 : 148 * 2);
+    if (smem <= 200 * 1024 && n_f >= 16 * t->n_bins) {
+      TCU(cudaFuncSetAttribute(k_varbin_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int g = vgrid < 148 ? vgrid : 148;
+      k_varbin_smem<<<g, 1024, smem, st>>>(f_pos, f_abs, n_f, t->bin_starts, t->n_bins, (unsigned long long *)t->counts,
+                                           (unsigned long long *)d_stats, has_prev, prev_last_pos);
+    } else {
+      k_varbin_global<<<vgrid, 256, 0, st>>>(f_pos, f_abs, n_f, t->bin_starts, t->n_bins, (unsigned long long *)t->counts,
+                                             (unsigned long long *)d_stats, has_prev, prev_last_pos);
     }
-    TDBG("varbin");
+    *launches += 1;
     TCU(cudaMemcpyAsync(h_stats, d_stats, 32, cudaMemcpyDeviceToHost, st));
     TCU(cudaStreamSynchronize(st));
-    TCU(cudaGetLastError());
-    TDBG("frees");
+    TDBG("varbin");
   }
-  t->n_positions = n_pos;
-  s.n_dupe_pairs = h_stats[0]; s.n_non_dupe_pairs = h_stats[1];
-  s.n_positions = n_pos; s.total_reads = n_f; s.dups_removed = h_stats[3]; s.reads_kept = n_f - h_stats[3];
+  smash_tail_stats s{};
+  s.n_dupe_pairs = t->a_dupes; s.n_non_dupe_pairs = t->a_non_dupes;
+  s.n_positions = t->n_positions; s.total_reads = n_f; s.dups_removed = h_stats[3]; s.reads_kept = n_f - h_stats[3];
   if (counts_device) TCU(cudaMemcpyAsync(counts_device, t->counts, 8 * t->n_bins, cudaMemcpyDeviceToDevice, st));
   if (counts_host) TCU(cudaMemcpyAsync(counts_host, t->counts, 8 * t->n_bins, cudaMemcpyDeviceToHost, st));
   TCU(cudaStreamSynchronize(st));
+  TCU(cudaGetLastError());
   if (stats) *stats = s;
+  return 0;
+}
+
+int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smash_tail_stats *stats,
+                cudaStream_t st, uint64_t *launches) {
+  int rc = tail_phase_a(t, 0, nullptr, 0, nullptr, st, launches);
+  if (rc) return rc;
+  return tail_phase_b(t, 0, 0, counts_host, counts_device, stats, st, launches);
+}
+
+// {fp1, fp2, ordinal} triples of this rank's non-empty pairs (device memory owned by the tail).
+int tail_export_keys(TailState *t, uint64_t ordinal_base, const uint64_t **dev_keys, uint64_t *n, cudaStream_t st, uint64_t *launches) {
+  const uint64_t P = t->n_pairs;
+  *dev_keys = nullptr; *n = 0;
+  if (!P) return 0;
+  int rcs;
+  if ((rcs = t->scr[5].reserve(4 * P, 0, st)) || (rcs = t->scr[7].reserve(8 * (P + 1), 0, st)) || (rcs = t->scr[9].reserve(8 * (P / 2048 + 8), 0, st)))
+    return rcs;
+  uint32_t *flag = (uint32_t *)t->scr[5].p; uint64_t *off = (uint64_t *)t->scr[7].p, *blk = (uint64_t *)t->scr[9].p;
+  const int grid = (int)((P + 255) / 256 < 148 * 8 ? (P + 255) / 256 : 148 * 8);
+  k_export_flags<<<grid, 256, 0, st>>>(t->pair_nhits.p, P, flag);
+  *launches += 1 + exclusive_scan_u32_public(flag, P, blk, off, st);
+  uint64_t cnt = 0;
+  TCU(cudaMemcpyAsync(&cnt, off + P, 8, cudaMemcpyDeviceToHost, st));
+  TCU(cudaStreamSynchronize(st));
+  if ((rcs = t->exp_keys.reserve(24 * (cnt + 1), 0, st))) return rcs;
+  k_export_keys<<<grid, 256, 0, st>>>(t->pair_nhits.p, t->pair_fp.p, off, P, ordinal_base, (uint64_t *)t->exp_keys.p);
+  *launches += 1;
+  TCU(cudaStreamSynchronize(st));
+  TCU(cudaGetLastError());
+  *dev_keys = (const uint64_t *)t->exp_keys.p; *n = cnt;
   return 0;
 }
 
@@ -396,7 +491,7 @@ int tail_reserve(TailState *t, uint64_t pairs, uint64_t hits, cudaStream_t st) {
       (rc = t->pair_hit_off.reserve(pairs, t->n_pairs, st)) || (rc = t->hits.reserve(hits + 1, t->n_hits_bound, st)))
     return rc;
   uint64_t tsize = 1024; while (tsize < 2 * pairs) tsize <<= 1;
-  const size_t want[12] = {8 * tsize, 4 * tsize, 4 * pairs, pairs, 64, 4 * pairs, 4 * pairs, 8 * (pairs + 1), 8 * (pairs + 1),
+  const size_t want[12] = {8 * tsize, 8 * tsize, 4 * pairs, pairs, 64, 4 * pairs, 4 * pairs, 8 * (pairs + 1), 8 * (pairs + 1),
                            8 * (pairs / 2048 + 8), 8 * (hits + 1), 8 * (hits + 1)};
   for (int i = 0; i < 12; ++i) if ((rc = t->scr[i].reserve(want[i], 0, st))) return rc;
   if (hits + 1 > t->pos_cap) {

@@ -28,6 +28,8 @@ struct TailState {
   DGrow<uint64_t> hits;             // tid << 40 | 0-based pos, r1 hits in HI order then r2 hits
   // scratch
   DGrow<uint8_t> scr[12];           // tail_finish work buffers (persistent)
+  DGrow<uint8_t> exp_keys;          // exported {fp1,fp2,ordinal} triples
+  bool a_done = false; uint64_t n_f = 0, a_dupes = 0, a_non_dupes = 0;
   uint32_t *batch_cnt = nullptr; uint64_t *batch_off = nullptr; uint64_t *blk = nullptr; size_t batch_cap = 0;
   // results of finish
   int64_t *counts = nullptr;        // n_bins
@@ -45,6 +47,11 @@ int tail_accumulate(TailState *t, const DevIndex &ix, const BatchDev &b, const W
                     uint64_t n_records_bound, cudaStream_t st, uint64_t *launches);
 int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smash_tail_stats *stats,
                 cudaStream_t st, uint64_t *launches);
+int tail_phase_a(TailState *t, uint64_t ordinal_base, const uint64_t *foreign_keys, uint64_t n_foreign,
+                 smash_tail_edge *edge, cudaStream_t st, uint64_t *launches);
+int tail_phase_b(TailState *t, int has_prev, int64_t prev_last_pos, int64_t *counts_host, int64_t *counts_device,
+                 smash_tail_stats *stats, cudaStream_t st, uint64_t *launches);
+int tail_export_keys(TailState *t, uint64_t ordinal_base, const uint64_t **dev_keys, uint64_t *n, cudaStream_t st, uint64_t *launches);
 int tail_reserve(TailState *t, uint64_t pairs, uint64_t hits, cudaStream_t st);
 int tail_positions(TailState *t, const int32_t **chrom, const int64_t **pos, uint64_t *n);
 

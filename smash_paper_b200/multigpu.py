@@ -1,0 +1,94 @@
+"""Read-sharded multi-GPU tail: the host-side exchange around smash_tail_export_keys / phase_a / phase_b.
+
+One process per GPU (torch.distributed: NCCL on GPUs, gloo in the CPU tests).  Ranks map contiguous
+ranges of read pairs against their own replica of the index; nothing is exchanged on the search/SAM
+path.  The tail needs three small exchanges so that the result equals the single-process run bit for
+bit:
+
+  1. all_gather of the dupe-set fingerprints {fp1, fp2, ordinal} -> every rank removes pairs whose key
+     first appeared on a LOWER rank (smashMEM.py:217-228 is first-wins in name order);
+  2. all_gather of the shard edges -> varbin's "same position as the previous kept line" rule
+     (varbin.py:56-58) sees the last position of the previous shard;
+  3. one all_reduce(sum) of the n_bins int64 counts (+ the five stats counters).
+
+`backend` is any object with export_keys() -> int64 tensor [n,3], phase_a(foreign [m,3]) ->
+(n_filtered, first_pos, last_pos), phase_b(has_prev, prev_last_pos) -> (counts tensor, stats dict);
+`ContextBackend` wraps a smash_ctx, the CPU tests plug in a numpy model.
+"""
+from __future__ import annotations
+
+import torch
+
+STAT_KEYS = ["total_reads", "dups_removed", "reads_kept", "n_dupe_pairs", "n_non_dupe_pairs", "n_positions"]
+
+
+def gather_varlen(t: torch.Tensor, dist, world):
+    """all_gather of tensors whose first dimension differs per rank."""
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(s.item()) for s in sizes]
+    m = max(sizes + [1])
+    pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
+    out = [torch.zeros_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    return [o[:s] for o, s in zip(out, sizes)]
+
+
+def lower_rank_keys(parts, rank):
+    """Keys of ranks < rank, concatenated (already sorted by ordinal: shards are contiguous)."""
+    lower = [p for p in parts[:rank] if p.shape[0]]
+    if not lower:
+        return parts[rank][:0]
+    return torch.cat(lower, dim=0).contiguous()
+
+
+def previous_last_pos(edges, rank):
+    """edges: list of (n_filtered, first_pos, last_pos) per rank -> (has_prev, last position of the nearest
+    lower rank that has any filtered position)."""
+    for r in range(rank - 1, -1, -1):
+        if edges[r][0] > 0:
+            return True, int(edges[r][2])
+    return False, 0
+
+
+def sharded_tail_finish(backend, dist, rank, world):
+    """Runs the three exchanges; returns (global counts tensor, global stats dict)."""
+    keys = backend.export_keys()
+    parts = gather_varlen(keys, dist, world) if world > 1 else [keys]
+    n_f, first, last = backend.phase_a(lower_rank_keys(parts, rank))
+    e = torch.tensor([[n_f, first, last]], dtype=torch.int64, device=keys.device)
+    edges = [tuple(int(v) for v in x[0]) for x in gather_varlen(e, dist, world)] if world > 1 else [(n_f, first, last)]
+    has_prev, prev = previous_last_pos(edges, rank)
+    counts, stats = backend.phase_b(has_prev, prev)
+    sv = torch.tensor([stats[k] for k in STAT_KEYS], dtype=torch.int64, device=counts.device)
+    if world > 1:
+        dist.all_reduce(counts)
+        dist.all_reduce(sv)
+    return counts, dict(zip(STAT_KEYS, [int(v) for v in sv]))
+
+
+class ContextBackend:
+    """smash_ctx behind the backend protocol (CUDA tensors, device pointers straight into the C ABI)."""
+
+    def __init__(self, ctx, ordinal_base, device):
+        from . import api
+        self.api, self.ctx, self.base, self.device = api, ctx, int(ordinal_base), device
+        self.counts = torch.zeros(ctx.n_bins, dtype=torch.int64, device=device)
+
+    def export_keys(self):
+        ptr, n = self.ctx.tail_export_keys(self.base)
+        t = torch.zeros((n, 3), dtype=torch.int64, device=self.device)
+        if n:
+            self.api.memcpy(t.data_ptr(), ptr, 24 * n)
+        return t
+
+    def phase_a(self, foreign):
+        foreign = foreign.contiguous()
+        torch.cuda.synchronize(self.device)
+        return self.ctx.tail_phase_a(self.base, foreign.data_ptr() if foreign.shape[0] else None, int(foreign.shape[0]))
+
+    def phase_b(self, has_prev, prev):
+        _, stats = self.ctx.tail_phase_b(has_prev, prev, self.counts.data_ptr())
+        return self.counts, stats

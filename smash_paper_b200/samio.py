@@ -91,6 +91,24 @@ def slice_batch(b, lo, hi):
     return out
 
 
+def concat_batches(batches):
+    def cat(blobs, offs):
+        out_off = [np.zeros(1, dtype=np.int64)]
+        base = 0
+        for o in offs:
+            out_off.append(o[1:] + base)
+            base += int(o[-1])
+        return np.concatenate(blobs), np.concatenate(out_off)
+    nb, no = cat([b.names for b in batches], [b.name_off for b in batches])
+    sb, so = cat([b.seq for b in batches], [b.seq_off for b in batches])
+    qb, _ = cat([b.qual for b in batches], [b.seq_off for b in batches])
+    ob, oo = cat([b.opt for b in batches], [b.opt_off for b in batches])
+    out = ReadBatch(names=nb, name_off=no, seq=sb, qual=qb, seq_off=so, flags=np.concatenate([b.flags for b in batches]),
+                    opt=ob, opt_off=oo)
+    out.read_flag = np.concatenate([read_flag_of(b) for b in batches])
+    return out
+
+
 def write_mapout(header: bytes, sam: bytes, directory="mapout", tag="b200", seq=1):
     """mapout/mapout<id>.<k>.txt = header + records (query.cpp:453-463)."""
     os.makedirs(directory, exist_ok=True)

@@ -260,3 +260,50 @@ def test_mummer_compatible_driver(case, workdir):
     r = subprocess.run([sys.executable, "-m", "smash_paper_b200.mummer", "-rcref", "-nomap", fa, "reads.sam"], cwd=d, env=env,
                        capture_output=True, text=True)
     assert r.returncode == 1 and r.stderr.startswith("Error\n-nomap can only be used with -sam_out")
+
+
+def test_two_shards_equal_one_run(case):
+    """Read-sharded tail on ONE GPU: two contexts take the two halves of the pairs; with the key and edge
+    exchange of multigpu.py (done in-process here) the summed counts equal the single-context run."""
+    import torch
+    from smash_paper_b200 import api, multigpu, samio
+    ix = api.Index.open(case["fa"])
+    base = case["reads"]
+    cut = (base.n // 4) * 2
+    # second shard = second half of the reads + a copy of 200 reads of the first shard (cross-shard dupes)
+    reads = samio.concat_batches([base, samio.slice_batch(base, 100, 300)])
+    exp = None
+    ctxs = []
+    try:
+        for _ in range(3):
+            c = api.Context(ix, min_len=20, nomap=True)
+            c.load_mappability_file(case["fa"] + ".bin/map.bin")
+            sam = case["oix"].map_batch(reads, min_len=20, n_threads=4)
+            if exp is None:
+                exp = oracle_tail(case["oix"], case["body"], sam, case["dir"], case["fa"])
+            ci = exp["chrominfo"]
+            c.tail_configure([int(b[2]) for b in exp["bins"]], list(ci.keys()), [int(v[2]) for v in ci.values()])
+            ctxs.append(c)
+        whole, a, b = ctxs
+        whole.map_batch(reads, want=api.WANT_TAIL)
+        counts, st = whole.tail_finish()
+        assert np.array_equal(counts, exp["counts"])
+        half = cut
+        a.map_batch(samio.slice_batch(reads, 0, half), want=api.WANT_TAIL)
+        b.map_batch(samio.slice_batch(reads, half, reads.n), want=api.WANT_TAIL)
+        dev = torch.device("cuda", 0)
+        ba, bb = multigpu.ContextBackend(a, 0, dev), multigpu.ContextBackend(b, half // 2, dev)
+        ka, kb = ba.export_keys(), bb.export_keys()
+        ea = ba.phase_a(ka[:0]); eb = bb.phase_a(multigpu.lower_rank_keys([ka, kb], 1))
+        ca, sa = ba.phase_b(False, 0)
+        hp, pv = multigpu.previous_last_pos([ea, eb], 1)
+        cb, sb = bb.phase_b(hp, pv)
+        torch.cuda.synchronize()
+        assert np.array_equal((ca + cb).cpu().numpy(), exp["counts"])
+        for k in multigpu.STAT_KEYS:
+            assert sa[k] + sb[k] == st[k], k
+        assert st["n_dupe_pairs"] == exp["n_dupe"] and st["n_non_dupe_pairs"] == exp["n_non"]
+    finally:
+        for c in ctxs:
+            c.close()
+        ix.close()
