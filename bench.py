@@ -440,6 +440,11 @@ def run_reference(args, wl, rank, world):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else that might write to fd 1 (NCCL's version banner,
+    # library chatter) is sent to stderr; the JSON goes to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -467,7 +472,8 @@ def main():
     for d in cleanup:
         shutil.rmtree(d, ignore_errors=True)
     if rank == 0 and out is not None:
-        print(json.dumps(out), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(out) + "\n").encode())
 
 
 if __name__ == "__main__":

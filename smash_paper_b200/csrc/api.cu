@@ -217,6 +217,8 @@ struct Slot {
   DBuf<ReadSum> sums; DBuf<uint32_t> nrec; DBuf<uint64_t> rec_base; DBuf<uint32_t> rec_read; DBuf<uint32_t> rec_bytes; DBuf<uint64_t> rec_off; DBuf<uint64_t> sam_total; DBuf<uint64_t> blk_sums2; DBuf<uint64_t> blk_sums;
   DBuf<char> sam; DBuf<uint32_t> flags;
   DBuf<int64_t> csr_off; DBuf<uint64_t> csr_triples;
+  DBuf<uint64_t> slot_off; DBuf<Aln> aln_scr; DBuf<uint16_t> ord_scr; DBuf<uint32_t> tmp32;   // MEM mode (CSR slots)
+  uint64_t slots_total = 0; bool csr = false;
   // results on host
   HBuf<char> h_sam; HBuf<int64_t> h_csr_off; HBuf<smash_match> h_matches; HBuf<uint64_t> h_small;
   // in flight
@@ -518,7 +520,7 @@ static void slot_release(Slot &s) {
   s.seq_off.release(); s.opt_off.release(); s.read_flag.release(); s.match_slots.release();
   s.match_cnt.release(); s.item_slots.release(); s.rec_slots.release(); s.sums.release();
   s.nrec.release(); s.rec_base.release(); s.rec_read.release(); s.rec_bytes.release(); s.rec_off.release(); s.sam_total.release(); s.blk_sums2.release(); s.blk_sums.release(); s.sam.release(); s.flags.release();
-  s.csr_off.release(); s.csr_triples.release(); s.h_sam.release(); s.h_csr_off.release();
+  s.csr_off.release(); s.csr_triples.release(); s.slot_off.release(); s.aln_scr.release(); s.ord_scr.release(); s.tmp32.release(); s.h_sam.release(); s.h_csr_off.release();
   s.h_matches.release(); s.h_small.release();
   if (s.ev0) cudaEventDestroy(s.ev0);
   if (s.ev1) cudaEventDestroy(s.ev1);
@@ -619,7 +621,8 @@ static int slot_prepare(smash_ctx *c, Slot &s, const smash_batch *b, bool copy) 
 
 static WorkDev work_of(Slot &s) {
   WorkDev w{};
-  w.cap = s.cap; w.match_slots = s.match_slots.p; w.match_cnt = s.match_cnt.p; w.item_slots = s.item_slots.p;
+  w.cap = s.cap; w.slot_off = s.csr ? s.slot_off.p : nullptr; w.slots_total = s.csr ? s.slots_total : s.n_reads * (uint64_t)s.cap;
+  w.aln_scratch = s.aln_scr.p; w.ord_scratch = s.ord_scr.p; w.match_slots = s.match_slots.p; w.match_cnt = s.match_cnt.p; w.item_slots = s.item_slots.p;
   w.rec_slots = s.rec_slots.p; w.sums = s.sums.p; w.nrec = s.nrec.p; w.rec_base = s.rec_base.p; w.rec_read = s.rec_read.p; w.rec_bytes = s.rec_bytes.p; w.rec_off = s.rec_off.p; w.sam_total = s.sam_total.p; w.blk_sums2 = s.blk_sums2.p;
   w.blk_sums = s.blk_sums.p; w.sam = s.sam.p; w.sam_cap = s.sam.cap; w.flags = s.flags.p;
   return w;
@@ -638,9 +641,26 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
     CU(cudaEventRecord(s.ev0, s.st));
     s.n_evs = 0;
     int nl;
-    if (c->prm.mode == SMASH_MODE_MEM) nl = launch_mem_search(c->dix, s.bd, w, c->sp, s.st);
-    else nl = launch_mam_search(c->dix, s.bd, w, c->sp, s.st);
-    if (nl < 0) return fail(SMASH_ERR_STATE, "MEM mode kernel not available in this build");
+    if (c->prm.mode == SMASH_MODE_MEM) {
+      // K2: count pass -> slot offsets (one spare slot per read) -> exact-size buffers -> write pass
+      int rc;
+      if ((rc = s.slot_off.ensure(n + 2)) || (rc = s.tmp32.ensure(n + 1))) return rc;
+      nl = launch_mem_count(c->dix, s.bd, c->sp, c->prm.min_len, s.match_cnt.p, s.st);
+      nl += launch_slot_offsets(s.match_cnt.p, n, s.tmp32.p, s.blk_sums.p, s.slot_off.p, s.st);
+      CU(cudaMemcpyAsync(s.h_small.p + 16, s.slot_off.p + n, 8, cudaMemcpyDeviceToHost, s.st));
+      CU(cudaStreamSynchronize(s.st));
+      const uint64_t total = s.h_small.p[16];
+      s.slots_total = total; s.csr = true;
+      if ((rc = s.match_slots.ensure(total + 1)) || (rc = s.item_slots.ensure(total + 1)) || (rc = s.rec_slots.ensure(total + 1)) ||
+          (rc = s.aln_scr.ensure(total + 1)) || (rc = s.ord_scr.ensure(total + 1)) || (rc = s.rec_read.ensure(total + 1)) ||
+          (rc = s.rec_bytes.ensure(total + 1)) || (rc = s.rec_off.ensure(total + 2)) || (rc = s.blk_sums2.ensure(total / 2048 + 8)))
+        return rc;
+      w = work_of(s);
+      nl += launch_mem_write(c->dix, s.bd, c->sp, c->prm.min_len, s.slot_off.p, s.match_slots.p, s.st);
+    } else {
+      s.csr = false;
+      nl = launch_mam_search(c->dix, s.bd, w, c->sp, s.st);
+    }
     c->launches += nl;
     MARK(0);
     c->launches += launch_records(c->dix, s.bd, w, c->sp, s.st);
@@ -684,13 +704,14 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
   if (want & SMASH_WANT_MATCHES) {
     int rc;
     if ((rc = s.csr_off.ensure(n + 2))) return rc;
-    if ((rc = s.csr_triples.ensure(3 * n * (size_t)s.cap + 8))) return rc;
+    const size_t mslots = s.csr ? (size_t)s.slots_total : n * (size_t)s.cap;
+    if ((rc = s.csr_triples.ensure(3 * mslots + 8))) return rc;
     WorkDev w = work_of(s);
     c->launches += launch_match_csr(s.bd, w, s.csr_off.p, s.csr_triples.p, s.blk_sums.p, s.st);
     MARK(4);
-    if ((rc = s.h_csr_off.ensure(n + 2)) || (rc = s.h_matches.ensure(n * (size_t)s.cap + 8))) return rc;
+    if ((rc = s.h_csr_off.ensure(n + 2)) || (rc = s.h_matches.ensure(mslots + 8))) return rc;
     CU(cudaMemcpyAsync(s.h_csr_off.p, s.csr_off.p, 8 * (n + 1), cudaMemcpyDeviceToHost, s.st));
-    CU(cudaMemcpyAsync(s.h_matches.p, s.csr_triples.p, 24 * n * (size_t)s.cap, cudaMemcpyDeviceToHost, s.st));
+    CU(cudaMemcpyAsync(s.h_matches.p, s.csr_triples.p, 24 * mslots, cudaMemcpyDeviceToHost, s.st));
   }
   if (want & SMASH_WANT_TAIL) {
     const double tt = now_ms();

@@ -186,7 +186,7 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     const int n = sm.nstage[warp];
     const int ns = n < STAGE_CAP ? n : STAGE_CAP;
     // ordered emission: rank by query offset (distinct per match in MAM mode)
-    Match *dst = w.match_slots + read * (uint64_t)w.cap;
+    Match *dst = w.match_slots + slot_base(w, read);
     for (int e = lane; e < ns; e += 32) {
       const Match me = sm.stage[warp][e];
       int rank = 0;
@@ -224,12 +224,12 @@ k_rec_build(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
   for (uint64_t read = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; read < b.n_reads; read += (uint64_t)gridDim.x * blockDim.x) {
     const int q = (int)(b.seq_off[read + 1] - b.seq_off[read]);
     int n_in = (int)w.match_cnt[read];
-    if (n_in > w.cap) n_in = w.cap;
+    if (n_in > slot_cap(w, read)) n_in = slot_cap(w, read);
     if (n_in > LOCAL_CAP) n_in = LOCAL_CAP;
     Aln aln[LOCAL_CAP]; uint16_t ord[LOCAL_CAP];
     ReadSum sum;
-    const int n_rec = build_records(ix, w.match_slots + read * (uint64_t)w.cap, n_in, q, sp.nomap, aln, ord,
-                                    w.item_slots + read * (uint64_t)w.cap, w.rec_slots + read * (uint64_t)w.cap, &sum);
+    const int n_rec = build_records(ix, w.match_slots + slot_base(w, read), n_in, q, sp.nomap, aln, ord,
+                                    w.item_slots + slot_base(w, read), w.rec_slots + slot_base(w, read), &sum);
     w.sums[read] = sum;
     w.nrec[read] = (uint32_t)n_rec;
   }
@@ -247,14 +247,33 @@ k_rec_build_serial(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
   for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
     const int q = (int)(b.seq_off[read + 1] - b.seq_off[read]);
     int n_in = (int)w.match_cnt[read];
-    if (n_in > w.cap) n_in = w.cap;
+    if (n_in > slot_cap(w, read)) n_in = slot_cap(w, read);
     if (n_in > SCR_CAP) n_in = SCR_CAP;
     if (lane == 0) {
-      const int n_rec = build_records(ix, w.match_slots + read * (uint64_t)w.cap, n_in, q, sp.nomap, sm.aln[warp], sm.ord[warp],
-                                      w.item_slots + read * (uint64_t)w.cap, w.rec_slots + read * (uint64_t)w.cap, &w.sums[read]);
+      const int n_rec = build_records(ix, w.match_slots + slot_base(w, read), n_in, q, sp.nomap, sm.aln[warp], sm.ord[warp],
+                                      w.item_slots + slot_base(w, read), w.rec_slots + slot_base(w, read), &w.sums[read]);
       w.nrec[read] = (uint32_t)n_rec;
     }
     __syncwarp();
+  }
+}
+
+// MEM mode: any number of matches per read, scratch in HBM next to the read's slots (lane 0 works;
+// -maxmatch is the secondary mode and its per-read record logic is inherently serial).
+__global__ void __launch_bounds__(THREADS)
+k_rec_build_big(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
+  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
+    if (lane == 0) {
+      const int q = (int)(b.seq_off[read + 1] - b.seq_off[read]);
+      const uint64_t base = slot_base(w, read);
+      int n_in = (int)w.match_cnt[read];
+      if (n_in > slot_cap(w, read) - 1) n_in = slot_cap(w, read) - 1;
+      const int n_rec = build_records(ix, w.match_slots + base, n_in, q, sp.nomap, w.aln_scratch + base, w.ord_scratch + base,
+                                      w.item_slots + base, w.rec_slots + base, &w.sums[read]);
+      w.nrec[read] = (uint32_t)n_rec;
+    }
   }
 }
 
@@ -300,8 +319,8 @@ k_rec_xe(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     const int64_t so = b.seq_off[read];
     const int q = (int)(b.seq_off[read + 1] - so);
     const uint8_t *seq = b.seq + so;
-    Item *items = w.item_slots + read * (uint64_t)w.cap;
-    Rec *recs = w.rec_slots + read * (uint64_t)w.cap;
+    Item *items = w.item_slots + slot_base(w, read);
+    Rec *recs = w.rec_slots + slot_base(w, read);
     for (int r0 = 0; r0 < n_rec; r0 += 4) {                 // 4 records per pass, 8 lanes each
       const int r = r0 + sub;
       int cnt = 0;
@@ -342,7 +361,9 @@ k_rec_xe(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
 static int exclusive_scan_u32(const uint32_t *in, uint64_t n, uint64_t *blk, uint64_t *out, cudaStream_t st);
 int launch_records(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
   if (!b.n_reads) return 0;
-  if (w.cap <= LOCAL_CAP) {
+  if (w.slot_off) {
+    k_rec_build_big<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p);
+  } else if (w.cap <= LOCAL_CAP) {
     const uint64_t need = (b.n_reads + 127) / 128, cap = (uint64_t)sm_count() * 16;
     k_rec_build<<<(unsigned)(need < cap ? need : cap), 128, 0, st>>>(ix, b, w, p);
   } else {
@@ -383,8 +404,8 @@ k_sizes(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     const int q = (int)(b.seq_off[read + 1] - b.seq_off[read]);
     const int name_len = (int)(b.name_off[read + 1] - b.name_off[read]);
     const int opt_len = b.opt ? (int)(b.opt_off[read + 1] - b.opt_off[read]) : 0;
-    const Item *items = w.item_slots + read * (uint64_t)w.cap;
-    Rec *recs = w.rec_slots + read * (uint64_t)w.cap;
+    const Item *items = w.item_slots + slot_base(w, read);
+    Rec *recs = w.rec_slots + slot_base(w, read);
     CountSink cs;
     put_head(cs, ix, (const char *)nullptr, name_len, flag, me.unmapped, recs[r], r, items, mv);
     const uint32_t seq_at = cs.n;                                  // offset of the SEQ column in the line
@@ -482,7 +503,7 @@ int launch_sizes_scan(const DevIndex &ix, const BatchDev &b, const WorkDev &w, c
   if (!b.n_reads) return 0;
   k_sizes<<<sm_count() * 16, 128, 0, st>>>(ix, b, w, p);
   // rec_off = exclusive scan of rec_bytes over the (device-side) record count; total -> sam_total[0]
-  return 1 + exclusive_scan_u32_devn(w.rec_bytes, b.n_reads * (uint64_t)w.cap, w.rec_base + b.n_reads, w.blk_sums2, w.rec_off,
+  return 1 + exclusive_scan_u32_devn(w.rec_bytes, w.slots_total, w.rec_base + b.n_reads, w.blk_sums2, w.rec_off,
                                      w.sam_total, st);
 }
 
@@ -522,8 +543,8 @@ k_emit_text(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp, uint64_t n_reco
       const ReadSum me = w.sums[read];
       uint16_t flag; MateView mv;
       read_mate(b, w, read, &flag, &mv);
-      const Item *items = w.item_slots + read * (uint64_t)w.cap;
-      const Rec *recs = w.rec_slots + read * (uint64_t)w.cap;
+      const Item *items = w.item_slots + slot_base(w, read);
+      const Rec *recs = w.rec_slots + slot_base(w, read);
       const int name_len = (int)(b.name_off[read + 1] - b.name_off[read]);
       const int q = (int)(b.seq_off[read + 1] - b.seq_off[read]);
       const int opt_len = b.opt ? (int)(b.opt_off[read + 1] - b.opt_off[read]) : 0;
@@ -575,7 +596,7 @@ k_emit_copy(BatchDev b, WorkDev w, uint64_t n_records) {
   for (uint64_t f = warp0; f < n_records; f += warps_total) {
     const uint64_t read = w.rec_read[f];
     const int hi = (int)(f - w.rec_base[read]);
-    const Rec *rec = w.rec_slots + read * (uint64_t)w.cap + hi;
+    const Rec *rec = w.rec_slots + slot_base(w, read) + hi;
     const int64_t so = b.seq_off[read];
     const int q = (int)(b.seq_off[read + 1] - so);
     const int64_t no = b.name_off[read];
@@ -643,9 +664,9 @@ __global__ void k_match_copy(BatchDev b, WorkDev w, const uint64_t *__restrict__
   const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
   for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
     const uint32_t n = w.match_cnt[read];
-    const Match *src = w.match_slots + read * (uint64_t)w.cap;
+    const Match *src = w.match_slots + slot_base(w, read);
     uint64_t *dst = triples + 3 * off[read];
-    for (uint32_t i = lane; i < n && i < (uint32_t)w.cap; i += 32) {
+    for (uint32_t i = lane; i < n && i < (uint32_t)slot_cap(w, read); i += 32) {
       dst[3 * i] = src[i].ref; dst[3 * i + 1] = src[i].qpos; dst[3 * i + 2] = src[i].len;
     }
   }
@@ -694,8 +715,13 @@ int launch_mappability(const DevIndex &ix, uint64_t *, uint8_t *body, cudaStream
   return launches;
 }
 
-int launch_mem_search(const DevIndex &, const BatchDev &, const WorkDev &, const SearchParams &, cudaStream_t) {
-  return -1;   // K2 lands in mem_search.cu
+__global__ void k_add_one(const uint32_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ out) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) out[i] = in[i] + 1u;
+}
+int launch_slot_offsets(const uint32_t *match_cnt, uint64_t n_reads, uint32_t *tmp, uint64_t *blk, uint64_t *slot_off, cudaStream_t st) {
+  if (!n_reads) return 0;
+  k_add_one<<<sm_count() * 4, 256, 0, st>>>(match_cnt, n_reads, tmp);
+  return 1 + exclusive_scan_u32(tmp, n_reads, blk, slot_off, st);
 }
 
 }  // namespace smash

@@ -17,7 +17,11 @@ struct BatchDev {
 enum { FLAG_OVERFLOW = 0, FLAG_MAPERR = 1, FLAG_LONGREAD = 2, FLAG_MAXCNT = 3, N_FLAGS = 8 };
 
 struct WorkDev {
-  int cap;                     // slots per read (matches / items / records)
+  int cap;                     // slots per read (matches / items / records) when slot_off is null
+  const uint64_t *slot_off;    // MEM mode: per-read slot ranges (CSR, n_reads + 1); null => read * cap
+  uint64_t slots_total;        // number of slots in the batch (n_reads * cap, or slot_off[n_reads])
+  Aln *aln_scratch;            // MEM mode: per-slot scratch for k_rec_build_big
+  uint16_t *ord_scratch;
   Match *match_slots;          // n_reads * cap
   uint32_t *match_cnt;         // n_reads (true count, may exceed cap => overflow flag)
   Item *item_slots;            // n_reads * cap
@@ -36,6 +40,13 @@ struct WorkDev {
   uint32_t *flags;             // N_FLAGS counters
 };
 
+HD uint64_t slot_base(const WorkDev &w, uint64_t read) { return w.slot_off ? w.slot_off[read] : read * (uint64_t)w.cap; }
+HD int slot_cap(const WorkDev &w, uint64_t read) {
+  if (!w.slot_off) return w.cap;
+  const uint64_t c = w.slot_off[read + 1] - w.slot_off[read];
+  return c > 65535 ? 65535 : (int)c;
+}
+
 struct SearchParams {
   uint32_t L;                  // effective min_len = max(min_len, 2)
   int k;                       // seed length used = min(seed_k, L)
@@ -51,7 +62,11 @@ int launch_uniq_build(const DevIndex &ix, uint8_t *uniq, cudaStream_t st);
 int launch_seed_build(const DevIndex &ix, void *seed, int k, int seed_w, cudaStream_t st);
 int launch_alpha(const uint8_t *text, uint64_t N, uint32_t *alpha8, cudaStream_t st);
 int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
-int launch_mem_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
+int launch_mem_count(const DevIndex &ix, const BatchDev &b, const SearchParams &p, uint32_t min_len_raw, uint32_t *cnt, cudaStream_t st);
+int launch_mem_write(const DevIndex &ix, const BatchDev &b, const SearchParams &p, uint32_t min_len_raw, const uint64_t *off,
+                     Match *matches, cudaStream_t st);
+// slot_off = exclusive scan of (match_cnt + 1): one spare slot per read for the unmapped placeholder
+int launch_slot_offsets(const uint32_t *match_cnt, uint64_t n_reads, uint32_t *tmp, uint64_t *blk, uint64_t *slot_off, cudaStream_t st);
 int launch_records(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
 int launch_sizes_scan(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
 int launch_emit(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st, uint64_t n_records);

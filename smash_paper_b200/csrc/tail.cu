@@ -100,13 +100,13 @@ template <class F>
 __device__ __forceinline__ void for_kept_hits(const BatchDev &b, const WorkDev &w, uint64_t p, const PairParams &pp, F f) {
   const uint64_t ra = 2 * p, rb = 2 * p + 1;
   const ReadSum sa = w.sums[ra];
-  const Rec *reca = w.rec_slots + ra * (uint64_t)w.cap;
+  const Rec *reca = w.rec_slots + slot_base(w, ra);
   const int na = sa.unmapped ? 0 : sa.n_rec;
   for (int i = 0; i < na; ++i)
     if (rec_passes(reca[i], pp.min_excess)) f((uint32_t)(reca[i].si >> 1), reca[i].pos);
   if (rb >= b.n_reads) return;
   const ReadSum sb = w.sums[rb];
-  const Rec *recb = w.rec_slots + rb * (uint64_t)w.cap;
+  const Rec *recb = w.rec_slots + slot_base(w, rb);
   const int nb = sb.unmapped ? 0 : sb.n_rec;
   for (int j = 0; j < nb; ++j) {
     if (!rec_passes(recb[j], pp.min_excess)) continue;

@@ -310,3 +310,27 @@ def test_two_shards_equal_one_run(case):
         for c in ctxs:
             c.close()
         ix.close()
+
+
+_GOLD_MEM = [(c, v) for c in ["case_basic", "case_adversarial"] for v in golden_variants(c) if v["mode"] == "mem"]
+
+
+@pytest.mark.parametrize("case_name,variant", _GOLD_MEM, ids=[f"{c}-{v['name']}" for c, v in _GOLD_MEM])
+def test_golden_mem_records(case_name, variant):
+    """-maxmatch (longSA::MEM): faithful control flow incl. the prefix=1 quirk, the expand_link threshold
+    and libstdc++ sort ties -- byte-exact vs what the reference printed."""
+    from smash_paper_b200 import api
+    g = load_golden_case(case_name)
+    hdr, lines = golden_lines(variant["path"])
+    oix = g["oix"]
+    ctx = api.Context.from_text(oix.text, oix.startpos, oix.sizes, oix.descr, w=4, mode=api.MODE_MEM,
+                                min_len=variant["min_len"], nomap=True)
+    try:
+        res = ctx.map_batch(g["reads"], want=api.WANT_SAM | api.WANT_MATCHES)
+        assert sorted(res.sam.splitlines(keepends=True)) == lines
+        osam, ooff, om = oix.map_batch(g["reads"], mode=O.MEM, min_len=variant["min_len"], n_threads=4, want_matches=True)
+        assert np.array_equal(res.match_off, ooff)
+        assert np.array_equal(res.matches, _triples(om))                      # emission order too
+        assert res.sam == osam
+    finally:
+        ctx.close()
