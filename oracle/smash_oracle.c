@@ -336,6 +336,39 @@ static void std_sort(int *v, int n, less_fn lt, const void *ctx) {
   }
 }
 
+/* longSA::MUM (longSA.cpp:549-585): MAM matches, sorted by (ref asc, len desc) with std::sort, then the
+ * MUMmer-3 cleanMUMcand sweep drops matches contained in / ending with an earlier one.  Survivors are
+ * handed on in that sorted order.  m[0..n) in place; returns the new count. */
+static int lt_by_ref(const void *ctx, int x, int y) {
+  const orc_match *M = (const orc_match *)ctx;
+  if (M[x].ref == M[y].ref) return M[x].len > M[y].len;
+  return M[x].ref < M[y].ref;
+}
+static uint64_t mum_clean(orc_match *m, uint64_t n) {
+  if (!n) return 0;
+  int *ord = (int *)malloc(sizeof(int) * n);
+  orc_match *tmp = (orc_match *)malloc(sizeof(orc_match) * n);
+  for (uint64_t i = 0; i < n; ++i) ord[i] = (int)i;
+  std_sort(ord, (int)n, lt_by_ref, m);
+  for (uint64_t i = 0; i < n; ++i) tmp[i] = m[ord[i]];
+  uint64_t out = 0, dbright = 0;
+  int ignoreprevious = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    int ignorecurrent = 0;
+    const uint64_t currentright = tmp[i].ref + tmp[i].len - 1;
+    if (dbright > currentright) ignorecurrent = 1;
+    else if (dbright == currentright) {
+      ignorecurrent = 1;
+      if (!ignoreprevious && i > 0 && tmp[i - 1].ref == tmp[i].ref) ignoreprevious = 1;
+    } else dbright = currentright;
+    if (i > 0 && !ignoreprevious) m[out++] = tmp[i - 1];
+    ignoreprevious = ignorecurrent;
+  }
+  if (!ignoreprevious) m[out++] = tmp[n - 1];
+  free(ord); free(tmp);
+  return out;
+}
+
 /* ------------------------------------------------------------------ records (query.cpp) */
 
 typedef struct {
@@ -401,6 +434,7 @@ static void run_read(const orc_index *ix, const orc_params *p, const uint8_t *se
     r->m_cap = s.n + 16; r->m = (orc_match *)realloc(r->m, sizeof(orc_match) * r->m_cap);
     s.out = r->m; s.cap = r->m_cap;
   }
+  if (p->mode == ORC_MUM) s.n = mum_clean(r->m, s.n);
   r->n_found = s.n;
   r->read_flag = read_flag; r->n = 0; r->n_aln = 0; r->best = -1; r->unmapped_placeholder = 0;
   rs_reserve(r, (int)s.n, q);

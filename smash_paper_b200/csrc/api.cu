@@ -274,6 +274,7 @@ static void set_search_params(smash_ctx *c) {
   sp.nucleotides_only = c->prm.nucleotides_only;
   sp.nomap = c->prm.nomap;
   sp.tag_mappability = c->prm.tag_mappability;
+  sp.mum = c->prm.mode == SMASH_MODE_MUM;
   // the anchor path enumerates seed buckets: only sensible when a k-mer of that length is rare
   const double expect = (double)c->dix.N / pow(4.0, (double)sp.k);
   sp.fast_ok = expect <= 16.0;
@@ -284,7 +285,7 @@ static void set_search_params(smash_ctx *c) {
 
 static int ctx_begin(const smash_params *p, smash_ctx **out) {
   if (smash_device_count() <= 0) return fail(SMASH_ERR_CUDA, "no sm_100 CUDA device available (this library has no CPU fallback)");
-  if (p->mode != SMASH_MODE_MAM && p->mode != SMASH_MODE_MEM) return fail(SMASH_ERR_ARG, "mode %d not supported (MAM or MEM)", p->mode);
+  if (p->mode != SMASH_MODE_MAM && p->mode != SMASH_MODE_MEM && p->mode != SMASH_MODE_MUM) return fail(SMASH_ERR_ARG, "mode %d not supported", p->mode);
   CU(cudaSetDevice(p->device));
   smash_ctx *c = new smash_ctx();
   c->prm = *p; c->device = p->device;

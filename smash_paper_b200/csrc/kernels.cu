@@ -193,8 +193,21 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
       for (int f = 0; f < ns; ++f) rank += sm.stage[warp][f].qpos < me.qpos;
       if (rank < w.cap) dst[rank] = me;
     }
+    int n_out = n;
+    if (sp.mum && n <= w.cap && n <= STAGE_CAP) {
+      // -mum: the sweep needs the matches in emission (query) order -> copy the ordered slots back into the
+      // stage, let lane 0 run the by_ref sort + cleanMUMcand sweep, survivors go to the slots in by_ref order
+      __syncwarp();
+      for (int e = lane; e < ns; e += 32) sm.stage[warp][e] = dst[e];
+      __syncwarp();
+      if (lane == 0) {
+        uint16_t ord[STAGE_CAP];
+        n_out = mum_clean(sm.stage[warp], ns, ord, dst);
+      }
+      n_out = __shfl_sync(0xffffffffu, n_out, 0);
+    }
     if (lane == 0) {
-      w.match_cnt[read] = (uint32_t)n;
+      w.match_cnt[read] = (uint32_t)n_out;
       if (n > w.cap || n > STAGE_CAP) atomicAdd(&w.flags[FLAG_OVERFLOW], 1u);
       atomicMax(&w.flags[FLAG_MAXCNT], (uint32_t)n);
     }

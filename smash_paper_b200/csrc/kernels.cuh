@@ -55,6 +55,7 @@ struct SearchParams {
   int nomap;
   int tag_mappability;
   int fast_ok;                 // 0 => every read takes the exact per-start path
+  int mum;                     // -mum: cleanMUMcand sweep over the MAM matches (longSA.cpp:549-585)
 };
 
 // launchers (all asynchronous on `st`); each returns the number of kernels it launched

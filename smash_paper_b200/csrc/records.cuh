@@ -150,6 +150,35 @@ struct LessPrint {   // to_print, query.cpp:221-229
   }
 };
 
+struct LessByRef {   // by_ref, longSA.cpp:492-499
+  const Match *m;
+  HDN bool operator()(uint16_t x, uint16_t y) const {
+    if (m[x].ref == m[y].ref) return m[x].len > m[y].len;
+    return m[x].ref < m[y].ref;
+  }
+};
+// longSA::MUM (longSA.cpp:549-585) after the MAM search: src[0..n) are the MAM matches in emission
+// order; dst receives the survivors of the cleanMUMcand sweep in by_ref order.  Returns their count.
+HDN inline int mum_clean(const Match *src, int n, uint16_t *ord, Match *dst) {
+  if (n <= 0) return 0;
+  for (int i = 0; i < n; ++i) ord[i] = (uint16_t)i;
+  StdSort<LessByRef> s{ord, LessByRef{src}}; s.run(n);
+  int out = 0; uint64_t dbright = 0; bool ignoreprevious = false;
+  for (int i = 0; i < n; ++i) {
+    bool ignorecurrent = false;
+    const uint64_t currentright = src[ord[i]].ref + src[ord[i]].len - 1;
+    if (dbright > currentright) ignorecurrent = true;
+    else if (dbright == currentright) {
+      ignorecurrent = true;
+      if (!ignoreprevious && i > 0 && src[ord[i - 1]].ref == src[ord[i]].ref) ignoreprevious = true;
+    } else dbright = currentright;
+    if (i > 0 && !ignoreprevious) dst[out++] = src[ord[i - 1]];
+    ignoreprevious = ignorecurrent;
+  }
+  if (!ignoreprevious) dst[out++] = src[ord[n - 1]];
+  return out;
+}
+
 // Alignment::resolve (query.cpp:68-97)
 HD void resolve_match(const DevIndex &ix, const Match &m, int q, Aln *a) {
   int lo = 0, hi = ix.n_descr;                       // upper_bound(startpos, ref)

@@ -334,3 +334,21 @@ def test_golden_mem_records(case_name, variant):
         assert res.sam == osam
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("min_len", [20, 14])
+def test_mum_mode(case, min_len):
+    """-mum (longSA::MUM, longSA.cpp:549-585): MAM + cleanMUMcand sweep, survivors in by_ref order."""
+    from smash_paper_b200 import api
+    ix = api.Index.open(case["fa"])
+    ctx = api.Context(ix, mode=api.MODE_MUM, min_len=min_len, nomap=True)
+    try:
+        osam, ooff, om = case["oix"].map_batch(case["reads"], mode=O.MUM, min_len=min_len, n_threads=4, want_matches=True)
+        res = ctx.map_batch(case["reads"], want=api.WANT_SAM | api.WANT_MATCHES)
+        assert np.array_equal(res.match_off, ooff) and np.array_equal(res.matches, _triples(om))
+        assert res.sam == osam
+    finally:
+        ctx.close(); ix.close()
+    if O.have_reference():
+        hdr, lines = O.ref_map(case["fa"], os.path.join(case["dir"], "reads.sam"), case["dir"], extra=["-mum", "-l", str(min_len)])
+        assert sorted(osam.splitlines(keepends=True)) == lines
