@@ -1,0 +1,310 @@
+// mummer_main.cpp -- `mummer`-compatible host driver (C++) over the C ABI of libsmash_b200.so.
+//
+// Same command line as the reference's mummer.cpp:73-183 (single-dash long flags), same <ref>.bin/
+// index files (loaded when present, otherwise built on the GPU and saved in the reference's formats),
+// same ./mapout/*.txt output (header of Sequence::sam_header + SAM records), same "Error\n<what>" /
+// exit 1 behaviour.  The query reader fills packed batches while the GPU still works on the previous
+// one (two slots, smash_submit / smash_wait) -- the counterpart of the reference's reader thread +
+// Pair workers (query.cpp:481-520, 614-687).
+#include <getopt.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/smash_b200.h"
+
+namespace {
+
+struct Options {
+  unsigned min_len = 20;
+  int mode = SMASH_MODE_MAM;
+  bool nucleotides_only = false, sam_out = false, verbose = false, nomap = false, rcref = false, fastq = false,
+       sam_in = false, mappability = false;
+  int threads = 2;
+  std::string ref;
+  std::vector<std::string> inputs;
+};
+
+[[noreturn]] void usage(const char *prog) {
+  std::cerr << "Usage: " << prog << " [options] <reference-file> <query-file> ...\n"
+            << "  -mum | -mumreference | -mumcand | -maxmatch   match type (default: -mumreference)\n"
+            << "  -l N   minimum match length (20)      -n   match only a, c, g, t\n"
+            << "  -samin -samout -nomap -rcref -fastq -verbose -qthreads N -mappability\n"
+            << "  -minblock N -cached -normalmem (accepted for compatibility)\n";
+  std::exit(1);
+}
+
+Options parse(int argc, char **argv) {
+  Options o;
+  enum { L = 1, MUMREF, MAXMATCH, MUM, MUMCAND, N, QTHREADS, SAMOUT, VERBOSE, NOMAP, RCREF, FASTQ, SAMIN, MAPPABILITY, CACHED, NORMALMEM, MINBLOCK };
+  static const option table[] = {
+      {"l", required_argument, nullptr, L},          {"mumreference", no_argument, nullptr, MUMREF},
+      {"maxmatch", no_argument, nullptr, MAXMATCH},  {"mum", no_argument, nullptr, MUM},
+      {"mumcand", no_argument, nullptr, MUMCAND},    {"n", no_argument, nullptr, N},
+      {"qthreads", required_argument, nullptr, QTHREADS}, {"samout", no_argument, nullptr, SAMOUT},
+      {"verbose", no_argument, nullptr, VERBOSE},    {"nomap", no_argument, nullptr, NOMAP},
+      {"rcref", no_argument, nullptr, RCREF},        {"fastq", no_argument, nullptr, FASTQ},
+      {"samin", no_argument, nullptr, SAMIN},        {"mappability", no_argument, nullptr, MAPPABILITY},
+      {"cached", no_argument, nullptr, CACHED},      {"normalmem", no_argument, nullptr, NORMALMEM},
+      {"minblock", required_argument, nullptr, MINBLOCK}, {nullptr, 0, nullptr, 0}};
+  for (;;) {
+    int idx = -1;
+    const int c = getopt_long_only(argc, argv, "", table, &idx);
+    if (c == -1) break;
+    switch (c) {
+      case L: o.min_len = (unsigned)atol(optarg); break;
+      case MUMREF: case MUMCAND: o.mode = SMASH_MODE_MAM; break;
+      case MAXMATCH: o.mode = SMASH_MODE_MEM; break;
+      case MUM: o.mode = SMASH_MODE_MUM; break;
+      case N: o.nucleotides_only = true; break;
+      case QTHREADS: o.threads = atoi(optarg); break;
+      case SAMOUT: o.sam_out = true; break;
+      case VERBOSE: o.verbose = true; break;
+      case NOMAP: o.nomap = true; break;
+      case RCREF: o.rcref = true; break;
+      case FASTQ: o.fastq = true; break;
+      case SAMIN: o.sam_in = true; break;
+      case MAPPABILITY: o.mappability = true; break;
+      case CACHED: case NORMALMEM: case MINBLOCK: break;
+      default: std::cerr << "Invalid arguments." << std::endl; usage(argv[0]);
+    }
+  }
+  if (argc - optind < 2) { std::cerr << "There are too few arguments" << std::endl; usage(argv[0]); }
+  if (o.fastq && o.sam_in) throw std::runtime_error("-fastq cannot be used with -samin");
+  if (o.nomap && !o.sam_out) throw std::runtime_error("-nomap can only be used with -sam_out");
+  if (o.mappability && !o.rcref) throw std::runtime_error("-mappability requires -rcref");
+  o.ref = argv[optind];
+  for (int i = optind + 1; i < argc; ++i) o.inputs.push_back(argv[i]);
+  return o;
+}
+
+void check(int rc) { if (rc) throw std::runtime_error(smash_last_error()); }
+
+// ---- reference text (Sequence build branch, fasta.cpp:138-203) ------------------------------------
+char complement(char c) {
+  switch (c) {
+    case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a';
+    case 'r': return 'y'; case 'y': return 'r'; case 'm': return 'k'; case 'k': return 'm';
+    case 'b': return 'v'; case 'd': return 'h'; case 'h': return 'd'; case 'v': return 'b';
+    default: return c;
+  }
+}
+struct RefText {
+  std::string text; std::vector<uint64_t> startpos, sizes; std::vector<std::string> descr;
+};
+RefText read_fasta(const std::string &path, bool rcref, bool verbose) {
+  std::ifstream in(path);
+  if (!in) throw std::runtime_error("unable to open " + path);
+  std::vector<std::string> names, seqs;
+  std::string line;
+  while (std::getline(in, line)) {
+    while (!line.empty() && (line.back() == '\r' || line.back() == ' ')) line.pop_back();
+    size_t b = 0; while (b < line.size() && line[b] == ' ') ++b;
+    if (b == line.size()) continue;
+    if (line[b] == '>') {
+      size_t s = b + 1; while (s < line.size() && line[s] == ' ') ++s;
+      size_t e = line.find(' ', s);
+      names.push_back(line.substr(s, e == std::string::npos ? std::string::npos : e - s));
+      seqs.emplace_back();
+    } else if (!seqs.empty()) {
+      for (size_t i = b; i < line.size(); ++i) seqs.back().push_back((char)tolower((unsigned char)line[i]));
+    }
+  }
+  RefText r;
+  for (size_t k = 0; k < names.size(); ++k) {
+    const bool last = k + 1 == names.size();
+    const std::string &s = seqs[k];
+    if (verbose) std::cerr << "# " << names[k] << " " << s.size() << " " << r.text.size() << std::endl;
+    r.startpos.push_back(r.text.size()); r.sizes.push_back(s.size()); r.descr.push_back(names[k]);
+    r.text += s;
+    if (rcref || !last) r.text.push_back('`');
+    if (rcref) {
+      r.startpos.push_back(r.text.size()); r.sizes.push_back(s.size()); r.descr.push_back(names[k]);
+      for (size_t i = s.size(); i-- > 0;) r.text.push_back(complement(s[i]));
+      if (!last) r.text.push_back('`');
+    }
+  }
+  r.text.push_back('$');
+  return r;
+}
+
+// ---- packed batch (what crosses the ABI) ------------------------------------------------------------
+struct Batch {
+  std::vector<uint8_t> names, seq, qual, opt;
+  std::vector<int64_t> name_off{0}, seq_off{0}, opt_off{0};
+  std::vector<uint16_t> read_flag;
+  size_t n() const { return read_flag.size(); }
+  void clear() { names.clear(); seq.clear(); qual.clear(); opt.clear(); name_off.assign(1, 0); seq_off.assign(1, 0); opt_off.assign(1, 0); read_flag.clear(); }
+  // QueryReader::run + Aligner::reset (query.cpp:643-644, 185-201)
+  void add(std::string name, unsigned flag, bool from_flag, const std::string &s, const std::string &q, const std::string &optional) {
+    if (from_flag) { if (flag & 64) name += ":0"; else if (flag & 128) name += ":1"; }
+    uint16_t rf = 0;
+    if (name.size() >= 2 && name[name.size() - 2] == ':') {
+      if (name.back() == '0') { name.resize(name.size() - 2); rf = 65; }
+      else if (name.back() == '1') { name.resize(name.size() - 2); rf = 129; }
+    }
+    names.insert(names.end(), name.begin(), name.end()); name_off.push_back((int64_t)names.size());
+    size_t end = s.size(); while (end && s[end - 1] == ' ') --end;
+    size_t len = 0;
+    for (size_t i = 0; i < end; ++i) if (s[i] != ' ') { seq.push_back((uint8_t)s[i]); ++len; }
+    std::string qq = q.empty() ? std::string(len, '!') : q;          // Aligner::run, query.cpp:323
+    qq.resize(len, '!');
+    qual.insert(qual.end(), qq.begin(), qq.end());
+    seq_off.push_back((int64_t)seq.size());
+    opt.insert(opt.end(), optional.begin(), optional.end()); opt_off.push_back((int64_t)opt.size());
+    read_flag.push_back(rf);
+  }
+  smash_batch view(uint64_t first_pair) const {
+    smash_batch b{};
+    b.n_reads = n(); b.names = names.data(); b.name_off = name_off.data(); b.seq = seq.data(); b.qual = qual.data();
+    b.seq_off = seq_off.data(); b.opt = opt.empty() ? nullptr : opt.data(); b.opt_off = opt.empty() ? nullptr : opt_off.data();
+    b.read_flag = read_flag.data(); b.first_pair_ordinal = first_pair;
+    return b;
+  }
+};
+
+// one input record per call; false at end of file
+struct QueryParser {
+  std::ifstream in; const Options &o;
+  QueryParser(const std::string &path, const Options &opt) : in(path), o(opt) { if (!in) throw std::runtime_error("unable to open " + path); }
+  bool next(Batch &b) {
+    std::string line;
+    while (std::getline(in, line)) {
+      if (line.empty()) continue;
+      if (o.sam_in) {                                    // query.cpp:639-648
+        std::istringstream f(line);
+        std::string name, ref, pos, mapq, cigar, mref, mpos, tlen, seq, errors, tok, optional;
+        unsigned flag = 0;
+        f >> name >> flag >> ref >> pos >> mapq >> cigar >> mref >> mpos >> tlen >> seq >> errors;
+        while (f >> tok) { optional += "\t"; optional += tok; }
+        b.add(name, flag, true, seq, errors, optional);
+        return true;
+      }
+      const char start = o.fastq ? '@' : '>';          // query.cpp:649-680
+      if (line[0] != start) throw std::runtime_error(std::string("missing query start character ") + start + " in input line " + line);
+      size_t s = 1; while (s < line.size() && line[s] == ' ') ++s;
+      size_t e = line.size(); while (e > s && line[e - 1] == ' ') --e;
+      std::string meta;
+      for (size_t i = s; i < e; ++i) {
+        if (line[i] == ' ') { if (i + 1 != e) { if (line[i + 1] == '1') meta += ":0"; else if (line[i + 1] == '2') meta += ":1"; } break; }
+        meta += line[i];
+      }
+      std::string seq, errors, plus;
+      if (!std::getline(in, seq) || seq.empty()) throw std::runtime_error("empty sequence");
+      if (o.fastq) { std::getline(in, plus); std::getline(in, errors); if (errors.empty()) throw std::runtime_error("empty errors"); }
+      b.add(meta, 0, false, seq, errors, "");
+      return true;
+    }
+    return false;
+  }
+};
+
+bool readable(const std::string &p) { return access(p.c_str(), R_OK) == 0; }
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  try {
+    const Options o = parse(argc, argv);
+    smash_params p; smash_params_default(&p);
+    p.mode = o.mode; p.min_len = o.min_len; p.nomap = o.nomap; p.nucleotides_only = o.nucleotides_only;
+    const std::string base = o.ref + ".bin/rc" + (o.rcref ? "1" : "0");
+    const bool have_index = readable(base + ".i4.index.bin") || readable(base + ".i8.index.bin");
+    smash_index *ix = nullptr; smash_ctx *ctx = nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    if (have_index) {
+      if (o.verbose) std::cerr << "# loading reference binary\n# loading index binary" << std::endl;
+      check(smash_index_open(o.ref.c_str(), o.rcref, &ix));
+      check(smash_ctx_create(ix, &p, &ctx));
+    } else {
+      if (o.verbose) std::cerr << "# loading reference from fasta" << std::endl;
+      RefText r = read_fasta(o.ref, o.rcref, o.verbose);
+      if (o.verbose) std::cerr << "# seq_vec.length=" << r.text.size() << "\n# creating index from reference" << std::endl;
+      std::vector<const char *> d; for (auto &s : r.descr) d.push_back(s.c_str());
+      const uint64_t N = r.text.size();
+      const int w = N >= 0xffffffffull - 100000 ? 8 : 4;             // mummer.cpp:156-183
+      check(smash_ctx_create_from_text((const uint8_t *)r.text.data(), N, r.descr.size(), r.startpos.data(), r.sizes.data(),
+                                       d.data(), o.rcref, w, 1, 0, &p, &ctx));
+      if (o.verbose) std::cerr << "# saving index" << std::endl;
+      check(smash_ctx_save_index(ctx, o.ref.c_str(), 0));
+      check(smash_index_open(o.ref.c_str(), o.rcref, &ix));
+    }
+    if (o.verbose)
+      std::cerr << "# constructed index in "
+                << std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - t0).count() << " seconds" << std::endl;
+    if (o.mappability) {                                             // mummer.cpp:50-53
+      check(smash_ctx_build_mappability(ctx, nullptr, 0));
+      // total forward bases = sum of @SQ lengths
+      std::vector<char> hdr(smash_index_sam_header(ix, nullptr, 0));
+      smash_index_sam_header(ix, hdr.data(), hdr.size());
+      uint64_t total = 0;
+      { std::istringstream hs(std::string(hdr.begin(), hdr.end())); std::string l;
+        while (std::getline(hs, l)) { size_t k = l.find("\tLN:"); if (l.rfind("@SQ", 0) == 0 && k != std::string::npos) total += strtoull(l.c_str() + k + 4, nullptr, 10); } }
+      std::vector<uint8_t> body(2 * total);
+      check(smash_ctx_build_mappability(ctx, body.data(), body.size()));
+      FILE *f = fopen(o.inputs[0].c_str(), "wb");
+      if (!f) throw std::runtime_error("could not open outfile " + o.inputs[0] + " for writing");
+      fputc(0, f); fputc(0, f);                                      // the reference's two junk bytes
+      fwrite(body.data(), 1, body.size(), f); fclose(f);
+      smash_ctx_destroy(ctx); smash_index_close(ix);
+      return 0;
+    }
+    std::vector<char> header(smash_index_sam_header(ix, nullptr, 0));
+    smash_index_sam_header(ix, header.data(), header.size());
+    if (o.verbose) std::cerr << "# running " << o.threads << " threads to answer queries\n# running " << o.inputs.size() << " query reader" << std::endl;
+    const size_t BATCH = 1u << 20;                                   // reads per batch (even)
+    uint64_t n_queries = 0, chunk = 0, pairs_done = 0;
+    const auto tq = std::chrono::steady_clock::now();
+    for (size_t fi = 0; fi < o.inputs.size(); ++fi) {
+      QueryParser qp(o.inputs[fi], o);
+      Batch buf[SMASH_N_SLOTS];
+      bool in_flight[SMASH_N_SLOTS] = {false, false};
+      auto drain = [&](int slot) {
+        smash_result r; check(smash_wait(ctx, slot, &r));
+        in_flight[slot] = false;
+        if (o.sam_out && r.sam_bytes) {
+          mkdir("mapout", 0755);
+          const std::string fn = "mapout/mapoutb200_" + std::to_string(fi) + "." + std::to_string(++chunk) + ".txt";
+          FILE *f = fopen(fn.c_str(), "wb");
+          if (!f) throw std::runtime_error("Problem opening out file");
+          fwrite(header.data(), 1, header.size(), f); fwrite(r.sam, 1, r.sam_bytes, f); fclose(f);
+        }
+      };
+      int slot = 0; bool more = true;
+      while (more) {
+        if (in_flight[slot]) drain(slot);
+        Batch &b = buf[slot]; b.clear();
+        while (b.n() < BATCH && (more = qp.next(b))) {}
+        if (b.n()) {
+          smash_batch v = b.view(pairs_done);
+          check(smash_submit(ctx, slot, &v, SMASH_WANT_SAM));      // the other slot's batch is still on the GPU
+          in_flight[slot] = true; n_queries += b.n(); pairs_done += (b.n() + 1) / 2;
+          slot = (slot + 1) % SMASH_N_SLOTS;
+        }
+      }
+      for (int s = 0; s < SMASH_N_SLOTS; ++s) { const int k = (slot + s) % SMASH_N_SLOTS; if (in_flight[k]) drain(k); }
+      if (o.verbose) std::cerr << "# query reader for " << o.inputs[fi] << " processed " << n_queries << " sequences" << std::endl;
+    }
+    if (!n_queries) std::cerr << "# no reads processed" << std::endl;
+    if (o.verbose)
+      std::cerr << "# ran " << n_queries << " queries in "
+                << std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - tq).count() << " seconds" << std::endl;
+    smash_ctx_destroy(ctx); smash_index_close(ix);
+    return 0;
+  } catch (const std::exception &e) {
+    const std::string what = e.what();
+    if (what.rfind("unable to open", 0) == 0) { std::cerr << what << std::endl; return 1; }   // reader thread path, query.cpp:689-695
+    std::cerr << "Error" << std::endl << what << std::endl;                                   // mummer.cpp:61-65
+    return 1;
+  }
+}

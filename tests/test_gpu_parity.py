@@ -229,10 +229,14 @@ def test_golden_map_bin():
             ctx.close()
 
 
-def test_mummer_compatible_driver(case, workdir):
-    """python -m smash_paper_b200.mummer: same flags, same files; index built on GPU when absent."""
+@pytest.mark.parametrize("driver", ["cxx", "python"])
+def test_mummer_compatible_driver(case, workdir, driver):
+    """The drop-in `mummer` (C++ binary over the C ABI, and its Python twin): same flags, same files;
+    index built on the GPU when absent."""
     import shutil, subprocess, sys, glob
-    d = os.path.join(workdir, "driver")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = [os.path.join(root, "smash_paper_b200", "bin", "mummer")] if driver == "cxx" else [sys.executable, "-m", "smash_paper_b200.mummer"]
+    d = os.path.join(workdir, "driver_" + driver)
     shutil.rmtree(d, ignore_errors=True)
     os.makedirs(d)
     fa = os.path.join(d, "ref.fa")
@@ -240,24 +244,24 @@ def test_mummer_compatible_driver(case, workdir):
     shutil.copy(os.path.join(case["dir"], "reads.sam"), os.path.join(d, "reads.sam"))
     env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     # index build (index_setup.sh:19): exits 1 on 'dummy' by design, leaves <fa>.bin/ behind
-    r = subprocess.run([sys.executable, "-m", "smash_paper_b200.mummer", "-verbose", "-rcref", fa, "dummy"], cwd=d, env=env,
+    r = subprocess.run(exe + ["-verbose", "-rcref", fa, "dummy"], cwd=d, env=env,
                        capture_output=True, text=True)
     assert r.returncode == 1 and "unable to open dummy" in r.stderr
     import filecmp
     for f in ["rc1.ref.bin", "rc1.ref.seq.bin", "rc1.i4.index.bin", "rc1.i4.index.sa.bin", "rc1.i4.index.isa.bin",
               "rc1.i4.index.lcp.vec.bin", "rc1.i4.index.lcp.m.bin"]:
         assert filecmp.cmp(os.path.join(fa + ".bin", f), os.path.join(case["fa"] + ".bin", f), shallow=False), f
-    r = subprocess.run([sys.executable, "-m", "smash_paper_b200.mummer", "-rcref", "-mappability", fa, fa + ".bin/map.bin"],
+    r = subprocess.run(exe + ["-rcref", "-mappability", fa, fa + ".bin/map.bin"],
                        cwd=d, env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert np.array_equal(np.fromfile(fa + ".bin/map.bin", dtype=np.uint8)[2:], case["body"])
-    r = subprocess.run([sys.executable, "-m", "smash_paper_b200.mummer", "-rcref", "-qthreads", "12", "-nomap", "-samin", "-samout",
+    r = subprocess.run(exe + ["-rcref", "-qthreads", "12", "-nomap", "-samin", "-samout",
                         fa, "reads.sam"], cwd=d, env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     got = b"".join(open(f, "rb").read() for f in sorted(glob.glob(os.path.join(d, "mapout", "*.txt"))))
     exp = case["oix"].sam_header().encode() + case["oix"].map_batch(case["reads"], min_len=20, n_threads=4)
     assert got == exp
-    r = subprocess.run([sys.executable, "-m", "smash_paper_b200.mummer", "-rcref", "-nomap", fa, "reads.sam"], cwd=d, env=env,
+    r = subprocess.run(exe + ["-rcref", "-nomap", fa, "reads.sam"], cwd=d, env=env,
                        capture_output=True, text=True)
     assert r.returncode == 1 and r.stderr.startswith("Error\n-nomap can only be used with -sam_out")
 
