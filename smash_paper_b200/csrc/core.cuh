@@ -217,40 +217,55 @@ HD bool exact_start(const DevIndex &ix, const uint8_t *P, int q, int p, uint32_t
   return true;
 }
 
-// Fast path for one anchor x = a*s (see DESIGN.md "mam_search"): every reportable match whose
-// start lies in (x-s, x] contains P[x..x+k); enumerate the seed bucket, extend each candidate
-// along its diagonal in the text and keep those that are long enough and unique.
-// Returns the number of matches appended to out (<= cap), or -1 if the anchor needs the exact path.
-HD int anchor_candidates(const DevIndex &ix, const uint8_t *P, int q, int x, int s, int k,
-                         uint32_t L, Match *out, int cap) {
-  uint64_t code = 0;
-  for (int j = 0; j < k; ++j) {
-    int b = base_code(P[x + j]);
-    if (b > 3) return 0;            // caller guarantees such a char is not in the text alphabet
-    code = (code << 2) | (uint64_t)b;
-  }
+// ---- anchor path building blocks ------------------------------------------------
+// 2-bit codes (a,c,g,t -> 0..3) of 4 consecutive read bytes, first byte in the top bits of the result
+// byte.  Bytes must be acgt (validity is tracked separately in a per-read bit mask).
+HD uint32_t code4(uint32_t w) {
+  uint32_t y = (w >> 1) & 0x03030303u;          // a,c,g,t -> 0,1,3,2
+  y ^= (y >> 1) & 0x01010101u;                  //         -> 0,1,2,3
+  return (y * 0x40100401u) >> 24;               // c0<<6 | c1<<4 | c2<<2 | c3
+}
+// k-mer code of P[x..x+k), k <= 16
+HD uint32_t kmer_code(const uint8_t *P, int x, int k) {
+  const uint64_t w0 = read8(P, x), w1 = read8(P, x + 8);
+  const uint32_t c = (code4((uint32_t)w0) << 24) | (code4((uint32_t)(w0 >> 32)) << 16) |
+                     (code4((uint32_t)w1) << 8) | code4((uint32_t)(w1 >> 32));
+  return k >= 16 ? c : c >> (2 * (16 - k));
+}
+// does P[x..x+k) contain a non-acgt byte?  inv: one bit per base (bit j of word j>>5), one spare word
+HD bool kmer_invalid(const uint32_t *inv, int x, int k) {
+  const int wd = x >> 5, sh = x & 31;
+  uint32_t m = inv[wd] >> sh;
+  if (sh) m |= inv[wd + 1] << (32 - sh);
+  return (m & ((k >= 32 ? 0u : (1u << k)) - 1u)) != 0;
+}
+// seed bucket of anchor x: [lo, hi) in SA order (a sorted superset of the k-mer's interval)
+HD void anchor_bucket(const DevIndex &ix, const uint8_t *P, int x, int k, uint64_t *lo, uint64_t *hi) {
+  const uint64_t code = kmer_code(P, x, k);
   const int sh = 2 * (ix.seed_k - k);
-  const uint64_t lo = seed_at(ix, code << sh), hi = seed_at(ix, (code + 1) << sh);
-  if (hi - lo > (uint64_t)BIG_BUCKET) return -1;
+  *lo = seed_at(ix, code << sh);
+  *hi = seed_at(ix, (code + 1) << sh);
+}
+// One candidate suffix c = SA[i] of anchor x (stride s): extend along the diagonal.
+//   returns 1 and fills m   -> a reportable match owned by this anchor
+//           0               -> nothing (junk, owned by an earlier anchor, too short, not unique)
+//          -1               -> U saturated: *pl holds the start whose exact answer the caller must compute
+HD int candidate_check(const DevIndex &ix, const uint8_t *P, int q, int x, int s, int k, uint32_t L, uint64_t c,
+                       Match *m, int *pl) {
   const uint8_t *T = ix.text;
-  int n = 0;
-  for (uint64_t i = lo; i < hi; ++i) {
-    const uint64_t c = sa_at(ix, i);
-    const int right = match_right(T, (int64_t)c, P, x, q - x);
-    if (right < k) continue;        // bucket is a superset: suffixes between two k-mers
-    // the 0xFE pad before the read and the zero pad before the text stop this at either start
-    const int left = match_left(T, (int64_t)c, P, x, s);
-    if (left >= s) continue;        // start <= x-s: an earlier anchor owns this diagonal
-    const uint32_t len = (uint32_t)(left + right);
-    if (len < L || len < 2) continue;
-    const uint64_t ref = c - (uint64_t)left;
-    uint8_t u = ix.uniq[ref];
-    if (u == 255 && len >= 255) return -1;
-    if (len < u) continue;
-    if (n < cap) { out[n].ref = ref; out[n].qpos = (uint32_t)(x - left); out[n].len = len; }
-    ++n;
-  }
-  return n;
+  // ownership first: the 0xFE pad before the read and the zero pad before the text stop this at either start
+  const int left = match_left(T, (int64_t)c, P, x, s);
+  if (left >= s) return 0;               // start <= x-s: an earlier anchor owns this diagonal
+  const int right = match_right(T, (int64_t)c, P, x, q - x);
+  if (right < k) return 0;               // bucket is a superset: suffixes between two k-mers
+  const uint32_t len = (uint32_t)(left + right);
+  if (len < L || len < 2) return 0;
+  const uint64_t ref = c - (uint64_t)left;
+  const uint8_t u = ix.uniq[ref];
+  if (u == 255 && len >= 255) { *pl = x - left; return -1; }
+  if (len < u) return 0;
+  m->ref = ref; m->qpos = (uint32_t)(x - left); m->len = len;
+  return 1;
 }
 
 }  // namespace smash

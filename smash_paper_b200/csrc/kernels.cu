@@ -122,16 +122,39 @@ __device__ __forceinline__ bool stage_read(const DevIndex &ix, const uint8_t *__
 }
 
 // ------------------------------------------------------------------ K1: MAM search
+//
+// One warp per read.  (1) lanes = anchors: SWAR k-mer code from the staged read, seed-table lookup,
+// bucket size.  (2) every (anchor, suffix) candidate of the read becomes one task in a shared-memory
+// list (warp prefix sum) so that (3) lanes = candidates: all lanes extend different candidates at
+// once -- SA entry, text words and the U byte of different candidates are in flight together and no
+// lane waits for a neighbour with a bigger bucket.  (4) matches are rank-sorted by query offset and
+// written in order.
+constexpr int TASK_CAP = 128;
 
 struct SearchSmem {
   uint8_t pbuf[WARPS][PBUF];
+  uint32_t inv[WARPS][MAXQ_FAST / 32 + 2];     // non-acgt mask of the read, one bit per base
   Match stage[WARPS][STAGE_CAP];
+  uint64_t task_sa[WARPS][TASK_CAP];           // SA index of the candidate
+  uint16_t task_x[WARPS][TASK_CAP];            // its anchor position
   int nstage[WARPS];
 };
 
 __device__ __forceinline__ void stage_push(SearchSmem &sm, int warp, const Match &m) {
   const int slot = atomicAdd(&sm.nstage[warp], 1);
   if (slot < STAGE_CAP) sm.stage[warp][slot] = m;
+}
+// lanes = tasks: extend every queued candidate
+__device__ __forceinline__ void run_tasks(const DevIndex &ix, SearchSmem &sm, int warp, int lane, const uint8_t *P, int q,
+                                          const SearchParams &sp, int ntask) {
+  for (int t = lane; t < ntask; t += 32) {
+    const uint64_t c = sa_at(ix, sm.task_sa[warp][t]);
+    Match m; int pl = 0;
+    const int r = candidate_check(ix, P, q, (int)sm.task_x[warp][t], sp.s, sp.k, sp.L, c, &m, &pl);
+    if (r > 0) stage_push(sm, warp, m);
+    else if (r < 0 && exact_start(ix, P, q, pl, sp.L, &m)) stage_push(sm, warp, m);
+  }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(THREADS)
@@ -153,19 +176,26 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     const int L = (int)sp.L;
     if (q >= L) {
       if (!odd && sp.fast_ok) {
+        // non-acgt mask (such bytes do not occur in the text here, so no match can contain them)
+        for (int c0 = 0; c0 <= q / 32 + 1; ++c0) {
+          const int j = c0 * 32 + lane;
+          const unsigned bad = __ballot_sync(0xffffffffu, j < q && base_code(P[j]) > 3);
+          if (lane == 0) sm.inv[warp][c0] = bad;
+        }
+        __syncwarp();
         const int s = sp.s, k = sp.k;
         const int n_anchor = (q - L + s - 1) / s + 1;        // anchors x = a*s cover starts 0..q-L
+        int ntask = 0;
         for (int a0 = 0; a0 < n_anchor; a0 += 32) {
           const int a = a0 + lane;
-          int r = 0;
-          Match loc[LANE_CAP];
-          if (a < n_anchor) {
-            r = anchor_candidates(ix, P, q, a * s, s, k, sp.L, loc, LANE_CAP);
-            if (r > LANE_CAP) r = -1;
-            for (int i = 0; i < r; ++i) stage_push(sm, warp, loc[i]);
+          uint64_t lo = 0, hi = 0;
+          bool big = false;
+          if (a < n_anchor && !kmer_invalid(sm.inv[warp], a * s, k)) {
+            anchor_bucket(ix, P, a * s, k, &lo, &hi);
+            if (hi - lo > (uint64_t)BIG_BUCKET) { big = true; hi = lo; }
           }
-          unsigned slow = __ballot_sync(0xffffffffu, r < 0);
-          while (slow) {                                     // exact per-start search for that window
+          unsigned slow = __ballot_sync(0xffffffffu, big);
+          while (slow) {                                     // huge bucket: exact per-start search for that window
             const int la = __ffs((int)slow) - 1; slow &= slow - 1;
             const int x = (a0 + la) * s;
             const int p_lo = x - s + 1 > 0 ? x - s + 1 : 0;
@@ -174,7 +204,28 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
               if (exact_start(ix, P, q, p, sp.L, &m)) stage_push(sm, warp, m);
             }
           }
+          // queue this round's candidates; flush the list whenever the round would not fit
+          int cnt = (int)(hi - lo);
+          int inc = cnt;
+          for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+          const int total = __shfl_sync(0xffffffffu, inc, 31);
+          if (ntask + total > TASK_CAP) { run_tasks(ix, sm, warp, lane, P, q, sp, ntask); ntask = 0; }
+          if (total > TASK_CAP) {                            // cannot happen: 32 * BIG_BUCKET > TASK_CAP only if many full buckets
+            for (int l2 = 0; l2 < 32; ++l2) {                // degrade gracefully: one lane's bucket at a time
+              const int c2 = __shfl_sync(0xffffffffu, cnt, l2);
+              const uint64_t lo2 = __shfl_sync(0xffffffffu, lo, l2);
+              for (int i = lane; i < c2; i += 32) { sm.task_sa[warp][i] = lo2 + (uint64_t)i; sm.task_x[warp][i] = (uint16_t)((a0 + l2) * s); }
+              __syncwarp();
+              run_tasks(ix, sm, warp, lane, P, q, sp, c2);
+            }
+          } else {
+            const int base = ntask + inc - cnt;
+            for (int i = 0; i < cnt; ++i) { sm.task_sa[warp][base + i] = lo + (uint64_t)i; sm.task_x[warp][base + i] = (uint16_t)(a * s); }
+            ntask += total;
+            __syncwarp();
+          }
         }
+        run_tasks(ix, sm, warp, lane, P, q, sp, ntask);
       } else {
         for (int p = lane; p + L <= q; p += 32) {
           Match m;

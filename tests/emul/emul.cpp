@@ -110,14 +110,23 @@ static int emul_search(const DevIndex &ix, const uint8_t *seq, int q, uint32_t m
   if (q >= (int)L) {
     if (!odd && fast_ok) {
       const int n_anchor = (q - (int)L + s - 1) / s + 1;
+      std::vector<uint32_t> inv(q / 32 + 3, 0);
+      for (int j = 0; j < q; ++j) if (base_code(P[j]) > 3) inv[j >> 5] |= 1u << (j & 31);
       for (int a = 0; a < n_anchor; ++a) {
-        Match loc[4];
-        int r = anchor_candidates(ix, P, q, a * s, s, k, L, loc, 4);
-        if (r > 4) r = -1;
-        for (int i = 0; i < r; ++i) stage.push_back(loc[i]);
-        if (r < 0) {
-          const int x = a * s, p_lo = x - s + 1 > 0 ? x - s + 1 : 0;
+        const int x = a * s;
+        if (kmer_invalid(inv.data(), x, k)) continue;
+        uint64_t lo, hi;
+        anchor_bucket(ix, P, x, k, &lo, &hi);
+        if (hi - lo > (uint64_t)BIG_BUCKET) {
+          const int p_lo = x - s + 1 > 0 ? x - s + 1 : 0;
           for (int p = p_lo; p <= x; ++p) { Match m; if (exact_start(ix, P, q, p, L, &m)) stage.push_back(m); }
+          continue;
+        }
+        for (uint64_t i = lo; i < hi; ++i) {
+          Match m; int pl = 0;
+          const int r = candidate_check(ix, P, q, x, s, k, L, sa_at(ix, i), &m, &pl);
+          if (r > 0) stage.push_back(m);
+          else if (r < 0 && exact_start(ix, P, q, pl, L, &m)) stage.push_back(m);
         }
       }
     } else {

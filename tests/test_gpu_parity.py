@@ -356,3 +356,53 @@ def test_mum_mode(case, min_len):
     if O.have_reference():
         hdr, lines = O.ref_map(case["fa"], os.path.join(case["dir"], "reads.sam"), case["dir"], extra=["-mum", "-l", str(min_len)])
         assert sorted(osam.splitlines(keepends=True)) == lines
+
+
+def test_large_sample_parity_and_invariants():
+    """10 Mb reference, 120k reads: byte-exact SAM vs the oracle on the GPU-built index, plus the
+    size-independent properties used at BASELINE.json's full sizes: batch-split invariance of SAM and
+    counts, sum(counts) == reads kept, records == SAM lines, NH/HI consistency."""
+    from smash_paper_b200 import api, samio, sequence, synth
+    ref = synth.make_reference([(f"chr{i + 1}", 2_500_000) for i in range(4)], seed=17, n_families=60, n_long=4)
+    text, startpos, sizes, descr = sequence.text_from_chromosomes(ref.names, ref.seqs)
+    reads = synth.make_reads_fast(ref.concat(), 60_000, seed=5)
+    ctx = api.Context.from_text(text, startpos, sizes, descr, min_len=20, nomap=True)
+    try:
+        sa, isa, vec, m = ctx.copy_index(len(text), 4)
+        lcpm = np.zeros(len(m) // 16, dtype=O.LCPM_DT)
+        if len(m):
+            r = m.reshape(-1, 16)
+            lcpm["idx"] = r[:, :8].copy().view("<u8").reshape(-1); lcpm["val"] = r[:, 8:12].copy().view("<u4").reshape(-1)
+        oix = O.Index(text, sa, isa, vec, lcpm, startpos, sizes, descr, 1, 4)
+        exp = oix.map_batch(reads, min_len=20, n_threads=os.cpu_count() or 4)
+        ctx.build_mappability(ref.total)
+        starts = np.arange(0, ref.total, 50_000, dtype=np.int64)
+        ctx.tail_configure(starts, ref.names, ref.offsets())
+        res = ctx.map_batch(reads, want=api.WANT_SAM | api.WANT_TAIL)
+        assert res.sam == exp
+        counts, st = ctx.tail_finish()
+        assert counts.sum() == st["reads_kept"] and st["total_reads"] == st["reads_kept"] + st["dups_removed"]
+        assert res.sam.count(b"\n") == sum(1 for _ in exp.splitlines())
+        # the same reads in 5 uneven batches: identical SAM bytes and identical counts
+        ctx.tail_reset()
+        cuts = [0, 10_000, 10_002, 55_554, 90_000, reads.n]
+        parts = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            parts.append(ctx.map_batch(samio.slice_batch(reads, a, b), want=api.WANT_SAM | api.WANT_TAIL, first_pair=a // 2).sam)
+        assert b"".join(parts) == exp
+        counts2, st2 = ctx.tail_finish()
+        assert np.array_equal(counts, counts2) and st == st2
+        # NH == number of records of the read, HI = 0..NH-1 in order
+        import re
+        by_read = {}
+        for ln in exp.splitlines()[:50_000]:
+            f = ln.split(b"\t")
+            mm = re.search(rb"NH:i:(\d+)(?:\tHI:i:(\d+))?", ln)
+            by_read.setdefault((f[0], int(f[1]) & 192), []).append((int(mm.group(1)), int(mm.group(2)) if mm.group(2) else 0))
+        for recs in list(by_read.values())[:-1]:
+            if recs[0][0] == 0:
+                assert len(recs) == 1
+            else:
+                assert [h for _, h in recs] == list(range(len(recs))) and all(n == len(recs) for n, _ in recs)
+    finally:
+        ctx.close()
