@@ -234,7 +234,7 @@ struct smash_ctx {
   SearchParams sp{};
   // index storage
   uint8_t *text_alloc = nullptr; void *sa = nullptr; void *isa = nullptr; uint8_t *lcp = nullptr;
-  LcpItem *lcp_m = nullptr; uint8_t *uniq = nullptr; void *seed = nullptr; uint64_t *startpos = nullptr;
+  LcpItem *lcp_m = nullptr; uint8_t *uniq = nullptr; void *seed = nullptr; uint16_t *ext = nullptr; uint64_t *startpos = nullptr;
   uint64_t *sizes = nullptr; char *descr = nullptr; int *descr_off = nullptr; uint32_t *alpha = nullptr;
   uint8_t *mapbody = nullptr; uint32_t *chrom_off32 = nullptr;
   uint64_t n_m = 0;
@@ -344,9 +344,16 @@ static int ctx_finish(smash_ctx *c, const smash_index *ix) {
   CK(dmalloc(&c->seed, ((1ull << (2 * k)) + 1) * d.seed_w, &c->index_bytes));
   c->launches += launch_seed_build(d, c->seed, k, d.seed_w, st);
   d.seed = c->seed;
+  set_search_params(c);
+  d.ext = nullptr;
+  if (c->prm.mode != SMASH_MODE_MEM && c->sp.fast_ok && (double)N / pow(4.0, (double)c->sp.k) >= 0.25) {
+    // the 4+4 character pre-filter pays off when chance hits of the seed are common (large references)
+    CK(dmalloc((void **)&c->ext, 2 * N, &c->index_bytes));
+    c->launches += launch_ext_build(d, c->sp.k, c->ext, st);
+    d.ext = c->ext;
+  }
   CUC(cudaStreamSynchronize(st));
   CUC(cudaGetLastError());
-  set_search_params(c);
   tail_init(&c->tail);
   return 0;
 }
@@ -535,7 +542,7 @@ extern "C" void smash_ctx_destroy(smash_ctx *c) {
   cudaDeviceSynchronize();
   for (int s = 0; s < SMASH_N_SLOTS; ++s) slot_release(c->slot[s]);
   tail_release(&c->tail);
-  void *ptrs[] = {c->text_alloc, c->sa, c->isa, c->lcp, c->lcp_m, c->uniq, c->seed, c->startpos, c->sizes,
+  void *ptrs[] = {c->ext, c->text_alloc, c->sa, c->isa, c->lcp, c->lcp_m, c->uniq, c->seed, c->startpos, c->sizes,
                   c->descr, c->descr_off, c->alpha, c->mapbody, c->chrom_off32};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->own_index) delete c->own_index;

@@ -87,6 +87,24 @@ __global__ void k_seed_build(DevIndex ix, SeedT *__restrict__ seed, int k) {
   }
 }
 
+__global__ void k_ext_build(DevIndex ix, int k, uint16_t *__restrict__ ext) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ix.N; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t c = sa_at(ix, i);
+    uint32_t r = 0, l = 0;
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t pr = c + (uint64_t)k + (uint64_t)j;
+      const int br = pr < ix.N ? base_code(ix.text[pr]) : 4;
+      r = (r << 2) | (uint32_t)(br > 3 ? 0 : br);
+      const int bl = c > (uint64_t)j ? base_code(ix.text[c - 1 - (uint64_t)j]) : 4;
+      l = (l << 2) | (uint32_t)(bl > 3 ? 0 : bl);
+    }
+    ext[i] = (uint16_t)(r | (l << 8));
+  }
+}
+int launch_ext_build(const DevIndex &ix, int k, uint16_t *ext, cudaStream_t st) {
+  k_ext_build<<<sm_count() * 8, 256, 0, st>>>(ix, k, ext);
+  return 1;
+}
 int launch_alpha(const uint8_t *text, uint64_t N, uint32_t *alpha8, cudaStream_t st) {
   cudaMemsetAsync(alpha8, 0, 32, st);
   k_alpha<<<sm_count() * 4, 256, 0, st>>>(text, N, alpha8);
@@ -148,9 +166,12 @@ __device__ __forceinline__ void stage_push(SearchSmem &sm, int warp, const Match
 __device__ __forceinline__ void run_tasks(const DevIndex &ix, SearchSmem &sm, int warp, int lane, const uint8_t *P, int q,
                                           const SearchParams &sp, int ntask) {
   for (int t = lane; t < ntask; t += 32) {
-    const uint64_t c = sa_at(ix, sm.task_sa[warp][t]);
+    const uint64_t i = sm.task_sa[warp][t];
+    const int x = (int)sm.task_x[warp][t];
+    if (ix.ext && !ext_may_reach(ix.ext[i], read_ext_codes(P, x, sp.k), sp.k, sp.L)) continue;   // 2-byte pre-filter
+    const uint64_t c = sa_at(ix, i);
     Match m; int pl = 0;
-    const int r = candidate_check(ix, P, q, (int)sm.task_x[warp][t], sp.s, sp.k, sp.L, c, &m, &pl);
+    const int r = candidate_check(ix, P, q, x, sp.s, sp.k, sp.L, c, &m, &pl);
     if (r > 0) stage_push(sm, warp, m);
     else if (r < 0 && exact_start(ix, P, q, pl, sp.L, &m)) stage_push(sm, warp, m);
   }

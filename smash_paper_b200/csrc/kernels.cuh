@@ -61,6 +61,7 @@ struct SearchParams {
 // launchers (all asynchronous on `st`); each returns the number of kernels it launched
 int launch_uniq_build(const DevIndex &ix, uint8_t *uniq, cudaStream_t st);
 int launch_seed_build(const DevIndex &ix, void *seed, int k, int seed_w, cudaStream_t st);
+int launch_ext_build(const DevIndex &ix, int k, uint16_t *ext, cudaStream_t st);
 int launch_alpha(const uint8_t *text, uint64_t N, uint32_t *alpha8, cudaStream_t st);
 int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
 int launch_mem_count(const DevIndex &ix, const BatchDev &b, const SearchParams &p, uint32_t min_len_raw, uint32_t *cnt, cudaStream_t st);

@@ -25,6 +25,7 @@ struct EmulIndex {
   std::string descr;
   std::vector<uint32_t> off32;
   std::vector<uint8_t> mapbody;
+  std::vector<uint16_t> ext;
 };
 
 static uint64_t kmers_le_suffix(const DevIndex &ix, uint64_t i, int k) {   // mirrors kernels.cu
@@ -87,6 +88,24 @@ void *emul_index_create(const uint8_t *text, uint64_t N, const void *sa, const v
   for (uint64_t i = 0; i < n_descr; i += rcref ? 2 : 1) { e->off32.push_back(acc); acc += (uint32_t)sizes[i]; }
   e->off32.push_back(acc);
   d.chrom_off32 = e->off32.data();
+  {
+    // 4+4 character pre-filter codes, mirrors k_ext_build (built for k = min(seed_k, 20): the tests use min_len >= 12)
+    const int kk = d.seed_k;
+    e->ext.assign(N, 0);
+    for (uint64_t i = 0; i < N; ++i) {
+      const uint64_t c = sa_at(d, i);
+      uint32_t r = 0, l = 0;
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t pr = c + (uint64_t)kk + (uint64_t)j;
+        const int br = pr < N ? base_code(text[pr]) : 4;
+        r = (r << 2) | (uint32_t)(br > 3 ? 0 : br);
+        const int bl = c > (uint64_t)j ? base_code(text[c - 1 - (uint64_t)j]) : 4;
+        l = (l << 2) | (uint32_t)(bl > 3 ? 0 : bl);
+      }
+      e->ext[i] = (uint16_t)(r | (l << 8));
+    }
+  }
+  d.ext = e->ext.data();
   if (mapbody && map_bytes) { e->mapbody.assign(mapbody, mapbody + map_bytes); d.mapbody = e->mapbody.data(); d.map_bytes = map_bytes; }
   return e;
 }
@@ -123,6 +142,7 @@ static int emul_search(const DevIndex &ix, const uint8_t *seq, int q, uint32_t m
           continue;
         }
         for (uint64_t i = lo; i < hi; ++i) {
+          if (k == ix.seed_k && ix.ext && !ext_may_reach(ix.ext[i], read_ext_codes(P, x, k), k, L)) continue;
           Match m; int pl = 0;
           const int r = candidate_check(ix, P, q, x, s, k, L, sa_at(ix, i), &m, &pl);
           if (r > 0) stage.push_back(m);

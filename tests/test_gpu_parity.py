@@ -6,6 +6,7 @@ import pytest
 
 from helpers import make_case, oracle_tail
 from oracle import oracle as O
+from oracle import tail as T
 
 pytestmark = pytest.mark.gpu
 
@@ -406,3 +407,72 @@ def test_large_sample_parity_and_invariants():
                 assert [h for _, h in recs] == list(range(len(recs))) and all(n == len(recs) for n, _ in recs)
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("read_len,min_len", [(100, 16), (250, 24), (151, 20), (36, 20)])
+def test_read_length_and_min_len_sweep(workdir, read_len, min_len):
+    """BASELINE.json config 5: 100-250 bp reads, min MEM 16-24 (search divergence / anchor stride changes)."""
+    from smash_paper_b200 import api
+    d = os.path.join(workdir, f"sweep_{read_len}_{min_len}")
+    ref, reads, fa, oix, body = make_case(d, n_pairs=500, seed=read_len + min_len, read_len=read_len, frag_min=2, frag_max=6)
+    ix = api.Index.open(fa)
+    ctx = api.Context(ix, min_len=min_len, nomap=True, tag_mappability=True)
+    try:
+        ctx.load_mappability(body)
+        sam = oix.map_batch(reads, min_len=min_len, n_threads=4)
+        exp = oracle_tail(oix, body, sam, d, fa)
+        assert ctx.map_batch(reads).sam == b"".join(exp["tagged"])
+    finally:
+        ctx.close(); ix.close()
+
+
+@pytest.mark.parametrize("parts", [1, 2, 10])
+def test_bin_resolution_sweep(case, workdir, parts):
+    """BASELINE.json config 4: finer bin sets (the 100k/500k bins.txt are missing from the reference
+    checkout, so they are split from the coarse set); covers both histogram kernels."""
+    from smash_paper_b200 import api, synth
+    src = os.path.join(case["dir"], "bins.txt")
+    dst = os.path.join(workdir, f"bins_x{parts}.txt")
+    synth.split_bins(src, dst, parts)
+    bins = T.read_table(dst)
+    ix = api.Index.open(case["fa"])
+    ctx = api.Context(ix, min_len=20, nomap=True)
+    try:
+        ctx.load_mappability(case["body"])
+        sam = case["oix"].map_batch(case["reads"], min_len=20, n_threads=4)
+        exp = oracle_tail(case["oix"], case["body"], sam, case["dir"], case["fa"])
+        counts_exp, total, dups, kept = T.varbin(exp["positions"], bins, exp["chrominfo"])
+        ci = exp["chrominfo"]
+        ctx.tail_configure([int(b[2]) for b in bins], list(ci.keys()), [int(v[2]) for v in ci.values()])
+        ctx.map_batch(case["reads"], want=api.WANT_TAIL)
+        counts, st = ctx.tail_finish()
+        assert np.array_equal(counts, np.array(counts_exp))
+        assert (st["total_reads"], st["dups_removed"], st["reads_kept"]) == (total, dups, kept)
+    finally:
+        ctx.close(); ix.close()
+
+
+def test_error_paths(workdir, case):
+    """Errors the reference raises as paa::Error come back as SmashError with the same wording."""
+    import shutil
+    from smash_paper_b200 import api
+    d = os.path.join(workdir, "errors")
+    shutil.rmtree(d, ignore_errors=True)
+    shutil.copytree(case["dir"], d)
+    fa = os.path.join(d, "ref.fa")
+    with pytest.raises(api.SmashError, match="could not open reference bin file"):
+        api.Index.open(os.path.join(d, "reads.sam"))                    # no <file>.bin/ next to it
+    with open(fa, "ab") as f:
+        f.write(b"\n")                                                   # FASTA size guard (fasta.cpp:115-119)
+    with pytest.raises(api.SmashError, match="reference fasta size has changed"):
+        api.Index.open(fa)
+    ix = api.Index.open(case["fa"])
+    try:
+        with pytest.raises(api.SmashError, match="mode"):
+            api.Context(ix, mode=7)
+        ctx = api.Context(ix, min_len=20, nomap=True)
+        with pytest.raises(api.SmashError, match="map.bin"):
+            ctx.tail_configure([0, 10], ["chr1"], [0])                  # tail without mappability
+        ctx.close()
+    finally:
+        ix.close()
