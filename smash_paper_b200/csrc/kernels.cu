@@ -594,151 +594,100 @@ int launch_sizes_scan(const DevIndex &ix, const BatchDev &b, const WorkDev &w, c
 
 // ------------------------------------------------------------------ K4b: emit
 //
-// Two kernels, both flat over records, both writing straight into the record's final place
-// (rec_off) in the SAM buffer:
-//  k_emit_text  the VARIABLE text (columns 2-9, tags, L/R tags, newline): a warp takes 32 consecutive
-//               records, each lane formats its record into private shared-memory buffers (32 records
-//               formatted at once), then the warp streams each record's pieces out with coalesced
-//               stores.  No global loads after the formatting phase => nothing to wait for.
-//  k_emit_copy  the BULK bytes (name, SEQ, QUAL, optional fields): one warp per record, all loads of
-//               the record issued before its stores, no shared memory, full occupancy so the DRAM
-//               round trips of different records overlap.
-constexpr int EWARPS = 4;
-constexpr int HEAD_CAP = 96;
-constexpr int TAIL_CAP = 320;
-
-struct EmitRec {           // what the streaming phase needs, one per lane, exchanged with shuffles
-  unsigned long long out;
-  int head_off, tags_off, lr_off, head_len, tags_len, lr_len, slow;
-};
-
-__global__ void __launch_bounds__(EWARPS * 32)
+// Two kernels write every record straight into its final place (rec_off) in the SAM buffer:
+//  k_emit_text  the VARIABLE text (columns 2-9, tags, L/R tags, newline): ONE THREAD PER RECORD formats
+//               it through a WordSink -- characters are gathered in a register and leave as aligned
+//               8-byte stores -- so 32 records are formatted at once, no shared memory is needed and
+//               the kernel runs at full occupancy.
+//  k_emit_copy  the BULK bytes (name, SEQ, QUAL, optional fields): one warp per READ loads them once
+//               into shared memory and streams them into each of the read's records (reverse-
+//               complemented for reverse-strand records) with coalesced byte stores.
+__global__ void __launch_bounds__(128)
 k_emit_text(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp, uint64_t n_records) {
-  extern __shared__ __align__(16) char esm[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  char *hbuf = esm + (size_t)warp * 32 * (HEAD_CAP + TAIL_CAP);
-  char *tbuf = hbuf + 32 * HEAD_CAP;
-  const uint64_t warps_total = (uint64_t)gridDim.x * EWARPS;
-  for (uint64_t f0 = ((uint64_t)blockIdx.x * EWARPS + warp) * 32; f0 < n_records; f0 += warps_total * 32) {
-    const uint64_t f = f0 + lane;
-    EmitRec e; memset(&e, 0, sizeof e);
-    if (f < n_records) {
-      const uint64_t read = w.rec_read[f];
-      const int hi = (int)(f - w.rec_base[read]);
-      const ReadSum me = w.sums[read];
-      uint16_t flag; MateView mv;
-      read_mate(b, w, read, &flag, &mv);
-      const Item *items = w.item_slots + slot_base(w, read);
-      const Rec *recs = w.rec_slots + slot_base(w, read);
-      const int name_len = (int)(b.name_off[read + 1] - b.name_off[read]);
-      const int q = (int)(b.seq_off[read + 1] - b.seq_off[read]);
-      const int opt_len = b.opt ? (int)(b.opt_off[read + 1] - b.opt_off[read]) : 0;
-      e.out = (unsigned long long)(w.sam + w.rec_off[f]);
-      CapSink hs{hbuf + lane * HEAD_CAP, (uint32_t)HEAD_CAP};
-      put_head(hs, ix, (const char *)nullptr, 0, flag, me.unmapped, recs[hi], hi, items, mv);
-      e.head_len = (int)hs.n;
-      CapSink ts{tbuf + lane * TAIL_CAP, (uint32_t)TAIL_CAP};
-      put_tags(ts, ix, me.unmapped, recs, hi, me.n_rec, items);
-      e.tags_len = (int)ts.n;
-      if (sp.tag_mappability && !me.unmapped) { put_lr_tags(ts, ix, recs[hi], items); e.lr_len = (int)ts.n - e.tags_len; }
-      e.head_off = name_len;
-      e.tags_off = name_len + e.head_len + 2 * q + 1;
-      e.lr_off = e.tags_off + e.tags_len + opt_len;
-      if (hs.n > (uint32_t)HEAD_CAP || ts.n > (uint32_t)TAIL_CAP) {
-        // rare: very long CIGARs -> this lane writes its variable text straight to HBM
-        e.slow = 1;
-        char *o = (char *)e.out;
-        BufSink h2{o + e.head_off}; put_head(h2, ix, (const char *)nullptr, 0, flag, me.unmapped, recs[hi], hi, items, mv);
-        BufSink t2{o + e.tags_off}; put_tags(t2, ix, me.unmapped, recs, hi, me.n_rec, items);
-        if (sp.tag_mappability && !me.unmapped) { BufSink l2{o + e.lr_off}; put_lr_tags(l2, ix, recs[hi], items); }
-      }
+  for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_records; f += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t read = w.rec_read[f];
+    const int hi = (int)(f - w.rec_base[read]);
+    const ReadSum me = w.sums[read];
+    uint16_t flag; MateView mv;
+    read_mate(b, w, read, &flag, &mv);
+    const Item *items = w.item_slots + slot_base(w, read);
+    const Rec *recs = w.rec_slots + slot_base(w, read);
+    const int name_len = (int)(b.name_off[read + 1] - b.name_off[read]);
+    const int q = (int)(b.seq_off[read + 1] - b.seq_off[read]);
+    const int opt_len = b.opt ? (int)(b.opt_off[read + 1] - b.opt_off[read]) : 0;
+    char *out = w.sam + w.rec_off[f];
+    WordSink hs(out + name_len);
+    put_head(hs, ix, (const char *)nullptr, 0, flag, me.unmapped, recs[hi], hi, items, mv);
+    hs.finish();
+    WordSink ts(out + name_len + hs.n + 2 * q + 1);
+    put_tags(ts, ix, me.unmapped, recs, hi, me.n_rec, items);
+    if (opt_len) {                                           // the optional fields sit between the tags and the L/R tags
+      ts.finish();
+      WordSink ls(out + name_len + hs.n + 2 * q + 1 + ts.n + opt_len);
+      if (sp.tag_mappability && !me.unmapped) put_lr_tags(ls, ix, recs[hi], items);
+      ls.ch('\n');
+      ls.finish();
+    } else {
+      if (sp.tag_mappability && !me.unmapped) put_lr_tags(ts, ix, recs[hi], items);
+      ts.ch('\n');
+      ts.finish();
     }
-    __syncwarp();
-    const int n_here = (int)(n_records - f0 < 32 ? n_records - f0 : 32);
-    for (int r = 0; r < n_here; ++r) {
-      char *out = (char *)__shfl_sync(0xffffffffu, e.out, r);
-      const int head_off = __shfl_sync(0xffffffffu, e.head_off, r), head_len = __shfl_sync(0xffffffffu, e.head_len, r);
-      const int tags_off = __shfl_sync(0xffffffffu, e.tags_off, r), tags_len = __shfl_sync(0xffffffffu, e.tags_len, r);
-      const int lr_off = __shfl_sync(0xffffffffu, e.lr_off, r), lr_len = __shfl_sync(0xffffffffu, e.lr_len, r);
-      const int slow = __shfl_sync(0xffffffffu, e.slow, r);
-      if (!slow) {
-        const char *h = hbuf + r * HEAD_CAP, *t = tbuf + r * TAIL_CAP;
-        for (int i = lane; i < head_len; i += 32) out[head_off + i] = h[i];
-        for (int i = lane; i < tags_len; i += 32) out[tags_off + i] = t[i];
-        for (int i = lane; i < lr_len; i += 32) out[lr_off + i] = t[tags_len + i];
-      }
-      if (lane == 0) out[lr_off + lr_len] = '\n';
-    }
-    __syncwarp();
   }
 }
 
-__global__ void __launch_bounds__(256)
-k_emit_copy(BatchDev b, WorkDev w, uint64_t n_records) {
-  const int lane = threadIdx.x & 31;
-  const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint64_t warps_total = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  for (uint64_t f = warp0; f < n_records; f += warps_total) {
-    const uint64_t read = w.rec_read[f];
-    const int hi = (int)(f - w.rec_base[read]);
-    const Rec *rec = w.rec_slots + slot_base(w, read) + hi;
-    const int64_t so = b.seq_off[read];
-    const int q = (int)(b.seq_off[read + 1] - so);
-    const int64_t no = b.name_off[read];
-    const int name_len = (int)(b.name_off[read + 1] - no);
-    const bool rc = rec->rc && !w.sums[read].unmapped;
-    const uint32_t line = w.rec_bytes[f];
-    char *out = w.sam + w.rec_off[f];
-    const uint8_t *__restrict__ seq = b.seq + so;
-    const uint8_t *__restrict__ qual = b.qual + so;
-    const uint8_t *__restrict__ name = b.names + no;
-    // the head length is whatever is left: line = name + head + 2q+1 + tags + opt + lr + 1; k_emit_text
-    // wrote head/tags/lr, so the SEQ column starts at line_end - (tail after QUAL) ... recompute from sizes:
-    // SEQ offset = name_len + head_len, and head_len = position of the 9th tab + 1 - name_len, which
-    // k_sizes stored in rec->seq_off.
-    const int seq_at = (int)rec->seq_off;
-    constexpr int NB = 8;                       // 8 x 32 = 256 bases per pass, all loads before the stores
-    uint8_t nm = lane < name_len ? name[lane] : 0;
-    uint8_t sb[NB], qb[NB];
-#pragma unroll
-    for (int u = 0; u < NB; ++u) {
-      const int j = lane + 32 * u;
-      const int src = rc ? q - 1 - j : j;
-      sb[u] = j < q ? seq[src] : 0; qb[u] = j < q ? qual[src] : 0;
+struct CopySmem { uint8_t seq[WARPS][MAXQ_FAST], qual[WARPS][MAXQ_FAST]; };
+
+__global__ void __launch_bounds__(THREADS)
+k_emit_copy(BatchDev b, WorkDev w) {
+  __shared__ CopySmem sm;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
+  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
+    const int n_rec = (int)w.nrec[read];
+    if (!n_rec) continue;
+    const uint64_t fbase = w.rec_base[read];
+    const int64_t so = b.seq_off[read], no = b.name_off[read];
+    const int q = (int)(b.seq_off[read + 1] - so), name_len = (int)(b.name_off[read + 1] - no);
+    const uint8_t *__restrict__ seq = b.seq + so, *__restrict__ qual = b.qual + so, *__restrict__ name = b.names + no;
+    const bool staged = q <= MAXQ_FAST;
+    if (staged) for (int j = lane; j < q; j += 32) { sm.seq[warp][j] = seq[j]; sm.qual[warp][j] = qual[j]; }
+    const uint8_t nm = lane < name_len ? name[lane] : 0;
+    const bool unmapped = w.sums[read].unmapped;
+    const Rec *recs = w.rec_slots + slot_base(w, read);
+    __syncwarp();
+    for (int r = 0; r < n_rec; ++r) {
+      const uint64_t f = fbase + (uint64_t)r;
+      char *out = w.sam + w.rec_off[f];
+      const bool rc = recs[r].rc && !unmapped;
+      if (lane < name_len) out[lane] = (char)nm;
+      for (int i = lane + 32; i < name_len; i += 32) out[i] = (char)name[i];
+      char *o2 = out + recs[r].seq_off;
+      if (staged) {
+        if (rc) for (int j = lane; j < q; j += 32) { o2[j] = (char)comp_char(sm.seq[warp][q - 1 - j]); o2[q + 1 + j] = (char)sm.qual[warp][q - 1 - j]; }
+        else for (int j = lane; j < q; j += 32) { o2[j] = (char)sm.seq[warp][j]; o2[q + 1 + j] = (char)sm.qual[warp][j]; }
+      } else {
+        for (int j = lane; j < q; j += 32) {
+          const int src = rc ? q - 1 - j : j;
+          o2[j] = (char)(rc ? comp_char(seq[src]) : seq[src]); o2[q + 1 + j] = (char)qual[src];
+        }
+      }
+      if (lane == 0) o2[q] = '\t';
+      if (b.opt) {
+        const int64_t oo = b.opt_off[read];
+        const int opt_len = (int)(b.opt_off[read + 1] - oo);
+        char *o3 = out + (w.rec_bytes[f] - 1u - recs[r].lr_len - (uint32_t)opt_len);
+        for (int i = lane; i < opt_len; i += 32) o3[i] = (char)b.opt[oo + i];
+      }
     }
-    if (lane < name_len) out[lane] = (char)nm;
-    for (int i = lane + 32; i < name_len; i += 32) out[i] = (char)name[i];
-    char *o2 = out + seq_at;
-#pragma unroll
-    for (int u = 0; u < NB; ++u) {
-      const int j = lane + 32 * u;
-      if (j < q) { o2[j] = (char)(rc ? comp_char(sb[u]) : sb[u]); o2[q + 1 + j] = (char)qb[u]; }
-    }
-    for (int j = lane + 32 * NB; j < q; j += 32) {
-      const int src = rc ? q - 1 - j : j;
-      o2[j] = (char)(rc ? comp_char(seq[src]) : seq[src]); o2[q + 1 + j] = (char)qual[src];
-    }
-    if (lane == 0) o2[q] = '\t';
-    if (b.opt) {
-      const int64_t oo = b.opt_off[read];
-      const int opt_len = (int)(b.opt_off[read + 1] - oo);
-      // optional fields sit right before the L/R tags and the newline: line - 1 - lr_len - opt_len
-      char *o3 = out + (line - 1u - rec->lr_len - (uint32_t)opt_len);
-      for (int i = lane; i < opt_len; i += 32) o3[i] = (char)b.opt[oo + i];
-    }
+    __syncwarp();
   }
 }
 
 int launch_emit(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st, uint64_t n_records) {
   if (!b.n_reads || !n_records) return 0;
-  const size_t smem = (size_t)EWARPS * 32 * (HEAD_CAP + TAIL_CAP);
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_emit_text, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-  uint64_t need = (n_records + 32 * EWARPS - 1) / (32 * EWARPS);
-  uint64_t cap = (uint64_t)sm_count() * 4;
-  k_emit_text<<<(unsigned)(need < cap ? need : cap), EWARPS * 32, smem, st>>>(ix, b, w, p, n_records);
-  need = (n_records + 7) / 8; cap = (uint64_t)sm_count() * 8;
-  k_emit_copy<<<(unsigned)(need < cap ? need : cap), 256, 0, st>>>(b, w, n_records);
+  uint64_t need = (n_records + 127) / 128, cap = (uint64_t)sm_count() * 16;
+  k_emit_text<<<(unsigned)(need < cap ? need : cap), 128, 0, st>>>(ix, b, w, p, n_records);
+  k_emit_copy<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(b, w);
   return 2;
 }
 

@@ -311,6 +311,24 @@ struct CapSink {
   HDN void ch(char c) { if (n < cap) p[n] = c; ++n; }
   HDN void put(const char *s, int len) { for (int i = 0; i < len; ++i) { if (n < cap) p[n] = s[i]; ++n; } }
 };
+// Byte stream -> HBM at ANY alignment with aligned 8-byte stores: characters are gathered in a register
+// and flushed a word at a time; the partial words at both ends of the region (shared with the
+// neighbouring column, which another kernel writes) are written byte by byte.
+struct WordSink {
+  char *w;            // aligned address of the word being filled
+  uint64_t acc;
+  int fill, lo;       // bytes gathered so far in this word; first byte of the word that belongs to us
+  uint32_t n;
+  HDN explicit WordSink(char *dst) : w(dst - ((uintptr_t)dst & 7)), acc(0), fill((int)((uintptr_t)dst & 7)), lo(fill), n(0) {}
+  HDN void flush() {
+    if (lo == 0 && fill == 8) *reinterpret_cast<uint64_t *>(w) = acc;
+    else for (int i = lo; i < fill; ++i) w[i] = (char)(acc >> (8 * i));
+    w += 8; acc = 0; fill = 0; lo = 0;
+  }
+  HDN void ch(char c) { acc |= (uint64_t)(uint8_t)c << (8 * fill); ++n; if (++fill == 8) flush(); }
+  HDN void put(const char *s, int len) { for (int i = 0; i < len; ++i) ch(s[i]); }
+  HDN void finish() { if (fill > lo) flush(); }
+};
 template <class S> HDN inline void put_u64(S &s, uint64_t v) {
   char t[20]; int n = 0;
   if (v <= 0xffffffffull) {                // 32-bit divide-by-constant: a multiply and a shift

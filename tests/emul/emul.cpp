@@ -245,4 +245,21 @@ uint64_t emul_map_batch(void *index, uint64_t n_reads, const uint8_t *names, con
   return sam.size();
 }
 
+// WordSink (aligned 8-byte stores at arbitrary byte alignment) against the plain byte sink.
+int emul_wordsink_selftest() {
+  alignas(8) char a[256], b[256];
+  for (int off = 0; off < 9; ++off)
+    for (int len = 0; len < 40; ++len) {
+      memset(a, '.', sizeof a); memset(b, '.', sizeof b);
+      BufSink bs{b + 16 + off};
+      WordSink ws(a + 16 + off);
+      for (int i = 0; i < len; ++i) { bs.ch((char)('A' + i % 26)); ws.ch((char)('A' + i % 26)); }
+      put_u64(bs, 1234567890123ull + (uint64_t)len); put_u64(ws, 1234567890123ull + (uint64_t)len);
+      put_i64(bs, -(int64_t)off); put_i64(ws, -(int64_t)off);
+      ws.finish();
+      if (ws.n != bs.n || memcmp(a, b, sizeof a) != 0) return 1 + off * 100 + len;
+    }
+  return 0;
+}
+
 }  // extern "C"

@@ -45,3 +45,9 @@ def test_tagged_output(workdir):
     exp = oracle_tail(oix, body, oix.map_batch(reads, min_len=20), os.path.join(workdir, "emul_tag"), fa)
     assert err == 0
     assert sam == b"".join(exp["tagged"])
+
+
+def test_wordsink_matches_byte_sink():
+    """records.cuh WordSink (register-gathered aligned 8-byte stores, byte stores at the region edges)
+    writes exactly the bytes the plain sink writes, at every alignment and length."""
+    assert E.lib().emul_wordsink_selftest() == 0
