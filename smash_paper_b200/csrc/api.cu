@@ -235,7 +235,7 @@ struct smash_ctx {
   // index storage
   uint8_t *text_alloc = nullptr; void *sa = nullptr; void *isa = nullptr; uint8_t *lcp = nullptr;
   LcpItem *lcp_m = nullptr; uint8_t *uniq = nullptr; void *seed = nullptr; uint16_t *ext = nullptr; uint64_t *startpos = nullptr;
-  uint64_t *sizes = nullptr; char *descr = nullptr; int *descr_off = nullptr; uint32_t *alpha = nullptr;
+  uint64_t *sizes = nullptr; char *descr = nullptr; int *descr_off = nullptr; uint64_t *descr8 = nullptr; uint32_t *alpha = nullptr;
   uint8_t *mapbody = nullptr; uint32_t *chrom_off32 = nullptr;
   uint64_t n_m = 0;
   smash_index *own_index = nullptr;
@@ -316,6 +316,10 @@ static int ctx_finish(smash_ctx *c, const smash_index *ix) {
     CK(dmalloc((void **)&c->descr_off, 4 * (nd + 1), &c->index_bytes));
     CUC(cudaMemcpy(c->descr, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     CUC(cudaMemcpy(c->descr_off, off.data(), 4 * (nd + 1), cudaMemcpyHostToDevice));
+    std::vector<uint64_t> d8(nd, 0);
+    for (int i = 0; i < nd; ++i) for (size_t j = 0; j < ix->descr[i].size() && j < 8; ++j) d8[i] |= (uint64_t)(uint8_t)ix->descr[i][j] << (8 * j);
+    CK(dmalloc((void **)&c->descr8, 8 * nd, &c->index_bytes));
+    CUC(cudaMemcpy(c->descr8, d8.data(), 8 * nd, cudaMemcpyHostToDevice));
     // mappability_tag's 32-bit offsets over all @SQ (chromosomes.h:29-66)
     std::vector<uint32_t> o32((nd + 1) / (ix->rcref ? 2 : 1) + 1, 0);
     uint32_t acc = 0; int k = 0;
@@ -327,7 +331,7 @@ static int ctx_finish(smash_ctx *c, const smash_index *ix) {
   DevIndex &d = c->dix;
   d.text = c->text_alloc + TEXT_PAD; d.N = N; d.sa = c->sa; d.isa = c->isa; d.w = ix->w; d.lcp = c->lcp;
   d.lcp_m = c->lcp_m; d.n_m = c->n_m; d.startpos = c->startpos; d.sizes = c->sizes; d.n_descr = nd;
-  d.rcref = ix->rcref; d.descr = c->descr; d.descr_off = c->descr_off;
+  d.rcref = ix->rcref; d.descr = c->descr; d.descr_off = c->descr_off; d.descr8 = c->descr8;
   d.logN = (uint64_t)ceil(log((double)N) / log(2.0));          // longSA.cpp:97
   d.mapbody = nullptr; d.map_bytes = 0; d.chrom_off32 = c->chrom_off32;
   // derived: alphabet bitmap, shortest-unique-length bytes, k-mer seed table
@@ -542,7 +546,7 @@ extern "C" void smash_ctx_destroy(smash_ctx *c) {
   cudaDeviceSynchronize();
   for (int s = 0; s < SMASH_N_SLOTS; ++s) slot_release(c->slot[s]);
   tail_release(&c->tail);
-  void *ptrs[] = {c->ext, c->text_alloc, c->sa, c->isa, c->lcp, c->lcp_m, c->uniq, c->seed, c->startpos, c->sizes,
+  void *ptrs[] = {c->descr8, c->ext, c->text_alloc, c->sa, c->isa, c->lcp, c->lcp_m, c->uniq, c->seed, c->startpos, c->sizes,
                   c->descr, c->descr_off, c->alpha, c->mapbody, c->chrom_off32};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->own_index) delete c->own_index;

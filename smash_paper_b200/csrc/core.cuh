@@ -50,6 +50,7 @@ struct DevIndex {
   int rcref;
   const char *descr;         // concatenated names
   const int *descr_off;      // n_descr + 1
+  const uint64_t *descr8;    // first 8 name bytes packed little-endian (used when the name has <= 8 chars)
   uint64_t logN;             // ceil(log2 N) as longSA.cpp:97 computes it
   // mappability (map.bin body) + 32-bit chromosome offsets of mappability_tag (chromosomes.h:109)
   const uint8_t *mapbody;

@@ -635,12 +635,21 @@ k_emit_text(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp, uint64_t n_reco
   }
 }
 
-struct CopySmem { uint8_t seq[WARPS][MAXQ_FAST], qual[WARPS][MAXQ_FAST]; };
+struct CopySmem {
+  uint8_t seq[WARPS][MAXQ_FAST], qual[WARPS][MAXQ_FAST];       // as given
+  uint8_t rseq[WARPS][MAXQ_FAST], rqual[WARPS][MAXQ_FAST];     // reverse-complemented / reversed
+  uint8_t comp[256];                                           // reverse_complement's character map (fasta.cpp:26-61)
+};
+constexpr int COPY_WARPS = 8;
+static_assert(COPY_WARPS == WARPS, "CopySmem is sized by WARPS");
 
 __global__ void __launch_bounds__(THREADS)
 k_emit_copy(BatchDev b, WorkDev w) {
-  __shared__ CopySmem sm;
+  extern __shared__ __align__(16) uint8_t copy_smem_raw[];
+  CopySmem &sm = *reinterpret_cast<CopySmem *>(copy_smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  sm.comp[threadIdx.x & 255] = comp_char((uint8_t)(threadIdx.x & 255));
+  __syncthreads();
   const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
   for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
     const int n_rec = (int)w.nrec[read];
@@ -649,11 +658,20 @@ k_emit_copy(BatchDev b, WorkDev w) {
     const int64_t so = b.seq_off[read], no = b.name_off[read];
     const int q = (int)(b.seq_off[read + 1] - so), name_len = (int)(b.name_off[read + 1] - no);
     const uint8_t *__restrict__ seq = b.seq + so, *__restrict__ qual = b.qual + so, *__restrict__ name = b.names + no;
-    const bool staged = q <= MAXQ_FAST;
-    if (staged) for (int j = lane; j < q; j += 32) { sm.seq[warp][j] = seq[j]; sm.qual[warp][j] = qual[j]; }
-    const uint8_t nm = lane < name_len ? name[lane] : 0;
     const bool unmapped = w.sums[read].unmapped;
     const Rec *recs = w.rec_slots + slot_base(w, read);
+    const bool staged = q <= MAXQ_FAST;
+    bool any_rc = false;
+    if (!unmapped) for (int r = lane; r < n_rec; r += 32) any_rc |= recs[r].rc != 0;
+    any_rc = __any_sync(0xffffffffu, any_rc);
+    if (staged) {
+      for (int j = lane; j < q; j += 32) {
+        const uint8_t sv = seq[j], qv = qual[j];
+        sm.seq[warp][j] = sv; sm.qual[warp][j] = qv;
+        if (any_rc) { sm.rseq[warp][q - 1 - j] = sm.comp[sv]; sm.rqual[warp][q - 1 - j] = qv; }
+      }
+    }
+    const uint8_t nm = lane < name_len ? name[lane] : 0;
     __syncwarp();
     for (int r = 0; r < n_rec; ++r) {
       const uint64_t f = fbase + (uint64_t)r;
@@ -663,12 +681,12 @@ k_emit_copy(BatchDev b, WorkDev w) {
       for (int i = lane + 32; i < name_len; i += 32) out[i] = (char)name[i];
       char *o2 = out + recs[r].seq_off;
       if (staged) {
-        if (rc) for (int j = lane; j < q; j += 32) { o2[j] = (char)comp_char(sm.seq[warp][q - 1 - j]); o2[q + 1 + j] = (char)sm.qual[warp][q - 1 - j]; }
-        else for (int j = lane; j < q; j += 32) { o2[j] = (char)sm.seq[warp][j]; o2[q + 1 + j] = (char)sm.qual[warp][j]; }
+        const uint8_t *S = rc ? sm.rseq[warp] : sm.seq[warp], *Q = rc ? sm.rqual[warp] : sm.qual[warp];
+        for (int j = lane; j < q; j += 32) { o2[j] = (char)S[j]; o2[q + 1 + j] = (char)Q[j]; }
       } else {
         for (int j = lane; j < q; j += 32) {
           const int src = rc ? q - 1 - j : j;
-          o2[j] = (char)(rc ? comp_char(seq[src]) : seq[src]); o2[q + 1 + j] = (char)qual[src];
+          o2[j] = (char)(rc ? sm.comp[seq[src]] : seq[src]); o2[q + 1 + j] = (char)qual[src];
         }
       }
       if (lane == 0) o2[q] = '\t';
@@ -687,7 +705,9 @@ int launch_emit(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const S
   if (!b.n_reads || !n_records) return 0;
   uint64_t need = (n_records + 127) / 128, cap = (uint64_t)sm_count() * 16;
   k_emit_text<<<(unsigned)(need < cap ? need : cap), 128, 0, st>>>(ix, b, w, p, n_records);
-  k_emit_copy<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(b, w);
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_emit_copy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CopySmem)); attr_set = true; }
+  k_emit_copy<<<grid_for_warps(b.n_reads, 6), THREADS, sizeof(CopySmem), st>>>(b, w);
   return 2;
 }
 

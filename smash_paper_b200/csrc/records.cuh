@@ -296,20 +296,25 @@ HD bool map_lr(const DevIndex &ix, uint32_t chrom, int64_t pos0, uint32_t off, u
 }
 
 // ---- SAM text --------------------------------------------------------------------------------
+// Every sink takes single chars, byte strings, and `word`: up to 8 chars packed little-endian in a
+// register (first char in the low byte) -- the form literals and decimal numbers are produced in.
 struct CountSink {
   uint32_t n = 0;
   HDN void ch(char) { ++n; }
   HDN void put(const char *, int len) { n += (uint32_t)len; }
+  HDN void word(uint64_t, int len) { n += (uint32_t)len; }
 };
 struct BufSink {
   char *p; uint32_t n = 0;
   HDN void ch(char c) { p[n++] = c; }
   HDN void put(const char *s, int len) { for (int i = 0; i < len; ++i) p[n + i] = s[i]; n += (uint32_t)len; }
+  HDN void word(uint64_t v, int len) { for (int i = 0; i < len; ++i) { p[n + i] = (char)v; v >>= 8; } n += (uint32_t)len; }
 };
 struct CapSink {
   char *p; uint32_t cap; uint32_t n = 0;
   HDN void ch(char c) { if (n < cap) p[n] = c; ++n; }
   HDN void put(const char *s, int len) { for (int i = 0; i < len; ++i) { if (n < cap) p[n] = s[i]; ++n; } }
+  HDN void word(uint64_t v, int len) { for (int i = 0; i < len; ++i) { if (n < cap) p[n] = (char)v; ++n; v >>= 8; } }
 };
 // Byte stream -> HBM at ANY alignment with aligned 8-byte stores: characters are gathered in a register
 // and flushed a word at a time; the partial words at both ends of the region (shared with the
@@ -327,24 +332,59 @@ struct WordSink {
   }
   HDN void ch(char c) { acc |= (uint64_t)(uint8_t)c << (8 * fill); ++n; if (++fill == 8) flush(); }
   HDN void put(const char *s, int len) { for (int i = 0; i < len; ++i) ch(s[i]); }
+  // up to 8 packed chars in O(1): merge into the word being filled, flush if it completes, keep the rest
+  HDN void word(uint64_t v, int len) {
+    if (len <= 0) return;
+    n += (uint32_t)len;
+    acc |= v << (8 * fill);
+    const int room = 8 - fill;
+    if (len >= room) {
+      fill = 8; flush();
+      if (len > room) { acc = v >> (8 * room); fill = len - room; }
+    } else fill += len;
+  }
   HDN void finish() { if (fill > lo) flush(); }
 };
+// up to 8 decimal digits of x as packed chars (most significant digit in the low byte)
+HDN inline uint64_t digits8(uint32_t x, bool pad8, int *nd) {
+  uint64_t packed = 0; int n = 0;
+  do { const uint32_t d = x / 10u; packed = (packed << 8) | (uint64_t)('0' + (x - d * 10u)); x = d; ++n; } while (x || (pad8 && n < 8));
+  *nd = n;
+  return packed;
+}
 template <class S> HDN inline void put_u64(S &s, uint64_t v) {
-  char t[20]; int n = 0;
-  if (v <= 0xffffffffull) {                // 32-bit divide-by-constant: a multiply and a shift
-    uint32_t x = (uint32_t)v;
-    do { const uint32_t d = x / 10u; t[n++] = (char)('0' + (x - d * 10u)); x = d; } while (x);
-  } else {
-    do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  int nd;
+  if (v < 100000000ull) {                        // the common case: at most 8 digits, one packed word
+    const uint64_t p = digits8((uint32_t)v, false, &nd);
+    s.word(p, nd);
+    return;
   }
-  while (n) s.ch(t[--n]);
+  // longer numbers: leading chunk unpadded, the following 8-digit chunks zero padded (no recursion)
+  const uint64_t top = v / 10000000000000000ull, rest = v % 10000000000000000ull;
+  const uint32_t mid = (uint32_t)(rest / 100000000ull), low = (uint32_t)(rest % 100000000ull);
+  if (top) { const uint64_t p = digits8((uint32_t)top, false, &nd); s.word(p, nd); }
+  { const uint64_t p = digits8(mid, top != 0, &nd); s.word(p, nd); }
+  { const uint64_t p = digits8(low, true, &nd); s.word(p, nd); }
 }
 template <class S> HDN inline void put_i64(S &s, int64_t v) {
   if (v < 0) { s.ch('-'); put_u64(s, (uint64_t)(-v)); } else put_u64(s, (uint64_t)v);
 }
-template <class S> HDN inline void put_lit(S &s, const char *lit) { int n = 0; while (lit[n]) ++n; s.put(lit, n); }
+// string literals are packed at compile time, 8 chars per word
+HDN constexpr uint64_t pack8(const char *s, int n) {
+  uint64_t v = 0;
+  for (int i = n - 1; i >= 0; --i) v = (v << 8) | (uint64_t)(uint8_t)s[i];
+  return v;
+}
+template <class S, int N> HDN inline void put_lit(S &s, const char (&lit)[N]) {
+  constexpr int len = N - 1;
+  if (len <= 8) { s.word(pack8(lit, len), len); }
+  else { s.word(pack8(lit, 8), 8); s.word(pack8(lit + 8, len - 8 > 8 ? 8 : len - 8), len - 8 > 8 ? 8 : len - 8); }
+  static_assert(N - 1 <= 16, "literal too long for put_lit");
+}
 template <class S> HDN inline void put_descr(S &s, const DevIndex &ix, uint32_t si) {
-  s.put(ix.descr + ix.descr_off[si], ix.descr_off[si + 1] - ix.descr_off[si]);
+  const int len = ix.descr_off[si + 1] - ix.descr_off[si];
+  if (len <= 8 && ix.descr8) s.word(ix.descr8[si], len);           // names of <= 8 chars: one packed word
+  else s.put(ix.descr + ix.descr_off[si], len);
 }
 // CIGAR of a record (query.cpp:260-268): [<prefix>S] len= [<gap>M len=]... [<suffix>S]
 template <class S> HDN inline void put_cigar(S &s, const Rec &r, const Item *items) {

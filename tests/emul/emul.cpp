@@ -26,6 +26,7 @@ struct EmulIndex {
   std::vector<uint32_t> off32;
   std::vector<uint8_t> mapbody;
   std::vector<uint16_t> ext;
+  std::vector<uint64_t> descr8;
 };
 
 static uint64_t kmers_le_suffix(const DevIndex &ix, uint64_t i, int k) {   // mirrors kernels.cu
@@ -65,6 +66,8 @@ void *emul_index_create(const uint8_t *text, uint64_t N, const void *sa, const v
   for (uint64_t i = 0; i < n_descr; ++i) { e->descr_off.push_back((int)e->descr.size()); e->descr += descr[i]; }
   e->descr_off.push_back((int)e->descr.size());
   d.descr = e->descr.data(); d.descr_off = e->descr_off.data();
+  for (uint64_t i = 0; i < n_descr; ++i) { uint64_t v = 0; for (size_t j = 0; j < strlen(descr[i]) && j < 8; ++j) v |= (uint64_t)(uint8_t)descr[i][j] << (8 * j); e->descr8.push_back(v); }
+  d.descr8 = e->descr8.data();
   d.logN = (uint64_t)ceil(log((double)N) / log(2.0));
   for (uint64_t i = 0; i < N; ++i) d.alpha[text[i] >> 5] |= 1u << (text[i] & 31);
   e->uniq.assign(N, 0);
@@ -255,6 +258,8 @@ int emul_wordsink_selftest() {
       WordSink ws(a + 16 + off);
       for (int i = 0; i < len; ++i) { bs.ch((char)('A' + i % 26)); ws.ch((char)('A' + i % 26)); }
       put_u64(bs, 1234567890123ull + (uint64_t)len); put_u64(ws, 1234567890123ull + (uint64_t)len);
+      put_lit(bs, "\tXM:i:0\tNH:i:0"); put_lit(ws, "\tXM:i:0\tNH:i:0"); put_u64(bs, (uint64_t)len * 7919u); put_u64(ws, (uint64_t)len * 7919u);
+      put_u64(bs, 100000000ull * (uint64_t)off + 42); put_u64(ws, 100000000ull * (uint64_t)off + 42);
       put_i64(bs, -(int64_t)off); put_i64(ws, -(int64_t)off);
       ws.finish();
       if (ws.n != bs.n || memcmp(a, b, sizeof a) != 0) return 1 + off * 100 + len;
