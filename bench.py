@@ -155,6 +155,14 @@ def run_ours(args, wl, rank, world):
     ctx.build_mappability_device(ref.total)
     t_map = time.time() - t0
     log(f"index built on GPU in {t_index:.1f}s, map.bin in {t_map:.1f}s, {ctx.index_bytes / 1e9:.2f} GB in HBM")
+    ref_files = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            ref_files = prepare_reference_files(ref, ctx, workdir)       # needs the ISA, so before it is dropped
+        except Exception as e:  # noqa: BLE001
+            ref_files = {"error": str(e)[:300]}
+    ctx.drop_isa()                                                       # 49.5 GB at hg19 scale
+    log(f"{ctx.index_bytes / 1e9:.2f} GB of index in HBM for the run")
     starts = make_bins(wl, ref, workdir)
     offs = ref.offsets()
     ctx.tail_configure(starts, names, offs)
@@ -271,7 +279,8 @@ def run_ours(args, wl, rank, world):
         sam_per_read = sam_bytes / max(B * args.steps, 1)
         alg = kernel_alg_bytes(wl, len(text), n_rec_per_read, sam_per_read)
         per_kernel = {}
-        for kname, skey in (("k_mam_search", "search"), ("k_rec_build+k_rec_xe", "records"), ("k_sizes", "sizes_scan"), ("k_emit", "emit")):
+        for kname, skey in (("k_mam_search", "search"), ("k_rec_build+k_rec_xe", "records"), ("k_sizes", "sizes_scan"),
+                            ("k_emit_text", "emit_text"), ("k_emit_copy", "emit_copy")):
             ms = stage[skey] / args.steps
             gbs = B * alg[kname] / (ms / 1e3) / 1e9 if ms > 0 else 0.0
             per_kernel[kname] = {"ms": ms, "alg_bytes_per_read": alg[kname], "achieved_gbs": gbs, "frac": gbs / peak}
@@ -305,7 +314,9 @@ def run_ours(args, wl, rank, world):
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                out["cpu_baseline"] = cpu_baseline(args, wl, ref, ctx, workdir, sample_pairs=args.cpu_sample_pairs, steps=1)
+                if "error" in ref_files:
+                    raise RuntimeError(ref_files["error"])
+                out["cpu_baseline"] = cpu_baseline(args, wl, ref, ref_files, sample_pairs=args.cpu_sample_pairs, steps=1)
             except Exception as e:  # noqa: BLE001 -- the baseline must never break the bench line
                 out["cpu_baseline"] = {"error": str(e)[:300]}
     ctx.close()
@@ -336,8 +347,10 @@ def kernel_alg_bytes(wl, N, n_rec, sam_bytes):
         "k_rec_build+k_rec_xe": 16 * n_rec + 44 * n_rec + 2 * q * n_rec + 2 * n_rec + 16,
         # per record: its Rec + neighbours' Rec/Item for the cc/CC tags, 4 B out
         "k_sizes": n_rec * (3 * 40 + 12 + 4 + 16),
-        # SAM text out; in: name + SEQ + QUAL per record, Rec/Item, offsets
-        "k_emit": sam_bytes + n_rec * (name + 2 * q + 3 * 40 + 12 + 8 + 16),
+        # variable text out (everything except name/SEQ/QUAL); in: Rec/Item of the record and its neighbours, offsets
+        "k_emit_text": (sam_bytes - n_rec * (name + 2 * q + 1)) + n_rec * (3 * 40 + 12 + 8 + 16),
+        # bulk bytes out (name + SEQ + tab + QUAL per record); in: the read once (name + SEQ + QUAL) + Rec + offset per record
+        "k_emit_copy": n_rec * (name + 2 * q + 1) + (name + 2 * q) + n_rec * (40 + 8),
     }
 
 
@@ -346,10 +359,10 @@ def kernel_alg_bytes(wl, N, n_rec, sam_bytes):
 cleanup = []
 
 
-def cpu_baseline(args, wl, ref, ctx, workdir, sample_pairs, steps):
-    """The UNMODIFIED reference (oracle/_ref/mummer[-long]) on the host cores, bounded sample.
-    ctx: a GPU context whose index is saved in the reference's file format (byte-identical files,
-    tests/test_gpu_parity.py) or None -> the reference builds its own index."""
+def prepare_reference_files(ref, ctx, workdir):
+    """FASTA + <fa>.bin/ index files for the reference binary.  ctx: a GPU context whose index is saved in
+    the reference's file format (byte-identical files, tests/test_gpu_parity.py), or None -> the reference
+    builds its own index (qsufsort).  Big indexes go to tmpfs (the box's disk is smaller than an hg19-scale index)."""
     from oracle import oracle as O
     if not O.have_reference():
         raise RuntimeError("oracle/_ref not built")
@@ -358,7 +371,6 @@ def cpu_baseline(args, wl, ref, ctx, workdir, sample_pairs, steps):
     w = 8 if N >= 0xFFFFFFFF - 100000 else 4
     need = N * (2 + 2 * w) + ref.total + (cores + 2) * 600_000_000      # index files + FASTA + mummer's 500 MB/thread arenas
     if need > 2_000_000_000:
-        # big index: files go to tmpfs (the box's disk is smaller than an hg19-scale index)
         import psutil
         avail = psutil.virtual_memory().available
         if avail < need + 24_000_000_000 or not os.path.isdir("/dev/shm"):
@@ -368,7 +380,7 @@ def cpu_baseline(args, wl, ref, ctx, workdir, sample_pairs, steps):
     fa = os.path.join(workdir, "ref.fa")
     t0 = time.time()
     synth.write_fasta(ref, fa)
-    long_ints = (2 * ref.total + 2 * len(ref.names)) >= 0xFFFFFFFF - 100000
+    long_ints = w == 8
     if ctx is not None:
         ctx.save_index(fa, with_mappability=False)
         built = "gpu builder (files byte-identical to the reference's, see tests)"
@@ -376,6 +388,14 @@ def cpu_baseline(args, wl, ref, ctx, workdir, sample_pairs, steps):
         O.ref_build_index(fa, long_ints=long_ints, mappability=False)
         built = "reference's own qsufsort build"
     log(f"reference index files ready in {time.time() - t0:.1f}s ({built})")
+    return {"fa": fa, "workdir": workdir, "long_ints": long_ints, "built": built}
+
+
+def cpu_baseline(args, wl, ref, files, sample_pairs, steps):
+    """The UNMODIFIED reference (oracle/_ref/mummer[-long]) on the host cores, bounded sample per step."""
+    from oracle import oracle as O
+    cores = os.cpu_count() or 2
+    fa, workdir, long_ints, built = files["fa"], files["workdir"], files["long_ints"], files["built"]
     exe = os.path.join(O.REF_BIN, "mummer-long" if long_ints else "mummer")
     empty = os.path.join(workdir, "empty.sam")
     open(empty, "w").close()
@@ -422,7 +442,10 @@ def run_reference(args, wl, rank, world):
         ctx = api.Context.from_text(text, startpos, sizes, descr, keep_isa=True, chunk_cap=wl["chunk_cap"])
         del text
     try:
-        cb = cpu_baseline(args, wl, ref, ctx, workdir, sample_pairs=args.cpu_sample_pairs, steps=args.warmup + args.steps)
+        files = prepare_reference_files(ref, ctx, workdir)
+        if ctx is not None:
+            ctx.close(); ctx = None
+        cb = cpu_baseline(args, wl, ref, files, sample_pairs=args.cpu_sample_pairs, steps=args.warmup + args.steps)
     finally:
         if ctx is not None:
             ctx.close()

@@ -86,6 +86,8 @@ int smash_ctx_copy_index(smash_ctx *ctx, void *sa, void *isa, uint8_t *lcp_vec, 
 /* Write <ref_fasta>.bin/rc{r}.* (and map.bin) in the reference's formats (fasta.cpp:215-236,
  * longSA.cpp:179-190): what `mummer -rcref <fa> dummy` leaves behind (index_setup.sh:19,22). */
 int smash_ctx_save_index(smash_ctx *ctx, const char *ref_fasta, int with_mappability);
+/* Free the inverse suffix array in HBM (only MEM mode, mappability build and index save need it). */
+int smash_ctx_drop_isa(smash_ctx *ctx);
 void smash_ctx_destroy(smash_ctx *ctx);
 /* map.bin (longSA::show_mappability output, longSA.cpp:612-690; 2 junk bytes + 2 bytes/base) for
  * the L/R tags and the smashMEM excess-mappability filter.  body = file contents after the two
@@ -190,7 +192,7 @@ int smash_memcpy(void *dst, const void *src, size_t bytes);
 /* ---- counters for bench.py: kernels launched by this library since ctx creation */
 uint64_t smash_ctx_launch_count(const smash_ctx *ctx);
 /* Device milliseconds accumulated per stage since the last reset, measured with CUDA events on the
- * launching stream: [0] search, [1] records, [2] sizes+scan, [3] emit, [4] match CSR, [5] tail. */
+ * launching stream: [0] search, [1] records, [2] sizes+scan, [3] emit_text, [4] match CSR, [5] tail, [6] emit_copy. */
 void smash_ctx_stage_ms(smash_ctx *ctx, double *out8, int reset);
 /* Bytes of HBM held by the index on this ctx (text, SA, LCP, seed table, ...). */
 uint64_t smash_ctx_index_bytes(const smash_ctx *ctx);

@@ -245,6 +245,9 @@ class Context:
         """map.bin body built and kept in HBM only (no host copy)."""
         _check(load_library().smash_ctx_build_mappability(self.h, None, C.c_uint64(0)))
 
+    def drop_isa(self):
+        _check(load_library().smash_ctx_drop_isa(self.h))
+
     def save_index(self, fasta, with_mappability=False):
         _check(load_library().smash_ctx_save_index(self.h, str(fasta).encode(), int(with_mappability)))
 
@@ -366,7 +369,7 @@ class Context:
     def stage_ms(self, reset=False):
         out = (C.c_double * 8)()
         load_library().smash_ctx_stage_ms(self.h, out, int(reset))
-        return dict(zip(["search", "records", "sizes_scan", "emit", "match_csr", "tail"], list(out)[:6]))
+        return dict(zip(["search", "records", "sizes_scan", "emit_text", "match_csr", "tail", "emit_copy"], list(out)[:7]))
 
     @property
     def launches(self):

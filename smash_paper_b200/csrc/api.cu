@@ -241,7 +241,7 @@ struct smash_ctx {
   smash_index *own_index = nullptr;
   uint64_t index_bytes = 0;
   uint64_t launches = 0;
-  double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // search, records, sizes+scan, emit, csr, tail
+  double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // search, records, sizes+scan, emit_text, csr, tail, emit_copy
   Slot slot[SMASH_N_SLOTS];
   TailState tail;
 };
@@ -706,8 +706,10 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
     int rc;
     if ((rc = s.sam.ensure(s.sam_bytes + 64))) return rc;
     WorkDev w = work_of(s);
-    c->launches += launch_emit(c->dix, s.bd, w, c->sp, s.st, s.n_records);
+    c->launches += launch_emit_text(c->dix, s.bd, w, c->sp, s.st, s.n_records);
     MARK(3);
+    c->launches += launch_emit_copy(s.bd, w, s.st, s.n_records);
+    MARK(6);
     if (to_host) {
       if ((rc = s.h_sam.ensure(s.sam_bytes + 64))) return rc;
       CU(cudaMemcpyAsync(s.h_sam.p, s.sam.p, s.sam_bytes, cudaMemcpyDeviceToHost, s.st));
@@ -907,6 +909,15 @@ extern "C" int smash_tail_reset(smash_ctx *c) {
   return 0;
 }
 
+// Release the inverse suffix array (49.5 GB at hg19 scale) once map.bin is built / the index is saved;
+// MEM mode needs it and keeps it.
+extern "C" int smash_ctx_drop_isa(smash_ctx *c) {
+  if (!c) return fail(SMASH_ERR_ARG, "null argument");
+  if (c->prm.mode == SMASH_MODE_MEM) return fail(SMASH_ERR_STATE, "MEM mode needs the inverse suffix array");
+  CU(cudaSetDevice(c->device));
+  if (c->isa) { cudaFree(c->isa); c->index_bytes -= c->dix.N * (uint64_t)c->dix.w; c->isa = nullptr; c->dix.isa = nullptr; }
+  return 0;
+}
 extern "C" int smash_memcpy(void *dst, const void *src, size_t bytes) {
   if (!bytes) return 0;
   CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));       // UVA: any of host/device on either side

@@ -701,14 +701,18 @@ k_emit_copy(BatchDev b, WorkDev w) {
   }
 }
 
-int launch_emit(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st, uint64_t n_records) {
+int launch_emit_text(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st, uint64_t n_records) {
   if (!b.n_reads || !n_records) return 0;
-  uint64_t need = (n_records + 127) / 128, cap = (uint64_t)sm_count() * 16;
+  const uint64_t need = (n_records + 127) / 128, cap = (uint64_t)sm_count() * 16;
   k_emit_text<<<(unsigned)(need < cap ? need : cap), 128, 0, st>>>(ix, b, w, p, n_records);
+  return 1;
+}
+int launch_emit_copy(const BatchDev &b, const WorkDev &w, cudaStream_t st, uint64_t n_records) {
+  if (!b.n_reads || !n_records) return 0;
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(k_emit_copy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CopySmem)); attr_set = true; }
   k_emit_copy<<<grid_for_warps(b.n_reads, 6), THREADS, sizeof(CopySmem), st>>>(b, w);
-  return 2;
+  return 1;
 }
 
 // ------------------------------------------------------------------ matches -> CSR for the host
