@@ -168,7 +168,8 @@ def run_ours(args, wl, rank, world):
     starts = make_bins(wl, ref, workdir)
     offs = ref.offsets()
     ctx.tail_configure(starts, names, offs)
-    ctx.tail_reserve((args.batch_reads // 2) * (args.steps + 1), 8 * args.batch_reads * (args.steps + 1))
+    # capacity hint: this rank's pairs/hits, and room in the dedupe table for the other ranks' keys
+    ctx.tail_reserve((args.batch_reads // 2) * (args.steps + 1) * world, 8 * args.batch_reads * (args.steps + 1))
     genome = ref.concat()
 
     B = args.batch_reads
@@ -225,7 +226,7 @@ def run_ours(args, wl, rank, world):
         stats_nrec += r.n_records
     # tail_finish runs on the library's own stream and returns synchronised; the allreduce runs on
     # torch's stream: time both on the host between two full synchronisations
-    torch.cuda.synchronize()
+    barrier()                                            # ranks reach the tail together (their untimed uploads differ)
     t_f = time.perf_counter()
     counts_g, stats = finish()                           # includes the one all_reduce of the per-bin counts
     torch.cuda.synchronize()

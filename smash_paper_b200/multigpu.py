@@ -55,18 +55,39 @@ def previous_last_pos(edges, rank):
 
 def sharded_tail_finish(backend, dist, rank, world):
     """Runs the three exchanges; returns (global counts tensor, global stats dict)."""
+    import os
+    import time
+    dbg = os.environ.get("SMASH_DEBUG_TIMING") and rank == world - 1
+    t = [time.perf_counter()]
+
+    def lap(label):
+        if dbg:
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            t.append(time.perf_counter())
+            print(f"[smash-dbg] sharded_finish:{label:14s} {1e3 * (t[-1] - t[-2]):8.3f} ms", flush=True)
+
     keys = backend.export_keys()
+    lap("export")
     parts = gather_varlen(keys, dist, world) if world > 1 else [keys]
-    n_f, first, last = backend.phase_a(lower_rank_keys(parts, rank))
+    lap("gather keys")
+    foreign = lower_rank_keys(parts, rank)
+    lap("cat")
+    n_f, first, last = backend.phase_a(foreign)
+    lap("phase_a")
     e = torch.tensor([[n_f, first, last]], dtype=torch.int64, device=keys.device)
     edges = [tuple(int(v) for v in x[0]) for x in gather_varlen(e, dist, world)] if world > 1 else [(n_f, first, last)]
     has_prev, prev = previous_last_pos(edges, rank)
+    lap("edges")
     counts, stats = backend.phase_b(has_prev, prev)
+    lap("phase_b")
     sv = torch.tensor([stats[k] for k in STAT_KEYS], dtype=torch.int64, device=counts.device)
     if world > 1:
         dist.all_reduce(counts)
         dist.all_reduce(sv)
-    return counts, dict(zip(STAT_KEYS, [int(v) for v in sv]))
+    out = counts, dict(zip(STAT_KEYS, [int(v) for v in sv]))
+    lap("allreduce")
+    return out
 
 
 class ContextBackend:
