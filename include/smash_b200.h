@@ -174,6 +174,12 @@ typedef struct { uint64_t n_filtered; int64_t first_pos, last_pos; } smash_tail_
 int smash_tail_export_keys(smash_ctx *ctx, uint64_t ordinal_base, const void **dev_keys, uint64_t *n_keys);
 int smash_tail_phase_a(smash_ctx *ctx, uint64_t ordinal_base, const void *foreign_keys_dev, uint64_t n_foreign,
                        smash_tail_edge *edge);
+/* Variant of phase A for many ranks: the host has already resolved the first-wins rule with a
+ * hash-partitioned exchange (every rank owns 1/N of the key space, multigpu.py) and passes, for each of
+ * this rank's exported keys (same order as smash_tail_export_keys), the smallest global ordinal that
+ * carries that key; a pair survives iff that ordinal is its own. */
+int smash_tail_phase_a_verdict(smash_ctx *ctx, uint64_t ordinal_base, const void *min_ordinal_dev, uint64_t n_keys,
+                               smash_tail_edge *edge);
 int smash_tail_phase_b(smash_ctx *ctx, int has_prev, int64_t prev_last_pos, int64_t *counts, void *counts_device,
                        smash_tail_stats *st);
 /* positions.txt rows produced so far by smash_tail_finish: chromosome index (into the forward

@@ -353,6 +353,12 @@ class Context:
                                                  C.c_uint64(n_foreign), C.byref(e)))
         return int(e.n_filtered), int(e.first_pos), int(e.last_pos)
 
+    def tail_phase_a_verdict(self, ordinal_base, min_ord_ptr, n_keys):
+        e = _TailEdge()
+        _check(load_library().smash_tail_phase_a_verdict(self.h, C.c_uint64(ordinal_base), C.c_void_p(min_ord_ptr) if n_keys else None,
+                                                         C.c_uint64(n_keys), C.byref(e)))
+        return int(e.n_filtered), int(e.first_pos), int(e.last_pos)
+
     def tail_phase_b(self, has_prev=False, prev_last_pos=0, counts_device_ptr=None):
         counts = np.zeros(self.n_bins, dtype=np.int64)
         st = _TailStats()

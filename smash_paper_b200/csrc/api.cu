@@ -219,6 +219,7 @@ struct Slot {
   DBuf<int64_t> csr_off; DBuf<uint64_t> csr_triples;
   DBuf<uint64_t> slot_off; DBuf<Aln> aln_scr; DBuf<uint16_t> ord_scr; DBuf<uint32_t> tmp32;   // MEM mode (CSR slots)
   uint64_t slots_total = 0; bool csr = false;
+  DBuf<uint8_t> long_scratch; int long_q = 0;
   // results on host
   HBuf<char> h_sam; HBuf<int64_t> h_csr_off; HBuf<smash_match> h_matches; HBuf<uint64_t> h_small;
   // in flight
@@ -532,7 +533,7 @@ static void slot_release(Slot &s) {
   s.seq_off.release(); s.opt_off.release(); s.read_flag.release(); s.match_slots.release();
   s.match_cnt.release(); s.item_slots.release(); s.rec_slots.release(); s.sums.release();
   s.nrec.release(); s.rec_base.release(); s.rec_read.release(); s.rec_bytes.release(); s.rec_off.release(); s.sam_total.release(); s.blk_sums2.release(); s.blk_sums.release(); s.sam.release(); s.flags.release();
-  s.csr_off.release(); s.csr_triples.release(); s.slot_off.release(); s.aln_scr.release(); s.ord_scr.release(); s.tmp32.release(); s.h_sam.release(); s.h_csr_off.release();
+  s.csr_off.release(); s.csr_triples.release(); s.long_scratch.release(); s.slot_off.release(); s.aln_scr.release(); s.ord_scr.release(); s.tmp32.release(); s.h_sam.release(); s.h_csr_off.release();
   s.h_matches.release(); s.h_small.release();
   if (s.ev0) cudaEventDestroy(s.ev0);
   if (s.ev1) cudaEventDestroy(s.ev1);
@@ -628,13 +629,23 @@ static int slot_prepare(smash_ctx *c, Slot &s, const smash_batch *b, bool copy) 
   s.bd.seq_off = s.seq_off.p; s.bd.opt = opt_bytes ? s.opt.p : nullptr; s.bd.opt_off = opt_bytes ? s.opt_off.p : nullptr;
   s.bd.read_flag = s.read_flag.p;
   s.n_reads = n; s.first_pair = b->first_pair_ordinal;
+  // reads longer than the shared-memory staging buffer get per-warp scratch in HBM (exact search path)
+  int64_t max_q = 0;
+  for (uint64_t i = 0; i < n; ++i) { const int64_t q = b->seq_off[i + 1] - b->seq_off[i]; if (q > max_q) max_q = q; }
+  s.long_q = 0;
+  if (max_q > MAXQ_FAST) {
+    if (max_q > 60000) return fail(SMASH_ERR_ARG, "read of %lld bases: reads longer than 60000 are not supported", (long long)max_q);
+    s.long_q = (int)max_q;
+    if ((rc = s.long_scratch.ensure((size_t)148 * 8 * 8 * (size_t)(max_q + P_FRONT + P_BACK + 8)))) return rc;
+  }
   return 0;
 }
 
 static WorkDev work_of(Slot &s) {
   WorkDev w{};
   w.cap = s.cap; w.slot_off = s.csr ? s.slot_off.p : nullptr; w.slots_total = s.csr ? s.slots_total : s.n_reads * (uint64_t)s.cap;
-  w.aln_scratch = s.aln_scr.p; w.ord_scratch = s.ord_scr.p; w.match_slots = s.match_slots.p; w.match_cnt = s.match_cnt.p; w.item_slots = s.item_slots.p;
+  w.aln_scratch = s.aln_scr.p; w.ord_scratch = s.ord_scr.p;
+  w.long_scratch = s.long_q ? s.long_scratch.p : nullptr; w.long_q = s.long_q; w.match_slots = s.match_slots.p; w.match_cnt = s.match_cnt.p; w.item_slots = s.item_slots.p;
   w.rec_slots = s.rec_slots.p; w.sums = s.sums.p; w.nrec = s.nrec.p; w.rec_base = s.rec_base.p; w.rec_read = s.rec_read.p; w.rec_bytes = s.rec_bytes.p; w.rec_off = s.rec_off.p; w.sam_total = s.sam_total.p; w.blk_sums2 = s.blk_sums2.p;
   w.blk_sums = s.blk_sums.p; w.sam = s.sam.p; w.sam_cap = s.sam.cap; w.flags = s.flags.p;
   return w;
@@ -684,7 +695,7 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
     CU(cudaMemcpyAsync(s.h_small.p + 1, s.flags.p, sizeof(uint32_t) * N_FLAGS, cudaMemcpyDeviceToHost, s.st));
     { const double ts = now_ms(); CU(cudaStreamSynchronize(s.st)); DBG_T("  run:sync for sizes", ts); }
     const uint32_t *fl = (const uint32_t *)(s.h_small.p + 1);
-    if (fl[FLAG_LONGREAD]) return fail(SMASH_ERR_ARG, "%u reads longer than %d bases are not supported by this build", fl[FLAG_LONGREAD], MAXQ_FAST);
+    if (fl[FLAG_LONGREAD]) return fail(SMASH_ERR_STATE, "%u long reads could not be staged", fl[FLAG_LONGREAD]);
     if (fl[FLAG_OVERFLOW]) {
       const uint32_t need = fl[FLAG_MAXCNT];
       if (need > (uint32_t)STAGE_CAP || attempt > 3)
@@ -876,7 +887,18 @@ extern "C" int smash_tail_phase_a(smash_ctx *c, uint64_t ordinal_base, const voi
   if (!c) return fail(SMASH_ERR_ARG, "null argument");
   CU(cudaSetDevice(c->device));
   for (int s = 0; s < SMASH_N_SLOTS; ++s) CU(cudaStreamSynchronize(c->slot[s].st));
-  int rc = tail_phase_a(&c->tail, ordinal_base, (const uint64_t *)foreign_keys_dev, n_foreign, edge, c->slot[0].st, &c->launches);
+  int rc = tail_phase_a(&c->tail, ordinal_base, (const uint64_t *)foreign_keys_dev, n_foreign, edge, c->slot[0].st, &c->launches, nullptr);
+  if (rc) return fail(rc, "tail: %s", tail_error());
+  return 0;
+}
+extern "C" int smash_tail_phase_a_verdict(smash_ctx *c, uint64_t ordinal_base, const void *min_ordinal_dev, uint64_t n_keys,
+                                          smash_tail_edge *edge) {
+  if (!c || (!min_ordinal_dev && n_keys)) return fail(SMASH_ERR_ARG, "null argument");
+  CU(cudaSetDevice(c->device));
+  for (int s = 0; s < SMASH_N_SLOTS; ++s) CU(cudaStreamSynchronize(c->slot[s].st));
+  static const uint64_t dummy = 0;
+  int rc = tail_phase_a(&c->tail, ordinal_base, nullptr, 0, edge, c->slot[0].st, &c->launches,
+                        n_keys ? (const uint64_t *)min_ordinal_dev : &dummy);
   if (rc) return fail(rc, "tail: %s", tail_error());
   return 0;
 }

@@ -188,10 +188,21 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     const int q = (int)(b.seq_off[read + 1] - so);
     if (lane == 0) sm.nstage[warp] = 0;
     if (q > MAXQ_FAST) {
-      if (lane == 0) { atomicAdd(&w.flags[FLAG_LONGREAD], 1u); w.match_cnt[read] = 0; }
-      __syncwarp();
-      continue;
-    }
+      // long read: staged (lower-cased, padded) in this warp's HBM scratch, exact per-start search
+      if (!w.long_scratch || q > w.long_q) {
+        if (lane == 0) { atomicAdd(&w.flags[FLAG_LONGREAD], 1u); w.match_cnt[read] = 0; }
+        __syncwarp();
+        continue;
+      }
+      uint8_t *gbuf = w.long_scratch + ((uint64_t)blockIdx.x * WARPS + warp) * (uint64_t)(w.long_q + P_FRONT + P_BACK + 8);
+      stage_read(ix, b.seq + so, q, sp.nucleotides_only, gbuf, lane);
+      __threadfence_block();
+      const uint8_t *PL = gbuf + P_FRONT;
+      for (int p = lane; p + (int)sp.L <= q; p += 32) {
+        Match m;
+        if (exact_start(ix, PL, q, p, sp.L, &m)) stage_push(sm, warp, m);
+      }
+    } else {
     const bool odd = stage_read(ix, b.seq + so, q, sp.nucleotides_only, sm.pbuf[warp], lane);
     const uint8_t *P = sm.pbuf[warp] + P_FRONT;
     const int L = (int)sp.L;
@@ -254,6 +265,7 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
         }
       }
     }
+    }   // q <= MAXQ_FAST
     __syncwarp();
     const int n = sm.nstage[warp];
     const int ns = n < STAGE_CAP ? n : STAGE_CAP;

@@ -38,6 +38,8 @@ struct WorkDev {
   char *sam;                   // output text
   uint64_t sam_cap;
   uint32_t *flags;             // N_FLAGS counters
+  uint8_t *long_scratch;       // per-warp staging for reads longer than MAXQ_FAST (null if the batch has none)
+  int long_q;                  // longest read of the batch
 };
 
 HD uint64_t slot_base(const WorkDev &w, uint64_t read) { return w.slot_off ? w.slot_off[read] : read * (uint64_t)w.cap; }

@@ -261,6 +261,23 @@ __global__ void k_dd_resolve(const uint32_t *__restrict__ nhits, const uint64_t 
     if (unres) atomicAdd((unsigned long long *)&stats[2], (unsigned long long)unres);
   }
 }
+// Dupe decision from a precomputed verdict: min_ord[j] = smallest global ordinal carrying the key of
+// this rank's j-th exported (non-empty) pair; off[i] = export index of pair i.
+__global__ void k_dd_from_verdict(const uint32_t *__restrict__ nhits, const uint64_t *__restrict__ off, const uint64_t *__restrict__ min_ord,
+                                  uint64_t n_pairs, uint64_t base, uint8_t *__restrict__ keep, uint64_t *stats) {
+  unsigned dup = 0, non = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (!nhits[i]) { keep[i] = 0; continue; }
+    const bool first = min_ord[off[i]] == base + i;
+    keep[i] = first ? 1 : 0;
+    if (first) ++non; else ++dup;
+  }
+  dup = __reduce_add_sync(0xffffffffu, dup); non = __reduce_add_sync(0xffffffffu, non);
+  if ((threadIdx.x & 31) == 0) {
+    if (dup) atomicAdd((unsigned long long *)&stats[0], (unsigned long long)dup);
+    if (non) atomicAdd((unsigned long long *)&stats[1], (unsigned long long)non);
+  }
+}
 // {fp1, fp2, ordinal} of every non-empty pair, in pair order (=> sorted by ordinal)
 __global__ void k_export_flags(const uint32_t *__restrict__ nhits, uint64_t n, uint32_t *__restrict__ flag) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) flag[i] = nhits[i] != 0;
@@ -338,7 +355,7 @@ __global__ void k_varbin_smem(const int64_t *__restrict__ f_pos, const int64_t *
 // Phase A: duplicate removal (local pairs + foreign keys), ordered compaction into the positions
 // list and the varbin-filtered list; reports the shard's edge (first/last filtered position).
 int tail_phase_a(TailState *t, uint64_t ordinal_base, const uint64_t *foreign_keys, uint64_t n_foreign,
-                 smash_tail_edge *edge, cudaStream_t st, uint64_t *launches) {
+                 smash_tail_edge *edge, cudaStream_t st, uint64_t *launches, const uint64_t *verdict_min_ord) {
   if (!t->configured) return tfail(SMASH_ERR_STATE, "smash_tail_configure has not been called");
   const uint64_t P = t->n_pairs;
   double tq = t_now();
@@ -361,6 +378,17 @@ int tail_phase_a(TailState *t, uint64_t ordinal_base, const uint64_t *foreign_ke
     uint8_t *keep = (uint8_t *)t->scr[3].p;
     TDBG("reserve");
     const int grid = (int)((P + 255) / 256 < 148 * 8 ? (P + 255) / 256 : 148 * 8);
+    if (verdict_min_ord) {
+      // the host already resolved the global first-wins rule (multigpu.py: partitioned exchange)
+      uint32_t *flag = c_pos;                       // scratch reuse: export index of every pair
+      k_export_flags<<<grid, 256, 0, st>>>(t->pair_nhits.p, P, flag);
+      *launches += 1 + exclusive_scan_u32_public(flag, P, blk, o_pos, st);
+      TCU(cudaMemsetAsync(d_stats, 0, 32, st));
+      k_dd_from_verdict<<<grid, 256, 0, st>>>(t->pair_nhits.p, o_pos, verdict_min_ord, P, ordinal_base, keep, d_stats);
+      *launches += 1;
+      TCU(cudaMemcpyAsync(h_stats, d_stats, 32, cudaMemcpyDeviceToHost, st));
+      TCU(cudaStreamSynchronize(st));
+    } else
     for (uint64_t seed = 1;; ++seed) {
       TCU(cudaMemsetAsync(keys, 0xff, 8 * tsize, st)); TCU(cudaMemsetAsync(minord, 0xff, 8 * tsize, st));
       TCU(cudaMemsetAsync(d_stats, 0, 32, st));
@@ -454,7 +482,7 @@ int tail_phase_b(TailState *t, int has_prev, int64_t prev_last_pos, int64_t *cou
 
 int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smash_tail_stats *stats,
                 cudaStream_t st, uint64_t *launches) {
-  int rc = tail_phase_a(t, 0, nullptr, 0, nullptr, st, launches);
+  int rc = tail_phase_a(t, 0, nullptr, 0, nullptr, st, launches, nullptr);
   if (rc) return rc;
   return tail_phase_b(t, 0, 0, counts_host, counts_device, stats, st, launches);
 }

@@ -48,7 +48,7 @@ int tail_accumulate(TailState *t, const DevIndex &ix, const BatchDev &b, const W
 int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smash_tail_stats *stats,
                 cudaStream_t st, uint64_t *launches);
 int tail_phase_a(TailState *t, uint64_t ordinal_base, const uint64_t *foreign_keys, uint64_t n_foreign,
-                 smash_tail_edge *edge, cudaStream_t st, uint64_t *launches);
+                 smash_tail_edge *edge, cudaStream_t st, uint64_t *launches, const uint64_t *verdict_min_ord);
 int tail_phase_b(TailState *t, int has_prev, int64_t prev_last_pos, int64_t *counts_host, int64_t *counts_device,
                  smash_tail_stats *stats, cudaStream_t st, uint64_t *launches);
 int tail_export_keys(TailState *t, uint64_t ordinal_base, const uint64_t **dev_keys, uint64_t *n, cudaStream_t st, uint64_t *launches);

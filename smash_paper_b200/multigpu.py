@@ -53,6 +53,73 @@ def previous_last_pos(edges, rank):
     return False, 0
 
 
+def _all_to_all_rows(chunks, dist, world):
+    """chunks[r] = rows this rank sends to rank r (2-D int64 tensors) -> list of rows received from each rank.
+    NCCL: one all_to_all_single with split sizes; gloo (CPU tests): all_gather of the padded buckets."""
+    dev = chunks[0].device
+    ncol = chunks[0].shape[1]
+    send_counts = torch.tensor([c.shape[0] for c in chunks], dtype=torch.int64, device=dev)
+    all_counts = [torch.zeros_like(send_counts) for _ in range(world)]
+    dist.all_gather(all_counts, send_counts)                       # all_counts[src][dst]
+    rank = dist.get_rank()
+    recv_counts = [int(all_counts[src][rank].item()) for src in range(world)]
+    send = torch.cat(chunks, dim=0).contiguous() if sum(c.shape[0] for c in chunks) else torch.zeros((0, ncol), dtype=torch.int64, device=dev)
+    if dist.get_backend() == "nccl":
+        recv = torch.zeros((sum(recv_counts), ncol), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=[int(c.shape[0]) for c in chunks])
+        out, o = [], 0
+        for n in recv_counts:
+            out.append(recv[o:o + n]); o += n
+        return out
+    everything = gather_varlen(send, dist, world)                  # CPU fallback: everyone sees every bucket
+    out = []
+    for src in range(world):
+        start = int(sum(int(all_counts[src][d].item()) for d in range(rank)))
+        out.append(everything[src][start:start + recv_counts[src]])
+    return out
+
+
+def partitioned_min_ordinals(keys, dist, rank, world):
+    """For every row {fp1, fp2, ordinal} of `keys` the smallest ordinal over ALL ranks that carries the same
+    (fp1, fp2).  The key space is hash-partitioned: rank r resolves the keys with fp1 mod world == r, so the
+    work and the traffic per rank stay constant as ranks are added (weak scaling), unlike an all_gather."""
+    n = keys.shape[0]
+    dev = keys.device
+    owner = torch.remainder(keys[:, 0], world) if n else torch.zeros(0, dtype=torch.int64, device=dev)
+    order = torch.argsort(owner, stable=True)
+    sorted_keys = keys[order]
+    counts = torch.bincount(owner, minlength=world).tolist() if n else [0] * world
+    chunks, o = [], 0
+    for c in counts:
+        chunks.append(sorted_keys[o:o + c]); o += c
+    got = _all_to_all_rows(chunks, dist, world)
+    recv_counts = [g.shape[0] for g in got]
+    allk = torch.cat(got, dim=0) if sum(recv_counts) else torch.zeros((0, 3), dtype=torch.int64, device=dev)
+    # group identical (fp1, fp2): three stable sorts (ordinal, fp2, fp1) -> the first row of a group has its minimum ordinal
+    if allk.shape[0]:
+        p = torch.argsort(allk[:, 2], stable=True)
+        p = p[torch.argsort(allk[p, 1], stable=True)]
+        p = p[torch.argsort(allk[p, 0], stable=True)]
+        s = allk[p]
+        head = torch.ones(s.shape[0], dtype=torch.bool, device=dev)
+        head[1:] = (s[1:, 0] != s[:-1, 0]) | (s[1:, 1] != s[:-1, 1])
+        gid = torch.cumsum(head.to(torch.int64), 0) - 1
+        group_min = s[head, 2]
+        mins_sorted = group_min[gid]
+        mins = torch.empty_like(mins_sorted)
+        mins[p] = mins_sorted
+    else:
+        mins = torch.zeros(0, dtype=torch.int64, device=dev)
+    back_chunks, o = [], 0
+    for c in recv_counts:
+        back_chunks.append(mins[o:o + c].reshape(-1, 1)); o += c
+    back = _all_to_all_rows(back_chunks, dist, world)
+    mins_for_sorted = torch.cat(back, dim=0).reshape(-1) if n else torch.zeros(0, dtype=torch.int64, device=dev)
+    result = torch.empty(n, dtype=torch.int64, device=dev)
+    result[order] = mins_for_sorted
+    return result
+
+
 def sharded_tail_finish(backend, dist, rank, world):
     """Runs the three exchanges; returns (global counts tensor, global stats dict)."""
     import os
@@ -69,11 +136,17 @@ def sharded_tail_finish(backend, dist, rank, world):
 
     keys = backend.export_keys()
     lap("export")
-    parts = gather_varlen(keys, dist, world) if world > 1 else [keys]
-    lap("gather keys")
-    foreign = lower_rank_keys(parts, rank)
-    lap("cat")
-    n_f, first, last = backend.phase_a(foreign)
+    if world > 2 and hasattr(backend, "phase_a_verdict"):
+        # many ranks: hash-partitioned exchange, O(1) keys per rank
+        mins = partitioned_min_ordinals(keys, dist, rank, world)
+        lap("partitioned")
+        n_f, first, last = backend.phase_a_verdict(mins)
+    else:
+        parts = gather_varlen(keys, dist, world) if world > 1 else [keys]
+        lap("gather keys")
+        foreign = lower_rank_keys(parts, rank)
+        lap("cat")
+        n_f, first, last = backend.phase_a(foreign)
     lap("phase_a")
     e = torch.tensor([[n_f, first, last]], dtype=torch.int64, device=keys.device)
     edges = [tuple(int(v) for v in x[0]) for x in gather_varlen(e, dist, world)] if world > 1 else [(n_f, first, last)]
@@ -109,6 +182,11 @@ class ContextBackend:
         foreign = foreign.contiguous()
         torch.cuda.synchronize(self.device)
         return self.ctx.tail_phase_a(self.base, foreign.data_ptr() if foreign.shape[0] else None, int(foreign.shape[0]))
+
+    def phase_a_verdict(self, min_ord):
+        min_ord = min_ord.contiguous()
+        torch.cuda.synchronize(self.device)
+        return self.ctx.tail_phase_a_verdict(self.base, min_ord.data_ptr() if min_ord.shape[0] else None, int(min_ord.shape[0]))
 
     def phase_b(self, has_prev, prev):
         _, stats = self.ctx.tail_phase_b(has_prev, prev, self.counts.data_ptr())

@@ -476,3 +476,68 @@ def test_error_paths(workdir, case):
         ctx.close()
     finally:
         ix.close()
+
+
+def test_three_shards_with_verdict_equal_one_run(case):
+    """The many-rank form of the sharded tail on ONE GPU: three contexts, the global first-wins verdict
+    computed from all exported fingerprints (what multigpu.partitioned_min_ordinals produces with its
+    all_to_all exchange), smash_tail_phase_a_verdict + edges + phase_b; summed counts == single run."""
+    import torch
+    from smash_paper_b200 import api, multigpu, samio
+    ix = api.Index.open(case["fa"])
+    base = case["reads"]
+    extra = samio.slice_batch(base, 40, 440)
+    extra.names = extra.names.copy()
+    extra.names[extra.name_off[:-1]] = ord("x")
+    reads = samio.concat_batches([base, extra])
+    sam = case["oix"].map_batch(reads, min_len=20, n_threads=4)
+    exp = oracle_tail(case["oix"], case["body"], sam, case["dir"], case["fa"])
+    ci = exp["chrominfo"]
+    cuts = [0, (reads.n // 6) * 2, (reads.n // 3) * 2 + 200, reads.n]
+    ctxs, backs = [], []
+    try:
+        dev = torch.device("cuda", 0)
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            c = api.Context(ix, min_len=20, nomap=True)
+            c.load_mappability(case["body"])
+            c.tail_configure([int(x[2]) for x in exp["bins"]], list(ci.keys()), [int(v[2]) for v in ci.values()])
+            c.map_batch(samio.slice_batch(reads, a, b), want=api.WANT_TAIL)
+            ctxs.append(c); backs.append(multigpu.ContextBackend(c, a // 2, dev))
+        keys = [bk.export_keys() for bk in backs]
+        allk = torch.cat(keys, 0)
+        uniq, inv = torch.unique(allk[:, :2], dim=0, return_inverse=True)
+        gmin = torch.full((uniq.shape[0],), 2 ** 62, dtype=torch.int64, device=dev).scatter_reduce(0, inv, allk[:, 2], "amin")
+        mins = gmin[inv]
+        edges, o = [], 0
+        for bk, k in zip(backs, keys):
+            edges.append(bk.phase_a_verdict(mins[o:o + k.shape[0]])); o += k.shape[0]
+        total = torch.zeros(len(exp["bins"]), dtype=torch.int64, device=dev)
+        stats = {k: 0 for k in multigpu.STAT_KEYS}
+        for r, bk in enumerate(backs):
+            hp, pv = multigpu.previous_last_pos(edges, r)
+            cts, st = bk.phase_b(hp, pv)
+            total += cts
+            for k in multigpu.STAT_KEYS:
+                stats[k] += st[k]
+        torch.cuda.synchronize()
+        assert np.array_equal(total.cpu().numpy(), exp["counts"])
+        assert (stats["total_reads"], stats["dups_removed"], stats["reads_kept"]) == (exp["total"], exp["dups"], exp["kept"])
+        assert (stats["n_dupe_pairs"], stats["n_non_dupe_pairs"]) == (exp["n_dupe"], exp["n_non"]) and exp["n_dupe"] >= 200
+    finally:
+        for c in ctxs:
+            c.close()
+        ix.close()
+
+
+def test_long_reads(workdir):
+    """Reads longer than the shared-memory staging buffer (1024) take the HBM-staged exact search path."""
+    from smash_paper_b200 import api
+    d = os.path.join(workdir, "long_reads")
+    ref, reads, fa, oix, body = make_case(d, n_pairs=60, seed=77, read_len=1500, frag_min=10, frag_max=30)
+    ix = api.Index.open(fa)
+    ctx = api.Context(ix, min_len=20, nomap=True)
+    try:
+        sam = oix.map_batch(reads, min_len=20, n_threads=4)
+        assert ctx.map_batch(reads).sam == sam
+    finally:
+        ctx.close(); ix.close()

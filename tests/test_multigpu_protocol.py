@@ -90,6 +90,21 @@ class NumpyTail:
             self.F.extend(p for _, p in h)
         return len(self.F), (self.F[0] if self.F else 0), (self.F[-1] if self.F else 0)
 
+    def phase_a_verdict(self, min_ord):
+        mo = min_ord.tolist()
+        self.F, self.nd, self.nn = [], 0, 0
+        j = 0
+        for i, h in enumerate(self.pairs):
+            if not h:
+                continue
+            if mo[j] == self.base + i:
+                self.nn += 1
+                self.F.extend(p for _, p in h)
+            else:
+                self.nd += 1
+            j += 1
+        return len(self.F), (self.F[0] if self.F else 0), (self.F[-1] if self.F else 0)
+
     def phase_b(self, has_prev, prev):
         counts = torch.zeros(N_BINS, dtype=torch.int64)
         dups = 0
@@ -116,11 +131,16 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_ranks_equal_single_process():
+import pytest
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ranks_equal_single_process(world):
+    """world 2: all_gather of the keys of lower ranks; world 3: hash-partitioned exchange + verdict."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + 7 * world) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     counts, stats = q.get(timeout=120)
