@@ -290,6 +290,15 @@ def run_ours(args, wl, rank, world):
             gbs = B * alg[kname] / (ms / 1e3) / 1e9 if ms > 0 else 0.0
             per_kernel[kname] = {"ms": ms, "alg_bytes_per_read": alg[kname], "achieved_gbs": gbs, "frac": gbs / peak}
         dom = max(per_kernel, key=lambda k: per_kernel[k]["ms"])
+        # DRAM traffic of that kernel from the committed ncu --set full capture of this workload (1 M reads per launch)
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", f"r01_dram_traffic_{args.workload}.json")))
+            if dom in tj:
+                traffic = (tj[dom]["dram_read_bytes"] + tj[dom]["dram_write_bytes"]) * (B / 1e6)
+                traffic_src = f"profiles/r01_ncu_full_{args.workload}_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum, scaled to {B} reads/launch)"
+        except (OSError, ValueError):
+            pass
         search_ms = per_kernel["k_mam_search"]["ms"]
         achieved = per_kernel[dom]["achieved_gbs"]
         out = {
@@ -306,7 +315,7 @@ def run_ours(args, wl, rank, world):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": dom, "kernel_ms": per_kernel[dom]["ms"], "alg_bytes_per_read": per_kernel[dom]["alg_bytes_per_read"],
                          "kernels": per_kernel,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
