@@ -10,9 +10,15 @@
 #if defined(__CUDACC__)
 #define HD __host__ __device__ __forceinline__
 #define HDN __host__ __device__
+#if defined(SMASH_EXACT_INLINE)
+#define HDNI __host__ __device__
+#else
+#define HDNI __host__ __device__ __noinline__
+#endif
 #else
 #define HD inline
 #define HDN
+#define HDNI
 #endif
 
 namespace smash {
@@ -178,7 +184,8 @@ HD bool is_unique(const DevIndex &ix, uint64_t r, uint32_t len, uint64_t sa_inde
 // Exact answer for ONE start p: longest prefix of P[p..q) in the text by
 // binary search over the suffix array (optionally inside the seed bucket), its uniqueness and
 // left-maximality.  Returns true and fills m when (p) is a reportable MAM.
-HD bool exact_start(const DevIndex &ix, const uint8_t *P, int q, int p, uint32_t L, Match *m) {
+// (kept out of line on the device: it is the rare path and is called from three places of k_mam_search)
+HDNI inline bool exact_start(const DevIndex &ix, const uint8_t *P, int q, int p, uint32_t L, Match *m) {
   if (q - p < (int)L) return false;
   const uint8_t *T = ix.text;
   uint64_t lo = 0, hi = ix.N;

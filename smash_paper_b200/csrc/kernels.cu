@@ -150,6 +150,7 @@ __device__ __forceinline__ bool stage_read(const DevIndex &ix, const uint8_t *__
 constexpr int TASK_CAP = 128;
 
 struct SearchSmem {
+  uint16_t lut[256];                           // byte -> lower-cased byte | 0x100 (not acgt) | 0x200 (not acgt but occurs in the text)
   uint8_t pbuf[WARPS][PBUF];
   uint32_t inv[WARPS][MAXQ_FAST / 32 + 2];     // non-acgt mask of the read, one bit per base
   Match stage[WARPS][STAGE_CAP];
@@ -161,6 +162,13 @@ struct SearchSmem {
 __device__ __forceinline__ void stage_push(SearchSmem &sm, int warp, const Match &m) {
   const int slot = atomicAdd(&sm.nstage[warp], 1);
   if (slot < STAGE_CAP) sm.stage[warp][slot] = m;
+}
+// every start of the read through the exact per-start search (reads the anchor path cannot take)
+__device__ __noinline__ void exact_all(const DevIndex &ix, SearchSmem &sm, int warp, int lane, const uint8_t *P, int q, const SearchParams &sp) {
+  for (int p = lane; p + (int)sp.L <= q; p += 32) {
+    Match m;
+    if (exact_start(ix, P, q, p, sp.L, &m)) stage_push(sm, warp, m);
+  }
 }
 // lanes = tasks: extend every queued candidate
 __device__ __forceinline__ void run_tasks(const DevIndex &ix, SearchSmem &sm, int warp, int lane, const uint8_t *P, int q,
@@ -178,43 +186,67 @@ __device__ __forceinline__ void run_tasks(const DevIndex &ix, SearchSmem &sm, in
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(THREADS)
+// Warp-cooperative staging for the search: lower-case the read into shared memory through the
+// per-CTA lookup table, build the non-acgt bit mask (one ballot per 32 bases) in the same pass, and
+// report whether a non-acgt byte that also occurs in the text was seen (=> exact path).
+__device__ __forceinline__ bool stage_read_masked(SearchSmem &sm, int warp, const uint8_t *__restrict__ seq, int q, int lane) {
+  uint8_t *pbuf = sm.pbuf[warp];
+  uint8_t *P = pbuf + P_FRONT;
+  bool odd = false;
+  const int rounds = q / 32 + 2;                 // one spare mask word (kmer_invalid reads word+1)
+  for (int it = 0; it < rounds; ++it) {
+    const int j = it * 32 + lane;
+    uint16_t e = 0;
+    if (j < q) { e = sm.lut[seq[j]]; P[j] = (uint8_t)e; odd |= (e & 0x200) != 0; }
+    const unsigned bad = __ballot_sync(0xffffffffu, (e & 0x100) != 0);
+    if (lane == 0) sm.inv[warp][it] = bad;
+  }
+  if (lane < P_FRONT) pbuf[lane] = 0xFE;
+  if (lane < P_BACK) P[q + lane] = 0xFF;
+  __syncwarp();
+  return __any_sync(0xffffffffu, odd);
+}
+
+#ifndef SMASH_MINBLK
+#define SMASH_MINBLK 4
+#endif
+#ifndef SMASH_LUT
+#define SMASH_LUT 1
+#endif
+__global__ void __launch_bounds__(THREADS, SMASH_MINBLK)
 k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
   __shared__ __align__(16) SearchSmem sm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {
+    const uint8_t c = query_char((uint8_t)threadIdx.x, sp.nucleotides_only);
+    const bool not_acgt = base_code(c) > 3;
+    sm.lut[threadIdx.x] = (uint16_t)(c | (not_acgt ? 0x100 : 0) | (not_acgt && in_alpha(ix, c) ? 0x200 : 0));
+  }
+  __syncthreads();
   const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
   for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
     const int64_t so = b.seq_off[read];
     const int q = (int)(b.seq_off[read + 1] - so);
     if (lane == 0) sm.nstage[warp] = 0;
-    if (q > MAXQ_FAST) {
-      // long read: staged (lower-cased, padded) in this warp's HBM scratch, exact per-start search
-      if (!w.long_scratch || q > w.long_q) {
-        if (lane == 0) { atomicAdd(&w.flags[FLAG_LONGREAD], 1u); w.match_cnt[read] = 0; }
-        __syncwarp();
-        continue;
-      }
-      uint8_t *gbuf = w.long_scratch + ((uint64_t)blockIdx.x * WARPS + warp) * (uint64_t)(w.long_q + P_FRONT + P_BACK + 8);
-      stage_read(ix, b.seq + so, q, sp.nucleotides_only, gbuf, lane);
-      __threadfence_block();
-      const uint8_t *PL = gbuf + P_FRONT;
-      for (int p = lane; p + (int)sp.L <= q; p += 32) {
-        Match m;
-        if (exact_start(ix, PL, q, p, sp.L, &m)) stage_push(sm, warp, m);
-      }
-    } else {
+    if (q > MAXQ_FAST) continue;                   // k_mam_search_long takes these
+    {
+#if SMASH_LUT
+    const bool odd = stage_read_masked(sm, warp, b.seq + so, q, lane);
+    const uint8_t *P = sm.pbuf[warp] + P_FRONT;
+#else
     const bool odd = stage_read(ix, b.seq + so, q, sp.nucleotides_only, sm.pbuf[warp], lane);
     const uint8_t *P = sm.pbuf[warp] + P_FRONT;
+    for (int c0 = 0; c0 <= q / 32 + 1; ++c0) {
+      const int j = c0 * 32 + lane;
+      const unsigned bad = __ballot_sync(0xffffffffu, j < q && base_code(P[j]) > 3);
+      if (lane == 0) sm.inv[warp][c0] = bad;
+    }
+    __syncwarp();
+#endif
     const int L = (int)sp.L;
     if (q >= L) {
       if (!odd && sp.fast_ok) {
-        // non-acgt mask (such bytes do not occur in the text here, so no match can contain them)
-        for (int c0 = 0; c0 <= q / 32 + 1; ++c0) {
-          const int j = c0 * 32 + lane;
-          const unsigned bad = __ballot_sync(0xffffffffu, j < q && base_code(P[j]) > 3);
-          if (lane == 0) sm.inv[warp][c0] = bad;
-        }
-        __syncwarp();
+        // (bytes flagged in the non-acgt mask do not occur in the text here, so no match can contain them)
         const int s = sp.s, k = sp.k;
         const int n_anchor = (q - L + s - 1) / s + 1;        // anchors x = a*s cover starts 0..q-L
         int ntask = 0;
@@ -259,10 +291,7 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
         }
         run_tasks(ix, sm, warp, lane, P, q, sp, ntask);
       } else {
-        for (int p = lane; p + L <= q; p += 32) {
-          Match m;
-          if (exact_start(ix, P, q, p, sp.L, &m)) stage_push(sm, warp, m);
-        }
+        exact_all(ix, sm, warp, lane, P, q, sp);
       }
     }
     }   // q <= MAXQ_FAST
@@ -299,9 +328,66 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
   }
 }
 
+// Reads longer than the shared-memory staging buffer: staged (lower-cased, padded) in this warp's HBM
+// scratch and searched with the exact per-start path.  Launched only when the batch has such reads.
+struct LongSmem { Match stage[WARPS][STAGE_CAP]; int nstage[WARPS]; };
+__global__ void __launch_bounds__(THREADS)
+k_mam_search_long(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
+  __shared__ __align__(16) LongSmem sm;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
+  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
+    const int64_t so = b.seq_off[read];
+    const int q = (int)(b.seq_off[read + 1] - so);
+    if (q <= MAXQ_FAST) continue;
+    if (lane == 0) sm.nstage[warp] = 0;
+    __syncwarp();
+    if (!w.long_scratch || q > w.long_q) {
+      if (lane == 0) { atomicAdd(&w.flags[FLAG_LONGREAD], 1u); w.match_cnt[read] = 0; }
+      continue;
+    }
+    uint8_t *gbuf = w.long_scratch + ((uint64_t)blockIdx.x * WARPS + warp) * (uint64_t)(w.long_q + P_FRONT + P_BACK + 8);
+    stage_read(ix, b.seq + so, q, sp.nucleotides_only, gbuf, lane);
+    __threadfence_block();
+    const uint8_t *P = gbuf + P_FRONT;
+    for (int p = lane; p + (int)sp.L <= q; p += 32) {
+      Match m;
+      if (exact_start(ix, P, q, p, sp.L, &m)) {
+        const int slot = atomicAdd(&sm.nstage[warp], 1);
+        if (slot < STAGE_CAP) sm.stage[warp][slot] = m;
+      }
+    }
+    __syncwarp();
+    const int n = sm.nstage[warp];
+    const int ns = n < STAGE_CAP ? n : STAGE_CAP;
+    Match *dst = w.match_slots + slot_base(w, read);
+    for (int e = lane; e < ns; e += 32) {
+      const Match me = sm.stage[warp][e];
+      int rank = 0;
+      for (int f = 0; f < ns; ++f) rank += sm.stage[warp][f].qpos < me.qpos;
+      if (rank < w.cap) dst[rank] = me;
+    }
+    int n_out = n;
+    if (sp.mum && n <= w.cap && n <= STAGE_CAP) {
+      __syncwarp();
+      for (int e = lane; e < ns; e += 32) sm.stage[warp][e] = dst[e];
+      __syncwarp();
+      if (lane == 0) { uint16_t ord[STAGE_CAP]; n_out = mum_clean(sm.stage[warp], ns, ord, dst); }
+      n_out = __shfl_sync(0xffffffffu, n_out, 0);
+    }
+    if (lane == 0) {
+      w.match_cnt[read] = (uint32_t)n_out;
+      if (n > w.cap || n > STAGE_CAP) atomicAdd(&w.flags[FLAG_OVERFLOW], 1u);
+      atomicMax(&w.flags[FLAG_MAXCNT], (uint32_t)n);
+    }
+    __syncwarp();
+  }
+}
+
 int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
   if (!b.n_reads) return 0;
   k_mam_search<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p);
+  if (w.long_q > MAXQ_FAST) { k_mam_search_long<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p); return 2; }
   return 1;
 }
 
