@@ -25,6 +25,7 @@ using namespace smash;
 static thread_local char g_err[1024] = "";
 #include <chrono>
 static const bool g_dbg = getenv("SMASH_DEBUG_TIMING") != nullptr;
+static cudaEvent_t g_tl_base = nullptr;
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 #define DBG_T(label, t0) do { if (g_dbg) fprintf(stderr, "[smash-dbg] %-28s %8.3f ms\n", label, now_ms() - (t0)); } while (0)
 static int fail(int code, const char *fmt, ...) {
@@ -193,7 +194,7 @@ template <class T> struct HBuf {        // growable pinned host buffer
     if (p) cudaFreeHost(p);
     p = nullptr;
     size_t want = n + n / 4 + 64;
-    cudaError_t e = cudaHostAlloc((void **)&p, want * sizeof(T), cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc((void **)&p, want * sizeof(T), cudaHostAllocMapped);
     if (e != cudaSuccess) { cap = 0; return fail(SMASH_ERR_NOMEM, "cudaHostAlloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e)); }
     cap = want;
     return 0;
@@ -206,6 +207,7 @@ struct Slot {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries
   int n_evs = 0; int ev_stage[8];
+  cudaEvent_t tl[3] = {nullptr, nullptr, nullptr};   // SMASH_DEBUG_TIMING timeline: submit, D2H begin, D2H end
   // batch on device
   DBuf<uint8_t> names, seq, qual, opt;
   DBuf<int64_t> name_off, seq_off, opt_off;
@@ -690,9 +692,7 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
     MARK(1);
     c->launches += launch_sizes_scan(c->dix, s.bd, w, c->sp, s.st);
     MARK(2);
-    CU(cudaMemcpyAsync(s.h_small.p, s.sam_total.p, 8, cudaMemcpyDeviceToHost, s.st));
-    CU(cudaMemcpyAsync(s.h_small.p + 8, s.rec_base.p + n, 8, cudaMemcpyDeviceToHost, s.st));
-    CU(cudaMemcpyAsync(s.h_small.p + 1, s.flags.p, sizeof(uint32_t) * N_FLAGS, cudaMemcpyDeviceToHost, s.st));
+    c->launches += launch_publish(s.h_small.p, (const uint64_t *)s.sam_total.p, (const uint64_t *)(s.rec_base.p + n), s.flags.p, s.st);
     { const double ts = now_ms(); CU(cudaStreamSynchronize(s.st)); DBG_T("  run:sync for sizes", ts); }
     const uint32_t *fl = (const uint32_t *)(s.h_small.p + 1);
     if (fl[FLAG_LONGREAD]) return fail(SMASH_ERR_STATE, "%u long reads could not be staged", fl[FLAG_LONGREAD]);
@@ -723,7 +723,9 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
     MARK(6);
     if (to_host) {
       if ((rc = s.h_sam.ensure(s.sam_bytes + 64))) return rc;
+      if (g_dbg && s.tl[1]) cudaEventRecord(s.tl[1], s.st);
       CU(cudaMemcpyAsync(s.h_sam.p, s.sam.p, s.sam_bytes, cudaMemcpyDeviceToHost, s.st));
+      if (g_dbg && s.tl[2]) cudaEventRecord(s.tl[2], s.st);
     }
   }
   if (want & SMASH_WANT_MATCHES) {
@@ -756,6 +758,12 @@ static int slot_finish(smash_ctx *c, Slot &s, smash_result *res) {
     cudaEvent_t prev = s.ev0;
     for (int e = 0; e < s.n_evs; ++e) { float ms = 0; if (cudaEventElapsedTime(&ms, prev, s.evs[e]) == cudaSuccess) c->stage_ms[s.ev_stage[e]] += ms; prev = s.evs[e]; }
     s.n_evs = 0;
+    if (g_dbg && s.tl[0] && g_tl_base && (s.want & SMASH_WANT_SAM)) {
+      float a = 0, b0 = 0, d0 = 0, d1 = 0, e1 = 0;
+      cudaEventElapsedTime(&a, g_tl_base, s.tl[0]); cudaEventElapsedTime(&b0, g_tl_base, s.ev0);
+      cudaEventElapsedTime(&d0, g_tl_base, s.tl[1]); cudaEventElapsedTime(&d1, g_tl_base, s.tl[2]); cudaEventElapsedTime(&e1, g_tl_base, s.ev1);
+      fprintf(stderr, "[smash-tl] slot %d  h2d %.2f..%.2f  compute ..%.2f  d2h %.2f..%.2f  end %.2f\n", (int)(&s - c->slot), a, b0, d0, d0, d1, e1);
+    }
   }
   if (res) {
     memset(res, 0, sizeof *res);
@@ -777,6 +785,11 @@ extern "C" int smash_submit(smash_ctx *c, int slot, const smash_batch *b, int wa
   if (s.busy) return fail(SMASH_ERR_STATE, "slot %d still has a batch in flight", slot);
   CU(cudaSetDevice(c->device));
   double t0 = now_ms();
+  if (g_dbg) {
+    if (!g_tl_base) { cudaEventCreate(&g_tl_base); cudaEventRecord(g_tl_base, s.st); }
+    for (int e = 0; e < 3; ++e) if (!s.tl[e]) cudaEventCreate(&s.tl[e]);
+    cudaEventRecord(s.tl[0], s.st);
+  }
   int rc = slot_prepare(c, s, b, true);
   DBG_T("submit:prepare+h2d enqueue", t0);
   if (rc) return rc;

@@ -682,6 +682,20 @@ static int exclusive_scan_u32_devn(const uint32_t *in, uint64_t n_bound, const u
   return 3;
 }
 
+// The three small results the host needs between the scan and the emit kernels (SAM bytes, record
+// count, flag counters) go to MAPPED pinned host memory with plain stores: a copy-engine transfer
+// would queue behind the other slot's in-flight SAM download and stall this slot for its whole length.
+__global__ void k_publish(uint64_t *__restrict__ host_small, const uint64_t *__restrict__ sam_total,
+                          const uint64_t *__restrict__ rec_total, const uint32_t *__restrict__ flags) {
+  if (threadIdx.x == 0) { host_small[0] = *sam_total; host_small[8] = *rec_total; }
+  if (threadIdx.x < N_FLAGS) ((uint32_t *)(host_small + 1))[threadIdx.x] = flags[threadIdx.x];
+  __threadfence_system();
+}
+int launch_publish(uint64_t *host_small, const uint64_t *sam_total, const uint64_t *rec_total, const uint32_t *flags, cudaStream_t st) {
+  k_publish<<<1, 32, 0, st>>>(host_small, sam_total, rec_total, flags);
+  return 1;
+}
+
 int launch_sizes_scan(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
   if (!b.n_reads) return 0;
   k_sizes<<<sm_count() * 16, 128, 0, st>>>(ix, b, w, p);

@@ -72,6 +72,7 @@ int launch_mem_write(const DevIndex &ix, const BatchDev &b, const SearchParams &
 // slot_off = exclusive scan of (match_cnt + 1): one spare slot per read for the unmapped placeholder
 int launch_slot_offsets(const uint32_t *match_cnt, uint64_t n_reads, uint32_t *tmp, uint64_t *blk, uint64_t *slot_off, cudaStream_t st);
 int launch_records(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
+int launch_publish(uint64_t *host_small, const uint64_t *sam_total, const uint64_t *rec_total, const uint32_t *flags, cudaStream_t st);
 int launch_sizes_scan(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
 int launch_emit_text(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st, uint64_t n_records);
 int launch_emit_copy(const BatchDev &b, const WorkDev &w, cudaStream_t st, uint64_t n_records);
