@@ -125,6 +125,10 @@ def pinned_batch(api, batch):
         out[k] = p.array
         keep.append(p)
     b = synth.ReadBatch(**out)
+    rf = api.PinnedArray(batch.flags.shape, np.uint16)        # reader-side flag word (query.h:56-64), 2 B/read
+    rf.array[...] = api.read_flags_from_sam_flags(batch.flags)
+    b.read_flag = rf.array
+    keep.append(rf)
     b._pinned = keep
     return b
 

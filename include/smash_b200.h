@@ -195,6 +195,12 @@ int smash_tail_reset(smash_ctx *ctx);
  * tail between library-owned device memory and its own (e.g. torch) tensors. */
 int smash_memcpy(void *dst, const void *src, size_t bytes);
 
+/* smash_submit cuts a batch into up to `max_chunks` (1..4) read ranges that flow through separate
+ * upload / kernel / download streams, so the SAM text of the first range crosses PCIe while later
+ * ranges are still searched; batches under `min_reads` reads go through whole.  Defaults 4 / 65536.
+ * The output is byte-identical either way (MEM mode and SMASH_WANT_MATCHES always go through whole). */
+int smash_ctx_set_chunking(smash_ctx *ctx, int max_chunks, uint64_t min_reads);
+
 /* ---- counters for bench.py: kernels launched by this library since ctx creation */
 uint64_t smash_ctx_launch_count(const smash_ctx *ctx);
 /* Device milliseconds accumulated per stage since the last reset, measured with CUDA events on the

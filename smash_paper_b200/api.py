@@ -372,6 +372,10 @@ class Context:
     def tail_reset(self):
         _check(load_library().smash_tail_reset(self.h))
 
+    def set_chunking(self, max_chunks=4, min_reads=65536):
+        """smash_ctx_set_chunking: how smash_submit pipelines one batch (output is identical either way)."""
+        _check(load_library().smash_ctx_set_chunking(self.h, int(max_chunks), C.c_uint64(int(min_reads))))
+
     def stage_ms(self, reset=False):
         out = (C.c_double * 8)()
         load_library().smash_ctx_stage_ms(self.h, out, int(reset))

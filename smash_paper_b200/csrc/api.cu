@@ -26,6 +26,7 @@ static thread_local char g_err[1024] = "";
 #include <chrono>
 static const bool g_dbg = getenv("SMASH_DEBUG_TIMING") != nullptr;
 static cudaEvent_t g_tl_base = nullptr;
+static const bool g_no_chunks = getenv("SMASH_NO_CHUNKS") != nullptr;   // A/B switch for the chunked submit pipeline
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 #define DBG_T(label, t0) do { if (g_dbg) fprintf(stderr, "[smash-dbg] %-28s %8.3f ms\n", label, now_ms() - (t0)); } while (0)
 static int fail(int code, const char *fmt, ...) {
@@ -199,14 +200,33 @@ template <class T> struct HBuf {        // growable pinned host buffer
     cap = want;
     return 0;
   }
+  int grow_keep(size_t n, size_t keep) {        // like ensure(), but the first `keep` elements survive
+    if (n <= cap) return 0;
+    T *old = p; p = nullptr; cap = 0;
+    int rc = ensure(n);
+    if (!rc && old && keep) memcpy(p, old, keep * sizeof(T));
+    if (old) cudaFreeHost(old);
+    return rc;
+  }
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
+
+// A submitted batch is cut into up to MAX_CHUNKS read ranges that flow through three streams of the
+// slot (upload -> kernels -> download), so that the SAM text of the first range is already crossing
+// PCIe while the later ranges are still being searched.
+constexpr int MAX_CHUNKS = 4;
+constexpr uint64_t CHUNK_MIN_READS = 65536;
+constexpr int N_EVS = 8 * MAX_CHUNKS;
 
 struct Slot {
   cudaStream_t st = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaEvent_t evs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // stage boundaries
-  int n_evs = 0; int ev_stage[8];
+  bool owns_out = false;
+  cudaStream_t st_in = nullptr, st_out = nullptr;                  // chunked submit: upload / download streams
+  cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_emit[MAX_CHUNKS] = {}, ev_out = nullptr;
+  int n_chunks = 1; uint64_t chunk_r[MAX_CHUNKS + 1] = {}; uint64_t sam_base = 0;
+  cudaEvent_t evs[N_EVS] = {};   // stage boundaries
+  int n_evs = 0; int ev_stage[N_EVS];
   cudaEvent_t tl[3] = {nullptr, nullptr, nullptr};   // SMASH_DEBUG_TIMING timeline: submit, D2H begin, D2H end
   // batch on device
   DBuf<uint8_t> names, seq, qual, opt;
@@ -222,6 +242,7 @@ struct Slot {
   DBuf<uint64_t> slot_off; DBuf<Aln> aln_scr; DBuf<uint16_t> ord_scr; DBuf<uint32_t> tmp32;   // MEM mode (CSR slots)
   uint64_t slots_total = 0; bool csr = false;
   DBuf<uint8_t> long_scratch; int long_q = 0;
+  HBuf<uint16_t> h_flag;       // pinned staging for a pageable read_flag array
   // results on host
   HBuf<char> h_sam; HBuf<int64_t> h_csr_off; HBuf<smash_match> h_matches; HBuf<uint64_t> h_small;
   // in flight
@@ -241,6 +262,7 @@ struct smash_ctx {
   uint64_t *sizes = nullptr; char *descr = nullptr; int *descr_off = nullptr; uint64_t *descr8 = nullptr; uint32_t *alpha = nullptr;
   uint8_t *mapbody = nullptr; uint32_t *chrom_off32 = nullptr;
   uint64_t n_m = 0;
+  int max_chunks = MAX_CHUNKS; uint64_t chunk_min_reads = CHUNK_MIN_READS;
   smash_index *own_index = nullptr;
   uint64_t index_bytes = 0;
   uint64_t launches = 0;
@@ -295,7 +317,15 @@ static int ctx_begin(const smash_params *p, smash_ctx **out) {
   for (int s = 0; s < SMASH_N_SLOTS; ++s) {
     CUC(cudaStreamCreateWithFlags(&c->slot[s].st, cudaStreamNonBlocking));
     CUC(cudaEventCreate(&c->slot[s].ev0)); CUC(cudaEventCreate(&c->slot[s].ev1));
-    for (int e = 0; e < 8; ++e) CUC(cudaEventCreate(&c->slot[s].evs[e]));
+    for (int e = 0; e < N_EVS; ++e) CUC(cudaEventCreate(&c->slot[s].evs[e]));
+    CUC(cudaStreamCreateWithFlags(&c->slot[s].st_in, cudaStreamNonBlocking));
+    if (s == 0) { CUC(cudaStreamCreateWithFlags(&c->slot[s].st_out, cudaStreamNonBlocking)); c->slot[s].owns_out = true; }
+    else c->slot[s].st_out = c->slot[0].st_out;     // ONE download stream: SAM ranges cross PCIe one after another, in submit order
+    for (int e = 0; e < MAX_CHUNKS; ++e) {
+      CUC(cudaEventCreateWithFlags(&c->slot[s].ev_in[e], cudaEventDisableTiming));
+      CUC(cudaEventCreateWithFlags(&c->slot[s].ev_emit[e], cudaEventDisableTiming));
+    }
+    CUC(cudaEventCreateWithFlags(&c->slot[s].ev_out, cudaEventDisableTiming));
   }
   *out = c;
   return 0;
@@ -536,10 +566,14 @@ static void slot_release(Slot &s) {
   s.match_cnt.release(); s.item_slots.release(); s.rec_slots.release(); s.sums.release();
   s.nrec.release(); s.rec_base.release(); s.rec_read.release(); s.rec_bytes.release(); s.rec_off.release(); s.sam_total.release(); s.blk_sums2.release(); s.blk_sums.release(); s.sam.release(); s.flags.release();
   s.csr_off.release(); s.csr_triples.release(); s.long_scratch.release(); s.slot_off.release(); s.aln_scr.release(); s.ord_scr.release(); s.tmp32.release(); s.h_sam.release(); s.h_csr_off.release();
-  s.h_matches.release(); s.h_small.release();
+  s.h_matches.release(); s.h_small.release(); s.h_flag.release();
   if (s.ev0) cudaEventDestroy(s.ev0);
   if (s.ev1) cudaEventDestroy(s.ev1);
-  for (int e = 0; e < 8; ++e) if (s.evs[e]) cudaEventDestroy(s.evs[e]);
+  for (int e = 0; e < N_EVS; ++e) if (s.evs[e]) cudaEventDestroy(s.evs[e]);
+  for (int e = 0; e < MAX_CHUNKS; ++e) { if (s.ev_in[e]) cudaEventDestroy(s.ev_in[e]); if (s.ev_emit[e]) cudaEventDestroy(s.ev_emit[e]); }
+  if (s.ev_out) cudaEventDestroy(s.ev_out);
+  if (s.st_in) cudaStreamDestroy(s.st_in);
+  if (s.st_out && s.owns_out) cudaStreamDestroy(s.st_out);
   if (s.st) cudaStreamDestroy(s.st);
 }
 
@@ -598,7 +632,8 @@ extern "C" int smash_ctx_build_mappability(smash_ctx *c, uint8_t *body, uint64_t
 
 // ------------------------------------------------------------------ batches
 
-static int slot_prepare(smash_ctx *c, Slot &s, const smash_batch *b, bool copy) {
+static int slot_prepare(smash_ctx *c, Slot &s, const smash_batch *b, bool copy, int chunks = 1) {
+  double t_prep = now_ms();
   const uint64_t n = b->n_reads;
   const size_t name_bytes = n ? (size_t)b->name_off[n] : 0, seq_bytes = n ? (size_t)b->seq_off[n] : 0;
   const size_t opt_bytes = (b->opt && n) ? (size_t)b->opt_off[n] : 0;
@@ -615,31 +650,54 @@ static int slot_prepare(smash_ctx *c, Slot &s, const smash_batch *b, bool copy) 
       (rc = s.blk_sums2.ensure(n * s.cap / 2048 + 8)) || (rc = s.flags.ensure(N_FLAGS)) ||
       (rc = s.h_small.ensure(32)))
     return rc;
+  DBG_T("  prepare:ensure", t_prep);
+  // read ranges of the chunked pipeline (even boundaries: mates stay together)
+  s.n_chunks = (chunks > 1 && n >= c->chunk_min_reads) ? (chunks > MAX_CHUNKS ? MAX_CHUNKS : chunks) : 1;
+  {
+    const uint64_t per = ((n + s.n_chunks - 1) / s.n_chunks + 1) & ~1ull;
+    for (int ch = 0; ch <= s.n_chunks; ++ch) { const uint64_t r = per * ch; s.chunk_r[ch] = r < n ? r : n; }
+    s.chunk_r[s.n_chunks] = n;
+  }
   if (copy && n) {
-    CU(cudaMemcpyAsync(s.names.p, b->names, name_bytes, cudaMemcpyHostToDevice, s.st));
-    CU(cudaMemcpyAsync(s.seq.p, b->seq, seq_bytes, cudaMemcpyHostToDevice, s.st));
-    CU(cudaMemcpyAsync(s.qual.p, b->qual, seq_bytes, cudaMemcpyHostToDevice, s.st));
-    CU(cudaMemcpyAsync(s.name_off.p, b->name_off, 8 * (n + 1), cudaMemcpyHostToDevice, s.st));
-    CU(cudaMemcpyAsync(s.seq_off.p, b->seq_off, 8 * (n + 1), cudaMemcpyHostToDevice, s.st));
-    CU(cudaMemcpyAsync(s.read_flag.p, b->read_flag, 2 * n, cudaMemcpyHostToDevice, s.st));
-    if (opt_bytes) {
-      CU(cudaMemcpyAsync(s.opt.p, b->opt, opt_bytes, cudaMemcpyHostToDevice, s.st));
-      CU(cudaMemcpyAsync(s.opt_off.p, b->opt_off, 8 * (n + 1), cudaMemcpyHostToDevice, s.st));
+    cudaStream_t in = s.n_chunks > 1 ? s.st_in : s.st;
+    // read_flag is usually computed on the fly by the caller (2 B/read): if it sits in pageable memory its
+    // copy would block this thread behind every upload queued before it, so it goes through pinned staging
+    const uint16_t *flag_src = b->read_flag;
+    {
+      cudaPointerAttributes at{};
+      if (cudaPointerGetAttributes(&at, b->read_flag) != cudaSuccess || at.type == cudaMemoryTypeUnregistered) {
+        cudaGetLastError();
+        if ((rc = s.h_flag.ensure(n + 1))) return rc;
+        memcpy(s.h_flag.p, b->read_flag, 2 * n);
+        flag_src = s.h_flag.p;
+      }
+    }
+    for (int ch = 0; ch < s.n_chunks; ++ch) {
+      const uint64_t r0 = s.chunk_r[ch], r1 = s.chunk_r[ch + 1];
+      if (r1 > r0) {
+        const size_t n0 = (size_t)b->name_off[r0], n1 = (size_t)b->name_off[r1], q0 = (size_t)b->seq_off[r0], q1 = (size_t)b->seq_off[r1];
+        CU(cudaMemcpyAsync(s.names.p + n0, b->names + n0, n1 - n0, cudaMemcpyHostToDevice, in));
+        CU(cudaMemcpyAsync(s.seq.p + q0, b->seq + q0, q1 - q0, cudaMemcpyHostToDevice, in));
+        CU(cudaMemcpyAsync(s.qual.p + q0, b->qual + q0, q1 - q0, cudaMemcpyHostToDevice, in));
+        CU(cudaMemcpyAsync(s.name_off.p + r0, b->name_off + r0, 8 * (r1 - r0 + 1), cudaMemcpyHostToDevice, in));
+        CU(cudaMemcpyAsync(s.seq_off.p + r0, b->seq_off + r0, 8 * (r1 - r0 + 1), cudaMemcpyHostToDevice, in));
+        CU(cudaMemcpyAsync(s.read_flag.p + r0, flag_src + r0, 2 * (r1 - r0), cudaMemcpyHostToDevice, in));
+        if (opt_bytes) {
+          const size_t o0 = (size_t)b->opt_off[r0], o1 = (size_t)b->opt_off[r1];
+          CU(cudaMemcpyAsync(s.opt.p + o0, b->opt + o0, o1 - o0, cudaMemcpyHostToDevice, in));
+          CU(cudaMemcpyAsync(s.opt_off.p + r0, b->opt_off + r0, 8 * (r1 - r0 + 1), cudaMemcpyHostToDevice, in));
+        }
+      }
+      if (s.n_chunks > 1) CU(cudaEventRecord(s.ev_in[ch], in));
     }
   }
+  DBG_T("  prepare:copies enqueued", t_prep);
+  t_prep = now_ms();
   s.bd.n_reads = n; s.bd.names = s.names.p; s.bd.name_off = s.name_off.p; s.bd.seq = s.seq.p; s.bd.qual = s.qual.p;
   s.bd.seq_off = s.seq_off.p; s.bd.opt = opt_bytes ? s.opt.p : nullptr; s.bd.opt_off = opt_bytes ? s.opt_off.p : nullptr;
   s.bd.read_flag = s.read_flag.p;
   s.n_reads = n; s.first_pair = b->first_pair_ordinal;
-  // reads longer than the shared-memory staging buffer get per-warp scratch in HBM (exact search path)
-  int64_t max_q = 0;
-  for (uint64_t i = 0; i < n; ++i) { const int64_t q = b->seq_off[i + 1] - b->seq_off[i]; if (q > max_q) max_q = q; }
-  s.long_q = 0;
-  if (max_q > MAXQ_FAST) {
-    if (max_q > 60000) return fail(SMASH_ERR_ARG, "read of %lld bases: reads longer than 60000 are not supported", (long long)max_q);
-    s.long_q = (int)max_q;
-    if ((rc = s.long_scratch.ensure((size_t)148 * 8 * 8 * (size_t)(max_q + P_FRONT + P_BACK + 8)))) return rc;
-  }
+  s.long_q = 0;               // reads longer than MAXQ_FAST: the search kernel reports them, run_range re-runs with scratch
   return 0;
 }
 
@@ -649,22 +707,25 @@ static WorkDev work_of(Slot &s) {
   w.aln_scratch = s.aln_scr.p; w.ord_scratch = s.ord_scr.p;
   w.long_scratch = s.long_q ? s.long_scratch.p : nullptr; w.long_q = s.long_q; w.match_slots = s.match_slots.p; w.match_cnt = s.match_cnt.p; w.item_slots = s.item_slots.p;
   w.rec_slots = s.rec_slots.p; w.sums = s.sums.p; w.nrec = s.nrec.p; w.rec_base = s.rec_base.p; w.rec_read = s.rec_read.p; w.rec_bytes = s.rec_bytes.p; w.rec_off = s.rec_off.p; w.sam_total = s.sam_total.p; w.blk_sums2 = s.blk_sums2.p;
-  w.blk_sums = s.blk_sums.p; w.sam = s.sam.p; w.sam_cap = s.sam.cap; w.flags = s.flags.p;
+  w.blk_sums = s.blk_sums.p; w.sam = s.sam.p ? s.sam.p + s.sam_base : nullptr; w.sam_cap = s.sam.cap > s.sam_base ? s.sam.cap - s.sam_base : 0; w.flags = s.flags.p;
   return w;
 }
 
-#define MARK(stage) do { if (s.n_evs < 8) { CU(cudaEventRecord(s.evs[s.n_evs], s.st)); s.ev_stage[s.n_evs++] = (stage); } } while (0)
-// search -> records -> sizes/scan -> (sync for the byte total) -> emit [-> D2H].
-// The only host synchronisation inside is the 8-byte read of the SAM size.
-static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
+#define MARK(stage) do { if (s.n_evs < N_EVS) { CU(cudaEventRecord(s.evs[s.n_evs], s.st)); s.ev_stage[s.n_evs++] = (stage); } } while (0)
+
+// One read range of the slot's batch (s.bd / s.n_reads are the range's view):
+// search -> records -> sizes/scan -> (sync for the byte total) -> emit [-> D2H] [-> tail append].
+// The only host synchronisation inside is the read of the published SAM size.
+static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint64_t n_full) {
   const uint64_t n = s.n_reads;
-  s.sam_bytes = 0; s.n_matches = 0; s.n_records = 0; s.want = want;
-  if (!n) return 0;
+  const bool chunked = s.n_chunks > 1;
+  const int evs_at_entry = s.n_evs;
   for (int attempt = 0;; ++attempt) {
     WorkDev w = work_of(s);
+    s.n_evs = evs_at_entry;
     CU(cudaMemsetAsync(s.flags.p, 0, sizeof(uint32_t) * N_FLAGS, s.st));
-    CU(cudaEventRecord(s.ev0, s.st));
-    s.n_evs = 0;
+    if (ch == 0 && !chunked) CU(cudaEventRecord(s.ev0, s.st));
+    else MARK(-1);                                           // stage timers restart here (after the upload wait)
     int nl;
     if (c->prm.mode == SMASH_MODE_MEM) {
       // K2: count pass -> slot offsets (one spare slot per read) -> exact-size buffers -> write pass
@@ -695,6 +756,15 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
     c->launches += launch_publish(s.h_small.p, (const uint64_t *)s.sam_total.p, (const uint64_t *)(s.rec_base.p + n), s.flags.p, s.st);
     { const double ts = now_ms(); CU(cudaStreamSynchronize(s.st)); DBG_T("  run:sync for sizes", ts); }
     const uint32_t *fl = (const uint32_t *)(s.h_small.p + 1);
+    if (fl[FLAG_LONGQ] > (uint32_t)s.long_q && c->prm.mode != SMASH_MODE_MEM) {
+      // reads longer than the shared-memory staging buffer get per-warp scratch in HBM (exact search path)
+      const uint32_t max_q = fl[FLAG_LONGQ];
+      if (max_q > 60000 || attempt > 3) return fail(SMASH_ERR_ARG, "read of %u bases: reads longer than 60000 are not supported", max_q);
+      int rc;
+      s.long_q = (int)max_q;
+      if ((rc = s.long_scratch.ensure((size_t)148 * 8 * 8 * (size_t)(max_q + P_FRONT + P_BACK + 8)))) return rc;
+      continue;                                              // rerun the range with the long-read kernel
+    }
     if (fl[FLAG_LONGREAD]) return fail(SMASH_ERR_STATE, "%u long reads could not be staged", fl[FLAG_LONGREAD]);
     if (fl[FLAG_OVERFLOW]) {
       const uint32_t need = fl[FLAG_MAXCNT];
@@ -702,30 +772,44 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
         return fail(SMASH_ERR_DATA, "a read produced %u matches; this build keeps at most %d per read", need, STAGE_CAP);
       s.cap = (int)need + 8 > STAGE_CAP ? STAGE_CAP : (int)need + 8;
       int rc;
-      if ((rc = s.match_slots.ensure(n * s.cap)) || (rc = s.item_slots.ensure(n * s.cap)) || (rc = s.rec_slots.ensure(n * s.cap)) ||
-          (rc = s.rec_read.ensure(n * s.cap + 1)) || (rc = s.rec_bytes.ensure(n * s.cap + 1)) || (rc = s.rec_off.ensure(n * s.cap + 2)) ||
-          (rc = s.blk_sums2.ensure(n * s.cap / 2048 + 8))) return rc;
-      continue;                                              // rerun the batch with wider slots
+      if ((rc = s.match_slots.ensure(n_full * s.cap)) || (rc = s.item_slots.ensure(n_full * s.cap)) || (rc = s.rec_slots.ensure(n_full * s.cap)) ||
+          (rc = s.rec_read.ensure(n_full * s.cap + 1)) || (rc = s.rec_bytes.ensure(n_full * s.cap + 1)) || (rc = s.rec_off.ensure(n_full * s.cap + 2)) ||
+          (rc = s.blk_sums2.ensure(n_full * s.cap / 2048 + 8))) return rc;
+      continue;                                              // rerun the range with wider slots
     }
     if (fl[FLAG_MAPERR] && ((want & SMASH_WANT_TAIL) || c->prm.tag_mappability))
       return fail(SMASH_ERR_DATA, "left/right mappability too big for %u records (mappability_tag.cpp:107-113 throws here)", fl[FLAG_MAPERR]);
     break;
   }
-  s.sam_bytes = s.h_small.p[0];
-  s.n_records = s.h_small.p[8];
+  const uint64_t bytes = s.h_small.p[0], recs = s.h_small.p[8];
   if (want & SMASH_WANT_SAM) {
     int rc;
-    if ((rc = s.sam.ensure(s.sam_bytes + 64))) return rc;
+    const uint64_t need = s.sam_base + bytes + 64;
+    // first range of a chunked batch: size both buffers for the whole batch from this range's density
+    const uint64_t guess = (chunked && ch == 0 && n) ? (uint64_t)((double)bytes * ((double)n_full / (double)n) * 1.03) + 4096 : 0;
+    if (need > s.sam.cap) {
+      if (s.sam_base) CU(cudaStreamSynchronize(s.st_out));   // earlier ranges are on the host already; their device copy may go
+      if ((rc = s.sam.ensure(need > guess ? need : guess))) return rc;
+    }
     WorkDev w = work_of(s);
-    c->launches += launch_emit_text(c->dix, s.bd, w, c->sp, s.st, s.n_records);
+    c->launches += launch_emit_text(c->dix, s.bd, w, c->sp, s.st, recs);
     MARK(3);
-    c->launches += launch_emit_copy(s.bd, w, s.st, s.n_records);
+    c->launches += launch_emit_copy(s.bd, w, s.st, recs);
     MARK(6);
     if (to_host) {
-      if ((rc = s.h_sam.ensure(s.sam_bytes + 64))) return rc;
-      if (g_dbg && s.tl[1]) cudaEventRecord(s.tl[1], s.st);
-      CU(cudaMemcpyAsync(s.h_sam.p, s.sam.p, s.sam_bytes, cudaMemcpyDeviceToHost, s.st));
-      if (g_dbg && s.tl[2]) cudaEventRecord(s.tl[2], s.st);
+      if (need > s.h_sam.cap) {
+        if (s.sam_base) CU(cudaStreamSynchronize(s.st_out));
+        if ((rc = s.h_sam.grow_keep(need > guess ? need : guess, s.sam_base))) return rc;
+      }
+      cudaStream_t out = s.st;
+      if (chunked) {
+        CU(cudaEventRecord(s.ev_emit[ch], s.st));
+        CU(cudaStreamWaitEvent(s.st_out, s.ev_emit[ch], 0));
+        out = s.st_out;
+      }
+      if (g_dbg && s.tl[1] && ch == 0) cudaEventRecord(s.tl[1], out);
+      CU(cudaMemcpyAsync(s.h_sam.p + s.sam_base, s.sam.p + s.sam_base, bytes, cudaMemcpyDeviceToHost, out));
+      if (g_dbg && s.tl[2] && ch == s.n_chunks - 1) cudaEventRecord(s.tl[2], out);
     }
   }
   if (want & SMASH_WANT_MATCHES) {
@@ -742,11 +826,42 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
   }
   if (want & SMASH_WANT_TAIL) {
     const double tt = now_ms();
-    int rc = tail_accumulate(&c->tail, c->dix, s.bd, work_of(s), s.n_records, s.st, &c->launches);
+    int rc = tail_accumulate(&c->tail, c->dix, s.bd, work_of(s), recs, s.st, &c->launches);
     DBG_T("  run:tail_accumulate", tt);
     if (rc) return fail(rc, "tail: %s", tail_error());
     MARK(5);
   }
+  s.sam_bytes += bytes; s.n_records += recs;
+  if (want & SMASH_WANT_SAM) s.sam_base += bytes;
+  return 0;
+}
+
+static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
+  s.sam_bytes = 0; s.n_matches = 0; s.n_records = 0; s.want = want; s.sam_base = 0; s.n_evs = 0;
+  if (!s.n_reads) return 0;
+  if (s.n_chunks > 1 && (!to_host || (want & SMASH_WANT_MATCHES) || c->prm.mode == SMASH_MODE_MEM))
+    return fail(SMASH_ERR_STATE, "internal: chunked batch on a path that cannot take one");
+  const BatchDev full = s.bd;
+  const uint64_t n_full = s.n_reads;
+  int rc = 0;
+  if (s.n_chunks > 1) CU(cudaEventRecord(s.ev0, s.st));
+  for (int ch = 0; ch < s.n_chunks && !rc; ++ch) {
+    const uint64_t r0 = s.n_chunks > 1 ? s.chunk_r[ch] : 0, r1 = s.n_chunks > 1 ? s.chunk_r[ch + 1] : n_full;
+    if (r1 <= r0) continue;
+    s.bd = full; s.bd.n_reads = r1 - r0;
+    s.bd.name_off = full.name_off + r0; s.bd.seq_off = full.seq_off + r0; s.bd.read_flag = full.read_flag + r0;
+    if (full.opt_off) s.bd.opt_off = full.opt_off + r0;
+    s.n_reads = r1 - r0;
+    if (s.n_chunks > 1) { cudaError_t e = cudaStreamWaitEvent(s.st, s.ev_in[ch], 0); if (e != cudaSuccess) { rc = fail(SMASH_ERR_CUDA, "%s", cudaGetErrorString(e)); break; } }
+    rc = run_range(c, s, want, to_host, ch, n_full);
+  }
+  s.bd = full; s.n_reads = n_full;
+  if (rc) return rc;
+  if (s.n_chunks > 1) {
+    CU(cudaEventRecord(s.ev_out, s.st_out));
+    CU(cudaStreamWaitEvent(s.st, s.ev_out, 0));
+  }
+  s.sam_base = 0;
   CU(cudaEventRecord(s.ev1, s.st));
   return 0;
 }
@@ -756,7 +871,7 @@ static int slot_finish(smash_ctx *c, Slot &s, smash_result *res) {
   CU(cudaGetLastError());
   if (s.n_reads) {
     cudaEvent_t prev = s.ev0;
-    for (int e = 0; e < s.n_evs; ++e) { float ms = 0; if (cudaEventElapsedTime(&ms, prev, s.evs[e]) == cudaSuccess) c->stage_ms[s.ev_stage[e]] += ms; prev = s.evs[e]; }
+    for (int e = 0; e < s.n_evs; ++e) { float ms = 0; if (s.ev_stage[e] >= 0 && cudaEventElapsedTime(&ms, prev, s.evs[e]) == cudaSuccess) c->stage_ms[s.ev_stage[e]] += ms; prev = s.evs[e]; }
     s.n_evs = 0;
     if (g_dbg && s.tl[0] && g_tl_base && (s.want & SMASH_WANT_SAM)) {
       float a = 0, b0 = 0, d0 = 0, d1 = 0, e1 = 0;
@@ -790,7 +905,8 @@ extern "C" int smash_submit(smash_ctx *c, int slot, const smash_batch *b, int wa
     for (int e = 0; e < 3; ++e) if (!s.tl[e]) cudaEventCreate(&s.tl[e]);
     cudaEventRecord(s.tl[0], s.st);
   }
-  int rc = slot_prepare(c, s, b, true);
+  const int chunks = (c->prm.mode != SMASH_MODE_MEM && !(want & SMASH_WANT_MATCHES) && (want & SMASH_WANT_SAM) && !g_no_chunks) ? c->max_chunks : 1;
+  int rc = slot_prepare(c, s, b, true, chunks);
   DBG_T("submit:prepare+h2d enqueue", t0);
   if (rc) return rc;
   t0 = now_ms();
@@ -956,6 +1072,11 @@ extern "C" int smash_ctx_drop_isa(smash_ctx *c) {
 extern "C" int smash_memcpy(void *dst, const void *src, size_t bytes) {
   if (!bytes) return 0;
   CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));       // UVA: any of host/device on either side
+  return 0;
+}
+extern "C" int smash_ctx_set_chunking(smash_ctx *c, int max_chunks, uint64_t min_reads) {
+  if (!c || max_chunks < 1 || max_chunks > MAX_CHUNKS) return fail(SMASH_ERR_ARG, "max_chunks must be 1..%d", MAX_CHUNKS);
+  c->max_chunks = max_chunks; c->chunk_min_reads = min_reads < 2 ? 2 : min_reads;
   return 0;
 }
 extern "C" uint64_t smash_ctx_launch_count(const smash_ctx *c) { return c ? c->launches : 0; }

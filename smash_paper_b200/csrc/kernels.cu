@@ -228,7 +228,10 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     const int64_t so = b.seq_off[read];
     const int q = (int)(b.seq_off[read + 1] - so);
     if (lane == 0) sm.nstage[warp] = 0;
-    if (q > MAXQ_FAST) continue;                   // k_mam_search_long takes these
+    if (q > MAXQ_FAST) {                           // k_mam_search_long takes these (the host learns the length from the flag)
+      if (lane == 0) { atomicMax(&w.flags[FLAG_LONGQ], (uint32_t)q); if (q > w.long_q) w.match_cnt[read] = 0; }
+      continue;
+    }
     {
 #if SMASH_LUT
     const bool odd = stage_read_masked(sm, warp, b.seq + so, q, lane);

@@ -14,7 +14,7 @@ struct BatchDev {
   const uint16_t *read_flag;
 };
 
-enum { FLAG_OVERFLOW = 0, FLAG_MAPERR = 1, FLAG_LONGREAD = 2, FLAG_MAXCNT = 3, N_FLAGS = 8 };
+enum { FLAG_OVERFLOW = 0, FLAG_MAPERR = 1, FLAG_LONGREAD = 2, FLAG_MAXCNT = 3, FLAG_LONGQ = 4, N_FLAGS = 8 };
 
 struct WorkDev {
   int cap;                     // slots per read (matches / items / records) when slot_off is null

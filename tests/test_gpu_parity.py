@@ -102,6 +102,37 @@ def test_tagged_sam_and_tail(case):
         ctx.close(); ix.close()
 
 
+@pytest.mark.parametrize("chunks,min_reads", [(4, 2), (3, 2), (2, 100), (4, 10**9)])
+def test_chunked_submit_is_byte_identical(case, chunks, min_reads):
+    """smash_ctx_set_chunking: a batch cut into read ranges (upload / kernel / download streams)
+    gives the same tagged SAM bytes, the same positions and the same bin counts as the whole batch."""
+    from smash_paper_b200 import api
+    ix = api.Index.open(case["fa"])
+    ctx = api.Context(ix, min_len=20, nomap=True, tag_mappability=True)
+    try:
+        ctx.load_mappability_file(case["fa"] + ".bin/map.bin")
+        sam = case["oix"].map_batch(case["reads"], min_len=20, n_threads=4)
+        exp = oracle_tail(case["oix"], case["body"], sam, case["dir"], case["fa"])
+        ci = exp["chrominfo"]
+        ctx.tail_configure([int(b[2]) for b in exp["bins"]], list(ci.keys()), [int(v[2]) for v in ci.values()])
+        ctx.set_chunking(chunks, min_reads)
+        for rep in range(2):                                   # second pass: buffers already sized
+            ctx.tail_reset()
+            ctx.submit(0, case["reads"], want=api.WANT_SAM | api.WANT_TAIL)
+            res = ctx.wait(0)
+            assert res.sam == b"".join(exp["tagged"])
+            counts, st = ctx.tail_finish()
+            chrom, pos = ctx.tail_positions()
+            names = case["oix"].descr[::2]
+            assert [f"{names[c]} {p}" for c, p in zip(chrom, pos)] == exp["positions"]
+            assert np.array_equal(counts, exp["counts"])
+            assert (st["total_reads"], st["dups_removed"], st["reads_kept"]) == (exp["total"], exp["dups"], exp["kept"])
+        with pytest.raises(api.SmashError):
+            ctx.set_chunking(9, 2)
+    finally:
+        ctx.close(); ix.close()
+
+
 def test_double_buffered_submit(case, gpu):
     api, ix, ctx = gpu
     sam = case["oix"].map_batch(case["reads"], min_len=20, n_threads=4)
