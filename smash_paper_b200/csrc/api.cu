@@ -26,6 +26,8 @@ static thread_local char g_err[1024] = "";
 #include <chrono>
 static const bool g_dbg = getenv("SMASH_DEBUG_TIMING") != nullptr;
 static cudaEvent_t g_tl_base = nullptr;
+static const bool g_force_split = getenv("SMASH_FORCE_SPLIT_SEARCH") != nullptr;
+static const bool g_no_split = getenv("SMASH_NO_SPLIT_SEARCH") != nullptr;   // A/B switch: verification inside k_mam_search
 static const bool g_no_chunks = getenv("SMASH_NO_CHUNKS") != nullptr;   // A/B switch for the chunked submit pipeline
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 #define DBG_T(label, t0) do { if (g_dbg) fprintf(stderr, "[smash-dbg] %-28s %8.3f ms\n", label, now_ms() - (t0)); } while (0)
@@ -242,6 +244,8 @@ struct Slot {
   DBuf<uint64_t> slot_off; DBuf<Aln> aln_scr; DBuf<uint16_t> ord_scr; DBuf<uint32_t> tmp32;   // MEM mode (CSR slots)
   uint64_t slots_total = 0; bool csr = false;
   DBuf<uint8_t> long_scratch; int long_q = 0;
+  bool split = false;
+  DBuf<uint64_t> surv; DBuf<uint8_t> surv_cnt; DBuf<uint8_t> lc;      // split search (k_mam_search -> k_mam_verify)
   HBuf<uint16_t> h_flag;       // pinned staging for a pageable read_flag array
   // results on host
   HBuf<char> h_sam; HBuf<int64_t> h_csr_off; HBuf<smash_match> h_matches; HBuf<uint64_t> h_small;
@@ -566,7 +570,7 @@ static void slot_release(Slot &s) {
   s.match_cnt.release(); s.item_slots.release(); s.rec_slots.release(); s.sums.release();
   s.nrec.release(); s.rec_base.release(); s.rec_read.release(); s.rec_bytes.release(); s.rec_off.release(); s.sam_total.release(); s.blk_sums2.release(); s.blk_sums.release(); s.sam.release(); s.flags.release();
   s.csr_off.release(); s.csr_triples.release(); s.long_scratch.release(); s.slot_off.release(); s.aln_scr.release(); s.ord_scr.release(); s.tmp32.release(); s.h_sam.release(); s.h_csr_off.release();
-  s.h_matches.release(); s.h_small.release(); s.h_flag.release();
+  s.h_matches.release(); s.h_small.release(); s.h_flag.release(); s.surv.release(); s.surv_cnt.release(); s.lc.release();
   if (s.ev0) cudaEventDestroy(s.ev0);
   if (s.ev1) cudaEventDestroy(s.ev1);
   for (int e = 0; e < N_EVS; ++e) if (s.evs[e]) cudaEventDestroy(s.evs[e]);
@@ -643,6 +647,11 @@ static int slot_prepare(smash_ctx *c, Slot &s, const smash_batch *b, bool copy, 
     return rc;
   if (opt_bytes && ((rc = s.opt.ensure(opt_bytes + 16)) || (rc = s.opt_off.ensure(n + 1)))) return rc;
   if (s.cap == 0) s.cap = 24;
+  // split search (k_mam_search parks candidates, k_mam_verify extends them): pays off on large references,
+  // where the 4+4 filter exists and every read has a few dozen seed hits; small references verify in place
+  s.split = c->prm.mode != SMASH_MODE_MEM && !g_no_split && (c->dix.ext != nullptr || g_force_split);
+  if (s.split && ((rc = s.surv.ensure(n * SURV_CAP + 1)) || (rc = s.surv_cnt.ensure(n + 1)) || (rc = s.lc.ensure(seq_bytes + 32 * n + 64))))
+    return rc;
   if ((rc = s.match_slots.ensure(n * s.cap)) || (rc = s.match_cnt.ensure(n + 1)) || (rc = s.item_slots.ensure(n * s.cap)) ||
       (rc = s.rec_slots.ensure(n * s.cap)) || (rc = s.sums.ensure(n + 2)) || (rc = s.nrec.ensure(n + 1)) ||
       (rc = s.rec_base.ensure(n + 2)) || (rc = s.rec_read.ensure(n * s.cap + 1)) || (rc = s.rec_bytes.ensure(n * s.cap + 1)) ||
@@ -705,6 +714,7 @@ static WorkDev work_of(Slot &s) {
   WorkDev w{};
   w.cap = s.cap; w.slot_off = s.csr ? s.slot_off.p : nullptr; w.slots_total = s.csr ? s.slots_total : s.n_reads * (uint64_t)s.cap;
   w.aln_scratch = s.aln_scr.p; w.ord_scratch = s.ord_scr.p;
+  if (!s.csr && s.surv.p && s.split) { w.surv = s.surv.p; w.surv_cnt = s.surv_cnt.p; w.lc = s.lc.p; }
   w.long_scratch = s.long_q ? s.long_scratch.p : nullptr; w.long_q = s.long_q; w.match_slots = s.match_slots.p; w.match_cnt = s.match_cnt.p; w.item_slots = s.item_slots.p;
   w.rec_slots = s.rec_slots.p; w.sums = s.sums.p; w.nrec = s.nrec.p; w.rec_base = s.rec_base.p; w.rec_read = s.rec_read.p; w.rec_bytes = s.rec_bytes.p; w.rec_off = s.rec_off.p; w.sam_total = s.sam_total.p; w.blk_sums2 = s.blk_sums2.p;
   w.blk_sums = s.blk_sums.p; w.sam = s.sam.p ? s.sam.p + s.sam_base : nullptr; w.sam_cap = s.sam.cap > s.sam_base ? s.sam.cap - s.sam_base : 0; w.flags = s.flags.p;

@@ -14,7 +14,7 @@ namespace smash {
 
 constexpr int WARPS = 8;
 constexpr int THREADS = WARPS * 32;
-constexpr int PBUF = P_FRONT + MAXQ_FAST + P_BACK;
+constexpr int PBUF = P_FRONT + MAXQ_FAST + P_BACK + 8;     // + word rounding of the word-wise staging
 constexpr int SCR_CAP = 64;       // alignments per read the shared-memory scratch holds
 constexpr int LANE_CAP = 4;
 constexpr int LINE_BUF = 1024;
@@ -152,7 +152,7 @@ constexpr int TASK_CAP = 128;
 struct SearchSmem {
   uint16_t lut[256];                           // byte -> lower-cased byte | 0x100 (not acgt) | 0x200 (not acgt but occurs in the text)
   uint8_t pbuf[WARPS][PBUF];
-  uint32_t inv[WARPS][MAXQ_FAST / 32 + 2];     // non-acgt mask of the read, one bit per base
+  uint32_t inv[WARPS][MAXQ_FAST / 32 + 12];    // non-acgt mask, one bit per byte of the staging buffer (bit 0 = pbuf[P_FRONT])
   Match stage[WARPS][STAGE_CAP];
   uint64_t task_sa[WARPS][TASK_CAP];           // SA index of the candidate
   uint16_t task_x[WARPS][TASK_CAP];            // its anchor position
@@ -170,18 +170,34 @@ __device__ __noinline__ void exact_all(const DevIndex &ix, SearchSmem &sm, int w
     if (exact_start(ix, P, q, p, sp.L, &m)) stage_push(sm, warp, m);
   }
 }
-// lanes = tasks: extend every queued candidate
+// lanes = tasks: 4+4 pre-filter on every queued candidate; the survivors are parked for k_mam_verify
+// (w.surv) or, when the read's parking row is full / absent, extended right here
 __device__ __forceinline__ void run_tasks(const DevIndex &ix, SearchSmem &sm, int warp, int lane, const uint8_t *P, int q,
-                                          const SearchParams &sp, int ntask) {
-  for (int t = lane; t < ntask; t += 32) {
-    const uint64_t i = sm.task_sa[warp][t];
-    const int x = (int)sm.task_x[warp][t];
-    if (ix.ext && !ext_may_reach(ix.ext[i], read_ext_codes(P, x, sp.k), sp.k, sp.L)) continue;   // 2-byte pre-filter
-    const uint64_t c = sa_at(ix, i);
-    Match m; int pl = 0;
-    const int r = candidate_check(ix, P, q, x, sp.s, sp.k, sp.L, c, &m, &pl);
-    if (r > 0) stage_push(sm, warp, m);
-    else if (r < 0 && exact_start(ix, P, q, pl, sp.L, &m)) stage_push(sm, warp, m);
+                                          const SearchParams &sp, int ntask, const WorkDev &w, uint64_t read, int &nsurv) {
+  for (int t0 = 0; t0 < ntask; t0 += 32) {
+    const int t = t0 + lane;
+    uint64_t i = 0; int x = 0;
+    bool pass = false;
+    if (t < ntask) {
+      i = sm.task_sa[warp][t]; x = (int)sm.task_x[warp][t];
+      pass = !ix.ext || ext_may_reach(ix.ext[i], read_ext_codes(P, x, sp.k), sp.k, sp.L);   // 2-byte pre-filter
+    }
+    if (w.surv) {
+      const unsigned mask = __ballot_sync(0xffffffffu, pass);
+      const int np = __popc(mask);
+      if (nsurv + np <= SURV_CAP) {
+        if (pass) w.surv[read * SURV_CAP + nsurv + __popc(mask & ((1u << lane) - 1u))] = ((uint64_t)x << 48) | i;
+        nsurv += np;
+        continue;
+      }
+    }
+    if (pass) {
+      const uint64_t c = sa_at(ix, i);
+      Match m; int pl = 0;
+      const int r = candidate_check(ix, P, q, x, sp.s, sp.k, sp.L, c, &m, &pl);
+      if (r > 0) stage_push(sm, warp, m);
+      else if (r < 0 && exact_start(ix, P, q, pl, sp.L, &m)) stage_push(sm, warp, m);
+    }
   }
   __syncwarp();
 }
@@ -189,7 +205,8 @@ __device__ __forceinline__ void run_tasks(const DevIndex &ix, SearchSmem &sm, in
 // Warp-cooperative staging for the search: lower-case the read into shared memory through the
 // per-CTA lookup table, build the non-acgt bit mask (one ballot per 32 bases) in the same pass, and
 // report whether a non-acgt byte that also occurs in the text was seen (=> exact path).
-__device__ __forceinline__ bool stage_read_masked(SearchSmem &sm, int warp, const uint8_t *__restrict__ seq, int q, int lane) {
+__device__ __forceinline__ bool stage_read_masked(SearchSmem &sm, int warp, const uint8_t *__restrict__ seq, int q, int lane,
+                                                  uint8_t *__restrict__ lc) {
   uint8_t *pbuf = sm.pbuf[warp];
   uint8_t *P = pbuf + P_FRONT;
   bool odd = false;
@@ -197,21 +214,83 @@ __device__ __forceinline__ bool stage_read_masked(SearchSmem &sm, int warp, cons
   for (int it = 0; it < rounds; ++it) {
     const int j = it * 32 + lane;
     uint16_t e = 0;
-    if (j < q) { e = sm.lut[seq[j]]; P[j] = (uint8_t)e; odd |= (e & 0x200) != 0; }
+    if (j < q) { e = sm.lut[seq[j]]; P[j] = (uint8_t)e; odd |= (e & 0x200) != 0; if (lc) lc[j] = (uint8_t)e; }
     const unsigned bad = __ballot_sync(0xffffffffu, (e & 0x100) != 0);
     if (lane == 0) sm.inv[warp][it] = bad;
   }
-  if (lane < P_FRONT) pbuf[lane] = 0xFE;
-  if (lane < P_BACK) P[q + lane] = 0xFF;
+  if (lane < P_FRONT) { pbuf[lane] = 0xFE; if (lc) lc[lane - P_FRONT] = 0xFE; }
+  if (lane < P_BACK) { P[q + lane] = 0xFF; if (lc) lc[q + lane] = 0xFF; }
   __syncwarp();
   return __any_sync(0xffffffffu, odd);
+}
+
+
+// Word-wise staging (K1a): the read is fetched as aligned 32-bit words, ALL of a 256-byte pass in
+// flight before the first one is used (one global latency per pass instead of one per 32 bytes),
+// lower-cased through the per-CTA table four bytes at a time and stored as words.  The staged read
+// starts at pbuf + P_FRONT + mis (mis = global misalignment of the read), so word boundaries of the
+// global blob, the shared buffer and the lower-cased HBM copy (lc) coincide.  The non-acgt mask is
+// kept in BUFFER coordinates (bit j + mis for base j).  Pads: 0xFE before, 0xFF after (core.cuh).
+__device__ __forceinline__ uint32_t lut4(const uint16_t *lut, uint32_t v, int j0, int q, unsigned &nib, unsigned &oddbits) {
+  const uint32_t e0 = lut[v & 0xffu], e1 = lut[(v >> 8) & 0xffu], e2 = lut[(v >> 16) & 0xffu], e3 = lut[v >> 24];
+  if (j0 >= 0 && j0 + 3 < q) {                    // whole word inside the read
+    nib = ((e0 >> 8) & 1u) | ((e1 >> 7) & 2u) | ((e2 >> 6) & 4u) | ((e3 >> 5) & 8u);
+    oddbits |= (e0 | e1 | e2 | e3) & 0x200u;
+    return (e0 & 0xffu) | ((e1 & 0xffu) << 8) | ((e2 & 0xffu) << 16) | (e3 << 24);
+  }
+  uint32_t out = 0; nib = 0;
+  const uint32_t e[4] = {e0, e1, e2, e3};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int j = j0 + t;
+    uint32_t byte;
+    if (j < 0) byte = 0xFEu;
+    else if (j >= q) byte = 0xFFu;
+    else { byte = e[t] & 0xffu; nib |= ((e[t] >> 8) & 1u) << t; oddbits |= e[t] & 0x200u; }
+    out |= byte << (8 * t);
+  }
+  return out;
+}
+__device__ __forceinline__ bool stage_read_words(SearchSmem &sm, int warp, const uint8_t *__restrict__ seq_blob, int64_t so, int q,
+                                                 int lane, uint8_t *__restrict__ lc) {
+  const int mis = (int)(so & 3);
+  uint8_t *pbuf = sm.pbuf[warp];
+  uint32_t *pw = reinterpret_cast<uint32_t *>(pbuf + P_FRONT);                 // word 0 holds bases -mis .. 3-mis
+  const uint32_t *gw = reinterpret_cast<const uint32_t *>(seq_blob + (so - mis));
+  uint32_t *lw = lc ? reinterpret_cast<uint32_t *>(lc - mis) : nullptr;
+  const int nwords = (mis + q + 3) >> 2;
+  unsigned oddbits = 0;
+  int w0 = 0;
+  for (; w0 < nwords; w0 += 64) {
+    const int i0 = w0 + lane, i1 = w0 + 32 + lane;
+    const uint32_t v0 = i0 < nwords ? __ldg(gw + i0) : 0u;
+    const uint32_t v1 = i1 < nwords ? __ldg(gw + i1) : 0u;
+    unsigned n0 = 0, n1 = 0;
+    if (i0 < nwords) { const uint32_t o = lut4(sm.lut, v0, 4 * i0 - mis, q, n0, oddbits); pw[i0] = o; if (lw) lw[i0] = o; }
+    if (i1 < nwords) { const uint32_t o = lut4(sm.lut, v1, 4 * i1 - mis, q, n1, oddbits); pw[i1] = o; if (lw) lw[i1] = o; }
+    // 8 lanes x 4 flag bits -> one mask word per 32 buffer bytes
+    unsigned m0 = n0 << (4 * (lane & 7)), m1 = n1 << (4 * (lane & 7));
+    m0 |= __shfl_xor_sync(0xffffffffu, m0, 1); m1 |= __shfl_xor_sync(0xffffffffu, m1, 1);
+    m0 |= __shfl_xor_sync(0xffffffffu, m0, 2); m1 |= __shfl_xor_sync(0xffffffffu, m1, 2);
+    m0 |= __shfl_xor_sync(0xffffffffu, m0, 4); m1 |= __shfl_xor_sync(0xffffffffu, m1, 4);
+    if ((lane & 7) == 0) { sm.inv[warp][i0 >> 3] = m0; sm.inv[warp][i1 >> 3] = m1; }
+  }
+  if (lane == 0) { sm.inv[warp][w0 >> 3] = 0; sm.inv[warp][(w0 >> 3) + 1] = 0; }   // spare words (kmer_invalid reads word+1)
+  // pads outside the staged words
+  if (lane < P_FRONT) { pbuf[lane] = 0xFE; if (lc && lane - P_FRONT < -mis) lc[lane - P_FRONT] = 0xFE; }
+  {
+    const int j = 4 * nwords - mis + lane;         // first byte after the last staged word, in read coordinates
+    if (j < q + P_BACK) { pbuf[P_FRONT + mis + j] = 0xFF; if (lc) lc[j] = 0xFF; }
+  }
+  __syncwarp();
+  return __any_sync(0xffffffffu, oddbits != 0);
 }
 
 #ifndef SMASH_MINBLK
 #define SMASH_MINBLK 4
 #endif
 #ifndef SMASH_LUT
-#define SMASH_LUT 1
+#define SMASH_LUT 2
 #endif
 __global__ void __launch_bounds__(THREADS, SMASH_MINBLK)
 k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
@@ -229,14 +308,21 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     const int q = (int)(b.seq_off[read + 1] - so);
     if (lane == 0) sm.nstage[warp] = 0;
     if (q > MAXQ_FAST) {                           // k_mam_search_long takes these (the host learns the length from the flag)
-      if (lane == 0) { atomicMax(&w.flags[FLAG_LONGQ], (uint32_t)q); if (q > w.long_q) w.match_cnt[read] = 0; }
+      if (lane == 0) { atomicMax(&w.flags[FLAG_LONGQ], (uint32_t)q); if (q > w.long_q) w.match_cnt[read] = 0; if (w.surv) w.surv_cnt[read] = 0; }
       continue;
     }
+    int nsurv = 0;
     {
-#if SMASH_LUT
-    const bool odd = stage_read_masked(sm, warp, b.seq + so, q, lane);
+#if SMASH_LUT == 2
+    const bool odd = stage_read_words(sm, warp, b.seq, so, q, lane, w.surv ? w.lc + so + 32 * read + 16 : nullptr);
+    const int mis = (int)(so & 3);
+    const uint8_t *P = sm.pbuf[warp] + P_FRONT + mis;
+#elif SMASH_LUT
+    const bool odd = stage_read_masked(sm, warp, b.seq + so, q, lane, w.surv ? w.lc + so + 32 * read + 16 : nullptr);
+    const int mis = 0;
     const uint8_t *P = sm.pbuf[warp] + P_FRONT;
 #else
+    const int mis = 0;
     const bool odd = stage_read(ix, b.seq + so, q, sp.nucleotides_only, sm.pbuf[warp], lane);
     const uint8_t *P = sm.pbuf[warp] + P_FRONT;
     for (int c0 = 0; c0 <= q / 32 + 1; ++c0) {
@@ -257,7 +343,7 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
           const int a = a0 + lane;
           uint64_t lo = 0, hi = 0;
           bool big = false;
-          if (a < n_anchor && !kmer_invalid(sm.inv[warp], a * s, k)) {
+          if (a < n_anchor && !kmer_invalid(sm.inv[warp], a * s + mis, k)) {
             anchor_bucket(ix, P, a * s, k, &lo, &hi);
             if (hi - lo > (uint64_t)BIG_BUCKET) { big = true; hi = lo; }
           }
@@ -276,14 +362,14 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
           int inc = cnt;
           for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
           const int total = __shfl_sync(0xffffffffu, inc, 31);
-          if (ntask + total > TASK_CAP) { run_tasks(ix, sm, warp, lane, P, q, sp, ntask); ntask = 0; }
+          if (ntask + total > TASK_CAP) { run_tasks(ix, sm, warp, lane, P, q, sp, ntask, w, read, nsurv); ntask = 0; }
           if (total > TASK_CAP) {                            // cannot happen: 32 * BIG_BUCKET > TASK_CAP only if many full buckets
             for (int l2 = 0; l2 < 32; ++l2) {                // degrade gracefully: one lane's bucket at a time
               const int c2 = __shfl_sync(0xffffffffu, cnt, l2);
               const uint64_t lo2 = __shfl_sync(0xffffffffu, lo, l2);
               for (int i = lane; i < c2; i += 32) { sm.task_sa[warp][i] = lo2 + (uint64_t)i; sm.task_x[warp][i] = (uint16_t)((a0 + l2) * s); }
               __syncwarp();
-              run_tasks(ix, sm, warp, lane, P, q, sp, c2);
+              run_tasks(ix, sm, warp, lane, P, q, sp, c2, w, read, nsurv);
             }
           } else {
             const int base = ntask + inc - cnt;
@@ -292,7 +378,7 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
             __syncwarp();
           }
         }
-        run_tasks(ix, sm, warp, lane, P, q, sp, ntask);
+        run_tasks(ix, sm, warp, lane, P, q, sp, ntask, w, read, nsurv);
       } else {
         exact_all(ix, sm, warp, lane, P, q, sp);
       }
@@ -310,7 +396,7 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
       if (rank < w.cap) dst[rank] = me;
     }
     int n_out = n;
-    if (sp.mum && n <= w.cap && n <= STAGE_CAP) {
+    if (sp.mum && n <= w.cap && n <= STAGE_CAP && nsurv == 0) {        // (with parked candidates k_mam_verify runs the sweep)
       // -mum: the sweep needs the matches in emission (query) order -> copy the ordered slots back into the
       // stage, let lane 0 run the by_ref sort + cleanMUMcand sweep, survivors go to the slots in by_ref order
       __syncwarp();
@@ -324,8 +410,114 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     }
     if (lane == 0) {
       w.match_cnt[read] = (uint32_t)n_out;
-      if (n > w.cap || n > STAGE_CAP) atomicAdd(&w.flags[FLAG_OVERFLOW], 1u);
-      atomicMax(&w.flags[FLAG_MAXCNT], (uint32_t)n);
+      if (w.surv) w.surv_cnt[read] = (uint8_t)nsurv;
+      if (n > w.cap || n > STAGE_CAP) { atomicAdd(&w.flags[FLAG_OVERFLOW], 1u); atomicMax(&w.flags[FLAG_MAXCNT], (uint32_t)n); }
+    }
+    __syncwarp();
+  }
+}
+
+// K1b: verification of the parked candidates.  One warp per read, lanes = its candidates: the SA
+// entries of all of them are fetched at once, then the text words left of the seed (ownership), then
+// the right extensions and the U bytes of the few that own their diagonal.  The matches join the ones
+// k_mam_search found on its exact paths, get rank-sorted by query offset and written in order.
+struct VerifySmem {
+  Match stage[WARPS][STAGE_CAP];
+  uint64_t own_c[WARPS][SURV_CAP];             // candidates that own their diagonal: suffix position,
+  uint32_t own_xl[WARPS][SURV_CAP];            // anchor offset << 16 | left extension
+};
+#ifndef SMASH_VERIFY_MINBLK
+#define SMASH_VERIFY_MINBLK 5
+#endif
+__global__ void __launch_bounds__(THREADS, SMASH_VERIFY_MINBLK)
+k_mam_verify(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
+  __shared__ __align__(16) VerifySmem sm;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
+  const uint8_t *T = ix.text;
+  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
+    const int nsv = (int)w.surv_cnt[read];
+    if (nsv == 0) continue;                                  // k_mam_search finished this read
+    const int64_t so = b.seq_off[read];
+    const int q = (int)(b.seq_off[read + 1] - so);
+    const uint8_t *P = w.lc + so + 32 * read + 16;
+    // (A) lanes = parked candidates: SA entry, ownership (left extension shorter than the stride)
+    bool own = false; uint64_t c = 0; int x = 0, left = 0;
+    if (lane < nsv) {
+      const uint64_t e = w.surv[read * SURV_CAP + lane];
+      x = (int)(e >> 48);
+      c = sa_at(ix, e & 0xffffffffffffull);
+      left = match_left(T, (int64_t)c, P, x, sp.s);
+      own = left < sp.s;
+    }
+    const unsigned om = __ballot_sync(0xffffffffu, own);
+    const int n_own = __popc(om);
+    if (own) { const int pos = __popc(om & ((1u << lane) - 1u)); sm.own_c[warp][pos] = c; sm.own_xl[warp][pos] = ((uint32_t)x << 16) | (uint32_t)left; }
+    const int n_e_true = (int)w.match_cnt[read];             // found by k_mam_search's exact paths (already in the slots)
+    int n_e = n_e_true < w.cap ? n_e_true : w.cap;
+    if (n_e > STAGE_CAP) n_e = STAGE_CAP;
+    Match *dst = w.match_slots + slot_base(w, read);
+    for (int e = lane; e < n_e; e += 32) sm.stage[warp][e] = dst[e];
+    __syncwarp();
+    // (B) 4 lanes per owning candidate, 8 candidates per pass: lane t of a group compares the words
+    // t, t+4, t+8, .. of the diagonal to the right of the anchor; the group's first mismatch wins
+    int n_new = 0;
+    const int g = lane >> 2, t = lane & 3;
+    for (int base = 0; base < n_own; base += 8) {
+      const bool have = base + g < n_own;
+      uint64_t cc = 0; int cx = 0, cl = 0;
+      if (have) { cc = sm.own_c[warp][base + g]; const uint32_t xl = sm.own_xl[warp][base + g]; cx = (int)(xl >> 16); cl = (int)(xl & 0xffffu); }
+      const int limit = q - cx;
+      int right = limit;                                      // stays `limit` when the read ends first
+      bool open = have;
+      for (int off = 8 * t; __any_sync(0xffffffffu, open); off += 32) {
+        int mm = 0x7fffffff;
+        if (open && off < limit) {
+          const uint64_t d = text8(T, (int64_t)cc + off) ^ read8(P, cx + off);
+          if (d) mm = off + (ctz64(d) >> 3);
+        }
+        const int o1 = __shfl_xor_sync(0xffffffffu, mm, 1); mm = o1 < mm ? o1 : mm;
+        const int o2 = __shfl_xor_sync(0xffffffffu, mm, 2); mm = o2 < mm ? o2 : mm;
+        if (open) {
+          if (mm != 0x7fffffff) { right = mm < limit ? mm : limit; open = false; }
+          else if (off - 8 * t + 32 >= limit) open = false;   // the whole group ran past the end of the read
+        }
+      }
+      // group leaders finish the candidate (candidate_check, core.cuh)
+      Match m; int r = 0;
+      if (have && t == 0 && right >= sp.k) {
+        const uint32_t len = (uint32_t)(cl + right);
+        if (len >= sp.L && len >= 2) {
+          const uint64_t ref = cc - (uint64_t)cl;
+          const uint8_t u = ix.uniq[ref];
+          if (u == 255 && len >= 255) r = exact_start(ix, P, q, cx - cl, sp.L, &m) ? 1 : 0;
+          else if (len >= u) { m.ref = ref; m.qpos = (uint32_t)(cx - cl); m.len = len; r = 1; }
+        }
+      }
+      const unsigned pass = __ballot_sync(0xffffffffu, r > 0);
+      if (r > 0) { const int pos = n_e + n_new + __popc(pass & ((1u << lane) - 1u)); if (pos < STAGE_CAP) sm.stage[warp][pos] = m; }
+      n_new += __popc(pass);
+    }
+    __syncwarp();
+    const int n = n_e_true + n_new;
+    const int ns = n_e + n_new < STAGE_CAP ? n_e + n_new : STAGE_CAP;
+    for (int e = lane; e < ns; e += 32) {
+      const Match me = sm.stage[warp][e];
+      int rank = 0;
+      for (int f = 0; f < ns; ++f) rank += sm.stage[warp][f].qpos < me.qpos;
+      if (rank < w.cap) dst[rank] = me;
+    }
+    int n_out = n;
+    if (sp.mum && n <= w.cap && n <= STAGE_CAP) {
+      __syncwarp();
+      for (int e = lane; e < ns; e += 32) sm.stage[warp][e] = dst[e];
+      __syncwarp();
+      if (lane == 0) { uint16_t ord[STAGE_CAP]; n_out = mum_clean(sm.stage[warp], ns, ord, dst); }
+      n_out = __shfl_sync(0xffffffffu, n_out, 0);
+    }
+    if (lane == 0) {
+      w.match_cnt[read] = (uint32_t)n_out;
+      if (n > w.cap || n > STAGE_CAP) { atomicAdd(&w.flags[FLAG_OVERFLOW], 1u); atomicMax(&w.flags[FLAG_MAXCNT], (uint32_t)n); }
     }
     __syncwarp();
   }
@@ -380,8 +572,7 @@ k_mam_search_long(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     }
     if (lane == 0) {
       w.match_cnt[read] = (uint32_t)n_out;
-      if (n > w.cap || n > STAGE_CAP) atomicAdd(&w.flags[FLAG_OVERFLOW], 1u);
-      atomicMax(&w.flags[FLAG_MAXCNT], (uint32_t)n);
+      if (n > w.cap || n > STAGE_CAP) { atomicAdd(&w.flags[FLAG_OVERFLOW], 1u); atomicMax(&w.flags[FLAG_MAXCNT], (uint32_t)n); }
     }
     __syncwarp();
   }
@@ -389,9 +580,11 @@ k_mam_search_long(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
 
 int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
   if (!b.n_reads) return 0;
+  int nl = 1;
   k_mam_search<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p);
-  if (w.long_q > MAXQ_FAST) { k_mam_search_long<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p); return 2; }
-  return 1;
+  if (w.surv) { k_mam_verify<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p); ++nl; }
+  if (w.long_q > MAXQ_FAST) { k_mam_search_long<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p); ++nl; }
+  return nl;
 }
 
 // ------------------------------------------------------------------ K3: records

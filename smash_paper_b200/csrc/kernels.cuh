@@ -14,6 +14,7 @@ struct BatchDev {
   const uint16_t *read_flag;
 };
 
+constexpr int SURV_CAP = 32;
 enum { FLAG_OVERFLOW = 0, FLAG_MAPERR = 1, FLAG_LONGREAD = 2, FLAG_MAXCNT = 3, FLAG_LONGQ = 4, N_FLAGS = 8 };
 
 struct WorkDev {
@@ -38,6 +39,11 @@ struct WorkDev {
   char *sam;                   // output text
   uint64_t sam_cap;
   uint32_t *flags;             // N_FLAGS counters
+  // split search (K1a/K1b): candidates that pass the seed + 4+4 filters are parked per read and verified
+  // by k_mam_verify with lanes = candidates of ONE read (null => verification inside k_mam_search)
+  uint64_t *surv;              // n_reads * SURV_CAP: anchor offset << 48 | SA index
+  uint8_t *surv_cnt;           // n_reads
+  uint8_t *lc;                 // lower-cased reads with the 16-byte pads of the staging buffer: read r at seq_off[r] + 32 r + 16
   uint8_t *long_scratch;       // per-warp staging for reads longer than MAXQ_FAST (null if the batch has none)
   int long_q;                  // longest read of the batch
 };
