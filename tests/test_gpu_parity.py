@@ -372,6 +372,22 @@ def test_golden_mem_records(case_name, variant):
         ctx.close()
 
 
+@pytest.mark.parametrize("seed_k", [5, 7, 9, 11])
+@pytest.mark.parametrize("mode", ["mam", "mum"])
+def test_seed_length_prefilter_and_split_search(case, seed_k, mode):
+    """Short seeds put many chance candidates into every bucket: the 4+4 character pre-filter is built
+    (N / 4^k >= 0.25), k_mam_search parks the survivors and k_mam_verify extends them (split search),
+    rows overflow into the in-kernel path, big buckets take the exact path -- same bytes as the oracle."""
+    from smash_paper_b200 import api
+    ix = api.Index.open(case["fa"])
+    ctx = api.Context(ix, min_len=20, nomap=True, seed_k=seed_k, mode=api.MODE_MUM if mode == "mum" else api.MODE_MAM)
+    try:
+        exp = case["oix"].map_batch(case["reads"], min_len=20, n_threads=4, mode=O.MUM if mode == "mum" else O.MAM)
+        assert ctx.map_batch(case["reads"]).sam == exp
+    finally:
+        ctx.close(); ix.close()
+
+
 @pytest.mark.parametrize("min_len", [20, 14])
 def test_mum_mode(case, min_len):
     """-mum (longSA::MUM, longSA.cpp:549-585): MAM + cleanMUMcand sweep, survivors in by_ref order."""
@@ -424,6 +440,12 @@ def test_large_sample_parity_and_invariants():
         assert b"".join(parts) == exp
         counts2, st2 = ctx.tail_finish()
         assert np.array_equal(counts, counts2) and st == st2
+        # short seed: pre-filter + split search at scale (rows of 32 parked candidates overflow here)
+        ctx2 = api.Context.from_text(text, startpos, sizes, descr, min_len=20, nomap=True, seed_k=10)
+        try:
+            assert ctx2.map_batch(reads).sam == exp
+        finally:
+            ctx2.close()
         # NH == number of records of the read, HI = 0..NH-1 in order
         import re
         by_read = {}
