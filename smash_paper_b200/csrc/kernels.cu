@@ -943,15 +943,50 @@ k_emit_text(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp, uint64_t n_reco
   }
 }
 
+// The bulk of a record is ONE contiguous run "SEQ \t QUAL" (2q+1 bytes).  The warp keeps that run (and
+// its reverse-complemented twin) in shared memory and streams it into every record of the read as
+// aligned 16-byte stores: lanes = 16-byte chunks of the destination, each assembled from five shared
+// words by funnel shifts; the <16 B before the first and after the last aligned chunk go out as one
+// predicated byte store (lanes 0-15 head, 16-31 tail).
+#ifndef SMASH_COPY_MAXQ
+#define SMASH_COPY_MAXQ MAXQ_FAST
+#endif
+constexpr int COPY_MAXQ = SMASH_COPY_MAXQ;                      // longer reads take the unstaged byte path
+constexpr int RUN_MAX = 2 * COPY_MAXQ + 1;
+constexpr int RUN_ROW = (RUN_MAX + 3 + 8) & ~3;                // word-aligned rows, slack for the 5-word window
 struct CopySmem {
-  uint8_t seq[WARPS][MAXQ_FAST], qual[WARPS][MAXQ_FAST];       // as given
-  uint8_t rseq[WARPS][MAXQ_FAST], rqual[WARPS][MAXQ_FAST];     // reverse-complemented / reversed
+  uint8_t fwd[WARPS][RUN_ROW];                                 // SEQ \t QUAL as given
+  uint8_t rev[WARPS][RUN_ROW];                                 // reverse complement \t reversed QUAL
   uint8_t comp[256];                                           // reverse_complement's character map (fasta.cpp:26-61)
 };
 constexpr int COPY_WARPS = 8;
 static_assert(COPY_WARPS == WARPS, "CopySmem is sized by WARPS");
 
-__global__ void __launch_bounds__(THREADS)
+__device__ __forceinline__ void copy_run(char *__restrict__ dst, const uint8_t *__restrict__ src, int len, int lane) {
+  const int head = (int)((16u - (unsigned)((uintptr_t)dst & 15u)) & 15u);
+  const int hl = head < len ? head : len;
+  const int nb = (len - hl) >> 4, tail = (len - hl) & 15;
+  {                                                            // edges: one byte store
+    const int t = lane & 15;
+    const int i = lane < 16 ? t : hl + 16 * nb + t;
+    if (lane < 16 ? t < hl : t < tail) dst[i] = (char)src[i];
+  }
+  const unsigned sh = (unsigned)(hl & 3) * 8u;
+  for (int k = lane; k < nb; k += 32) {
+    const int s0 = hl + 16 * k;
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(src + (s0 & ~3));   // rows are word-aligned
+    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+    uint4 v;
+    v.x = __funnelshift_r(w0, w1, sh); v.y = __funnelshift_r(w1, w2, sh);
+    v.z = __funnelshift_r(w2, w3, sh); v.w = __funnelshift_r(w3, w4, sh);
+    *reinterpret_cast<uint4 *>(dst + s0) = v;
+  }
+}
+
+#ifndef SMASH_COPY_MINBLK
+#define SMASH_COPY_MINBLK 6
+#endif
+__global__ void __launch_bounds__(THREADS, SMASH_COPY_MINBLK)
 k_emit_copy(BatchDev b, WorkDev w) {
   extern __shared__ __align__(16) uint8_t copy_smem_raw[];
   CopySmem &sm = *reinterpret_cast<CopySmem *>(copy_smem_raw);
@@ -959,53 +994,110 @@ k_emit_copy(BatchDev b, WorkDev w) {
   sm.comp[threadIdx.x & 255] = comp_char((uint8_t)(threadIdx.x & 255));
   __syncthreads();
   const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
-  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
-    const int n_rec = (int)w.nrec[read];
-    if (!n_rec) continue;
-    const uint64_t fbase = w.rec_base[read];
-    const int64_t so = b.seq_off[read], no = b.name_off[read];
-    const int q = (int)(b.seq_off[read + 1] - so), name_len = (int)(b.name_off[read + 1] - no);
-    const uint8_t *__restrict__ seq = b.seq + so, *__restrict__ qual = b.qual + so, *__restrict__ name = b.names + no;
-    const bool unmapped = w.sums[read].unmapped;
-    const Rec *recs = w.rec_slots + slot_base(w, read);
-    const bool staged = q <= MAXQ_FAST;
-    bool any_rc = false;
-    if (!unmapped) for (int r = lane; r < n_rec; r += 32) any_rc |= recs[r].rc != 0;
-    any_rc = __any_sync(0xffffffffu, any_rc);
-    if (staged) {
-      for (int j = lane; j < q; j += 32) {
-        const uint8_t sv = seq[j], qv = qual[j];
-        sm.seq[warp][j] = sv; sm.qual[warp][j] = qv;
-        if (any_rc) { sm.rseq[warp][q - 1 - j] = sm.comp[sv]; sm.rqual[warp][q - 1 - j] = qv; }
-      }
+  // a warp takes 32 consecutive reads: lane l fetches the placement data of read l (coalesced, one round
+  // of latency per 32 reads), then the warp walks the reads with shuffles
+  for (uint64_t blk = (uint64_t)blockIdx.x * WARPS + warp; blk * 32 < b.n_reads; blk += warps_total) {
+    const uint64_t rd = blk * 32 + (uint64_t)lane;
+    int m_nrec = 0; uint64_t m_fbase = 0; int64_t m_so = 0, m_no = 0; int m_q = 0, m_nl = 0; int m_unm = 0;
+    if (rd < b.n_reads) {
+      m_nrec = (int)w.nrec[rd]; m_fbase = w.rec_base[rd];
+      m_so = b.seq_off[rd]; m_q = (int)(b.seq_off[rd + 1] - m_so);
+      m_no = b.name_off[rd]; m_nl = (int)(b.name_off[rd + 1] - m_no);
+      m_unm = w.sums[rd].unmapped ? 1 : 0;
     }
+  for (int ri = 0; ri < 32; ++ri) {
+    const int n_rec = __shfl_sync(0xffffffffu, m_nrec, ri);
+    if (!n_rec) continue;
+    const uint64_t read = blk * 32 + (uint64_t)ri;
+    const uint64_t fbase = __shfl_sync(0xffffffffu, m_fbase, ri);
+    const int64_t so = __shfl_sync(0xffffffffu, m_so, ri), no = __shfl_sync(0xffffffffu, m_no, ri);
+    const int q = __shfl_sync(0xffffffffu, m_q, ri), name_len = __shfl_sync(0xffffffffu, m_nl, ri);
+    const uint8_t *__restrict__ name = b.names + no;
+    const bool unmapped = __shfl_sync(0xffffffffu, m_unm, ri) != 0;
+    const Rec *recs = w.rec_slots + slot_base(w, read);
+    const bool staged = q <= COPY_MAXQ;
     const uint8_t nm = lane < name_len ? name[lane] : 0;
-    __syncwarp();
-    for (int r = 0; r < n_rec; ++r) {
-      const uint64_t f = fbase + (uint64_t)r;
-      char *out = w.sam + w.rec_off[f];
-      const bool rc = recs[r].rc && !unmapped;
-      if (lane < name_len) out[lane] = (char)nm;
-      for (int i = lane + 32; i < name_len; i += 32) out[i] = (char)name[i];
-      char *o2 = out + recs[r].seq_off;
-      if (staged) {
-        const uint8_t *S = rc ? sm.rseq[warp] : sm.seq[warp], *Q = rc ? sm.rqual[warp] : sm.qual[warp];
-        for (int j = lane; j < q; j += 32) { o2[j] = (char)S[j]; o2[q + 1 + j] = (char)Q[j]; }
-      } else {
-        for (int j = lane; j < q; j += 32) {
-          const int src = rc ? q - 1 - j : j;
-          o2[j] = (char)(rc ? sm.comp[seq[src]] : seq[src]); o2[q + 1 + j] = (char)qual[src];
+    // lanes = first 32 records: their placement, requested together with the read's bytes
+    uint64_t my_off = 0; uint32_t my_meta = 0, my_tail = 0;
+    if (lane < n_rec) {
+      const Rec rr = recs[lane];
+      my_off = w.rec_off[fbase + (uint64_t)lane];
+      my_meta = (uint32_t)rr.seq_off | (rr.rc && !unmapped ? 0x80000000u : 0u);
+      if (b.opt) my_tail = w.rec_bytes[fbase + (uint64_t)lane] - 1u - rr.lr_len;
+    }
+    if (staged) {
+      // word-wise fetch of SEQ and QUAL (same misalignment: they share seq_off), all words of a
+      // 256-byte pass in flight together; bytes are scattered into the forward and reversed runs
+      uint8_t *F = sm.fwd[warp], *R = sm.rev[warp];
+      const int mis = (int)(so & 3);
+      const uint32_t *sw = reinterpret_cast<const uint32_t *>(b.seq + (so - mis));
+      const uint32_t *qw = reinterpret_cast<const uint32_t *>(b.qual + (so - mis));
+      const int nwords = (mis + q + 3) >> 2;
+      for (int w0 = 0; w0 < nwords; w0 += 64) {
+        const int i0 = w0 + lane, i1 = w0 + 32 + lane;
+        uint32_t s0 = 0, q0 = 0, s1 = 0, q1 = 0;
+        if (i0 < nwords) { s0 = __ldg(sw + i0); q0 = __ldg(qw + i0); }
+        if (i1 < nwords) { s1 = __ldg(sw + i1); q1 = __ldg(qw + i1); }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = h ? i1 : i0;
+          const uint32_t sv4 = h ? s1 : s0, qv4 = h ? q1 : q0;
+          if (i < nwords) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int j = 4 * i - mis + t;
+              if (j >= 0 && j < q) {
+                const uint8_t sv = (uint8_t)(sv4 >> (8 * t)), qv = (uint8_t)(qv4 >> (8 * t));
+                F[j] = sv; F[q + 1 + j] = qv;
+                R[q - 1 - j] = sm.comp[sv]; R[2 * q - j] = qv;
+              }
+            }
+          }
         }
       }
-      if (lane == 0) o2[q] = '\t';
-      if (b.opt) {
-        const int64_t oo = b.opt_off[read];
-        const int opt_len = (int)(b.opt_off[read + 1] - oo);
-        char *o3 = out + (w.rec_bytes[f] - 1u - recs[r].lr_len - (uint32_t)opt_len);
-        for (int i = lane; i < opt_len; i += 32) o3[i] = (char)b.opt[oo + i];
+      if (lane == 0) { F[q] = '\t'; R[q] = '\t'; }
+    }
+    __syncwarp();
+    for (int r0 = 0; r0 < n_rec; r0 += 32) {
+      if (r0) {                                              // more than 32 records: next block's placement
+        my_off = 0; my_meta = 0; my_tail = 0;
+        if (r0 + lane < n_rec) {
+          const Rec rr = recs[r0 + lane];
+          my_off = w.rec_off[fbase + (uint64_t)(r0 + lane)];
+          my_meta = (uint32_t)rr.seq_off | (rr.rc && !unmapped ? 0x80000000u : 0u);
+          if (b.opt) my_tail = w.rec_bytes[fbase + (uint64_t)(r0 + lane)] - 1u - rr.lr_len;
+        }
+      }
+      const int nr = n_rec - r0 < 32 ? n_rec - r0 : 32;
+      for (int r = 0; r < nr; ++r) {
+        const uint64_t off = __shfl_sync(0xffffffffu, my_off, r);
+        const uint32_t meta = __shfl_sync(0xffffffffu, my_meta, r);
+        char *out = w.sam + off;
+        const bool rc = (meta >> 31) != 0;
+        if (lane < name_len) out[lane] = (char)nm;
+        for (int i = lane + 32; i < name_len; i += 32) out[i] = (char)name[i];
+        char *o2 = out + (meta & 0x7fffffffu);
+        if (staged) {
+          copy_run(o2, rc ? sm.rev[warp] : sm.fwd[warp], 2 * q + 1, lane);
+        } else {
+          const uint8_t *__restrict__ seq = b.seq + so, *__restrict__ qual = b.qual + so;
+          for (int j = lane; j < q; j += 32) {
+            const int src = rc ? q - 1 - j : j;
+            o2[j] = (char)(rc ? sm.comp[seq[src]] : seq[src]); o2[q + 1 + j] = (char)qual[src];
+          }
+          if (lane == 0) o2[q] = '\t';
+        }
+        if (b.opt) {
+          const uint32_t tail = __shfl_sync(0xffffffffu, my_tail, r);
+          const int64_t oo = b.opt_off[read];
+          const int opt_len = (int)(b.opt_off[read + 1] - oo);
+          char *o3 = out + (tail - (uint32_t)opt_len);
+          for (int i = lane; i < opt_len; i += 32) o3[i] = (char)b.opt[oo + i];
+        }
       }
     }
     __syncwarp();
+  }
   }
 }
 
@@ -1019,7 +1111,7 @@ int launch_emit_copy(const BatchDev &b, const WorkDev &w, cudaStream_t st, uint6
   if (!b.n_reads || !n_records) return 0;
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(k_emit_copy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CopySmem)); attr_set = true; }
-  k_emit_copy<<<grid_for_warps(b.n_reads, 6), THREADS, sizeof(CopySmem), st>>>(b, w);
+  k_emit_copy<<<grid_for_warps((b.n_reads + 31) / 32, SMASH_COPY_MINBLK), THREADS, sizeof(CopySmem), st>>>(b, w);
   return 1;
 }
 
