@@ -684,7 +684,10 @@ __device__ __forceinline__ int xe_word_g(const DevIndex &ix, const uint8_t *__re
   return cnt;
 }
 
-__global__ void __launch_bounds__(THREADS)
+#ifndef SMASH_XE_MINBLK
+#define SMASH_XE_MINBLK 8
+#endif
+__global__ void __launch_bounds__(THREADS, SMASH_XE_MINBLK)
 k_rec_xe(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane >> 3, sl = lane & 7;
@@ -910,7 +913,10 @@ int launch_sizes_scan(const DevIndex &ix, const BatchDev &b, const WorkDev &w, c
 //  k_emit_copy  the BULK bytes (name, SEQ, QUAL, optional fields): one warp per READ loads them once
 //               into shared memory and streams them into each of the read's records (reverse-
 //               complemented for reverse-strand records) with coalesced byte stores.
-__global__ void __launch_bounds__(128)
+#ifndef SMASH_TEXT_MINBLK
+#define SMASH_TEXT_MINBLK 1
+#endif
+__global__ void __launch_bounds__(128, SMASH_TEXT_MINBLK)
 k_emit_text(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp, uint64_t n_records) {
   for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_records; f += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t read = w.rec_read[f];
