@@ -204,7 +204,8 @@ int smash_ctx_set_chunking(smash_ctx *ctx, int max_chunks, uint64_t min_reads);
 /* ---- counters for bench.py: kernels launched by this library since ctx creation */
 uint64_t smash_ctx_launch_count(const smash_ctx *ctx);
 /* Device milliseconds accumulated per stage since the last reset, measured with CUDA events on the
- * launching stream: [0] search, [1] records, [2] sizes+scan, [3] emit_text, [4] match CSR, [5] tail, [6] emit_copy. */
+ * launching stream: [0] search, [1] records, [2] sizes+scan, [3] emit_text, [4] match CSR, [5] tail, [6] emit_copy,
+ * [7] verify (k_mam_verify of the split search, 0 when candidates are verified inside k_mam_search). */
 void smash_ctx_stage_ms(smash_ctx *ctx, double *out8, int reset);
 /* Bytes of HBM held by the index on this ctx (text, SA, LCP, seed table, ...). */
 uint64_t smash_ctx_index_bytes(const smash_ctx *ctx);

@@ -379,7 +379,7 @@ class Context:
     def stage_ms(self, reset=False):
         out = (C.c_double * 8)()
         load_library().smash_ctx_stage_ms(self.h, out, int(reset))
-        return dict(zip(["search", "records", "sizes_scan", "emit_text", "match_csr", "tail", "emit_copy"], list(out)[:7]))
+        return dict(zip(["search", "records", "sizes_scan", "emit_text", "match_csr", "tail", "emit_copy", "verify"], list(out)[:8]))
 
     @property
     def launches(self):

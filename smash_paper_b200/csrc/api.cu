@@ -218,7 +218,7 @@ template <class T> struct HBuf {        // growable pinned host buffer
 // PCIe while the later ranges are still being searched.
 constexpr int MAX_CHUNKS = 4;
 constexpr uint64_t CHUNK_MIN_READS = 65536;
-constexpr int N_EVS = 8 * MAX_CHUNKS;
+constexpr int N_EVS = 10 * MAX_CHUNKS;
 
 struct Slot {
   cudaStream_t st = nullptr;
@@ -270,7 +270,7 @@ struct smash_ctx {
   smash_index *own_index = nullptr;
   uint64_t index_bytes = 0;
   uint64_t launches = 0;
-  double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // search, records, sizes+scan, emit_text, csr, tail, emit_copy
+  double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // search, records, sizes+scan, emit_text, csr, tail, emit_copy, verify
   Slot slot[SMASH_N_SLOTS];
   TailState tail;
 };
@@ -759,6 +759,11 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
     }
     c->launches += nl;
     MARK(0);
+    if (!s.csr) {
+      const int nv = launch_mam_verify(c->dix, s.bd, w, c->sp, s.st);
+      c->launches += nv;
+      if (nv) MARK(7);
+    }
     c->launches += launch_records(c->dix, s.bd, w, c->sp, s.st);
     MARK(1);
     c->launches += launch_sizes_scan(c->dix, s.bd, w, c->sp, s.st);

@@ -580,8 +580,13 @@ k_mam_search_long(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
 
 int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
   if (!b.n_reads) return 0;
-  int nl = 1;
   k_mam_search<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p);
+  return 1;
+}
+// after launch_mam_search: extension of the parked candidates (split search) and the long-read kernel
+int launch_mam_verify(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
+  if (!b.n_reads) return 0;
+  int nl = 0;
   if (w.surv) { k_mam_verify<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p); ++nl; }
   if (w.long_q > MAXQ_FAST) { k_mam_search_long<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p); ++nl; }
   return nl;

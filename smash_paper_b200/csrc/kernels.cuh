@@ -72,6 +72,7 @@ int launch_seed_build(const DevIndex &ix, void *seed, int k, int seed_w, cudaStr
 int launch_ext_build(const DevIndex &ix, int k, uint16_t *ext, cudaStream_t st);
 int launch_alpha(const uint8_t *text, uint64_t N, uint32_t *alpha8, cudaStream_t st);
 int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
+int launch_mam_verify(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
 int launch_mem_count(const DevIndex &ix, const BatchDev &b, const SearchParams &p, uint32_t min_len_raw, uint32_t *cnt, cudaStream_t st);
 int launch_mem_write(const DevIndex &ix, const BatchDev &b, const SearchParams &p, uint32_t min_len_raw, const uint64_t *off,
                      Match *matches, cudaStream_t st);
