@@ -522,6 +522,7 @@ int tail_reserve(TailState *t, uint64_t pairs, uint64_t hits, cudaStream_t st) {
   const size_t want[12] = {8 * tsize, 8 * tsize, 4 * pairs, pairs, 64, 4 * pairs, 4 * pairs, 8 * (pairs + 1), 8 * (pairs + 1),
                            8 * (pairs / 2048 + 8), 8 * (hits + 1), 8 * (hits + 1)};
   for (int i = 0; i < 12; ++i) if ((rc = t->scr[i].reserve(want[i], 0, st))) return rc;
+  if ((rc = t->exp_keys.reserve(24 * (pairs + 1), 0, st))) return rc;          // smash_tail_export_keys (multi-GPU tail)
   if (hits + 1 > t->pos_cap) {
     if (t->pos_chrom) cudaFree(t->pos_chrom);
     if (t->pos_pos) cudaFree(t->pos_pos);

@@ -83,6 +83,17 @@ def partitioned_min_ordinals(keys, dist, rank, world):
     """For every row {fp1, fp2, ordinal} of `keys` the smallest ordinal over ALL ranks that carries the same
     (fp1, fp2).  The key space is hash-partitioned: rank r resolves the keys with fp1 mod world == r, so the
     work and the traffic per rank stay constant as ranks are added (weak scaling), unlike an all_gather."""
+    import os, time
+    dbg = os.environ.get("SMASH_DEBUG_TIMING") and rank == world - 1
+    tl = [time.perf_counter()]
+
+    def lap(label):
+        if dbg:
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
+            tl.append(time.perf_counter())
+            print(f"[smash-dbg]   partitioned:{label:14s} {1e3 * (tl[-1] - tl[-2]):8.3f} ms", flush=True)
+
     n = keys.shape[0]
     dev = keys.device
     owner = torch.remainder(keys[:, 0], world) if n else torch.zeros(0, dtype=torch.int64, device=dev)
@@ -92,7 +103,9 @@ def partitioned_min_ordinals(keys, dist, rank, world):
     chunks, o = [], 0
     for c in counts:
         chunks.append(sorted_keys[o:o + c]); o += c
+    lap("bucket")
     got = _all_to_all_rows(chunks, dist, world)
+    lap("all_to_all")
     recv_counts = [g.shape[0] for g in got]
     allk = torch.cat(got, dim=0) if sum(recv_counts) else torch.zeros((0, 3), dtype=torch.int64, device=dev)
     # group identical (fp1, fp2): three stable sorts (ordinal, fp2, fp1) -> the first row of a group has its minimum ordinal
@@ -110,10 +123,12 @@ def partitioned_min_ordinals(keys, dist, rank, world):
         mins[p] = mins_sorted
     else:
         mins = torch.zeros(0, dtype=torch.int64, device=dev)
+    lap("group")
     back_chunks, o = [], 0
     for c in recv_counts:
         back_chunks.append(mins[o:o + c].reshape(-1, 1)); o += c
     back = _all_to_all_rows(back_chunks, dist, world)
+    lap("all_to_all 2")
     mins_for_sorted = torch.cat(back, dim=0).reshape(-1) if n else torch.zeros(0, dtype=torch.int64, device=dev)
     result = torch.empty(n, dtype=torch.int64, device=dev)
     result[order] = mins_for_sorted
@@ -136,7 +151,7 @@ def sharded_tail_finish(backend, dist, rank, world):
 
     keys = backend.export_keys()
     lap("export")
-    if world > 2 and hasattr(backend, "phase_a_verdict"):
+    if (world > 2 or os.environ.get("SMASH_FORCE_PARTITIONED")) and hasattr(backend, "phase_a_verdict"):
         # many ranks: hash-partitioned exchange, O(1) keys per rank
         mins = partitioned_min_ordinals(keys, dist, rank, world)
         lap("partitioned")
