@@ -1,7 +1,7 @@
 /* include/smash_b200.h -- C ABI of libsmash_b200.so (hand-written sm_100a CUDA behind it).
  *
  * The reference (yamrom/smash-paper) has no plugin/FFI interface; its boundary is the `mummer`
- * process + the `<ref>.bin/` index files + `mapout/*.txt`, and inside the process the seam
+ * process + the `<ref>.bin/` index files + `mapout/<chunk>.txt`, and inside the process the seam
  * `Aligner::run -> longSA::MAM|MEM(Aligner&) -> Aligner::process_match` (query.cpp:322-329,
  * 436-438).  Every entry point below names the reference interface it replaces.  Plain
  * pointers and sizes only; all calls return 0 on success or a negative smash_status, with the
@@ -143,6 +143,42 @@ int smash_batch_upload(smash_ctx *ctx, const smash_batch *b);
 int smash_map_resident(smash_ctx *ctx, int want, smash_result *res);  /* no H2D/D2H; res->sam NULL */
 /* Copy the resident run's SAM text to host (for checks). */
 int smash_fetch_sam(smash_ctx *ctx, const char **sam, uint64_t *n_bytes);
+
+/* ---- input side on the device: raw text in, the reader's parse runs on the GPU.
+ * SMASH_TEXT_SAM replaces QueryReader::run's SAM branch (query.cpp:625-648: getline, whitespace-separated
+ * fields name flag <7 ignored> seq errors [optional...], ":0"/":1" from flag 64/128) together with
+ * NewQuery::add_optional (query.cpp:150-153) and Aligner::reset (query.cpp:185-201).
+ * SMASH_TEXT_FASTQ_PAIR takes the two (decompressed) FASTQ texts of a mate pair and replaces
+ * `fastqs_to_sam fq1 fq2 [1]` (fastqs_to_sam.cpp:47-95: records alternate between the files, blank lines
+ * before '@' and '+' are skipped, second header token -> XO:Z:, '>' records reuse the bases as errors,
+ * empty reads print nothing, flags 77/141) followed by that SAM branch -- the producer/consumer pair of
+ * smash_mapping.sh:19.  SMASH_TEXT_REPLACE_N = fastqs_to_sam's third argument (N -> Z in the bases).
+ * Without SMASH_TEXT_FINAL the text is one chunk of a longer stream: only complete lines (FASTQ: complete
+ * record pairs, less the last one, which may be cut) are taken, and an odd trailing read is left for the
+ * next chunk so that the reader's pairing by arrival parity (query.cpp:629-637) is unchanged; `consumed`
+ * says how many bytes of each text were used -- the caller passes the rest again, followed by more input.
+ * Input the reference would misparse silently (fewer than 11 SAM fields, a non-numeric flag, SEQ/QUAL of
+ * different lengths, a truncated FASTQ record) fails with SMASH_ERR_DATA, the FASTQ '@' / '+' checks with
+ * the reference's own messages.  The text buffers may be reused as soon as the call returns. */
+enum { SMASH_TEXT_SAM = 0, SMASH_TEXT_FASTQ_PAIR = 1 };
+enum { SMASH_TEXT_FINAL = 1, SMASH_TEXT_REPLACE_N = 2 };
+typedef struct {
+  int kind;                      /* SMASH_TEXT_* */
+  int flags;                     /* SMASH_TEXT_FINAL | SMASH_TEXT_REPLACE_N */
+  const char *text[2];           /* SAM: text[0]; FASTQ pair: mate-1 text, mate-2 text (host memory, pinned or not) */
+  uint64_t n_bytes[2];
+  uint64_t first_pair_ordinal;   /* as in smash_batch */
+} smash_text;
+typedef struct { uint64_t n_reads; uint64_t consumed[2]; } smash_text_info;
+/* smash_submit with the batch parsed on the device; collect the result with smash_wait. */
+int smash_submit_text(smash_ctx *ctx, int slot, const smash_text *t, int want, smash_text_info *info);
+/* Device-resident variant (slot 0): parse only; run it with smash_map_resident. */
+int smash_text_upload(smash_ctx *ctx, const smash_text *t, smash_text_info *info);
+/* The packed batch a slot holds in HBM, for checks: sizes, then a copy into caller buffers of those sizes
+ * (offset arrays n_reads+1; any pointer may be NULL). */
+int smash_batch_sizes(smash_ctx *ctx, int slot, uint64_t *n_reads, uint64_t *name_bytes, uint64_t *seq_bytes, uint64_t *opt_bytes);
+int smash_fetch_batch(smash_ctx *ctx, int slot, uint8_t *names, int64_t *name_off, uint8_t *seq, uint8_t *qual, int64_t *seq_off,
+                      uint8_t *opt, int64_t *opt_off, uint16_t *read_flag);
 
 /* ---- tail: smashMEM.py filter (smashMEM.py:84-92,193-228 with "0 0 10000 4") + awk/perl chromosome
  * filter (smash_mapping.sh:29) + varbin.py (varbin.py:6-118).  Bins are bins.txt column 3

@@ -45,6 +45,30 @@ class _TailStats(C.Structure):
                 ("n_dupe_pairs", C.c_uint64), ("n_non_dupe_pairs", C.c_uint64), ("n_positions", C.c_uint64)]
 
 
+class _Text(C.Structure):
+    _fields_ = [("kind", C.c_int), ("flags", C.c_int), ("text", C.c_char_p * 2), ("n_bytes", C.c_uint64 * 2),
+                ("first_pair_ordinal", C.c_uint64)]
+
+
+class _TextInfo(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("consumed", C.c_uint64 * 2)]
+
+
+TEXT_SAM, TEXT_FASTQ_PAIR = 0, 1
+TEXT_FINAL, TEXT_REPLACE_N = 1, 2
+
+
+class DeviceBatch:
+    """Host copy of the packed batch a slot holds in HBM (smash_fetch_batch)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    @property
+    def n(self):
+        return len(self.read_flag)
+
+
 class _TailEdge(C.Structure):
     _fields_ = [("n_filtered", C.c_uint64), ("first_pos", C.c_int64), ("last_pos", C.c_int64)]
 
@@ -308,6 +332,44 @@ class Context:
         r = _Result()
         _check(load_library().smash_map_resident(self.h, want, C.byref(r)))
         return r
+
+    # -- input side on the device (raw SAM text / FASTQ pair text in; ingest.cu) ------------------------
+    @staticmethod
+    def _ctext(kind, text0, text1, final, replace_n, first_pair):
+        t = _Text()
+        t.kind = kind
+        t.flags = (TEXT_FINAL if final else 0) | (TEXT_REPLACE_N if replace_n else 0)
+        t.text[0], t.text[1] = text0, (text1 if kind == TEXT_FASTQ_PAIR else None)
+        t.n_bytes[0], t.n_bytes[1] = len(text0), (len(text1) if kind == TEXT_FASTQ_PAIR else 0)
+        t.first_pair_ordinal = first_pair
+        return t
+
+    def text_upload(self, kind, text0, text1=b"", final=True, replace_n=False, first_pair=0):
+        """Parse raw text on the GPU into slot 0's resident batch -> (n_reads, (consumed0, consumed1))."""
+        t = self._ctext(kind, bytes(text0), bytes(text1), final, replace_n, first_pair)
+        info = _TextInfo()
+        _check(load_library().smash_text_upload(self.h, C.byref(t), C.byref(info)))
+        return int(info.n_reads), (int(info.consumed[0]), int(info.consumed[1]))
+
+    def submit_text(self, slot, kind, text0, text1=b"", final=True, replace_n=False, first_pair=0, want=WANT_SAM):
+        t = self._ctext(kind, bytes(text0), bytes(text1), final, replace_n, first_pair)
+        info = _TextInfo()
+        _check(load_library().smash_submit_text(self.h, slot, C.byref(t), want, C.byref(info)))
+        self._inflight[slot] = (None, None, t, want)
+        return int(info.n_reads), (int(info.consumed[0]), int(info.consumed[1]))
+
+    def fetch_batch(self, slot=0):
+        L = load_library()
+        n, nb, sb, ob = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(L.smash_batch_sizes(self.h, slot, C.byref(n), C.byref(nb), C.byref(sb), C.byref(ob)))
+        n, nb, sb, ob = n.value, nb.value, sb.value, ob.value
+        names = np.zeros(nb, np.uint8); seq = np.zeros(sb, np.uint8); qual = np.zeros(sb, np.uint8); opt = np.zeros(ob, np.uint8)
+        name_off = np.zeros(n + 1, np.int64); seq_off = np.zeros(n + 1, np.int64); opt_off = np.zeros(n + 1, np.int64)
+        rf = np.zeros(n, np.uint16)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)          # noqa: E731 -- empty arrays still need a valid pointer
+        _check(L.smash_fetch_batch(self.h, slot, vp(names), vp(name_off), vp(seq), vp(qual), vp(seq_off), vp(opt), vp(opt_off), vp(rf)))
+        return DeviceBatch(names=names, name_off=name_off, seq=seq, qual=qual, seq_off=seq_off, opt=opt, opt_off=opt_off,
+                           read_flag=rf, flags=np.zeros(n, np.uint16))
 
     def fetch_sam(self):
         p = C.c_void_p()

@@ -19,6 +19,7 @@
 #include "kernels.cuh"
 #include "tail.cuh"
 #include "sabuild.cuh"
+#include "ingest_launch.cuh"
 
 using namespace smash;
 
@@ -247,6 +248,12 @@ struct Slot {
   bool split = false;
   DBuf<uint64_t> surv; DBuf<uint8_t> surv_cnt; DBuf<uint8_t> lc;      // split search (k_mam_search -> k_mam_verify)
   HBuf<uint16_t> h_flag;       // pinned staging for a pageable read_flag array
+  // device-side input stage (smash_submit_text): raw text, line tables, per-record parse results, scan scratch
+  DBuf<uint8_t> ing_raw[2]; DBuf<uint64_t> ing_ls[2]; DBuf<uint64_t> ing_hdr[2]; DBuf<uint8_t> ing_hdr_flag;
+  DBuf<uint64_t> ing_blk64; DBuf<uint32_t> ing_blk32; DBuf<Ing4> ing_blk4; DBuf<Ing4> ing_pre; DBuf<LineRec> ing_recs;
+  DBuf<unsigned long long> ing_scal;      // [0] first error, [1..2] FASTQ records per text
+  HBuf<uint64_t> h_ing;
+  uint64_t name_bytes = 0, seq_bytes = 0, opt_bytes = 0;   // sizes of the batch blobs on the device
   // results on host
   HBuf<char> h_sam; HBuf<int64_t> h_csr_off; HBuf<smash_match> h_matches; HBuf<uint64_t> h_small;
   // in flight
@@ -571,6 +578,9 @@ static void slot_release(Slot &s) {
   s.nrec.release(); s.rec_base.release(); s.rec_read.release(); s.rec_bytes.release(); s.rec_off.release(); s.sam_total.release(); s.blk_sums2.release(); s.blk_sums.release(); s.sam.release(); s.flags.release();
   s.csr_off.release(); s.csr_triples.release(); s.long_scratch.release(); s.slot_off.release(); s.aln_scr.release(); s.ord_scr.release(); s.tmp32.release(); s.h_sam.release(); s.h_csr_off.release();
   s.h_matches.release(); s.h_small.release(); s.h_flag.release(); s.surv.release(); s.surv_cnt.release(); s.lc.release();
+  for (int f = 0; f < 2; ++f) { s.ing_raw[f].release(); s.ing_ls[f].release(); s.ing_hdr[f].release(); }
+  s.ing_hdr_flag.release(); s.ing_blk64.release(); s.ing_blk32.release(); s.ing_blk4.release(); s.ing_pre.release();
+  s.ing_recs.release(); s.ing_scal.release(); s.h_ing.release();
   if (s.ev0) cudaEventDestroy(s.ev0);
   if (s.ev1) cudaEventDestroy(s.ev1);
   for (int e = 0; e < N_EVS; ++e) if (s.evs[e]) cudaEventDestroy(s.evs[e]);
@@ -636,11 +646,11 @@ extern "C" int smash_ctx_build_mappability(smash_ctx *c, uint8_t *body, uint64_t
 
 // ------------------------------------------------------------------ batches
 
-static int slot_prepare(smash_ctx *c, Slot &s, const smash_batch *b, bool copy, int chunks = 1) {
+// Device buffers of a slot for a batch of n reads with blobs of the given sizes, and the read ranges of the
+// chunked pipeline.  The batch itself arrives either by H2D copies (slot_prepare) or from the device-side
+// input stage (ingest_text).
+static int slot_reserve(smash_ctx *c, Slot &s, uint64_t n, size_t name_bytes, size_t seq_bytes, size_t opt_bytes, int chunks) {
   double t_prep = now_ms();
-  const uint64_t n = b->n_reads;
-  const size_t name_bytes = n ? (size_t)b->name_off[n] : 0, seq_bytes = n ? (size_t)b->seq_off[n] : 0;
-  const size_t opt_bytes = (b->opt && n) ? (size_t)b->opt_off[n] : 0;
   int rc;
   if ((rc = s.names.ensure(name_bytes + 16)) || (rc = s.seq.ensure(seq_bytes + 16)) || (rc = s.qual.ensure(seq_bytes + 16)) ||
       (rc = s.name_off.ensure(n + 1)) || (rc = s.seq_off.ensure(n + 1)) || (rc = s.read_flag.ensure(n + 1)))
@@ -667,6 +677,22 @@ static int slot_prepare(smash_ctx *c, Slot &s, const smash_batch *b, bool copy, 
     for (int ch = 0; ch <= s.n_chunks; ++ch) { const uint64_t r = per * ch; s.chunk_r[ch] = r < n ? r : n; }
     s.chunk_r[s.n_chunks] = n;
   }
+  s.name_bytes = name_bytes; s.seq_bytes = seq_bytes; s.opt_bytes = opt_bytes;
+  s.bd.n_reads = n; s.bd.names = s.names.p; s.bd.name_off = s.name_off.p; s.bd.seq = s.seq.p; s.bd.qual = s.qual.p;
+  s.bd.seq_off = s.seq_off.p; s.bd.opt = opt_bytes ? s.opt.p : nullptr; s.bd.opt_off = opt_bytes ? s.opt_off.p : nullptr;
+  s.bd.read_flag = s.read_flag.p;
+  s.n_reads = n;
+  s.long_q = 0;               // reads longer than MAXQ_FAST: the search kernel reports them, run_range re-runs with scratch
+  return 0;
+}
+
+static int slot_prepare(smash_ctx *c, Slot &s, const smash_batch *b, bool copy, int chunks = 1) {
+  const uint64_t n = b->n_reads;
+  const size_t name_bytes = n ? (size_t)b->name_off[n] : 0, seq_bytes = n ? (size_t)b->seq_off[n] : 0;
+  const size_t opt_bytes = (b->opt && n) ? (size_t)b->opt_off[n] : 0;
+  int rc;
+  if ((rc = slot_reserve(c, s, n, name_bytes, seq_bytes, opt_bytes, chunks))) return rc;
+  double t_prep = now_ms();
   if (copy && n) {
     cudaStream_t in = s.n_chunks > 1 ? s.st_in : s.st;
     // read_flag is usually computed on the fly by the caller (2 B/read): if it sits in pageable memory its
@@ -701,12 +727,7 @@ static int slot_prepare(smash_ctx *c, Slot &s, const smash_batch *b, bool copy, 
     }
   }
   DBG_T("  prepare:copies enqueued", t_prep);
-  t_prep = now_ms();
-  s.bd.n_reads = n; s.bd.names = s.names.p; s.bd.name_off = s.name_off.p; s.bd.seq = s.seq.p; s.bd.qual = s.qual.p;
-  s.bd.seq_off = s.seq_off.p; s.bd.opt = opt_bytes ? s.opt.p : nullptr; s.bd.opt_off = opt_bytes ? s.opt_off.p : nullptr;
-  s.bd.read_flag = s.read_flag.p;
-  s.n_reads = n; s.first_pair = b->first_pair_ordinal;
-  s.long_q = 0;               // reads longer than MAXQ_FAST: the search kernel reports them, run_range re-runs with scratch
+  s.first_pair = b->first_pair_ordinal;
   return 0;
 }
 
@@ -906,6 +927,187 @@ static int slot_finish(smash_ctx *c, Slot &s, smash_result *res) {
     }
   }
   s.busy = false;
+  return 0;
+}
+
+// ------------------------------------------------------------------ device-side input stage
+
+static const char *ing_err_text(uint32_t code) {
+  switch (code) {
+    case ING_FEW_FIELDS: return "SAM line with fewer than 11 fields (the reference would reuse the previous line's fields, query.cpp:640-642)";
+    case ING_BAD_FLAG: return "SAM flag field is not an unsigned integer";
+    case ING_LEN_MISMATCH: return "SEQ and QUAL lengths differ";
+    case ING_FQ_AT: return "Fastq @ parse error";                 // fastqs_to_sam.cpp:74
+    case ING_FQ_PLUS: return "Fastq + parse error";               // fastqs_to_sam.cpp:71
+    case ING_FQ_NAME: return "Problem reading read name";         // fastqs_to_sam.cpp:57
+    case ING_FQ_TRUNC: return "FASTQ record cut short by the end of the input";
+    case ING_FQ_COLUMNS: return "FASTQ bases/errors line is not one token (the SAM columns would shift)";
+    case ING_TOO_LONG: return "field longer than 2^31 bytes";
+    default: return "unknown input error";
+  }
+}
+
+// Raw text (host) -> packed batch in the slot's device buffers; the parse runs on the GPU.  Synchronises the
+// slot's stream (sizes have to reach the host before buffers are sized), so the text buffers may be reused
+// when it returns.  info->consumed: bytes of each text that went into this batch.
+static int ingest_text(smash_ctx *c, Slot &s, const smash_text *t, smash_text_info *info) {
+  const bool fastq = t->kind == SMASH_TEXT_FASTQ_PAIR;
+  const int final = (t->flags & SMASH_TEXT_FINAL) ? 1 : 0;
+  const int n_text = fastq ? 2 : 1;
+  cudaStream_t st = s.st;
+  int rc;
+  uint64_t nb[2] = {0, 0};
+  for (int f = 0; f < n_text; ++f) {
+    nb[f] = t->n_bytes[f];
+    if (nb[f] && !t->text[f]) return fail(SMASH_ERR_ARG, "null text");
+    if (!final) {                                            // a non-final chunk ends at its last complete line
+      while (nb[f] && t->text[f][nb[f] - 1] != '\n') --nb[f];
+    }
+  }
+  if (info) { info->n_reads = 0; info->consumed[0] = info->consumed[1] = 0; }
+  s.first_pair = t->first_pair_ordinal;
+  if ((rc = s.h_ing.ensure(16)) || (rc = s.ing_scal.ensure(4))) return rc;
+  uint64_t n_lines[2] = {0, 0};
+  // 1. upload + count lines
+  const uint64_t tiles[2] = {ing_tiles((nb[0] + 15) / 16), ing_tiles((nb[1] + 15) / 16)};
+  if ((rc = s.ing_blk64.ensure(tiles[0] + tiles[1] + 4))) return rc;
+  uint64_t *blk_lines[2] = {s.ing_blk64.p, s.ing_blk64.p + tiles[0] + 2};
+  for (int f = 0; f < n_text; ++f) {
+    if (!nb[f]) continue;
+    if ((rc = s.ing_raw[f].ensure(nb[f] + 64))) return rc;
+    CU(cudaMemcpyAsync(s.ing_raw[f].p, t->text[f], nb[f], cudaMemcpyHostToDevice, st));
+    c->launches += launch_ing_count_lines(s.ing_raw[f].p, nb[f], blk_lines[f], st);
+    CU(cudaMemcpyAsync(s.h_ing.p + 8 + f, blk_lines[f] + tiles[f], 8, cudaMemcpyDeviceToHost, st));
+  }
+  if (nb[0] || nb[1]) CU(cudaStreamSynchronize(st));
+  for (int f = 0; f < n_text; ++f) n_lines[f] = nb[f] ? s.h_ing.p[8 + f] : 0;
+  // 2. line starts (+ FASTQ: header lines)
+  CU(cudaMemsetAsync(s.ing_scal.p, 0xff, 8, st));
+  CU(cudaMemsetAsync(s.ing_scal.p + 1, 0, 16, st));
+  for (int f = 0; f < n_text; ++f) {
+    if (!n_lines[f]) continue;
+    if ((rc = s.ing_ls[f].ensure(n_lines[f] + 2))) return rc;
+    c->launches += launch_ing_line_starts(s.ing_raw[f].p, nb[f], blk_lines[f], s.ing_ls[f].p, st);
+  }
+  uint64_t m = 0, n_rec[2] = {n_lines[0], 0}, n_take[2] = {0, 0};
+  if (fastq) {
+    const uint64_t max_lines = n_lines[0] > n_lines[1] ? n_lines[0] : n_lines[1];
+    if (max_lines && ((rc = s.ing_hdr_flag.ensure(max_lines + 1)) || (rc = s.ing_blk32.ensure(ing_tiles(max_lines) + 2)))) return rc;
+    for (int f = 0; f < 2; ++f) {
+      if (!n_lines[f]) continue;
+      if ((rc = s.ing_hdr[f].ensure(n_lines[f] + ing_tiles(n_lines[f]) + 4))) return rc;
+      uint64_t *hdr = s.ing_hdr[f].p, *blk = s.ing_hdr[f].p + n_lines[f] + 1;    // record -> line table, then its scan tiles
+      c->launches += launch_ing_fastq_headers(s.ing_raw[f].p, s.ing_ls[f].p, n_lines[f], s.ing_blk32.p, blk, s.ing_hdr_flag.p, hdr,
+                                              (uint64_t *)(s.ing_scal.p + 1 + f), st);
+    }
+    CU(cudaMemcpyAsync(s.h_ing.p + 10, s.ing_scal.p + 1, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    n_rec[0] = s.h_ing.p[10]; n_rec[1] = s.h_ing.p[11];
+    ing_fastq_take(n_rec[0], n_rec[1], final, &n_take[0], &n_take[1]);
+    m = n_take[0] + n_take[1];
+  } else {
+    m = n_lines[0];
+  }
+  // 3. one LineRec per line / record, ordered compaction
+  uint64_t n_reads = 0, name_bytes = 0, seq_bytes = 0, opt_bytes = 0, m_used = 0;
+  if (m) {
+    if ((rc = s.ing_recs.ensure(m + 1)) || (rc = s.ing_pre.ensure(m + 2)) || (rc = s.ing_blk4.ensure(ing_tiles(m) + 2))) return rc;
+    if (fastq) {
+      const int replace_n = (t->flags & SMASH_TEXT_REPLACE_N) ? 1 : 0;
+      for (int f = 0; f < 2; ++f)
+        c->launches += launch_ing_parse_fastq(s.ing_raw[f].p, s.ing_ls[f].p, n_lines[f], s.ing_hdr[f].p, n_take[f], f, replace_n, s.ing_recs.p,
+                                              s.ing_scal.p, st);
+    } else {
+      c->launches += launch_ing_parse_sam(s.ing_raw[0].p, s.ing_ls[0].p, n_lines[0], s.ing_recs.p, s.ing_scal.p, st);
+    }
+    c->launches += launch_ing_scan_recs(s.ing_recs.p, m, s.ing_blk4.p, s.ing_pre.p, st);
+    IngPublish pb{};
+    pb.pre = s.ing_pre.p; pb.m = m; pb.final = final; pb.fastq = fastq ? 1 : 0;
+    for (int f = 0; f < 2; ++f) { pb.ls[f] = s.ing_ls[f].p; pb.hdr[f] = s.ing_hdr[f].p; pb.n_rec[f] = n_rec[f]; pb.n_bytes[f] = nb[f]; }
+    pb.err = s.ing_scal.p; pb.host = s.h_ing.p;
+    c->launches += launch_ing_publish(pb, st);
+    CU(cudaStreamSynchronize(st));
+    const uint64_t err = s.h_ing.p[7];
+    if (err != ~0ull) {
+      const uint32_t code = (uint32_t)(err & 0xff);
+      const uint64_t idx = err >> 8;
+      if (fastq) return fail(SMASH_ERR_DATA, "%s (record %llu of mate file %d)", ing_err_text(code), (unsigned long long)(idx / 2 + 1), (int)(idx & 1) + 1);
+      return fail(SMASH_ERR_DATA, "%s (input line %llu of this chunk)", ing_err_text(code), (unsigned long long)(idx + 1));
+    }
+    n_reads = s.h_ing.p[0]; name_bytes = s.h_ing.p[1]; seq_bytes = s.h_ing.p[2]; opt_bytes = s.h_ing.p[3]; m_used = s.h_ing.p[4];
+    if (info) { info->consumed[0] = s.h_ing.p[5]; info->consumed[1] = s.h_ing.p[6]; }
+  } else if (info) {
+    // nothing to parse: a final call consumes what is left, a non-final one waits for more input
+    info->consumed[0] = final ? t->n_bytes[0] : 0; info->consumed[1] = (final && fastq) ? t->n_bytes[1] : 0;
+  }
+  if (final && info) { info->consumed[0] = t->n_bytes[0]; info->consumed[1] = fastq ? t->n_bytes[1] : 0; }
+  // 4. batch buffers, then the copy
+  if ((rc = slot_reserve(c, s, n_reads, name_bytes, seq_bytes, opt_bytes, 1))) return rc;
+  if (n_reads) {
+    IngCopy cp{};
+    cp.text[0] = s.ing_raw[0].p; cp.text[1] = s.ing_raw[1].p; cp.recs = s.ing_recs.p; cp.pre = s.ing_pre.p; cp.m = m_used;
+    cp.names = s.names.p; cp.name_off = s.name_off.p; cp.seq = s.seq.p; cp.qual = s.qual.p; cp.seq_off = s.seq_off.p;
+    cp.opt = opt_bytes ? s.opt.p : nullptr; cp.opt_off = opt_bytes ? s.opt_off.p : nullptr; cp.read_flag = s.read_flag.p;
+    c->launches += launch_ing_copy(cp, st);
+  }
+  if (info) info->n_reads = n_reads;
+  return 0;
+}
+
+extern "C" int smash_submit_text(smash_ctx *c, int slot, const smash_text *t, int want, smash_text_info *info) {
+  if (!c || !t || slot < 0 || slot >= SMASH_N_SLOTS) return fail(SMASH_ERR_ARG, "bad argument");
+  if (t->kind != SMASH_TEXT_SAM && t->kind != SMASH_TEXT_FASTQ_PAIR) return fail(SMASH_ERR_ARG, "unknown text kind %d", t->kind);
+  Slot &s = c->slot[slot];
+  if (s.busy) return fail(SMASH_ERR_STATE, "slot %d still has a batch in flight", slot);
+  CU(cudaSetDevice(c->device));
+  int rc = ingest_text(c, s, t, info);
+  if (rc) return rc;
+  rc = slot_run(c, s, want, true);
+  if (rc) return rc;
+  s.busy = true;
+  return 0;
+}
+extern "C" int smash_text_upload(smash_ctx *c, const smash_text *t, smash_text_info *info) {
+  if (!c || !t) return fail(SMASH_ERR_ARG, "null argument");
+  if (t->kind != SMASH_TEXT_SAM && t->kind != SMASH_TEXT_FASTQ_PAIR) return fail(SMASH_ERR_ARG, "unknown text kind %d", t->kind);
+  CU(cudaSetDevice(c->device));
+  Slot &s = c->slot[0];
+  if (s.busy) return fail(SMASH_ERR_STATE, "slot 0 still has a batch in flight");
+  int rc = ingest_text(c, s, t, info);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(s.st));
+  CU(cudaGetLastError());
+  return 0;
+}
+extern "C" int smash_batch_sizes(smash_ctx *c, int slot, uint64_t *n_reads, uint64_t *name_bytes, uint64_t *seq_bytes, uint64_t *opt_bytes) {
+  if (!c || slot < 0 || slot >= SMASH_N_SLOTS) return fail(SMASH_ERR_ARG, "bad argument");
+  const Slot &s = c->slot[slot];
+  if (n_reads) *n_reads = s.n_reads;
+  if (name_bytes) *name_bytes = s.name_bytes;
+  if (seq_bytes) *seq_bytes = s.seq_bytes;
+  if (opt_bytes) *opt_bytes = s.opt_bytes;
+  return 0;
+}
+extern "C" int smash_fetch_batch(smash_ctx *c, int slot, uint8_t *names, int64_t *name_off, uint8_t *seq, uint8_t *qual, int64_t *seq_off,
+                                 uint8_t *opt, int64_t *opt_off, uint16_t *read_flag) {
+  if (!c || slot < 0 || slot >= SMASH_N_SLOTS) return fail(SMASH_ERR_ARG, "bad argument");
+  CU(cudaSetDevice(c->device));
+  Slot &s = c->slot[slot];
+  CU(cudaStreamSynchronize(s.st));
+  const uint64_t n = s.n_reads;
+  if (!n) return 0;
+  if (names) CU(cudaMemcpy(names, s.names.p, s.name_bytes, cudaMemcpyDeviceToHost));
+  if (name_off) CU(cudaMemcpy(name_off, s.name_off.p, 8 * (n + 1), cudaMemcpyDeviceToHost));
+  if (seq) CU(cudaMemcpy(seq, s.seq.p, s.seq_bytes, cudaMemcpyDeviceToHost));
+  if (qual) CU(cudaMemcpy(qual, s.qual.p, s.seq_bytes, cudaMemcpyDeviceToHost));
+  if (seq_off) CU(cudaMemcpy(seq_off, s.seq_off.p, 8 * (n + 1), cudaMemcpyDeviceToHost));
+  if (s.opt_bytes) {
+    if (opt) CU(cudaMemcpy(opt, s.opt.p, s.opt_bytes, cudaMemcpyDeviceToHost));
+    if (opt_off) CU(cudaMemcpy(opt_off, s.opt_off.p, 8 * (n + 1), cudaMemcpyDeviceToHost));
+  } else if (opt_off) {
+    memset(opt_off, 0, 8 * (n + 1));
+  }
+  if (read_flag) CU(cudaMemcpy(read_flag, s.read_flag.p, 2 * n, cudaMemcpyDeviceToHost));
   return 0;
 }
 

@@ -1,0 +1,277 @@
+// ingest.cuh -- input side on the device: raw SAM text, or the raw text of a FASTQ
+// pair, becomes the packed read batch (BatchDev) in HBM without a host-side parser.
+//
+// Restated semantics (reference file:line):
+//  * QueryReader::run, SAM branch (query.cpp:625-648): getline; empty lines are skipped; the line is
+//    tokenised by `istringstream >>` (any C-locale whitespace separates fields): name, flag (unsigned;
+//    digits only -- what follows the digits inside the same token becomes the NEXT token, as num_get leaves
+//    it in the stream), seven ignored fields, seq, errors, then every further token as "\t" + token
+//    (add_optional, query.cpp:150-153).  `flag & 64` appends ":0", else `flag & 128` appends ":1".
+//  * Aligner::reset (query.cpp:185-201): a trailing ":0" / ":1" is cut off the name and becomes
+//    read_flag 65 / 129.
+//  * fastqs_to_sam main loop (fastqs_to_sam.cpp:47-95): alternately one record from each file; `in >> ch`
+//    skips whitespace INCLUDING blank lines before the '@'/'>' and before the '+'; name = first token of
+//    the rest of the header line, second token = optional -> "XO:Z:<optional>"; bases = next line verbatim;
+//    '@' records: '+' line, then the error line verbatim; '>' records: errors = bases; N -> Z in bases when a
+//    third argument is given; records with an empty bases line print nothing; flags 77 / 141.  The loop ends
+//    at the first file that has no further record.
+// Deliberate deviation: where the reference's stream state makes it silently reuse the previous line's
+// fields (fewer than 11 fields, non-numeric flag, truncated FASTQ record, bases or errors holding interior
+// whitespace) or print SEQ and QUAL of different lengths, the ingest reports SMASH_ERR_DATA instead.
+//
+// Everything here is __host__ __device__: tests/emul runs the same functions on the host.
+#pragma once
+#include "core.cuh"
+
+namespace smash {
+
+enum IngErr : uint32_t {
+  ING_OK = 0,
+  ING_FEW_FIELDS = 1,     // SAM line with fewer than 11 fields
+  ING_BAD_FLAG = 2,       // flag field does not start with an unsigned integer that fits 32 bits
+  ING_LEN_MISMATCH = 3,   // SEQ and QUAL lengths differ
+  ING_FQ_AT = 4,          // "Fastq @ parse error" (fastqs_to_sam.cpp:73-75)
+  ING_FQ_PLUS = 5,        // "Fastq + parse error" (fastqs_to_sam.cpp:70-72)
+  ING_FQ_NAME = 6,        // "Problem reading read name" (fastqs_to_sam.cpp:56-57)
+  ING_FQ_TRUNC = 7,       // record cut short by the end of the file
+  ING_FQ_COLUMNS = 8,     // bases / errors line is not exactly one token: the SAM columns would shift
+  ING_TOO_LONG = 9        // a field longer than 2^31 bytes
+};
+
+enum { ING_EMIT = 1, ING_OPT_SAM = 2, ING_OPT_XO = 4, ING_N2Z = 8 };
+
+// One input line (SAM) or one FASTQ record, located in its source text.
+struct LineRec {
+  uint64_t name_pos, seq_pos, qual_pos, opt_pos;   // byte offsets into text[src]
+  uint32_t name_len, seq_len;
+  uint32_t opt_len;        // bytes this read adds to the batch's `opt` blob
+  uint32_t opt_src_len;    // ING_OPT_SAM: source bytes from opt_pos-1 (the separator) to the end of the line;
+                           // ING_OPT_XO: length of the header's second token
+  uint16_t read_flag;      // 0 / 65 / 129
+  uint8_t src;             // which text (0: SAM text or FASTQ mate 1, 1: FASTQ mate 2)
+  uint8_t bits;            // ING_EMIT | ING_OPT_* | ING_N2Z
+  uint32_t err;            // IngErr
+};
+
+// what the scan adds up per record: reads emitted, name / seq / opt bytes
+struct Ing4 { uint64_t reads, name, seq, opt; };
+HD Ing4 ing4_add(const Ing4 &a, const Ing4 &b) { return Ing4{a.reads + b.reads, a.name + b.name, a.seq + b.seq, a.opt + b.opt}; }
+HD Ing4 ing4_of(const LineRec &r) {
+  if (!(r.bits & ING_EMIT)) return Ing4{0, 0, 0, 0};
+  return Ing4{1, r.name_len, r.seq_len, r.opt_len};
+}
+
+// C-locale isspace: what `operator>>` skips and what ends a token
+HD bool ing_space(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }
+
+// ---- lines ------------------------------------------------------------------------------------
+// A line starts at 0 and after every '\n' that is not the last byte.  Line starts are counted per 16-byte
+// chunk of the text; a start is attributed to the chunk that holds the newline BEFORE it (the first
+// line to chunk 0), which keeps them in order.
+HD uint32_t ing_chunk_starts(const uint8_t *b16, uint64_t base, uint64_t n) {
+  uint32_t c = (base == 0 && n > 0) ? 1u : 0u;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c += (base + (uint64_t)i + 1 < n && b16[i] == '\n') ? 1u : 0u;
+  return c;
+}
+// content of line j = [ls[j], ing_line_end(ls, j)); ls[n_lines] is a sentinel placed one past the
+// (possibly absent) newline of the last line
+HD uint64_t ing_line_end(const uint64_t *ls, uint64_t j) { return ls[j + 1] - 1; }
+HD uint64_t ing_sentinel(const uint8_t *text, uint64_t n) { return n == 0 ? 1 : (text[n - 1] == '\n' ? n : n + 1); }
+
+// ---- SAM line (query.cpp:639-648 + 185-201) ------------------------------------------------------
+HD void ing_name_flag(const uint8_t *t, LineRec &r, uint32_t flag) {
+  if (flag & 64) r.read_flag = 65;                       // name + ":0" -> stripped again
+  else if (flag & 128) r.read_flag = 129;
+  else {
+    r.read_flag = 0;
+    if (r.name_len >= 2 && t[r.name_pos + r.name_len - 2] == ':') {
+      const uint8_t c = t[r.name_pos + r.name_len - 1];
+      if (c == '0') { r.name_len -= 2; r.read_flag = 65; }
+      else if (c == '1') { r.name_len -= 2; r.read_flag = 129; }
+    }
+  }
+}
+
+HDN inline void ing_parse_sam_line(const uint8_t *t, uint64_t b, uint64_t e, LineRec &r) {
+  r = LineRec{};
+  if (e <= b) return;                                     // empty line: skipped (query.cpp:627)
+  r.bits = ING_EMIT;
+  uint64_t i = b;
+#define ING_SKIP_WS() while (i < e && ing_space(t[i])) ++i
+#define ING_TOKEN() while (i < e && !ing_space(t[i])) ++i
+  ING_SKIP_WS();
+  if (i == e) { r.err = ING_FEW_FIELDS; return; }
+  r.name_pos = i;
+  ING_TOKEN();
+  if (i - r.name_pos > 0x7fffffffull) { r.err = ING_TOO_LONG; return; }
+  r.name_len = (uint32_t)(i - r.name_pos);
+  // flag: [+-]digits (num_get for unsigned, base 10); stops at the first non-digit
+  ING_SKIP_WS();
+  if (i == e) { r.err = ING_FEW_FIELDS; return; }
+  bool neg = false;
+  if (t[i] == '+' || t[i] == '-') { neg = t[i] == '-'; ++i; }
+  uint64_t v = 0; int digits = 0; bool over = false;
+  while (i < e && t[i] >= '0' && t[i] <= '9') {
+    v = v * 10 + (uint64_t)(t[i] - '0');
+    if (v > 0xffffffffull) { over = true; v = 0xffffffffull; }
+    ++digits; ++i;
+  }
+  if (!digits || over) { r.err = ING_BAD_FLAG; return; }
+  const uint32_t flag = neg ? (uint32_t)(0u - (uint32_t)v) : (uint32_t)v;
+  // seven ignored fields; whatever followed the digits inside the flag token is the first of them
+  for (int k = 0; k < 7; ++k) {
+    ING_SKIP_WS();
+    if (i == e) { r.err = ING_FEW_FIELDS; return; }
+    ING_TOKEN();
+  }
+  ING_SKIP_WS();
+  if (i == e) { r.err = ING_FEW_FIELDS; return; }
+  r.seq_pos = i;
+  ING_TOKEN();
+  const uint64_t sl = i - r.seq_pos;
+  ING_SKIP_WS();
+  if (i == e) { r.err = ING_FEW_FIELDS; return; }
+  r.qual_pos = i;
+  ING_TOKEN();
+  const uint64_t ql = i - r.qual_pos;
+  if (sl > 0x7fffffffull) { r.err = ING_TOO_LONG; return; }
+  if (sl != ql) { r.err = ING_LEN_MISMATCH; return; }
+  r.seq_len = (uint32_t)sl;
+  // optional fields: "\t" + token for every further token
+  const uint64_t sep = i;                                  // the separator before the first optional token (or e)
+  uint64_t ol = 0;
+  for (;;) {
+    ING_SKIP_WS();
+    if (i == e) break;
+    if (!ol) r.opt_pos = i;
+    const uint64_t s = i;
+    ING_TOKEN();
+    ol += 1 + (i - s);
+  }
+#undef ING_SKIP_WS
+#undef ING_TOKEN
+  if (ol) {
+    if (ol > 0x7fffffffull || e - sep > 0x7fffffffull) { r.err = ING_TOO_LONG; return; }
+    r.bits |= ING_OPT_SAM;
+    r.opt_len = (uint32_t)ol;
+    r.opt_src_len = (uint32_t)(e - (r.opt_pos - 1));      // from the whitespace byte before the first token
+  }
+  ing_name_flag(t, r, flag);
+}
+
+// Optional-field text of a SAM line: source byte i of [opt_pos-1, line end) -> output byte, or -1 for none.
+// Token bytes pass through; the LAST whitespace byte before a token becomes the single '\t'.
+HD int ing_opt_char(const uint8_t *t, uint64_t i, uint64_t e) {
+  const uint8_t c = t[i];
+  if (!ing_space(c)) return c;
+  return (i + 1 < e && !ing_space(t[i + 1])) ? '\t' : -1;
+}
+
+// ---- FASTQ (fastqs_to_sam.cpp:47-95) ---------------------------------------------------------------
+// The reader is a 6-state machine over LINES; a line's effect on the state depends only on whether it is
+// blank (whitespace only) and on its first non-blank byte, so the state before every line follows from an
+// exclusive scan of per-line transition functions under composition.
+enum { FQ_H = 0, FQ_BA = 1, FQ_BG = 2, FQ_P = 3, FQ_Q = 4, FQ_E = 5 };   // expect: header, bases ('@'), bases ('>'), plus, errors; error
+constexpr uint32_t FQ_IDENT = 0u | (1u << 3) | (2u << 6) | (3u << 9) | (4u << 12) | (5u << 15);
+HD uint32_t fq_pack(int h, int ba, int bg, int p, int q, int e) {
+  return (uint32_t)h | ((uint32_t)ba << 3) | ((uint32_t)bg << 6) | ((uint32_t)p << 9) | ((uint32_t)q << 12) | ((uint32_t)e << 15);
+}
+HD int fq_apply(uint32_t f, int s) { return (int)((f >> (3 * s)) & 7u); }
+HD uint32_t fq_compose(uint32_t f, uint32_t g) {             // first f, then g
+  uint32_t h = 0;
+#pragma unroll
+  for (int s = 0; s < 6; ++s) h |= (uint32_t)fq_apply(g, fq_apply(f, s)) << (3 * s);
+  return h;
+}
+// first non-blank byte of the line, or -1 when the line is blank
+HD int ing_first_char(const uint8_t *t, uint64_t b, uint64_t e) {
+  for (uint64_t i = b; i < e; ++i) if (!ing_space(t[i])) return t[i];
+  return -1;
+}
+HD uint32_t fq_line_fn(int first) {
+  //                         H      BA    BG    P     Q     E
+  if (first < 0) return fq_pack(FQ_H, FQ_P, FQ_H, FQ_P, FQ_H, FQ_E);            // blank: skipped where `>> ch` reads
+  if (first == '@') return fq_pack(FQ_BA, FQ_P, FQ_H, FQ_E, FQ_H, FQ_E);
+  if (first == '>') return fq_pack(FQ_BG, FQ_P, FQ_H, FQ_E, FQ_H, FQ_E);
+  if (first == '+') return fq_pack(FQ_E, FQ_P, FQ_H, FQ_Q, FQ_H, FQ_E);
+  return fq_pack(FQ_E, FQ_P, FQ_H, FQ_E, FQ_H, FQ_E);
+}
+
+// exactly one token on [b,e) (leading / trailing whitespace, e.g. '\r', allowed): its position and length
+HD bool ing_single_token(const uint8_t *t, uint64_t b, uint64_t e, uint64_t *pos, uint64_t *len) {
+  uint64_t i = b;
+  while (i < e && ing_space(t[i])) ++i;
+  if (i == e) return false;
+  *pos = i;
+  while (i < e && !ing_space(t[i])) ++i;
+  *len = i - *pos;
+  while (i < e && ing_space(t[i])) ++i;
+  return i == e;
+}
+
+// Record whose header is line j of this file (ls: line starts with sentinel, n_lines lines).
+HDN inline void ing_parse_fastq_record(const uint8_t *t, const uint64_t *ls, uint64_t n_lines, uint64_t j, int file,
+                                       int replace_n, LineRec &r) {
+  r = LineRec{};
+  r.src = (uint8_t)file;
+  r.read_flag = file ? 129 : 65;                           // flags 77 / 141 (fastqs_to_sam.cpp:78), query.cpp:643-644
+  uint64_t i = ls[j];
+  const uint64_t e = ing_line_end(ls, j);
+  while (i < e && ing_space(t[i])) ++i;
+  const uint8_t amp = t[i];                                // the caller guarantees a non-blank line
+  ++i;
+  while (i < e && ing_space(t[i])) ++i;
+  if (i == e) { r.err = ING_FQ_NAME; return; }
+  r.name_pos = i;
+  while (i < e && !ing_space(t[i])) ++i;
+  if (i - r.name_pos > 0x7fffffffull) { r.err = ING_TOO_LONG; return; }
+  r.name_len = (uint32_t)(i - r.name_pos);
+  while (i < e && ing_space(t[i])) ++i;
+  if (i < e) {                                             // second token -> "\tXO:Z:" + token
+    r.opt_pos = i;
+    while (i < e && !ing_space(t[i])) ++i;
+    if (i - r.opt_pos > 0x7ffffff0ull) { r.err = ING_TOO_LONG; return; }
+    r.opt_src_len = (uint32_t)(i - r.opt_pos);
+    r.opt_len = r.opt_src_len + 6;
+    r.bits |= ING_OPT_XO;
+  }
+  if (j + 1 >= n_lines) { r.err = ING_FQ_TRUNC; return; }
+  const uint64_t bb = ls[j + 1], be = ing_line_end(ls, j + 1);
+  const bool printed = be > bb;                            // `if (bases.size())`, fastqs_to_sam.cpp:76
+  uint64_t sp = 0, sl = 0, qp = 0, ql = 0;
+  if (printed && !ing_single_token(t, bb, be, &sp, &sl)) { r.err = ING_FQ_COLUMNS; return; }
+  if (amp == '@') {
+    uint64_t p = j + 2;
+    while (p < n_lines && ing_first_char(t, ls[p], ing_line_end(ls, p)) < 0) ++p;
+    if (p >= n_lines) { r.err = ING_FQ_TRUNC; return; }
+    if (ing_first_char(t, ls[p], ing_line_end(ls, p)) != '+') { r.err = ING_FQ_PLUS; return; }
+    if (p + 1 >= n_lines) { r.err = ING_FQ_TRUNC; return; }
+    if (printed && !ing_single_token(t, ls[p + 1], ing_line_end(ls, p + 1), &qp, &ql)) { r.err = ING_FQ_COLUMNS; return; }
+  } else if (amp == '>') {
+    qp = sp; ql = sl;                                      // errors = bases, before the N -> Z replacement
+  } else {
+    r.err = ING_FQ_AT; return;
+  }
+  if (!printed) { r.opt_len = 0; r.bits = 0; return; }
+  if (sl > 0x7fffffffull) { r.err = ING_TOO_LONG; return; }
+  if (sl != ql) { r.err = ING_LEN_MISMATCH; return; }
+  r.seq_pos = sp; r.seq_len = (uint32_t)sl; r.qual_pos = qp;
+  r.bits |= ING_EMIT;
+  if (replace_n) r.bits |= ING_N2Z;
+}
+
+// how many records of each file the reference's loop prints from (fastqs_to_sam.cpp:47-53): it stops at the
+// first file without a further record.  final = 0: the last record of either text may be cut, keep pairs only.
+HD void ing_fastq_take(uint64_t r1, uint64_t r2, int final, uint64_t *n1, uint64_t *n2) {
+  if (!final) {
+    r1 = r1 ? r1 - 1 : 0; r2 = r2 ? r2 - 1 : 0;
+    const uint64_t n = r1 < r2 ? r1 : r2;
+    *n1 = n; *n2 = n;
+    return;
+  }
+  *n1 = r1 < r2 + 1 ? r1 : r2 + 1;
+  *n2 = r2 < *n1 ? r2 : *n1;
+}
+
+}  // namespace smash

@@ -62,3 +62,47 @@ class EmulIndex:
                                     _p(moff), _p(mt), C.c_uint64(mcap), C.byref(err))
         assert need <= cap and moff[-1] <= mcap
         return out[:need].tobytes(), moff, mt[:3 * moff[-1]].reshape(-1, 3), err.value
+
+
+# ---- device-side input stage (smash_paper_b200/csrc/ingest.cu) ----------------------------------------
+_ING = None
+
+
+def ingest_lib():
+    global _ING
+    if _ING is None:
+        so = os.path.join(HERE, "libemul_ingest.so")
+        src = os.path.join(HERE, "emul_ingest.cpp")
+        deps = [src] + [os.path.join(HERE, "../../smash_paper_b200/csrc", f) for f in ("core.cuh", "ingest.cuh")]
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src])
+        _ING = C.CDLL(so)
+    return _ING
+
+
+class IngestError(Exception):
+    def __init__(self, code, index):
+        super().__init__(f"ingest error {code} at record {index}")
+        self.code, self.index = code, index
+
+
+def ingest(kind, text0, text1=b"", final=True, replace_n=False):
+    """Emulated smash_text_upload: dict of the packed batch arrays + consumed bytes."""
+    n0, n1 = len(text0), len(text1)
+    a0 = np.frombuffer(text0 + b"\0", dtype=np.uint8)
+    a1 = np.frombuffer(text1 + b"\0", dtype=np.uint8)
+    cap = n0 + n1 + 64
+    nl = text0.count(b"\n") + text1.count(b"\n") + 4
+    names = np.zeros(cap, np.uint8); seq = np.zeros(cap, np.uint8); qual = np.zeros(cap, np.uint8); opt = np.zeros(cap, np.uint8)
+    name_off = np.zeros(nl, np.int64); seq_off = np.zeros(nl, np.int64); opt_off = np.zeros(nl, np.int64)
+    rf = np.zeros(nl, np.uint16)
+    info = np.zeros(6, np.uint64)
+    err_index = C.c_uint64(0)
+    rc = ingest_lib().emul_ingest(int(kind), int(final), int(replace_n), _p(a0), C.c_uint64(n0), _p(a1), C.c_uint64(n1),
+                                  _p(names), _p(name_off), _p(seq), _p(qual), _p(seq_off), _p(opt), _p(opt_off), _p(rf),
+                                  _p(info), C.byref(err_index))
+    if rc:
+        raise IngestError(rc, err_index.value)
+    n, nb, sb, ob = (int(x) for x in info[:4])
+    return dict(n=n, names=names[:nb], name_off=name_off[:n + 1], seq=seq[:sb], qual=qual[:sb], seq_off=seq_off[:n + 1],
+                opt=opt[:ob], opt_off=opt_off[:n + 1], read_flag=rf[:n], consumed=(int(info[4]), int(info[5])))

@@ -1,0 +1,149 @@
+// tests/emul/emul_ingest.cpp -- TEST INFRASTRUCTURE ONLY.
+// Host-side emulation of the device-side input stage (smash_paper_b200/csrc/ingest.cu) built from the same
+// __host__ __device__ building blocks (ingest.cuh), stage by stage in the order the kernels run:
+// chunk line-start counts -> line starts -> [FASTQ: transition-function scan, header compaction] ->
+// LineRec per line/record -> Ing4 scan -> publish rule -> copy.  It lets the CPU test-suite check the
+// kernels' logic against oracle/ingest.py where no GPU exists.  Never linked into libsmash_b200.so.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../smash_paper_b200/csrc/ingest.cuh"
+
+using namespace smash;
+
+namespace {
+
+struct Lines { std::vector<uint64_t> ls; uint64_t n_lines = 0; };
+
+// k_ing_scan_tiles/top/apply with ChunkIn / LineStartOut
+Lines line_starts(const uint8_t *text, uint64_t n) {
+  Lines L;
+  if (!n) return L;
+  const uint64_t n_chunks = (n + 15) / 16;
+  std::vector<uint8_t> padded((size_t)n_chunks * 16 + 16, 0xAB);          // bytes past n are garbage on the device too
+  memcpy(padded.data(), text, n);
+  std::vector<uint64_t> cnt(n_chunks), pre(n_chunks + 1, 0);
+  for (uint64_t c = 0; c < n_chunks; ++c) cnt[c] = ing_chunk_starts(padded.data() + 16 * c, 16 * c, n);
+  for (uint64_t c = 0; c < n_chunks; ++c) pre[c + 1] = pre[c] + cnt[c];
+  L.n_lines = pre[n_chunks];
+  L.ls.assign(L.n_lines + 1, 0);
+  for (uint64_t c = 0; c < n_chunks; ++c) {
+    if (!cnt[c]) continue;
+    uint64_t idx = pre[c];
+    if (c == 0) L.ls[idx++] = 0;
+    for (int i = 0; i < 16; ++i)
+      if (16 * c + (uint64_t)i + 1 < n && padded[16 * c + i] == '\n') L.ls[idx++] = 16 * c + (uint64_t)i + 1;
+  }
+  L.ls[L.n_lines] = ing_sentinel(text, n);
+  return L;
+}
+
+// FsmIn/FsmOut + FlagIn/HdrOut
+std::vector<uint64_t> fastq_headers(const uint8_t *text, const Lines &L) {
+  std::vector<uint64_t> hdr;
+  uint32_t before = FQ_IDENT;
+  for (uint64_t j = 0; j < L.n_lines; ++j) {
+    const uint32_t fn = fq_line_fn(ing_first_char(text, L.ls[j], ing_line_end(L.ls.data(), j)));
+    if (fq_apply(before, FQ_H) == FQ_H && fq_apply(fn, FQ_H) != FQ_H) hdr.push_back(j);
+    before = fq_compose(before, fn);
+  }
+  return hdr;
+}
+
+}  // namespace
+
+extern "C" {
+
+// kind 0: SAM text (text1 ignored), 1: FASTQ pair.  Outputs are caller buffers sized generously
+// (names/seq/qual/opt: n0 + n1 bytes; offsets / read_flag: line count + 1).  Returns 0, or the IngErr code
+// with *err_index = record index.  out_info: n_reads, name_bytes, seq_bytes, opt_bytes, consumed0, consumed1.
+int emul_ingest(int kind, int final, int replace_n, const uint8_t *text0, uint64_t n0, const uint8_t *text1, uint64_t n1,
+                uint8_t *names, int64_t *name_off, uint8_t *seq, uint8_t *qual, int64_t *seq_off, uint8_t *opt, int64_t *opt_off,
+                uint16_t *read_flag, uint64_t *out_info, uint64_t *err_index) {
+  const uint8_t *text[2] = {text0, text1};
+  const uint64_t full[2] = {n0, kind ? n1 : 0};
+  uint64_t nb[2] = {n0, kind ? n1 : 0};
+  if (!final) for (int f = 0; f < 2; ++f) while (nb[f] && text[f][nb[f] - 1] != '\n') --nb[f];
+  Lines L[2];
+  std::vector<uint64_t> hdr[2];
+  uint64_t n_rec[2] = {0, 0}, n_take[2] = {0, 0};
+  for (int f = 0; f < (kind ? 2 : 1); ++f) L[f] = line_starts(text[f], nb[f]);
+  std::vector<LineRec> recs;
+  uint64_t m = 0;
+  if (kind) {
+    for (int f = 0; f < 2; ++f) { hdr[f] = fastq_headers(text[f], L[f]); n_rec[f] = hdr[f].size(); }
+    ing_fastq_take(n_rec[0], n_rec[1], final, &n_take[0], &n_take[1]);
+    m = n_take[0] + n_take[1];
+    recs.resize(m + 1);
+    for (int f = 0; f < 2; ++f)
+      for (uint64_t k = 0; k < n_take[f]; ++k)
+        ing_parse_fastq_record(text[f], L[f].ls.data(), L[f].n_lines, hdr[f][k], f, replace_n, recs[2 * k + f]);
+  } else {
+    n_rec[0] = L[0].n_lines;
+    m = L[0].n_lines;
+    recs.resize(m + 1);
+    for (uint64_t j = 0; j < m; ++j) ing_parse_sam_line(text[0], L[0].ls[j], ing_line_end(L[0].ls.data(), j), recs[j]);
+  }
+  uint64_t err = ~0ull;
+  for (uint64_t i = 0; i < m; ++i) if (recs[i].err) { const uint64_t v = (i << 8) | recs[i].err; if (v < err) err = v; }
+  // Ing4 scan
+  std::vector<Ing4> pre(m + 1);
+  Ing4 acc{0, 0, 0, 0};
+  for (uint64_t i = 0; i < m; ++i) { pre[i] = acc; acc = ing4_add(acc, ing4_of(recs[i])); }
+  pre[m] = acc;
+  // k_ing_publish
+  uint64_t mu = m;
+  Ing4 tot = pre[m];
+  if (m && !final && (tot.reads & 1ull)) {
+    uint64_t lo = 0, hi = m;
+    while (lo < hi) { const uint64_t mid = lo + (hi - lo) / 2; if (pre[mid + 1].reads >= tot.reads) hi = mid; else lo = mid + 1; }
+    mu = lo; tot = pre[mu];
+  }
+  uint64_t consumed[2] = {nb[0], nb[1]};
+  if (m) {
+    if (kind) {
+      const uint64_t take[2] = {(mu + 1) / 2, mu / 2};
+      for (int f = 0; f < 2; ++f) if (take[f] < n_rec[f]) consumed[f] = L[f].ls[hdr[f][take[f]]];
+    } else {
+      if (mu < n_rec[0]) consumed[0] = L[0].ls[mu];
+      consumed[1] = 0;
+    }
+  } else {
+    consumed[0] = final ? full[0] : 0; consumed[1] = final ? full[1] : 0;
+  }
+  if (final) { consumed[0] = full[0]; consumed[1] = full[1]; }
+  if (err != ~0ull) { *err_index = err >> 8; return (int)(err & 0xff); }
+  out_info[0] = tot.reads; out_info[1] = tot.name; out_info[2] = tot.seq; out_info[3] = tot.opt; out_info[4] = consumed[0]; out_info[5] = consumed[1];
+  // k_ing_copy
+  name_off[tot.reads] = (int64_t)tot.name; seq_off[tot.reads] = (int64_t)tot.seq; opt_off[tot.reads] = (int64_t)tot.opt;
+  for (uint64_t i = 0; i < mu; ++i) {
+    const LineRec &r = recs[i];
+    if (!(r.bits & ING_EMIT)) continue;
+    const Ing4 p = pre[i];
+    const uint8_t *t = text[r.src];
+    name_off[p.reads] = (int64_t)p.name; seq_off[p.reads] = (int64_t)p.seq; opt_off[p.reads] = (int64_t)p.opt; read_flag[p.reads] = r.read_flag;
+    for (uint32_t k = 0; k < r.name_len; ++k) names[p.name + k] = t[r.name_pos + k];
+    for (uint32_t k = 0; k < r.seq_len; ++k) {
+      uint8_t ch = t[r.seq_pos + k];
+      if ((r.bits & ING_N2Z) && ch == 'N') ch = 'Z';
+      seq[p.seq + k] = ch;
+      qual[p.seq + k] = t[r.qual_pos + k];
+    }
+    if (r.bits & ING_OPT_SAM) {
+      const uint64_t b = r.opt_pos - 1, e = b + r.opt_src_len;
+      uint64_t o = p.opt;
+      for (uint64_t k = b; k < e; ++k) { const int ch = ing_opt_char(t, k, e); if (ch >= 0) opt[o++] = (uint8_t)ch; }
+      if (o != p.opt + r.opt_len) return 100;                // internal: the size pass and the copy disagree
+    } else if (r.bits & ING_OPT_XO) {
+      const uint64_t lit = 0x3a5a3a4f5809ull;
+      for (int k = 0; k < 6; ++k) opt[p.opt + k] = (uint8_t)(lit >> (8 * k));
+      for (uint32_t k = 0; k < r.opt_src_len; ++k) opt[p.opt + 6 + k] = t[r.opt_pos + k];
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"
