@@ -353,11 +353,49 @@ def run_ours(args, wl, rank, world):
                 out["cpu_baseline"] = cpu_baseline(args, wl, ref, ref_files, sample_pairs=args.cpu_sample_pairs, steps=1)
             except Exception as e:  # noqa: BLE001 -- the baseline must never break the bench line
                 out["cpu_baseline"] = {"error": str(e)[:300]}
+    if out is not None and world == 1:
+        # input stage, measured last and on its own so that it can never disturb the numbers above
+        try:
+            out["ingest"] = measure_ingest(api, ctx, batches[args.warmup], peak if rank == 0 else 6650.0, steps=min(args.steps, 5))
+        except Exception as e:  # noqa: BLE001
+            out["ingest"] = {"error": str(e)[:300]}
     ctx.close()
     shutil.rmtree(workdir, ignore_errors=True)
     if dist:
         dist.destroy_process_group()
     return out
+
+
+def measure_ingest(api, ctx, batch, peak, steps):
+    """Raw SAM text (what fastqs_to_sam pipes into `mummer -samin`, smash_mapping.sh:19) of one batch, in pinned host
+    memory -> packed batch in HBM, parsed by ingest.cu.  wall = H2D copy + parse (host clock around the call);
+    device = CUDA events from the end of the copy to the end of k_ing_copy.  Algorithmic bytes per read: the text
+    once in, the batch (names, SEQ, QUAL, two 8-byte offsets, 2-byte flag) once out."""
+    text = synth.sam_text_fast(batch)
+    pin = api.PinnedArray(text.shape, np.uint8)
+    pin.array[...] = text
+    n = batch.n
+    for _ in range(2):
+        got, cons = ctx.text_upload(api.TEXT_SAM, pin.array)
+    parsed = ctx.fetch_batch(0)
+    exact = bool(got == n and cons[0] == text.size and np.array_equal(parsed.names, batch.names) and np.array_equal(parsed.seq, batch.seq)
+                 and np.array_equal(parsed.qual, batch.qual) and np.array_equal(parsed.seq_off, batch.seq_off)
+                 and np.array_equal(parsed.read_flag, api.read_flags_from_sam_flags(batch.flags)))
+    ctx.ingest_ms(reset=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ctx.text_upload(api.TEXT_SAM, pin.array)
+    wall_ms = (time.perf_counter() - t0) * 1e3 / steps
+    dev_ms = ctx.ingest_ms(reset=True) / steps
+    alg = text.size / n + (batch.names.size + 2 * batch.seq.size) / n + 18
+    gbs = n * alg / (dev_ms / 1e3) / 1e9 if dev_ms > 0 else 0.0
+    pin.free()
+    return {"what": "SAM text -> packed batch on the device (smash_text_upload), 1 batch", "reads_per_step": int(n), "steps": steps,
+            "text_bytes_per_read": text.size / n, "wall_ms_per_step": wall_ms, "device_ms_per_step": dev_ms,
+            "reads_per_s_wall": n / (wall_ms / 1e3), "reads_per_s_device": n / (dev_ms / 1e3) if dev_ms > 0 else None,
+            "alg_bytes_per_read": alg, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / peak if peak else None,
+            "matches_generated_batch": exact,
+            "note": "device time spans 3 host round trips (line count, totals) and 9 kernels; wall adds the H2D copy of the text"}
 
 
 def kernel_alg_bytes(wl, N, n_rec, sam_bytes, split=False):

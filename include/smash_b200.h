@@ -156,20 +156,22 @@ int smash_fetch_sam(smash_ctx *ctx, const char **sam, uint64_t *n_bytes);
  * Without SMASH_TEXT_FINAL the text is one chunk of a longer stream: only complete lines (FASTQ: complete
  * record pairs, less the last one, which may be cut) are taken, and an odd trailing read is left for the
  * next chunk so that the reader's pairing by arrival parity (query.cpp:629-637) is unchanged; `consumed`
- * says how many bytes of each text were used -- the caller passes the rest again, followed by more input.
+ * says how many bytes of each text were used -- the caller passes the rest again, followed by more input.  A chunk of
+ * a FASTQ pair may end after a mate-1 record: `mate2_first_next` is then 1 and the caller sets
+ * SMASH_TEXT_MATE2_FIRST on the next call, so that the alternation of the two files goes on where it stopped.
  * Input the reference would misparse silently (fewer than 11 SAM fields, a non-numeric flag, SEQ/QUAL of
  * different lengths, a truncated FASTQ record) fails with SMASH_ERR_DATA, the FASTQ '@' / '+' checks with
  * the reference's own messages.  The text buffers may be reused as soon as the call returns. */
 enum { SMASH_TEXT_SAM = 0, SMASH_TEXT_FASTQ_PAIR = 1 };
-enum { SMASH_TEXT_FINAL = 1, SMASH_TEXT_REPLACE_N = 2 };
+enum { SMASH_TEXT_FINAL = 1, SMASH_TEXT_REPLACE_N = 2, SMASH_TEXT_MATE2_FIRST = 4 };
 typedef struct {
   int kind;                      /* SMASH_TEXT_* */
-  int flags;                     /* SMASH_TEXT_FINAL | SMASH_TEXT_REPLACE_N */
+  int flags;                     /* SMASH_TEXT_FINAL | SMASH_TEXT_REPLACE_N | SMASH_TEXT_MATE2_FIRST */
   const char *text[2];           /* SAM: text[0]; FASTQ pair: mate-1 text, mate-2 text (host memory, pinned or not) */
   uint64_t n_bytes[2];
   uint64_t first_pair_ordinal;   /* as in smash_batch */
 } smash_text;
-typedef struct { uint64_t n_reads; uint64_t consumed[2]; } smash_text_info;
+typedef struct { uint64_t n_reads; uint64_t consumed[2]; int mate2_first_next; } smash_text_info;
 /* smash_submit with the batch parsed on the device; collect the result with smash_wait. */
 int smash_submit_text(smash_ctx *ctx, int slot, const smash_text *t, int want, smash_text_info *info);
 /* Device-resident variant (slot 0): parse only; run it with smash_map_resident. */
@@ -243,6 +245,9 @@ uint64_t smash_ctx_launch_count(const smash_ctx *ctx);
  * launching stream: [0] search, [1] records, [2] sizes+scan, [3] emit_text, [4] match CSR, [5] tail, [6] emit_copy,
  * [7] verify (k_mam_verify of the split search, 0 when candidates are verified inside k_mam_search). */
 void smash_ctx_stage_ms(smash_ctx *ctx, double *out8, int reset);
+/* Device milliseconds of the input stage (smash_submit_text / smash_text_upload) since the last reset: from the end of
+ * the text's H2D copy to the end of the kernel that writes the packed batch, CUDA events on the slot's stream. */
+double smash_ctx_ingest_ms(smash_ctx *ctx, int reset);
 /* Bytes of HBM held by the index on this ctx (text, SA, LCP, seed table, ...). */
 uint64_t smash_ctx_index_bytes(const smash_ctx *ctx);
 /* Raw CUDA stream (cudaStream_t) the ctx launches on, for external event timing. */

@@ -46,16 +46,16 @@ class _TailStats(C.Structure):
 
 
 class _Text(C.Structure):
-    _fields_ = [("kind", C.c_int), ("flags", C.c_int), ("text", C.c_char_p * 2), ("n_bytes", C.c_uint64 * 2),
+    _fields_ = [("kind", C.c_int), ("flags", C.c_int), ("text", C.c_void_p * 2), ("n_bytes", C.c_uint64 * 2),
                 ("first_pair_ordinal", C.c_uint64)]
 
 
 class _TextInfo(C.Structure):
-    _fields_ = [("n_reads", C.c_uint64), ("consumed", C.c_uint64 * 2)]
+    _fields_ = [("n_reads", C.c_uint64), ("consumed", C.c_uint64 * 2), ("mate2_first_next", C.c_int)]
 
 
 TEXT_SAM, TEXT_FASTQ_PAIR = 0, 1
-TEXT_FINAL, TEXT_REPLACE_N = 1, 2
+TEXT_FINAL, TEXT_REPLACE_N, TEXT_MATE2_FIRST = 1, 2, 4
 
 
 class DeviceBatch:
@@ -91,6 +91,7 @@ def load_library():
     L.smash_ctx_launch_count.restype = C.c_uint64
     L.smash_ctx_index_bytes.restype = C.c_uint64
     L.smash_ctx_stream.restype = C.c_void_p
+    L.smash_ctx_ingest_ms.restype = C.c_double
     L.smash_host_alloc.restype = C.c_void_p
     L.smash_host_alloc.argtypes = [C.c_size_t]
     L.smash_host_free.argtypes = [C.c_void_p]
@@ -335,28 +336,42 @@ class Context:
 
     # -- input side on the device (raw SAM text / FASTQ pair text in; ingest.cu) ------------------------
     @staticmethod
-    def _ctext(kind, text0, text1, final, replace_n, first_pair):
+    def _ctext(kind, text0, text1, final, replace_n, first_pair, mate2_first=False):
+        """text: bytes or a uint8 numpy array (e.g. PinnedArray.array); returns (struct, objects to keep alive)."""
         t = _Text()
         t.kind = kind
-        t.flags = (TEXT_FINAL if final else 0) | (TEXT_REPLACE_N if replace_n else 0)
-        t.text[0], t.text[1] = text0, (text1 if kind == TEXT_FASTQ_PAIR else None)
-        t.n_bytes[0], t.n_bytes[1] = len(text0), (len(text1) if kind == TEXT_FASTQ_PAIR else 0)
+        t.flags = (TEXT_FINAL if final else 0) | (TEXT_REPLACE_N if replace_n else 0) | (TEXT_MATE2_FIRST if mate2_first else 0)
+        keep = []
+        for f, x in enumerate((text0, text1 if kind == TEXT_FASTQ_PAIR else b"")):
+            if isinstance(x, np.ndarray):
+                x = np.ascontiguousarray(x, dtype=np.uint8)
+                t.text[f], t.n_bytes[f] = (x.ctypes.data if x.size else None), x.size
+            else:
+                x = bytes(x)
+                t.text[f], t.n_bytes[f] = (C.cast(C.c_char_p(x), C.c_void_p).value if len(x) else None), len(x)
+            keep.append(x)
         t.first_pair_ordinal = first_pair
-        return t
+        return t, keep
 
-    def text_upload(self, kind, text0, text1=b"", final=True, replace_n=False, first_pair=0):
-        """Parse raw text on the GPU into slot 0's resident batch -> (n_reads, (consumed0, consumed1))."""
-        t = self._ctext(kind, bytes(text0), bytes(text1), final, replace_n, first_pair)
+    def text_upload(self, kind, text0, text1=b"", final=True, replace_n=False, first_pair=0, mate2_first=False):
+        """Parse raw text on the GPU into slot 0's resident batch -> (n_reads, (consumed0, consumed1)).
+        self.mate2_first_next: pass it as mate2_first with the next chunk of a FASTQ pair stream."""
+        t, keep = self._ctext(kind, text0, text1, final, replace_n, first_pair, mate2_first)
         info = _TextInfo()
         _check(load_library().smash_text_upload(self.h, C.byref(t), C.byref(info)))
+        self.mate2_first_next = bool(info.mate2_first_next)
         return int(info.n_reads), (int(info.consumed[0]), int(info.consumed[1]))
 
-    def submit_text(self, slot, kind, text0, text1=b"", final=True, replace_n=False, first_pair=0, want=WANT_SAM):
-        t = self._ctext(kind, bytes(text0), bytes(text1), final, replace_n, first_pair)
+    def submit_text(self, slot, kind, text0, text1=b"", final=True, replace_n=False, first_pair=0, want=WANT_SAM, mate2_first=False):
+        t, keep = self._ctext(kind, text0, text1, final, replace_n, first_pair, mate2_first)
         info = _TextInfo()
         _check(load_library().smash_submit_text(self.h, slot, C.byref(t), want, C.byref(info)))
-        self._inflight[slot] = (None, None, t, want)
+        self.mate2_first_next = bool(info.mate2_first_next)
+        self._inflight[slot] = (keep, None, t, want)
         return int(info.n_reads), (int(info.consumed[0]), int(info.consumed[1]))
+
+    def ingest_ms(self, reset=False):
+        return float(load_library().smash_ctx_ingest_ms(self.h, int(reset)))
 
     def fetch_batch(self, slot=0):
         L = load_library()

@@ -254,6 +254,7 @@ struct Slot {
   DBuf<unsigned long long> ing_scal;      // [0] first error, [1..2] FASTQ records per text
   HBuf<uint64_t> h_ing;
   uint64_t name_bytes = 0, seq_bytes = 0, opt_bytes = 0;   // sizes of the batch blobs on the device
+  cudaEvent_t ev_ing0 = nullptr, ev_ing1 = nullptr; bool ing_timed = false;   // device time of the input stage (after the H2D copy)
   // results on host
   HBuf<char> h_sam; HBuf<int64_t> h_csr_off; HBuf<smash_match> h_matches; HBuf<uint64_t> h_small;
   // in flight
@@ -278,6 +279,7 @@ struct smash_ctx {
   uint64_t index_bytes = 0;
   uint64_t launches = 0;
   double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // search, records, sizes+scan, emit_text, csr, tail, emit_copy, verify
+  double ingest_ms = 0;                            // device-side input stage (smash_submit_text / smash_text_upload)
   Slot slot[SMASH_N_SLOTS];
   TailState tail;
 };
@@ -581,6 +583,8 @@ static void slot_release(Slot &s) {
   for (int f = 0; f < 2; ++f) { s.ing_raw[f].release(); s.ing_ls[f].release(); s.ing_hdr[f].release(); }
   s.ing_hdr_flag.release(); s.ing_blk64.release(); s.ing_blk32.release(); s.ing_blk4.release(); s.ing_pre.release();
   s.ing_recs.release(); s.ing_scal.release(); s.h_ing.release();
+  if (s.ev_ing0) cudaEventDestroy(s.ev_ing0);
+  if (s.ev_ing1) cudaEventDestroy(s.ev_ing1);
   if (s.ev0) cudaEventDestroy(s.ev0);
   if (s.ev1) cudaEventDestroy(s.ev1);
   for (int e = 0; e < N_EVS; ++e) if (s.evs[e]) cudaEventDestroy(s.evs[e]);
@@ -902,9 +906,18 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
   return 0;
 }
 
+// device time of the input stage; call after the slot's stream has been synchronised
+static void ingest_collect(smash_ctx *c, Slot &s) {
+  if (!s.ing_timed) return;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, s.ev_ing0, s.ev_ing1) == cudaSuccess) c->ingest_ms += ms; else cudaGetLastError();
+  s.ing_timed = false;
+}
+
 static int slot_finish(smash_ctx *c, Slot &s, smash_result *res) {
   CU(cudaStreamSynchronize(s.st));
   CU(cudaGetLastError());
+  ingest_collect(c, s);
   if (s.n_reads) {
     cudaEvent_t prev = s.ev0;
     for (int e = 0; e < s.n_evs; ++e) { float ms = 0; if (s.ev_stage[e] >= 0 && cudaEventElapsedTime(&ms, prev, s.evs[e]) == cudaSuccess) c->stage_ms[s.ev_stage[e]] += ms; prev = s.evs[e]; }
@@ -954,6 +967,7 @@ static int ingest_text(smash_ctx *c, Slot &s, const smash_text *t, smash_text_in
   const bool fastq = t->kind == SMASH_TEXT_FASTQ_PAIR;
   const int final = (t->flags & SMASH_TEXT_FINAL) ? 1 : 0;
   const int n_text = fastq ? 2 : 1;
+  const int phase = (fastq && (t->flags & SMASH_TEXT_MATE2_FIRST)) ? 1 : 0;
   cudaStream_t st = s.st;
   int rc;
   uint64_t nb[2] = {0, 0};
@@ -964,7 +978,7 @@ static int ingest_text(smash_ctx *c, Slot &s, const smash_text *t, smash_text_in
       while (nb[f] && t->text[f][nb[f] - 1] != '\n') --nb[f];
     }
   }
-  if (info) { info->n_reads = 0; info->consumed[0] = info->consumed[1] = 0; }
+  if (info) { info->n_reads = 0; info->consumed[0] = info->consumed[1] = 0; info->mate2_first_next = phase; }
   s.first_pair = t->first_pair_ordinal;
   if ((rc = s.h_ing.ensure(16)) || (rc = s.ing_scal.ensure(4))) return rc;
   uint64_t n_lines[2] = {0, 0};
@@ -976,6 +990,12 @@ static int ingest_text(smash_ctx *c, Slot &s, const smash_text *t, smash_text_in
     if (!nb[f]) continue;
     if ((rc = s.ing_raw[f].ensure(nb[f] + 64))) return rc;
     CU(cudaMemcpyAsync(s.ing_raw[f].p, t->text[f], nb[f], cudaMemcpyHostToDevice, st));
+  }
+  if (!s.ev_ing0) { CU(cudaEventCreate(&s.ev_ing0)); CU(cudaEventCreate(&s.ev_ing1)); }
+  CU(cudaEventRecord(s.ev_ing0, st));
+  s.ing_timed = false;
+  for (int f = 0; f < n_text; ++f) {
+    if (!nb[f]) continue;
     c->launches += launch_ing_count_lines(s.ing_raw[f].p, nb[f], blk_lines[f], st);
     CU(cudaMemcpyAsync(s.h_ing.p + 8 + f, blk_lines[f] + tiles[f], 8, cudaMemcpyDeviceToHost, st));
   }
@@ -1003,7 +1023,7 @@ static int ingest_text(smash_ctx *c, Slot &s, const smash_text *t, smash_text_in
     CU(cudaMemcpyAsync(s.h_ing.p + 10, s.ing_scal.p + 1, 16, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     n_rec[0] = s.h_ing.p[10]; n_rec[1] = s.h_ing.p[11];
-    ing_fastq_take(n_rec[0], n_rec[1], final, &n_take[0], &n_take[1]);
+    ing_fastq_take(n_rec[phase], n_rec[phase ^ 1], final, &n_take[phase], &n_take[phase ^ 1]);
     m = n_take[0] + n_take[1];
   } else {
     m = n_lines[0];
@@ -1015,14 +1035,14 @@ static int ingest_text(smash_ctx *c, Slot &s, const smash_text *t, smash_text_in
     if (fastq) {
       const int replace_n = (t->flags & SMASH_TEXT_REPLACE_N) ? 1 : 0;
       for (int f = 0; f < 2; ++f)
-        c->launches += launch_ing_parse_fastq(s.ing_raw[f].p, s.ing_ls[f].p, n_lines[f], s.ing_hdr[f].p, n_take[f], f, replace_n, s.ing_recs.p,
-                                              s.ing_scal.p, st);
+        c->launches += launch_ing_parse_fastq(s.ing_raw[f].p, s.ing_ls[f].p, n_lines[f], s.ing_hdr[f].p, n_take[f], f, phase, replace_n,
+                                              s.ing_recs.p, s.ing_scal.p, st);
     } else {
       c->launches += launch_ing_parse_sam(s.ing_raw[0].p, s.ing_ls[0].p, n_lines[0], s.ing_recs.p, s.ing_scal.p, st);
     }
     c->launches += launch_ing_scan_recs(s.ing_recs.p, m, s.ing_blk4.p, s.ing_pre.p, st);
     IngPublish pb{};
-    pb.pre = s.ing_pre.p; pb.m = m; pb.final = final; pb.fastq = fastq ? 1 : 0;
+    pb.pre = s.ing_pre.p; pb.m = m; pb.final = final; pb.fastq = fastq ? 1 : 0; pb.phase = phase;
     for (int f = 0; f < 2; ++f) { pb.ls[f] = s.ing_ls[f].p; pb.hdr[f] = s.ing_hdr[f].p; pb.n_rec[f] = n_rec[f]; pb.n_bytes[f] = nb[f]; }
     pb.err = s.ing_scal.p; pb.host = s.h_ing.p;
     c->launches += launch_ing_publish(pb, st);
@@ -1031,11 +1051,11 @@ static int ingest_text(smash_ctx *c, Slot &s, const smash_text *t, smash_text_in
     if (err != ~0ull) {
       const uint32_t code = (uint32_t)(err & 0xff);
       const uint64_t idx = err >> 8;
-      if (fastq) return fail(SMASH_ERR_DATA, "%s (record %llu of mate file %d)", ing_err_text(code), (unsigned long long)(idx / 2 + 1), (int)(idx & 1) + 1);
+      if (fastq) return fail(SMASH_ERR_DATA, "%s (record %llu of mate file %d in this chunk)", ing_err_text(code), (unsigned long long)(idx / 2 + 1), (int)((idx & 1) ^ phase) + 1);
       return fail(SMASH_ERR_DATA, "%s (input line %llu of this chunk)", ing_err_text(code), (unsigned long long)(idx + 1));
     }
     n_reads = s.h_ing.p[0]; name_bytes = s.h_ing.p[1]; seq_bytes = s.h_ing.p[2]; opt_bytes = s.h_ing.p[3]; m_used = s.h_ing.p[4];
-    if (info) { info->consumed[0] = s.h_ing.p[5]; info->consumed[1] = s.h_ing.p[6]; }
+    if (info) { info->consumed[0] = s.h_ing.p[5]; info->consumed[1] = s.h_ing.p[6]; info->mate2_first_next = (int)s.h_ing.p[12]; }
   } else if (info) {
     // nothing to parse: a final call consumes what is left, a non-final one waits for more input
     info->consumed[0] = final ? t->n_bytes[0] : 0; info->consumed[1] = (final && fastq) ? t->n_bytes[1] : 0;
@@ -1050,6 +1070,8 @@ static int ingest_text(smash_ctx *c, Slot &s, const smash_text *t, smash_text_in
     cp.opt = opt_bytes ? s.opt.p : nullptr; cp.opt_off = opt_bytes ? s.opt_off.p : nullptr; cp.read_flag = s.read_flag.p;
     c->launches += launch_ing_copy(cp, st);
   }
+  CU(cudaEventRecord(s.ev_ing1, st));
+  s.ing_timed = true;
   if (info) info->n_reads = n_reads;
   return 0;
 }
@@ -1077,7 +1099,14 @@ extern "C" int smash_text_upload(smash_ctx *c, const smash_text *t, smash_text_i
   if (rc) return rc;
   CU(cudaStreamSynchronize(s.st));
   CU(cudaGetLastError());
+  ingest_collect(c, s);
   return 0;
+}
+extern "C" double smash_ctx_ingest_ms(smash_ctx *c, int reset) {
+  if (!c) return 0.0;
+  const double v = c->ingest_ms;
+  if (reset) c->ingest_ms = 0;
+  return v;
 }
 extern "C" int smash_batch_sizes(smash_ctx *c, int slot, uint64_t *n_reads, uint64_t *name_bytes, uint64_t *seq_bytes, uint64_t *opt_bytes) {
   if (!c || slot < 0 || slot >= SMASH_N_SLOTS) return fail(SMASH_ERR_ARG, "bad argument");

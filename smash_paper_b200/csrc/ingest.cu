@@ -24,6 +24,17 @@ constexpr int IT = IB * II;        // items per tile
 
 uint64_t ing_tiles(uint64_t n) { return (n + IT - 1) / IT; }
 
+// every launch goes through here (the CPU test-suite substitutes a host executor, tests/emul/cuda_shim)
+template <class... KArgs, class... Args>
+static void ing_launch(void (*k)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
+#if defined(__CUDACC__)
+  k<<<grid, block, 0, st>>>(args...);
+#else
+  (void)st;
+  shim_launch(k, grid, block, args...);
+#endif
+}
+
 // ---- generic tiled scan: V value type, In(i) -> V, Op(a, b) = "a then b" (associative), Out(i, prefix, v) ----
 __device__ __forceinline__ uint32_t shfl_up_v(uint32_t v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 __device__ __forceinline__ uint64_t shfl_up_v(uint64_t v, int d) { return __shfl_up_sync(0xffffffffu, (unsigned long long)v, d); }
@@ -121,9 +132,9 @@ __global__ void __launch_bounds__(IB) k_ing_scan_apply(In in, uint64_t n, const 
 template <class V, class In, class Op, class Out>
 static int scan3(In in, uint64_t n, V *blk, Op op, V ident, Out out, cudaStream_t st) {
   const unsigned n_blk = (unsigned)ing_tiles(n);
-  k_ing_scan_tiles<V, In, Op><<<n_blk, IB, 0, st>>>(in, n, blk, op, ident);
-  k_ing_scan_top<V, Op><<<1, IB, 0, st>>>(blk, n_blk, op, ident);
-  k_ing_scan_apply<V, In, Op, Out><<<n_blk, IB, 0, st>>>(in, n, blk, op, ident, out);
+  ing_launch(k_ing_scan_tiles<V, In, Op>, n_blk, IB, st, in, n, blk, op, ident);
+  ing_launch(k_ing_scan_top<V, Op>, 1, IB, st, blk, n_blk, op, ident);
+  ing_launch(k_ing_scan_apply<V, In, Op, Out>, n_blk, IB, st, in, n, blk, op, ident, out);
   return 3;
 }
 
@@ -156,14 +167,14 @@ struct LineStartOut {
 int launch_ing_count_lines(const uint8_t *text, uint64_t n, uint64_t *blk, cudaStream_t st) {
   const uint64_t n_chunks = (n + 15) / 16;
   const unsigned n_blk = (unsigned)ing_tiles(n_chunks);
-  k_ing_scan_tiles<uint64_t, ChunkIn, OpAdd64><<<n_blk, IB, 0, st>>>(ChunkIn{text, n}, n_chunks, blk, OpAdd64(), 0ull);
-  k_ing_scan_top<uint64_t, OpAdd64><<<1, IB, 0, st>>>(blk, n_blk, OpAdd64(), 0ull);
+  ing_launch(k_ing_scan_tiles<uint64_t, ChunkIn, OpAdd64>, n_blk, IB, st, ChunkIn{text, n}, n_chunks, blk, OpAdd64(), 0ull);
+  ing_launch(k_ing_scan_top<uint64_t, OpAdd64>, 1, IB, st, blk, n_blk, OpAdd64(), 0ull);
   return 2;
 }
 int launch_ing_line_starts(const uint8_t *text, uint64_t n, const uint64_t *blk, uint64_t *ls, cudaStream_t st) {
   const uint64_t n_chunks = (n + 15) / 16;
   const unsigned n_blk = (unsigned)ing_tiles(n_chunks);
-  k_ing_scan_apply<uint64_t, ChunkIn, OpAdd64, LineStartOut><<<n_blk, IB, 0, st>>>(ChunkIn{text, n}, n_chunks, blk, OpAdd64(), 0ull,
+  ing_launch(k_ing_scan_apply<uint64_t, ChunkIn, OpAdd64, LineStartOut>, n_blk, IB, st, ChunkIn{text, n}, n_chunks, blk, OpAdd64(), 0ull,
                                                                                    LineStartOut{text, n, ls});
   return 1;
 }
@@ -185,7 +196,7 @@ __global__ void __launch_bounds__(128) k_ing_parse_sam(const uint8_t *__restrict
 int launch_ing_parse_sam(const uint8_t *text, const uint64_t *ls, uint64_t n_lines, LineRec *recs, unsigned long long *err, cudaStream_t st) {
   const uint64_t want = (n_lines + 127) / 128;
   const unsigned grid = (unsigned)(want < 148ull * 64 ? (want ? want : 1) : 148ull * 64);
-  k_ing_parse_sam<<<grid, 128, 0, st>>>(text, ls, n_lines, recs, err);
+  ing_launch(k_ing_parse_sam, grid, 128, st, text, ls, n_lines, recs, err);
   return 1;
 }
 
@@ -218,21 +229,22 @@ int launch_ing_fastq_headers(const uint8_t *text, const uint64_t *ls, uint64_t n
 }
 
 __global__ void __launch_bounds__(128) k_ing_parse_fastq(const uint8_t *__restrict__ text, const uint64_t *__restrict__ ls, uint64_t n_lines,
-                                                         const uint64_t *__restrict__ hdr, uint64_t n_take, int file, int replace_n,
+                                                         const uint64_t *__restrict__ hdr, uint64_t n_take, int file, int phase, int replace_n,
                                                          LineRec *__restrict__ recs, unsigned long long *err) {
   for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_take; k += (uint64_t)gridDim.x * blockDim.x) {
     LineRec r;
     ing_parse_fastq_record(text, ls, n_lines, hdr[k], file, replace_n, r);
-    recs[2 * k + (uint64_t)file] = r;                       // mate 1 / mate 2 alternate (fastqs_to_sam.cpp:49)
-    ing_report(err, 2 * k + (uint64_t)file, r.err);
+    const uint64_t pos = ing_fastq_pos(k, file, phase);     // mate 1 / mate 2 alternate (fastqs_to_sam.cpp:49)
+    recs[pos] = r;
+    ing_report(err, pos, r.err);
   }
 }
 int launch_ing_parse_fastq(const uint8_t *text, const uint64_t *ls, uint64_t n_lines, const uint64_t *hdr, uint64_t n_take, int file,
-                           int replace_n, LineRec *recs, unsigned long long *err, cudaStream_t st) {
+                           int phase, int replace_n, LineRec *recs, unsigned long long *err, cudaStream_t st) {
   if (!n_take) return 0;
   const uint64_t want = (n_take + 127) / 128;
   const unsigned grid = (unsigned)(want < 148ull * 64 ? want : 148ull * 64);
-  k_ing_parse_fastq<<<grid, 128, 0, st>>>(text, ls, n_lines, hdr, n_take, file, replace_n, recs, err);
+  ing_launch(k_ing_parse_fastq, grid, 128, st, text, ls, n_lines, hdr, n_take, file, phase, replace_n, recs, err);
   return 1;
 }
 
@@ -265,8 +277,10 @@ __global__ void k_ing_publish(IngPublish p) {
   }
   uint64_t consumed[2] = {p.n_bytes[0], p.n_bytes[1]};
   if (p.fastq) {
-    const uint64_t take[2] = {(m + 1) / 2, m / 2};
-    for (int f = 0; f < 2; ++f) if (take[f] < p.n_rec[f]) consumed[f] = p.ls[f][p.hdr[f][take[f]]];
+    for (int f = 0; f < 2; ++f) {
+      const uint64_t take = ing_fastq_taken(m, f, p.phase);
+      if (take < p.n_rec[f]) consumed[f] = p.ls[f][p.hdr[f][take]];
+    }
   } else {
     if (m < p.n_rec[0]) consumed[0] = p.ls[0][m];
     consumed[1] = 0;
@@ -274,10 +288,11 @@ __global__ void k_ing_publish(IngPublish p) {
   volatile uint64_t *h = p.host;
   h[0] = tot.reads; h[1] = tot.name; h[2] = tot.seq; h[3] = tot.opt; h[4] = m; h[5] = consumed[0]; h[6] = consumed[1];
   h[7] = (uint64_t)*p.err;
+  h[12] = (uint64_t)((p.phase ^ (int)(m & 1ull)) & 1);      // FASTQ: which mate file the next chunk starts with
   __threadfence_system();
 }
 int launch_ing_publish(const IngPublish &p, cudaStream_t st) {
-  k_ing_publish<<<1, 32, 0, st>>>(p);
+  ing_launch(k_ing_publish, 1, 32, st, p);
   return 1;
 }
 
@@ -327,7 +342,7 @@ __global__ void __launch_bounds__(256) k_ing_copy(IngCopy c) {
 int launch_ing_copy(const IngCopy &c, cudaStream_t st) {
   const uint64_t want = (c.m + 7) / 8;                      // 8 warps per block
   const unsigned grid = (unsigned)(want < 148ull * 16 ? (want ? want : 1) : 148ull * 16);
-  k_ing_copy<<<grid, 256, 0, st>>>(c);
+  ing_launch(k_ing_copy, grid, 256, st, c);
   return 1;
 }
 

@@ -261,17 +261,18 @@ HDN inline void ing_parse_fastq_record(const uint8_t *t, const uint64_t *ls, uin
   if (replace_n) r.bits |= ING_N2Z;
 }
 
-// how many records of each file the reference's loop prints from (fastqs_to_sam.cpp:47-53): it stops at the
-// first file without a further record.  final = 0: the last record of either text may be cut, keep pairs only.
-HD void ing_fastq_take(uint64_t r1, uint64_t r2, int final, uint64_t *n1, uint64_t *n2) {
-  if (!final) {
-    r1 = r1 ? r1 - 1 : 0; r2 = r2 ? r2 - 1 : 0;
-    const uint64_t n = r1 < r2 ? r1 : r2;
-    *n1 = n; *n2 = n;
-    return;
-  }
-  *n1 = r1 < r2 + 1 ? r1 : r2 + 1;
-  *n2 = r2 < *n1 ? r2 : *n1;
+// How many records the reference's loop prints from the file it reads FIRST in a round (ra records available)
+// and from the other one (rb) (fastqs_to_sam.cpp:47-53): it stops at the first file without a further record.
+// final = 0: the last record of either text may be cut by the chunk edge and is left out.
+HD void ing_fastq_take(uint64_t ra, uint64_t rb, int final, uint64_t *na, uint64_t *nb) {
+  if (!final) { ra = ra ? ra - 1 : 0; rb = rb ? rb - 1 : 0; }
+  *na = ra < rb + 1 ? ra : rb + 1;
+  *nb = rb < *na ? rb : *na;
 }
+// Records alternate between the mate files; a chunk of a stream may have to START with mate 2 (phase 1) because the
+// previous chunk ended after a mate-1 record.  Record k of file f sits at position 2k + (f ^ phase).
+HD uint64_t ing_fastq_pos(uint64_t k, int file, int phase) { return 2 * k + (uint64_t)((file ^ phase) & 1); }
+// records of file f among the first m positions
+HD uint64_t ing_fastq_taken(uint64_t m, int file, int phase) { return ((file ^ phase) & 1) ? m / 2 : (m + 1) / 2; }
 
 }  // namespace smash

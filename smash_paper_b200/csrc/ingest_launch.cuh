@@ -11,12 +11,13 @@ uint64_t ing_tiles(uint64_t n);            // scan tiles over n items: scratch a
 struct IngPublish {
   const Ing4 *pre; uint64_t m;             // exclusive scan over the m records (+ total at [m])
   int final, fastq;
+  int phase;                               // FASTQ: 1 = this chunk starts with a mate-2 record
   const uint64_t *ls[2];                   // line starts per text
   const uint64_t *hdr[2];                  // FASTQ: record -> header line
   uint64_t n_rec[2];                       // SAM: n_lines; FASTQ: records per text
   uint64_t n_bytes[2];
   const unsigned long long *err;           // min over (record index << 8 | IngErr), ~0 when clean
-  uint64_t *host;                          // mapped pinned: reads, name, seq, opt bytes, records used, consumed[2], err
+  uint64_t *host;                          // mapped pinned: [0..7] reads, name, seq, opt bytes, records used, consumed[2], err; [12] next phase
 };
 struct IngCopy {
   const uint8_t *text[2];
@@ -33,7 +34,7 @@ int launch_ing_parse_sam(const uint8_t *text, const uint64_t *ls, uint64_t n_lin
 int launch_ing_fastq_headers(const uint8_t *text, const uint64_t *ls, uint64_t n_lines, uint32_t *blk32, uint64_t *blk64, uint8_t *hdr_flag,
                              uint64_t *hdr, uint64_t *count, cudaStream_t st);
 int launch_ing_parse_fastq(const uint8_t *text, const uint64_t *ls, uint64_t n_lines, const uint64_t *hdr, uint64_t n_take, int file,
-                           int replace_n, LineRec *recs, unsigned long long *err, cudaStream_t st);
+                           int phase, int replace_n, LineRec *recs, unsigned long long *err, cudaStream_t st);
 int launch_ing_scan_recs(const LineRec *recs, uint64_t m, Ing4 *blk4, Ing4 *pre, cudaStream_t st);
 int launch_ing_publish(const IngPublish &p, cudaStream_t st);
 int launch_ing_copy(const IngCopy &c, cudaStream_t st);

@@ -10,6 +10,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -265,9 +266,8 @@ int main(int argc, char **argv) {
     const size_t BATCH = 1u << 20;                                   // reads per batch (even)
     uint64_t n_queries = 0, chunk = 0, pairs_done = 0;
     const auto tq = std::chrono::steady_clock::now();
+    const bool device_reader = o.sam_in && !getenv("SMASH_HOST_READER");   // -samin text is parsed on the GPU (smash_submit_text)
     for (size_t fi = 0; fi < o.inputs.size(); ++fi) {
-      QueryParser qp(o.inputs[fi], o);
-      Batch buf[SMASH_N_SLOTS];
       bool in_flight[SMASH_N_SLOTS] = {false, false};
       auto drain = [&](int slot) {
         smash_result r; check(smash_wait(ctx, slot, &r));
@@ -281,7 +281,41 @@ int main(int argc, char **argv) {
         }
       };
       int slot = 0; bool more = true;
+      if (device_reader) {
+        // QueryReader::run's SAM branch (query.cpp:625-648) on the device: the file is streamed through a pinned
+        // buffer in large chunks; what a chunk leaves unconsumed (a cut line, an odd trailing read) is carried over.
+        FILE *f = fopen(o.inputs[fi].c_str(), "rb");
+        if (!f) throw std::runtime_error("unable to open " + o.inputs[fi]);
+        size_t cap = (size_t)256 << 20, len = 0;
+        if (const char *e = getenv("SMASH_TEXT_CHUNK")) cap = std::max<size_t>(4096, strtoull(e, nullptr, 10));
+        char *text = (char *)smash_host_alloc(cap);
+        if (!text) throw std::runtime_error("out of pinned host memory");
+        bool eof = false;
+        while (!eof) {
+          while (len < cap && !eof) { const size_t got = fread(text + len, 1, cap - len, f); len += got; if (!got) eof = true; }
+          if (in_flight[slot]) drain(slot);
+          smash_text t{}; smash_text_info info{};
+          t.kind = SMASH_TEXT_SAM; t.flags = eof ? SMASH_TEXT_FINAL : 0; t.text[0] = text; t.n_bytes[0] = len;
+          t.first_pair_ordinal = pairs_done;
+          check(smash_submit_text(ctx, slot, &t, SMASH_WANT_SAM, &info));
+          in_flight[slot] = true; n_queries += info.n_reads; pairs_done += (info.n_reads + 1) / 2;
+          slot = (slot + 1) % SMASH_N_SLOTS;
+          if (!eof && info.consumed[0] == 0 && len == cap) {          // a single line longer than the buffer: grow it
+            char *bigger = (char *)smash_host_alloc(2 * cap);
+            if (!bigger) throw std::runtime_error("out of pinned host memory");
+            memcpy(bigger, text, len); smash_host_free(text); text = bigger; cap *= 2;
+          }
+          len -= info.consumed[0];
+          memmove(text, text + info.consumed[0], len);
+        }
+        fclose(f);
+        smash_host_free(text);
+        more = false;
+      }
+      QueryParser *qpp = device_reader ? nullptr : new QueryParser(o.inputs[fi], o);
+      Batch buf[SMASH_N_SLOTS];
       while (more) {
+        QueryParser &qp = *qpp;
         if (in_flight[slot]) drain(slot);
         Batch &b = buf[slot]; b.clear();
         while (b.n() < BATCH && (more = qp.next(b))) {}
@@ -292,6 +326,7 @@ int main(int argc, char **argv) {
           slot = (slot + 1) % SMASH_N_SLOTS;
         }
       }
+      delete qpp;
       for (int s = 0; s < SMASH_N_SLOTS; ++s) { const int k = (slot + s) % SMASH_N_SLOTS; if (in_flight[k]) drain(k); }
       if (o.verbose) std::cerr << "# query reader for " << o.inputs[fi] << " processed " << n_queries << " sequences" << std::endl;
     }

@@ -288,6 +288,30 @@ def make_reads_fast(genome, n_pairs, read_len=150, seed=2, frag_min=3, frag_max=
                      opt=np.zeros(0, dtype=np.uint8), opt_off=np.zeros(n + 1, dtype=np.int64))
 
 
+def sam_text_fast(batch: ReadBatch):
+    """The text write_sam() writes, as one uint8 array, built with array operations.  Only for batches of the
+    make_reads_fast shape: names and reads of one fixed length each, flags 77/141 alternating, no optional fields."""
+    n = batch.n
+    assert n % 2 == 0 and n > 0 and batch.opt.size == 0
+    ln, q = int(batch.name_off[1]), int(batch.seq_off[1])
+    assert batch.names.size == n * ln and batch.seq.size == n * q
+    mid = [np.frombuffer(b"\t77\t*\t0\t0\t*\t*\t0\t0\t", dtype=np.uint8), np.frombuffer(b"\t141\t*\t0\t0\t*\t*\t0\t0\t", dtype=np.uint8)]
+    names = batch.names.reshape(n // 2, 2, ln); seq = batch.seq.reshape(n // 2, 2, q); qual = batch.qual.reshape(n // 2, 2, q)
+    cols = []
+    for m in (0, 1):
+        w = ln + len(mid[m]) + q + 1 + q + 1
+        row = np.empty((n // 2, w), dtype=np.uint8)
+        o = 0
+        row[:, o:o + ln] = names[:, m]; o += ln
+        row[:, o:o + len(mid[m])] = mid[m]; o += len(mid[m])
+        row[:, o:o + q] = seq[:, m]; o += q
+        row[:, o] = 9; o += 1
+        row[:, o:o + q] = qual[:, m]; o += q
+        row[:, o] = 10
+        cols.append(row)
+    return np.concatenate(cols, axis=1).reshape(-1)
+
+
 def write_sam(batch: ReadBatch, path):
     """Unaligned SAM lines as fastqs_to_sam.cpp:80-93 prints them (flags 77/141)."""
     with open(path, "wb") as f:

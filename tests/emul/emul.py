@@ -86,8 +86,31 @@ class IngestError(Exception):
         self.code, self.index = code, index
 
 
-def ingest(kind, text0, text1=b"", final=True, replace_n=False):
-    """Emulated smash_text_upload: dict of the packed batch arrays + consumed bytes."""
+_INGK = None
+
+
+def ingest_kernels_lib():
+    """ingest.cu itself, compiled with g++ against tests/emul/cuda_shim: its kernels run on host threads."""
+    global _INGK
+    if _INGK is None:
+        so = os.path.join(HERE, "libemul_ingest_kernels.so")
+        src = os.path.join(HERE, "emul_ingest_kernels.cpp")
+        deps = [src, os.path.join(HERE, "cuda_shim", "cuda_runtime.h")] + [os.path.join(HERE, "../../smash_paper_b200/csrc", f)
+                                                                          for f in ("core.cuh", "ingest.cuh", "ingest_launch.cuh", "ingest.cu")]
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["g++", "-O1", "-std=c++20", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas",
+                                   "-I", os.path.join(HERE, "cuda_shim"), "-o", so, src])
+        _INGK = C.CDLL(so)
+    return _INGK
+
+
+def ingest_kernels(kind, text0, text1=b"", final=True, replace_n=False, mate2_first=False):
+    return ingest(kind, text0, text1, final, replace_n, mate2_first, kernels=True)
+
+
+def ingest(kind, text0, text1=b"", final=True, replace_n=False, mate2_first=False, kernels=False):
+    """Emulated smash_text_upload: dict of the packed batch arrays + consumed bytes.  kernels=False: the building
+    blocks of ingest.cuh in plain loops; kernels=True: the kernels of ingest.cu executed block by block."""
     n0, n1 = len(text0), len(text1)
     a0 = np.frombuffer(text0 + b"\0", dtype=np.uint8)
     a1 = np.frombuffer(text1 + b"\0", dtype=np.uint8)
@@ -96,13 +119,15 @@ def ingest(kind, text0, text1=b"", final=True, replace_n=False):
     names = np.zeros(cap, np.uint8); seq = np.zeros(cap, np.uint8); qual = np.zeros(cap, np.uint8); opt = np.zeros(cap, np.uint8)
     name_off = np.zeros(nl, np.int64); seq_off = np.zeros(nl, np.int64); opt_off = np.zeros(nl, np.int64)
     rf = np.zeros(nl, np.uint16)
-    info = np.zeros(6, np.uint64)
+    info = np.zeros(8, np.uint64)
     err_index = C.c_uint64(0)
-    rc = ingest_lib().emul_ingest(int(kind), int(final), int(replace_n), _p(a0), C.c_uint64(n0), _p(a1), C.c_uint64(n1),
+    fn = ingest_kernels_lib().emul_ingest_kernels if kernels else ingest_lib().emul_ingest
+    rc = fn(int(kind), int(final), int(replace_n), int(mate2_first), _p(a0), C.c_uint64(n0), _p(a1), C.c_uint64(n1),
                                   _p(names), _p(name_off), _p(seq), _p(qual), _p(seq_off), _p(opt), _p(opt_off), _p(rf),
                                   _p(info), C.byref(err_index))
     if rc:
         raise IngestError(rc, err_index.value)
     n, nb, sb, ob = (int(x) for x in info[:4])
     return dict(n=n, names=names[:nb], name_off=name_off[:n + 1], seq=seq[:sb], qual=qual[:sb], seq_off=seq_off[:n + 1],
-                opt=opt[:ob], opt_off=opt_off[:n + 1], read_flag=rf[:n], consumed=(int(info[4]), int(info[5])))
+                opt=opt[:ob], opt_off=opt_off[:n + 1], read_flag=rf[:n], consumed=(int(info[4]), int(info[5])),
+                mate2_first_next=bool(info[6]))

@@ -59,10 +59,11 @@ extern "C" {
 
 // kind 0: SAM text (text1 ignored), 1: FASTQ pair.  Outputs are caller buffers sized generously
 // (names/seq/qual/opt: n0 + n1 bytes; offsets / read_flag: line count + 1).  Returns 0, or the IngErr code
-// with *err_index = record index.  out_info: n_reads, name_bytes, seq_bytes, opt_bytes, consumed0, consumed1.
-int emul_ingest(int kind, int final, int replace_n, const uint8_t *text0, uint64_t n0, const uint8_t *text1, uint64_t n1,
+// with *err_index = record index.  out_info: n_reads, name_bytes, seq_bytes, opt_bytes, consumed0, consumed1, next phase.
+int emul_ingest(int kind, int final, int replace_n, int phase, const uint8_t *text0, uint64_t n0, const uint8_t *text1, uint64_t n1,
                 uint8_t *names, int64_t *name_off, uint8_t *seq, uint8_t *qual, int64_t *seq_off, uint8_t *opt, int64_t *opt_off,
                 uint16_t *read_flag, uint64_t *out_info, uint64_t *err_index) {
+  phase = kind ? (phase & 1) : 0;
   const uint8_t *text[2] = {text0, text1};
   const uint64_t full[2] = {n0, kind ? n1 : 0};
   uint64_t nb[2] = {n0, kind ? n1 : 0};
@@ -75,12 +76,12 @@ int emul_ingest(int kind, int final, int replace_n, const uint8_t *text0, uint64
   uint64_t m = 0;
   if (kind) {
     for (int f = 0; f < 2; ++f) { hdr[f] = fastq_headers(text[f], L[f]); n_rec[f] = hdr[f].size(); }
-    ing_fastq_take(n_rec[0], n_rec[1], final, &n_take[0], &n_take[1]);
+    ing_fastq_take(n_rec[phase], n_rec[phase ^ 1], final, &n_take[phase], &n_take[phase ^ 1]);
     m = n_take[0] + n_take[1];
     recs.resize(m + 1);
     for (int f = 0; f < 2; ++f)
       for (uint64_t k = 0; k < n_take[f]; ++k)
-        ing_parse_fastq_record(text[f], L[f].ls.data(), L[f].n_lines, hdr[f][k], f, replace_n, recs[2 * k + f]);
+        ing_parse_fastq_record(text[f], L[f].ls.data(), L[f].n_lines, hdr[f][k], f, replace_n, recs[ing_fastq_pos(k, f, phase)]);
   } else {
     n_rec[0] = L[0].n_lines;
     m = L[0].n_lines;
@@ -105,8 +106,7 @@ int emul_ingest(int kind, int final, int replace_n, const uint8_t *text0, uint64
   uint64_t consumed[2] = {nb[0], nb[1]};
   if (m) {
     if (kind) {
-      const uint64_t take[2] = {(mu + 1) / 2, mu / 2};
-      for (int f = 0; f < 2; ++f) if (take[f] < n_rec[f]) consumed[f] = L[f].ls[hdr[f][take[f]]];
+      for (int f = 0; f < 2; ++f) { const uint64_t take = ing_fastq_taken(mu, f, phase); if (take < n_rec[f]) consumed[f] = L[f].ls[hdr[f][take]]; }
     } else {
       if (mu < n_rec[0]) consumed[0] = L[0].ls[mu];
       consumed[1] = 0;
@@ -116,7 +116,7 @@ int emul_ingest(int kind, int final, int replace_n, const uint8_t *text0, uint64
   }
   if (final) { consumed[0] = full[0]; consumed[1] = full[1]; }
   if (err != ~0ull) { *err_index = err >> 8; return (int)(err & 0xff); }
-  out_info[0] = tot.reads; out_info[1] = tot.name; out_info[2] = tot.seq; out_info[3] = tot.opt; out_info[4] = consumed[0]; out_info[5] = consumed[1];
+  out_info[0] = tot.reads; out_info[1] = tot.name; out_info[2] = tot.seq; out_info[3] = tot.opt; out_info[4] = consumed[0]; out_info[5] = consumed[1]; out_info[6] = m ? (uint64_t)((phase ^ (int)(mu & 1)) & 1) : (uint64_t)phase;
   // k_ing_copy
   name_off[tot.reads] = (int64_t)tot.name; seq_off[tot.reads] = (int64_t)tot.seq; opt_off[tot.reads] = (int64_t)tot.opt;
   for (uint64_t i = 0; i < mu; ++i) {

@@ -261,13 +261,13 @@ def test_golden_map_bin():
             ctx.close()
 
 
-@pytest.mark.parametrize("driver", ["cxx", "python"])
+@pytest.mark.parametrize("driver", ["cxx", "cxx_host_reader", "python"])
 def test_mummer_compatible_driver(case, workdir, driver):
     """The drop-in `mummer` (C++ binary over the C ABI, and its Python twin): same flags, same files;
     index built on the GPU when absent."""
     import shutil, subprocess, sys, glob
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = [os.path.join(root, "smash_paper_b200", "bin", "mummer")] if driver == "cxx" else [sys.executable, "-m", "smash_paper_b200.mummer"]
+    exe = [os.path.join(root, "smash_paper_b200", "bin", "mummer")] if driver.startswith("cxx") else [sys.executable, "-m", "smash_paper_b200.mummer"]
     d = os.path.join(workdir, "driver_" + driver)
     shutil.rmtree(d, ignore_errors=True)
     os.makedirs(d)
@@ -275,6 +275,8 @@ def test_mummer_compatible_driver(case, workdir, driver):
     shutil.copy(case["fa"], fa)
     shutil.copy(os.path.join(case["dir"], "reads.sam"), os.path.join(d, "reads.sam"))
     env = dict(os.environ, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    if driver == "cxx_host_reader":
+        env["SMASH_HOST_READER"] = "1"                   # -samin parsed by the host QueryParser instead of ingest.cu
     # index build (index_setup.sh:19): exits 1 on 'dummy' by design, leaves <fa>.bin/ behind
     r = subprocess.run(exe + ["-verbose", "-rcref", fa, "dummy"], cwd=d, env=env,
                        capture_output=True, text=True)
@@ -296,6 +298,30 @@ def test_mummer_compatible_driver(case, workdir, driver):
     r = subprocess.run(exe + ["-rcref", "-nomap", fa, "reads.sam"], cwd=d, env=env,
                        capture_output=True, text=True)
     assert r.returncode == 1 and r.stderr.startswith("Error\n-nomap can only be used with -sam_out")
+
+
+def test_driver_streams_sam_text_in_chunks(case, workdir):
+    """`mummer -samin` with the reader on the GPU and a text buffer far smaller than the file: chunk edges cut
+    lines and pairs, the concatenated chunk files must still be the single-batch SAM."""
+    import shutil, subprocess, glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "smash_paper_b200", "bin", "mummer")
+    d = os.path.join(workdir, "driver_chunks")
+    shutil.rmtree(d, ignore_errors=True)
+    os.makedirs(d)
+    env = dict(os.environ, SMASH_TEXT_CHUNK="30011")
+    r = subprocess.run([exe, "-rcref", "-nomap", "-samin", "-samout", case["fa"], os.path.join(case["dir"], "reads.sam")],
+                       cwd=d, env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    files = sorted(glob.glob(os.path.join(d, "mapout", "*.txt")), key=lambda f: int(f.split(".")[-2]))
+    assert len(files) > 3
+    hdr = case["oix"].sam_header().encode()
+    got = b""
+    for f in files:
+        data = open(f, "rb").read()
+        assert data.startswith(hdr)
+        got += data[len(hdr):]
+    assert got == case["oix"].map_batch(case["reads"], min_len=20, n_threads=4)
 
 
 def test_two_shards_equal_one_run(case):

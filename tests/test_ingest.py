@@ -63,14 +63,15 @@ def stream(parse, kind, texts, sizes, replace_n=False):
     """Feed the text(s) in chunks the way a streaming host does: unconsumed bytes are passed again."""
     pend = [b"", b""]
     pos = [0, 0]
-    parts, n_calls = [], 0
+    parts, n_calls, phase = [], 0, False
     while True:
         for f in range(len(texts)):
             take = sizes[n_calls % len(sizes)]
             pend[f] += texts[f][pos[f]:pos[f] + take]
             pos[f] += take
         final = all(pos[f] >= len(texts[f]) for f in range(len(texts)))
-        r = parse(kind, pend[0], pend[1], final, replace_n)
+        r = parse(kind, pend[0], pend[1], final, replace_n, phase)
+        phase = get(r, "mate2_first_next")
         n_calls += 1
         n = get(r, "n") if isinstance(r, dict) else r.n
         if not final:
@@ -192,6 +193,47 @@ def test_empty_and_ragged_inputs_emulated():
     assert r["n"] == 2 and r["consumed"][0] == 2 * len(one)
 
 
+# ---- the kernels of ingest.cu themselves, executed on host threads (tests/emul/cuda_shim) ----------------------
+
+def test_real_kernels_on_host_golden_inputs():
+    q = gz("quirks.sam.gz")
+    assert_same_batch(E.ingest_kernels(0, q), I.parse_sam_text(q))
+    fq1, fq2 = gz("r1.fq.gz"), gz("r2.fq.gz")
+    for rep in (False, True):
+        assert_same_batch(E.ingest_kernels(1, fq1, fq2, True, rep), I.parse_fastq_pair(fq1, fq2, rep))
+
+
+def test_real_kernels_on_host_fuzz_and_streaming():
+    rng = np.random.default_rng(301)
+    text = fuzz_sam(rng, 1500)                                   # 2 tiles of lines, ~7 tiles of chunks
+    want = I.parse_sam_text(text)
+    assert_same_batch(E.ingest_kernels(0, text), want)
+    assert_same_batch(stream(E.ingest_kernels, 0, [text], [40000, 7, 3000]), want)
+    fq1, fq2 = fuzz_fastq(rng, 700, 0), fuzz_fastq(rng, 698, 1)
+    want = I.parse_fastq_pair(fq1, fq2, True)
+    assert_same_batch(E.ingest_kernels(1, fq1, fq2, True, True), want)
+    assert_same_batch(stream(E.ingest_kernels, 1, [fq1, fq2], [30000, 11, 9000], True), want)
+    for text, code in BAD_SAM[:3]:
+        with pytest.raises(E.IngestError) as ei:
+            E.ingest_kernels(0, b"ok 0 * 0 0 * * 0 0 AC II\n" * 1100 + text)      # the error sits in the second tile
+        assert ei.value.code == code and ei.value.index == 1100
+
+
+def test_real_kernels_on_host_many_tiles():
+    """4.5 MB of text in 32 very long lines: > 256 scan tiles, so k_ing_scan_top loops with a carry."""
+    rng = np.random.default_rng(9)
+    lines = []
+    for i in range(32):
+        L = 70000 + int(rng.integers(0, 999))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=L))
+        qual = bytes(rng.integers(33, 127, size=L).astype(np.uint8))
+        lines.append(b"long%d\t%d\t*\t0\t0\t*\t*\t0\t0\t" % (i, 77 if i % 2 == 0 else 141) + seq + b"\t" + qual
+                     + (b"\tXX:Z:tail  \t YY:i:1" if i % 3 == 0 else b"") + b"\n")
+    text = b"".join(lines)
+    assert len(text) // 16 // 1024 > 256
+    assert_same_batch(E.ingest_kernels(0, text), I.parse_sam_text(text))
+
+
 BAD_SAM = [(b"a 77 * 0 0 * * 0 0 ACGT\n", 1), (b"a x77 * 0 0 * * 0 0 ACGT IIII\n", 2), (b"a 99999999999 * 0 0 * * 0 0 ACGT IIII\n", 2),
            (b"a 77 * 0 0 * * 0 0 ACGT III\n", 3), (b"\r\n", 1), (b"ok 0 * 0 0 * * 0 0 AC II\nbad\n", 1)]
 BAD_FASTQ = [(b"Xa\nAC\n+\nII\n", 4), (b"@a\nAC\n-\nII\n", 5), (b"@\nAC\n+\nII\n", 6), (b"@a\nAC\n+\n", 7), (b"@a\nAC\n", 7), (b"@a\n", 7),
@@ -230,11 +272,12 @@ def gctx():
 
 
 def gpu_parse(ctx):
-    def parse(kind, t0, t1=b"", final=True, replace_n=False):
-        n, cons = ctx.text_upload(kind, t0, t1, final, replace_n)
+    def parse(kind, t0, t1=b"", final=True, replace_n=False, mate2_first=False):
+        n, cons = ctx.text_upload(kind, t0, t1, final, replace_n, mate2_first=mate2_first)
         b = ctx.fetch_batch(0)
         assert b.n == n
         b.consumed = cons
+        b.mate2_first_next = ctx.mate2_first_next
         return b
     return parse
 
