@@ -7,9 +7,9 @@
 //     -> one LineRec per SAM line / FASTQ record (thread per line: sequential tokeniser, bytes stay in L1)
 //     -> exclusive scan of {reads, name bytes, seq bytes, opt bytes}  (ordered compaction: output order
 //        = input order, mates of a FASTQ pair interleaved as fastqs_to_sam prints them)
-//     -> k_ing_copy (warp per read): names / SEQ / QUAL / optional fields into the packed batch blobs,
-//        offsets and read_flag; whitespace runs of the optional fields collapse to one tab with a
-//        ballot + popc placement.
+//     -> k_ing_copy (8 lanes per read): names / SEQ / QUAL / optional fields into the packed batch blobs as aligned
+//        16-byte stores assembled with funnel shifts, offsets and read_flag; whitespace runs of the optional
+//        fields collapse to one tab.
 // HBM-bound streaming work: the text is read three times (count, place, parse+copy; the last two hit L2
 // for batches under ~100 MB) and the batch (~ the same bytes) is written once.
 #include <cuda_runtime.h>
@@ -18,8 +18,15 @@
 
 namespace smash {
 
-constexpr int IB = 256;            // threads per block
-constexpr int II = 4;              // items per thread
+#ifndef ING_IB
+#define ING_IB 256
+#endif
+#ifndef ING_II
+#define ING_II 4
+#endif
+constexpr int IB = ING_IB;         // threads per block (the CPU test-suite also builds a small-tile variant)
+constexpr int II = ING_II;         // items per thread
+static_assert(IB % 32 == 0 && IB >= 32 && IB <= 1024 && II >= 1, "scan tile geometry");
 constexpr int IT = IB * II;        // items per tile
 
 uint64_t ing_tiles(uint64_t n) { return (n + IT - 1) / IT; }
@@ -89,20 +96,25 @@ __global__ void __launch_bounds__(IB) k_ing_scan_tiles(In in, uint64_t n, V *__r
   if (threadIdx.x == 0) blk[blockIdx.x] = total;
 }
 
-// blk[0..n_blk) -> exclusive prefixes, blk[n_blk] = grand total (one block)
+// blk[0..n_blk) -> exclusive prefixes, blk[n_blk] = grand total (one block, IT entries per round)
 template <class V, class Op>
 __global__ void __launch_bounds__(IB) k_ing_scan_top(V *blk, uint64_t n_blk, Op op, V ident) {
   __shared__ V wsum[IB / 32 + 1];
   __shared__ V carry;
   if (threadIdx.x == 0) carry = ident;
   __syncthreads();
-  for (uint64_t b0 = 0; b0 < n_blk; b0 += IB) {
-    const uint64_t i = b0 + threadIdx.x;
-    const V v = i < n_blk ? blk[i] : ident;
+  for (uint64_t b0 = 0; b0 < n_blk; b0 += IT) {
+    const uint64_t base = b0 + (uint64_t)threadIdx.x * II;
+    V v[II];
+    V s = ident;
+#pragma unroll
+    for (int i = 0; i < II; ++i) { v[i] = base + i < n_blk ? blk[base + i] : ident; s = op(s, v[i]); }
     V total;
-    const V ex = block_scan_excl(v, op, ident, wsum, &total);
+    const V ex = block_scan_excl(s, op, ident, wsum, &total);
     const V c = carry;
-    if (i < n_blk) blk[i] = op(c, ex);
+    V run = op(c, ex);
+#pragma unroll
+    for (int i = 0; i < II; ++i) { if (base + i < n_blk) blk[base + i] = run; run = op(run, v[i]); }
     __syncthreads();
     if (threadIdx.x == 0) carry = op(c, total);
     __syncthreads();
@@ -143,9 +155,7 @@ struct ChunkIn {
   const uint8_t *text; uint64_t n;
   __device__ __forceinline__ uint64_t operator()(uint64_t c) const {
     const uint4 v = *reinterpret_cast<const uint4 *>(text + 16 * c);     // buffer is 256-byte aligned and padded
-    alignas(16) uint8_t b[16];
-    *reinterpret_cast<uint4 *>(b) = v;
-    return ing_chunk_starts(b, 16 * c, n);
+    return ing_chunk_starts((uint64_t)v.x | ((uint64_t)v.y << 32), (uint64_t)v.z | ((uint64_t)v.w << 32), 16 * c, n);
   }
 };
 struct LineStartOut {
@@ -153,13 +163,7 @@ struct LineStartOut {
   __device__ __forceinline__ void operator()(uint64_t c, uint64_t ex, uint64_t cnt) const {
     if (!cnt) return;
     const uint4 v = *reinterpret_cast<const uint4 *>(text + 16 * c);
-    alignas(16) uint8_t b[16];
-    *reinterpret_cast<uint4 *>(b) = v;
-    uint64_t idx = ex;
-    if (c == 0) ls[idx++] = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (16 * c + (uint64_t)i + 1 < n && b[i] == '\n') ls[idx++] = 16 * c + (uint64_t)i + 1;
+    ing_chunk_place((uint64_t)v.x | ((uint64_t)v.y << 32), (uint64_t)v.z | ((uint64_t)v.w << 32), 16 * c, n, ls, ex);
   }
   __device__ __forceinline__ void total(uint64_t, uint64_t tot) const { ls[tot] = ing_sentinel(text, n); }
 };
@@ -296,51 +300,74 @@ int launch_ing_publish(const IngPublish &p, cudaStream_t st) {
   return 1;
 }
 
+// One run of bytes (SEQ or QUAL) copied by the 8 lanes of a read's group: the destination's aligned 16-byte chunks
+// are assembled from five aligned source words by funnel shifts, the < 16 bytes either side go out as byte stores.
+// fix = 1 replaces 'N' by 'Z' (fastqs_to_sam.cpp:69).  May read up to 7 bytes beyond the run (buffer slack).
+__device__ __forceinline__ uint32_t ing_n2z_word(uint32_t w) {
+  const uint32_t x = w ^ 0x4e4e4e4eu;                                   // 'N'
+  const uint32_t t = ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x;
+  return w ^ (((~t & 0x80808080u) >> 7) * 0x14u);                       // 'N' ^ 'Z' == 0x14
+}
+__device__ __forceinline__ void ing_copy_run8(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, uint32_t len, int l, bool fix) {
+  const uint32_t head = (16u - (uint32_t)((uintptr_t)dst & 15u)) & 15u;
+  const uint32_t hl = head < len ? head : len;
+  const uint32_t nb = (len - hl) >> 4, tail = (len - hl) & 15u, t0 = hl + 16u * nb;
+  for (uint32_t k = l; k < hl; k += 8) { uint8_t ch = src[k]; if (fix && ch == 'N') ch = 'Z'; dst[k] = ch; }
+  for (uint32_t k = l; k < tail; k += 8) { uint8_t ch = src[t0 + k]; if (fix && ch == 'N') ch = 'Z'; dst[t0 + k] = ch; }
+  for (uint32_t k = l; k < nb; k += 8) {
+    const uint32_t s0 = hl + 16u * k;
+    const uintptr_t a = (uintptr_t)(src + s0);
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    const unsigned sh = (unsigned)(a & 3) * 8u;
+    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+    uint4 v;
+    v.x = __funnelshift_r(w0, w1, sh); v.y = __funnelshift_r(w1, w2, sh);
+    v.z = __funnelshift_r(w2, w3, sh); v.w = __funnelshift_r(w3, w4, sh);
+    if (fix) { v.x = ing_n2z_word(v.x); v.y = ing_n2z_word(v.y); v.z = ing_n2z_word(v.z); v.w = ing_n2z_word(v.w); }
+    *reinterpret_cast<uint4 *>(dst + s0) = v;
+  }
+}
+
+// 8 lanes per read, 4 reads per warp in flight; no warp-level collectives (the groups diverge freely).
 __global__ void __launch_bounds__(256) k_ing_copy(IngCopy c) {
-  const int lane = threadIdx.x & 31;
-  const uint64_t warp0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint64_t n_warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-  if (warp0 == 0 && lane == 0) {                            // end sentinels of the offset arrays
+  const int l = threadIdx.x & 7;
+  const uint64_t group0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const uint64_t n_groups = ((uint64_t)gridDim.x * blockDim.x) >> 3;
+  if (group0 == 0 && l == 0) {                              // end sentinels of the offset arrays
     const Ing4 tot = c.pre[c.m];
     c.name_off[tot.reads] = (int64_t)tot.name; c.seq_off[tot.reads] = (int64_t)tot.seq;
     if (c.opt_off) c.opt_off[tot.reads] = (int64_t)tot.opt;
   }
-  for (uint64_t i = warp0; i < c.m; i += n_warps) {
+  for (uint64_t i = group0; i < c.m; i += n_groups) {
     const LineRec r = c.recs[i];
     if (!(r.bits & ING_EMIT)) continue;
     const Ing4 p = c.pre[i];
     const uint8_t *__restrict__ t = c.text[r.src];
-    if (lane == 0) {
+    if (l == 0) {
       c.name_off[p.reads] = (int64_t)p.name; c.seq_off[p.reads] = (int64_t)p.seq; c.read_flag[p.reads] = r.read_flag;
       if (c.opt_off) c.opt_off[p.reads] = (int64_t)p.opt;
     }
-    for (uint32_t k = lane; k < r.name_len; k += 32) c.names[p.name + k] = t[r.name_pos + k];
-    const bool n2z = (r.bits & ING_N2Z) != 0;
-    for (uint32_t k = lane; k < r.seq_len; k += 32) {
-      uint8_t ch = t[r.seq_pos + k];
-      if (n2z && ch == 'N') ch = 'Z';                       // replace(bases, 'N', 'Z'), fastqs_to_sam.cpp:69
-      c.seq[p.seq + k] = ch;
-      c.qual[p.seq + k] = t[r.qual_pos + k];
-    }
+    for (uint32_t k = l; k < r.name_len; k += 8) c.names[p.name + k] = t[r.name_pos + k];
+    ing_copy_run8(c.seq + p.seq, t + r.seq_pos, r.seq_len, l, (r.bits & ING_N2Z) != 0);
+    ing_copy_run8(c.qual + p.seq, t + r.qual_pos, r.seq_len, l, false);
     if (r.bits & ING_OPT_SAM) {
       const uint64_t b = r.opt_pos - 1, e = b + r.opt_src_len;
-      uint64_t o = p.opt;
-      for (uint64_t base = b; base < e; base += 32) {
-        const uint64_t k = base + lane;
-        const int ch = k < e ? ing_opt_char(t, k, e) : -1;
-        const uint32_t mask = __ballot_sync(0xffffffffu, ch >= 0);
-        if (ch >= 0) c.opt[o + __popc(mask & ((1u << lane) - 1u))] = (uint8_t)ch;
-        o += __popc(mask);
+      if (r.opt_len == r.opt_src_len) {
+        // no whitespace run to collapse: every source byte yields one output byte (separators become tabs)
+        for (uint32_t k = l; k < r.opt_src_len; k += 8) { const uint8_t ch = t[b + k]; c.opt[p.opt + k] = ing_space(ch) ? (uint8_t)'\t' : ch; }
+      } else if (l == 0) {
+        uint64_t o = p.opt;
+        for (uint64_t k = b; k < e; ++k) { const int ch = ing_opt_char(t, k, e); if (ch >= 0) c.opt[o++] = (uint8_t)ch; }
       }
     } else if (r.bits & ING_OPT_XO) {
       const uint64_t lit = 0x3a5a3a4f5809ull;                // "\tXO:Z:" little-endian (fastqs_to_sam.cpp:88-91 + add_optional's tab)
-      if (lane < 6) c.opt[p.opt + lane] = (uint8_t)(lit >> (8 * lane));
-      for (uint32_t k = lane; k < r.opt_src_len; k += 32) c.opt[p.opt + 6 + k] = t[r.opt_pos + k];
+      if (l < 6) c.opt[p.opt + l] = (uint8_t)(lit >> (8 * l));
+      for (uint32_t k = l; k < r.opt_src_len; k += 8) c.opt[p.opt + 6 + k] = t[r.opt_pos + k];
     }
   }
 }
 int launch_ing_copy(const IngCopy &c, cudaStream_t st) {
-  const uint64_t want = (c.m + 7) / 8;                      // 8 warps per block
+  const uint64_t want = (c.m + 31) / 32;                     // 32 groups of 8 lanes per block
   const unsigned grid = (unsigned)(want < 148ull * 16 ? (want ? want : 1) : 148ull * 16);
   ing_launch(k_ing_copy, grid, 256, st, c);
   return 1;

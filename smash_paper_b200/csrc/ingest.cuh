@@ -64,15 +64,80 @@ HD Ing4 ing4_of(const LineRec &r) {
 // C-locale isspace: what `operator>>` skips and what ends a token
 HD bool ing_space(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }
 
+// ---- SWAR over 8 text bytes (little-endian word) ------------------------------------------------------
+constexpr uint64_t ING_LO7 = 0x7f7f7f7f7f7f7f7full, ING_HI = 0x8080808080808080ull, ING_ONES = 0x0101010101010101ull;
+HD int ing_ctz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)x) - 1;
+#else
+  return __builtin_ctzll(x);
+#endif
+}
+HD int ing_popc64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __popcll(x);
+#else
+  return __builtin_popcountll(x);
+#endif
+}
+// 0x80 in every byte of w that equals c (exact: no carries between bytes)
+HD uint64_t ing_eq_mask(uint64_t w, uint8_t c) {
+  const uint64_t x = w ^ (ING_ONES * c);
+  const uint64_t t = ((x & ING_LO7) + ING_LO7) | x;
+  return ~t & ING_HI;
+}
+// 0x80 in every whitespace byte (0x20, 0x09..0x0d)
+HD uint64_t ing_ws_mask(uint64_t w) {
+  const uint64_t w7 = (w & ING_LO7) | ING_HI;
+  const uint64_t ge9 = w7 - ING_ONES * 9, ge14 = w7 - ING_ONES * 14;     // top bit of a byte stays set iff (byte & 0x7f) >= 9 / 14
+  return (ge9 & ~ge14 & ~w & ING_HI) | ing_eq_mask(w, ' ');
+}
+// 8 bytes at any offset, from the two aligned words that hold them.  May touch up to 15 bytes past t[i+7]: every
+// text buffer carries 64 bytes of slack (device: ing_raw; host emulation: padded copies).
+HD uint64_t ing_load8(const uint8_t *t, uint64_t i) {
+  const uintptr_t a = (uintptr_t)(t + i);
+  const uint64_t *p = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
+  const unsigned sh = (unsigned)(a & 7) * 8u;
+  const uint64_t lo = p[0];
+  if (!sh) return lo;
+  return (lo >> sh) | (p[1] << (64u - sh));
+}
+// end of the token that starts at or after i (first whitespace byte, or e)
+HD uint64_t ing_token_end(const uint8_t *t, uint64_t i, uint64_t e) {
+  while (i + 8 <= e) {
+    const uint64_t m = ing_ws_mask(ing_load8(t, i));
+    if (m) return i + (uint64_t)(ing_ctz64(m) >> 3);
+    i += 8;
+  }
+  while (i < e && !ing_space(t[i])) ++i;
+  return i;
+}
+
 // ---- lines ------------------------------------------------------------------------------------
 // A line starts at 0 and after every '\n' that is not the last byte.  Line starts are counted per 16-byte
-// chunk of the text; a start is attributed to the chunk that holds the newline BEFORE it (the first
-// line to chunk 0), which keeps them in order.
-HD uint32_t ing_chunk_starts(const uint8_t *b16, uint64_t base, uint64_t n) {
-  uint32_t c = (base == 0 && n > 0) ? 1u : 0u;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) c += (base + (uint64_t)i + 1 < n && b16[i] == '\n') ? 1u : 0u;
-  return c;
+// chunk of the text (two little-endian words lo, hi); a start is attributed to the chunk that holds the
+// newline BEFORE it (the first line to chunk 0), which keeps them in order.
+HD uint64_t ing_low_bytes(int k) { return k >= 8 ? ~0ull : (k <= 0 ? 0ull : ((1ull << (8 * k)) - 1ull)); }
+HD void ing_chunk_masks(uint64_t lo, uint64_t hi, uint64_t base, uint64_t n, uint64_t *m0, uint64_t *m1) {
+  *m0 = ing_eq_mask(lo, '\n'); *m1 = ing_eq_mask(hi, '\n');
+  if (base + 17 > n) {                                   // last chunk: only newlines at j with j + 1 < n start a line
+    const int keep = (int)(n - 1 - base);                // bytes 0 .. keep-1 of the chunk qualify (n > base)
+    *m0 &= ing_low_bytes(keep); *m1 &= ing_low_bytes(keep - 8);
+  }
+}
+HD uint32_t ing_chunk_starts(uint64_t lo, uint64_t hi, uint64_t base, uint64_t n) {
+  uint64_t m0, m1;
+  ing_chunk_masks(lo, hi, base, n, &m0, &m1);
+  return ((base == 0 && n > 0) ? 1u : 0u) + (uint32_t)ing_popc64(m0) + (uint32_t)ing_popc64(m1);
+}
+// writes the chunk's line starts to ls[idx...]; returns the next idx
+HD uint64_t ing_chunk_place(uint64_t lo, uint64_t hi, uint64_t base, uint64_t n, uint64_t *ls, uint64_t idx) {
+  uint64_t m0, m1;
+  ing_chunk_masks(lo, hi, base, n, &m0, &m1);
+  if (base == 0 && n > 0) ls[idx++] = 0;
+  while (m0) { ls[idx++] = base + (uint64_t)(ing_ctz64(m0) >> 3) + 1; m0 &= m0 - 1; }
+  while (m1) { ls[idx++] = base + 8 + (uint64_t)(ing_ctz64(m1) >> 3) + 1; m1 &= m1 - 1; }
+  return idx;
 }
 // content of line j = [ls[j], ing_line_end(ls, j)); ls[n_lines] is a sentinel placed one past the
 // (possibly absent) newline of the last line
@@ -99,7 +164,7 @@ HDN inline void ing_parse_sam_line(const uint8_t *t, uint64_t b, uint64_t e, Lin
   r.bits = ING_EMIT;
   uint64_t i = b;
 #define ING_SKIP_WS() while (i < e && ing_space(t[i])) ++i
-#define ING_TOKEN() while (i < e && !ing_space(t[i])) ++i
+#define ING_TOKEN() i = ing_token_end(t, i, e)
   ING_SKIP_WS();
   if (i == e) { r.err = ING_FEW_FIELDS; return; }
   r.name_pos = i;
@@ -204,7 +269,7 @@ HD bool ing_single_token(const uint8_t *t, uint64_t b, uint64_t e, uint64_t *pos
   while (i < e && ing_space(t[i])) ++i;
   if (i == e) return false;
   *pos = i;
-  while (i < e && !ing_space(t[i])) ++i;
+  i = ing_token_end(t, i, e);
   *len = i - *pos;
   while (i < e && ing_space(t[i])) ++i;
   return i == e;

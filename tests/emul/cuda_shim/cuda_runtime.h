@@ -37,6 +37,7 @@ inline ShimBlock *g_shim = nullptr;
 inline void __syncthreads() { g_shim->block_barrier->arrive_and_wait(); }
 inline void __threadfence_system() {}
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { return (unsigned)(((((uint64_t)hi) << 32) | lo) >> (sh & 31)); }
 
 template <class T> inline T shim_shfl_up(T v, int d) {
   static_assert(sizeof(T) <= 8, "shim shuffles move up to 64 bits");

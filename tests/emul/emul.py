@@ -86,26 +86,32 @@ class IngestError(Exception):
         self.code, self.index = code, index
 
 
-_INGK = None
+_INGK = {}
 
 
-def ingest_kernels_lib():
-    """ingest.cu itself, compiled with g++ against tests/emul/cuda_shim: its kernels run on host threads."""
-    global _INGK
-    if _INGK is None:
-        so = os.path.join(HERE, "libemul_ingest_kernels.so")
+def ingest_kernels_lib(small_tiles=False):
+    """ingest.cu itself, compiled with g++ against tests/emul/cuda_shim: its kernels run on host threads.
+    small_tiles: scan tiles of 64 x 2 items instead of 256 x 4, so that the multi-round paths of the scans
+    (carry between rounds of k_ing_scan_top, many tiles) are reached with small inputs."""
+    if small_tiles not in _INGK:
+        so = os.path.join(HERE, "libemul_ingest_kernels_small.so" if small_tiles else "libemul_ingest_kernels.so")
         src = os.path.join(HERE, "emul_ingest_kernels.cpp")
         deps = [src, os.path.join(HERE, "cuda_shim", "cuda_runtime.h")] + [os.path.join(HERE, "../../smash_paper_b200/csrc", f)
                                                                           for f in ("core.cuh", "ingest.cuh", "ingest_launch.cuh", "ingest.cu")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-            subprocess.check_call(["g++", "-O1", "-std=c++20", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas",
-                                   "-I", os.path.join(HERE, "cuda_shim"), "-o", so, src])
-        _INGK = C.CDLL(so)
-    return _INGK
+            subprocess.check_call(["g++", "-O1", "-std=c++20", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas"]
+                                  + (["-DING_IB=64", "-DING_II=2"] if small_tiles else [])
+                                  + ["-I", os.path.join(HERE, "cuda_shim"), "-o", so, src])
+        _INGK[small_tiles] = C.CDLL(so)
+    return _INGK[small_tiles]
 
 
 def ingest_kernels(kind, text0, text1=b"", final=True, replace_n=False, mate2_first=False):
     return ingest(kind, text0, text1, final, replace_n, mate2_first, kernels=True)
+
+
+def ingest_kernels_small(kind, text0, text1=b"", final=True, replace_n=False, mate2_first=False):
+    return ingest(kind, text0, text1, final, replace_n, mate2_first, kernels="small")
 
 
 def ingest(kind, text0, text1=b"", final=True, replace_n=False, mate2_first=False, kernels=False):
@@ -121,7 +127,7 @@ def ingest(kind, text0, text1=b"", final=True, replace_n=False, mate2_first=Fals
     rf = np.zeros(nl, np.uint16)
     info = np.zeros(8, np.uint64)
     err_index = C.c_uint64(0)
-    fn = ingest_kernels_lib().emul_ingest_kernels if kernels else ingest_lib().emul_ingest
+    fn = ingest_kernels_lib(kernels == "small").emul_ingest_kernels if kernels else ingest_lib().emul_ingest
     rc = fn(int(kind), int(final), int(replace_n), int(mate2_first), _p(a0), C.c_uint64(n0), _p(a1), C.c_uint64(n1),
                                   _p(names), _p(name_off), _p(seq), _p(qual), _p(seq_off), _p(opt), _p(opt_off), _p(rf),
                                   _p(info), C.byref(err_index))

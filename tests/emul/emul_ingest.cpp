@@ -18,24 +18,22 @@ namespace {
 
 struct Lines { std::vector<uint64_t> ls; uint64_t n_lines = 0; };
 
-// k_ing_scan_tiles/top/apply with ChunkIn / LineStartOut
+static inline uint64_t word_at(const uint8_t *p) { uint64_t w; memcpy(&w, p, 8); return w; }
+
+// k_ing_scan_tiles/top/apply with ChunkIn / LineStartOut.  text: padded copy (64 bytes of slack, like ing_raw)
 Lines line_starts(const uint8_t *text, uint64_t n) {
   Lines L;
   if (!n) return L;
   const uint64_t n_chunks = (n + 15) / 16;
-  std::vector<uint8_t> padded((size_t)n_chunks * 16 + 16, 0xAB);          // bytes past n are garbage on the device too
-  memcpy(padded.data(), text, n);
   std::vector<uint64_t> cnt(n_chunks), pre(n_chunks + 1, 0);
-  for (uint64_t c = 0; c < n_chunks; ++c) cnt[c] = ing_chunk_starts(padded.data() + 16 * c, 16 * c, n);
+  for (uint64_t c = 0; c < n_chunks; ++c) cnt[c] = ing_chunk_starts(word_at(text + 16 * c), word_at(text + 16 * c + 8), 16 * c, n);
   for (uint64_t c = 0; c < n_chunks; ++c) pre[c + 1] = pre[c] + cnt[c];
   L.n_lines = pre[n_chunks];
   L.ls.assign(L.n_lines + 1, 0);
   for (uint64_t c = 0; c < n_chunks; ++c) {
     if (!cnt[c]) continue;
-    uint64_t idx = pre[c];
-    if (c == 0) L.ls[idx++] = 0;
-    for (int i = 0; i < 16; ++i)
-      if (16 * c + (uint64_t)i + 1 < n && padded[16 * c + i] == '\n') L.ls[idx++] = 16 * c + (uint64_t)i + 1;
+    const uint64_t end = ing_chunk_place(word_at(text + 16 * c), word_at(text + 16 * c + 8), 16 * c, n, L.ls.data(), pre[c]);
+    if (end != pre[c + 1]) abort();
   }
   L.ls[L.n_lines] = ing_sentinel(text, n);
   return L;
@@ -57,6 +55,40 @@ std::vector<uint64_t> fastq_headers(const uint8_t *text, const Lines &L) {
 
 extern "C" {
 
+// SWAR primitives against their byte-wise definitions: every byte value at every position, random words, and
+// ing_load8 / ing_token_end at every alignment.  Returns the number of disagreements.
+int emul_ingest_swar_check(void) {
+  int bad = 0;
+  uint64_t x = 0x9E3779B97F4A7C15ull;
+  for (int it = 0; it < 200000; ++it) {
+    x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+    uint64_t w = x;
+    if (it < 256 * 8) { const int pos = it & 7; w = (w & ~(0xffull << (8 * pos))) | ((uint64_t)(it >> 3) << (8 * pos)); }
+    if (it & 1) w &= 0x3f3f3f3f3f3f3f3full;                   // more low bytes: whitespace and newlines show up
+    uint64_t ws = 0, nl = 0;
+    for (int b = 0; b < 8; ++b) {
+      const uint8_t c = (uint8_t)(w >> (8 * b));
+      if (ing_space(c)) ws |= 0x80ull << (8 * b);
+      if (c == 10) nl |= 0x80ull << (8 * b);
+    }
+    if (ing_ws_mask(w) != ws) ++bad;
+    if (ing_eq_mask(w, 10) != nl) ++bad;
+  }
+  alignas(16) uint8_t buf[96];
+  for (int i = 0; i < 96; ++i) buf[i] = (uint8_t)(33 + (i * 7) % 90);
+  for (int off = 0; off < 24; ++off) {
+    uint64_t w; memcpy(&w, buf + off, 8);
+    if (ing_load8(buf, off) != w) ++bad;
+    for (int len = 0; len < 40; ++len) {
+      uint8_t t[96]; memcpy(t, buf, 96);
+      t[off + len] = (len % 3 == 0) ? ' ' : (len % 3 == 1 ? '\t' : '\r');
+      if (ing_token_end(t, off, 80) != (uint64_t)(off + len)) ++bad;
+      if (ing_token_end(t, off, off + len) != (uint64_t)(off + len)) ++bad;      // token runs to e
+    }
+  }
+  return bad;
+}
+
 // kind 0: SAM text (text1 ignored), 1: FASTQ pair.  Outputs are caller buffers sized generously
 // (names/seq/qual/opt: n0 + n1 bytes; offsets / read_flag: line count + 1).  Returns 0, or the IngErr code
 // with *err_index = record index.  out_info: n_reads, name_bytes, seq_bytes, opt_bytes, consumed0, consumed1, next phase.
@@ -64,10 +96,13 @@ int emul_ingest(int kind, int final, int replace_n, int phase, const uint8_t *te
                 uint8_t *names, int64_t *name_off, uint8_t *seq, uint8_t *qual, int64_t *seq_off, uint8_t *opt, int64_t *opt_off,
                 uint16_t *read_flag, uint64_t *out_info, uint64_t *err_index) {
   phase = kind ? (phase & 1) : 0;
-  const uint8_t *text[2] = {text0, text1};
+  const uint8_t *given[2] = {text0, text1};
   const uint64_t full[2] = {n0, kind ? n1 : 0};
   uint64_t nb[2] = {n0, kind ? n1 : 0};
-  if (!final) for (int f = 0; f < 2; ++f) while (nb[f] && text[f][nb[f] - 1] != '\n') --nb[f];
+  if (!final) for (int f = 0; f < 2; ++f) while (nb[f] && given[f][nb[f] - 1] != '\n') --nb[f];
+  std::vector<uint8_t> padded[2];                            // the device buffers: garbage past the text, 64 bytes of slack
+  const uint8_t *text[2];
+  for (int f = 0; f < 2; ++f) { padded[f].assign(nb[f] + 64, 0xAB); if (nb[f]) memcpy(padded[f].data(), given[f], nb[f]); text[f] = padded[f].data(); }
   Lines L[2];
   std::vector<uint64_t> hdr[2];
   uint64_t n_rec[2] = {0, 0}, n_take[2] = {0, 0};

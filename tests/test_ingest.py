@@ -177,6 +177,10 @@ def test_emulated_kernels_match_oracle_fuzz(seed):
             assert_same_batch(stream(E.ingest, 1, [fq1, fq2], sizes, rep), want)
 
 
+def test_swar_primitives():
+    assert E.ingest_lib().emul_ingest_swar_check() == 0
+
+
 def test_empty_and_ragged_inputs_emulated():
     for text in (b"", b"\n", b"\n\n\n"):
         r = E.ingest(0, text)
@@ -220,18 +224,24 @@ def test_real_kernels_on_host_fuzz_and_streaming():
 
 
 def test_real_kernels_on_host_many_tiles():
-    """4.5 MB of text in 32 very long lines: > 256 scan tiles, so k_ing_scan_top loops with a carry."""
+    """The same kernels built with scan tiles of 64 x 2 items: 1200 lines / 90 kB of text are 10 tiles of lines and
+    ~45 tiles of chunks, and 340 kB in long lines are ~165 tiles, so k_ing_scan_top runs a second round with a carry
+    (in the product geometry that takes 16 MB of text)."""
     rng = np.random.default_rng(9)
+    text = fuzz_sam(rng, 1200)
+    assert_same_batch(E.ingest_kernels_small(0, text), I.parse_sam_text(text))
+    fq1, fq2 = fuzz_fastq(rng, 400, 0), fuzz_fastq(rng, 403, 1)
+    assert_same_batch(E.ingest_kernels_small(1, fq1, fq2, True, True), I.parse_fastq_pair(fq1, fq2, True))
     lines = []
-    for i in range(32):
-        L = 70000 + int(rng.integers(0, 999))
+    for i in range(8):
+        L = 21000 + int(rng.integers(0, 999))
         seq = bytes(rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=L))
         qual = bytes(rng.integers(33, 127, size=L).astype(np.uint8))
         lines.append(b"long%d\t%d\t*\t0\t0\t*\t*\t0\t0\t" % (i, 77 if i % 2 == 0 else 141) + seq + b"\t" + qual
                      + (b"\tXX:Z:tail  \t YY:i:1" if i % 3 == 0 else b"") + b"\n")
     text = b"".join(lines)
-    assert len(text) // 16 // 1024 > 256
-    assert_same_batch(E.ingest_kernels(0, text), I.parse_sam_text(text))
+    assert len(text) // 16 // 128 > 128
+    assert_same_batch(E.ingest_kernels_small(0, text), I.parse_sam_text(text))
 
 
 BAD_SAM = [(b"a 77 * 0 0 * * 0 0 ACGT\n", 1), (b"a x77 * 0 0 * * 0 0 ACGT IIII\n", 2), (b"a 99999999999 * 0 0 * * 0 0 ACGT IIII\n", 2),
