@@ -30,7 +30,7 @@ struct Options {
   unsigned min_len = 20;
   int mode = SMASH_MODE_MAM;
   bool nucleotides_only = false, sam_out = false, verbose = false, nomap = false, rcref = false, fastq = false,
-       sam_in = false, mappability = false;
+       sam_in = false, mappability = false, fastq_pair = false, replace_n = false;
   int threads = 2;
   std::string ref;
   std::vector<std::string> inputs;
@@ -41,13 +41,15 @@ struct Options {
             << "  -mum | -mumreference | -mumcand | -maxmatch   match type (default: -mumreference)\n"
             << "  -l N   minimum match length (20)      -n   match only a, c, g, t\n"
             << "  -samin -samout -nomap -rcref -fastq -verbose -qthreads N -mappability\n"
-            << "  -minblock N -cached -normalmem (accepted for compatibility)\n";
+            << "  -minblock N -cached -normalmem (accepted for compatibility)\n"
+            << "  -fastqpair [-replaceN] <ref> <mate1.fq> <mate2.fq>   (extension) the two FASTQ files of a mate pair instead of\n"
+            << "      `-samin <(fastqs_to_sam mate1.fq mate2.fq [1])`; both are parsed on the GPU\n";
   std::exit(1);
 }
 
 Options parse(int argc, char **argv) {
   Options o;
-  enum { L = 1, MUMREF, MAXMATCH, MUM, MUMCAND, N, QTHREADS, SAMOUT, VERBOSE, NOMAP, RCREF, FASTQ, SAMIN, MAPPABILITY, CACHED, NORMALMEM, MINBLOCK };
+  enum { L = 1, MUMREF, MAXMATCH, MUM, MUMCAND, N, QTHREADS, SAMOUT, VERBOSE, NOMAP, RCREF, FASTQ, SAMIN, MAPPABILITY, CACHED, NORMALMEM, MINBLOCK, FASTQPAIR, REPLACEN };
   static const option table[] = {
       {"l", required_argument, nullptr, L},          {"mumreference", no_argument, nullptr, MUMREF},
       {"maxmatch", no_argument, nullptr, MAXMATCH},  {"mum", no_argument, nullptr, MUM},
@@ -57,7 +59,8 @@ Options parse(int argc, char **argv) {
       {"rcref", no_argument, nullptr, RCREF},        {"fastq", no_argument, nullptr, FASTQ},
       {"samin", no_argument, nullptr, SAMIN},        {"mappability", no_argument, nullptr, MAPPABILITY},
       {"cached", no_argument, nullptr, CACHED},      {"normalmem", no_argument, nullptr, NORMALMEM},
-      {"minblock", required_argument, nullptr, MINBLOCK}, {nullptr, 0, nullptr, 0}};
+      {"minblock", required_argument, nullptr, MINBLOCK}, {"fastqpair", no_argument, nullptr, FASTQPAIR},
+      {"replaceN", no_argument, nullptr, REPLACEN},  {nullptr, 0, nullptr, 0}};
   for (;;) {
     int idx = -1;
     const int c = getopt_long_only(argc, argv, "", table, &idx);
@@ -74,6 +77,8 @@ Options parse(int argc, char **argv) {
       case NOMAP: o.nomap = true; break;
       case RCREF: o.rcref = true; break;
       case FASTQ: o.fastq = true; break;
+      case FASTQPAIR: o.fastq_pair = true; break;
+      case REPLACEN: o.replace_n = true; break;
       case SAMIN: o.sam_in = true; break;
       case MAPPABILITY: o.mappability = true; break;
       case CACHED: case NORMALMEM: case MINBLOCK: break;
@@ -82,6 +87,9 @@ Options parse(int argc, char **argv) {
   }
   if (argc - optind < 2) { std::cerr << "There are too few arguments" << std::endl; usage(argv[0]); }
   if (o.fastq && o.sam_in) throw std::runtime_error("-fastq cannot be used with -samin");
+  if (o.fastq_pair && (o.fastq || o.sam_in)) throw std::runtime_error("-fastqpair cannot be used with -fastq or -samin");
+  if (o.fastq_pair && argc - optind != 3) throw std::runtime_error("-fastqpair takes the reference and exactly two fastq files");
+  if (o.replace_n && !o.fastq_pair) throw std::runtime_error("-replaceN can only be used with -fastqpair");
   if (o.nomap && !o.sam_out) throw std::runtime_error("-nomap can only be used with -sam_out");
   if (o.mappability && !o.rcref) throw std::runtime_error("-mappability requires -rcref");
   o.ref = argv[optind];
@@ -268,6 +276,7 @@ int main(int argc, char **argv) {
     const auto tq = std::chrono::steady_clock::now();
     const bool device_reader = o.sam_in && !getenv("SMASH_HOST_READER");   // -samin text is parsed on the GPU (smash_submit_text)
     for (size_t fi = 0; fi < o.inputs.size(); ++fi) {
+      if (o.fastq_pair && fi > 0) break;                            // the two inputs are ONE stream of pairs
       bool in_flight[SMASH_N_SLOTS] = {false, false};
       auto drain = [&](int slot) {
         smash_result r; check(smash_wait(ctx, slot, &r));
@@ -281,7 +290,48 @@ int main(int argc, char **argv) {
         }
       };
       int slot = 0; bool more = true;
-      if (device_reader) {
+      if (o.fastq_pair) {
+        // fastqs_to_sam's loop (fastqs_to_sam.cpp:47-95) + the SAM reader, both on the device: the two files are
+        // streamed through two pinned buffers; each call says how much of either it used and which mate the next
+        // chunk starts with.
+        FILE *f[2]; char *text[2]; size_t cap[2], len[2] = {0, 0}; bool eof[2] = {false, false};
+        size_t chunk_bytes = (size_t)128 << 20;
+        if (const char *e = getenv("SMASH_TEXT_CHUNK")) chunk_bytes = std::max<size_t>(4096, strtoull(e, nullptr, 10));
+        for (int k = 0; k < 2; ++k) {
+          f[k] = fopen(o.inputs[k].c_str(), "rb");
+          if (!f[k]) throw std::runtime_error("Could not open fastq file " + o.inputs[k]);      // fastqs_to_sam.cpp:35-37
+          cap[k] = chunk_bytes; text[k] = (char *)smash_host_alloc(cap[k]);
+          if (!text[k]) throw std::runtime_error("out of pinned host memory");
+        }
+        int mate2_first = 0;
+        for (;;) {
+          for (int k = 0; k < 2; ++k)
+            while (len[k] < cap[k] && !eof[k]) { const size_t got = fread(text[k] + len[k], 1, cap[k] - len[k], f[k]); len[k] += got; if (!got) eof[k] = true; }
+          const bool final = eof[0] && eof[1];
+          if (in_flight[slot]) drain(slot);
+          smash_text t{}; smash_text_info info{};
+          t.kind = SMASH_TEXT_FASTQ_PAIR;
+          t.flags = (final ? SMASH_TEXT_FINAL : 0) | (o.replace_n ? SMASH_TEXT_REPLACE_N : 0) | (mate2_first ? SMASH_TEXT_MATE2_FIRST : 0);
+          for (int k = 0; k < 2; ++k) { t.text[k] = text[k]; t.n_bytes[k] = len[k]; }
+          t.first_pair_ordinal = pairs_done;
+          check(smash_submit_text(ctx, slot, &t, SMASH_WANT_SAM, &info));
+          in_flight[slot] = true; n_queries += info.n_reads; pairs_done += (info.n_reads + 1) / 2;
+          mate2_first = info.mate2_first_next;
+          slot = (slot + 1) % SMASH_N_SLOTS;
+          if (final) break;
+          for (int k = 0; k < 2; ++k) {
+            if (!eof[k] && info.consumed[k] == 0 && len[k] == cap[k]) {     // nothing of a full buffer was usable: grow it
+              char *bigger = (char *)smash_host_alloc(2 * cap[k]);
+              if (!bigger) throw std::runtime_error("out of pinned host memory");
+              memcpy(bigger, text[k], len[k]); smash_host_free(text[k]); text[k] = bigger; cap[k] *= 2;
+            }
+            len[k] -= info.consumed[k];
+            memmove(text[k], text[k] + info.consumed[k], len[k]);
+          }
+        }
+        for (int k = 0; k < 2; ++k) { fclose(f[k]); smash_host_free(text[k]); }
+        more = false;
+      } else if (device_reader) {
         // QueryReader::run's SAM branch (query.cpp:625-648) on the device: the file is streamed through a pinned
         // buffer in large chunks; what a chunk leaves unconsumed (a cut line, an odd trailing read) is carried over.
         FILE *f = fopen(o.inputs[fi].c_str(), "rb");
@@ -312,7 +362,7 @@ int main(int argc, char **argv) {
         smash_host_free(text);
         more = false;
       }
-      QueryParser *qpp = device_reader ? nullptr : new QueryParser(o.inputs[fi], o);
+      QueryParser *qpp = (device_reader || o.fastq_pair) ? nullptr : new QueryParser(o.inputs[fi], o);
       Batch buf[SMASH_N_SLOTS];
       while (more) {
         QueryParser &qp = *qpp;

@@ -324,6 +324,33 @@ def test_driver_streams_sam_text_in_chunks(case, workdir):
     assert got == case["oix"].map_batch(case["reads"], min_len=20, n_threads=4)
 
 
+def test_driver_fastq_pair_matches_reference_pipeline(workdir):
+    """`mummer -fastqpair -replaceN ref r1.fq r2.fq` (both FASTQ files parsed on the GPU, streamed in small chunks)
+    against what the unmodified `fastqs_to_sam r1.fq r2.fq 1 | mummer -samin` printed (tests/golden/case_ingest)."""
+    import shutil, subprocess, glob, gzip
+    from helpers import GOLDEN, golden_lines
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "smash_paper_b200", "bin", "mummer")
+    d = os.path.join(workdir, "driver_fastqpair")
+    shutil.rmtree(d, ignore_errors=True)
+    os.makedirs(d)
+    for name, src in (("ref.fa", "case_basic/ref.fa.gz"), ("r1.fq", "case_ingest/r1.fq.gz"), ("r2.fq", "case_ingest/r2.fq.gz")):
+        open(os.path.join(d, name), "wb").write(gzip.open(os.path.join(GOLDEN, src)).read())
+    env = dict(os.environ, SMASH_TEXT_CHUNK="9000")
+    r = subprocess.run([exe, "-rcref", "-nomap", "-samout", "-fastqpair", "-replaceN", "ref.fa", "r1.fq", "r2.fq"],
+                       cwd=d, env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    hdr, lines = golden_lines(os.path.join(GOLDEN, "case_ingest", "mapout_fastq.sam.gz"))
+    got = []
+    files = glob.glob(os.path.join(d, "mapout", "*.txt"))
+    assert len(files) > 3
+    for f in files:
+        data = open(f, "rb").read()
+        assert data.startswith(hdr)
+        got += data[len(hdr):].splitlines(keepends=True)
+    assert sorted(got) == lines
+
+
 def test_two_shards_equal_one_run(case):
     """Read-sharded tail on ONE GPU: two contexts take the two halves of the pairs; with the key and edge
     exchange of multigpu.py (done in-process here) the summed counts equal the single-context run."""

@@ -268,6 +268,72 @@ def test_rejected_inputs_emulated():
             I.parse_fastq_pair(text, good, False)
 
 
+# ---- the C++ driver's streaming loops, over a fake library (tests/emul/fake_smash.cpp) -------------------------
+
+def _fake_smash():
+    import subprocess
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul")
+    so = os.path.join(here, "libfake_smash.so")
+    srcs = [os.path.join(here, "fake_smash.cpp"), os.path.join(here, "emul_ingest.cpp")]
+    deps = srcs + [os.path.join(here, "../../smash_paper_b200/csrc/ingest.cuh"), os.path.join(here, "../../include/smash_b200.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so] + srcs)
+    return so
+
+
+def _dump(batch):
+    out = []
+    for i in range(batch["n"]):
+        no, so, oo = batch["name_off"], batch["seq_off"], batch["opt_off"]
+        out.append(bytes(batch["names"][no[i]:no[i + 1]]) + b"\t%d\t" % batch["read_flag"][i] + bytes(batch["seq"][so[i]:so[i + 1]]) + b"\t"
+                   + bytes(batch["qual"][so[i]:so[i + 1]]) + bytes(batch["opt"][oo[i]:oo[i + 1]]) + b"\n")
+    return b"".join(out)
+
+
+def _run_driver(workdir, tag, args, files, chunk):
+    import glob, shutil, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "smash_paper_b200", "bin", "mummer")
+    if not os.path.exists(exe):
+        pytest.skip("smash_paper_b200/bin/mummer not built")
+    d = os.path.join(workdir, "fake_" + tag)
+    shutil.rmtree(d, ignore_errors=True)
+    os.makedirs(os.path.join(d, "ref.fa.bin"))
+    open(os.path.join(d, "ref.fa"), "w").write(">chr1\nACGT\n")
+    open(os.path.join(d, "ref.fa.bin", "rc1.i4.index.bin"), "w").write("present")
+    for name, data in files.items():
+        open(os.path.join(d, name), "wb").write(data)
+    env = dict(os.environ, LD_PRELOAD=_fake_smash(), SMASH_TEXT_CHUNK=str(chunk))
+    r = subprocess.run([exe, "-rcref", "-nomap", "-samout"] + args, cwd=d, env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    got = b""
+    for f in sorted(glob.glob(os.path.join(d, "mapout", "*.txt")), key=lambda f: int(f.split(".")[-2])):
+        data = open(f, "rb").read()
+        assert data.startswith(b"@HD\tfake\n")
+        got += data[len(b"@HD\tfake\n"):]
+    return got
+
+
+@pytest.mark.parametrize("chunk", [4096, 20000, 1 << 24])
+def test_driver_streaming_loops_over_fake_library(workdir, chunk):
+    """bin/mummer -samin and -fastqpair with text buffers smaller than the files (and smaller than some lines:
+    the buffer has to grow): what reaches the library, chunk after chunk, is the oracle's parse of the whole input."""
+    fq1, fq2 = gz("r1.fq.gz"), gz("r2.fq.gz")
+    got = _run_driver(workdir, "fq%d" % chunk, ["-fastqpair", "-replaceN", "ref.fa", "r1.fq", "r2.fq"], {"r1.fq": fq1, "r2.fq": fq2}, chunk)
+    assert got == _dump(I.parse_fastq_pair(fq1, fq2, True))
+    rng = np.random.default_rng(77)
+    a, b = fuzz_fastq(rng, 300, 0), fuzz_fastq(rng, 120, 1)          # mate 2 ends early: the rest of mate 1 is never printed
+    got = _run_driver(workdir, "fqn%d" % chunk, ["-fastqpair", "ref.fa", "r1.fq", "r2.fq"], {"r1.fq": a, "r2.fq": b}, chunk)
+    assert got == _dump(I.parse_fastq_pair(a, b, False))
+    got = _run_driver(workdir, "fqm%d" % chunk, ["-fastqpair", "ref.fa", "r1.fq", "r2.fq"], {"r1.fq": b, "r2.fq": a}, chunk)
+    assert got == _dump(I.parse_fastq_pair(b, a, False))
+    q = gz("quirks.sam.gz")
+    long_line = b"big\t77\t*\t0\t0\t*\t*\t0\t0\t" + b"A" * 9000 + b"\t" + b"I" * 9000 + b"\n"
+    text = q + long_line + q
+    got = _run_driver(workdir, "sam%d" % chunk, ["-samin", "ref.fa", "reads.sam"], {"reads.sam": text}, chunk)
+    assert got == _dump(I.parse_sam_text(text))
+
+
 # ------------------------------------------------------------------------------------------- GPU
 
 @pytest.fixture(scope="module")
