@@ -6,7 +6,8 @@ Runs the `-m gpu` parity tests HERE, without a GPU, against the product's own ke
 
     python tests/emul/run_on_cpu.py                       # 56 of the 62 parity tests (~15 min; see BUILDER_TESTS for the rest)
     python tests/emul/run_on_cpu.py -k "golden and mam"   # any pytest selection
-    python tests/emul/run_on_cpu.py --sanitize -k smoke   # kernels built with -fsanitize=alignment,bounds
+    python tests/emul/run_on_cpu.py --sanitize -k golden  # kernels built with -fsanitize=alignment,bounds
+    python tests/emul/run_on_cpu.py --tsan -k test_header # ThreadSanitizer: a missing __syncwarp/__syncthreads is a data race
 
 What it is for: finding logic, indexing, scan, shuffle and synchronisation bugs in a kernel change BEFORE spending
 GPU time on it.  What it is not: a CPU path of the product (nothing under smash_paper_b200/ can load it; the library
@@ -41,12 +42,16 @@ def env_for_shim(sanitize=False):
     env["SMASH_B200_LIB"] = so                                   # smash_paper_b200/api.py (tests opt in explicitly)
     env["LD_PRELOAD"] = so + (":" + env["LD_PRELOAD"] if env.get("LD_PRELOAD") else "")    # smash_paper_b200/bin/mummer
     env["SMASH_CUDA_SHIM"] = "1"
+    if sanitize == "thread":
+        tsan = subprocess.check_output(["gcc", "-print-file-name=libtsan.so"], text=True).strip()
+        env["LD_PRELOAD"] = tsan + ":" + env["LD_PRELOAD"]
+        env.setdefault("TSAN_OPTIONS", "halt_on_error=0 report_signal_unsafe=0 exitcode=66")
     return env
 
 
 def main(argv):
-    sanitize = "--sanitize" in argv                              # -fsanitize=alignment,bounds build of the kernels
-    argv = [a for a in argv if a != "--sanitize"]
+    sanitize = "thread" if "--tsan" in argv else "--sanitize" in argv    # sanitizer builds of the kernels
+    argv = [a for a in argv if a not in ("--sanitize", "--tsan")]
     args = [sys.executable, "-m", "pytest", "tests", "-m", "gpu", "-q", "-p", "no:cacheprovider", "--timeout=900"]
     for t in BUILDER_TESTS:
         args += ["--deselect", t]

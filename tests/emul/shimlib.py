@@ -81,9 +81,11 @@ def rewrite(text):
 
 def build(force=False, sanitize=False):
     """sanitize=True: a second library built with -fsanitize=alignment,bounds (aborts on a misaligned vector load or an
-    out-of-range index of a fixed-size array -- both fault or corrupt on the GPU, both are silent on a plain CPU build)."""
-    so = SO.replace(".so", "_san.so") if sanitize else SO
-    tag = "_san" if sanitize else ""
+    out-of-range index of a fixed-size array -- both fault or corrupt on the GPU, both are silent on a plain CPU build).
+    sanitize="thread": built with ThreadSanitizer (run under LD_PRELOAD=libtsan.so): lanes that exchange data through
+    shared or global memory without the __syncwarp / __syncthreads / atomic the GPU needs show up as data races."""
+    tag = "" if not sanitize else ("_tsan" if sanitize == "thread" else "_san")
+    so = SO.replace(".so", tag + ".so")
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
     deps += [os.path.join(HERE, "cuda_shim", "cuda_runtime.h"), os.path.abspath(__file__), os.path.join(ROOT, "include", "smash_b200.h")]
     if not force and os.path.exists(so) and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps):
@@ -102,8 +104,9 @@ def build(force=False, sanitize=False):
     open(stub, "w").write(STUB)
     srcs.append(stub)
     flags = ["-O1", "-std=c++20", "-fPIC", "-pthread", "-w", "-I", os.path.join(HERE, "cuda_shim"), "-I", GEN, "-I", os.path.join(ROOT, "include")]
+    san = [] if not sanitize else (["-fsanitize=thread"] if sanitize == "thread" else ["-fsanitize=alignment,bounds"])
     if sanitize:
-        flags += ["-g", "-fsanitize=alignment,bounds", "-fno-sanitize-recover=alignment,bounds"]
+        flags += ["-g"] + san + ([] if sanitize == "thread" else ["-fno-sanitize-recover=alignment,bounds"])
     procs = []
     for s in srcs:
         o = s.replace(".cpp", tag + ".o")
@@ -113,7 +116,7 @@ def build(force=False, sanitize=False):
         out, _ = p.communicate()
         if p.returncode:
             raise RuntimeError(f"shim build of {os.path.basename(s)} failed:\n{out[-6000:]}")
-    subprocess.check_call(["g++", "-shared", "-pthread"] + (["-fsanitize=alignment,bounds"] if sanitize else []) + ["-o", so] + objs)
+    subprocess.check_call(["g++", "-shared", "-pthread"] + san + ["-o", so] + objs)
     return so
 
 
@@ -123,4 +126,4 @@ def load(sanitize=False):
 
 if __name__ == "__main__":
     import sys
-    print(build(force="-f" in sys.argv, sanitize="--sanitize" in sys.argv))
+    print(build(force="-f" in sys.argv, sanitize="thread" if "--tsan" in sys.argv else "--sanitize" in sys.argv))
