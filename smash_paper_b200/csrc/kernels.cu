@@ -163,6 +163,34 @@ __device__ __forceinline__ void stage_push(SearchSmem &sm, int warp, const Match
   const int slot = atomicAdd(&sm.nstage[warp], 1);
   if (slot < STAGE_CAP) sm.stage[warp][slot] = m;
 }
+// Ordered emission of a warp's staged matches: rank by query offset.  A query offset carries at most ONE reportable
+// match (two unique maximal matches with the same start would make the shorter one a repeat), but it can be STAGED more
+// than once: every candidate of a saturated repeat family (U == 255, diagonal >= 255) falls back to exact_start at
+// the same start and finds the same match.  Copies are dropped here; returns the number of distinct matches written
+// (those with rank < cap).  All lanes of the warp must call it.
+__device__ __forceinline__ int emit_ranked(const Match *stage, int ns, Match *dst, int cap, int lane) {
+  static_assert(STAGE_CAP <= 64, "two ballots cover the stage");
+  bool f0 = false, f1 = false;
+  if (lane < ns) {
+    f0 = true;
+    const uint32_t qp = stage[lane].qpos;
+    for (int f = 0; f < lane; ++f) if (stage[f].qpos == qp) { f0 = false; break; }
+  }
+  if (lane + 32 < ns) {
+    f1 = true;
+    const uint32_t qp = stage[lane + 32].qpos;
+    for (int f = 0; f < lane + 32; ++f) if (stage[f].qpos == qp) { f1 = false; break; }
+  }
+  const unsigned m0 = __ballot_sync(0xffffffffu, f0), m1 = __ballot_sync(0xffffffffu, f1);
+  for (int e = lane; e < ns; e += 32) {
+    if (!(((e < 32 ? m0 >> e : m1 >> (e - 32)) & 1u))) continue;
+    const Match me = stage[e];
+    int rank = 0;
+    for (int f = 0; f < ns; ++f) rank += (stage[f].qpos < me.qpos && (((f < 32 ? m0 >> f : m1 >> (f - 32)) & 1u) != 0)) ? 1 : 0;
+    if (rank < cap) dst[rank] = me;
+  }
+  return __popc(m0) + __popc(m1);
+}
 // every start of the read through the exact per-start search (reads the anchor path cannot take)
 __device__ __noinline__ void exact_all(const DevIndex &ix, SearchSmem &sm, int warp, int lane, const uint8_t *P, int q, const SearchParams &sp) {
   for (int p = lane; p + (int)sp.L <= q; p += 32) {
@@ -385,26 +413,22 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     }
     }   // q <= MAXQ_FAST
     __syncwarp();
-    const int n = sm.nstage[warp];
-    const int ns = n < STAGE_CAP ? n : STAGE_CAP;
-    // ordered emission: rank by query offset (distinct per match in MAM mode)
+    const int n_raw = sm.nstage[warp];
+    const int ns = n_raw < STAGE_CAP ? n_raw : STAGE_CAP;
+    // ordered emission: rank by query offset, copies of a match dropped
     Match *dst = w.match_slots + slot_base(w, read);
-    for (int e = lane; e < ns; e += 32) {
-      const Match me = sm.stage[warp][e];
-      int rank = 0;
-      for (int f = 0; f < ns; ++f) rank += sm.stage[warp][f].qpos < me.qpos;
-      if (rank < w.cap) dst[rank] = me;
-    }
+    const int nu = emit_ranked(sm.stage[warp], ns, dst, w.cap, lane);
+    const int n = nu + (n_raw - ns);                                    // distinct matches (+ what did not fit the stage)
     int n_out = n;
     if (sp.mum && n <= w.cap && n <= STAGE_CAP && nsurv == 0) {        // (with parked candidates k_mam_verify runs the sweep)
       // -mum: the sweep needs the matches in emission (query) order -> copy the ordered slots back into the
       // stage, let lane 0 run the by_ref sort + cleanMUMcand sweep, survivors go to the slots in by_ref order
       __syncwarp();
-      for (int e = lane; e < ns; e += 32) sm.stage[warp][e] = dst[e];
+      for (int e = lane; e < nu; e += 32) sm.stage[warp][e] = dst[e];
       __syncwarp();
       if (lane == 0) {
         uint16_t ord[STAGE_CAP];
-        n_out = mum_clean(sm.stage[warp], ns, ord, dst);
+        n_out = mum_clean(sm.stage[warp], nu, ord, dst);
       }
       n_out = __shfl_sync(0xffffffffu, n_out, 0);
     }
@@ -499,20 +523,16 @@ k_mam_verify(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
       n_new += __popc(pass);
     }
     __syncwarp();
-    const int n = n_e_true + n_new;
+    const int n_raw = n_e_true + n_new;
     const int ns = n_e + n_new < STAGE_CAP ? n_e + n_new : STAGE_CAP;
-    for (int e = lane; e < ns; e += 32) {
-      const Match me = sm.stage[warp][e];
-      int rank = 0;
-      for (int f = 0; f < ns; ++f) rank += sm.stage[warp][f].qpos < me.qpos;
-      if (rank < w.cap) dst[rank] = me;
-    }
+    const int nu = emit_ranked(sm.stage[warp], ns, dst, w.cap, lane);
+    const int n = nu + (n_raw - ns);                                    // distinct matches (+ what did not fit the stage)
     int n_out = n;
     if (sp.mum && n <= w.cap && n <= STAGE_CAP) {
       __syncwarp();
-      for (int e = lane; e < ns; e += 32) sm.stage[warp][e] = dst[e];
+      for (int e = lane; e < nu; e += 32) sm.stage[warp][e] = dst[e];
       __syncwarp();
-      if (lane == 0) { uint16_t ord[STAGE_CAP]; n_out = mum_clean(sm.stage[warp], ns, ord, dst); }
+      if (lane == 0) { uint16_t ord[STAGE_CAP]; n_out = mum_clean(sm.stage[warp], nu, ord, dst); }
       n_out = __shfl_sync(0xffffffffu, n_out, 0);
     }
     if (lane == 0) {
@@ -553,21 +573,17 @@ k_mam_search_long(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
       }
     }
     __syncwarp();
-    const int n = sm.nstage[warp];
-    const int ns = n < STAGE_CAP ? n : STAGE_CAP;
+    const int n_raw = sm.nstage[warp];
+    const int ns = n_raw < STAGE_CAP ? n_raw : STAGE_CAP;
     Match *dst = w.match_slots + slot_base(w, read);
-    for (int e = lane; e < ns; e += 32) {
-      const Match me = sm.stage[warp][e];
-      int rank = 0;
-      for (int f = 0; f < ns; ++f) rank += sm.stage[warp][f].qpos < me.qpos;
-      if (rank < w.cap) dst[rank] = me;
-    }
+    const int nu = emit_ranked(sm.stage[warp], ns, dst, w.cap, lane);
+    const int n = nu + (n_raw - ns);                                    // distinct matches (+ what did not fit the stage)
     int n_out = n;
     if (sp.mum && n <= w.cap && n <= STAGE_CAP) {
       __syncwarp();
-      for (int e = lane; e < ns; e += 32) sm.stage[warp][e] = dst[e];
+      for (int e = lane; e < nu; e += 32) sm.stage[warp][e] = dst[e];
       __syncwarp();
-      if (lane == 0) { uint16_t ord[STAGE_CAP]; n_out = mum_clean(sm.stage[warp], ns, ord, dst); }
+      if (lane == 0) { uint16_t ord[STAGE_CAP]; n_out = mum_clean(sm.stage[warp], nu, ord, dst); }
       n_out = __shfl_sync(0xffffffffu, n_out, 0);
     }
     if (lane == 0) {

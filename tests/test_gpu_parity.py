@@ -351,6 +351,33 @@ def test_driver_fastq_pair_matches_reference_pipeline(workdir):
     assert sorted(got) == lines
 
 
+def test_saturated_repeat_family_reports_each_match_once(workdir):
+    """Found by fuzzing the emulated kernels: a read that runs through a > 255 bp repeat family (U saturated) makes
+    EVERY copy's candidate fall back to exact_start at the same query start, so the one true match was staged several
+    times; the rank sort then left slots unwritten and match_cnt counted the copies (bogus zero-length records).
+    The match CSR must equal the oracle's per read -- counts included."""
+    from smash_paper_b200 import api
+    kw = dict(n_chrom=2, chrom_len=4098, n_pairs=51, seed=945792, read_len=400, n_families=4, family_len=229, n_long=2,
+              n_highcopy=0, highcopy_copies=42, n_pad=200, sub_rate=0.0, z_rate=0.01)
+    ref, reads, fa, oix, body = make_case(os.path.join(workdir, "satrep"), **kw)
+    ix = api.Index.open(fa)
+    for min_len, nuc in ((9, True), (12, False), (20, False)):
+        ctx = api.Context(ix, device=0, min_len=min_len, nomap=True, nucleotides_only=nuc)
+        try:
+            res = ctx.map_batch(reads, want=api.WANT_SAM | api.WANT_MATCHES)
+            for i in range(reads.n):
+                q = bytes(reads.seq[reads.seq_off[i]:reads.seq_off[i + 1]]).lower()
+                if nuc:
+                    q = bytes(c if c in b"acgt" else ord("~") for c in q)
+                want = [tuple(int(x) for x in m) for m in oix.mam(q, min_len)]
+                got = [tuple(int(x) for x in m) for m in res.matches[res.match_off[i]:res.match_off[i + 1]]]
+                assert got == want, (min_len, nuc, i)
+            assert res.sam == oix.map_batch(reads, min_len=min_len, nucleotides_only=nuc)
+        finally:
+            ctx.close()
+    ix.close()
+
+
 def test_two_shards_equal_one_run(case):
     """Read-sharded tail on ONE GPU: two contexts take the two halves of the pairs; with the key and edge
     exchange of multigpu.py (done in-process here) the summed counts equal the single-context run."""

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SUBSET = ("test_header or test_mam_matches_and_sam or test_tagged_sam_and_tail or test_double_buffered_submit "
           "or (test_golden_mam_records and case_basic-mam_l20) or (test_golden_mem_records and case_basic-mem_l20) "
           "or (test_mum_mode and 20) or test_gpu_text_to_sam_matches_reference_records or test_gpu_empty_and_rejected_inputs "
-          "or test_driver_fastq_pair_matches_reference_pipeline")
+          "or test_driver_fastq_pair_matches_reference_pipeline or test_saturated_repeat_family_reports_each_match_once")
 
 
 @pytest.mark.skipif(os.environ.get("SMASH_CUDA_SHIM") == "1", reason="already inside the emulation")
