@@ -34,6 +34,7 @@ for seed in [x for x in range(lo, hi) for _ in range(REP)]:
               sub_rate=float(rng.choice([0.0, 0.0075, 0.03])), z_rate=float(rng.choice([0.0, 0.01, 0.05])))
     if os.environ.get('READ_LEN'): kw['read_len'] = int(os.environ['READ_LEN']); kw['n_pairs'] = min(kw['n_pairs'], 12)   # e.g. 1500: the long-read kernel
     min_len = int(rng.integers(8, 32)); mode = int(rng.choice([api.MODE_MAM, api.MODE_MAM, api.MODE_MUM, api.MODE_MEM]))
+    if os.environ.get('MODE'): mode = {'mam': api.MODE_MAM, 'mum': api.MODE_MUM, 'mem': api.MODE_MEM}[os.environ['MODE']]
     nomap = bool(rng.integers(0, 2)); nuc = bool(rng.integers(0, 2)); seed_k = int(rng.choice([0, 0, 5, 7, 9]))
     try:
         with tempfile.TemporaryDirectory() as d:
