@@ -350,7 +350,8 @@ def run_ours(args, wl, rank, world):
             try:
                 if "error" in ref_files:
                     raise RuntimeError(ref_files["error"])
-                out["cpu_baseline"] = cpu_baseline(args, wl, ref, ref_files, sample_pairs=args.cpu_sample_pairs, steps=1)
+                out["cpu_baseline"] = cpu_baseline(args, wl, ref, ref_files, sample_pairs=args.cpu_sample_pairs, steps=1, check_ctx=ctx)
+                out["parity_check"] = out["cpu_baseline"].pop("parity_check")
             except Exception as e:  # noqa: BLE001 -- the baseline must never break the bench line
                 out["cpu_baseline"] = {"error": str(e)[:300]}
     if out is not None and world == 1:
@@ -493,8 +494,43 @@ def prepare_reference_files(ref, ctx, workdir):
     return {"fa": fa, "workdir": workdir, "long_ints": long_ints, "built": built}
 
 
-def cpu_baseline(args, wl, ref, files, sample_pairs, steps):
-    """The UNMODIFIED reference (oracle/_ref/mummer[-long]) on the host cores, bounded sample per step."""
+def mapout_lines(workdir):
+    """Record lines of every chunk file the reference wrote under <workdir>/mapout (headers dropped)."""
+    import glob
+    lines = []
+    for fn in glob.glob(os.path.join(workdir, "mapout", "*.txt")):
+        with open(fn, "rb") as f:
+            lines += [ln for ln in f if not ln.startswith(b"@")]
+    return lines
+
+
+def parity_check(ctx, batch, ref_lines):
+    """The reads the reference binary has just mapped, through the GPU path (smash_map_batch, host buffers in,
+    SAM text out), compared line for line as sorted multisets (the reference's chunk membership and in-chunk order
+    depend on thread scheduling).  Returns the JSON object of the bench line."""
+    from smash_paper_b200 import api
+    ctx.set_tag_mappability(False)                       # the reference's mapout has no L/R tags (a later stage adds them)
+    try:
+        res = ctx.map_batch(batch, want=api.WANT_SAM)
+    finally:
+        ctx.set_tag_mappability(True)
+    ours = sorted(res.sam.splitlines(keepends=True))
+    theirs = sorted(ref_lines)
+    equal = ours == theirs
+    out = {"what": "sorted SAM record lines: oracle/_ref binary vs smash_map_batch on the same reads, this workload's index",
+           "reads": int(batch.n), "lines": len(theirs), "lines_gpu": len(ours), "equal": bool(equal)}
+    if not equal:
+        for a, b in zip(ours, theirs):
+            if a != b:
+                out["first_difference"] = {"gpu": a[:300].decode(errors="replace"), "reference": b[:300].decode(errors="replace")}
+                break
+    return out
+
+
+def cpu_baseline(args, wl, ref, files, sample_pairs, steps, check_ctx=None):
+    """The UNMODIFIED reference (oracle/_ref/mummer[-long]) on the host cores, bounded sample per step.
+    check_ctx: a GPU context on the same reference -> the first sample's mapout is kept and compared with the GPU
+    path's records for the same reads (`parity_check`)."""
     from oracle import oracle as O
     cores = os.cpu_count() or 2
     fa, workdir, long_ints, built = files["fa"], files["workdir"], files["long_ints"], files["built"]
@@ -510,6 +546,7 @@ def cpu_baseline(args, wl, ref, files, sample_pairs, steps):
         return time.perf_counter() - t
 
     genome = ref.concat()
+    parity = None
     # production flags (MAP_POPULATE): the zero-read run measures index mmap+populate and the per-thread
     # 500 MB arena initialisation, which is subtracted so that only mapping+SAM time remains
     run(empty)
@@ -520,6 +557,12 @@ def cpu_baseline(args, wl, ref, files, sample_pairs, steps):
         sam = os.path.join(workdir, f"sample{s}.sam")
         synth.write_sam(b, sam)
         wall = run(sam)
+        if check_ctx is not None and s == 0:
+            try:
+                parity = parity_check(check_ctx, b, mapout_lines(workdir))
+            except Exception as e:  # noqa: BLE001
+                parity = {"equal": False, "error": str(e)[:300]}
+            log(f"parity_check: {parity}")
         vals.append(2 * sample_pairs / max(wall - startup, 0.1 * wall))
         log(f"reference step {s}: {2 * sample_pairs} reads wall {wall:.2f}s startup {startup:.2f}s -> {vals[-1]:.0f} reads/s")
         os.unlink(sam)
@@ -527,7 +570,7 @@ def cpu_baseline(args, wl, ref, files, sample_pairs, steps):
             "sample": f"{2 * sample_pairs} reads/step x {steps} through oracle/_ref/{os.path.basename(exe)} -rcref -qthreads {max(2, cores)} "
                       f"-nomap -samin -samout; wall minus a zero-read run ({startup:.2f}s index mmap + buffer init); "
                       f"mapping+SAM only (mappability_tag/smashMEM/varbin stages not included)",
-            "index": built, "per_step": vals}
+            "index": built, "per_step": vals, "parity_check": parity}
 
 
 def run_reference(args, wl, rank, world):
@@ -599,6 +642,10 @@ def main():
     if rank == 0 and out is not None:
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(out) + "\n").encode())
+        pc = out.get("parity_check")
+        if pc is not None and not pc.get("equal"):
+            log("PARITY MISMATCH between the reference binary and the GPU path:", pc)
+            sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -96,6 +96,10 @@ int smash_ctx_load_mappability(smash_ctx *ctx, const uint8_t *body, uint64_t n_b
 /* Build map.bin's body on the GPU from SA/ISA/LCP (needs isa). Copies to host if body != NULL. */
 int smash_ctx_build_mappability(smash_ctx *ctx, uint8_t *body, uint64_t cap_bytes);
 
+/* Switch the L<i>/R<i> tagging of smash_params.tag_mappability on or off between batches (mappability_tag is a separate
+ * stage of smash_mapping.sh:23: `mummer`'s own mapout has no such tags).  Needs map.bin when switched on. */
+int smash_ctx_set_tag_mappability(smash_ctx *ctx, int on);
+
 /* ---- one batch of reads = what QueryReader::run hands to Pair::run (query.cpp:614-687, 481-520).
  * Reads 2k and 2k+1 are mates-by-arrival; n_reads must be even except for the last batch.
  * names: SAM column 1 without the :0/:1 suffix; read_flag: 0/65/129 as Aligner::reset derives it

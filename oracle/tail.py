@@ -70,9 +70,60 @@ def tag_lines(lines, names, sizes, mapbody):
     return [ln if ln.startswith(b"@") else tag_line(ln, offs, mapbody) for ln in lines]
 
 
-def _natural_key(name: bytes):
-    """samtools 0.1.x strnum_cmp order: digit runs compare numerically."""
-    return [int(t) if t.isdigit() else t for t in re.split(rb"(\d+)", name)]
+def strnum_cmp(a: bytes, b: bytes) -> int:
+    """`samtools sort -n` name order (smash_mapping.sh:23).  samtools is a third-party dependency that is absent from
+    /root/reference and from this image: the legacy `sort -n - prefix` syntax the script uses is samtools 0.1.x, whose
+    bam_sort.c compares query names with strnum_cmp -- digit runs compare as numbers (leading zeros skipped; equal
+    numbers: the run with FEWER leading zeros is greater), everything else bytewise -- and breaks ties with
+    flag & 0xc0 (read 1 before read 2) in a stable merge sort.  Restated here from that published algorithm."""
+    na, nb = len(a), len(b)
+    pa = pb = 0
+
+    def dig(s, i):
+        return i < len(s) and 48 <= s[i] <= 57
+
+    while pa < na and pb < nb:
+        if dig(a, pa) and dig(b, pb):
+            while pa < na and a[pa] == 48:
+                pa += 1
+            while pb < nb and b[pb] == 48:
+                pb += 1
+            while dig(a, pa) and dig(b, pb) and a[pa] == b[pb]:
+                pa += 1
+                pb += 1
+            if dig(a, pa) and dig(b, pb):
+                i = 0
+                while dig(a, pa + i) and dig(b, pb + i):
+                    i += 1
+                return 1 if dig(a, pa + i) else -1 if dig(b, pb + i) else a[pa] - b[pb]
+            if dig(a, pa):
+                return 1
+            if dig(b, pb):
+                return -1
+            if pa != pb:
+                return 1 if pa < pb else -1
+        else:
+            if a[pa] != b[pb]:
+                return a[pa] - b[pb]
+            pa += 1
+            pb += 1
+    return 1 if pa < na else -1 if pb < nb else 0
+
+
+def name_sort_lines(record_lines):
+    """Record lines (no header) in `samtools sort -n` order: strnum_cmp(qname), then flag & 0xc0, stable."""
+    import functools
+
+    def key(ln):
+        f = ln.split(b"\t", 2)
+        return f[0], int(f[1]) & 0xC0
+
+    def cmp(x, y):
+        return strnum_cmp(x[0][0], y[0][0]) or (x[0][1] - y[0][1])
+
+    keyed = [(key(ln), ln) for ln in record_lines]
+    keyed.sort(key=functools.cmp_to_key(cmp))
+    return [ln for _, ln in keyed]
 
 
 class _Hit:
@@ -127,7 +178,8 @@ def smash_filter(tagged_lines, chrom_names, min_match=0, min_ratio=0.0, hit_wind
     tid_of = {n: i for i, n in enumerate(chrom_names)}
     hits = [_parse_hit(ln, tid_of) for ln in tagged_lines if not ln.startswith(b"@")]
     if not presorted:
-        hits.sort(key=lambda h: _natural_key(h.name))          # samtools sort -n (stable here)
+        import functools
+        hits.sort(key=functools.cmp_to_key(lambda x, y: strnum_cmp(x.name, y.name) or ((x.flag & 0xC0) - (y.flag & 0xC0))))
     rows, dupes, n_dupe, n_non = [], set(), 0, 0
     i = 0
     while i < len(hits):

@@ -179,6 +179,11 @@ class Index:
     def text_len(self):
         return int(load_library().smash_index_text_len(self.h))
 
+    @property
+    def int_width(self):
+        """4 or 8: which of rc1.i4.index.* / rc1.i8.index.* was opened (size.h:9-22)."""
+        return int(load_library().smash_index_int_width(self.h))
+
     def sam_header(self):
         L = load_library()
         n = L.smash_index_sam_header(self.h, None, C.c_size_t(0))
@@ -448,6 +453,9 @@ class Context:
 
     def tail_reset(self):
         _check(load_library().smash_tail_reset(self.h))
+
+    def set_tag_mappability(self, on):
+        _check(load_library().smash_ctx_set_tag_mappability(self.h, int(bool(on))))
 
     def set_chunking(self, max_chunks=4, min_reads=65536):
         """smash_ctx_set_chunking: how smash_submit pipelines one batch (output is identical either way)."""

@@ -390,7 +390,9 @@ static int ctx_finish(smash_ctx *c, const smash_index *ix) {
   if (k <= 0) { k = (int)ceil(log((double)N) / log(4.0)) + 1; }
   if (k > 16) k = 16;
   if (k < 4) k = 4;
-  d.seed_k = k; d.seed_w = N < 0xffffffffull ? 4 : 8;
+  // seed entries follow the index's integer width (size.h:9-22): an i8 index of a small text runs the very
+  // code path of the hg19-scale one (8-byte SA entries AND 8-byte seed entries)
+  d.seed_k = k; d.seed_w = (ix->w == 8 || N >= 0xffffffffull) ? 8 : 4;
   CK(dmalloc(&c->seed, ((1ull << (2 * k)) + 1) * d.seed_w, &c->index_bytes));
   c->launches += launch_seed_build(d, c->seed, k, d.seed_w, st);
   d.seed = c->seed;
@@ -1318,6 +1320,13 @@ extern "C" int smash_ctx_drop_isa(smash_ctx *c) {
 extern "C" int smash_memcpy(void *dst, const void *src, size_t bytes) {
   if (!bytes) return 0;
   CU(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));       // UVA: any of host/device on either side
+  return 0;
+}
+extern "C" int smash_ctx_set_tag_mappability(smash_ctx *c, int on) {
+  if (!c) return fail(SMASH_ERR_ARG, "null argument");
+  if (on && !c->dix.mapbody) return fail(SMASH_ERR_STATE, "tagging needs map.bin (smash_ctx_load_mappability / smash_ctx_build_mappability)");
+  for (int s = 0; s < SMASH_N_SLOTS; ++s) if (c->slot[s].busy) return fail(SMASH_ERR_STATE, "slot %d still has a batch in flight", s);
+  c->prm.tag_mappability = on ? 1 : 0; c->sp.tag_mappability = c->prm.tag_mappability;
   return 0;
 }
 extern "C" int smash_ctx_set_chunking(smash_ctx *c, int max_chunks, uint64_t min_reads) {

@@ -64,6 +64,39 @@ def test_tagger_and_varbin_equal_reference():
     assert T.varbin_text(bins, counts, kept).encode() == gzip.open(os.path.join(d, "varbin.txt.gz")).read()   # varbin.py output
 
 
+@pytest.mark.parametrize("case", ["case_basic", "case_tail"])
+def test_smash_filter_equals_unmodified_smashmem_script(case):
+    """oracle/tail.py:smash_filter against what the UNMODIFIED /root/reference/smashMEM.py printed for the same tagged SAM
+    (tests/golden/make_golden_smash.py: the script run over a test-only pysam stand-in and the restated samtools name
+    sort).  case_tail: read-2 hits at 500/9999/10000/10001/25000 bp from a read-1 hit, cross-pair duplicates far apart,
+    read names whose name order is not the input order, chrM/_gl000 hits, excess-mappability failures."""
+    d = os.path.join(GOLDEN, case)
+    tagged = gzip.open(os.path.join(d, "tagged.sam.gz")).read().splitlines(keepends=True)
+    names = [ln.split(b"\t")[1][3:].decode() for ln in tagged if ln.startswith(b"@SQ")]
+    rows, nd, nn = T.smash_filter(tagged, names)
+    assert T.smash_text(rows, nd, nn).encode() == gzip.open(os.path.join(d, "smash.txt.gz")).read()
+    pos = T.positions(rows)
+    assert "".join(p + "\n" for p in pos).encode() == gzip.open(os.path.join(d, "positions.txt.gz")).read()
+    bins = T.read_table(os.path.join(d, "bins.txt"))
+    ci = T.read_chrominfo(os.path.join(d, "chrom_sizes.txt"))
+    counts, total, dups, kept = T.varbin(pos, bins, ci)
+    assert T.varbin_text(bins, counts, kept).encode() == gzip.open(os.path.join(d, "varbin.txt.gz")).read()   # varbin.py output
+    if case == "case_tail":
+        assert nd > 10 and dups > 0 and total > kept                       # the stress cases are really in there
+        in_order = [ln.split(b"\t")[0] for ln in gzip.open(os.path.join(d, "reads.sam.gz")).read().splitlines()][::2]
+        assert in_order != [ln.split(b"\t")[0] for ln in T.name_sort_lines([n + b"\t77\t" for n in in_order])]
+
+
+def test_samtools_name_order():
+    """strnum_cmp (samtools 0.1.x bam_sort.c): digit runs as numbers, fewer leading zeros sorts later, ties by mate."""
+    c = T.strnum_cmp
+    assert c(b"r9", b"r10") < 0 and c(b"r10", b"r9") > 0 and c(b"r10", b"r10") == 0
+    assert c(b"r010", b"r10") < 0 and c(b"r10", b"r010") > 0
+    assert c(b"x:12:5", b"x:2:50") > 0 and c(b"a1b", b"a1c") < 0 and c(b"a", b"a1") < 0 and c(b"a2", b"ab") < 0
+    lines = [b"b\t141\tx\n", b"a10\t77\tx\n", b"b\t77\tx\n", b"a9\t141\tx\n", b"a9\t77\tx\n"]
+    assert T.name_sort_lines(lines) == [lines[4], lines[3], lines[1], lines[2], lines[0]]
+
+
 def test_bruteforce_spec_agrees_with_faithful_mam():
     """SURVEY App. A.1 (index-free brute force) == the faithful suffix-link MAM on a tiny text."""
     rng = np.random.default_rng(5)
