@@ -110,7 +110,9 @@ typedef struct {
   const uint8_t *seq;    const uint8_t *qual;  const int64_t *seq_off;
   const uint8_t *opt;    const int64_t *opt_off;    /* may be NULL */
   const uint16_t *read_flag;
-  uint64_t first_pair_ordinal;   /* global index of the batch's first pair (dedupe order) */
+  uint64_t first_pair_ordinal;   /* informational only (kept for layout compatibility): the tail orders read pairs the way
+                                  * the reference pipeline does -- by read name, `samtools sort -n` order (smash_mapping.sh:23) --
+                                  * which is the order of submission whenever the input is already name-ordered */
 } smash_batch;
 
 typedef struct {
@@ -198,7 +200,13 @@ typedef struct {
   uint64_t n_dupe_pairs, n_non_dupe_pairs;          /* smashMEM.py:230 trailer */
   uint64_t n_positions;                             /* lines of <id>.positions.txt */
 } smash_tail_stats;
-/* counts: n_bins int64 (this rank's counts; the caller allreduces across GPUs).  If
+/* Pair order: smashMEM.py reads a BAM that `samtools sort -n` has put in read-name order, so its first-wins duplicate
+ * rule, the order of positions.txt and varbin's adjacent-duplicate rule follow NAME order (samtools 0.1.x strnum_cmp),
+ * not arrival order.  The library keeps the name of every pair (reads 2k and 2k+1 are mates and share it), checks the
+ * order while batches are appended and, if any pair arrived out of order, sorts the pairs by name on the device before
+ * counting -- results do not depend on the order or batching of the input.  The read-sharded phases below need
+ * name-ordered input (shards are contiguous ranges) and fail with SMASH_ERR_DATA otherwise.
+ * counts: n_bins int64 (this rank's counts; the caller allreduces across GPUs).  If
  * counts_device != NULL the counts are also left in that device buffer (for NCCL). */
 int smash_tail_finish(smash_ctx *ctx, int64_t *counts, void *counts_device, smash_tail_stats *st);
 /* ---- read-sharded multi-GPU tail (one context per rank; the host moves the small arrays with

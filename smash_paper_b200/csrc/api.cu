@@ -228,6 +228,7 @@ struct Slot {
   cudaStream_t st_in = nullptr, st_out = nullptr;                  // chunked submit: upload / download streams
   cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_emit[MAX_CHUNKS] = {}, ev_out = nullptr;
   int n_chunks = 1; uint64_t chunk_r[MAX_CHUNKS + 1] = {}; uint64_t sam_base = 0;
+  uint64_t chunk_name_bytes[MAX_CHUNKS] = {};                      // name bytes of each read range (upper bound)
   cudaEvent_t evs[N_EVS] = {};   // stage boundaries
   int n_evs = 0; int ev_stage[N_EVS];
   cudaEvent_t tl[3] = {nullptr, nullptr, nullptr};   // SMASH_DEBUG_TIMING timeline: submit, D2H begin, D2H end
@@ -321,10 +322,18 @@ static void set_search_params(smash_ctx *c) {
 #define CK(x) do { if ((rc = (x))) { smash_ctx_destroy(c); return rc; } } while (0)
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { smash_ctx_destroy(c); return fail(SMASH_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
 
-static int ctx_begin(const smash_params *p, smash_ctx **out) {
+static int ctx_begin(const smash_params *p, smash_ctx **out, int rcref) {
+  if (p->tag_mappability && !rcref) return fail(SMASH_ERR_ARG, "tag_mappability requires an -rcref index (mummer.cpp:145)");
   if (smash_device_count() <= 0) return fail(SMASH_ERR_CUDA, "no sm_100 CUDA device available (this library has no CPU fallback)");
   if (p->mode != SMASH_MODE_MAM && p->mode != SMASH_MODE_MEM && p->mode != SMASH_MODE_MUM) return fail(SMASH_ERR_ARG, "mode %d not supported", p->mode);
   CU(cudaSetDevice(p->device));
+  {
+    // The index is probed with isolated 2..16-byte reads scattered over > 100 GB: ask the L2 to fetch single 32-byte
+    // sectors on a miss instead of its default multi-sector granule (a hint; SMASH_L2_FETCH=64|128 for A/B runs).
+    size_t gran = 32;
+    if (const char *e = getenv("SMASH_L2_FETCH")) gran = (size_t)atoi(e);
+    if (gran == 32 || gran == 64 || gran == 128) { if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) cudaGetLastError(); }
+  }
   smash_ctx *c = new smash_ctx();
   c->prm = *p; c->device = p->device;
   for (int s = 0; s < SMASH_N_SLOTS; ++s) {
@@ -415,7 +424,7 @@ extern "C" int smash_ctx_create(const smash_index *ix, const smash_params *p, sm
   if (!ix->text || !ix->sa) return fail(SMASH_ERR_ARG, "index has no host arrays");
   if (p->mode == SMASH_MODE_MEM && !ix->isa) return fail(SMASH_ERR_ARG, "MEM mode needs the .isa.bin array");
   smash_ctx *c = nullptr;
-  int rc = ctx_begin(p, &c);
+  int rc = ctx_begin(p, &c, ix->rcref);
   if (rc) return rc;
   c->hix = ix;
   const uint64_t N = ix->N; const int w = ix->w;
@@ -458,7 +467,7 @@ extern "C" int smash_ctx_create_from_text(const uint8_t *text, uint64_t N, uint6
     return fail(SMASH_ERR_ARG, "bad argument");
   if (w == 4 && N >= 0xffffffffull) return fail(SMASH_ERR_ARG, "text too long for 4-byte index integers");
   smash_ctx *c = nullptr;
-  int rc = ctx_begin(p, &c);
+  int rc = ctx_begin(p, &c, rcref ? 1 : 0);
   if (rc) return rc;
   smash_index *ix = new smash_index();
   ix->N = N; ix->w = w; ix->rcref = rcref ? 1 : 0;
@@ -612,6 +621,8 @@ extern "C" void smash_ctx_destroy(smash_ctx *c) {
 
 extern "C" int smash_ctx_load_mappability(smash_ctx *c, const uint8_t *body, uint64_t n) {
   if (!c || !body) return fail(SMASH_ERR_ARG, "null argument");
+  // map.bin exists only for -rcref indexes (mummer.cpp:145); the L/R tags and the tail index it by forward chromosome
+  if (!c->hix->rcref) return fail(SMASH_ERR_ARG, "mappability requires an -rcref index");
   CU(cudaSetDevice(c->device));
   if (c->mapbody) { cudaFree(c->mapbody); c->mapbody = nullptr; }
   int rc = dmalloc((void **)&c->mapbody, n, &c->index_bytes);
@@ -684,6 +695,7 @@ static int slot_reserve(smash_ctx *c, Slot &s, uint64_t n, size_t name_bytes, si
     s.chunk_r[s.n_chunks] = n;
   }
   s.name_bytes = name_bytes; s.seq_bytes = seq_bytes; s.opt_bytes = opt_bytes;
+  for (int ch = 0; ch < MAX_CHUNKS; ++ch) s.chunk_name_bytes[ch] = name_bytes;
   s.bd.n_reads = n; s.bd.names = s.names.p; s.bd.name_off = s.name_off.p; s.bd.seq = s.seq.p; s.bd.qual = s.qual.p;
   s.bd.seq_off = s.seq_off.p; s.bd.opt = opt_bytes ? s.opt.p : nullptr; s.bd.opt_off = opt_bytes ? s.opt_off.p : nullptr;
   s.bd.read_flag = s.read_flag.p;
@@ -717,6 +729,7 @@ static int slot_prepare(smash_ctx *c, Slot &s, const smash_batch *b, bool copy, 
       const uint64_t r0 = s.chunk_r[ch], r1 = s.chunk_r[ch + 1];
       if (r1 > r0) {
         const size_t n0 = (size_t)b->name_off[r0], n1 = (size_t)b->name_off[r1], q0 = (size_t)b->seq_off[r0], q1 = (size_t)b->seq_off[r1];
+        s.chunk_name_bytes[ch] = n1 - n0;
         CU(cudaMemcpyAsync(s.names.p + n0, b->names + n0, n1 - n0, cudaMemcpyHostToDevice, in));
         CU(cudaMemcpyAsync(s.seq.p + q0, b->seq + q0, q1 - q0, cudaMemcpyHostToDevice, in));
         CU(cudaMemcpyAsync(s.qual.p + q0, b->qual + q0, q1 - q0, cudaMemcpyHostToDevice, in));
@@ -868,7 +881,7 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
   }
   if (want & SMASH_WANT_TAIL) {
     const double tt = now_ms();
-    int rc = tail_accumulate(&c->tail, c->dix, s.bd, work_of(s), recs, s.st, &c->launches);
+    int rc = tail_accumulate(&c->tail, c->dix, s.bd, work_of(s), recs, s.chunk_name_bytes[ch], s.st, &c->launches);
     DBG_T("  run:tail_accumulate", tt);
     if (rc) return fail(rc, "tail: %s", tail_error());
     MARK(5);
@@ -1215,6 +1228,7 @@ extern "C" int smash_tail_configure(smash_ctx *c, const int64_t *bin_starts, uin
                                     uint64_t n_chroms, int64_t hit_window, int32_t min_excess) {
   if (!c || !bin_starts || !n_bins) return fail(SMASH_ERR_ARG, "bad argument");
   if (!c->dix.mapbody) return fail(SMASH_ERR_STATE, "the tail needs map.bin (smash_ctx_load_mappability / smash_ctx_build_mappability)");
+  if (!c->hix->rcref) return fail(SMASH_ERR_ARG, "the tail requires an -rcref index (forward sequences at even seq_index)");
   CU(cudaSetDevice(c->device));
   // per forward chromosome: passes /^chr(\d+|[XY])$/ (smash_mapping.sh:29) and is listed in
   // chrom_sizes.txt without '_' / chrM (varbin.py:38-49) -> its absolute offset, else -1
@@ -1264,7 +1278,7 @@ extern "C" int smash_tail_phase_a(smash_ctx *c, uint64_t ordinal_base, const voi
   if (!c) return fail(SMASH_ERR_ARG, "null argument");
   CU(cudaSetDevice(c->device));
   for (int s = 0; s < SMASH_N_SLOTS; ++s) CU(cudaStreamSynchronize(c->slot[s].st));
-  int rc = tail_phase_a(&c->tail, ordinal_base, (const uint64_t *)foreign_keys_dev, n_foreign, edge, c->slot[0].st, &c->launches, nullptr);
+  int rc = tail_phase_a(&c->tail, ordinal_base, (const uint64_t *)foreign_keys_dev, n_foreign, edge, c->slot[0].st, &c->launches, nullptr, true);
   if (rc) return fail(rc, "tail: %s", tail_error());
   return 0;
 }
@@ -1275,7 +1289,7 @@ extern "C" int smash_tail_phase_a_verdict(smash_ctx *c, uint64_t ordinal_base, c
   for (int s = 0; s < SMASH_N_SLOTS; ++s) CU(cudaStreamSynchronize(c->slot[s].st));
   static const uint64_t dummy = 0;
   int rc = tail_phase_a(&c->tail, ordinal_base, nullptr, 0, edge, c->slot[0].st, &c->launches,
-                        n_keys ? (const uint64_t *)min_ordinal_dev : &dummy);
+                        n_keys ? (const uint64_t *)min_ordinal_dev : &dummy, true);
   if (rc) return fail(rc, "tail: %s", tail_error());
   return 0;
 }

@@ -435,7 +435,9 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     if (lane == 0) {
       w.match_cnt[read] = (uint32_t)n_out;
       if (w.surv) w.surv_cnt[read] = (uint8_t)nsurv;
-      if (n > w.cap || n > STAGE_CAP) { atomicAdd(&w.flags[FLAG_OVERFLOW], 1u); atomicMax(&w.flags[FLAG_MAXCNT], (uint32_t)n); }
+      // more staged entries than the stage holds (copies of a saturated repeat family included): the dropped ones may
+      // have been distinct matches, so this is always an overflow, never a silent count
+      if (n > w.cap || n_raw > STAGE_CAP) { atomicAdd(&w.flags[FLAG_OVERFLOW], 1u); atomicMax(&w.flags[FLAG_MAXCNT], (uint32_t)(n_raw > STAGE_CAP ? n_raw : n)); }
     }
     __syncwarp();
   }
@@ -537,7 +539,9 @@ k_mam_verify(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     }
     if (lane == 0) {
       w.match_cnt[read] = (uint32_t)n_out;
-      if (n > w.cap || n > STAGE_CAP) { atomicAdd(&w.flags[FLAG_OVERFLOW], 1u); atomicMax(&w.flags[FLAG_MAXCNT], (uint32_t)n); }
+      // more staged entries than the stage holds (copies of a saturated repeat family included): the dropped ones may
+      // have been distinct matches, so this is always an overflow, never a silent count
+      if (n > w.cap || n_raw > STAGE_CAP) { atomicAdd(&w.flags[FLAG_OVERFLOW], 1u); atomicMax(&w.flags[FLAG_MAXCNT], (uint32_t)(n_raw > STAGE_CAP ? n_raw : n)); }
     }
     __syncwarp();
   }
@@ -588,7 +592,9 @@ k_mam_search_long(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     }
     if (lane == 0) {
       w.match_cnt[read] = (uint32_t)n_out;
-      if (n > w.cap || n > STAGE_CAP) { atomicAdd(&w.flags[FLAG_OVERFLOW], 1u); atomicMax(&w.flags[FLAG_MAXCNT], (uint32_t)n); }
+      // more staged entries than the stage holds (copies of a saturated repeat family included): the dropped ones may
+      // have been distinct matches, so this is always an overflow, never a silent count
+      if (n > w.cap || n_raw > STAGE_CAP) { atomicAdd(&w.flags[FLAG_OVERFLOW], 1u); atomicMax(&w.flags[FLAG_MAXCNT], (uint32_t)(n_raw > STAGE_CAP ? n_raw : n)); }
     }
     __syncwarp();
   }

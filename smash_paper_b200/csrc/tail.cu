@@ -16,6 +16,11 @@
 #include <vector>
 
 #include "tail.cuh"
+#if !defined(SMASH_CUDA_SHIM)
+#include <cub/device/device_merge_sort.cuh>
+#else
+#include <algorithm>
+#endif
 #include <chrono>
 #include <stdlib.h>
 static const bool t_dbg = getenv("SMASH_DEBUG_TIMING") != nullptr;
@@ -51,10 +56,17 @@ template struct DGrow<uint32_t>;
 template struct DGrow<uint8_t>;
 template struct DGrow<uint64_t>;
 
+// device-side running totals (t->d_nhits): kept hits, bytes in name_blob, pairs out of name order
+enum { CNT_HITS = 0, CNT_NAME_BYTES = 1, CNT_ORDER_VIOLATIONS = 2, N_TAIL_COUNTERS = 4 };
+
 void tail_init(TailState *) {}
-void tail_reset(TailState *t) { t->n_pairs = 0; t->n_hits_bound = 0; t->n_positions = 0; if (t->d_nhits) cudaMemset(t->d_nhits, 0, 8); }
+void tail_reset(TailState *t) {
+  t->n_pairs = 0; t->n_hits_bound = 0; t->n_name_bound = 0; t->n_positions = 0; t->order_violations = 0;
+  if (t->d_nhits) cudaMemset(t->d_nhits, 0, 8 * N_TAIL_COUNTERS);
+}
 void tail_release(TailState *t) {
   t->pair_nhits.release(); t->pair_fp.release(); t->pair_hit_off.release(); t->hits.release();
+  t->name_blob.release(); t->pair_name_off.release();
   for (auto &b : t->scr) b.release();
   t->exp_keys.release();
   void *d[] = {t->bin_starts, t->chrom_off, t->batch_cnt, t->batch_off, t->blk, t->counts, t->pos_chrom, t->pos_pos, t->d_nhits};
@@ -147,6 +159,78 @@ __global__ void k_pair_write(BatchDev b, WorkDev w, PairParams pp, uint64_t n_pa
   }
 }
 
+// ---- read-name order.  smashMEM.py walks a BAM that `samtools sort -n` has put in name order (smash_mapping.sh:23-26):
+// its first-wins dedupe, the order of positions.txt and with it varbin's adjacent-duplicate rule (varbin.py:56-58) all
+// follow that order, not the order the reads were mapped in.  samtools 0.1.x compares names with strnum_cmp (bam_sort.c:
+// digit runs as numbers, leading zeros skipped, of two equal numbers the one with FEWER leading zeros is greater; other
+// bytes by value), ties broken by mate.  The pairs' names are kept, every pair is checked against its predecessor while
+// its batch is appended, and tail_finish sorts the pairs by name only if some pair was out of order.
+__host__ __device__ inline bool nm_digit(const uint8_t *s, uint64_t n, uint64_t i) { return i < n && s[i] >= '0' && s[i] <= '9'; }
+__host__ __device__ inline int strnum_cmp(const uint8_t *a, uint64_t na, const uint8_t *b, uint64_t nb) {
+  uint64_t pa = 0, pb = 0;
+  while (pa < na && pb < nb) {
+    if (nm_digit(a, na, pa) && nm_digit(b, nb, pb)) {
+      while (pa < na && a[pa] == '0') ++pa;
+      while (pb < nb && b[pb] == '0') ++pb;
+      while (nm_digit(a, na, pa) && nm_digit(b, nb, pb) && a[pa] == b[pb]) { ++pa; ++pb; }
+      if (nm_digit(a, na, pa) && nm_digit(b, nb, pb)) {
+        uint64_t i = 0;
+        while (nm_digit(a, na, pa + i) && nm_digit(b, nb, pb + i)) ++i;
+        return nm_digit(a, na, pa + i) ? 1 : nm_digit(b, nb, pb + i) ? -1 : (int)a[pa] - (int)b[pb];
+      }
+      if (nm_digit(a, na, pa)) return 1;
+      if (nm_digit(b, nb, pb)) return -1;
+      if (pa != pb) return pa < pb ? 1 : -1;
+    } else {
+      if (a[pa] != b[pb]) return (int)a[pa] - (int)b[pb];
+      ++pa; ++pb;
+    }
+  }
+  return pa < na ? 1 : pb < nb ? -1 : 0;
+}
+__global__ void k_pair_name_len(BatchDev b, uint64_t n_pairs, uint32_t *__restrict__ cnt) {
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (uint64_t)gridDim.x * blockDim.x)
+    cnt[p] = (uint32_t)(b.name_off[2 * p + 1] - b.name_off[2 * p]);
+}
+__global__ void k_pair_name_copy(BatchDev b, uint64_t n_pairs, const uint64_t *__restrict__ off, uint64_t pair_base,
+                                 uint64_t *counters, uint8_t *__restrict__ blob, uint64_t *__restrict__ pair_name_off) {
+  const uint64_t base = counters[CNT_NAME_BYTES];
+  unsigned viol = 0;
+  for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (uint64_t)gridDim.x * blockDim.x) {
+    const uint8_t *nm = b.names + b.name_off[2 * p];
+    const uint64_t len = (uint64_t)(b.name_off[2 * p + 1] - b.name_off[2 * p]), o = base + off[p];
+    for (uint64_t i = 0; i < len; ++i) blob[o + i] = nm[i];
+    pair_name_off[pair_base + p] = o;
+    if (p + 1 == n_pairs) pair_name_off[pair_base + n_pairs] = o + len;
+    if (p) {
+      const uint64_t lp = (uint64_t)(b.name_off[2 * p - 1] - b.name_off[2 * p - 2]);
+      if (strnum_cmp(b.names + b.name_off[2 * p - 2], lp, nm, len) > 0) ++viol;
+    } else if (pair_base) {                                   // against the last pair of the previous batch
+      const uint64_t po = pair_name_off[pair_base - 1];
+      if (strnum_cmp(blob + po, base - po, nm, len) > 0) ++viol;
+    }
+  }
+  if (viol) atomicAdd((unsigned long long *)&counters[CNT_ORDER_VIOLATIONS], (unsigned long long)viol);
+}
+struct NameLess {
+  const uint8_t *blob; const uint64_t *off;
+  __host__ __device__ bool operator()(uint32_t x, uint32_t y) const {
+    const int c = strnum_cmp(blob + off[x], off[x + 1] - off[x], blob + off[y], off[y + 1] - off[y]);
+    return c < 0 || (c == 0 && x < y);                        // equal names keep their arrival order (stable merge sort)
+  }
+};
+__global__ void k_perm_iota(uint32_t *__restrict__ v, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) v[i] = (uint32_t)i;
+}
+__global__ void k_permute_pairs(const uint32_t *__restrict__ perm, uint64_t n, const uint32_t *__restrict__ nhits, const uint64_t *__restrict__ fp,
+                                const uint64_t *__restrict__ hit_off, uint32_t *__restrict__ nhits2, uint64_t *__restrict__ fp2,
+                                uint64_t *__restrict__ hit_off2) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t j = perm[i];
+    nhits2[i] = nhits[j]; fp2[2 * i] = fp[2 * j]; fp2[2 * i + 1] = fp[2 * j + 1]; hit_off2[i] = hit_off[j];
+  }
+}
+
 // exclusive scan helper lives in kernels.cu
 int exclusive_scan_u32_public(const uint32_t *in, uint64_t n, uint64_t *blk, uint64_t *out, cudaStream_t st);
 
@@ -155,12 +239,12 @@ __global__ void k_bump(uint64_t *total, const uint64_t *batch_total) { *total +=
 // No host synchronisation here: the running hit total lives on the device (t->d_nhits) and the
 // host only keeps an upper bound (every kept hit is one of the batch's records) for capacity.
 int tail_accumulate(TailState *t, const DevIndex &ix, const BatchDev &b, const WorkDev &w,
-                    uint64_t n_records_bound, cudaStream_t st, uint64_t *launches) {
+                    uint64_t n_records_bound, uint64_t name_bytes_bound, cudaStream_t st, uint64_t *launches) {
   if (!t->configured) return tfail(SMASH_ERR_STATE, "smash_tail_configure has not been called");
   if (!ix.mapbody) return tfail(SMASH_ERR_STATE, "map.bin not loaded");
   const uint64_t n_pairs = (b.n_reads + 1) / 2;
   if (!n_pairs) return 0;
-  if (!t->d_nhits) { TCU(cudaMalloc((void **)&t->d_nhits, 8)); TCU(cudaMemset(t->d_nhits, 0, 8)); }
+  if (!t->d_nhits) { TCU(cudaMalloc((void **)&t->d_nhits, 8 * N_TAIL_COUNTERS)); TCU(cudaMemset(t->d_nhits, 0, 8 * N_TAIL_COUNTERS)); }
   if (!t->last_ev) TCU(cudaEventCreateWithFlags(&t->last_ev, cudaEventDisableTiming));
   // batches come from SMASH_N_SLOTS streams: chain the appends so they never overlap
   if (t->ev_recorded) TCU(cudaStreamWaitEvent(st, t->last_ev, 0));
@@ -174,12 +258,16 @@ int tail_accumulate(TailState *t, const DevIndex &ix, const BatchDev &b, const W
     TCU(cudaMalloc((void **)&t->blk, 8 * (t->batch_cap / 2048 + 8)));
   }
   int rc;
-  if (t->ev_recorded && (t->n_pairs + n_pairs > t->pair_nhits.cap || t->n_hits_bound + n_records_bound + 1 > t->hits.cap))
+  if (t->ev_recorded && (t->n_pairs + n_pairs > t->pair_nhits.cap || t->n_hits_bound + n_records_bound + 1 > t->hits.cap ||
+                         t->n_pairs + n_pairs + 1 > t->pair_name_off.cap || t->n_name_bound + name_bytes_bound + 1 > t->name_blob.cap))
     TCU(cudaEventSynchronize(t->last_ev));          // growing: the previous append must have landed
   const size_t want_pairs = t->pair_nhits.cap ? t->n_pairs + n_pairs : 8 * n_pairs;      // first batch: room for 8
   const size_t want_hits = t->hits.cap ? t->n_hits_bound + n_records_bound + 1 : 8 * (n_records_bound + 1);
   if ((rc = t->pair_nhits.reserve(want_pairs, t->n_pairs, st)) || (rc = t->pair_fp.reserve(2 * want_pairs, 2 * t->n_pairs, st)) ||
       (rc = t->pair_hit_off.reserve(want_pairs, t->n_pairs, st)) || (rc = t->hits.reserve(want_hits, t->n_hits_bound, st)))
+    return rc;
+  const size_t want_names = t->name_blob.cap ? t->n_name_bound + name_bytes_bound + 1 : 8 * (name_bytes_bound + 1);
+  if ((rc = t->pair_name_off.reserve(want_pairs + 1, t->n_pairs + 1, st)) || (rc = t->name_blob.reserve(want_names, t->n_name_bound, st)))
     return rc;
   PairParams pp{t->hit_window, t->min_excess};
   const int grid = (int)((n_pairs + 255) / 256 < 148 * 8 ? (n_pairs + 255) / 256 : 148 * 8);
@@ -187,11 +275,17 @@ int tail_accumulate(TailState *t, const DevIndex &ix, const BatchDev &b, const W
   *launches += 1 + exclusive_scan_u32_public(t->batch_cnt, n_pairs, t->blk, t->batch_off, st);
   k_pair_write<<<grid, 256, 0, st>>>(b, w, pp, n_pairs, t->batch_off, t->n_pairs, t->d_nhits, t->pair_nhits.p,
                                      t->pair_fp.p, t->pair_hit_off.p, t->hits.p);
-  k_bump<<<1, 1, 0, st>>>(t->d_nhits, t->batch_off + n_pairs);
+  k_bump<<<1, 1, 0, st>>>(t->d_nhits + CNT_HITS, t->batch_off + n_pairs);
+  *launches += 2;
+  // the pairs' read names + the name-order check (batch_cnt / batch_off are free again: same stream)
+  k_pair_name_len<<<grid, 256, 0, st>>>(b, n_pairs, t->batch_cnt);
+  *launches += 1 + exclusive_scan_u32_public(t->batch_cnt, n_pairs, t->blk, t->batch_off, st);
+  k_pair_name_copy<<<grid, 256, 0, st>>>(b, n_pairs, t->batch_off, t->n_pairs, t->d_nhits, t->name_blob.p, t->pair_name_off.p);
+  k_bump<<<1, 1, 0, st>>>(t->d_nhits + CNT_NAME_BYTES, t->batch_off + n_pairs);
   *launches += 2;
   TCU(cudaGetLastError());
   TCU(cudaEventRecord(t->last_ev, st)); t->ev_recorded = true;
-  t->n_pairs += n_pairs; t->n_hits_bound += n_records_bound;
+  t->n_pairs += n_pairs; t->n_hits_bound += n_records_bound; t->n_name_bound += name_bytes_bound;
   return 0;
 }
 
@@ -355,7 +449,7 @@ __global__ void k_varbin_smem(const int64_t *__restrict__ f_pos, const int64_t *
 // Phase A: duplicate removal (local pairs + foreign keys), ordered compaction into the positions
 // list and the varbin-filtered list; reports the shard's edge (first/last filtered position).
 int tail_phase_a(TailState *t, uint64_t ordinal_base, const uint64_t *foreign_keys, uint64_t n_foreign,
-                 smash_tail_edge *edge, cudaStream_t st, uint64_t *launches, const uint64_t *verdict_min_ord) {
+                 smash_tail_edge *edge, cudaStream_t st, uint64_t *launches, const uint64_t *verdict_min_ord, bool sharded) {
   if (!t->configured) return tfail(SMASH_ERR_STATE, "smash_tail_configure has not been called");
   const uint64_t P = t->n_pairs;
   double tq = t_now();
@@ -378,13 +472,48 @@ int tail_phase_a(TailState *t, uint64_t ordinal_base, const uint64_t *foreign_ke
     uint8_t *keep = (uint8_t *)t->scr[3].p;
     TDBG("reserve");
     const int grid = (int)((P + 255) / 256 < 148 * 8 ? (P + 255) / 256 : 148 * 8);
+    // pairs in `samtools sort -n` order: the arrival order unless the append-time check saw a pair out of place
+    const uint32_t *nh = t->pair_nhits.p; const uint64_t *pfp = t->pair_fp.p, *pho = t->pair_hit_off.p;
+    {
+      uint64_t h_cnt[N_TAIL_COUNTERS] = {0, 0, 0, 0};
+      TCU(cudaMemcpyAsync(h_cnt, t->d_nhits, sizeof h_cnt, cudaMemcpyDeviceToHost, st));
+      TCU(cudaStreamSynchronize(st));
+      t->order_violations = h_cnt[CNT_ORDER_VIOLATIONS];
+    }
+    if (t->order_violations) {
+      if (sharded)
+        return tfail(SMASH_ERR_DATA, "%llu read pairs are out of `samtools sort -n` name order: the read-sharded tail needs name-ordered "
+                     "input (smashMEM.py sees a name-sorted BAM, smash_mapping.sh:23); use smash_tail_finish on one GPU",
+                     (unsigned long long)t->order_violations);
+      if (P >= 0xffffffffull) return tfail(SMASH_ERR_ARG, "too many pairs for the name sort");
+      if ((rcs = t->scr[12].reserve(4 * P, 0, st)) || (rcs = t->scr[13].reserve(4 * P, 0, st)) || (rcs = t->scr[14].reserve(16 * P, 0, st)) ||
+          (rcs = t->scr[15].reserve(8 * P, 0, st)))
+        return rcs;
+      uint32_t *perm = (uint32_t *)t->scr[12].p, *nh2 = (uint32_t *)t->scr[13].p;
+      uint64_t *fp2 = (uint64_t *)t->scr[14].p, *ho2 = (uint64_t *)t->scr[15].p;
+      k_perm_iota<<<grid, 256, 0, st>>>(perm, P);
+      const NameLess less{t->name_blob.p, t->pair_name_off.p};
+#if !defined(SMASH_CUDA_SHIM)
+      size_t tmp_bytes = 0;
+      TCU(cub::DeviceMergeSort::SortKeys(nullptr, tmp_bytes, perm, (int64_t)P, less, st));
+      if ((rcs = t->scr[16].reserve(tmp_bytes + 16, 0, st))) return rcs;
+      TCU(cub::DeviceMergeSort::SortKeys(t->scr[16].p, tmp_bytes, perm, (int64_t)P, less, st));
+#else
+      TCU(cudaStreamSynchronize(st));
+      std::sort(perm, perm + P, less);                       // host emulation (tests/emul): device memory is host memory there
+#endif
+      k_permute_pairs<<<grid, 256, 0, st>>>(perm, P, t->pair_nhits.p, t->pair_fp.p, t->pair_hit_off.p, nh2, fp2, ho2);
+      *launches += 3;
+      nh = nh2; pfp = fp2; pho = ho2;
+      TDBG("name sort");
+    }
     if (verdict_min_ord) {
       // the host already resolved the global first-wins rule (multigpu.py: partitioned exchange)
       uint32_t *flag = c_pos;                       // scratch reuse: export index of every pair
-      k_export_flags<<<grid, 256, 0, st>>>(t->pair_nhits.p, P, flag);
+      k_export_flags<<<grid, 256, 0, st>>>(nh, P, flag);
       *launches += 1 + exclusive_scan_u32_public(flag, P, blk, o_pos, st);
       TCU(cudaMemsetAsync(d_stats, 0, 32, st));
-      k_dd_from_verdict<<<grid, 256, 0, st>>>(t->pair_nhits.p, o_pos, verdict_min_ord, P, ordinal_base, keep, d_stats);
+      k_dd_from_verdict<<<grid, 256, 0, st>>>(nh, o_pos, verdict_min_ord, P, ordinal_base, keep, d_stats);
       *launches += 1;
       TCU(cudaMemcpyAsync(h_stats, d_stats, 32, cudaMemcpyDeviceToHost, st));
       TCU(cudaStreamSynchronize(st));
@@ -394,8 +523,8 @@ int tail_phase_a(TailState *t, uint64_t ordinal_base, const uint64_t *foreign_ke
       TCU(cudaMemsetAsync(d_stats, 0, 32, st));
       const uint64_t sd = seed * 0x9e3779b97f4a7c15ULL;
       if (n_foreign) { k_dd_insert_foreign<<<grid, 256, 0, st>>>(foreign_keys, n_foreign, sd, keys, minord, tsize - 1); *launches += 1; }
-      k_dd_insert<<<grid, 256, 0, st>>>(t->pair_nhits.p, t->pair_fp.p, P, ordinal_base, sd, keys, minord, tsize - 1, slot_of);
-      k_dd_resolve<<<grid, 256, 0, st>>>(t->pair_nhits.p, t->pair_fp.p, t->pair_hit_off.p, t->hits.p, P, ordinal_base, minord, slot_of,
+      k_dd_insert<<<grid, 256, 0, st>>>(nh, pfp, P, ordinal_base, sd, keys, minord, tsize - 1, slot_of);
+      k_dd_resolve<<<grid, 256, 0, st>>>(nh, pfp, pho, t->hits.p, P, ordinal_base, minord, slot_of,
                                          foreign_keys, n_foreign, keep, d_stats);
       *launches += 2;
       TCU(cudaMemcpyAsync(h_stats, d_stats, 32, cudaMemcpyDeviceToHost, st));
@@ -404,7 +533,7 @@ int tail_phase_a(TailState *t, uint64_t ordinal_base, const uint64_t *foreign_ke
       if (seed > 8) return tfail(SMASH_ERR_DATA, "duplicate-key table could not be resolved");
     }
     TDBG("dedupe");
-    k_pair_out_count<<<grid, 256, 0, st>>>(t->pair_nhits.p, t->pair_hit_off.p, t->hits.p, keep, P, t->chrom_off, c_pos, c_bin);
+    k_pair_out_count<<<grid, 256, 0, st>>>(nh, pho, t->hits.p, keep, P, t->chrom_off, c_pos, c_bin);
     *launches += 1 + exclusive_scan_u32_public(c_pos, P, blk, o_pos, st);
     *launches += exclusive_scan_u32_public(c_bin, P, blk, o_bin, st);
     TCU(cudaMemcpyAsync(&n_pos, o_pos + P, 8, cudaMemcpyDeviceToHost, st));
@@ -419,7 +548,7 @@ int tail_phase_a(TailState *t, uint64_t ordinal_base, const uint64_t *foreign_ke
     TDBG("out_count+scans");
     if ((rcs = t->scr[10].reserve(8 * (n_f + 1), 0, st)) || (rcs = t->scr[11].reserve(8 * (n_f + 1), 0, st))) return rcs;
     int64_t *f_pos = (int64_t *)t->scr[10].p, *f_abs = (int64_t *)t->scr[11].p;
-    k_pair_out_write<<<grid, 256, 0, st>>>(t->pair_nhits.p, t->pair_hit_off.p, t->hits.p, keep, P, t->chrom_off, o_pos, o_bin,
+    k_pair_out_write<<<grid, 256, 0, st>>>(nh, pho, t->hits.p, keep, P, t->chrom_off, o_pos, o_bin,
                                            t->pos_chrom, t->pos_pos, f_pos, f_abs);
     *launches += 1;
     TDBG("out_write");
@@ -482,7 +611,7 @@ int tail_phase_b(TailState *t, int has_prev, int64_t prev_last_pos, int64_t *cou
 
 int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smash_tail_stats *stats,
                 cudaStream_t st, uint64_t *launches) {
-  int rc = tail_phase_a(t, 0, nullptr, 0, nullptr, st, launches, nullptr);
+  int rc = tail_phase_a(t, 0, nullptr, 0, nullptr, st, launches, nullptr, false);
   if (rc) return rc;
   return tail_phase_b(t, 0, 0, counts_host, counts_device, stats, st, launches);
 }
@@ -519,6 +648,7 @@ int tail_reserve(TailState *t, uint64_t pairs, uint64_t hits, cudaStream_t st) {
       (rc = t->pair_hit_off.reserve(pairs, t->n_pairs, st)) || (rc = t->hits.reserve(hits + 1, t->n_hits_bound, st)))
     return rc;
   uint64_t tsize = 1024; while (tsize < 2 * pairs) tsize <<= 1;
+  if ((rc = t->pair_name_off.reserve(pairs + 2, t->n_pairs + 1, st))) return rc;
   const size_t want[12] = {8 * tsize, 8 * tsize, 4 * pairs, pairs, 64, 4 * pairs, 4 * pairs, 8 * (pairs + 1), 8 * (pairs + 1),
                            8 * (pairs / 2048 + 8), 8 * (hits + 1), 8 * (hits + 1)};
   for (int i = 0; i < 12; ++i) if ((rc = t->scr[i].reserve(want[i], 0, st))) return rc;

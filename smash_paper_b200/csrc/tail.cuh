@@ -26,8 +26,12 @@ struct TailState {
   DGrow<uint64_t> pair_fp;          // 2 per pair: 128-bit fingerprint of the dupe key
   DGrow<uint64_t> pair_hit_off;     // first hit of the pair in `hits`
   DGrow<uint64_t> hits;             // tid << 40 | 0-based pos, r1 hits in HI order then r2 hits
+  // read names of the pairs (name of read 2p), for the `samtools sort -n` order smashMEM.py sees (smash_mapping.sh:23)
+  DGrow<uint8_t> name_blob; DGrow<uint64_t> pair_name_off;   // n_pairs + 1 offsets into name_blob
+  uint64_t n_name_bound = 0;        // host-side upper bound of the bytes in name_blob (exact total in d_nhits[1])
+  uint64_t order_violations = 0;    // pairs whose name sorts before their predecessor's (as of the last phase A)
   // scratch
-  DGrow<uint8_t> scr[12];           // tail_finish work buffers (persistent)
+  DGrow<uint8_t> scr[17];           // tail_finish work buffers (persistent)
   DGrow<uint8_t> exp_keys;          // exported {fp1,fp2,ordinal} triples
   bool a_done = false; uint64_t n_f = 0, a_dupes = 0, a_non_dupes = 0;
   uint32_t *batch_cnt = nullptr; uint64_t *batch_off = nullptr; uint64_t *blk = nullptr; size_t batch_cap = 0;
@@ -44,11 +48,11 @@ const char *tail_error();
 int tail_configure(TailState *t, const int64_t *bin_starts, uint64_t n_bins, const int64_t *chrom_off,
                    uint64_t n_chrom, int64_t hit_window, int32_t min_excess);
 int tail_accumulate(TailState *t, const DevIndex &ix, const BatchDev &b, const WorkDev &w,
-                    uint64_t n_records_bound, cudaStream_t st, uint64_t *launches);
+                    uint64_t n_records_bound, uint64_t name_bytes_bound, cudaStream_t st, uint64_t *launches);
 int tail_finish(TailState *t, int64_t *counts_host, int64_t *counts_device, smash_tail_stats *stats,
                 cudaStream_t st, uint64_t *launches);
 int tail_phase_a(TailState *t, uint64_t ordinal_base, const uint64_t *foreign_keys, uint64_t n_foreign,
-                 smash_tail_edge *edge, cudaStream_t st, uint64_t *launches, const uint64_t *verdict_min_ord);
+                 smash_tail_edge *edge, cudaStream_t st, uint64_t *launches, const uint64_t *verdict_min_ord, bool sharded);
 int tail_phase_b(TailState *t, int has_prev, int64_t prev_last_pos, int64_t *counts_host, int64_t *counts_device,
                  smash_tail_stats *stats, cudaStream_t st, uint64_t *launches);
 int tail_export_keys(TailState *t, uint64_t ordinal_base, const uint64_t **dev_keys, uint64_t *n, cudaStream_t st, uint64_t *launches);

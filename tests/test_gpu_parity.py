@@ -428,6 +428,58 @@ def test_two_shards_equal_one_run(case):
         ix.close()
 
 
+def _perm_pairs(reads, order):
+    from smash_paper_b200 import samio
+    return samio.concat_batches([samio.slice_batch(reads, 2 * int(p), 2 * int(p) + 2) for p in order])
+
+
+@pytest.mark.parametrize("case_name", ["case_basic", "case_tail"])
+@pytest.mark.parametrize("feed", ["one_batch", "three_batches", "shuffled_input", "name_sorted_input"])
+def test_golden_smashmem_stage(case_name, feed):
+    """The fused tail against what the UNMODIFIED smashMEM.py + awk/perl + varbin.py printed (tests/golden/
+    make_golden_smash.py).  case_tail's read names are NOT in `samtools sort -n` order: the positions list must come out
+    in name order whatever order (and however many batches) the reads arrive in."""
+    import gzip
+    from smash_paper_b200 import api, samio
+    g = load_golden_case(case_name)
+    d, oix = g["dir"], g["oix"]
+    smash = gzip.open(os.path.join(d, "smash.txt.gz")).read().splitlines()
+    gold_pos = gzip.open(os.path.join(d, "positions.txt.gz")).read().decode().splitlines()
+    gold_counts = np.array([int(r.split("\t")[3]) for r in gzip.open(os.path.join(d, "varbin.txt.gz")).read().decode().splitlines()])
+    nd, nn = (int(x.split()[0]) for x in smash[-1].decode().split("\t"))
+    bins = T.read_table(os.path.join(d, "bins.txt"))
+    ci = T.read_chrominfo(os.path.join(d, "chrom_sizes.txt"))
+    reads = g["reads"]
+    n_pairs = reads.n // 2
+    rng = np.random.default_rng(3)
+    if feed == "shuffled_input":
+        reads = _perm_pairs(reads, rng.permutation(n_pairs))
+    elif feed == "name_sorted_input":
+        import functools
+        nm = [bytes(reads.names[reads.name_off[2 * p]:reads.name_off[2 * p + 1]]) for p in range(n_pairs)]
+        reads = _perm_pairs(reads, sorted(range(n_pairs), key=functools.cmp_to_key(lambda x, y: T.strnum_cmp(nm[x], nm[y]) or x - y)))
+    ctx = api.Context.from_text(oix.text, oix.startpos, oix.sizes, oix.descr, w=4, min_len=20, nomap=True, tag_mappability=True)
+    try:
+        ctx.build_mappability_device()
+        ctx.tail_configure([int(b[2]) for b in bins], list(ci.keys()), [int(v[2]) for v in ci.values()])
+        if feed == "three_batches":
+            cuts = [0, 2 * (n_pairs // 3), 2 * (2 * n_pairs // 3) , reads.n]
+            sam = b"".join(ctx.map_batch(samio.slice_batch(reads, a, b), want=api.WANT_SAM | api.WANT_TAIL).sam for a, b in zip(cuts, cuts[1:]))
+        else:
+            sam = ctx.map_batch(reads, want=api.WANT_SAM | api.WANT_TAIL).sam
+        tagged = [ln for ln in gzip.open(os.path.join(d, "tagged.sam.gz")).read().splitlines(keepends=True) if not ln.startswith(b"@")]
+        assert sorted(sam.splitlines(keepends=True)) == sorted(tagged)            # mappability_tag binary's output
+        counts, st = ctx.tail_finish()
+        chrom, pos = ctx.tail_positions()
+        names = oix.descr[::2]
+        assert [f"{names[c]} {p}" for c, p in zip(chrom, pos)] == gold_pos        # smashMEM.py | awk | perl
+        assert np.array_equal(counts, gold_counts)                                 # varbin.py
+        assert (st["n_dupe_pairs"], st["n_non_dupe_pairs"]) == (nd, nn)           # smashMEM.py trailer
+        assert st["n_positions"] == len(gold_pos) and st["reads_kept"] == int(gold_counts.sum())
+    finally:
+        ctx.close()
+
+
 _GOLD_MEM = [(c, v) for c in ["case_basic", "case_adversarial"] for v in golden_variants(c) if v["mode"] == "mem"]
 
 
