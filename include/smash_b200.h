@@ -125,7 +125,11 @@ typedef struct {
   float gpu_ms;                   /* device time of this batch's kernels (CUDA events) */
 } smash_result;
 
-enum { SMASH_WANT_SAM = 1, SMASH_WANT_MATCHES = 2, SMASH_WANT_TAIL = 4 };
+/* SMASH_WANT_SORTED (with SMASH_WANT_SAM): the batch is one chunk of the reference's OutputSorter -- its lines come back
+ * in the order OutputSorter::flush writes them (query.cpp:448-468): sorted by MemSam::operator< (memsam.h:136-158), i.e.
+ * (MemSam::chromosomes[RNAME] + POS, name, flag & (64|128|16)); lines equal in all three fail with SMASH_ERR_DATA where
+ * the reference throws "flags equal".  Without it the lines are in input order (read 0's records in HI order, ...). */
+enum { SMASH_WANT_SAM = 1, SMASH_WANT_MATCHES = 2, SMASH_WANT_TAIL = 4, SMASH_WANT_SORTED = 8 };
 
 /* Pinned host memory for batches (cudaHostAlloc): buffers handed to smash_map_batch /
  * smash_submit from here are copied with true asynchronous DMA. */

@@ -300,6 +300,34 @@ def ref_map(fasta, reads_sam, workdir, threads=2, extra=(), long_ints=False):
     return header, sorted(lines)
 
 
+def ref_map_chunks(fasta, reads_sam, workdir, threads=2, extra=(), long_ints=False):
+    """Like ref_map, but every chunk file as the reference wrote it: list of record-line lists (file order kept)."""
+    exe = os.path.join(REF_BIN, "mummer-long" if long_ints else "mummer")
+    shutil.rmtree(os.path.join(workdir, "mapout"), ignore_errors=True)
+    subprocess.run([exe, "-rcref", "-qthreads", str(max(2, threads)), "-nomap", "-samin", "-samout", *extra, fasta, reads_sam],
+                   cwd=workdir, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    out = []
+    for fn in sorted(glob.glob(os.path.join(workdir, "mapout", "*.txt"))):
+        with open(fn, "rb") as f:
+            out.append([ln for ln in f if not ln.startswith(b"@")])
+    return out
+
+
+def memsam_sort_key(names, sizes):
+    """Key function for SAM record lines reproducing MemSam::operator< (memsam.h:136-158) with MemSam::chromosomes
+    as Pairs::Pairs fills it (query.cpp:546-552): (offset[RNAME] + POS, name bytes, flag & (64|128|16))."""
+    off, acc = {}, 0
+    for n, s in zip(names, sizes):
+        off[n.encode() if isinstance(n, str) else n] = acc
+        acc += int(s)
+    off[b"*"] = acc
+
+    def key(line):
+        f = line.split(b"\t", 4)
+        return off[f[2]] + int(f[3]), f[0], int(f[1]) & (64 | 128 | 16)
+    return key
+
+
 def ref_mappability_tag(fasta, sam_path):
     """smash_mapping.sh:23 first stage; returns stdout bytes."""
     exe = os.path.join(REF_BIN, "mappability_tag")

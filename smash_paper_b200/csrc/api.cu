@@ -248,6 +248,8 @@ struct Slot {
   DBuf<uint8_t> long_scratch; int long_q = 0;
   bool split = false;
   DBuf<uint64_t> surv; DBuf<uint8_t> surv_cnt; DBuf<uint8_t> lc;      // split search (k_mam_search -> k_mam_verify)
+  DBuf<uint64_t> sort_abs, sort_off; DBuf<uint8_t> sort_flag, sort_tmp; DBuf<uint32_t> sort_perm, sort_bytes;   // K5 record_sort
+  bool sorted = false;
   HBuf<uint16_t> h_flag;       // pinned staging for a pageable read_flag array
   // device-side input stage (smash_submit_text): raw text, line tables, per-record parse results, scan scratch
   DBuf<uint8_t> ing_raw[2]; DBuf<uint64_t> ing_ls[2]; DBuf<uint64_t> ing_hdr[2]; DBuf<uint8_t> ing_hdr_flag;
@@ -273,7 +275,7 @@ struct smash_ctx {
   uint8_t *text_alloc = nullptr; void *sa = nullptr; void *isa = nullptr; uint8_t *lcp = nullptr;
   LcpItem *lcp_m = nullptr; uint8_t *uniq = nullptr; void *seed = nullptr; uint16_t *ext = nullptr; uint64_t *startpos = nullptr;
   uint64_t *sizes = nullptr; char *descr = nullptr; int *descr_off = nullptr; uint64_t *descr8 = nullptr; uint32_t *alpha = nullptr;
-  uint8_t *mapbody = nullptr; uint32_t *chrom_off32 = nullptr;
+  uint8_t *mapbody = nullptr; uint32_t *chrom_off32 = nullptr; uint64_t *chrom_abs64 = nullptr;
   uint64_t n_m = 0;
   int max_chunks = MAX_CHUNKS; uint64_t chunk_min_reads = CHUNK_MIN_READS;
   smash_index *own_index = nullptr;
@@ -381,6 +383,13 @@ static int ctx_finish(smash_ctx *c, const smash_index *ix) {
     for (int i = 0; i < nd; i += ix->rcref ? 2 : 1) { o32[k++] = acc; acc += (uint32_t)ix->sizes[i]; }
     CK(dmalloc((void **)&c->chrom_off32, 4 * o32.size(), &c->index_bytes));
     CUC(cudaMemcpy(c->chrom_off32, o32.data(), 4 * o32.size(), cudaMemcpyHostToDevice));
+    // MemSam::chromosomes (query.cpp:546-552): 64-bit offsets of the forward sequences, "*" = total
+    std::vector<uint64_t> o64;
+    uint64_t acc64 = 0;
+    for (int i = 0; i < nd; i += ix->rcref ? 2 : 1) { o64.push_back(acc64); acc64 += ix->sizes[i]; }
+    o64.push_back(acc64);
+    CK(dmalloc((void **)&c->chrom_abs64, 8 * o64.size(), &c->index_bytes));
+    CUC(cudaMemcpy(c->chrom_abs64, o64.data(), 8 * o64.size(), cudaMemcpyHostToDevice));
   }
   CK(dmalloc((void **)&c->alpha, 32, nullptr));
   DevIndex &d = c->dix;
@@ -388,7 +397,7 @@ static int ctx_finish(smash_ctx *c, const smash_index *ix) {
   d.lcp_m = c->lcp_m; d.n_m = c->n_m; d.startpos = c->startpos; d.sizes = c->sizes; d.n_descr = nd;
   d.rcref = ix->rcref; d.descr = c->descr; d.descr_off = c->descr_off; d.descr8 = c->descr8;
   d.logN = (uint64_t)ceil(log((double)N) / log(2.0));          // longSA.cpp:97
-  d.mapbody = nullptr; d.map_bytes = 0; d.chrom_off32 = c->chrom_off32;
+  d.mapbody = nullptr; d.map_bytes = 0; d.chrom_off32 = c->chrom_off32; d.chrom_abs64 = c->chrom_abs64;
   // derived: alphabet bitmap, shortest-unique-length bytes, k-mer seed table
   c->launches += launch_alpha(d.text, N, c->alpha, st);
   CUC(cudaMemcpyAsync(d.alpha, c->alpha, 32, cudaMemcpyDeviceToHost, st));
@@ -591,6 +600,7 @@ static void slot_release(Slot &s) {
   s.nrec.release(); s.rec_base.release(); s.rec_read.release(); s.rec_bytes.release(); s.rec_off.release(); s.sam_total.release(); s.blk_sums2.release(); s.blk_sums.release(); s.sam.release(); s.flags.release();
   s.csr_off.release(); s.csr_triples.release(); s.long_scratch.release(); s.slot_off.release(); s.aln_scr.release(); s.ord_scr.release(); s.tmp32.release(); s.h_sam.release(); s.h_csr_off.release();
   s.h_matches.release(); s.h_small.release(); s.h_flag.release(); s.surv.release(); s.surv_cnt.release(); s.lc.release();
+  s.sort_abs.release(); s.sort_off.release(); s.sort_flag.release(); s.sort_tmp.release(); s.sort_perm.release(); s.sort_bytes.release();
   for (int f = 0; f < 2; ++f) { s.ing_raw[f].release(); s.ing_ls[f].release(); s.ing_hdr[f].release(); }
   s.ing_hdr_flag.release(); s.ing_blk64.release(); s.ing_blk32.release(); s.ing_blk4.release(); s.ing_pre.release();
   s.ing_recs.release(); s.ing_scal.release(); s.h_ing.release();
@@ -613,7 +623,7 @@ extern "C" void smash_ctx_destroy(smash_ctx *c) {
   for (int s = 0; s < SMASH_N_SLOTS; ++s) slot_release(c->slot[s]);
   tail_release(&c->tail);
   void *ptrs[] = {c->descr8, c->ext, c->text_alloc, c->sa, c->isa, c->lcp, c->lcp_m, c->uniq, c->seed, c->startpos, c->sizes,
-                  c->descr, c->descr_off, c->alpha, c->mapbody, c->chrom_off32};
+                  c->descr, c->descr_off, c->alpha, c->mapbody, c->chrom_off32, c->chrom_abs64};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->own_index) delete c->own_index;
   delete c;
@@ -757,6 +767,8 @@ static WorkDev work_of(Slot &s) {
   if (!s.csr && s.surv.p && s.split) { w.surv = s.surv.p; w.surv_cnt = s.surv_cnt.p; w.lc = s.lc.p; }
   w.long_scratch = s.long_q ? s.long_scratch.p : nullptr; w.long_q = s.long_q; w.match_slots = s.match_slots.p; w.match_cnt = s.match_cnt.p; w.item_slots = s.item_slots.p;
   w.rec_slots = s.rec_slots.p; w.sums = s.sums.p; w.nrec = s.nrec.p; w.rec_base = s.rec_base.p; w.rec_read = s.rec_read.p; w.rec_bytes = s.rec_bytes.p; w.rec_off = s.rec_off.p; w.sam_total = s.sam_total.p; w.blk_sums2 = s.blk_sums2.p;
+  w.sort_abs = s.sort_abs.p; w.sort_flag = s.sort_flag.p; w.sort_perm = s.sort_perm.p; w.sort_bytes = s.sort_bytes.p; w.sort_off = s.sort_off.p;
+  w.sort_tmp = s.sort_tmp.p; w.sort_tmp_bytes = s.sort_tmp.cap;
   w.blk_sums = s.blk_sums.p; w.sam = s.sam.p ? s.sam.p + s.sam_base : nullptr; w.sam_cap = s.sam.cap > s.sam_base ? s.sam.cap - s.sam_base : 0; w.flags = s.flags.p;
   return w;
 }
@@ -846,11 +858,24 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
       if (s.sam_base) CU(cudaStreamSynchronize(s.st_out));   // earlier ranges are on the host already; their device copy may go
       if ((rc = s.sam.ensure(need > guess ? need : guess))) return rc;
     }
+    if ((want & SMASH_WANT_SORTED) && recs) {
+      // K5: the batch is one chunk of the reference's OutputSorter -> its lines in MemSam::operator< order
+      if (recs >= 0xffffffffull) return fail(SMASH_ERR_ARG, "too many records in one batch for SMASH_WANT_SORTED");
+      size_t tmp_bytes = 0;
+      launch_record_sort(c->dix, s.bd, work_of(s), recs, s.st, &tmp_bytes);
+      if ((rc = s.sort_abs.ensure(recs + 1)) || (rc = s.sort_off.ensure(recs + 2)) || (rc = s.sort_flag.ensure(recs + 1)) ||
+          (rc = s.sort_perm.ensure(recs + 1)) || (rc = s.sort_bytes.ensure(recs + 1)) || (rc = s.sort_tmp.ensure(tmp_bytes + 16)) ||
+          (rc = s.blk_sums2.ensure(recs / 2048 + 8)))
+        return rc;
+      c->launches += launch_record_sort(c->dix, s.bd, work_of(s), recs, s.st, nullptr);
+      s.sorted = true;
+    }
     WorkDev w = work_of(s);
     c->launches += launch_emit_text(c->dix, s.bd, w, c->sp, s.st, recs);
     MARK(3);
     c->launches += launch_emit_copy(s.bd, w, s.st, recs);
     MARK(6);
+    if (s.sorted) c->launches += launch_publish(s.h_small.p, (const uint64_t *)s.sam_total.p, (const uint64_t *)(s.rec_base.p + n), s.flags.p, s.st);
     if (to_host) {
       if (need > s.h_sam.cap) {
         if (s.sam_base) CU(cudaStreamSynchronize(s.st_out));
@@ -892,7 +917,7 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
 }
 
 static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
-  s.sam_bytes = 0; s.n_matches = 0; s.n_records = 0; s.want = want; s.sam_base = 0; s.n_evs = 0;
+  s.sam_bytes = 0; s.n_matches = 0; s.n_records = 0; s.want = want; s.sam_base = 0; s.n_evs = 0; s.sorted = false;
   if (!s.n_reads) return 0;
   if (s.n_chunks > 1 && (!to_host || (want & SMASH_WANT_MATCHES) || c->prm.mode == SMASH_MODE_MEM))
     return fail(SMASH_ERR_STATE, "internal: chunked batch on a path that cannot take one");
@@ -933,6 +958,11 @@ static int slot_finish(smash_ctx *c, Slot &s, smash_result *res) {
   CU(cudaStreamSynchronize(s.st));
   CU(cudaGetLastError());
   ingest_collect(c, s);
+  if (s.sorted && ((const uint32_t *)(s.h_small.p + 1))[FLAG_SORTDUP]) {
+    s.busy = false;
+    return fail(SMASH_ERR_DATA, "flags equal: %u lines of the batch share absolute position, name and first/second/reversed bits "
+                "(MemSam::operator<, memsam.h:143-150, throws here: read names must be unique per mate)", ((const uint32_t *)(s.h_small.p + 1))[FLAG_SORTDUP]);
+  }
   if (s.n_reads) {
     cudaEvent_t prev = s.ev0;
     for (int e = 0; e < s.n_evs; ++e) { float ms = 0; if (s.ev_stage[e] >= 0 && cudaEventElapsedTime(&ms, prev, s.evs[e]) == cudaSuccess) c->stage_ms[s.ev_stage[e]] += ms; prev = s.evs[e]; }
@@ -1166,7 +1196,8 @@ extern "C" int smash_submit(smash_ctx *c, int slot, const smash_batch *b, int wa
     for (int e = 0; e < 3; ++e) if (!s.tl[e]) cudaEventCreate(&s.tl[e]);
     cudaEventRecord(s.tl[0], s.st);
   }
-  const int chunks = (c->prm.mode != SMASH_MODE_MEM && !(want & SMASH_WANT_MATCHES) && (want & SMASH_WANT_SAM) && !g_no_chunks) ? c->max_chunks : 1;
+  // (a sorted batch is ONE chunk of the reference's OutputSorter: it goes through whole)
+  const int chunks = (c->prm.mode != SMASH_MODE_MEM && !(want & (SMASH_WANT_MATCHES | SMASH_WANT_SORTED)) && (want & SMASH_WANT_SAM) && !g_no_chunks) ? c->max_chunks : 1;
   int rc = slot_prepare(c, s, b, true, chunks);
   DBG_T("submit:prepare+h2d enqueue", t0);
   if (rc) return rc;

@@ -62,6 +62,7 @@ struct DevIndex {
   const uint8_t *mapbody;
   uint64_t map_bytes;
   const uint32_t *chrom_off32;   // per forward chromosome
+  const uint64_t *chrom_abs64;   // MemSam::chromosomes (query.cpp:546-552): 64-bit running sums per forward chromosome, [n_fwd] = total ("*")
 };
 
 HD uint64_t sa_at(const DevIndex &ix, uint64_t i) {

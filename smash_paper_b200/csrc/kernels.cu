@@ -9,6 +9,11 @@
 // One warp owns one read in every per-read kernel; the read is staged once in shared memory.
 // All kernels are grid-stride over reads with a grid sized from the SM count.
 #include "kernels.cuh"
+#if !defined(SMASH_CUDA_SHIM)
+#include <cub/device/device_merge_sort.cuh>
+#else
+#include <algorithm>
+#endif
 
 namespace smash {
 
@@ -453,7 +458,7 @@ struct VerifySmem {
   uint32_t own_xl[WARPS][SURV_CAP];            // anchor offset << 16 | left extension
 };
 #ifndef SMASH_VERIFY_MINBLK
-#define SMASH_VERIFY_MINBLK 5
+#define SMASH_VERIFY_MINBLK 8
 #endif
 __global__ void __launch_bounds__(THREADS, SMASH_VERIFY_MINBLK)
 k_mam_verify(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
@@ -1146,6 +1151,97 @@ int launch_emit_copy(const BatchDev &b, const WorkDev &w, cudaStream_t st, uint6
   if (!attr_set) { cudaFuncSetAttribute(k_emit_copy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CopySmem)); attr_set = true; }
   k_emit_copy<<<grid_for_warps((b.n_reads + 31) / 32, SMASH_COPY_MINBLK), THREADS, sizeof(CopySmem), st>>>(b, w);
   return 1;
+}
+
+// ------------------------------------------------------------------ K5: record_sort
+//
+// A reference worker sorts the lines of a chunk before it writes the file (OutputSorter::flush, query.cpp:448-468) with
+// MemSam::operator< (memsam.h:136-158): absolute position = MemSam::chromosomes[RNAME] + POS as PRINTED (an unmapped
+// placeholder carries its mate's RNAME/POS, "*" sorts after every chromosome, query.cpp:546-552), then the name
+// (std::string <, bytes as unsigned), then flag & (first | second | reversed); two lines equal in all three make the
+// reference throw "flags equal".  The order is decided before any text exists: keys from the records, a merge sort of
+// the flat record indices, and rec_off re-derived, so k_emit_* write every line straight into its sorted place.
+__global__ void __launch_bounds__(128)
+k_sort_keys(DevIndex ix, BatchDev b, WorkDev w, uint64_t n_records) {
+  for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_records; f += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t read = w.rec_read[f];
+    const int r = (int)(f - w.rec_base[read]);
+    const ReadSum me = w.sums[read];
+    uint16_t flag; MateView mv;
+    read_mate(b, w, read, &flag, &mv);
+    const int n_fwd = ix.rcref ? ix.n_descr / 2 : ix.n_descr;
+    uint64_t abs;
+    if (me.unmapped) {
+      abs = mv.has ? ix.chrom_abs64[ix.rcref ? mv.si >> 1 : mv.si] + (uint64_t)(mv.pos + 1) : ix.chrom_abs64[n_fwd];
+    } else {
+      const Rec rr = (w.rec_slots + slot_base(w, read))[r];
+      abs = ix.chrom_abs64[ix.rcref ? rr.si >> 1 : rr.si] + (uint64_t)(rr.pos + 1);
+      flag = (uint16_t)(flag | (rr.rc ? 16 : 0));
+    }
+    w.sort_abs[f] = abs;
+    w.sort_flag[f] = (uint8_t)(flag & (64 | 128 | 16));
+    w.sort_perm[f] = (uint32_t)f;
+  }
+}
+struct RecLess {
+  const uint64_t *abs; const uint8_t *fl; const uint32_t *rec_read; const uint8_t *names; const int64_t *name_off;
+  __host__ __device__ int cmp_name(uint32_t x, uint32_t y) const {
+    const uint32_t rx = rec_read[x], ry = rec_read[y];
+    if (rx == ry) return 0;
+    const uint8_t *a = names + name_off[rx], *c = names + name_off[ry];
+    const int64_t la = name_off[rx + 1] - name_off[rx], lc = name_off[ry + 1] - name_off[ry];
+    const int64_t m = la < lc ? la : lc;
+    for (int64_t i = 0; i < m; ++i) if (a[i] != c[i]) return a[i] < c[i] ? -1 : 1;
+    return la < lc ? -1 : la > lc ? 1 : 0;
+  }
+  __host__ __device__ bool operator()(uint32_t x, uint32_t y) const {
+    if (abs[x] != abs[y]) return abs[x] < abs[y];
+    const int c = cmp_name(x, y);
+    if (c) return c < 0;
+    if (fl[x] != fl[y]) return fl[x] < fl[y];
+    return x < y;
+  }
+};
+__global__ void k_sort_scatter(WorkDev w, RecLess less, uint64_t n) {
+  unsigned dup = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t f = w.sort_perm[i];
+    w.sort_bytes[i] = w.rec_bytes[f];
+    if (i) {                                                   // "flags equal" (memsam.h:143-150)
+      const uint32_t g = w.sort_perm[i - 1];
+      if (less.abs[f] == less.abs[g] && less.fl[f] == less.fl[g] && less.cmp_name(f, g) == 0) ++dup;
+    }
+  }
+  if (dup) atomicAdd(&w.flags[FLAG_SORTDUP], dup);
+}
+__global__ void k_sort_gather(WorkDev w, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    w.rec_off[w.sort_perm[i]] = w.sort_off[i];
+}
+int launch_record_sort(const DevIndex &ix, const BatchDev &b, const WorkDev &w, uint64_t n, cudaStream_t st, size_t *tmp_bytes_needed) {
+  const RecLess less{w.sort_abs, w.sort_flag, w.rec_read, b.names, b.name_off};
+  if (tmp_bytes_needed) {
+    *tmp_bytes_needed = 0;
+#if !defined(SMASH_CUDA_SHIM)
+    cub::DeviceMergeSort::SortKeys(nullptr, *tmp_bytes_needed, (uint32_t *)nullptr, (int64_t)n, less, st);
+#endif
+    return 0;
+  }
+  if (!n) return 0;
+  const uint64_t need = (n + 127) / 128, cap = (uint64_t)sm_count() * 16;
+  const unsigned grid = (unsigned)(need < cap ? need : cap);
+  k_sort_keys<<<grid, 128, 0, st>>>(ix, b, w, n);
+#if !defined(SMASH_CUDA_SHIM)
+  size_t tb = w.sort_tmp_bytes;
+  cub::DeviceMergeSort::SortKeys(w.sort_tmp, tb, w.sort_perm, (int64_t)n, less, st);
+#else
+  cudaStreamSynchronize(st);
+  std::sort(w.sort_perm, w.sort_perm + n, less);             // host emulation (tests/emul)
+#endif
+  k_sort_scatter<<<grid, 128, 0, st>>>(w, less, n);
+  const int ns = exclusive_scan_u32(w.sort_bytes, n, w.blk_sums2, w.sort_off, st);
+  k_sort_gather<<<grid, 128, 0, st>>>(w, n);
+  return 4 + ns;
 }
 
 // ------------------------------------------------------------------ matches -> CSR for the host

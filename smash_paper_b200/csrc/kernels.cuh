@@ -15,7 +15,7 @@ struct BatchDev {
 };
 
 constexpr int SURV_CAP = 32;
-enum { FLAG_OVERFLOW = 0, FLAG_MAPERR = 1, FLAG_LONGREAD = 2, FLAG_MAXCNT = 3, FLAG_LONGQ = 4, N_FLAGS = 8 };
+enum { FLAG_OVERFLOW = 0, FLAG_MAPERR = 1, FLAG_LONGREAD = 2, FLAG_MAXCNT = 3, FLAG_LONGQ = 4, FLAG_SORTDUP = 5, N_FLAGS = 8 };
 
 struct WorkDev {
   int cap;                     // slots per read (matches / items / records) when slot_off is null
@@ -44,6 +44,8 @@ struct WorkDev {
   uint64_t *surv;              // n_reads * SURV_CAP: anchor offset << 48 | SA index
   uint8_t *surv_cnt;           // n_reads
   uint8_t *lc;                 // lower-cased reads with the 16-byte pads of the staging buffer: read r at seq_off[r] + 32 r + 16
+  // K5 record_sort (OutputSorter::flush, query.cpp:448-468): sort keys and permutation of the batch's flat records
+  uint64_t *sort_abs; uint8_t *sort_flag; uint32_t *sort_perm; uint32_t *sort_bytes; uint64_t *sort_off; void *sort_tmp; size_t sort_tmp_bytes;
   uint8_t *long_scratch;       // per-warp staging for reads longer than MAXQ_FAST (null if the batch has none)
   int long_q;                  // longest read of the batch
 };
@@ -83,6 +85,9 @@ int launch_publish(uint64_t *host_small, const uint64_t *sam_total, const uint64
 int launch_sizes_scan(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
 int launch_emit_text(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st, uint64_t n_records);
 int launch_emit_copy(const BatchDev &b, const WorkDev &w, cudaStream_t st, uint64_t n_records);
+// K5: rec_off re-derived so that the emit kernels write the records in MemSam::operator< order (memsam.h:136-158);
+// n_records is the host-known record count.  tmp_bytes_needed != null: only report the sort's scratch size.
+int launch_record_sort(const DevIndex &ix, const BatchDev &b, const WorkDev &w, uint64_t n_records, cudaStream_t st, size_t *tmp_bytes_needed);
 // matches -> CSR (offsets int64[n+1] + smash_match-compatible {u64 ref, u64 query, u64 len})
 int launch_match_csr(const BatchDev &b, const WorkDev &w, int64_t *off, uint64_t *triples, uint64_t *scratch, cudaStream_t st);
 int launch_mappability(const DevIndex &ix, uint64_t *min_len_scratch, uint8_t *body, cudaStream_t st);

@@ -267,6 +267,8 @@ inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes *a, const void
   return cudaSuccess;
 }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+enum cudaLimit { cudaLimitMaxL2FetchGranularity = 5 };
+inline cudaError_t cudaDeviceSetLimit(cudaLimit, size_t) { return cudaSuccess; }
 
 // ---- kernel<<<grid, block, smem, stream>>>(args...)  ==  shim_bind(kernel, grid, block, smem, stream)(args...) --------------
 template <class... KArgs> struct ShimBound {

@@ -428,6 +428,34 @@ def test_two_shards_equal_one_run(case):
         ix.close()
 
 
+@pytest.mark.parametrize("tagged", [False, True])
+def test_record_sort_equals_outputsorter_order(case, tagged):
+    """SMASH_WANT_SORTED: the batch's lines in the order OutputSorter::flush writes a chunk (MemSam::operator<,
+    memsam.h:136-158; the restated key is pinned on the reference's own chunk files in test_oracle_vs_reference.py),
+    same bytes as the input-order output, and the tail is unaffected."""
+    from smash_paper_b200 import api
+    ix = api.Index.open(case["fa"])
+    ctx = api.Context(ix, min_len=20, nomap=True, tag_mappability=tagged)
+    try:
+        if tagged:
+            ctx.load_mappability_file(case["fa"] + ".bin/map.bin")
+        key = O.memsam_sort_key(case["ref"].names, case["ref"].sizes)
+        plain = ctx.map_batch(case["reads"], want=api.WANT_SAM).sam
+        for rep in range(2):
+            got = ctx.map_batch(case["reads"], want=api.WANT_SAM | api.WANT_SORTED).sam
+            assert got == b"".join(sorted(plain.splitlines(keepends=True), key=key))
+        ctx.submit(0, case["reads"], want=api.WANT_SAM | api.WANT_SORTED); ctx.submit(1, case["reads"], want=api.WANT_SAM)
+        assert ctx.wait(0).sam == got and ctx.wait(1).sam == plain
+        # two reads with one name and the same mate bits at one position: the reference throws "flags equal"
+        from smash_paper_b200 import samio
+        twice = samio.concat_batches([samio.slice_batch(case["reads"], 0, 40), samio.slice_batch(case["reads"], 0, 40)])
+        with pytest.raises(api.SmashError, match="flags equal"):
+            ctx.map_batch(twice, want=api.WANT_SAM | api.WANT_SORTED)
+        assert ctx.map_batch(case["reads"], want=api.WANT_SAM | api.WANT_SORTED).sam == got        # the context survives it
+    finally:
+        ctx.close(); ix.close()
+
+
 def _perm_pairs(reads, order):
     from smash_paper_b200 import samio
     return samio.concat_batches([samio.slice_batch(reads, 2 * int(p), 2 * int(p) + 2) for p in order])

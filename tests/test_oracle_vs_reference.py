@@ -45,3 +45,19 @@ def test_tagger(live):
     body = np.fromfile(live["fa"] + ".bin/map.bin", dtype=np.uint8)[2:]
     mine = T.tag_lines(hdr.splitlines(keepends=True) + lines, live["oix"].descr[::2], live["oix"].sizes[::2], body)
     assert mine == O.ref_mappability_tag(live["fa"], p).splitlines(keepends=True)
+
+
+def test_chunk_files_are_sorted_by_the_restated_memsam_order(tmp_path):
+    """OutputSorter::flush (query.cpp:448-468) sorts a chunk with MemSam::operator< before writing it: every chunk file
+    of the unmodified binary must already be in the order of oracle.memsam_sort_key (which the GPU's K5 record_sort and
+    its tests use), ties included."""
+    from smash_paper_b200 import synth
+    d = str(tmp_path)
+    ref, reads, fa = synth.small_case(d, n_pairs=600, seed=19)
+    O.ref_build_index(fa, mappability=False)
+    chunks = O.ref_map_chunks(fa, os.path.join(d, "reads.sam"), d, threads=3)
+    key = O.memsam_sort_key(ref.names, ref.sizes)
+    assert sum(len(c) for c in chunks) > 1500
+    for lines in chunks:
+        assert lines == sorted(lines, key=key)
+        assert len(set(key(ln) for ln in lines)) == len(lines)          # a strict order: no two lines share a key
