@@ -280,11 +280,33 @@ def run_ours(args, wl, rank, world):
     d2h += host_counts.numel() * 8
     barrier()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop()
     t_e = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{dev}")
     if dist:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
     e2e_value = total_reads / float(t_e.item())
+
+    # ---------------- the same loop for a caller that archives no mapout: reads in, bin counts out (WANT_TAIL only).
+    # The production pipeline's product is the bin counts (binning.sh); the SAM text is an intermediate file.
+    ctx.tail_reset()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        slot = i % api.N_SLOTS
+        if i >= api.N_SLOTS:
+            ctx.wait(slot, copy=False)
+        ctx.submit(slot, batches[args.warmup + i], want=api.WANT_TAIL, first_pair=i * pairs_per_batch)
+    for i in range(max(0, args.steps - api.N_SLOTS), args.steps):
+        ctx.wait(i % api.N_SLOTS, copy=False)
+    counts_g3, stats3 = finish()
+    host_counts3 = counts_g3.cpu()
+    barrier()
+    t_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{dev}")
+    if dist:
+        dist.all_reduce(t_t, op=dist.ReduceOp.MAX)
+    e2e_tail_value = total_reads / float(t_t.item())
+    tail_counts_equal = bool(torch.equal(host_counts3, host_counts))
+    clocks = sampler.stop()
+    dma = dma_ceiling(torch, dev, dist)
 
     out = None
     if rank == 0:
@@ -330,7 +352,15 @@ def run_ours(args, wl, rank, world):
                        "l2": "inputs (index touches, 1.7 KB/read SAM) far larger than L2; distinct batch per step",
                        "timing": "sum of per-step CUDA-event durations with the batch resident + tail_finish/allreduce; max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // max(args.steps, 1),
-                    "d2h_bytes_per_step": d2h // max(args.steps, 1)},
+                    "d2h_bytes_per_step": d2h // max(args.steps, 1), "want": "SAM text + bin counts (SMASH_WANT_SAM | SMASH_WANT_TAIL)",
+                    # the SAM text crossing PCIe bounds this number: share of the box's measured pinned-copy ceiling it uses
+                    "d2h_gbs_per_gpu": (d2h / max(args.steps, 1)) * (e2e_value / world / B) / 1e9,
+                    "frac_of_d2h_ceiling": ((d2h / max(args.steps, 1)) * (e2e_value / world / B) / 1e9) / dma["d2h_gbs_concurrent_per_gpu"]
+                    if dma.get("d2h_gbs_concurrent_per_gpu") else None},
+            "e2e_tail_only": {"value": e2e_tail_value, "unit": UNIT, "h2d_bytes_per_step": h2d // max(args.steps, 1),
+                              "d2h_bytes_per_step": int(host_counts.numel() * 8 // max(args.steps, 1)),
+                              "want": "bin counts only (SMASH_WANT_TAIL): no mapout text leaves the GPU", "counts_equal_sam_run": tail_counts_equal},
+            "dma_ceiling": dma,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -365,6 +395,48 @@ def run_ours(args, wl, rank, world):
     if dist:
         dist.destroy_process_group()
     return out
+
+
+def dma_ceiling(torch, dev, dist, mb=256, reps=6):
+    """What the box's host<->device DMA can do for THIS rank while every rank does the same: pinned cudaMemcpyAsync of
+    256 MB buffers, D2H alone, H2D alone and both directions at once (CUDA events, all ranks started together)."""
+    n = mb << 20
+    try:
+        hp_in = torch.empty(n, dtype=torch.uint8, pin_memory=True); hp_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        d_in = torch.empty(n, dtype=torch.uint8, device=f"cuda:{dev}"); d_out = torch.zeros(n, dtype=torch.uint8, device=f"cuda:{dev}")
+        s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+        def run(h2d, d2h):
+            torch.cuda.synchronize()
+            if dist:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            s1.wait_event(e0); s2.wait_event(e0)
+            with torch.cuda.stream(s1):
+                for _ in range(reps if h2d else 0):
+                    d_in.copy_(hp_in, non_blocking=True)
+                e1.record()
+            with torch.cuda.stream(s2):
+                for _ in range(reps if d2h else 0):
+                    hp_out.copy_(d_out, non_blocking=True)
+                e2.record()
+            torch.cuda.synchronize()
+            return (reps * n / (e0.elapsed_time(e1) / 1e3) / 1e9 if h2d else None, reps * n / (e0.elapsed_time(e2) / 1e3) / 1e9 if d2h else None)
+
+        run(True, True)
+        h_alone = run(True, False)[0]
+        d_alone = run(False, True)[1]
+        h_both, d_both = run(True, True)
+        vals = torch.tensor([h_alone, d_alone, h_both, d_both], dtype=torch.float64, device=f"cuda:{dev}")
+        if dist:
+            dist.all_reduce(vals, op=dist.ReduceOp.MIN)          # the slowest rank's view (ranks run concurrently)
+        h_alone, d_alone, h_both, d_both = [float(x) for x in vals.tolist()]
+        return {"what": f"pinned cudaMemcpyAsync, {mb} MB x {reps}, every rank at once; min over ranks", "h2d_gbs_alone_per_gpu": h_alone,
+                "d2h_gbs_alone_per_gpu": d_alone, "h2d_gbs_concurrent_per_gpu": h_both, "d2h_gbs_concurrent_per_gpu": d_both}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
 
 
 def measure_ingest(api, ctx, batch, peak, steps):

@@ -246,8 +246,8 @@ struct Slot {
   DBuf<uint64_t> slot_off; DBuf<Aln> aln_scr; DBuf<uint16_t> ord_scr; DBuf<uint32_t> tmp32;   // MEM mode (CSR slots)
   uint64_t slots_total = 0; bool csr = false;
   DBuf<uint8_t> long_scratch; int long_q = 0;
-  bool split = false;
-  DBuf<uint64_t> surv; DBuf<uint8_t> surv_cnt; DBuf<uint8_t> lc;      // split search (k_mam_search -> k_mam_verify)
+  bool split = false, seed_ok = false;
+  DBuf<uint64_t> surv; DBuf<uint8_t> surv_cnt; DBuf<uint8_t> lc; DBuf<uint8_t> slow;      // split search (k_mam_seed [-> k_mam_search] -> k_mam_verify)
   DBuf<uint64_t> sort_abs, sort_off; DBuf<uint8_t> sort_flag, sort_tmp; DBuf<uint32_t> sort_perm, sort_bytes;   // K5 record_sort
   bool sorted = false;
   HBuf<uint16_t> h_flag;       // pinned staging for a pageable read_flag array
@@ -599,7 +599,7 @@ static void slot_release(Slot &s) {
   s.match_cnt.release(); s.item_slots.release(); s.rec_slots.release(); s.sums.release();
   s.nrec.release(); s.rec_base.release(); s.rec_read.release(); s.rec_bytes.release(); s.rec_off.release(); s.sam_total.release(); s.blk_sums2.release(); s.blk_sums.release(); s.sam.release(); s.flags.release();
   s.csr_off.release(); s.csr_triples.release(); s.long_scratch.release(); s.slot_off.release(); s.aln_scr.release(); s.ord_scr.release(); s.tmp32.release(); s.h_sam.release(); s.h_csr_off.release();
-  s.h_matches.release(); s.h_small.release(); s.h_flag.release(); s.surv.release(); s.surv_cnt.release(); s.lc.release();
+  s.h_matches.release(); s.h_small.release(); s.h_flag.release(); s.surv.release(); s.surv_cnt.release(); s.lc.release(); s.slow.release();
   s.sort_abs.release(); s.sort_off.release(); s.sort_flag.release(); s.sort_tmp.release(); s.sort_perm.release(); s.sort_bytes.release();
   for (int f = 0; f < 2; ++f) { s.ing_raw[f].release(); s.ing_ls[f].release(); s.ing_hdr[f].release(); }
   s.ing_hdr_flag.release(); s.ing_blk64.release(); s.ing_blk32.release(); s.ing_blk4.release(); s.ing_pre.release();
@@ -687,7 +687,9 @@ static int slot_reserve(smash_ctx *c, Slot &s, uint64_t n, size_t name_bytes, si
   // split search (k_mam_search parks candidates, k_mam_verify extends them): pays off on large references,
   // where the 4+4 filter exists and every read has a few dozen seed hits; small references verify in place
   s.split = c->prm.mode != SMASH_MODE_MEM && !g_no_split && (c->dix.ext != nullptr || g_force_split);
-  if (s.split && ((rc = s.surv.ensure(n * SURV_CAP + 1)) || (rc = s.surv_cnt.ensure(n + 1)) || (rc = s.lc.ensure(seq_bytes + 32 * n + 64))))
+  s.seed_ok = s.split && c->dix.ext != nullptr && c->sp.fast_ok;
+  if (s.split && ((rc = s.surv.ensure(n * SURV_CAP + 1)) || (rc = s.surv_cnt.ensure(n + 1)) || (rc = s.lc.ensure(seq_bytes + 32 * n + 64)) ||
+                  (rc = s.slow.ensure(n + 1))))
     return rc;
   if ((rc = s.match_slots.ensure(n * s.cap)) || (rc = s.match_cnt.ensure(n + 1)) || (rc = s.item_slots.ensure(n * s.cap)) ||
       (rc = s.rec_slots.ensure(n * s.cap)) || (rc = s.sums.ensure(n + 2)) || (rc = s.nrec.ensure(n + 1)) ||
@@ -764,7 +766,12 @@ static WorkDev work_of(Slot &s) {
   WorkDev w{};
   w.cap = s.cap; w.slot_off = s.csr ? s.slot_off.p : nullptr; w.slots_total = s.csr ? s.slots_total : s.n_reads * (uint64_t)s.cap;
   w.aln_scratch = s.aln_scr.p; w.ord_scratch = s.ord_scr.p;
-  if (!s.csr && s.surv.p && s.split) { w.surv = s.surv.p; w.surv_cnt = s.surv_cnt.p; w.lc = s.lc.p; }
+  if (!s.csr && s.surv.p && s.split) {
+    w.surv = s.surv.p; w.surv_cnt = s.surv_cnt.p; w.lc = s.lc.p;
+    // the lean seed stage needs the ext table and a seed rare enough for the anchor path; SMASH_NO_SEED_KERNEL: A/B switch
+    static const bool no_seed = getenv("SMASH_NO_SEED_KERNEL") != nullptr;
+    if (!no_seed && s.slow.p && s.seed_ok) w.slow = s.slow.p;
+  }
   w.long_scratch = s.long_q ? s.long_scratch.p : nullptr; w.long_q = s.long_q; w.match_slots = s.match_slots.p; w.match_cnt = s.match_cnt.p; w.item_slots = s.item_slots.p;
   w.rec_slots = s.rec_slots.p; w.sums = s.sums.p; w.nrec = s.nrec.p; w.rec_base = s.rec_base.p; w.rec_read = s.rec_read.p; w.rec_bytes = s.rec_bytes.p; w.rec_off = s.rec_off.p; w.sam_total = s.sam_total.p; w.blk_sums2 = s.blk_sums2.p;
   w.sort_abs = s.sort_abs.p; w.sort_flag = s.sort_flag.p; w.sort_perm = s.sort_perm.p; w.sort_bytes = s.sort_bytes.p; w.sort_off = s.sort_off.p;

@@ -250,13 +250,12 @@ HD bool kmer_invalid(const uint32_t *inv, int x, int k) {
   return (m & ((k >= 32 ? 0u : (1u << k)) - 1u)) != 0;
 }
 // ---- 4+4 character pre-filter -----------------------------------------------------------------------
-// ext[i] holds the 2-bit codes of T[SA[i]+k .. +k+4) (low byte, first char in the top bits) and of
-// T[SA[i]-1], T[SA[i]-2], .. (high byte, nearest char in the top bits); non-acgt / out-of-text chars
-// are stored as code 0.  A candidate whose k-mer matches can only reach length L if enough of these
-// agree with the read, so most chance hits of the seed are dismissed from ONE coalesced 2-byte load per
-// bucket entry, before the SA entry and the text are touched.  The test is conservative: codes of
-// non-acgt bytes may agree by accident (=> the candidate is merely verified on the text), but a
-// disagreement of codes is always a true mismatch on the fast path.
+// ext[i] holds the 2-bit codes of T[SA[i]+k .. +k+4) (low byte) and of T[SA[i]-4 .. SA[i]) (high byte), both in TEXT
+// order with the first char in the top bits; non-acgt / out-of-text chars are stored as code 0.  A candidate whose
+// k-mer matches can only reach length L if enough of these agree with the read, so most chance hits of the seed are
+// dismissed from ONE coalesced 2-byte load per bucket entry, before the SA entry and the text are touched.  The test
+// is conservative: codes of non-acgt bytes may agree by accident (=> the candidate is merely verified on the text),
+// but a disagreement of codes is always a true mismatch on the fast path.
 HD uint32_t lead_pairs8(uint32_t x) {      // number of leading equal 2-bit groups of an 8-bit xor (0..4)
 #if defined(__CUDA_ARCH__)
   return x ? (uint32_t)(__clz((int)x) - 24) >> 1 : 4u;
@@ -264,16 +263,21 @@ HD uint32_t lead_pairs8(uint32_t x) {      // number of leading equal 2-bit grou
   return x ? (uint32_t)(__builtin_clz(x) - 24) >> 1 : 4u;
 #endif
 }
+HD uint32_t trail_pairs8(uint32_t x) {     // number of trailing equal 2-bit groups of an 8-bit xor (0..4)
+#if defined(__CUDA_ARCH__)
+  return x ? (uint32_t)(__ffs((int)x) - 1) >> 1 : 4u;
+#else
+  return x ? (uint32_t)__builtin_ctz(x) >> 1 : 4u;
+#endif
+}
 HD uint32_t read_ext_codes(const uint8_t *P, int x, int k) {
   const uint64_t r = read8(P, x + k), l = read8(P, x - 4);
-  uint32_t lw = (uint32_t)l;                                  // bytes P[x-4..x): nearest char is the top byte
-  lw = (lw >> 24) | ((lw >> 8) & 0xff00u) | ((lw << 8) & 0xff0000u) | (lw << 24);
-  return code4((uint32_t)r) | (code4(lw) << 8);
+  return code4((uint32_t)r) | (code4((uint32_t)l) << 8);      // bytes P[x-4..x) in read order
 }
 // can a candidate with these ext codes still reach length L?
 HD bool ext_may_reach(uint32_t cand_ext, uint32_t read_ext, int k, uint32_t L) {
   const uint32_t x = cand_ext ^ read_ext;
-  const uint32_t r4 = lead_pairs8(x & 0xffu), l4 = lead_pairs8(x >> 8);
+  const uint32_t r4 = lead_pairs8(x & 0xffu), l4 = trail_pairs8(x >> 8);   // right: from the char after the k-mer; left: from the char before it
   return r4 == 4 || l4 == 4 || (uint32_t)k + r4 + l4 >= L;
 }
 

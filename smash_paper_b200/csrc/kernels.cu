@@ -100,7 +100,7 @@ __global__ void k_ext_build(DevIndex ix, int k, uint16_t *__restrict__ ext) {
       const uint64_t pr = c + (uint64_t)k + (uint64_t)j;
       const int br = pr < ix.N ? base_code(ix.text[pr]) : 4;
       r = (r << 2) | (uint32_t)(br > 3 ? 0 : br);
-      const int bl = c > (uint64_t)j ? base_code(ix.text[c - 1 - (uint64_t)j]) : 4;
+      const int bl = c >= (uint64_t)(4 - j) ? base_code(ix.text[c - (uint64_t)(4 - j)]) : 4;      // T[c-4], T[c-3], T[c-2], T[c-1]
       l = (l << 2) | (uint32_t)(bl > 3 ? 0 : bl);
     }
     ext[i] = (uint16_t)(r | (l << 8));
@@ -337,6 +337,7 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
   __syncthreads();
   const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
   for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
+    if (w.slow && !w.slow[read]) continue;         // k_mam_seed finished this read
     const int64_t so = b.seq_off[read];
     const int q = (int)(b.seq_off[read + 1] - so);
     if (lane == 0) sm.nstage[warp] = 0;
@@ -443,6 +444,136 @@ k_mam_search(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
       // more staged entries than the stage holds (copies of a saturated repeat family included): the dropped ones may
       // have been distinct matches, so this is always an overflow, never a silent count
       if (n > w.cap || n_raw > STAGE_CAP) { atomicAdd(&w.flags[FLAG_OVERFLOW], 1u); atomicMax(&w.flags[FLAG_MAXCNT], (uint32_t)(n_raw > STAGE_CAP ? n_raw : n)); }
+    }
+    __syncwarp();
+  }
+}
+
+// K1a': the seed stage of the split search, written for instruction count.  One warp per read, lanes = anchors, no
+// task lists and no per-byte staging:
+//   (0) the read's aligned words are fetched once (coalesced); each lane lower-cases its word through the per-CTA table,
+//       writes it to the lower-cased HBM copy k_mam_verify works on, and reduces it to ONE byte of 2-bit codes; an
+//       8-lane OR builds the non-acgt bit mask.  The 2-bit stream lives in shared memory (38 bytes for a 150 bp read).
+//   (1) lane a takes anchor x = a*s: one unaligned 64-bit window of the 2-bit stream holds, in order, the 4 bases
+//       before the k-mer, the k-mer and the 4 bases after it -> k-mer code, both halves of the read's ext code;
+//   (2) seed lookup [S[x], S[x+1]);
+//   (3) the bucket entries' 2-byte ext codes are tested where they lie (first four entries of every lane at once, the
+//       rare longer buckets in a warp-uniform loop) and the survivors are parked for k_mam_verify by ballot.
+// Reads that need the exact machinery -- a non-acgt byte that occurs in the text, a bucket over BIG_BUCKET, more than
+// SURV_CAP survivors -- are flagged in w.slow and redone by k_mam_search, which skips everything else.
+constexpr int CODE_PAD = 4;                                   // code bytes (16 bases) in front of the stream
+constexpr int CODE_BYTES = (MAXQ_FAST + 8) / 4 + CODE_PAD + 12;
+struct SeedSmem {
+  uint16_t lut[256];                                           // as SearchSmem::lut
+  uint8_t code[WARPS][(CODE_BYTES + 3) & ~3];                  // byte CODE_PAD + i: 2-bit codes of buffer bytes 4i..4i+3, first base in the top bits
+  uint32_t inv[WARPS][MAXQ_FAST / 32 + 12];                    // non-acgt mask in buffer coordinates (bit j + mis for base j)
+};
+// 8 bytes of the code stream starting at byte `bi`, as one big-endian number (first base in the top bits)
+__device__ __forceinline__ uint64_t code_window(const uint8_t *code, int bi) {
+  const uint32_t *a = reinterpret_cast<const uint32_t *>(code + (bi & ~3));
+  const uint32_t w0 = __byte_perm(a[0], 0, 0x0123), w1 = __byte_perm(a[1], 0, 0x0123), w2 = __byte_perm(a[2], 0, 0x0123);
+  const unsigned sh = (unsigned)(bi & 3) * 8u;
+  return ((uint64_t)__funnelshift_l(w1, w0, sh) << 32) | __funnelshift_l(w2, w1, sh);
+}
+#ifndef SMASH_SEED_MINBLK
+#define SMASH_SEED_MINBLK 6
+#endif
+__global__ void __launch_bounds__(THREADS, SMASH_SEED_MINBLK)
+k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
+  __shared__ __align__(16) SeedSmem sm;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  {
+    const uint8_t c = query_char((uint8_t)threadIdx.x, sp.nucleotides_only);
+    const bool not_acgt = base_code(c) > 3;
+    sm.lut[threadIdx.x] = (uint16_t)(c | (not_acgt ? 0x100 : 0) | (not_acgt && in_alpha(ix, c) ? 0x200 : 0));
+  }
+  __syncthreads();
+  const int L = (int)sp.L, s = sp.s, k = sp.k;
+  uint8_t *code = sm.code[warp];
+  uint32_t *inv = sm.inv[warp];
+  const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
+  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
+    const int64_t so = b.seq_off[read];
+    const int q = (int)(b.seq_off[read + 1] - so);
+    if (q > MAXQ_FAST) {                           // k_mam_search_long takes these (the host learns the length from the flag)
+      if (lane == 0) { atomicMax(&w.flags[FLAG_LONGQ], (uint32_t)q); if (q > w.long_q) w.match_cnt[read] = 0; w.surv_cnt[read] = 0; w.slow[read] = 0; }
+      continue;
+    }
+    // (0) words in, lower-cased copy out, 2-bit stream + non-acgt mask into shared memory
+    const int mis = (int)(so & 3);
+    const uint32_t *gw = reinterpret_cast<const uint32_t *>(b.seq + (so - mis));
+    uint8_t *lc = w.lc + so + 32 * read + 16;
+    uint32_t *lw = reinterpret_cast<uint32_t *>(lc - mis);
+    const int nwords = (mis + q + 3) >> 2;
+    unsigned oddbits = 0;
+    int w0 = 0;
+    for (; w0 < nwords; w0 += 32) {
+      const int i = w0 + lane;
+      unsigned nib = 0;
+      if (i < nwords) {
+        const uint32_t o = lut4(sm.lut, __ldg(gw + i), 4 * i - mis, q, nib, oddbits);
+        lw[i] = o;
+        code[CODE_PAD + i] = (uint8_t)code4(o);
+        if (4 * i - mis < 0 || 4 * i - mis + 3 >= q) {        // edge words: bytes outside the read can start no k-mer
+          for (int t = 0; t < 4; ++t) { const int j = 4 * i - mis + t; if (j < 0 || j >= q) nib |= 1u << t; }
+        }
+      }
+      unsigned m = nib << (4 * (lane & 7));
+      m |= __shfl_xor_sync(0xffffffffu, m, 1); m |= __shfl_xor_sync(0xffffffffu, m, 2); m |= __shfl_xor_sync(0xffffffffu, m, 4);
+      if ((lane & 7) == 0) inv[i >> 3] = m;
+    }
+    if (lane < 2) inv[(w0 >> 3) + lane] = 0xffffffffu;        // spare words (kmer_invalid reads word + 1): nothing starts there
+    if (lane < CODE_PAD) code[lane] = 0;
+    if (lane < 12) code[CODE_PAD + nwords + lane] = 0;
+    // pads of the lower-cased copy (core.cuh: 0xFE before, 0xFF after the read)
+    if (lane < P_FRONT && lane - P_FRONT < -mis) lc[lane - P_FRONT] = 0xFE;
+    { const int j = 4 * nwords - mis + lane; if (j < q + P_BACK) lc[j] = 0xFF; }
+    __syncwarp();
+    const bool odd = __any_sync(0xffffffffu, oddbits != 0);
+    int nsurv = 0;
+    bool slow = odd;
+    if (q >= L && !odd) {
+      const int n_anchor = (q - L + s - 1) / s + 1;          // anchors x = a*s cover starts 0..q-L
+      for (int a0 = 0; a0 < n_anchor && !slow; a0 += 32) {
+        const int a = a0 + lane, x = a * s;
+        uint64_t lo = 0; int cnt = 0; uint32_t rext = 0;
+        if (a < n_anchor && !kmer_invalid(inv, x + mis, k)) {
+          // (1) window = bases x-4 .. x+k+4 of the read
+          const int xb = x + mis + 4 * CODE_PAD - 4;           // stream position of base x-4
+          const uint64_t win = code_window(code, xb >> 2) << (2 * (xb & 3));
+          const uint32_t lcode = (uint32_t)(win >> 56);
+          const uint64_t kc = (win >> (56 - 2 * k)) & ((1ull << (2 * k)) - 1ull);
+          const uint32_t rcode = (uint32_t)(win >> (48 - 2 * k)) & 0xffu;
+          rext = rcode | (lcode << 8);
+          // (2) seed bucket (a sorted superset of the k-mer's suffix-array interval)
+          const int shk = 2 * (ix.seed_k - k);
+          lo = seed_at(ix, kc << shk);
+          const uint64_t hi = seed_at(ix, (kc + 1) << shk);
+          cnt = (int)(hi - lo < (uint64_t)(BIG_BUCKET + 1) ? hi - lo : (uint64_t)(BIG_BUCKET + 1));
+        }
+        if (__any_sync(0xffffffffu, cnt > BIG_BUCKET)) { slow = true; break; }
+        // (3) ext filter on the bucket entries; survivors parked in (entry, lane) order
+        for (int j0 = 0; !slow && __any_sync(0xffffffffu, j0 < cnt); j0 += 4) {
+          uint32_t e[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) e[t] = j0 + t < cnt ? (uint32_t)__ldg(ix.ext + lo + (uint64_t)(j0 + t)) : 0u;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const bool pass = j0 + t < cnt && ext_may_reach(e[t], rext, k, sp.L);
+            const unsigned mask = __ballot_sync(0xffffffffu, pass);
+            if (!mask) continue;
+            const int np = __popc(mask);
+            if (nsurv + np > SURV_CAP) { slow = true; break; }
+            if (pass) w.surv[read * SURV_CAP + nsurv + __popc(mask & ((1u << lane) - 1u))] = ((uint64_t)x << 48) | (lo + (uint64_t)(j0 + t));
+            nsurv += np;
+          }
+        }
+      }
+    }
+    if (lane == 0) {
+      w.slow[read] = slow ? 1 : 0;
+      w.surv_cnt[read] = (uint8_t)(slow ? 0 : nsurv);
+      w.match_cnt[read] = 0;
     }
     __syncwarp();
   }
@@ -607,6 +738,11 @@ k_mam_search_long(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
 
 int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
   if (!b.n_reads) return 0;
+  if (w.slow) {                                    // split search with the lean seed stage; k_mam_search redoes the flagged reads
+    k_mam_seed<<<grid_for_warps(b.n_reads, SMASH_SEED_MINBLK), THREADS, 0, st>>>(ix, b, w, p);
+    k_mam_search<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p);
+    return 2;
+  }
   k_mam_search<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p);
   return 1;
 }

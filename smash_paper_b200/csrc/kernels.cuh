@@ -43,6 +43,7 @@ struct WorkDev {
   // by k_mam_verify with lanes = candidates of ONE read (null => verification inside k_mam_search)
   uint64_t *surv;              // n_reads * SURV_CAP: anchor offset << 48 | SA index
   uint8_t *surv_cnt;           // n_reads
+  uint8_t *slow;               // n_reads: 1 = k_mam_seed left the read to k_mam_search (null => k_mam_search takes every read)
   uint8_t *lc;                 // lower-cased reads with the 16-byte pads of the staging buffer: read r at seq_off[r] + 32 r + 16
   // K5 record_sort (OutputSorter::flush, query.cpp:448-468): sort keys and permutation of the batch's flat records
   uint64_t *sort_abs; uint8_t *sort_flag; uint32_t *sort_perm; uint32_t *sort_bytes; uint64_t *sort_off; void *sort_tmp; size_t sort_tmp_bytes;

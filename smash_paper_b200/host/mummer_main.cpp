@@ -272,6 +272,10 @@ int main(int argc, char **argv) {
     smash_index_sam_header(ix, header.data(), header.size());
     if (o.verbose) std::cerr << "# running " << o.threads << " threads to answer queries\n# running " << o.inputs.size() << " query reader" << std::endl;
     const size_t BATCH = 1u << 20;                                   // reads per batch (even)
+    // every batch becomes one chunk file, its lines sorted as OutputSorter::flush sorts a chunk (query.cpp:448-468);
+    // SMASH_CHUNK_ORDER=input keeps them in input order instead
+    const char *ord_env = getenv("SMASH_CHUNK_ORDER");
+    const int want_sam = SMASH_WANT_SAM | ((ord_env && !strcmp(ord_env, "input")) ? 0 : SMASH_WANT_SORTED);
     uint64_t n_queries = 0, chunk = 0, pairs_done = 0;
     const auto tq = std::chrono::steady_clock::now();
     const bool device_reader = o.sam_in && !getenv("SMASH_HOST_READER");   // -samin text is parsed on the GPU (smash_submit_text)
@@ -314,7 +318,7 @@ int main(int argc, char **argv) {
           t.flags = (final ? SMASH_TEXT_FINAL : 0) | (o.replace_n ? SMASH_TEXT_REPLACE_N : 0) | (mate2_first ? SMASH_TEXT_MATE2_FIRST : 0);
           for (int k = 0; k < 2; ++k) { t.text[k] = text[k]; t.n_bytes[k] = len[k]; }
           t.first_pair_ordinal = pairs_done;
-          check(smash_submit_text(ctx, slot, &t, SMASH_WANT_SAM, &info));
+          check(smash_submit_text(ctx, slot, &t, want_sam, &info));
           in_flight[slot] = true; n_queries += info.n_reads; pairs_done += (info.n_reads + 1) / 2;
           mate2_first = info.mate2_first_next;
           slot = (slot + 1) % SMASH_N_SLOTS;
@@ -347,7 +351,7 @@ int main(int argc, char **argv) {
           smash_text t{}; smash_text_info info{};
           t.kind = SMASH_TEXT_SAM; t.flags = eof ? SMASH_TEXT_FINAL : 0; t.text[0] = text; t.n_bytes[0] = len;
           t.first_pair_ordinal = pairs_done;
-          check(smash_submit_text(ctx, slot, &t, SMASH_WANT_SAM, &info));
+          check(smash_submit_text(ctx, slot, &t, want_sam, &info));
           in_flight[slot] = true; n_queries += info.n_reads; pairs_done += (info.n_reads + 1) / 2;
           slot = (slot + 1) % SMASH_N_SLOTS;
           if (!eof && info.consumed[0] == 0 && len == cap) {          // a single line longer than the buffer: grow it
@@ -371,7 +375,7 @@ int main(int argc, char **argv) {
         while (b.n() < BATCH && (more = qp.next(b))) {}
         if (b.n()) {
           smash_batch v = b.view(pairs_done);
-          check(smash_submit(ctx, slot, &v, SMASH_WANT_SAM));      // the other slot's batch is still on the GPU
+          check(smash_submit(ctx, slot, &v, want_sam));      // the other slot's batch is still on the GPU
           in_flight[slot] = true; n_queries += b.n(); pairs_done += (b.n() + 1) / 2;
           slot = (slot + 1) % SMASH_N_SLOTS;
         }

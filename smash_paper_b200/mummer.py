@@ -130,7 +130,9 @@ def main(argv=None):
             for lo in range(0, batch.n, step):
                 hi = min(batch.n, lo + step)
                 sub = samio.slice_batch(batch, lo, hi)
-                res = ctx.map_batch(sub)
+                # a chunk's lines in OutputSorter order (query.cpp:448-468) unless SMASH_CHUNK_ORDER=input
+                want = api.WANT_SAM | (0 if os.environ.get("SMASH_CHUNK_ORDER") == "input" else api.WANT_SORTED)
+                res = ctx.map_batch(sub, want=want)
                 if a.samout:
                     chunk += 1
                     samio.write_mapout(header, res.sam, tag=f"b200_{k}", seq=chunk)

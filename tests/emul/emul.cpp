@@ -102,7 +102,7 @@ void *emul_index_create(const uint8_t *text, uint64_t N, const void *sa, const v
         const uint64_t pr = c + (uint64_t)kk + (uint64_t)j;
         const int br = pr < N ? base_code(text[pr]) : 4;
         r = (r << 2) | (uint32_t)(br > 3 ? 0 : br);
-        const int bl = c > (uint64_t)j ? base_code(text[c - 1 - (uint64_t)j]) : 4;
+        const int bl = c >= (uint64_t)(4 - j) ? base_code(text[c - (uint64_t)(4 - j)]) : 4;
         l = (l << 2) | (uint32_t)(bl > 3 ? 0 : bl);
       }
       e->ext[i] = (uint16_t)(r | (l << 8));

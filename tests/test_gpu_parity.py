@@ -290,11 +290,20 @@ def test_mummer_compatible_driver(case, workdir, driver):
     assert r.returncode == 0, r.stderr
     assert np.array_equal(np.fromfile(fa + ".bin/map.bin", dtype=np.uint8)[2:], case["body"])
     r = subprocess.run(exe + ["-rcref", "-qthreads", "12", "-nomap", "-samin", "-samout",
-                        fa, "reads.sam"], cwd=d, env=env, capture_output=True, text=True)
+                        fa, "reads.sam"], cwd=d, env=dict(env, SMASH_CHUNK_ORDER="input"), capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     got = b"".join(open(f, "rb").read() for f in sorted(glob.glob(os.path.join(d, "mapout", "*.txt"))))
     exp = case["oix"].sam_header().encode() + case["oix"].map_batch(case["reads"], min_len=20, n_threads=4)
     assert got == exp
+    # default: a chunk file is what a reference worker writes for the same chunk -- header + lines in MemSam order
+    shutil.rmtree(os.path.join(d, "mapout"))
+    r = subprocess.run(exe + ["-rcref", "-qthreads", "12", "-nomap", "-samin", "-samout", fa, "reads.sam"], cwd=d, env=env,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = b"".join(open(f, "rb").read() for f in sorted(glob.glob(os.path.join(d, "mapout", "*.txt"))))
+    hdr = case["oix"].sam_header().encode()
+    key = O.memsam_sort_key(case["ref"].names, case["ref"].sizes)
+    assert got == hdr + b"".join(sorted(exp[len(hdr):].splitlines(keepends=True), key=key))
     r = subprocess.run(exe + ["-rcref", "-nomap", fa, "reads.sam"], cwd=d, env=env,
                        capture_output=True, text=True)
     assert r.returncode == 1 and r.stderr.startswith("Error\n-nomap can only be used with -sam_out")
@@ -309,7 +318,7 @@ def test_driver_streams_sam_text_in_chunks(case, workdir):
     d = os.path.join(workdir, "driver_chunks")
     shutil.rmtree(d, ignore_errors=True)
     os.makedirs(d)
-    env = dict(os.environ, SMASH_TEXT_CHUNK="30011")
+    env = dict(os.environ, SMASH_TEXT_CHUNK="30011", SMASH_CHUNK_ORDER="input")
     r = subprocess.run([exe, "-rcref", "-nomap", "-samin", "-samout", case["fa"], os.path.join(case["dir"], "reads.sam")],
                        cwd=d, env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
