@@ -258,32 +258,42 @@ def run_ours(args, wl, rank, world):
     value = total_reads / (dev_ms_max / 1e3)
 
     # ---------------- end to end: pinned host batches in, SAM bytes + counts back on the host
-    ctx.tail_reset()
-    for i in range(max(api.N_SLOTS, min(2 * api.N_SLOTS, args.warmup))):   # warm every slot (buffers, pinned results)
-        ctx.submit(i % api.N_SLOTS, batches[i % len(batches)], want=want)
-        ctx.wait(i % api.N_SLOTS, copy=False)
-    ctx.tail_reset()
-    barrier()
-    t0 = time.perf_counter()
-    h2d = d2h = 0
-    for i in range(args.steps):
-        slot = i % api.N_SLOTS
-        if i >= api.N_SLOTS:
-            r = ctx.wait(slot, copy=False); d2h += int(r.sam_bytes)
-        b = batches[args.warmup + i]
-        ctx.submit(slot, b, want=want, first_pair=i * pairs_per_batch)
-        h2d += b.names.nbytes + b.name_off.nbytes + b.seq.nbytes + b.qual.nbytes + b.seq_off.nbytes + 2 * b.n
-    for i in range(max(0, args.steps - api.N_SLOTS), args.steps):
-        r = ctx.wait(i % api.N_SLOTS, copy=False); d2h += int(r.sam_bytes)
-    counts_g2, stats2 = finish()
-    host_counts = counts_g2.cpu()
-    d2h += host_counts.numel() * 8
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{dev}")
-    if dist:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = total_reads / float(t_e.item())
+    host_cores = len(os.sched_getaffinity(0))
+    host_threads = max(1, min(16, host_cores // max(world, 1)))
+
+    def e2e_loop(full_sam_text):
+        """smash_submit / smash_wait over both slots.  Default transport: the text the GPU computes + 32 B per record come
+        back and `host_threads` library threads rebuild the byte-identical SAM lines in host memory from the submitted
+        batch; full_sam_text: the whole SAM text crosses PCIe (round 1's path, kept as the A/B line)."""
+        ctx.set_transport(full_sam_text=full_sam_text, host_threads=host_threads)
+        ctx.tail_reset()
+        for i in range(max(api.N_SLOTS, min(2 * api.N_SLOTS, args.warmup))):   # warm every slot (buffers, pinned results, threads)
+            ctx.submit(i % api.N_SLOTS, batches[i % len(batches)], want=want)
+            ctx.wait(i % api.N_SLOTS, copy=False)
+        ctx.tail_reset()
+        ctx.io_bytes(reset=True)
+        barrier()
+        t0 = time.perf_counter()
+        sam_out = 0
+        for i in range(args.steps):
+            slot = i % api.N_SLOTS
+            if i >= api.N_SLOTS:
+                sam_out += int(ctx.wait(slot, copy=False).sam_bytes)
+            ctx.submit(slot, batches[args.warmup + i], want=want, first_pair=i * pairs_per_batch)
+        for i in range(max(0, args.steps - api.N_SLOTS), args.steps):
+            sam_out += int(ctx.wait(i % api.N_SLOTS, copy=False).sam_bytes)
+        counts_e, stats_e = finish()
+        host_counts_e = counts_e.cpu()
+        barrier()
+        t_e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{dev}")
+        if dist:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        h2d_b, d2h_b = ctx.io_bytes(reset=True)
+        return total_reads / float(t_e.item()), h2d_b, d2h_b + host_counts_e.numel() * 8, sam_out, host_counts_e
+
+    e2e_full_value, h2d_full, d2h_full, _, host_counts_full = e2e_loop(True)
+    e2e_value, h2d, d2h, sam_out_e2e, host_counts = e2e_loop(False)
+    counts_equal_full = bool(torch.equal(host_counts_full, host_counts))
 
     # ---------------- the same loop for a caller that archives no mapout: reads in, bin counts out (WANT_TAIL only).
     # The production pipeline's product is the bin counts (binning.sh); the SAM text is an intermediate file.
@@ -353,10 +363,16 @@ def run_ours(args, wl, rank, world):
                        "timing": "sum of per-step CUDA-event durations with the batch resident + tail_finish/allreduce; max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // max(args.steps, 1),
                     "d2h_bytes_per_step": d2h // max(args.steps, 1), "want": "SAM text + bin counts (SMASH_WANT_SAM | SMASH_WANT_TAIL)",
-                    # the SAM text crossing PCIe bounds this number: share of the box's measured pinned-copy ceiling it uses
+                    "transport": "compact: head/tags/L-R text + 32 B per record over PCIe, SAM lines rebuilt in host memory by the library's host threads (byte-identical, tests/test_transport.py)",
+                    "host_threads": host_threads, "host_cores": host_cores,
+                    "sam_bytes_in_host_memory_per_step": sam_out_e2e // max(args.steps, 1),
                     "d2h_gbs_per_gpu": (d2h / max(args.steps, 1)) * (e2e_value / world / B) / 1e9,
                     "frac_of_d2h_ceiling": ((d2h / max(args.steps, 1)) * (e2e_value / world / B) / 1e9) / dma["d2h_gbs_concurrent_per_gpu"]
                     if dma.get("d2h_gbs_concurrent_per_gpu") else None},
+            "e2e_full_sam_text": {"value": e2e_full_value, "unit": UNIT, "h2d_bytes_per_step": h2d_full // max(args.steps, 1),
+                                  "d2h_bytes_per_step": d2h_full // max(args.steps, 1), "counts_equal_compact_run": counts_equal_full,
+                                  "transport": "whole SAM text over PCIe (smash_ctx_set_transport(full_sam_text=1)): round 1's path, A/B line",
+                                  "d2h_gbs_per_gpu": (d2h_full / max(args.steps, 1)) * (e2e_full_value / world / B) / 1e9},
             "e2e_tail_only": {"value": e2e_tail_value, "unit": UNIT, "h2d_bytes_per_step": h2d // max(args.steps, 1),
                               "d2h_bytes_per_step": int(host_counts.numel() * 8 // max(args.steps, 1)),
                               "want": "bin counts only (SMASH_WANT_TAIL): no mapout text leaves the GPU", "counts_equal_sam_run": tail_counts_equal},

@@ -141,9 +141,18 @@ void smash_host_free(void *p);
 int smash_map_batch(smash_ctx *ctx, const smash_batch *b, int want, smash_result *res);
 
 /* Double-buffered form of smash_map_batch: a ctx owns SMASH_N_SLOTS independent slots (device
- * buffers + pinned result buffers + stream).  submit() enqueues H2D + kernels + D2H on the slot's
- * stream and returns; wait() blocks until that slot's result is in host memory.  The batch's
- * host buffers must stay valid until wait(). */
+ * buffers + pinned result buffers + streams + one host worker thread).  submit() hands the batch to
+ * the slot's worker and returns at once; the worker enqueues H2D + kernels + D2H (this is where the
+ * reference's Pair::run workers sit, query.cpp:481-520); wait() blocks until that slot's result is in
+ * host memory and reports any error of the batch.  The batch's host buffers must stay valid until
+ * wait().  Batches are appended to the tail in the order they were submitted, whichever slot they use.
+ *
+ * Transport of the SAM text: a line is NAME head SEQ QUAL tags [optional fields] L/R-tags (print_matches,
+ * query.cpp:331-415), and NAME/SEQ/QUAL/optional fields are the caller's own bytes.  By default only the
+ * text the GPU computes (head, tags, L/R tags: ~40 % of the line) plus 32 bytes per record cross PCIe and
+ * the library's host threads rebuild the byte-identical lines from the submitted batch ("compact
+ * transport", the `-qthreads` workers of the reference become these threads).  smash_submit_text and the
+ * device-resident calls always produce the whole text on the device. */
 #define SMASH_N_SLOTS 2
 int smash_submit(smash_ctx *ctx, int slot, const smash_batch *b, int want);
 int smash_wait(smash_ctx *ctx, int slot, smash_result *res);
@@ -254,6 +263,17 @@ int smash_memcpy(void *dst, const void *src, size_t bytes);
  * ranges are still searched; batches under `min_reads` reads go through whole.  Defaults 4 / 65536.
  * The output is byte-identical either way (MEM mode and SMASH_WANT_MATCHES always go through whole). */
 int smash_ctx_set_chunking(smash_ctx *ctx, int max_chunks, uint64_t min_reads);
+
+/* full_sam_text != 0: smash_submit downloads the whole SAM text instead of using the compact transport (A/B runs,
+ * tests).  host_threads: size of the context's line-building pool (0 = one per available core, at most 16; the
+ * reference's -qthreads).  Not while batches are in flight. */
+int smash_ctx_set_transport(smash_ctx *ctx, int full_sam_text, int host_threads);
+/* Bytes copied host->device / device->host by smash_submit* / smash_batch_upload / smash_map_* since the last reset,
+ * counted from the copies the library enqueues. */
+void smash_ctx_io_bytes(smash_ctx *ctx, uint64_t *h2d, uint64_t *d2h, int reset);
+/* Host half of the compact transport, exported for tests (no GPU needed): n_records CmpMeta entries (csrc/compact.h:
+ * {u64 sam_off; u32 cmp_off, read, head_len, tags_len, lr_len | rc << 31, pad}) + compact text -> SAM lines. */
+int smash_host_expand(const smash_batch *b, uint64_t read_base, const void *meta, uint64_t n_records, const char *cmp, char *sam);
 
 /* ---- counters for bench.py: kernels launched by this library since ctx creation */
 uint64_t smash_ctx_launch_count(const smash_ctx *ctx);

@@ -69,7 +69,7 @@ def child(args):
     cudart = ctypes.CDLL("/usr/local/cuda/lib64/libcudart.so")
     cudart.cudaSetDevice(0)
     t0 = time.time()
-    os.environ["SMASH_L2_FETCH"] = "0"                       # the library leaves the limit alone; this script sets it
+    os.environ["SMASH_L2_FETCH"] = os.environ.get("AB_L2_FETCH", "0")     # 0: the library leaves the limit alone; this script sets it
     ctx = api.Context.from_text(text, meta["startpos"], meta["sizes"], meta["descr"], keep_isa=True, chunk_cap=wl["chunk_cap"],
                                 min_len=wl["min_len"], nomap=True, tag_mappability=True, seed_k=int(args.seed_k))
     n_text = len(text)

@@ -461,6 +461,16 @@ class Context:
         """smash_ctx_set_chunking: how smash_submit pipelines one batch (output is identical either way)."""
         _check(load_library().smash_ctx_set_chunking(self.h, int(max_chunks), C.c_uint64(int(min_reads))))
 
+    def set_transport(self, full_sam_text=False, host_threads=0):
+        """smash_ctx_set_transport: whole SAM text over PCIe (A/B, tests) or the compact transport + host line building."""
+        _check(load_library().smash_ctx_set_transport(self.h, int(bool(full_sam_text)), int(host_threads)))
+
+    def io_bytes(self, reset=False):
+        """(h2d, d2h) bytes the library copied since the last reset."""
+        a, b = C.c_uint64(), C.c_uint64()
+        load_library().smash_ctx_io_bytes(self.h, C.byref(a), C.byref(b), int(reset))
+        return int(a.value), int(b.value)
+
     def stage_ms(self, reset=False):
         out = (C.c_double * 8)()
         load_library().smash_ctx_stage_ms(self.h, out, int(reset))

@@ -12,14 +12,21 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+#include <sched.h>
 
 #include "../../include/smash_b200.h"
 #include "kernels.cuh"
 #include "tail.cuh"
 #include "sabuild.cuh"
 #include "ingest_launch.cuh"
+#include "expand.h"
 
 using namespace smash;
 
@@ -30,6 +37,7 @@ static cudaEvent_t g_tl_base = nullptr;
 static const bool g_force_split = getenv("SMASH_FORCE_SPLIT_SEARCH") != nullptr;
 static const bool g_no_split = getenv("SMASH_NO_SPLIT_SEARCH") != nullptr;   // A/B switch: verification inside k_mam_search
 static const bool g_no_chunks = getenv("SMASH_NO_CHUNKS") != nullptr;   // A/B switch for the chunked submit pipeline
+static const bool g_full_sam = getenv("SMASH_FULL_SAM_D2H") != nullptr; // A/B switch: whole SAM text over PCIe instead of the compact transport
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 #define DBG_T(label, t0) do { if (g_dbg) fprintf(stderr, "[smash-dbg] %-28s %8.3f ms\n", label, now_ms() - (t0)); } while (0)
 static int fail(int code, const char *fmt, ...) {
@@ -263,6 +271,28 @@ struct Slot {
   // in flight
   bool busy = false; int want = 0; uint64_t n_reads = 0; uint64_t first_pair = 0;
   uint64_t sam_bytes = 0, n_matches = 0, n_records = 0;
+  uint64_t launches = 0, io_h2d = 0, io_d2h = 0;                  // merged into the ctx by slot_finish (caller's thread)
+  // compact transport (compact.h): per read range, head|tags|lr text + CmpMeta cross PCIe; host threads rebuild the lines
+  bool compact = false;
+  DBuf<uint32_t> cmp_bytes; DBuf<uint64_t> cmp_off;
+  DBuf<char> cmp[MAX_CHUNKS]; DBuf<CmpMeta> cmeta[MAX_CHUNKS];
+  HBuf<char> h_cmp[MAX_CHUNKS]; HBuf<CmpMeta> h_cmeta[MAX_CHUNKS];
+  cudaEvent_t ev_d2h[MAX_CHUNKS] = {};
+  uint64_t cmp_recs[MAX_CHUNKS] = {}; int n_ranges = 0, n_dispatched = 0;
+  std::atomic<int> pending{0};                                     // expansion tasks not finished yet
+  // the slot's host worker: H2D enqueue, the per-range launches (with their size read-backs) and the expansion run
+  // here, so smash_submit returns at once and two slots never serialise on each other's host synchronisations
+  std::thread worker; std::mutex mu; std::condition_variable cv;
+  int job_state = 0;                                               // 0 idle, 1 queued, 2 running, 3 done
+  bool quit = false;
+  smash_batch hb{}; bool job_prepare = false; int job_want = 0, job_chunks = 1, job_rc = 0; char job_err[1024] = "";
+  uint64_t job_seq = 0; bool turn_held = false, turn_done = true;     // order of the tail appends = order of submission
+};
+
+// host threads that expand compact records into SAM lines (one pool per context)
+struct ExpandTask { Slot *s; int ch; uint64_t f0, f1; };
+struct HostPool {
+  std::vector<std::thread> th; std::mutex mu; std::condition_variable cv; std::deque<ExpandTask> q; bool quit = false;
 };
 
 struct smash_ctx {
@@ -280,12 +310,18 @@ struct smash_ctx {
   int max_chunks = MAX_CHUNKS; uint64_t chunk_min_reads = CHUNK_MIN_READS;
   smash_index *own_index = nullptr;
   uint64_t index_bytes = 0;
-  uint64_t launches = 0;
+  uint64_t launches = 0, io_h2d = 0, io_d2h = 0;
+  int transport = 0;                                // 0: compact when the batch came from host buffers, 1: full SAM text over PCIe
+  int host_threads = 0;                             // expansion threads (0 = auto)
+  HostPool pool;
+  std::mutex turn_mu; std::condition_variable turn_cv; uint64_t next_seq = 0, tail_turn = 0;
   double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // search, records, sizes+scan, emit_text, csr, tail, emit_copy, verify
   double ingest_ms = 0;                            // device-side input stage (smash_submit_text / smash_text_upload)
   Slot slot[SMASH_N_SLOTS];
   TailState tail;
 };
+
+static int job_start(smash_ctx *c, Slot &s);
 
 static int dmalloc(void **p, size_t bytes, uint64_t *acct) {
   cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
@@ -348,6 +384,7 @@ static int ctx_begin(const smash_params *p, smash_ctx **out, int rcref) {
     for (int e = 0; e < MAX_CHUNKS; ++e) {
       CUC(cudaEventCreateWithFlags(&c->slot[s].ev_in[e], cudaEventDisableTiming));
       CUC(cudaEventCreateWithFlags(&c->slot[s].ev_emit[e], cudaEventDisableTiming));
+      CUC(cudaEventCreateWithFlags(&c->slot[s].ev_d2h[e], cudaEventDisableTiming));
     }
     CUC(cudaEventCreateWithFlags(&c->slot[s].ev_out, cudaEventDisableTiming));
   }
@@ -593,6 +630,125 @@ extern "C" int smash_ctx_save_index(smash_ctx *c, const char *ref_fasta, int wit
   return 0;
 }
 
+// ------------------------------------------------------------------ host threads: expansion pool, tail turn
+
+static void expand_task_run(const ExpandTask &t) {
+  Slot &s = *t.s;
+  ExpandArgs a{};
+  a.names = s.hb.names; a.name_off = s.hb.name_off; a.seq = s.hb.seq; a.qual = s.hb.qual; a.seq_off = s.hb.seq_off;
+  a.opt = s.opt_bytes ? s.hb.opt : nullptr; a.opt_off = s.opt_bytes ? s.hb.opt_off : nullptr;
+  a.read_base = s.chunk_r[t.ch];
+  a.meta = s.h_cmeta[t.ch].p; a.cmp = s.h_cmp[t.ch].p; a.sam = s.h_sam.p;
+  expand_records(a, t.f0, t.f1);
+  if (s.pending.fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(s.mu); s.cv.notify_all(); }
+}
+static bool pool_try_run_one(HostPool &p) {
+  ExpandTask t;
+  {
+    std::lock_guard<std::mutex> lk(p.mu);
+    if (p.q.empty()) return false;
+    t = p.q.front(); p.q.pop_front();
+  }
+  expand_task_run(t);
+  return true;
+}
+static void pool_main(HostPool *p) {
+  for (;;) {
+    ExpandTask t;
+    {
+      std::unique_lock<std::mutex> lk(p->mu);
+      p->cv.wait(lk, [&] { return p->quit || !p->q.empty(); });
+      if (p->q.empty()) return;                              // quit
+      t = p->q.front(); p->q.pop_front();
+    }
+    expand_task_run(t);
+  }
+}
+static int host_cpu_count() {
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof set, &set) == 0) { const int n = CPU_COUNT(&set); if (n > 0) return n; }
+  const unsigned h = std::thread::hardware_concurrency();
+  return h ? (int)h : 1;
+}
+static void pool_start(smash_ctx *c) {
+#if !defined(SMASH_CUDA_SHIM)
+  if (!c->pool.th.empty()) return;
+  int n = c->host_threads;
+  if (n <= 0) { if (const char *e = getenv("SMASH_HOST_THREADS")) n = atoi(e); }
+  if (n <= 0) { n = host_cpu_count(); if (n > 16) n = 16; }
+  for (int i = 0; i < n; ++i) c->pool.th.emplace_back(pool_main, &c->pool);
+#endif
+}
+constexpr uint64_t EXPAND_GRAIN = 4096;                      // records per task
+static void expand_dispatch(smash_ctx *c, Slot &s, int ch) {
+  const uint64_t recs = s.cmp_recs[ch];
+  if (!recs) return;
+  std::vector<ExpandTask> ts;
+  for (uint64_t f0 = 0; f0 < recs; f0 += EXPAND_GRAIN) ts.push_back(ExpandTask{&s, ch, f0, f0 + EXPAND_GRAIN < recs ? f0 + EXPAND_GRAIN : recs});
+  s.pending.fetch_add((int)ts.size());
+  { std::lock_guard<std::mutex> lk(c->pool.mu); c->pool.q.insert(c->pool.q.end(), ts.begin(), ts.end()); }
+  c->pool.cv.notify_all();
+}
+// read ranges whose download has landed become expansion tasks; block: wait for the downloads still in flight
+static int expand_poll(smash_ctx *c, Slot &s, bool block) {
+  while (s.n_dispatched < s.n_ranges) {
+    const int ch = s.n_dispatched;
+    if (block) CU(cudaEventSynchronize(s.ev_d2h[ch]));
+    else {
+      const cudaError_t e = cudaEventQuery(s.ev_d2h[ch]);
+      if (e == cudaErrorNotReady) return 0;
+      if (e != cudaSuccess) return fail(SMASH_ERR_CUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
+    }
+    expand_dispatch(c, s, ch);
+    ++s.n_dispatched;
+  }
+  return 0;
+}
+// every dispatched task has finished (the calling thread works too)
+static void expand_drain(smash_ctx *c, Slot &s) {
+  while (s.pending.load() > 0) {
+    if (pool_try_run_one(c->pool)) continue;
+    std::unique_lock<std::mutex> lk(s.mu);
+    s.cv.wait_for(lk, std::chrono::microseconds(200), [&] { return s.pending.load() <= 0; });
+  }
+}
+
+// The tail's appends must happen in the order the batches were submitted (first-wins dedupe, positions order), whichever
+// slot worker gets there first: a batch takes the turn before its first append and passes it on when it has enqueued
+// everything (or has nothing to append).
+static void slot_begin_job(smash_ctx *c, Slot &s) {
+  std::lock_guard<std::mutex> lk(c->turn_mu);
+  s.job_seq = c->next_seq++; s.turn_held = false; s.turn_done = false;
+}
+static void tail_turn_acquire(smash_ctx *c, Slot &s) {
+  if (s.turn_held || s.turn_done) return;
+  std::unique_lock<std::mutex> lk(c->turn_mu);
+  c->turn_cv.wait(lk, [&] { return c->tail_turn == s.job_seq; });
+  s.turn_held = true;
+}
+static void tail_turn_release(smash_ctx *c, Slot &s) {
+  if (s.turn_done) return;
+  std::unique_lock<std::mutex> lk(c->turn_mu);
+  if (!s.turn_held) c->turn_cv.wait(lk, [&] { return c->tail_turn == s.job_seq; });
+  c->tail_turn = s.job_seq + 1; s.turn_held = false; s.turn_done = true;
+  lk.unlock();
+  c->turn_cv.notify_all();
+}
+static void host_threads_stop(smash_ctx *c) {
+  for (int i = 0; i < SMASH_N_SLOTS; ++i) {
+    Slot &s = c->slot[i];
+    if (s.worker.joinable()) {
+      { std::lock_guard<std::mutex> lk(s.mu); s.quit = true; }
+      s.cv.notify_all();
+      s.worker.join();
+    }
+  }
+  { std::lock_guard<std::mutex> lk(c->pool.mu); c->pool.quit = true; }
+  c->pool.cv.notify_all();
+  for (auto &t : c->pool.th) t.join();
+  c->pool.th.clear();
+}
+
 static void slot_release(Slot &s) {
   s.names.release(); s.seq.release(); s.qual.release(); s.opt.release(); s.name_off.release();
   s.seq_off.release(); s.opt_off.release(); s.read_flag.release(); s.match_slots.release();
@@ -609,7 +765,13 @@ static void slot_release(Slot &s) {
   if (s.ev0) cudaEventDestroy(s.ev0);
   if (s.ev1) cudaEventDestroy(s.ev1);
   for (int e = 0; e < N_EVS; ++e) if (s.evs[e]) cudaEventDestroy(s.evs[e]);
-  for (int e = 0; e < MAX_CHUNKS; ++e) { if (s.ev_in[e]) cudaEventDestroy(s.ev_in[e]); if (s.ev_emit[e]) cudaEventDestroy(s.ev_emit[e]); }
+  for (int e = 0; e < MAX_CHUNKS; ++e) {
+    if (s.ev_in[e]) cudaEventDestroy(s.ev_in[e]);
+    if (s.ev_emit[e]) cudaEventDestroy(s.ev_emit[e]);
+    if (s.ev_d2h[e]) cudaEventDestroy(s.ev_d2h[e]);
+    s.cmp[e].release(); s.cmeta[e].release(); s.h_cmp[e].release(); s.h_cmeta[e].release();
+  }
+  s.cmp_bytes.release(); s.cmp_off.release();
   if (s.ev_out) cudaEventDestroy(s.ev_out);
   if (s.st_in) cudaStreamDestroy(s.st_in);
   if (s.st_out && s.owns_out) cudaStreamDestroy(s.st_out);
@@ -620,6 +782,7 @@ extern "C" void smash_ctx_destroy(smash_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  host_threads_stop(c);
   for (int s = 0; s < SMASH_N_SLOTS; ++s) slot_release(c->slot[s]);
   tail_release(&c->tail);
   void *ptrs[] = {c->descr8, c->ext, c->text_alloc, c->sa, c->isa, c->lcp, c->lcp_m, c->uniq, c->seed, c->startpos, c->sizes,
@@ -698,6 +861,7 @@ static int slot_reserve(smash_ctx *c, Slot &s, uint64_t n, size_t name_bytes, si
       (rc = s.blk_sums2.ensure(n * s.cap / 2048 + 8)) || (rc = s.flags.ensure(N_FLAGS)) ||
       (rc = s.h_small.ensure(32)))
     return rc;
+  if (s.compact && ((rc = s.cmp_bytes.ensure(n * s.cap + 1)) || (rc = s.cmp_off.ensure(n * s.cap + 2)))) return rc;
   DBG_T("  prepare:ensure", t_prep);
   // read ranges of the chunked pipeline (even boundaries: mates stay together)
   s.n_chunks = (chunks > 1 && n >= c->chunk_min_reads) ? (chunks > MAX_CHUNKS ? MAX_CHUNKS : chunks) : 1;
@@ -748,10 +912,12 @@ static int slot_prepare(smash_ctx *c, Slot &s, const smash_batch *b, bool copy, 
         CU(cudaMemcpyAsync(s.name_off.p + r0, b->name_off + r0, 8 * (r1 - r0 + 1), cudaMemcpyHostToDevice, in));
         CU(cudaMemcpyAsync(s.seq_off.p + r0, b->seq_off + r0, 8 * (r1 - r0 + 1), cudaMemcpyHostToDevice, in));
         CU(cudaMemcpyAsync(s.read_flag.p + r0, flag_src + r0, 2 * (r1 - r0), cudaMemcpyHostToDevice, in));
+        s.io_h2d += (n1 - n0) + 2 * (q1 - q0) + 16 * (r1 - r0 + 1) + 2 * (r1 - r0);
         if (opt_bytes) {
           const size_t o0 = (size_t)b->opt_off[r0], o1 = (size_t)b->opt_off[r1];
           CU(cudaMemcpyAsync(s.opt.p + o0, b->opt + o0, o1 - o0, cudaMemcpyHostToDevice, in));
           CU(cudaMemcpyAsync(s.opt_off.p + r0, b->opt_off + r0, 8 * (r1 - r0 + 1), cudaMemcpyHostToDevice, in));
+          s.io_h2d += (o1 - o0) + 8 * (r1 - r0 + 1);
         }
       }
       if (s.n_chunks > 1) CU(cudaEventRecord(s.ev_in[ch], in));
@@ -776,6 +942,7 @@ static WorkDev work_of(Slot &s) {
   w.rec_slots = s.rec_slots.p; w.sums = s.sums.p; w.nrec = s.nrec.p; w.rec_base = s.rec_base.p; w.rec_read = s.rec_read.p; w.rec_bytes = s.rec_bytes.p; w.rec_off = s.rec_off.p; w.sam_total = s.sam_total.p; w.blk_sums2 = s.blk_sums2.p;
   w.sort_abs = s.sort_abs.p; w.sort_flag = s.sort_flag.p; w.sort_perm = s.sort_perm.p; w.sort_bytes = s.sort_bytes.p; w.sort_off = s.sort_off.p;
   w.sort_tmp = s.sort_tmp.p; w.sort_tmp_bytes = s.sort_tmp.cap;
+  if (s.compact) { w.cmp_bytes = s.cmp_bytes.p; w.cmp_off = s.cmp_off.p; w.sam_base = s.sam_base; }
   w.blk_sums = s.blk_sums.p; w.sam = s.sam.p ? s.sam.p + s.sam_base : nullptr; w.sam_cap = s.sam.cap > s.sam_base ? s.sam.cap - s.sam_base : 0; w.flags = s.flags.p;
   return w;
 }
@@ -810,24 +977,25 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
           (rc = s.aln_scr.ensure(total + 1)) || (rc = s.ord_scr.ensure(total + 1)) || (rc = s.rec_read.ensure(total + 1)) ||
           (rc = s.rec_bytes.ensure(total + 1)) || (rc = s.rec_off.ensure(total + 2)) || (rc = s.blk_sums2.ensure(total / 2048 + 8)))
         return rc;
+      if (s.compact && ((rc = s.cmp_bytes.ensure(total + 1)) || (rc = s.cmp_off.ensure(total + 2)))) return rc;
       w = work_of(s);
       nl += launch_mem_write(c->dix, s.bd, c->sp, c->prm.min_len, s.slot_off.p, s.match_slots.p, s.st);
     } else {
       s.csr = false;
       nl = launch_mam_search(c->dix, s.bd, w, c->sp, s.st);
     }
-    c->launches += nl;
+    s.launches += nl;
     MARK(0);
     if (!s.csr) {
       const int nv = launch_mam_verify(c->dix, s.bd, w, c->sp, s.st);
-      c->launches += nv;
+      s.launches += nv;
       if (nv) MARK(7);
     }
-    c->launches += launch_records(c->dix, s.bd, w, c->sp, s.st);
+    s.launches += launch_records(c->dix, s.bd, w, c->sp, s.st);
     MARK(1);
-    c->launches += launch_sizes_scan(c->dix, s.bd, w, c->sp, s.st);
+    s.launches += launch_sizes_scan(c->dix, s.bd, w, c->sp, s.st);
     MARK(2);
-    c->launches += launch_publish(s.h_small.p, (const uint64_t *)s.sam_total.p, (const uint64_t *)(s.rec_base.p + n), s.flags.p, s.st);
+    s.launches += launch_publish(s.h_small.p, (const uint64_t *)s.sam_total.p, (const uint64_t *)(s.rec_base.p + n), s.flags.p, s.st);
     { const double ts = now_ms(); CU(cudaStreamSynchronize(s.st)); DBG_T("  run:sync for sizes", ts); }
     const uint32_t *fl = (const uint32_t *)(s.h_small.p + 1);
     if (fl[FLAG_LONGQ] > (uint32_t)s.long_q && c->prm.mode != SMASH_MODE_MEM) {
@@ -849,6 +1017,7 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
       if ((rc = s.match_slots.ensure(n_full * s.cap)) || (rc = s.item_slots.ensure(n_full * s.cap)) || (rc = s.rec_slots.ensure(n_full * s.cap)) ||
           (rc = s.rec_read.ensure(n_full * s.cap + 1)) || (rc = s.rec_bytes.ensure(n_full * s.cap + 1)) || (rc = s.rec_off.ensure(n_full * s.cap + 2)) ||
           (rc = s.blk_sums2.ensure(n_full * s.cap / 2048 + 8))) return rc;
+      if (s.compact && ((rc = s.cmp_bytes.ensure(n_full * s.cap + 1)) || (rc = s.cmp_off.ensure(n_full * s.cap + 2)))) return rc;
       continue;                                              // rerun the range with wider slots
     }
     if (fl[FLAG_MAPERR] && ((want & SMASH_WANT_TAIL) || c->prm.tag_mappability))
@@ -856,7 +1025,52 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
     break;
   }
   const uint64_t bytes = s.h_small.p[0], recs = s.h_small.p[8];
-  if (want & SMASH_WANT_SAM) {
+  if ((want & SMASH_WANT_SAM) && s.compact) {
+    // compact transport: only the text the GPU computes + one CmpMeta per record cross PCIe (compact.h)
+    int rc;
+    const uint64_t cbytes = s.h_small.p[9];
+    if (cbytes >= 0xffffff00ull) return fail(SMASH_ERR_ARG, "read range too large for the compact transport (%llu bytes)", (unsigned long long)cbytes);
+    if ((rc = s.cmp[ch].ensure(cbytes + 64)) || (rc = s.cmeta[ch].ensure(recs + 1)) || (rc = s.h_cmp[ch].ensure(cbytes + 64)) ||
+        (rc = s.h_cmeta[ch].ensure(recs + 1)))
+      return rc;
+    const uint64_t need = s.sam_base + bytes + 64;
+    const uint64_t guess = (chunked && ch == 0 && n) ? (uint64_t)((double)bytes * ((double)n_full / (double)n) * 1.03) + 4096 : 0;
+    if (need > s.h_sam.cap) {
+      expand_drain(c, s);                                     // lines of earlier ranges are being written into the old buffer
+      if ((rc = s.h_sam.grow_keep(need > guess ? need : guess, s.sam_base))) return rc;
+    }
+    if ((want & SMASH_WANT_SORTED) && recs) {
+      if (recs >= 0xffffffffull) return fail(SMASH_ERR_ARG, "too many records in one batch for SMASH_WANT_SORTED");
+      size_t tmp_bytes = 0;
+      launch_record_sort(c->dix, s.bd, work_of(s), recs, s.st, &tmp_bytes);
+      if ((rc = s.sort_abs.ensure(recs + 1)) || (rc = s.sort_off.ensure(recs + 2)) || (rc = s.sort_flag.ensure(recs + 1)) ||
+          (rc = s.sort_perm.ensure(recs + 1)) || (rc = s.sort_bytes.ensure(recs + 1)) || (rc = s.sort_tmp.ensure(tmp_bytes + 16)) ||
+          (rc = s.blk_sums2.ensure(recs / 2048 + 8)))
+        return rc;
+      s.launches += launch_record_sort(c->dix, s.bd, work_of(s), recs, s.st, nullptr);
+      s.sorted = true;
+    }
+    WorkDev w = work_of(s);
+    w.cmp = s.cmp[ch].p; w.cmeta = s.cmeta[ch].p;
+    s.launches += launch_emit_compact(c->dix, s.bd, w, c->sp, s.st, recs);
+    MARK(3);
+    if (s.sorted) s.launches += launch_publish(s.h_small.p, (const uint64_t *)s.sam_total.p, (const uint64_t *)(s.rec_base.p + n), s.flags.p, s.st);
+    cudaStream_t out = s.st;
+    if (chunked) {
+      CU(cudaEventRecord(s.ev_emit[ch], s.st));
+      CU(cudaStreamWaitEvent(s.st_out, s.ev_emit[ch], 0));
+      out = s.st_out;
+    }
+    if (g_dbg && s.tl[1] && ch == 0) cudaEventRecord(s.tl[1], out);
+    if (recs) {
+      CU(cudaMemcpyAsync(s.h_cmeta[ch].p, s.cmeta[ch].p, recs * sizeof(CmpMeta), cudaMemcpyDeviceToHost, out));
+      CU(cudaMemcpyAsync(s.h_cmp[ch].p, s.cmp[ch].p, cbytes, cudaMemcpyDeviceToHost, out));
+    }
+    if (g_dbg && s.tl[2] && ch == s.n_chunks - 1) cudaEventRecord(s.tl[2], out);
+    CU(cudaEventRecord(s.ev_d2h[ch], out));
+    s.cmp_recs[ch] = recs; s.n_ranges = ch + 1;
+    s.io_d2h += recs * sizeof(CmpMeta) + cbytes;
+  } else if (want & SMASH_WANT_SAM) {
     int rc;
     const uint64_t need = s.sam_base + bytes + 64;
     // first range of a chunked batch: size both buffers for the whole batch from this range's density
@@ -874,15 +1088,15 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
           (rc = s.sort_perm.ensure(recs + 1)) || (rc = s.sort_bytes.ensure(recs + 1)) || (rc = s.sort_tmp.ensure(tmp_bytes + 16)) ||
           (rc = s.blk_sums2.ensure(recs / 2048 + 8)))
         return rc;
-      c->launches += launch_record_sort(c->dix, s.bd, work_of(s), recs, s.st, nullptr);
+      s.launches += launch_record_sort(c->dix, s.bd, work_of(s), recs, s.st, nullptr);
       s.sorted = true;
     }
     WorkDev w = work_of(s);
-    c->launches += launch_emit_text(c->dix, s.bd, w, c->sp, s.st, recs);
+    s.launches += launch_emit_text(c->dix, s.bd, w, c->sp, s.st, recs);
     MARK(3);
-    c->launches += launch_emit_copy(s.bd, w, s.st, recs);
+    s.launches += launch_emit_copy(s.bd, w, s.st, recs);
     MARK(6);
-    if (s.sorted) c->launches += launch_publish(s.h_small.p, (const uint64_t *)s.sam_total.p, (const uint64_t *)(s.rec_base.p + n), s.flags.p, s.st);
+    if (s.sorted) s.launches += launch_publish(s.h_small.p, (const uint64_t *)s.sam_total.p, (const uint64_t *)(s.rec_base.p + n), s.flags.p, s.st);
     if (to_host) {
       if (need > s.h_sam.cap) {
         if (s.sam_base) CU(cudaStreamSynchronize(s.st_out));
@@ -896,6 +1110,7 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
       }
       if (g_dbg && s.tl[1] && ch == 0) cudaEventRecord(s.tl[1], out);
       CU(cudaMemcpyAsync(s.h_sam.p + s.sam_base, s.sam.p + s.sam_base, bytes, cudaMemcpyDeviceToHost, out));
+      s.io_d2h += bytes;
       if (g_dbg && s.tl[2] && ch == s.n_chunks - 1) cudaEventRecord(s.tl[2], out);
     }
   }
@@ -905,15 +1120,17 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
     const size_t mslots = s.csr ? (size_t)s.slots_total : n * (size_t)s.cap;
     if ((rc = s.csr_triples.ensure(3 * mslots + 8))) return rc;
     WorkDev w = work_of(s);
-    c->launches += launch_match_csr(s.bd, w, s.csr_off.p, s.csr_triples.p, s.blk_sums.p, s.st);
+    s.launches += launch_match_csr(s.bd, w, s.csr_off.p, s.csr_triples.p, s.blk_sums.p, s.st);
     MARK(4);
     if ((rc = s.h_csr_off.ensure(n + 2)) || (rc = s.h_matches.ensure(mslots + 8))) return rc;
     CU(cudaMemcpyAsync(s.h_csr_off.p, s.csr_off.p, 8 * (n + 1), cudaMemcpyDeviceToHost, s.st));
     CU(cudaMemcpyAsync(s.h_matches.p, s.csr_triples.p, 24 * mslots, cudaMemcpyDeviceToHost, s.st));
+    s.io_d2h += 8 * (n + 1) + 24 * mslots;
   }
   if (want & SMASH_WANT_TAIL) {
+    tail_turn_acquire(c, s);                                  // appends happen in the order the batches were submitted
     const double tt = now_ms();
-    int rc = tail_accumulate(&c->tail, c->dix, s.bd, work_of(s), recs, s.chunk_name_bytes[ch], s.st, &c->launches);
+    int rc = tail_accumulate(&c->tail, c->dix, s.bd, work_of(s), recs, s.chunk_name_bytes[ch], s.st, &s.launches);
     DBG_T("  run:tail_accumulate", tt);
     if (rc) return fail(rc, "tail: %s", tail_error());
     MARK(5);
@@ -925,6 +1142,8 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
 
 static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
   s.sam_bytes = 0; s.n_matches = 0; s.n_records = 0; s.want = want; s.sam_base = 0; s.n_evs = 0; s.sorted = false;
+  s.n_ranges = 0; s.n_dispatched = 0;
+  for (int ch = 0; ch < MAX_CHUNKS; ++ch) s.cmp_recs[ch] = 0;
   if (!s.n_reads) return 0;
   if (s.n_chunks > 1 && (!to_host || (want & SMASH_WANT_MATCHES) || c->prm.mode == SMASH_MODE_MEM))
     return fail(SMASH_ERR_STATE, "internal: chunked batch on a path that cannot take one");
@@ -941,6 +1160,7 @@ static int slot_run(smash_ctx *c, Slot &s, int want, bool to_host) {
     s.n_reads = r1 - r0;
     if (s.n_chunks > 1) { cudaError_t e = cudaStreamWaitEvent(s.st, s.ev_in[ch], 0); if (e != cudaSuccess) { rc = fail(SMASH_ERR_CUDA, "%s", cudaGetErrorString(e)); break; } }
     rc = run_range(c, s, want, to_host, ch, n_full);
+    if (!rc && s.compact) rc = expand_poll(c, s, false);      // ranges already on the host: their lines are built meanwhile
   }
   s.bd = full; s.n_reads = n_full;
   if (rc) return rc;
@@ -964,6 +1184,8 @@ static void ingest_collect(smash_ctx *c, Slot &s) {
 static int slot_finish(smash_ctx *c, Slot &s, smash_result *res) {
   CU(cudaStreamSynchronize(s.st));
   CU(cudaGetLastError());
+  c->launches += s.launches; c->io_h2d += s.io_h2d; c->io_d2h += s.io_d2h;
+  s.launches = 0; s.io_h2d = 0; s.io_d2h = 0;
   ingest_collect(c, s);
   if (s.sorted && ((const uint32_t *)(s.h_small.p + 1))[FLAG_SORTDUP]) {
     s.busy = false;
@@ -1134,12 +1356,11 @@ extern "C" int smash_submit_text(smash_ctx *c, int slot, const smash_text *t, in
   Slot &s = c->slot[slot];
   if (s.busy) return fail(SMASH_ERR_STATE, "slot %d still has a batch in flight", slot);
   CU(cudaSetDevice(c->device));
+  s.compact = false;                                         // the packed batch exists only on the device: full SAM text comes back
   int rc = ingest_text(c, s, t, info);
   if (rc) return rc;
-  rc = slot_run(c, s, want, true);
-  if (rc) return rc;
-  s.busy = true;
-  return 0;
+  s.job_prepare = false; s.job_want = want; s.job_chunks = 1;
+  return job_start(c, s);
 }
 extern "C" int smash_text_upload(smash_ctx *c, const smash_text *t, smash_text_info *info) {
   if (!c || !t) return fail(SMASH_ERR_ARG, "null argument");
@@ -1192,34 +1413,88 @@ extern "C" int smash_fetch_batch(smash_ctx *c, int slot, uint8_t *names, int64_t
   return 0;
 }
 
+// One batch on its slot's worker thread: H2D enqueue, the per-range kernel launches (each reads its sizes back before
+// the emit kernels), the tail appends in submission order, and -- compact transport -- the expansion into SAM lines.
+static int run_job(smash_ctx *c, Slot &s) {
+  int rc = 0;
+  if (s.job_prepare) rc = slot_prepare(c, s, &s.hb, true, s.job_chunks);
+  if (!rc) rc = slot_run(c, s, s.job_want, true);
+  tail_turn_release(c, s);                                   // the next batch may append now
+  if (s.compact) {
+    if (!rc) rc = expand_poll(c, s, true);
+    expand_drain(c, s);                                      // also on errors: tasks reference the slot's buffers
+  }
+  return rc;
+}
+static void slot_worker_main(smash_ctx *c, Slot *sp) {
+  Slot &s = *sp;
+  cudaSetDevice(c->device);
+  for (;;) {
+    {
+      std::unique_lock<std::mutex> lk(s.mu);
+      s.cv.wait(lk, [&] { return s.quit || s.job_state == 1; });
+      if (s.quit) return;
+      s.job_state = 2;
+    }
+    const int rc = run_job(c, s);
+    if (rc) { strncpy(s.job_err, g_err, sizeof s.job_err - 1); s.job_err[sizeof s.job_err - 1] = 0; }
+    { std::lock_guard<std::mutex> lk(s.mu); s.job_rc = rc; s.job_state = 3; }
+    s.cv.notify_all();
+  }
+}
+static int job_start(smash_ctx *c, Slot &s) {
+  slot_begin_job(c, s);
+  s.busy = true;
+#if defined(SMASH_CUDA_SHIM)
+  s.job_rc = run_job(c, s);                                  // host emulation (tests/emul): no threads
+  if (s.job_rc) { strncpy(s.job_err, g_err, sizeof s.job_err - 1); s.job_err[sizeof s.job_err - 1] = 0; }
+  s.job_state = 3;
+#else
+  if (s.compact) pool_start(c);
+  if (!s.worker.joinable()) s.worker = std::thread(slot_worker_main, c, &s);
+  { std::lock_guard<std::mutex> lk(s.mu); s.job_state = 1; }
+  s.cv.notify_all();
+#endif
+  return 0;
+}
+
 extern "C" int smash_submit(smash_ctx *c, int slot, const smash_batch *b, int want) {
   if (!c || !b || slot < 0 || slot >= SMASH_N_SLOTS) return fail(SMASH_ERR_ARG, "bad argument");
   Slot &s = c->slot[slot];
   if (s.busy) return fail(SMASH_ERR_STATE, "slot %d still has a batch in flight", slot);
+  if (b->n_reads && (!b->names || !b->name_off || !b->seq || !b->qual || !b->seq_off || !b->read_flag)) return fail(SMASH_ERR_ARG, "batch with null arrays");
   CU(cudaSetDevice(c->device));
-  double t0 = now_ms();
   if (g_dbg) {
     if (!g_tl_base) { cudaEventCreate(&g_tl_base); cudaEventRecord(g_tl_base, s.st); }
     for (int e = 0; e < 3; ++e) if (!s.tl[e]) cudaEventCreate(&s.tl[e]);
     cudaEventRecord(s.tl[0], s.st);
   }
   // (a sorted batch is ONE chunk of the reference's OutputSorter: it goes through whole)
-  const int chunks = (c->prm.mode != SMASH_MODE_MEM && !(want & (SMASH_WANT_MATCHES | SMASH_WANT_SORTED)) && (want & SMASH_WANT_SAM) && !g_no_chunks) ? c->max_chunks : 1;
-  int rc = slot_prepare(c, s, b, true, chunks);
-  DBG_T("submit:prepare+h2d enqueue", t0);
-  if (rc) return rc;
-  t0 = now_ms();
-  rc = slot_run(c, s, want, true);
-  DBG_T("submit:run", t0);
-  if (rc) return rc;
-  s.busy = true;
-  return 0;
+  s.job_chunks = (c->prm.mode != SMASH_MODE_MEM && !(want & (SMASH_WANT_MATCHES | SMASH_WANT_SORTED)) && (want & SMASH_WANT_SAM) && !g_no_chunks) ? c->max_chunks : 1;
+  s.hb = *b; s.job_prepare = true; s.job_want = want;
+  // the caller's batch stays valid until smash_wait, so the lines can be rebuilt from it on the host: compact transport
+  s.compact = (want & SMASH_WANT_SAM) && !g_full_sam && c->transport == 0;
+  return job_start(c, s);
 }
 extern "C" int smash_wait(smash_ctx *c, int slot, smash_result *res) {
   if (!c || slot < 0 || slot >= SMASH_N_SLOTS) return fail(SMASH_ERR_ARG, "bad argument");
   CU(cudaSetDevice(c->device));
   const double t0 = now_ms();
-  const int rc = slot_finish(c, c->slot[slot], res);
+  Slot &s = c->slot[slot];
+  if (s.job_state != 0) {
+    {
+      std::unique_lock<std::mutex> lk(s.mu);
+      s.cv.wait(lk, [&] { return s.job_state == 3; });
+      s.job_state = 0;
+    }
+    if (s.job_rc) {
+      cudaStreamSynchronize(s.st); cudaGetLastError();
+      c->launches += s.launches; s.launches = 0; s.io_h2d = 0; s.io_d2h = 0;
+      s.busy = false;
+      return fail(s.job_rc, "%s", s.job_err);
+    }
+  }
+  const int rc = slot_finish(c, s, res);
   DBG_T("wait", t0);
   return rc;
 }
@@ -1233,16 +1508,23 @@ extern "C" int smash_batch_upload(smash_ctx *c, const smash_batch *b) {
   if (!c || !b) return fail(SMASH_ERR_ARG, "null argument");
   CU(cudaSetDevice(c->device));
   Slot &s = c->slot[0];
+  if (s.busy) return fail(SMASH_ERR_STATE, "slot 0 still has a batch in flight");
+  s.compact = false;
   int rc = slot_prepare(c, s, b, true);
   if (rc) return rc;
   CU(cudaStreamSynchronize(s.st));
+  c->io_h2d += s.io_h2d; s.io_h2d = 0;
   return 0;
 }
 extern "C" int smash_map_resident(smash_ctx *c, int want, smash_result *res) {
   if (!c) return fail(SMASH_ERR_ARG, "null argument");
   CU(cudaSetDevice(c->device));
   Slot &s = c->slot[0];
+  if (s.busy) return fail(SMASH_ERR_STATE, "slot 0 still has a batch in flight");
+  s.compact = false;
+  slot_begin_job(c, s);
   int rc = slot_run(c, s, want & ~SMASH_WANT_MATCHES, false);
+  tail_turn_release(c, s);
   if (rc) return rc;
   rc = slot_finish(c, s, res);
   if (res) res->sam = nullptr;
@@ -1261,6 +1543,12 @@ extern "C" int smash_fetch_sam(smash_ctx *c, const char **sam, uint64_t *n_bytes
 
 // ------------------------------------------------------------------ tail + misc
 
+// the tail calls below read or reset what the slot workers append to
+static int require_idle(smash_ctx *c) {
+  for (int i = 0; i < SMASH_N_SLOTS; ++i)
+    if (c->slot[i].busy) return fail(SMASH_ERR_STATE, "slot %d still has a batch in flight: collect it with smash_wait first", i);
+  return 0;
+}
 extern "C" int smash_tail_configure(smash_ctx *c, const int64_t *bin_starts, uint64_t n_bins,
                                     const char *const *chrom_names, const int64_t *chrom_offsets,
                                     uint64_t n_chroms, int64_t hit_window, int32_t min_excess) {
@@ -1293,6 +1581,7 @@ extern "C" int smash_tail_configure(smash_ctx *c, const int64_t *bin_starts, uin
 }
 extern "C" int smash_tail_finish(smash_ctx *c, int64_t *counts, void *counts_device, smash_tail_stats *st) {
   if (!c) return fail(SMASH_ERR_ARG, "null argument");
+  if (int idle_rc = require_idle(c)) return idle_rc;
   CU(cudaSetDevice(c->device));
   for (int s = 0; s < SMASH_N_SLOTS; ++s) CU(cudaStreamSynchronize(c->slot[s].st));
   const double tf = now_ms();
@@ -1303,6 +1592,7 @@ extern "C" int smash_tail_finish(smash_ctx *c, int64_t *counts, void *counts_dev
 }
 extern "C" int smash_tail_export_keys(smash_ctx *c, uint64_t ordinal_base, const void **dev_keys, uint64_t *n_keys) {
   if (!c || !dev_keys || !n_keys) return fail(SMASH_ERR_ARG, "null argument");
+  if (int idle_rc = require_idle(c)) return idle_rc;
   CU(cudaSetDevice(c->device));
   for (int s = 0; s < SMASH_N_SLOTS; ++s) CU(cudaStreamSynchronize(c->slot[s].st));
   const uint64_t *k = nullptr;
@@ -1314,6 +1604,7 @@ extern "C" int smash_tail_export_keys(smash_ctx *c, uint64_t ordinal_base, const
 extern "C" int smash_tail_phase_a(smash_ctx *c, uint64_t ordinal_base, const void *foreign_keys_dev, uint64_t n_foreign,
                                   smash_tail_edge *edge) {
   if (!c) return fail(SMASH_ERR_ARG, "null argument");
+  if (int idle_rc = require_idle(c)) return idle_rc;
   CU(cudaSetDevice(c->device));
   for (int s = 0; s < SMASH_N_SLOTS; ++s) CU(cudaStreamSynchronize(c->slot[s].st));
   int rc = tail_phase_a(&c->tail, ordinal_base, (const uint64_t *)foreign_keys_dev, n_foreign, edge, c->slot[0].st, &c->launches, nullptr, true);
@@ -1323,6 +1614,7 @@ extern "C" int smash_tail_phase_a(smash_ctx *c, uint64_t ordinal_base, const voi
 extern "C" int smash_tail_phase_a_verdict(smash_ctx *c, uint64_t ordinal_base, const void *min_ordinal_dev, uint64_t n_keys,
                                           smash_tail_edge *edge) {
   if (!c || (!min_ordinal_dev && n_keys)) return fail(SMASH_ERR_ARG, "null argument");
+  if (int idle_rc = require_idle(c)) return idle_rc;
   CU(cudaSetDevice(c->device));
   for (int s = 0; s < SMASH_N_SLOTS; ++s) CU(cudaStreamSynchronize(c->slot[s].st));
   static const uint64_t dummy = 0;
@@ -1334,6 +1626,7 @@ extern "C" int smash_tail_phase_a_verdict(smash_ctx *c, uint64_t ordinal_base, c
 extern "C" int smash_tail_phase_b(smash_ctx *c, int has_prev, int64_t prev_last_pos, int64_t *counts, void *counts_device,
                                   smash_tail_stats *st) {
   if (!c) return fail(SMASH_ERR_ARG, "null argument");
+  if (int idle_rc = require_idle(c)) return idle_rc;
   CU(cudaSetDevice(c->device));
   int rc = tail_phase_b(&c->tail, has_prev, prev_last_pos, counts, (int64_t *)counts_device, st, c->slot[0].st, &c->launches);
   if (rc) return fail(rc, "tail: %s", tail_error());
@@ -1355,6 +1648,7 @@ extern "C" int smash_tail_reserve(smash_ctx *c, uint64_t max_pairs, uint64_t max
 }
 extern "C" int smash_tail_reset(smash_ctx *c) {
   if (!c) return fail(SMASH_ERR_ARG, "null argument");
+  if (int idle_rc = require_idle(c)) return idle_rc;
   CU(cudaSetDevice(c->device));
   tail_reset(&c->tail);
   return 0;
@@ -1384,6 +1678,34 @@ extern "C" int smash_ctx_set_tag_mappability(smash_ctx *c, int on) {
 extern "C" int smash_ctx_set_chunking(smash_ctx *c, int max_chunks, uint64_t min_reads) {
   if (!c || max_chunks < 1 || max_chunks > MAX_CHUNKS) return fail(SMASH_ERR_ARG, "max_chunks must be 1..%d", MAX_CHUNKS);
   c->max_chunks = max_chunks; c->chunk_min_reads = min_reads < 2 ? 2 : min_reads;
+  return 0;
+}
+extern "C" int smash_ctx_set_transport(smash_ctx *c, int full_sam_text, int host_threads) {
+  if (!c) return fail(SMASH_ERR_ARG, "null argument");
+  for (int i = 0; i < SMASH_N_SLOTS; ++i) if (c->slot[i].busy) return fail(SMASH_ERR_STATE, "slot %d has a batch in flight", i);
+  c->transport = full_sam_text ? 1 : 0;
+  if (host_threads != c->host_threads && !c->pool.th.empty()) {       // restart the expansion pool with the new size
+    { std::lock_guard<std::mutex> lk(c->pool.mu); c->pool.quit = true; }
+    c->pool.cv.notify_all();
+    for (auto &t : c->pool.th) t.join();
+    c->pool.th.clear(); c->pool.quit = false;
+  }
+  c->host_threads = host_threads;
+  return 0;
+}
+extern "C" void smash_ctx_io_bytes(smash_ctx *c, uint64_t *h2d, uint64_t *d2h, int reset) {
+  if (!c) return;
+  if (h2d) *h2d = c->io_h2d;
+  if (d2h) *d2h = c->io_d2h;
+  if (reset) { c->io_h2d = 0; c->io_d2h = 0; }
+}
+extern "C" int smash_host_expand(const smash_batch *b, uint64_t read_base, const void *meta, uint64_t n_records, const char *cmp, char *sam) {
+  if (!b || !meta || !cmp || !sam) return fail(SMASH_ERR_ARG, "null argument");
+  ExpandArgs a{};
+  a.names = b->names; a.name_off = b->name_off; a.seq = b->seq; a.qual = b->qual; a.seq_off = b->seq_off;
+  a.opt = b->opt; a.opt_off = b->opt ? b->opt_off : nullptr;
+  a.read_base = read_base; a.meta = (const CmpMeta *)meta; a.cmp = cmp; a.sam = sam;
+  expand_records(a, 0, n_records);
   return 0;
 }
 extern "C" uint64_t smash_ctx_launch_count(const smash_ctx *c) { return c ? c->launches : 0; }

@@ -964,6 +964,7 @@ k_sizes(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     if (sp.tag_mappability && !me.unmapped) put_lr_tags(cs, ix, recs[r], items);
     recs[r].seq_off = (uint16_t)seq_at; recs[r].lr_len = (uint16_t)(cs.n - before_lr);
     w.rec_bytes[f] = cs.n + 2u * (uint32_t)q + 1u /*tab between SEQ and QUAL*/ + (uint32_t)opt_len + 1u /*\n*/;
+    if (w.cmp_bytes) w.cmp_bytes[f] = cs.n - (uint32_t)name_len + 1u;      // compact transport: head + tags + lr-tags + \n
   }
 }
 
@@ -1054,7 +1055,7 @@ static int exclusive_scan_u32_devn(const uint32_t *in, uint64_t n_bound, const u
 // would queue behind the other slot's in-flight SAM download and stall this slot for its whole length.
 __global__ void k_publish(uint64_t *__restrict__ host_small, const uint64_t *__restrict__ sam_total,
                           const uint64_t *__restrict__ rec_total, const uint32_t *__restrict__ flags) {
-  if (threadIdx.x == 0) { host_small[0] = *sam_total; host_small[8] = *rec_total; }
+  if (threadIdx.x == 0) { host_small[0] = sam_total[0]; host_small[8] = *rec_total; host_small[9] = sam_total[1]; }
   if (threadIdx.x < N_FLAGS) ((uint32_t *)(host_small + 1))[threadIdx.x] = flags[threadIdx.x];
   __threadfence_system();
 }
@@ -1067,8 +1068,11 @@ int launch_sizes_scan(const DevIndex &ix, const BatchDev &b, const WorkDev &w, c
   if (!b.n_reads) return 0;
   k_sizes<<<sm_count() * 16, 128, 0, st>>>(ix, b, w, p);
   // rec_off = exclusive scan of rec_bytes over the (device-side) record count; total -> sam_total[0]
-  return 1 + exclusive_scan_u32_devn(w.rec_bytes, w.slots_total, w.rec_base + b.n_reads, w.blk_sums2, w.rec_off,
-                                     w.sam_total, st);
+  int n = 1 + exclusive_scan_u32_devn(w.rec_bytes, w.slots_total, w.rec_base + b.n_reads, w.blk_sums2, w.rec_off,
+                                      w.sam_total, st);
+  if (w.cmp_bytes)                                             // compact transport: the same for the compact text
+    n += exclusive_scan_u32_devn(w.cmp_bytes, w.slots_total, w.rec_base + b.n_reads, w.blk_sums2, w.cmp_off, w.sam_total + 1, st);
+  return n;
 }
 
 // ------------------------------------------------------------------ K4b: emit
@@ -1114,6 +1118,37 @@ k_emit_text(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp, uint64_t n_reco
       ts.ch('\n');
       ts.finish();
     }
+  }
+}
+
+// Compact transport (compact.h): the same formatting, but head, tags and L/R tags of a record form ONE contiguous run
+// in the range's compact text, followed by the newline; the bytes the caller already has (name, SEQ, QUAL, optional
+// fields) are not written at all -- the host puts the line together (expand.cpp) -- so k_emit_copy is not launched.
+__global__ void __launch_bounds__(128, SMASH_TEXT_MINBLK)
+k_emit_compact(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp, uint64_t n_records) {
+  for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_records; f += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t read = w.rec_read[f];
+    const int hi = (int)(f - w.rec_base[read]);
+    const ReadSum me = w.sums[read];
+    uint16_t flag; MateView mv;
+    read_mate(b, w, read, &flag, &mv);
+    const Item *items = w.item_slots + slot_base(w, read);
+    const Rec *recs = w.rec_slots + slot_base(w, read);
+    const uint64_t co = w.cmp_off[f];
+    WordSink s(w.cmp + co);
+    put_head(s, ix, (const char *)nullptr, 0, flag, me.unmapped, recs[hi], hi, items, mv);
+    const uint32_t head_len = s.n;
+    put_tags(s, ix, me.unmapped, recs, hi, me.n_rec, items);
+    const uint32_t tags_len = s.n - head_len;
+    if (sp.tag_mappability && !me.unmapped) put_lr_tags(s, ix, recs[hi], items);
+    s.ch('\n');
+    s.finish();
+    const uint32_t lr_len = s.n - head_len - tags_len;
+    const bool rc = recs[hi].rc && !me.unmapped;
+    uint4 *m = reinterpret_cast<uint4 *>(w.cmeta + f);
+    const uint64_t so = w.sam_base + w.rec_off[f];
+    m[0] = make_uint4((uint32_t)so, (uint32_t)(so >> 32), (uint32_t)co, (uint32_t)read);
+    m[1] = make_uint4(head_len, tags_len, lr_len | (rc ? 0x80000000u : 0u), 0u);
   }
 }
 
@@ -1279,6 +1314,12 @@ int launch_emit_text(const DevIndex &ix, const BatchDev &b, const WorkDev &w, co
   if (!b.n_reads || !n_records) return 0;
   const uint64_t need = (n_records + 127) / 128, cap = (uint64_t)sm_count() * 16;
   k_emit_text<<<(unsigned)(need < cap ? need : cap), 128, 0, st>>>(ix, b, w, p, n_records);
+  return 1;
+}
+int launch_emit_compact(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st, uint64_t n_records) {
+  if (!b.n_reads || !n_records) return 0;
+  const uint64_t need = (n_records + 127) / 128, cap = (uint64_t)sm_count() * 16;
+  k_emit_compact<<<(unsigned)(need < cap ? need : cap), 128, 0, st>>>(ix, b, w, p, n_records);
   return 1;
 }
 int launch_emit_copy(const BatchDev &b, const WorkDev &w, cudaStream_t st, uint64_t n_records) {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include "core.cuh"
 #include "records.cuh"
+#include "compact.h"
 
 namespace smash {
 
@@ -47,6 +48,12 @@ struct WorkDev {
   uint8_t *lc;                 // lower-cased reads with the 16-byte pads of the staging buffer: read r at seq_off[r] + 32 r + 16
   // K5 record_sort (OutputSorter::flush, query.cpp:448-468): sort keys and permutation of the batch's flat records
   uint64_t *sort_abs; uint8_t *sort_flag; uint32_t *sort_perm; uint32_t *sort_bytes; uint64_t *sort_off; void *sort_tmp; size_t sort_tmp_bytes;
+  // compact transport (compact.h): null => the full SAM text is written on the device (k_emit_text + k_emit_copy)
+  uint32_t *cmp_bytes;         // per flat record: head + tags + lr-tags + newline
+  uint64_t *cmp_off;           // per flat record (+1): exclusive scan of cmp_bytes = offset in `cmp`; total -> sam_total[1]
+  char *cmp;                   // compact text of the range
+  CmpMeta *cmeta;              // per flat record
+  uint64_t sam_base;           // offset of the range's first line in the batch's SAM text (added to rec_off in CmpMeta)
   uint8_t *long_scratch;       // per-warp staging for reads longer than MAXQ_FAST (null if the batch has none)
   int long_q;                  // longest read of the batch
 };
@@ -82,9 +89,12 @@ int launch_mem_write(const DevIndex &ix, const BatchDev &b, const SearchParams &
 // slot_off = exclusive scan of (match_cnt + 1): one spare slot per read for the unmapped placeholder
 int launch_slot_offsets(const uint32_t *match_cnt, uint64_t n_reads, uint32_t *tmp, uint64_t *blk, uint64_t *slot_off, cudaStream_t st);
 int launch_records(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
+// host_small: [0] SAM bytes, [1..4] flags, [8] records, [9] compact bytes (sam_total[1])
 int launch_publish(uint64_t *host_small, const uint64_t *sam_total, const uint64_t *rec_total, const uint32_t *flags, cudaStream_t st);
 int launch_sizes_scan(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
 int launch_emit_text(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st, uint64_t n_records);
+// compact transport: head | tags | lr-tags \n of every record + its CmpMeta (no name / SEQ / QUAL bytes are written)
+int launch_emit_compact(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st, uint64_t n_records);
 int launch_emit_copy(const BatchDev &b, const WorkDev &w, cudaStream_t st, uint64_t n_records);
 // K5: rec_off re-derived so that the emit kernels write the records in MemSam::operator< order (memsam.h:136-158);
 // n_records is the host-known record count.  tmp_bytes_needed != null: only report the sort's scratch size.

@@ -86,7 +86,7 @@ def build(force=False, sanitize=False):
     shared or global memory without the __syncwarp / __syncthreads / atomic the GPU needs show up as data races."""
     tag = "" if not sanitize else ("_tsan" if sanitize == "thread" else "_san")
     so = SO.replace(".so", tag + ".so")
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".cpp"))]
     deps += [os.path.join(HERE, "cuda_shim", "cuda_runtime.h"), os.path.abspath(__file__), os.path.join(ROOT, "include", "smash_b200.h")]
     if not force and os.path.exists(so) and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps):
         return so
@@ -100,6 +100,9 @@ def build(force=False, sanitize=False):
         out = os.path.join(GEN, f.replace(".cu", "_shim.cpp"))
         open(out, "w").write(rewrite(open(os.path.join(CSRC, f)).read()))
         srcs.append(out)
+    for f in ("compact.h", "expand.h", "expand.cpp"):                # plain host C++: compiled as it is
+        open(os.path.join(GEN, f), "w").write(open(os.path.join(CSRC, f)).read())
+    srcs.append(os.path.join(GEN, "expand.cpp"))
     stub = os.path.join(GEN, "sabuild_stub.cpp")
     open(stub, "w").write(STUB)
     srcs.append(stub)
