@@ -258,16 +258,20 @@ int smash_tail_reset(smash_ctx *ctx);
  * tail between library-owned device memory and its own (e.g. torch) tensors. */
 int smash_memcpy(void *dst, const void *src, size_t bytes);
 
-/* smash_submit cuts a batch into up to `max_chunks` (1..4) read ranges that flow through separate
+/* smash_submit cuts a batch into up to `max_chunks` (1..8) read ranges that flow through separate
  * upload / kernel / download streams, so the SAM text of the first range crosses PCIe while later
- * ranges are still searched; batches under `min_reads` reads go through whole.  Defaults 4 / 65536.
+ * ranges are still searched; ranges hold at least `min_reads` reads (smaller batches go through whole).
+ * `max_chunks` 1..8; defaults 8 / 65536.
  * The output is byte-identical either way (MEM mode and SMASH_WANT_MATCHES always go through whole). */
 int smash_ctx_set_chunking(smash_ctx *ctx, int max_chunks, uint64_t min_reads);
 
-/* full_sam_text != 0: smash_submit downloads the whole SAM text instead of using the compact transport (A/B runs,
- * tests).  host_threads: size of the context's line-building pool (0 = one per available core, at most 16; the
- * reference's -qthreads).  Not while batches are in flight. */
-int smash_ctx_set_transport(smash_ctx *ctx, int full_sam_text, int host_threads);
+/* transport 0 (default): each read range of a batch travels whichever way gets its lines into host memory first --
+ * whole text over the download stream, or compact + host threads -- from the measured rate and the backlog of both
+ * (PCIe-bound hosts use both at once, hosts short of cores or memory bandwidth fall back to the download stream);
+ * 1: always the whole SAM text (A/B runs, tests); 2: always compact.  host_threads: size of the context's
+ * line-building pool (0 = one per available core, at most 16; the reference's -qthreads).  Not while batches are in
+ * flight.  The output bytes are the same in every case. */
+int smash_ctx_set_transport(smash_ctx *ctx, int transport, int host_threads);
 /* Bytes copied host->device / device->host by smash_submit* / smash_batch_upload / smash_map_* since the last reset,
  * counted from the copies the library enqueues. */
 void smash_ctx_io_bytes(smash_ctx *ctx, uint64_t *h2d, uint64_t *d2h, int reset);

@@ -461,9 +461,12 @@ class Context:
         """smash_ctx_set_chunking: how smash_submit pipelines one batch (output is identical either way)."""
         _check(load_library().smash_ctx_set_chunking(self.h, int(max_chunks), C.c_uint64(int(min_reads))))
 
-    def set_transport(self, full_sam_text=False, host_threads=0):
-        """smash_ctx_set_transport: whole SAM text over PCIe (A/B, tests) or the compact transport + host line building."""
-        _check(load_library().smash_ctx_set_transport(self.h, int(bool(full_sam_text)), int(host_threads)))
+    def set_transport(self, full_sam_text=False, host_threads=0, compact_only=False, mode=None):
+        """smash_ctx_set_transport: 0 = per read range whichever way is faster (default), 1 = whole SAM text over PCIe,
+        2 = compact transport + host line building only."""
+        if mode is None:
+            mode = 2 if compact_only else int(bool(full_sam_text))
+        _check(load_library().smash_ctx_set_transport(self.h, int(mode), int(host_threads)))     # mode 3 (tests): ranges alternate
 
     def io_bytes(self, reset=False):
         """(h2d, d2h) bytes the library copied since the last reset."""

@@ -225,7 +225,7 @@ template <class T> struct HBuf {        // growable pinned host buffer
 // A submitted batch is cut into up to MAX_CHUNKS read ranges that flow through three streams of the
 // slot (upload -> kernels -> download), so that the SAM text of the first range is already crossing
 // PCIe while the later ranges are still being searched.
-constexpr int MAX_CHUNKS = 4;
+constexpr int MAX_CHUNKS = 8;
 constexpr uint64_t CHUNK_MIN_READS = 65536;
 constexpr int N_EVS = 10 * MAX_CHUNKS;
 
@@ -279,7 +279,9 @@ struct Slot {
   HBuf<char> h_cmp[MAX_CHUNKS]; HBuf<CmpMeta> h_cmeta[MAX_CHUNKS];
   cudaEvent_t ev_d2h[MAX_CHUNKS] = {};
   uint64_t cmp_recs[MAX_CHUNKS] = {}; int n_ranges = 0, n_dispatched = 0;
+  smash_ctx *ctx = nullptr;
   std::atomic<int> pending{0};                                     // expansion tasks not finished yet
+  std::atomic<uint64_t> expand_ns{0};                              // SMASH_DEBUG_TIMING: summed task time of the batch
   // the slot's host worker: H2D enqueue, the per-range launches (with their size read-backs) and the expansion run
   // here, so smash_submit returns at once and two slots never serialise on each other's host synchronisations
   std::thread worker; std::mutex mu; std::condition_variable cv;
@@ -311,9 +313,12 @@ struct smash_ctx {
   smash_index *own_index = nullptr;
   uint64_t index_bytes = 0;
   uint64_t launches = 0, io_h2d = 0, io_d2h = 0;
-  int transport = 0;                                // 0: compact when the batch came from host buffers, 1: full SAM text over PCIe
+  int transport = 0;                                // 0: per read range, whichever is faster; 1: full SAM text over PCIe; 2: compact only
   int host_threads = 0;                             // expansion threads (0 = auto)
   HostPool pool;
+  // transport scheduler: when the download stream and the line-building threads are expected to be free [host clock, ms],
+  // the measured rate of each; a read range takes whichever way gets its lines into host memory first
+  std::mutex sched_mu; double dma_free_at = 0, cpu_free_at = 0, dma_bytes_per_ms = 45e6, cpu_ns_per_rec = 100.0; bool dma_calibrated = false;
   std::mutex turn_mu; std::condition_variable turn_cv; uint64_t next_seq = 0, tail_turn = 0;
   double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // search, records, sizes+scan, emit_text, csr, tail, emit_copy, verify
   double ingest_ms = 0;                            // device-side input stage (smash_submit_text / smash_text_upload)
@@ -632,6 +637,8 @@ extern "C" int smash_ctx_save_index(smash_ctx *c, const char *ref_fasta, int wit
 
 // ------------------------------------------------------------------ host threads: expansion pool, tail turn
 
+static void sched_note_task(smash_ctx *c, double ns_per_rec);
+static void sched_calibrate_dma(smash_ctx *c, cudaStream_t st);
 static void expand_task_run(const ExpandTask &t) {
   Slot &s = *t.s;
   ExpandArgs a{};
@@ -639,7 +646,11 @@ static void expand_task_run(const ExpandTask &t) {
   a.opt = s.opt_bytes ? s.hb.opt : nullptr; a.opt_off = s.opt_bytes ? s.hb.opt_off : nullptr;
   a.read_base = s.chunk_r[t.ch];
   a.meta = s.h_cmeta[t.ch].p; a.cmp = s.h_cmp[t.ch].p; a.sam = s.h_sam.p;
+  const double te = now_ms();
   expand_records(a, t.f0, t.f1);
+  const double dt_ns = (now_ms() - te) * 1e6;
+  if (g_dbg) s.expand_ns.fetch_add((uint64_t)dt_ns);
+  if (s.ctx && t.f1 > t.f0) sched_note_task(s.ctx, dt_ns / (double)(t.f1 - t.f0));
   if (s.pending.fetch_sub(1) == 1) { std::lock_guard<std::mutex> lk(s.mu); s.cv.notify_all(); }
 }
 static bool pool_try_run_one(HostPool &p) {
@@ -672,12 +683,57 @@ static int host_cpu_count() {
 }
 static void pool_start(smash_ctx *c) {
 #if !defined(SMASH_CUDA_SHIM)
+  if (c->transport == 0) sched_calibrate_dma(c, c->slot[0].st_out);
   if (!c->pool.th.empty()) return;
   int n = c->host_threads;
   if (n <= 0) { if (const char *e = getenv("SMASH_HOST_THREADS")) n = atoi(e); }
   if (n <= 0) { n = host_cpu_count(); if (n > 16) n = 16; }
   for (int i = 0; i < n; ++i) c->pool.th.emplace_back(pool_main, &c->pool);
 #endif
+}
+
+// ---- which way a read range's lines travel (SMASH transport, include/smash_b200.h)
+static void sched_note_task(smash_ctx *c, double ns_per_rec) {
+  std::lock_guard<std::mutex> lk(c->sched_mu);
+  c->cpu_ns_per_rec += 0.05 * (ns_per_rec - c->cpu_ns_per_rec);      // under memory contention tasks stretch and the rate follows
+}
+static void sched_calibrate_dma(smash_ctx *c, cudaStream_t st) {
+  if (c->dma_calibrated) return;
+  c->dma_calibrated = true;
+  const size_t n = 32u << 20;
+  void *d = nullptr, *h = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (cudaMalloc(&d, n) == cudaSuccess && cudaHostAlloc(&h, n, cudaHostAllocDefault) == cudaSuccess &&
+      cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) {
+    cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(e0, st);
+    cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st);
+    cudaEventRecord(e1, st);
+    float ms = 0;
+    if (cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess && ms > 0)
+      c->dma_bytes_per_ms = 0.9 * (double)n / ms;             // (uploads share the link's host side)
+  }
+  cudaGetLastError();
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (h) cudaFreeHost(h);
+  if (d) cudaFree(d);
+  if (g_dbg) fprintf(stderr, "[smash-dbg] download rate %.1f GB/s\n", c->dma_bytes_per_ms / 1e6);
+}
+// true: compact transport for this range.  Both engines are modelled as queues: the download stream moves
+// dma_bytes_per_ms, the pool builds a record in cpu_ns_per_rec per thread.
+static bool sched_choose_compact(smash_ctx *c, uint64_t sam_bytes, uint64_t cmp_bytes, uint64_t recs, int ch) {
+  if (c->transport == 2) return true;
+  if (c->transport == 3) return (ch & 1) != 0;                 // tests: both ways inside one batch
+  std::lock_guard<std::mutex> lk(c->sched_mu);
+  const double now = now_ms();
+  const double dma0 = c->dma_free_at > now ? c->dma_free_at : now, cpu0 = c->cpu_free_at > now ? c->cpu_free_at : now;
+  const double t_full = dma0 + (double)sam_bytes / c->dma_bytes_per_ms;
+  const double dma_c = dma0 + (double)(cmp_bytes + recs * sizeof(CmpMeta)) / c->dma_bytes_per_ms;
+  const double threads = (double)(c->pool.th.size() + 1);
+  const double t_cmp = (dma_c > cpu0 ? dma_c : cpu0) + (double)recs * c->cpu_ns_per_rec / 1e6 / threads;
+  if (t_cmp <= t_full) { c->dma_free_at = dma_c; c->cpu_free_at = t_cmp; return true; }
+  c->dma_free_at = t_full;
+  return false;
 }
 constexpr uint64_t EXPAND_GRAIN = 4096;                      // records per task
 static void expand_dispatch(smash_ctx *c, Slot &s, int ch) {
@@ -864,7 +920,11 @@ static int slot_reserve(smash_ctx *c, Slot &s, uint64_t n, size_t name_bytes, si
   if (s.compact && ((rc = s.cmp_bytes.ensure(n * s.cap + 1)) || (rc = s.cmp_off.ensure(n * s.cap + 2)))) return rc;
   DBG_T("  prepare:ensure", t_prep);
   // read ranges of the chunked pipeline (even boundaries: mates stay together)
-  s.n_chunks = (chunks > 1 && n >= c->chunk_min_reads) ? (chunks > MAX_CHUNKS ? MAX_CHUNKS : chunks) : 1;
+  {
+    const uint64_t by_size = c->chunk_min_reads ? n / c->chunk_min_reads : n;      // ranges of at least chunk_min_reads reads
+    const int lim = chunks > MAX_CHUNKS ? MAX_CHUNKS : chunks;
+    s.n_chunks = (chunks > 1 && by_size >= 1) ? (int)(by_size < (uint64_t)lim ? (by_size > 1 ? by_size : 1) : (uint64_t)lim) : 1;
+  }
   {
     const uint64_t per = ((n + s.n_chunks - 1) / s.n_chunks + 1) & ~1ull;
     for (int ch = 0; ch <= s.n_chunks; ++ch) { const uint64_t r = per * ch; s.chunk_r[ch] = r < n ? r : n; }
@@ -1025,7 +1085,9 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
     break;
   }
   const uint64_t bytes = s.h_small.p[0], recs = s.h_small.p[8];
-  if ((want & SMASH_WANT_SAM) && s.compact) {
+  const bool range_compact = (want & SMASH_WANT_SAM) && s.compact && sched_choose_compact(c, bytes, s.h_small.p[9], recs, ch);
+  if (g_dbg && s.compact) fprintf(stderr, "[smash-dbg]   range %d of slot %d: %s\n", ch, (int)(&s - c->slot), range_compact ? "compact" : "full text");
+  if (range_compact) {
     // compact transport: only the text the GPU computes + one CmpMeta per record cross PCIe (compact.h)
     int rc;
     const uint64_t cbytes = s.h_small.p[9];
@@ -1037,6 +1099,7 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
     const uint64_t guess = (chunked && ch == 0 && n) ? (uint64_t)((double)bytes * ((double)n_full / (double)n) * 1.03) + 4096 : 0;
     if (need > s.h_sam.cap) {
       expand_drain(c, s);                                     // lines of earlier ranges are being written into the old buffer
+      if (s.sam_base) CU(cudaStreamSynchronize(s.st_out));
       if ((rc = s.h_sam.grow_keep(need > guess ? need : guess, s.sam_base))) return rc;
     }
     if ((want & SMASH_WANT_SORTED) && recs) {
@@ -1100,6 +1163,7 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
     if (to_host) {
       if (need > s.h_sam.cap) {
         if (s.sam_base) CU(cudaStreamSynchronize(s.st_out));
+        if (s.compact) expand_drain(c, s);
         if ((rc = s.h_sam.grow_keep(need > guess ? need : guess, s.sam_base))) return rc;
       }
       cudaStream_t out = s.st;
@@ -1111,6 +1175,7 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
       if (g_dbg && s.tl[1] && ch == 0) cudaEventRecord(s.tl[1], out);
       CU(cudaMemcpyAsync(s.h_sam.p + s.sam_base, s.sam.p + s.sam_base, bytes, cudaMemcpyDeviceToHost, out));
       s.io_d2h += bytes;
+      if (s.compact) { CU(cudaEventRecord(s.ev_d2h[ch], out)); s.cmp_recs[ch] = 0; s.n_ranges = ch + 1; }
       if (g_dbg && s.tl[2] && ch == s.n_chunks - 1) cudaEventRecord(s.tl[2], out);
     }
   }
@@ -1417,13 +1482,20 @@ extern "C" int smash_fetch_batch(smash_ctx *c, int slot, uint8_t *names, int64_t
 // the emit kernels), the tail appends in submission order, and -- compact transport -- the expansion into SAM lines.
 static int run_job(smash_ctx *c, Slot &s) {
   int rc = 0;
+  const double t0 = now_ms();
+  s.expand_ns = 0;
   if (s.job_prepare) rc = slot_prepare(c, s, &s.hb, true, s.job_chunks);
+  const double t1 = now_ms();
   if (!rc) rc = slot_run(c, s, s.job_want, true);
+  const double t2 = now_ms();
   tail_turn_release(c, s);                                   // the next batch may append now
   if (s.compact) {
     if (!rc) rc = expand_poll(c, s, true);
+    const double t3 = now_ms();
     expand_drain(c, s);                                      // also on errors: tasks reference the slot's buffers
-  }
+    if (g_dbg) fprintf(stderr, "[smash-dbg] job slot %d @%.2f: prepare %.2f  run %.2f  d2h-wait %.2f  drain %.2f  (task time %.2f ms over %zu threads)\n",
+                       (int)(&s - c->slot), t0, t1 - t0, t2 - t1, t3 - t2, now_ms() - t3, (double)s.expand_ns.load() / 1e6, c->pool.th.size());
+  } else if (g_dbg) fprintf(stderr, "[smash-dbg] job slot %d @%.2f: prepare %.2f  run %.2f\n", (int)(&s - c->slot), t0, t1 - t0, t2 - t1);
   return rc;
 }
 static void slot_worker_main(smash_ctx *c, Slot *sp) {
@@ -1473,7 +1545,8 @@ extern "C" int smash_submit(smash_ctx *c, int slot, const smash_batch *b, int wa
   s.job_chunks = (c->prm.mode != SMASH_MODE_MEM && !(want & (SMASH_WANT_MATCHES | SMASH_WANT_SORTED)) && (want & SMASH_WANT_SAM) && !g_no_chunks) ? c->max_chunks : 1;
   s.hb = *b; s.job_prepare = true; s.job_want = want;
   // the caller's batch stays valid until smash_wait, so the lines can be rebuilt from it on the host: compact transport
-  s.compact = (want & SMASH_WANT_SAM) && !g_full_sam && c->transport == 0;
+  s.compact = (want & SMASH_WANT_SAM) && !g_full_sam && c->transport != 1;
+  s.ctx = c;
   return job_start(c, s);
 }
 extern "C" int smash_wait(smash_ctx *c, int slot, smash_result *res) {
@@ -1683,7 +1756,8 @@ extern "C" int smash_ctx_set_chunking(smash_ctx *c, int max_chunks, uint64_t min
 extern "C" int smash_ctx_set_transport(smash_ctx *c, int full_sam_text, int host_threads) {
   if (!c) return fail(SMASH_ERR_ARG, "null argument");
   for (int i = 0; i < SMASH_N_SLOTS; ++i) if (c->slot[i].busy) return fail(SMASH_ERR_STATE, "slot %d has a batch in flight", i);
-  c->transport = full_sam_text ? 1 : 0;
+  if (full_sam_text < 0 || full_sam_text > 3) return fail(SMASH_ERR_ARG, "transport %d: 0 = per range whichever is faster, 1 = full SAM text, 2 = compact only", full_sam_text);
+  c->transport = full_sam_text;
   if (host_threads != c->host_threads && !c->pool.th.empty()) {       // restart the expansion pool with the new size
     { std::lock_guard<std::mutex> lk(c->pool.mu); c->pool.quit = true; }
     c->pool.cv.notify_all();

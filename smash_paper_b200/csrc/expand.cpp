@@ -3,6 +3,7 @@
 // byte reversal + two 16-entry table look-ups per 32 bytes (AVX2), with a scalar twin for CPUs without it.
 #include "expand.h"
 
+#include <stdlib.h>
 #include <string.h>
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -48,10 +49,13 @@ static void reverse_bytes_scalar(char *dst, const uint8_t *src, size_t n) {
 }
 
 #if defined(__x86_64__)
+struct CompTables {
+  alignas(32) uint8_t lo[32], hi[32];
+  CompTables() { for (int i = 0; i < 16; ++i) { lo[i] = lo[i + 16] = comp5((uint8_t)i); hi[i] = hi[i + 16] = comp5((uint8_t)(16 + i)); } }
+};
+static const CompTables g_comp;
 __attribute__((target("avx2"))) static void reverse_complement_avx2(char *dst, const uint8_t *src, size_t n) {
-  alignas(32) uint8_t tlo[32], thi[32];
-  for (int i = 0; i < 16; ++i) { tlo[i] = tlo[i + 16] = comp5((uint8_t)i); thi[i] = thi[i + 16] = comp5((uint8_t)(16 + i)); }
-  const __m256i TL = _mm256_load_si256((const __m256i *)tlo), TH = _mm256_load_si256((const __m256i *)thi);
+  const __m256i TL = _mm256_load_si256((const __m256i *)g_comp.lo), TH = _mm256_load_si256((const __m256i *)g_comp.hi);
   const __m256i REV = _mm256_setr_epi8(15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 1, 0);
   const __m256i M0F = _mm256_set1_epi8(0x0F), M10 = _mm256_set1_epi8(0x10), ME0 = _mm256_set1_epi8((char)0xE0),
                 MC0 = _mm256_set1_epi8((char)0xC0), M40 = _mm256_set1_epi8(0x40);
@@ -99,36 +103,148 @@ void reverse_bytes(char *dst, const uint8_t *src, size_t n) {
   reverse_bytes_scalar(dst, src, n);
 }
 
-void expand_records(const ExpandArgs &a, uint64_t f0, uint64_t f1) {
+// One record's line at d (scalar / SSE moves); returns the line's length.
+static inline size_t put_line(const ExpandArgs &a, const CmpMeta &m, char *d0) {
+  char *d = d0;
+  const uint64_t read = a.read_base + m.read;
+  const char *c = a.cmp + m.cmp_off;
+  const int64_t no = a.name_off[read];
+  const size_t nl = (size_t)(a.name_off[read + 1] - no);
+  copy_bytes(d, a.names + no, nl); d += nl;
+  copy_bytes(d, c, m.head_len); d += m.head_len; c += m.head_len;
+  const int64_t so = a.seq_off[read];
+  const size_t q = (size_t)(a.seq_off[read + 1] - so);
+  if (m.lr_len & 0x80000000u) {
+    reverse_complement(d, a.seq + so, q);
+    d[q] = '\t';
+    reverse_bytes(d + q + 1, a.qual + so, q);
+  } else {
+    copy_bytes(d, a.seq + so, q);
+    d[q] = '\t';
+    copy_bytes(d + q + 1, a.qual + so, q);
+  }
+  d += 2 * q + 1;
+  copy_bytes(d, c, m.tags_len); d += m.tags_len; c += m.tags_len;
+  if (a.opt) {
+    const int64_t oo = a.opt_off[read];
+    const size_t ol = (size_t)(a.opt_off[read + 1] - oo);
+    copy_bytes(d, a.opt + oo, ol); d += ol;
+  }
+  const size_t ll = m.lr_len & 0x7fffffffu;
+  copy_bytes(d, c, ll); d += ll;
+  return (size_t)(d - d0);
+}
+static inline size_t line_len(const ExpandArgs &a, const CmpMeta &m) {
+  const uint64_t read = a.read_base + m.read;
+  size_t n = (size_t)(a.name_off[read + 1] - a.name_off[read]) + m.head_len + 2 * (size_t)(a.seq_off[read + 1] - a.seq_off[read]) + 1 +
+             m.tags_len + (m.lr_len & 0x7fffffffu);
+  if (a.opt) n += (size_t)(a.opt_off[read + 1] - a.opt_off[read]);
+  return n;
+}
+
+#if defined(__x86_64__)
+// the same with 32-byte moves (the staging buffer has slack after the line, the sources are read with an overlapping tail)
+__attribute__((target("avx2"))) static inline void copy32(char *d, const void *s_, size_t n) {
+  const char *s = (const char *)s_;
+  if (n >= 32) {
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) _mm256_storeu_si256((__m256i *)(d + i), _mm256_loadu_si256((const __m256i *)(s + i)));
+    if (i < n) _mm256_storeu_si256((__m256i *)(d + n - 32), _mm256_loadu_si256((const __m256i *)(s + n - 32)));
+    return;
+  }
+  copy_bytes(d, s, n);
+}
+__attribute__((target("avx2"))) static inline size_t put_line_avx2(const ExpandArgs &a, const CmpMeta &m, char *d0) {
+  char *d = d0;
+  const uint64_t read = a.read_base + m.read;
+  const char *c = a.cmp + m.cmp_off;
+  const int64_t no = a.name_off[read];
+  const size_t nl = (size_t)(a.name_off[read + 1] - no);
+  copy32(d, a.names + no, nl); d += nl;
+  copy32(d, c, m.head_len); d += m.head_len; c += m.head_len;
+  const int64_t so = a.seq_off[read];
+  const size_t q = (size_t)(a.seq_off[read + 1] - so);
+  if (m.lr_len & 0x80000000u) {
+    reverse_complement_avx2(d, a.seq + so, q);
+    d[q] = '\t';
+    reverse_bytes_avx2(d + q + 1, a.qual + so, q);
+  } else {
+    copy32(d, a.seq + so, q);
+    d[q] = '\t';
+    copy32(d + q + 1, a.qual + so, q);
+  }
+  d += 2 * q + 1;
+  copy32(d, c, m.tags_len); d += m.tags_len; c += m.tags_len;
+  if (a.opt) {
+    const int64_t oo = a.opt_off[read];
+    const size_t ol = (size_t)(a.opt_off[read + 1] - oo);
+    copy32(d, a.opt + oo, ol); d += ol;
+  }
+  const size_t ll = m.lr_len & 0x7fffffffu;
+  copy32(d, c, ll); d += ll;
+  return (size_t)(d - d0);
+}
+
+// Lines of consecutive records are consecutive in the SAM text (input order), so a task's output is one long run.
+// The run is assembled in a cache-resident staging buffer and leaves as aligned 64-byte NON-TEMPORAL stores: the
+// destination lines are never read into the cache first (no read-for-ownership), which is what bounds a plain copy
+// when every core of the host writes at once.  Bytes before the first / after the last full cache line of a run (lines
+// shared with a neighbouring task) are written with ordinary stores.
+struct alignas(64) StreamWriter {
+  static constexpr size_t STAGE = 16384, MAX_LINE = 8192;
+  char buf[STAGE + MAX_LINE + 64];
+  char *dst = nullptr;                                       // destination of buf[fill]
+  size_t fill = 0;
+};
+__attribute__((target("avx2"))) static void sw_flush(StreamWriter &w, bool all) {
+  char *base = w.dst - w.fill;                               // destination of buf[0]
+  size_t done = 0;
+  if (w.fill >= 128) {
+    const size_t head = (64 - ((uintptr_t)base & 63)) & 63;
+    memcpy(base, w.buf, head);
+    const size_t n64 = (w.fill - head) / 64;
+    const char *src = w.buf + head;
+    char *d = base + head;
+    for (size_t i = 0; i < n64; ++i) {
+      const __m256i x = _mm256_loadu_si256((const __m256i *)(src + 64 * i)), y = _mm256_loadu_si256((const __m256i *)(src + 64 * i + 32));
+      _mm256_stream_si256((__m256i *)(d + 64 * i), x);
+      _mm256_stream_si256((__m256i *)(d + 64 * i + 32), y);
+    }
+    done = head + 64 * n64;
+  }
+  const size_t rest = w.fill - done;
+  if (all) { memcpy(base + done, w.buf + done, rest); w.fill = 0; }
+  else { memmove(w.buf, w.buf + done, rest); w.fill = rest; }
+}
+__attribute__((target("avx2"))) static void expand_records_stream(const ExpandArgs &a, uint64_t f0, uint64_t f1) {
+  StreamWriter w;
   for (uint64_t f = f0; f < f1; ++f) {
     const CmpMeta m = a.meta[f];
-    const uint64_t read = a.read_base + m.read;
     char *d = a.sam + m.sam_off;
-    const char *c = a.cmp + m.cmp_off;
-    const int64_t no = a.name_off[read];
-    const size_t nl = (size_t)(a.name_off[read + 1] - no);
-    copy_bytes(d, a.names + no, nl); d += nl;
-    copy_bytes(d, c, m.head_len); d += m.head_len; c += m.head_len;
-    const int64_t so = a.seq_off[read];
-    const size_t q = (size_t)(a.seq_off[read + 1] - so);
-    if (m.lr_len & 0x80000000u) {
-      reverse_complement(d, a.seq + so, q);
-      d[q] = '\t';
-      reverse_bytes(d + q + 1, a.qual + so, q);
-    } else {
-      copy_bytes(d, a.seq + so, q);
-      d[q] = '\t';
-      copy_bytes(d + q + 1, a.qual + so, q);
+    if (d != w.dst) {                                        // a new run (first record of the task, sorted output)
+      if (w.fill) sw_flush(w, true);
+      w.dst = d;
     }
-    d += 2 * q + 1;
-    copy_bytes(d, c, m.tags_len); d += m.tags_len; c += m.tags_len;
-    if (a.opt) {
-      const int64_t oo = a.opt_off[read];
-      const size_t ol = (size_t)(a.opt_off[read + 1] - oo);
-      copy_bytes(d, a.opt + oo, ol); d += ol;
+    if (line_len(a, m) > StreamWriter::MAX_LINE) {           // oversized line (long read): straight to its place
+      if (w.fill) sw_flush(w, true);
+      put_line(a, m, d); w.dst = nullptr;
+      continue;
     }
-    copy_bytes(d, c, m.lr_len & 0x7fffffffu);
+    const size_t n = put_line_avx2(a, m, w.buf + w.fill);
+    w.fill += n; w.dst += n;
+    if (w.fill >= StreamWriter::STAGE) sw_flush(w, false);
   }
+  if (w.fill) sw_flush(w, true);
+  _mm_sfence();
+}
+#endif
+
+void expand_records(const ExpandArgs &a, uint64_t f0, uint64_t f1) {
+#if defined(__x86_64__)
+  static const bool no_stream = getenv("SMASH_NO_STREAM_STORES") != nullptr;       // A/B switch
+  if (g_avx2 && !no_stream) { expand_records_stream(a, f0, f1); return; }
+#endif
+  for (uint64_t f = f0; f < f1; ++f) put_line(a, a.meta[f], a.sam + a.meta[f].sam_off);
 }
 
 }  // namespace smash

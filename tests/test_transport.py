@@ -71,6 +71,14 @@ def test_host_expand_rebuilds_the_oracles_lines(case):
     assert rc == 0
     assert out[:len(sam)].tobytes() == sam
     assert not out[len(sam):].any()                              # nothing written past the last line
+    # record ranges expanded separately, in any order (what the library's host threads do): runs share cache lines
+    out2 = np.zeros(len(sam) + 64, dtype=np.uint8)
+    cuts = [0, 1, 7, len(meta) // 3, len(meta) // 3 + 1, 2 * len(meta) // 3, len(meta)]
+    for a, z in reversed(list(zip(cuts, cuts[1:]))):
+        part = meta[a:z]
+        assert api.load_library().smash_host_expand(C.byref(b), C.c_uint64(0), part.ctypes.data_as(C.c_void_p), C.c_uint64(len(part)),
+                                                    cbuf.ctypes.data_as(C.c_char_p), out2.ctypes.data_as(C.c_char_p)) == 0
+    assert out2[:len(sam)].tobytes() == sam and not out2[len(sam):].any()
 
 
 def test_host_reverse_complement_table():
@@ -119,15 +127,18 @@ def test_full_and_compact_transport_agree(case, tagged, chunks):
             sam = b"".join(oracle_tail(case["oix"], case["body"], sam, case["dir"], case["fa"])["tagged"])
         ctx.set_chunking(chunks, 2)
         got = {}
-        for full in (False, True):
-            ctx.set_transport(full_sam_text=full, host_threads=3)
+        for mode in (0, 1, 2, 3):                                  # scheduler's choice, full text, compact, ranges alternating
+            ctx.set_transport(mode=mode, host_threads=3)
             ctx.io_bytes(reset=True)
             for rep in range(2):
                 res = ctx.map_batch(case["reads"])
-                assert res.sam == sam, ("full" if full else "compact", rep)
-            got[full] = ctx.io_bytes(reset=True)
-        assert got[False][0] == got[True][0]                       # same upload
-        assert got[False][1] < 0.62 * got[True][1]                 # ~40 % of the text + 32 B per record come back
+                assert res.sam == sam, (mode, rep)
+            got[mode] = ctx.io_bytes(reset=True)
+        assert got[1][0] == got[2][0] == got[0][0]                 # same upload
+        assert got[2][1] < 0.62 * got[1][1]                        # ~40 % of the text + 32 B per record come back
+        assert got[2][1] <= got[0][1] <= got[1][1]
+        if chunks > 1:
+            assert got[2][1] < got[3][1] < got[1][1]
     finally:
         ctx.close(); ix.close()
 
@@ -152,10 +163,10 @@ def test_compact_transport_output_modes(case, variant):
     try:
         want = api.WANT_SAM | (api.WANT_SORTED if variant == "sorted" else 0) | (api.WANT_MATCHES if variant == "matches" else 0)
         out = []
-        for full in (False, True):
-            ctx.set_transport(full_sam_text=full, host_threads=2)
+        for mode in (2, 1, 0):
+            ctx.set_transport(mode=mode, host_threads=2)
             out.append(ctx.map_batch(reads, want=want).sam)
-        assert out[0] == out[1]
+        assert out[0] == out[1] == out[2]
         exp = oix.map_batch(reads, min_len=20, n_threads=4, mode=O.MEM if variant == "mem" else O.MAM)
         if variant == "sorted":
             key = O.memsam_sort_key(oix.descr[::2], oix.sizes[::2])
@@ -181,6 +192,7 @@ def test_workers_keep_submission_order_in_the_tail(case):
         ci = exp["chrominfo"]
         ctx.tail_configure([int(b[2]) for b in exp["bins"]], list(ci.keys()), [int(v[2]) for v in ci.values()])
         ctx.set_chunking(2, 2)
+        ctx.set_transport(mode=3, host_threads=2)                  # every batch: one range as full text, one compact
         cuts = [0, 400, 402, 1000, 1700, 1702, reads.n]            # uneven batches (even boundaries: mates stay together)
         parts = [samio.slice_batch(reads, a, b) for a, b in zip(cuts, cuts[1:])]
         for rep in range(2):
