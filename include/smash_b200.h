@@ -153,7 +153,7 @@ int smash_map_batch(smash_ctx *ctx, const smash_batch *b, int want, smash_result
  * the library's host threads rebuild the byte-identical lines from the submitted batch ("compact
  * transport", the `-qthreads` workers of the reference become these threads).  smash_submit_text and the
  * device-resident calls always produce the whole text on the device. */
-#define SMASH_N_SLOTS 2
+#define SMASH_N_SLOTS 4
 int smash_submit(smash_ctx *ctx, int slot, const smash_batch *b, int want);
 int smash_wait(smash_ctx *ctx, int slot, smash_result *res);
 

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--reads", type=int, default=1_000_000)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--threads", default="1,2,4,8,16")
+    ap.add_argument("--slots", default="2")
     a = ap.parse_args()
     import bench
     from smash_paper_b200 import api, sequence, synth
@@ -53,14 +54,15 @@ def main():
     ctx.tail_configure(starts, ref.names, ref.offsets())
     genome = ref.concat()
     batches = [bench.pinned_batch(api, synth.make_reads_fast(genome, a.reads // 2, read_len=150, seed=1000, first_pair=i * (a.reads // 2))) for i in range(4)]
+    assert max(int(x) for x in a.slots.split(",")) <= min(api.N_SLOTS, 4)
     want = api.WANT_SAM | api.WANT_TAIL
     ctx.tail_reserve((a.reads // 2) * (a.steps + 6), 8 * a.reads * (a.steps + 6))
     for full, mode in ((True, 1), (False, 2), (False, 0)):
-        for th in ([0] if full else [int(x) for x in a.threads.split(",")]):
+        for th, ns in [(t_, n_) for t_ in ([0] if full else [int(x) for x in a.threads.split(",")]) for n_ in [int(x) for x in a.slots.split(",")]]:
             ctx.set_transport(mode=mode, host_threads=th)
             ctx.tail_reset()
-            for i in range(3):
-                ctx.submit(i % 2, batches[i % 4], want=want); ctx.wait(i % 2, copy=False)
+            for i in range(2 * ns):
+                ctx.submit(i % ns, batches[i % 4], want=want); ctx.wait(i % ns, copy=False)
             print(f"--- mode={mode} threads={th}: isolated batch", file=sys.stderr, flush=True)
             t0 = time.perf_counter()
             ctx.submit(0, batches[0], want=want); r = ctx.wait(0, copy=False)
@@ -69,14 +71,14 @@ def main():
             ctx.io_bytes(reset=True)
             t0 = time.perf_counter()
             for i in range(a.steps):
-                if i >= 2:
-                    ctx.wait(i % 2, copy=False)
-                ctx.submit(i % 2, batches[i % 4], want=want)
-            for i in range(max(0, a.steps - 2), a.steps):
-                ctx.wait(i % 2, copy=False)
+                if i >= ns:
+                    ctx.wait(i % ns, copy=False)
+                ctx.submit(i % ns, batches[i % 4], want=want)
+            for i in range(max(0, a.steps - ns), a.steps):
+                ctx.wait(i % ns, copy=False)
             dt = time.perf_counter() - t0
             h2d, d2h = ctx.io_bytes(reset=True)
-            print(json.dumps({"transport": {0: "auto", 1: "full", 2: "compact"}[mode], "host_threads": th, "isolated_batch_ms": one * 1e3, "pipelined_reads_per_s": a.reads * a.steps / dt,
+            print(json.dumps({"transport": {0: "auto", 1: "full", 2: "compact"}[mode], "host_threads": th, "slots": ns, "isolated_batch_ms": one * 1e3, "pipelined_reads_per_s": a.reads * a.steps / dt,
                               "ms_per_batch": dt / a.steps * 1e3, "d2h_bytes_per_batch": d2h // a.steps, "sam_bytes": int(r.sam_bytes)}), flush=True)
     ctx.close()
 

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SMASH_B200_LIB") or os.path.join(_HERE, "libsmash_b200.so")   # override: kernel A/B builds
 MODE_MUM, MODE_MAM, MODE_MEM = 0, 1, 2
 WANT_SAM, WANT_MATCHES, WANT_TAIL, WANT_SORTED = 1, 2, 4, 8
-N_SLOTS = 2
+N_SLOTS = 4
 
 
 class SmashError(RuntimeError):

@@ -720,18 +720,23 @@ static void sched_calibrate_dma(smash_ctx *c, cudaStream_t st) {
   if (g_dbg) fprintf(stderr, "[smash-dbg] download rate %.1f GB/s\n", c->dma_bytes_per_ms / 1e6);
 }
 // true: compact transport for this range.  Both engines are modelled as queues: the download stream moves
-// dma_bytes_per_ms, the pool builds a record in cpu_ns_per_rec per thread.
+// dma_bytes_per_ms, the pool builds a record in cpu_ns_per_rec per thread.  A compact range keeps the pool busy and
+// takes 60 % less of the download stream, which is what later ranges queue behind: it is chosen as long as the pool
+// would finish it no later than one full-text range after the moment the stream alone would have -- the two queues end
+// up the same length, each engine working at its own measured rate (a host short of cores or of memory bandwidth
+// stretches cpu_ns_per_rec and the ranges go back to the stream).
 static bool sched_choose_compact(smash_ctx *c, uint64_t sam_bytes, uint64_t cmp_bytes, uint64_t recs, int ch) {
   if (c->transport == 2) return true;
   if (c->transport == 3) return (ch & 1) != 0;                 // tests: both ways inside one batch
   std::lock_guard<std::mutex> lk(c->sched_mu);
   const double now = now_ms();
   const double dma0 = c->dma_free_at > now ? c->dma_free_at : now, cpu0 = c->cpu_free_at > now ? c->cpu_free_at : now;
-  const double t_full = dma0 + (double)sam_bytes / c->dma_bytes_per_ms;
+  const double full_cost = (double)sam_bytes / c->dma_bytes_per_ms;
+  const double t_full = dma0 + full_cost;
   const double dma_c = dma0 + (double)(cmp_bytes + recs * sizeof(CmpMeta)) / c->dma_bytes_per_ms;
   const double threads = (double)(c->pool.th.size() + 1);
   const double t_cmp = (dma_c > cpu0 ? dma_c : cpu0) + (double)recs * c->cpu_ns_per_rec / 1e6 / threads;
-  if (t_cmp <= t_full) { c->dma_free_at = dma_c; c->cpu_free_at = t_cmp; return true; }
+  if (t_cmp <= t_full + full_cost) { c->dma_free_at = dma_c; c->cpu_free_at = t_cmp; return true; }
   c->dma_free_at = t_full;
   return false;
 }

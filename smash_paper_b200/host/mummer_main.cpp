@@ -281,7 +281,7 @@ int main(int argc, char **argv) {
     const bool device_reader = o.sam_in && !getenv("SMASH_HOST_READER");   // -samin text is parsed on the GPU (smash_submit_text)
     for (size_t fi = 0; fi < o.inputs.size(); ++fi) {
       if (o.fastq_pair && fi > 0) break;                            // the two inputs are ONE stream of pairs
-      bool in_flight[SMASH_N_SLOTS] = {false, false};
+      bool in_flight[SMASH_N_SLOTS] = {};
       auto drain = [&](int slot) {
         smash_result r; check(smash_wait(ctx, slot, &r));
         in_flight[slot] = false;
