@@ -852,63 +852,94 @@ __device__ __forceinline__ int xe_word_g(const DevIndex &ix, const uint8_t *__re
   return cnt;
 }
 
+// 8 bytes of a lower-cased staged read (w.lc: 16 pad bytes either side) at offset j, unaligned
+__device__ __forceinline__ uint64_t lc8(const uint8_t *__restrict__ P, int j) {
+  const uint8_t *p = P + j;
+  const uint64_t *a = reinterpret_cast<const uint64_t *>(p - ((uintptr_t)p & 7));
+  const unsigned sh = (unsigned)((uintptr_t)p & 7) * 8u;
+  const uint64_t lo = a[0];
+  if (sh == 0) return lo;
+  return (lo >> sh) | (a[1] << (64u - sh));
+}
+__device__ __forceinline__ int zero_bytes(uint64_t d) {      // number of zero bytes of d
+  uint64_t t = (d & 0x7f7f7f7f7f7f7f7fULL) + 0x7f7f7f7f7f7f7f7fULL;
+  t = ~(t | d | 0x7f7f7f7f7f7f7f7fULL);
+  return __popcll(t);
+}
+
+// K3b, flat: 8 lanes per RECORD, four records per warp pass, over the batch's flat record list (rec_read was filled by
+// the rec_base scan).  XE (query.cpp:270-274) = matching characters of the WHOLE read along the record's diagonal:
+// lane t compares the 8-byte words t, t+8, t+16, .. of the lower-cased read copy the search stage left in HBM (its
+// 0xFE/0xFF pads and the zero pads of the text never match anything, so neither end needs a branch) against the text.
+// Then lanes = the record's '=' blocks: L/R of each from map.bin (map_lr), kept in the Item for the size / emit / tail
+// kernels, and the tagger's range check.
 #ifndef SMASH_XE_MINBLK
-#define SMASH_XE_MINBLK 8
+#define SMASH_XE_MINBLK 6
 #endif
 __global__ void __launch_bounds__(THREADS, SMASH_XE_MINBLK)
 k_rec_xe(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int sub = lane >> 3, sl = lane & 7;
+  const unsigned gmask = 0xffu << (8 * sub);
+  const uint64_t n_records = w.rec_base[b.n_reads];
   const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
-  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
-    const int n_rec = (int)w.nrec[read];
-    if (!n_rec) continue;
-    const uint64_t fbase = w.rec_base[read];
-    for (int r = lane; r < n_rec; r += 32) w.rec_read[fbase + r] = (uint32_t)read;
-    if (w.sums[read].unmapped) continue;
-    const int64_t so = b.seq_off[read];
-    const int q = (int)(b.seq_off[read + 1] - so);
-    const uint8_t *seq = b.seq + so;
-    Item *items = w.item_slots + slot_base(w, read);
-    Rec *recs = w.rec_slots + slot_base(w, read);
-    for (int r0 = 0; r0 < n_rec; r0 += 4) {                 // 4 records per pass, 8 lanes each
-      const int r = r0 + sub;
-      int cnt = 0;
-      if (r < n_rec) {
-        const int64_t rcpos = recs[r].rcpos;
+  for (uint64_t f0 = ((uint64_t)blockIdx.x * WARPS + (threadIdx.x >> 5)) * 4; f0 < n_records; f0 += warps_total * 4) {
+    const uint64_t f = f0 + (uint64_t)sub;
+    const bool have = f < n_records;
+    uint64_t read = 0; int r = 0; bool mapped = false;
+    if (have) { read = w.rec_read[f]; r = (int)(f - w.rec_base[read]); mapped = !w.sums[read].unmapped; }
+    int cnt = 0;
+    Rec *rec = nullptr; Item *items = nullptr;
+    int64_t pos = 0; uint32_t si = 0; int item_begin = 0, item_cnt = 0;
+    if (mapped) {
+      const uint64_t sb = slot_base(w, read);
+      rec = w.rec_slots + sb + r; items = w.item_slots + sb;
+      const int64_t rcpos = rec->rcpos;
+      pos = rec->pos; si = rec->si; item_begin = rec->item_begin; item_cnt = rec->item_cnt;
+      const int64_t so = b.seq_off[read];
+      const int q = (int)(b.seq_off[read + 1] - so);
+      if (w.lc && q <= MAXQ_FAST) {
+        const uint8_t *P = w.lc + so + 32 * read + 16;
+        for (int j0 = sl * 8; j0 < q; j0 += 64) {
+          const int64_t rp = rcpos + j0;
+          if (rp >= -(int64_t)(TEXT_PAD - 8) && rp <= (int64_t)ix.N + (TEXT_PAD - 16)) cnt += zero_bytes(text8(ix.text, rp) ^ lc8(P, j0));
+        }
+      } else {
+        const uint8_t *seq = b.seq + so;
         for (int j0 = sl * 8; j0 < q; j0 += 64) cnt += xe_word_g(ix, seq, q, rcpos, j0, sp.nucleotides_only);
       }
-      cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
-      cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
-      cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
-      if (r < n_rec && sl == 0) recs[r].xe = (uint16_t)cnt;
     }
-    if (ix.mapbody) {                                        // L0/R0 + the tagger's range check
-      for (int r = lane; r < n_rec; r += 32) {
-        bool ok = true; int L0 = 0, R0 = 0;
-        const Rec rr = recs[r];
-        for (int u = 0; u < rr.item_cnt; ++u) {
-          const Item it = items[rr.item_begin + u];
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 4);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+    if (mapped && sl == 0) rec->xe = (uint16_t)cnt;
+    if (ix.mapbody) {                                        // L/R of every '=' block + the tagger's range check
+      bool bad = false;
+      if (mapped) {
+        for (int u = sl; u < item_cnt; u += 8) {
+          Item it = items[item_begin + u];
           int L, R;
-          ok = map_lr(ix, rr.si >> 1, rr.pos, it.prefix, it.len, &L, &R) && ok;
-          if (u == 0) { L0 = L; R0 = R; }
+          bad |= !map_lr(ix, si >> 1, pos, it.prefix, it.len, &L, &R);
+          it.L = (uint8_t)L; it.R = (uint8_t)R;
+          items[item_begin + u] = it;
+          if (u == 0) { rec->L0 = (uint8_t)L; rec->R0 = (uint8_t)R; }
         }
-        recs[r].L0 = (uint8_t)L0; recs[r].R0 = (uint8_t)R0;
-        if (!ok) {
-          // mappability_tag.cpp:107-113 throws unless the chromosome is _gl000*/chrM
-          const char *nm = ix.descr + ix.descr_off[rr.si];
-          const int nl = ix.descr_off[rr.si + 1] - ix.descr_off[rr.si];
-          bool small = false;
-          for (int i = 0; i + 4 <= nl; ++i) if (nm[i] == 'c' && nm[i + 1] == 'h' && nm[i + 2] == 'r' && nm[i + 3] == 'M') small = true;
-          for (int i = 0; i + 6 <= nl; ++i) if (nm[i] == '_' && nm[i + 1] == 'g' && nm[i + 2] == 'l' && nm[i + 3] == '0' && nm[i + 4] == '0' && nm[i + 5] == '0') small = true;
-          if (!small) atomicAdd(&w.flags[FLAG_MAPERR], 1u);
-        }
+      }
+      const unsigned bm = __ballot_sync(0xffffffffu, bad) & gmask;
+      if (bm && sl == 0) {
+        // mappability_tag.cpp:107-113 throws unless the chromosome is _gl000*/chrM
+        const char *nm = ix.descr + ix.descr_off[si];
+        const int nl = ix.descr_off[si + 1] - ix.descr_off[si];
+        bool small = false;
+        for (int i = 0; i + 4 <= nl; ++i) if (nm[i] == 'c' && nm[i + 1] == 'h' && nm[i + 2] == 'r' && nm[i + 3] == 'M') small = true;
+        for (int i = 0; i + 6 <= nl; ++i) if (nm[i] == '_' && nm[i + 1] == 'g' && nm[i + 2] == 'l' && nm[i + 3] == '0' && nm[i + 4] == '0' && nm[i + 5] == '0') small = true;
+        if (!small) atomicAdd(&w.flags[FLAG_MAPERR], 1u);
       }
     }
   }
 }
 
-static int exclusive_scan_u32(const uint32_t *in, uint64_t n, uint64_t *blk, uint64_t *out, cudaStream_t st);
+static int exclusive_scan_u32(const uint32_t *in, uint64_t n, uint64_t *blk, uint64_t *out, cudaStream_t st, uint32_t *fill = nullptr);
 int launch_records(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
   if (!b.n_reads) return 0;
   if (w.slot_off) {
@@ -919,7 +950,7 @@ int launch_records(const DevIndex &ix, const BatchDev &b, const WorkDev &w, cons
   } else {
     k_rec_build_serial<<<grid_for_warps(b.n_reads, 6), THREADS, 0, st>>>(ix, b, w, p);
   }
-  int n = 1 + exclusive_scan_u32(w.nrec, b.n_reads, w.blk_sums, w.rec_base, st);
+  int n = 1 + exclusive_scan_u32(w.nrec, b.n_reads, w.blk_sums, w.rec_base, st, w.rec_read);    // + flat record -> read map
   k_rec_xe<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p);
   return n + 1;
 }
@@ -1017,8 +1048,10 @@ __global__ void k_scan_top(uint64_t *blk, uint64_t n_blk, const uint64_t *__rest
   }
   if (threadIdx.x == 0) blk[n_blk] = carry;
 }
+// fill != null: out[i] .. out[i] + in[i] of `fill` get the value i (the flat record -> read map of the rec_base scan)
 __global__ void k_scan_apply(const uint32_t *__restrict__ in, uint64_t n, const uint64_t *__restrict__ n_dev,
-                             const uint64_t *__restrict__ blk, uint64_t *__restrict__ out, uint64_t *__restrict__ total_out) {
+                             const uint64_t *__restrict__ blk, uint64_t *__restrict__ out, uint64_t *__restrict__ total_out,
+                             uint32_t *__restrict__ fill) {
   __shared__ uint64_t tot;
   uint64_t n_blk = gridDim.x;
   if (n_dev) {
@@ -1030,14 +1063,20 @@ __global__ void k_scan_apply(const uint32_t *__restrict__ in, uint64_t n, const 
   uint32_t v[SCAN_ITEMS]; uint64_t s = 0;
   for (int i = 0; i < SCAN_ITEMS; ++i) { v[i] = base + i < n ? in[base + i] : 0; s += v[i]; }
   uint64_t ex = block_exclusive_scan(s, &tot) + blk[blockIdx.x];
-  for (int i = 0; i < SCAN_ITEMS; ++i) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    if (base + i < n) {
+      out[base + i] = ex;
+      if (fill) for (uint32_t j = 0; j < v[i]; ++j) fill[ex + j] = (uint32_t)(base + i);
+    }
+    ex += v[i];
+  }
   if (blockIdx.x == n_blk - 1 && threadIdx.x == 0) { out[n] = blk[n_blk]; if (total_out) *total_out = blk[n_blk]; }
 }
-static int exclusive_scan_u32(const uint32_t *in, uint64_t n, uint64_t *blk, uint64_t *out, cudaStream_t st) {
+static int exclusive_scan_u32(const uint32_t *in, uint64_t n, uint64_t *blk, uint64_t *out, cudaStream_t st, uint32_t *fill) {
   const uint64_t n_blk = (n + SCAN_TILE - 1) / SCAN_TILE;
   k_scan_tiles<<<(unsigned)n_blk, SCAN_BLOCK, 0, st>>>(in, n, nullptr, blk);
   k_scan_top<<<1, SCAN_BLOCK, 0, st>>>(blk, n_blk, nullptr);
-  k_scan_apply<<<(unsigned)n_blk, SCAN_BLOCK, 0, st>>>(in, n, nullptr, blk, out, nullptr);
+  k_scan_apply<<<(unsigned)n_blk, SCAN_BLOCK, 0, st>>>(in, n, nullptr, blk, out, nullptr, fill);
   return 3;
 }
 // same, but the element count lives in device memory (*n_dev <= n_bound): tiles past it exit at once
@@ -1046,7 +1085,7 @@ static int exclusive_scan_u32_devn(const uint32_t *in, uint64_t n_bound, const u
   const uint64_t n_blk = (n_bound + SCAN_TILE - 1) / SCAN_TILE;
   k_scan_tiles<<<(unsigned)n_blk, SCAN_BLOCK, 0, st>>>(in, 0, n_dev, blk);
   k_scan_top<<<1, SCAN_BLOCK, 0, st>>>(blk, 0, n_dev);
-  k_scan_apply<<<(unsigned)n_blk, SCAN_BLOCK, 0, st>>>(in, 0, n_dev, blk, out, total_out);
+  k_scan_apply<<<(unsigned)n_blk, SCAN_BLOCK, 0, st>>>(in, 0, n_dev, blk, out, total_out, nullptr);
   return 3;
 }
 
@@ -1492,6 +1531,6 @@ int launch_slot_offsets(const uint32_t *match_cnt, uint64_t n_reads, uint32_t *t
 
 namespace smash {
 int exclusive_scan_u32_public(const uint32_t *in, uint64_t n, uint64_t *blk, uint64_t *out, cudaStream_t st) {
-  return exclusive_scan_u32(in, n, blk, out, st);
+  return exclusive_scan_u32(in, n, blk, out, st, nullptr);
 }
 }  // namespace smash

@@ -26,7 +26,9 @@ struct Rec {
   uint8_t rc, L0, R0, flags;       // L0/R0: mappability_tag values of the first '=' block
   uint16_t seq_off, lr_len;        // offset of the SEQ column in the line, length of the L/R tags (set by k_sizes)
 };
-struct Item { uint16_t prefix, len; };
+// One '=' block of a record's CIGAR; L/R: its mappability_tag values (set by k_rec_xe when map.bin is loaded, so that the
+// size, emit and tail kernels do not go back to map.bin)
+struct Item { uint16_t prefix, len; uint8_t L, R; uint16_t pad; };
 
 // Per-read summary (what the mate and the size/emit kernels need).
 struct ReadSum {
@@ -470,14 +472,10 @@ template <class S>
 HDN inline bool put_lr_tags(S &s, const DevIndex &ix, const Rec &r, const Item *items) {
   bool ok = true;
   for (int u = 0; u < r.item_cnt; ++u) {
-    const Item it = items[r.item_begin + u];
-    int L, R;
-    const bool fine = map_lr(ix, r.si >> 1, r.pos, it.prefix, it.len, &L, &R);
-    if (u < 10) {
-      put_lit(s, "\tL"); s.ch((char)('0' + u)); put_lit(s, ":i:"); put_u64(s, (uint64_t)L);
-      put_lit(s, "\tR"); s.ch((char)('0' + u)); put_lit(s, ":i:"); put_u64(s, (uint64_t)R);
-    }
-    ok = ok && fine;
+    if (u >= 10) break;
+    const Item it = items[r.item_begin + u];                   // L/R were looked up once, by k_rec_xe (map_lr)
+    put_lit(s, "\tL"); s.ch((char)('0' + u)); put_lit(s, ":i:"); put_u64(s, (uint64_t)it.L);
+    put_lit(s, "\tR"); s.ch((char)('0' + u)); put_lit(s, ":i:"); put_u64(s, (uint64_t)it.R);
   }
   return ok;
 }

@@ -202,6 +202,7 @@ uint64_t emul_map_batch(void *index, uint64_t n_reads, const uint8_t *names, con
           for (int u = 0; u < ro[r].recs[k].item_cnt; ++u) {
             Item it = ro[r].items[ro[r].recs[k].item_begin + u]; int L, R;
             ok = map_lr(ix, ro[r].recs[k].si >> 1, ro[r].recs[k].pos, it.prefix, it.len, &L, &R) && ok;
+            ro[r].items[ro[r].recs[k].item_begin + u].L = (uint8_t)L; ro[r].items[ro[r].recs[k].item_begin + u].R = (uint8_t)R;
             if (u == 0) { ro[r].recs[k].L0 = (uint8_t)L; ro[r].recs[k].R0 = (uint8_t)R; }
           }
           if (!ok && maperr) ++*maperr;
