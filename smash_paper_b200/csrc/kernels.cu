@@ -988,7 +988,7 @@ k_sizes(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     const Item *items = w.item_slots + slot_base(w, read);
     Rec *recs = w.rec_slots + slot_base(w, read);
     CountSink cs;
-    put_head(cs, ix, (const char *)nullptr, name_len, flag, me.unmapped, recs[r], r, items, mv);
+    put_head(cs, ix, (const char *)nullptr, name_len, flag, me.unmapped, recs, r, me.n_rec, items, mv);
     const uint32_t seq_at = cs.n;                                  // offset of the SEQ column in the line
     put_tags(cs, ix, me.unmapped, recs, r, me.n_rec, items);
     const uint32_t before_lr = cs.n;
@@ -1142,21 +1142,17 @@ k_emit_text(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp, uint64_t n_reco
     const int opt_len = b.opt ? (int)(b.opt_off[read + 1] - b.opt_off[read]) : 0;
     char *out = w.sam + w.rec_off[f];
     WordSink hs(out + name_len);
-    put_head(hs, ix, (const char *)nullptr, 0, flag, me.unmapped, recs[hi], hi, items, mv);
+    put_head(hs, ix, (const char *)nullptr, 0, flag, me.unmapped, recs, hi, me.n_rec, items, mv);
     hs.finish();
     WordSink ts(out + name_len + hs.n + 2 * q + 1);
     put_tags(ts, ix, me.unmapped, recs, hi, me.n_rec, items);
     if (opt_len) {                                           // the optional fields sit between the tags and the L/R tags
       ts.finish();
-      WordSink ls(out + name_len + hs.n + 2 * q + 1 + ts.n + opt_len);
-      if (sp.tag_mappability && !me.unmapped) put_lr_tags(ls, ix, recs[hi], items);
-      ls.ch('\n');
-      ls.finish();
-    } else {
-      if (sp.tag_mappability && !me.unmapped) put_lr_tags(ts, ix, recs[hi], items);
-      ts.ch('\n');
-      ts.finish();
+      ts = WordSink(out + name_len + hs.n + 2 * q + 1 + ts.n + opt_len);
     }
+    if (sp.tag_mappability && !me.unmapped) put_lr_tags(ts, ix, recs[hi], items);
+    ts.ch('\n');
+    ts.finish();
   }
 }
 
@@ -1175,7 +1171,7 @@ k_emit_compact(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp, uint64_t n_r
     const Rec *recs = w.rec_slots + slot_base(w, read);
     const uint64_t co = w.cmp_off[f];
     WordSink s(w.cmp + co);
-    put_head(s, ix, (const char *)nullptr, 0, flag, me.unmapped, recs[hi], hi, items, mv);
+    put_head(s, ix, (const char *)nullptr, 0, flag, me.unmapped, recs, hi, me.n_rec, items, mv);
     const uint32_t head_len = s.n;
     put_tags(s, ix, me.unmapped, recs, hi, me.n_rec, items);
     const uint32_t tags_len = s.n - head_len;

@@ -388,17 +388,26 @@ template <class S> HDN inline void put_descr(S &s, const DevIndex &ix, uint32_t 
   if (len <= 8 && ix.descr8) s.word(ix.descr8[si], len);           // names of <= 8 chars: one packed word
   else s.put(ix.descr + ix.descr_off[si], len);
 }
-// CIGAR of a record (query.cpp:260-268): [<prefix>S] len= [<gap>M len=]... [<suffix>S]
+// CIGAR of a record (query.cpp:260-268): [<prefix>S] len= [<gap>M len=]... [<suffix>S].  One loop over its
+// <number><letter> tokens, so that the number formatter exists ONCE in the emitted code (see put_fields).
 template <class S> HDN inline void put_cigar(S &s, const Rec &r, const Item *items) {
   if (r.item_cnt == 0) { s.ch('*'); return; }
   uint32_t last_end = 0;
-  for (int i = 0; i < r.item_cnt; ++i) {
-    const Item it = items[r.item_begin + i];
-    if (it.prefix) { put_u64(s, it.prefix - last_end); s.ch(last_end ? 'M' : 'S'); }
-    put_u64(s, it.len); s.ch('=');
-    last_end = (uint32_t)it.prefix + it.len;
+  const int n_tok = 2 * (int)r.item_cnt + 1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int t = 0; t < n_tok; ++t) {
+    uint32_t num; char c; bool present;
+    if (t == n_tok - 1) { num = r.suffix; c = 'S'; present = r.suffix != 0; }
+    else {
+      const Item it = items[r.item_begin + (t >> 1)];
+      if (t & 1) { num = it.len; c = '='; present = true; last_end = (uint32_t)it.prefix + it.len; }
+      else { num = it.prefix - last_end; c = last_end ? 'M' : 'S'; present = it.prefix != 0; }
+    }
+    if (!present) continue;
+    put_u64(s, num); s.ch(c);
   }
-  if (r.suffix) { put_u64(s, r.suffix); s.ch('S'); }
 }
 
 struct MateView { uint8_t has; uint32_t si; int64_t pos; };
@@ -420,64 +429,124 @@ HD void mate_view(uint16_t my_flag, const ReadSum &me, uint16_t other_flag, cons
   }
 }
 
-// Columns 1-9 (up to and including the tab before SEQ).
+// A SAM line's computed text is a sequence of FIELDS: a literal of up to 8 characters followed by one value (number,
+// sequence name, character, CIGAR).  put_head / put_tags walk the field list in ONE loop whose body holds the only copy
+// of every formatter: the kernels stay small enough for the instruction cache (the fully inlined version was 35 k
+// instructions and spent 30 % of its issue slots waiting for instruction fetches), and the threads of a warp are at the
+// same field at the same time whatever their records look like.
+enum { FK_NONE = 0, FK_U64, FK_I64, FK_DESCR, FK_CHAR, FK_CIGAR };
+struct Field { uint64_t lit; int lit_len; int kind; int64_t val; const Rec *rec; };
+constexpr int F_HEAD_END = 7, F_TAGS_END = 21;
+#define SMASH_LIT(str) f.lit = pack8(str, (int)sizeof(str) - 1); f.lit_len = (int)sizeof(str) - 1
+HD Field line_field(int fi, uint16_t flag, bool unmapped, const Rec *recs, int hi, int n_rec, const MateView &mv) {
+  Field f{0, 0, FK_NONE, 0, nullptr};
+  const Rec &r = recs[hi];
+  if (fi < 4) {                                                // FLAG RNAME POS MAPQ CIGAR (query.cpp:331-372)
+    if (unmapped) {
+      switch (fi) {
+        case 0: SMASH_LIT("\t"); f.kind = FK_U64; f.val = flag; break;
+        case 1: if (mv.has) { SMASH_LIT("\t"); f.kind = FK_DESCR; f.val = mv.si; } else { SMASH_LIT("\t*\t0"); } break;
+        case 2: if (mv.has) { SMASH_LIT("\t"); f.kind = FK_I64; f.val = mv.pos + 1; } break;
+        default: SMASH_LIT("\t0\t*"); break;
+      }
+    } else {
+      switch (fi) {
+        case 0: SMASH_LIT("\t"); f.kind = FK_U64; f.val = (int64_t)(flag | (r.rc ? 16 : 0) | (hi ? 256 : 0)); break;
+        case 1: SMASH_LIT("\t"); f.kind = FK_DESCR; f.val = r.si; break;
+        case 2: SMASH_LIT("\t"); f.kind = FK_I64; f.val = r.pos + 1; break;
+        default: SMASH_LIT("\t50\t"); f.kind = FK_CIGAR; f.rec = &r; break;
+      }
+    }
+  } else if (fi < F_HEAD_END) {                                // RNEXT PNEXT TLEN
+    if (mv.has) {
+      switch (fi) {
+        case 4: SMASH_LIT("\t"); f.kind = FK_DESCR; f.val = mv.si; break;
+        case 5: SMASH_LIT("\t"); f.kind = FK_I64; f.val = mv.pos + 1; break;
+        default: SMASH_LIT("\t0\t"); break;
+      }
+    } else if (fi == 4) { SMASH_LIT("\t*\t0\t0\t"); }
+  } else if (unmapped) {                                       // tags of a placeholder
+    if (fi == 7) { SMASH_LIT("\tXM:i:0"); } else if (fi == 8) { SMASH_LIT("\tNH:i:0"); }
+  } else if (fi < 13) {
+    switch (fi) {
+      case 7: SMASH_LIT("\tXM:i:"); f.kind = FK_U64; f.val = r.item_cnt; break;
+      case 8: SMASH_LIT("\tXU:i:"); f.kind = FK_U64; f.val = r.xu; break;
+      case 9: SMASH_LIT("\tXE:i:"); f.kind = FK_U64; f.val = r.xe; break;
+      case 10: SMASH_LIT("\tXS:A:"); f.kind = FK_CHAR; f.val = r.rc ? '-' : '+'; break;
+      case 11: SMASH_LIT("\tNH:i:"); f.kind = FK_U64; f.val = n_rec; break;
+      default: SMASH_LIT("\tHI:i:"); f.kind = FK_U64; f.val = hi; break;
+    }
+  } else if (fi < 17) {                                        // previous record of the read (lower-case tags)
+    if (hi > 0) {
+      const Rec &p = recs[hi - 1];
+      switch (fi) {
+        case 13: SMASH_LIT("\tcc:Z:"); f.kind = FK_DESCR; f.val = p.si; break;
+        case 14: SMASH_LIT("\tcp:i:"); f.kind = FK_I64; f.val = p.pos + 1; break;
+        case 15: SMASH_LIT("\txo:A:"); f.kind = FK_CHAR; f.val = p.rc == r.rc ? '=' : '!'; break;
+        default: SMASH_LIT("\txc:Z:"); f.kind = FK_CIGAR; f.rec = &p; break;
+      }
+    }
+  } else if (hi + 1 < n_rec) {                                 // next record (upper-case tags)
+    const Rec &x = recs[hi + 1];
+    switch (fi) {
+      case 17: SMASH_LIT("\tCC:Z:"); f.kind = FK_DESCR; f.val = x.si; break;
+      case 18: SMASH_LIT("\tCP:i:"); f.kind = FK_I64; f.val = x.pos + 1; break;
+      case 19: SMASH_LIT("\tXO:A:"); f.kind = FK_CHAR; f.val = x.rc == r.rc ? '=' : '!'; break;
+      default: SMASH_LIT("\tXC:Z:"); f.kind = FK_CIGAR; f.rec = &x; break;
+    }
+  }
+  return f;
+}
+#undef SMASH_LIT
+template <class S>
+HDN inline void put_fields(S &s, const DevIndex &ix, int f0, int f1, uint16_t flag, bool unmapped, const Rec *recs, int hi,
+                           int n_rec, const Item *items, const MateView &mv) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int fi = f0; fi < f1; ++fi) {
+    const Field f = line_field(fi, flag, unmapped, recs, hi, n_rec, mv);
+    if (!f.lit_len) continue;
+    s.word(f.lit, f.lit_len);
+    if (f.kind == FK_U64 || f.kind == FK_I64) {
+      uint64_t v = (uint64_t)f.val;
+      if (f.kind == FK_I64 && f.val < 0) { s.ch('-'); v = (uint64_t)(-f.val); }
+      put_u64(s, v);
+    } else if (f.kind == FK_DESCR) put_descr(s, ix, (uint32_t)f.val);
+    else if (f.kind == FK_CHAR) s.ch((char)f.val);
+    else if (f.kind == FK_CIGAR) put_cigar(s, *f.rec, items);
+  }
+}
+// Columns 1-9 (up to and including the tab before SEQ).  `recs` = the read's records, `hi` = this one.
 template <class S>
 HDN inline void put_head(S &s, const DevIndex &ix, const char *name, int name_len, uint16_t flag,
-                         bool unmapped, const Rec &r, int hi, const Item *items, const MateView &mv) {
-  s.put(name, name_len); s.ch('\t');
-  if (unmapped) {
-    put_u64(s, flag); s.ch('\t');
-    if (mv.has) { put_descr(s, ix, mv.si); s.ch('\t'); put_i64(s, mv.pos + 1); } else put_lit(s, "*\t0");
-    put_lit(s, "\t0\t*");
-  } else {
-    put_u64(s, (uint64_t)(flag | (r.rc ? 16 : 0) | (hi ? 256 : 0))); s.ch('\t');
-    put_descr(s, ix, r.si); s.ch('\t'); put_i64(s, r.pos + 1); put_lit(s, "\t50\t");
-    put_cigar(s, r, items);
-  }
-  if (mv.has) { s.ch('\t'); put_descr(s, ix, mv.si); s.ch('\t'); put_i64(s, mv.pos + 1); put_lit(s, "\t0\t"); }
-  else put_lit(s, "\t*\t0\t0\t");
+                         bool unmapped, const Rec *recs, int hi, int n_rec, const Item *items, const MateView &mv) {
+  s.put(name, name_len);
+  put_fields(s, ix, 0, F_HEAD_END, flag, unmapped, recs, hi, n_rec, items, mv);
 }
 // Everything after QUAL up to (not including) the optional fields / L,R tags / newline.
 template <class S>
 HDN inline void put_tags(S &s, const DevIndex &ix, bool unmapped, const Rec *recs, int hi, int n_rec,
                          const Item *items) {
-  const Rec &r = recs[hi];
-  if (!unmapped) {
-    put_lit(s, "\tXM:i:"); put_u64(s, r.item_cnt);
-    put_lit(s, "\tXU:i:"); put_u64(s, r.xu);
-    put_lit(s, "\tXE:i:"); put_u64(s, r.xe);
-    put_lit(s, "\tXS:A:"); s.ch(r.rc ? '-' : '+');
-    put_lit(s, "\tNH:i:"); put_u64(s, (uint64_t)n_rec);
-    put_lit(s, "\tHI:i:"); put_u64(s, (uint64_t)hi);
-    if (hi > 0) {
-      const Rec &p = recs[hi - 1];
-      put_lit(s, "\tcc:Z:"); put_descr(s, ix, p.si);
-      put_lit(s, "\tcp:i:"); put_i64(s, p.pos + 1);
-      put_lit(s, "\txo:A:"); s.ch(p.rc == r.rc ? '=' : '!');
-      put_lit(s, "\txc:Z:"); put_cigar(s, p, items);
-    }
-    if (hi + 1 < n_rec) {
-      const Rec &x = recs[hi + 1];
-      put_lit(s, "\tCC:Z:"); put_descr(s, ix, x.si);
-      put_lit(s, "\tCP:i:"); put_i64(s, x.pos + 1);
-      put_lit(s, "\tXO:A:"); s.ch(x.rc == r.rc ? '=' : '!');
-      put_lit(s, "\tXC:Z:"); put_cigar(s, x, items);
-    }
-  } else {
-    put_lit(s, "\tXM:i:0\tNH:i:0");
-  }
+  const MateView none{0, 0, 0};
+  put_fields(s, ix, F_HEAD_END, F_TAGS_END, 0, unmapped, recs, hi, n_rec, items, none);
 }
 // mappability_tag's appended tags (after the optional fields): \tL<u>:i:x\tR<u>:i:y for u < 10.
 template <class S>
 HDN inline bool put_lr_tags(S &s, const DevIndex &ix, const Rec &r, const Item *items) {
-  bool ok = true;
-  for (int u = 0; u < r.item_cnt; ++u) {
-    if (u >= 10) break;
-    const Item it = items[r.item_begin + u];                   // L/R were looked up once, by k_rec_xe (map_lr)
-    put_lit(s, "\tL"); s.ch((char)('0' + u)); put_lit(s, ":i:"); put_u64(s, (uint64_t)it.L);
-    put_lit(s, "\tR"); s.ch((char)('0' + u)); put_lit(s, ":i:"); put_u64(s, (uint64_t)it.R);
+  const int n = r.item_cnt < 10 ? (int)r.item_cnt : 10;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int t = 0; t < 2 * n; ++t) {
+    const Item it = items[r.item_begin + (t >> 1)];            // L/R were looked up once, by k_rec_xe (map_lr)
+    // "\tL<u>:i:" as one packed word
+    const uint64_t lit = (uint64_t)'\t' | ((uint64_t)((t & 1) ? 'R' : 'L') << 8) | ((uint64_t)('0' + (t >> 1)) << 16) |
+                         ((uint64_t)':' << 24) | ((uint64_t)'i' << 32) | ((uint64_t)':' << 40);
+    s.word(lit, 6);
+    put_u64(s, (uint64_t)((t & 1) ? it.R : it.L));
   }
-  return ok;
+  return true;
 }
 
 // reverse_complement (fasta.cpp:26-61) for one character

@@ -227,8 +227,8 @@ uint64_t emul_map_batch(void *index, uint64_t n_reads, const uint8_t *names, con
     for (int k = 0; k < me.n_rec; ++k) {
       std::vector<char> buf(name_len + 4096 + 64 * ro[r].items.size());
       BufSink bs{buf.data()};
-      put_head(bs, ix, name, name_len, flag, me.unmapped, ro[r].recs[k], k, ro[r].items.data(), mv);
-      CountSink cs; put_head(cs, ix, name, name_len, flag, me.unmapped, ro[r].recs[k], k, ro[r].items.data(), mv);
+      put_head(bs, ix, name, name_len, flag, me.unmapped, ro[r].recs.data(), k, me.n_rec, ro[r].items.data(), mv);
+      CountSink cs; put_head(cs, ix, name, name_len, flag, me.unmapped, ro[r].recs.data(), k, me.n_rec, ro[r].items.data(), mv);
       if (cs.n != bs.n) abort();
       sam.append(buf.data(), bs.n);
       const uint8_t *sq = seq + seq_off[r], *ql = qual + seq_off[r];
