@@ -973,10 +973,7 @@ __device__ __forceinline__ void read_mate(const BatchDev &b, const WorkDev &w, u
 }
 
 // One THREAD per record (flat index): exact byte length of its SAM line.
-#ifndef SMASH_SIZES_MINBLK
-#define SMASH_SIZES_MINBLK 1
-#endif
-__global__ void __launch_bounds__(128, SMASH_SIZES_MINBLK)
+__global__ void __launch_bounds__(128)
 k_sizes(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
   const uint64_t n_records = w.rec_base[b.n_reads];
   for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_records; f += (uint64_t)gridDim.x * blockDim.x) {
@@ -990,17 +987,12 @@ k_sizes(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     const int opt_len = b.opt ? (int)(b.opt_off[read + 1] - b.opt_off[read]) : 0;
     const Item *items = w.item_slots + slot_base(w, read);
     Rec *recs = w.rec_slots + slot_base(w, read);
-    // the line's computed text, segment by segment (records.cuh put_segment: ONE formatter loop in the kernel)
-    const LineCtx lc = line_ctx(ix, flag, me.unmapped, recs, r, me.n_rec, items, mv, sp.tag_mappability != 0, false);
     CountSink cs;
-    cs.n = (uint32_t)name_len;
-    uint32_t seq_at = 0, before_lr = 0;
-#pragma unroll 1
-    for (int seg = 0; seg < 3; ++seg) {
-      put_segment(cs, lc, seg == 0 ? 0 : seg == 1 ? F_HEAD_END : F_TAGS_END, seg == 0 ? F_HEAD_END : seg == 1 ? F_TAGS_END : F_LR_END);
-      if (seg == 0) seq_at = cs.n;                                  // offset of the SEQ column in the line
-      else if (seg == 1) before_lr = cs.n;
-    }
+    put_head(cs, ix, (const char *)nullptr, name_len, flag, me.unmapped, recs, r, me.n_rec, items, mv);
+    const uint32_t seq_at = cs.n;                                  // offset of the SEQ column in the line
+    put_tags(cs, ix, me.unmapped, recs, r, me.n_rec, items);
+    const uint32_t before_lr = cs.n;
+    if (sp.tag_mappability && !me.unmapped) put_lr_tags(cs, ix, recs[r], items);
     recs[r].seq_off = (uint16_t)seq_at; recs[r].lr_len = (uint16_t)(cs.n - before_lr);
     w.rec_bytes[f] = cs.n + 2u * (uint32_t)q + 1u /*tab between SEQ and QUAL*/ + (uint32_t)opt_len + 1u /*\n*/;
     if (w.cmp_bytes) w.cmp_bytes[f] = cs.n - (uint32_t)name_len + 1u;      // compact transport: head + tags + lr-tags + \n
@@ -1149,17 +1141,18 @@ k_emit_text(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp, uint64_t n_reco
     const int q = (int)(b.seq_off[read + 1] - b.seq_off[read]);
     const int opt_len = b.opt ? (int)(b.opt_off[read + 1] - b.opt_off[read]) : 0;
     char *out = w.sam + w.rec_off[f];
-    const LineCtx lc = line_ctx(ix, flag, me.unmapped, recs, hi, me.n_rec, items, mv, sp.tag_mappability != 0, true);
-    // head | SEQ QUAL (k_emit_copy) | tags | optional fields (k_emit_copy) | L/R tags + newline
-    char *dst = out + name_len;
-    const int n_seg = opt_len ? 3 : 2;
-#pragma unroll 1
-    for (int seg = 0; seg < n_seg; ++seg) {
-      WordSink s(dst);
-      put_segment(s, lc, seg == 0 ? 0 : seg == 1 ? F_HEAD_END : F_TAGS_END, seg == 0 ? F_HEAD_END : (seg == 1 && opt_len) ? F_TAGS_END : F_LINE_END);
-      s.finish();
-      dst += s.n + (seg == 0 ? 2 * q + 1 : opt_len);
+    WordSink hs(out + name_len);
+    put_head(hs, ix, (const char *)nullptr, 0, flag, me.unmapped, recs, hi, me.n_rec, items, mv);
+    hs.finish();
+    WordSink ts(out + name_len + hs.n + 2 * q + 1);
+    put_tags(ts, ix, me.unmapped, recs, hi, me.n_rec, items);
+    if (opt_len) {                                           // the optional fields sit between the tags and the L/R tags
+      ts.finish();
+      ts = WordSink(out + name_len + hs.n + 2 * q + 1 + ts.n + opt_len);
     }
+    if (sp.tag_mappability && !me.unmapped) put_lr_tags(ts, ix, recs[hi], items);
+    ts.ch('\n');
+    ts.finish();
   }
 }
 
@@ -1177,14 +1170,13 @@ k_emit_compact(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp, uint64_t n_r
     const Item *items = w.item_slots + slot_base(w, read);
     const Rec *recs = w.rec_slots + slot_base(w, read);
     const uint64_t co = w.cmp_off[f];
-    const LineCtx lc = line_ctx(ix, flag, me.unmapped, recs, hi, me.n_rec, items, mv, sp.tag_mappability != 0, true);
     WordSink s(w.cmp + co);
-    uint32_t head_len = 0, tags_len = 0;
-#pragma unroll 1
-    for (int seg = 0; seg < 3; ++seg) {
-      put_segment(s, lc, seg == 0 ? 0 : seg == 1 ? F_HEAD_END : F_TAGS_END, seg == 0 ? F_HEAD_END : seg == 1 ? F_TAGS_END : F_LINE_END);
-      if (seg == 0) head_len = s.n; else if (seg == 1) tags_len = s.n - head_len;
-    }
+    put_head(s, ix, (const char *)nullptr, 0, flag, me.unmapped, recs, hi, me.n_rec, items, mv);
+    const uint32_t head_len = s.n;
+    put_tags(s, ix, me.unmapped, recs, hi, me.n_rec, items);
+    const uint32_t tags_len = s.n - head_len;
+    if (sp.tag_mappability && !me.unmapped) put_lr_tags(s, ix, recs[hi], items);
+    s.ch('\n');
     s.finish();
     const uint32_t lr_len = s.n - head_len - tags_len;
     const bool rc = recs[hi].rc && !me.unmapped;

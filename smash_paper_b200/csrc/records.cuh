@@ -430,37 +430,28 @@ HD void mate_view(uint16_t my_flag, const ReadSum &me, uint16_t other_flag, cons
 }
 
 // A SAM line's computed text is a sequence of FIELDS: a literal of up to 8 characters followed by one value (number,
-// sequence name, character, CIGAR), and every field is a sequence of ATOMS of up to 8 packed characters.  put_segment
-// is ONE loop that produces the next atom and hands it to the sink -- a single call site of the sink's `word`, a single
-// copy of every formatter -- so the emit kernels are a few hundred instructions around that loop (the fully inlined
-// version was 35 k instructions and spent a third of its issue slots waiting for instruction fetches) and the threads
-// of a warp walk the same field list in step whatever their records look like.
+// sequence name, character, CIGAR).  put_head / put_tags walk the field list in ONE loop whose body holds the only copy
+// of every formatter: the kernels stay small enough for the instruction cache (the fully inlined version was 35 k
+// instructions and spent 30 % of its issue slots waiting for instruction fetches), and the threads of a warp are at the
+// same field at the same time whatever their records look like.
 enum { FK_NONE = 0, FK_U64, FK_I64, FK_DESCR, FK_CHAR, FK_CIGAR };
 struct Field { uint64_t lit; int lit_len; int kind; int64_t val; const Rec *rec; };
-// fields [0,7): columns 2-9; [7,21): tags; [21,41): mappability_tag's L<u>/R<u> tags; 41: the newline
-constexpr int F_HEAD_END = 7, F_TAGS_END = 21, F_LR_END = 41, F_LINE_END = 42;
-struct LineCtx {
-  const DevIndex *ix; uint16_t flag; bool unmapped; const Rec *recs; int hi, n_rec; const Item *items; MateView mv;
-  bool lr_tags;        // append the L/R tags (fields 21..40)
-  bool newline;        // field 41
-};
+constexpr int F_HEAD_END = 7, F_TAGS_END = 21;
 #define SMASH_LIT(str) f.lit = pack8(str, (int)sizeof(str) - 1); f.lit_len = (int)sizeof(str) - 1
-HD Field line_field(int fi, const LineCtx &lc) {
+HD Field line_field(int fi, uint16_t flag, bool unmapped, const Rec *recs, int hi, int n_rec, const MateView &mv) {
   Field f{0, 0, FK_NONE, 0, nullptr};
-  const Rec &r = lc.recs[lc.hi];
-  const MateView &mv = lc.mv;
-  const int hi = lc.hi;
+  const Rec &r = recs[hi];
   if (fi < 4) {                                                // FLAG RNAME POS MAPQ CIGAR (query.cpp:331-372)
-    if (lc.unmapped) {
+    if (unmapped) {
       switch (fi) {
-        case 0: SMASH_LIT("\t"); f.kind = FK_U64; f.val = lc.flag; break;
+        case 0: SMASH_LIT("\t"); f.kind = FK_U64; f.val = flag; break;
         case 1: if (mv.has) { SMASH_LIT("\t"); f.kind = FK_DESCR; f.val = mv.si; } else { SMASH_LIT("\t*\t0"); } break;
         case 2: if (mv.has) { SMASH_LIT("\t"); f.kind = FK_I64; f.val = mv.pos + 1; } break;
         default: SMASH_LIT("\t0\t*"); break;
       }
     } else {
       switch (fi) {
-        case 0: SMASH_LIT("\t"); f.kind = FK_U64; f.val = (int64_t)(lc.flag | (r.rc ? 16 : 0) | (hi ? 256 : 0)); break;
+        case 0: SMASH_LIT("\t"); f.kind = FK_U64; f.val = (int64_t)(flag | (r.rc ? 16 : 0) | (hi ? 256 : 0)); break;
         case 1: SMASH_LIT("\t"); f.kind = FK_DESCR; f.val = r.si; break;
         case 2: SMASH_LIT("\t"); f.kind = FK_I64; f.val = r.pos + 1; break;
         default: SMASH_LIT("\t50\t"); f.kind = FK_CIGAR; f.rec = &r; break;
@@ -474,18 +465,7 @@ HD Field line_field(int fi, const LineCtx &lc) {
         default: SMASH_LIT("\t0\t"); break;
       }
     } else if (fi == 4) { SMASH_LIT("\t*\t0\t0\t"); }
-  } else if (fi >= F_TAGS_END) {
-    if (fi == F_LR_END) { if (lc.newline) { SMASH_LIT("\n"); } }
-    else if (lc.lr_tags && !lc.unmapped) {                     // \tL<u>:i:x\tR<u>:i:y for u < 10 (mappability_tag.cpp:93-121)
-      const int t = fi - F_TAGS_END, u = t >> 1;
-      if (u < (int)r.item_cnt) {
-        const Item it = lc.items[r.item_begin + u];            // L/R were looked up once, by k_rec_xe (map_lr)
-        f.lit = (uint64_t)'\t' | ((uint64_t)((t & 1) ? 'R' : 'L') << 8) | ((uint64_t)('0' + u) << 16) | ((uint64_t)':' << 24) |
-                ((uint64_t)'i' << 32) | ((uint64_t)':' << 40);
-        f.lit_len = 6; f.kind = FK_U64; f.val = (t & 1) ? it.R : it.L;
-      }
-    }
-  } else if (lc.unmapped) {                                    // tags of a placeholder
+  } else if (unmapped) {                                       // tags of a placeholder
     if (fi == 7) { SMASH_LIT("\tXM:i:0"); } else if (fi == 8) { SMASH_LIT("\tNH:i:0"); }
   } else if (fi < 13) {
     switch (fi) {
@@ -493,12 +473,12 @@ HD Field line_field(int fi, const LineCtx &lc) {
       case 8: SMASH_LIT("\tXU:i:"); f.kind = FK_U64; f.val = r.xu; break;
       case 9: SMASH_LIT("\tXE:i:"); f.kind = FK_U64; f.val = r.xe; break;
       case 10: SMASH_LIT("\tXS:A:"); f.kind = FK_CHAR; f.val = r.rc ? '-' : '+'; break;
-      case 11: SMASH_LIT("\tNH:i:"); f.kind = FK_U64; f.val = lc.n_rec; break;
+      case 11: SMASH_LIT("\tNH:i:"); f.kind = FK_U64; f.val = n_rec; break;
       default: SMASH_LIT("\tHI:i:"); f.kind = FK_U64; f.val = hi; break;
     }
   } else if (fi < 17) {                                        // previous record of the read (lower-case tags)
     if (hi > 0) {
-      const Rec &p = lc.recs[hi - 1];
+      const Rec &p = recs[hi - 1];
       switch (fi) {
         case 13: SMASH_LIT("\tcc:Z:"); f.kind = FK_DESCR; f.val = p.si; break;
         case 14: SMASH_LIT("\tcp:i:"); f.kind = FK_I64; f.val = p.pos + 1; break;
@@ -506,8 +486,8 @@ HD Field line_field(int fi, const LineCtx &lc) {
         default: SMASH_LIT("\txc:Z:"); f.kind = FK_CIGAR; f.rec = &p; break;
       }
     }
-  } else if (hi + 1 < lc.n_rec) {                              // next record (upper-case tags)
-    const Rec &x = lc.recs[hi + 1];
+  } else if (hi + 1 < n_rec) {                                 // next record (upper-case tags)
+    const Rec &x = recs[hi + 1];
     switch (fi) {
       case 17: SMASH_LIT("\tCC:Z:"); f.kind = FK_DESCR; f.val = x.si; break;
       case 18: SMASH_LIT("\tCP:i:"); f.kind = FK_I64; f.val = x.pos + 1; break;
@@ -518,104 +498,54 @@ HD Field line_field(int fi, const LineCtx &lc) {
   return f;
 }
 #undef SMASH_LIT
-// fields [f0, f1) of the line, atom by atom
 template <class S>
-HDN inline void put_segment(S &s, const LineCtx &lc, int f0, int f1) {
-  int fi = f0;
-  bool in_value = false;
-  Field f{0, 0, FK_NONE, 0, nullptr};
-  uint64_t num = 0; int part = 0, n_part = 0;                  // numbers: 8-digit chunks, most significant first
-  int tok = 0, n_tok = 0; uint32_t last_end = 0;               // CIGAR tokens; name chunks (tok)
+HDN inline void put_fields(S &s, const DevIndex &ix, int f0, int f1, uint16_t flag, bool unmapped, const Rec *recs, int hi,
+                           int n_rec, const Item *items, const MateView &mv) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-  while (fi < f1) {
-    uint64_t av = 0; int al = 0;                               // the next atom
-    if (!in_value) {
-      f = line_field(fi, lc);
-      if (!f.lit_len) { ++fi; continue; }
-      av = f.lit; al = f.lit_len;
-      if (f.kind == FK_NONE) ++fi;
-      else {
-        in_value = true;
-        if (f.kind == FK_U64 || f.kind == FK_I64) {
-          num = (uint64_t)f.val; part = -1;
-          if (f.kind == FK_I64 && f.val < 0) num = (uint64_t)(-f.val); else f.kind = FK_U64;      // FK_I64 from here on: a '-' is due
-          n_part = num < 100000000ull ? 1 : num < 10000000000000000ull ? 2 : 3;
-        } else if (f.kind == FK_CIGAR) { tok = 0; n_tok = f.rec->item_cnt ? 2 * (int)f.rec->item_cnt + 1 : 0; last_end = 0; }
-        else tok = 0;
-      }
-    } else if (f.kind == FK_I64) { av = (uint64_t)'-'; al = 1; f.kind = FK_U64; }
-    else if (f.kind == FK_U64) {
-      ++part;
-      uint32_t chunk;
-      if (n_part == 1) chunk = (uint32_t)num;
-      else {
-        const int shift = n_part - 1 - part;                  // 8-digit groups below this one
-        const uint64_t hi = shift == 2 ? num / 10000000000000000ull : shift == 1 ? num / 100000000ull : num;
-        chunk = (uint32_t)(hi % 100000000ull);
-      }
-      av = digits8(chunk, part != 0, &al);
-      if (part + 1 == n_part) { in_value = false; ++fi; }
-    } else if (f.kind == FK_CHAR) { av = (uint64_t)(uint8_t)f.val; al = 1; in_value = false; ++fi; }
-    else if (f.kind == FK_DESCR) {
-      const uint32_t si = (uint32_t)f.val;
-      const int len = lc.ix->descr_off[si + 1] - lc.ix->descr_off[si];
-      if (len <= 8 && lc.ix->descr8) { av = lc.ix->descr8[si]; al = len; in_value = false; ++fi; }     // one packed word
-      else {
-        const char *nm = lc.ix->descr + lc.ix->descr_off[si] + 8 * tok;
-        al = len - 8 * tok < 8 ? len - 8 * tok : 8;
-        for (int i = 0; i < al; ++i) av |= (uint64_t)(uint8_t)nm[i] << (8 * i);
-        ++tok;
-        if (8 * tok >= len) { in_value = false; ++fi; }
-      }
-    } else {                                                   // FK_CIGAR (query.cpp:260-268): [<prefix>S] len= [<gap>M len=].. [<suffix>S]
-      const Rec &r = *f.rec;
-      if (!n_tok) { av = (uint64_t)'*'; al = 1; in_value = false; ++fi; }
-      else {
-        uint32_t v; char c; bool present;
-        if (tok == n_tok - 1) { v = r.suffix; c = 'S'; present = r.suffix != 0; }
-        else {
-          const Item it = lc.items[r.item_begin + (tok >> 1)];
-          if (tok & 1) { v = it.len; c = '='; present = true; last_end = (uint32_t)it.prefix + it.len; }
-          else { v = it.prefix - last_end; c = last_end ? 'M' : 'S'; present = it.prefix != 0; }
-        }
-        if (present) {
-          if (v < 10000000u) { int nd; av = digits8(v, false, &nd); av |= (uint64_t)(uint8_t)c << (8 * nd); al = nd + 1; }
-          else { put_u64(s, v); av = (uint64_t)(uint8_t)c; al = 1; }                  // (cannot happen with 16-bit items; kept exact)
-        }
-        if (++tok == n_tok) { in_value = false; ++fi; }
-      }
-    }
-    s.word(av, al);
+  for (int fi = f0; fi < f1; ++fi) {
+    const Field f = line_field(fi, flag, unmapped, recs, hi, n_rec, mv);
+    if (!f.lit_len) continue;
+    s.word(f.lit, f.lit_len);
+    if (f.kind == FK_U64 || f.kind == FK_I64) {
+      uint64_t v = (uint64_t)f.val;
+      if (f.kind == FK_I64 && f.val < 0) { s.ch('-'); v = (uint64_t)(-f.val); }
+      put_u64(s, v);
+    } else if (f.kind == FK_DESCR) put_descr(s, ix, (uint32_t)f.val);
+    else if (f.kind == FK_CHAR) s.ch((char)f.val);
+    else if (f.kind == FK_CIGAR) put_cigar(s, *f.rec, items);
   }
-}
-HD LineCtx line_ctx(const DevIndex &ix, uint16_t flag, bool unmapped, const Rec *recs, int hi, int n_rec, const Item *items,
-                    const MateView &mv, bool lr_tags, bool newline) {
-  LineCtx lc;
-  lc.ix = &ix; lc.flag = flag; lc.unmapped = unmapped; lc.recs = recs; lc.hi = hi; lc.n_rec = n_rec; lc.items = items; lc.mv = mv;
-  lc.lr_tags = lr_tags; lc.newline = newline;
-  return lc;
 }
 // Columns 1-9 (up to and including the tab before SEQ).  `recs` = the read's records, `hi` = this one.
 template <class S>
 HDN inline void put_head(S &s, const DevIndex &ix, const char *name, int name_len, uint16_t flag,
                          bool unmapped, const Rec *recs, int hi, int n_rec, const Item *items, const MateView &mv) {
   s.put(name, name_len);
-  put_segment(s, line_ctx(ix, flag, unmapped, recs, hi, n_rec, items, mv, false, false), 0, F_HEAD_END);
+  put_fields(s, ix, 0, F_HEAD_END, flag, unmapped, recs, hi, n_rec, items, mv);
 }
 // Everything after QUAL up to (not including) the optional fields / L,R tags / newline.
 template <class S>
 HDN inline void put_tags(S &s, const DevIndex &ix, bool unmapped, const Rec *recs, int hi, int n_rec,
                          const Item *items) {
   const MateView none{0, 0, 0};
-  put_segment(s, line_ctx(ix, 0, unmapped, recs, hi, n_rec, items, none, false, false), F_HEAD_END, F_TAGS_END);
+  put_fields(s, ix, F_HEAD_END, F_TAGS_END, 0, unmapped, recs, hi, n_rec, items, none);
 }
 // mappability_tag's appended tags (after the optional fields): \tL<u>:i:x\tR<u>:i:y for u < 10.
 template <class S>
-HDN inline bool put_lr_tags(S &s, const DevIndex &ix, const Rec *recs, int hi, const Item *items) {
-  const MateView none{0, 0, 0};
-  put_segment(s, line_ctx(ix, 0, false, recs, hi, 0, items, none, true, false), F_TAGS_END, F_LR_END);
+HDN inline bool put_lr_tags(S &s, const DevIndex &ix, const Rec &r, const Item *items) {
+  const int n = r.item_cnt < 10 ? (int)r.item_cnt : 10;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int t = 0; t < 2 * n; ++t) {
+    const Item it = items[r.item_begin + (t >> 1)];            // L/R were looked up once, by k_rec_xe (map_lr)
+    // "\tL<u>:i:" as one packed word
+    const uint64_t lit = (uint64_t)'\t' | ((uint64_t)((t & 1) ? 'R' : 'L') << 8) | ((uint64_t)('0' + (t >> 1)) << 16) |
+                         ((uint64_t)':' << 24) | ((uint64_t)'i' << 32) | ((uint64_t)':' << 40);
+    s.word(lit, 6);
+    put_u64(s, (uint64_t)((t & 1) ? it.R : it.L));
+  }
   return true;
 }
 

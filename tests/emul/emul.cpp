@@ -241,7 +241,7 @@ uint64_t emul_map_batch(void *index, uint64_t n_reads, const uint8_t *names, con
       put_tags(ts, ix, me.unmapped, ro[r].recs.data(), k, me.n_rec, ro[r].items.data());
       sam.append(buf.data(), ts.n);
       if (opt) sam.append((const char *)opt + opt_off[r], (size_t)(opt_off[r + 1] - opt_off[r]));
-      if (tag_map && !me.unmapped) { BufSink ls{buf.data()}; put_lr_tags(ls, ix, ro[r].recs.data(), k, ro[r].items.data()); sam.append(buf.data(), ls.n); }
+      if (tag_map && !me.unmapped) { BufSink ls{buf.data()}; put_lr_tags(ls, ix, ro[r].recs[k], ro[r].items.data()); sam.append(buf.data(), ls.n); }
       sam.push_back('\n');
     }
   }
