@@ -321,6 +321,16 @@ struct CapSink {
 // Byte stream -> HBM at ANY alignment with aligned 8-byte stores: characters are gathered in a register
 // and flushed a word at a time; the partial words at both ends of the region (shared with the
 // neighbouring column, which another kernel writes) are written byte by byte.
+// the partial words at the two ends of a WordSink's region, byte by byte (kept out of line: the sink's `word` is inlined at
+// every formatter call site and this loop would be copied into each)
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+void wordsink_flush_partial(char *w, uint64_t acc, int lo, int fill) {
+  for (int i = lo; i < fill; ++i) w[i] = (char)(acc >> (8 * i));
+}
 struct WordSink {
   char *w;            // aligned address of the word being filled
   uint64_t acc;
@@ -329,7 +339,7 @@ struct WordSink {
   HDN explicit WordSink(char *dst) : w(dst - ((uintptr_t)dst & 7)), acc(0), fill((int)((uintptr_t)dst & 7)), lo(fill), n(0) {}
   HDN void flush() {
     if (lo == 0 && fill == 8) *reinterpret_cast<uint64_t *>(w) = acc;
-    else for (int i = lo; i < fill; ++i) w[i] = (char)(acc >> (8 * i));
+    else wordsink_flush_partial(w, acc, lo, fill);
     w += 8; acc = 0; fill = 0; lo = 0;
   }
   HDN void ch(char c) { acc |= (uint64_t)(uint8_t)c << (8 * fill); ++n; if (++fill == 8) flush(); }
