@@ -305,7 +305,7 @@ struct smash_ctx {
   SearchParams sp{};
   // index storage
   uint8_t *text_alloc = nullptr; void *sa = nullptr; void *isa = nullptr; uint8_t *lcp = nullptr;
-  LcpItem *lcp_m = nullptr; uint8_t *uniq = nullptr; void *seed = nullptr; uint16_t *ext = nullptr; uint64_t *startpos = nullptr;
+  LcpItem *lcp_m = nullptr; uint8_t *uniq = nullptr; void *seed = nullptr; uint32_t *ext = nullptr; uint64_t *startpos = nullptr;
   uint64_t *sizes = nullptr; char *descr = nullptr; int *descr_off = nullptr; uint64_t *descr8 = nullptr; uint32_t *alpha = nullptr;
   uint8_t *mapbody = nullptr; uint32_t *chrom_off32 = nullptr; uint64_t *chrom_abs64 = nullptr;
   uint64_t n_m = 0;
@@ -459,8 +459,8 @@ static int ctx_finish(smash_ctx *c, const smash_index *ix) {
   set_search_params(c);
   d.ext = nullptr;
   if (c->prm.mode != SMASH_MODE_MEM && c->sp.fast_ok && (double)N / pow(4.0, (double)c->sp.k) >= 0.25) {
-    // the 4+4 character pre-filter pays off when chance hits of the seed are common (large references)
-    CK(dmalloc((void **)&c->ext, 2 * N, &c->index_bytes));
+    // the 8+6 character pre-filter pays off when chance hits of the seed are common (large references)
+    CK(dmalloc((void **)&c->ext, 4 * N, &c->index_bytes));
     c->launches += launch_ext_build(d, c->sp.k, c->ext, st);
     d.ext = c->ext;
   }

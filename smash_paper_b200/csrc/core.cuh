@@ -47,7 +47,7 @@ struct DevIndex {
   const void *seed;          // S[x] = #suffixes < k-mer x (monotone, 4^k + 1 entries)
   int seed_k;
   int seed_w;                // 4 or 8 bytes per entry
-  const uint16_t *ext;       // per SA rank i: 2-bit codes of the 4 text chars after SA[i]+k (low byte) and the 4 before SA[i] (high byte)
+  const uint32_t *ext;       // per SA rank i: 2-bit codes of the 6 text chars after SA[i]+k, the 8 before SA[i], and how many of those are acgt (ext_entry)
   uint32_t alpha[8];         // bitmap of byte values present in text
   // Sequence metadata (fasta.h:24-42)
   const uint64_t *startpos;  // n_descr
@@ -249,36 +249,59 @@ HD bool kmer_invalid(const uint32_t *inv, int x, int k) {
   if (sh) m |= inv[wd + 1] << (32 - sh);
   return (m & ((k >= 32 ? 0u : (1u << k)) - 1u)) != 0;
 }
-// ---- 4+4 character pre-filter -----------------------------------------------------------------------
-// ext[i] holds the 2-bit codes of T[SA[i]+k .. +k+4) (low byte) and of T[SA[i]-4 .. SA[i]) (high byte), both in TEXT
-// order with the first char in the top bits; non-acgt / out-of-text chars are stored as code 0.  A candidate whose
-// k-mer matches can only reach length L if enough of these agree with the read, so most chance hits of the seed are
-// dismissed from ONE coalesced 2-byte load per bucket entry, before the SA entry and the text are touched.  The test
-// is conservative: codes of non-acgt bytes may agree by accident (=> the candidate is merely verified on the text),
-// but a disagreement of codes is always a true mismatch on the fast path.
-HD uint32_t lead_pairs8(uint32_t x) {      // number of leading equal 2-bit groups of an 8-bit xor (0..4)
+// ---- 8+6 character pre-filter ------------------------------------------------------------------------
+// ext[i] (32 bits) describes the text around the suffix c = SA[i] in 2-bit codes (a,c,g,t -> 0..3, anything else -> 0):
+//   bits  0..11  the 6 characters after the k-mer, T[c+k .. c+k+6), first one in the top bits;
+//   bits 12..27  the 8 characters before it, T[c-8 .. c), in text order (T[c-1] in bits 13:12);
+//   bits 28..31  lv: how many of the characters immediately before c are acgt (0..8; stops at the first other byte or at
+//                the start of the text).
+// One coalesced 4-byte load per bucket entry therefore tells, before the SA entry or the text is touched,
+//   * whether the candidate can reach length L at all (most chance hits of the seed end here), and
+//   * its LEFT extension exactly whenever that is shorter than 8 -- i.e. whether an earlier anchor owns this diagonal
+//     (left >= stride) -- because within the lv valid characters equal codes are equal bytes, and beyond them the text
+//     holds a byte no anchor-path read can match.
+// The right-hand codes are only an upper bound (codes of other bytes may agree by accident): a pass is verified on the text.
+HD uint32_t ext_entry(const uint8_t *T, uint64_t N, uint64_t c, int k) {
+  uint32_t r = 0, l = 0, lv = 0; bool open = true;
+  for (int j = 0; j < 6; ++j) {
+    const uint64_t pr = c + (uint64_t)k + (uint64_t)j;
+    const int br = pr < N ? base_code(T[pr]) : 4;
+    r = (r << 2) | (uint32_t)(br > 3 ? 0 : br);
+  }
+  for (int j = 1; j <= 8; ++j) {                               // T[c-1], T[c-2], ..
+    const int bl = c >= (uint64_t)j ? base_code(T[c - (uint64_t)j]) : 4;
+    l |= (uint32_t)(bl > 3 ? 0 : bl) << (2 * (j - 1));
+    if (bl > 3) open = false;
+    if (open) ++lv;
+  }
+  return r | (l << 12) | (lv << 28);
+}
+HD uint32_t ext_right_pairs(uint32_t x12) {   // leading equal 2-bit groups of a 12-bit xor (0..6)
 #if defined(__CUDA_ARCH__)
-  return x ? (uint32_t)(__clz((int)x) - 24) >> 1 : 4u;
+  return x12 ? (uint32_t)(__clz((int)x12) - 20) >> 1 : 6u;
 #else
-  return x ? (uint32_t)(__builtin_clz(x) - 24) >> 1 : 4u;
+  return x12 ? (uint32_t)(__builtin_clz(x12) - 20) >> 1 : 6u;
 #endif
 }
-HD uint32_t trail_pairs8(uint32_t x) {     // number of trailing equal 2-bit groups of an 8-bit xor (0..4)
+HD uint32_t ext_left_pairs(uint32_t x16) {    // trailing equal 2-bit groups of a 16-bit xor (0..8)
 #if defined(__CUDA_ARCH__)
-  return x ? (uint32_t)(__ffs((int)x) - 1) >> 1 : 4u;
+  return x16 ? (uint32_t)(__ffs((int)x16) - 1) >> 1 : 8u;
 #else
-  return x ? (uint32_t)__builtin_ctz(x) >> 1 : 4u;
+  return x16 ? (uint32_t)__builtin_ctz(x16) >> 1 : 8u;
 #endif
 }
+// the read's side of the comparison, from the staged bytes: P[x-8 .. x) and P[x+k .. x+k+6) (lv bits zero)
 HD uint32_t read_ext_codes(const uint8_t *P, int x, int k) {
-  const uint64_t r = read8(P, x + k), l = read8(P, x - 4);
-  return code4((uint32_t)r) | (code4((uint32_t)l) << 8);      // bytes P[x-4..x) in read order
+  const uint64_t r = read8(P, x + k), l = read8(P, x - 8);
+  const uint32_t r12 = (code4((uint32_t)r) << 4) | (code4((uint32_t)(r >> 32)) >> 4);
+  const uint32_t l16 = (code4((uint32_t)l) << 8) | code4((uint32_t)(l >> 32));      // P[x-8] in the top bits
+  return r12 | (l16 << 12);
 }
-// can a candidate with these ext codes still reach length L?
+// conservative form (no validity information about the read): can a candidate with these codes still reach length L?
 HD bool ext_may_reach(uint32_t cand_ext, uint32_t read_ext, int k, uint32_t L) {
   const uint32_t x = cand_ext ^ read_ext;
-  const uint32_t r4 = lead_pairs8(x & 0xffu), l4 = trail_pairs8(x >> 8);   // right: from the char after the k-mer; left: from the char before it
-  return r4 == 4 || l4 == 4 || (uint32_t)k + r4 + l4 >= L;
+  const uint32_t r = ext_right_pairs(x & 0xfffu), l = ext_left_pairs((x >> 12) & 0xffffu);
+  return r == 6 || l == 8 || (uint32_t)k + r + l >= L;
 }
 
 // seed bucket of anchor x: [lo, hi) in SA order (a sorted superset of the k-mer's interval)

@@ -92,21 +92,11 @@ __global__ void k_seed_build(DevIndex ix, SeedT *__restrict__ seed, int k) {
   }
 }
 
-__global__ void k_ext_build(DevIndex ix, int k, uint16_t *__restrict__ ext) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ix.N; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t c = sa_at(ix, i);
-    uint32_t r = 0, l = 0;
-    for (int j = 0; j < 4; ++j) {
-      const uint64_t pr = c + (uint64_t)k + (uint64_t)j;
-      const int br = pr < ix.N ? base_code(ix.text[pr]) : 4;
-      r = (r << 2) | (uint32_t)(br > 3 ? 0 : br);
-      const int bl = c >= (uint64_t)(4 - j) ? base_code(ix.text[c - (uint64_t)(4 - j)]) : 4;      // T[c-4], T[c-3], T[c-2], T[c-1]
-      l = (l << 2) | (uint32_t)(bl > 3 ? 0 : bl);
-    }
-    ext[i] = (uint16_t)(r | (l << 8));
-  }
+__global__ void k_ext_build(DevIndex ix, int k, uint32_t *__restrict__ ext) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ix.N; i += (uint64_t)gridDim.x * blockDim.x)
+    ext[i] = ext_entry(ix.text, ix.N, sa_at(ix, i), k);
 }
-int launch_ext_build(const DevIndex &ix, int k, uint16_t *ext, cudaStream_t st) {
+int launch_ext_build(const DevIndex &ix, int k, uint32_t *ext, cudaStream_t st) {
   k_ext_build<<<sm_count() * 8, 256, 0, st>>>(ix, k, ext);
   return 1;
 }
@@ -213,13 +203,13 @@ __device__ __forceinline__ void run_tasks(const DevIndex &ix, SearchSmem &sm, in
     bool pass = false;
     if (t < ntask) {
       i = sm.task_sa[warp][t]; x = (int)sm.task_x[warp][t];
-      pass = !ix.ext || ext_may_reach(ix.ext[i], read_ext_codes(P, x, sp.k), sp.k, sp.L);   // 2-byte pre-filter
+      pass = !ix.ext || ext_may_reach(ix.ext[i], read_ext_codes(P, x, sp.k), sp.k, sp.L);   // 4-byte pre-filter (conservative form)
     }
     if (w.surv) {
       const unsigned mask = __ballot_sync(0xffffffffu, pass);
       const int np = __popc(mask);
       if (nsurv + np <= SURV_CAP) {
-        if (pass) w.surv[read * SURV_CAP + nsurv + __popc(mask & ((1u << lane) - 1u))] = ((uint64_t)x << 48) | i;
+        if (pass) w.surv[read * SURV_CAP + nsurv + __popc(mask & ((1u << lane) - 1u))] = ((uint64_t)x << 48) | (8ull << 40) | i;   // left extension not known here
         nsurv += np;
         continue;
       }
@@ -536,15 +526,24 @@ k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
       const int n_anchor = (q - L + s - 1) / s + 1;          // anchors x = a*s cover starts 0..q-L
       for (int a0 = 0; a0 < n_anchor && !slow; a0 += 32) {
         const int a = a0 + lane, x = a * s;
-        uint64_t lo = 0; int cnt = 0; uint32_t rext = 0;
+        uint64_t lo = 0; int cnt = 0; uint32_t rext = 0, lvr = 0;
         if (a < n_anchor && !kmer_invalid(inv, x + mis, k)) {
-          // (1) window = bases x-4 .. x+k+4 of the read
-          const int xb = x + mis + 4 * CODE_PAD - 4;           // stream position of base x-4
+          // (1) two windows of the 2-bit stream: bases x-8 .. x+k (8 before the k-mer + the k-mer), bases x+k .. x+k+6
+          const int xb = x + mis + 4 * CODE_PAD - 8;           // stream position of base x-8
           const uint64_t win = code_window(code, xb >> 2) << (2 * (xb & 3));
-          const uint32_t lcode = (uint32_t)(win >> 56);
-          const uint64_t kc = (win >> (56 - 2 * k)) & ((1ull << (2 * k)) - 1ull);
-          const uint32_t rcode = (uint32_t)(win >> (48 - 2 * k)) & 0xffu;
-          rext = rcode | (lcode << 8);
+          const uint32_t lcode = (uint32_t)(win >> 48);        // base x-8 in the top bits
+          const uint64_t kc = (win >> (48 - 2 * k)) & ((1ull << (2 * k)) - 1ull);
+          const int xr = xb + 8 + k;
+          const uint32_t rcode = (uint32_t)((code_window(code, xr >> 2) << (2 * (xr & 3))) >> 52);   // 6 bases after the k-mer
+          rext = rcode | (lcode << 12);
+          // how many read bases immediately left of x are acgt (0..8; bases before the read's start are not)
+          {
+            const int p = x + mis;                             // mask bit of base x (buffer coordinates)
+            uint32_t m8;
+            if (p >= 8) { const int q0 = p - 8, wd = q0 >> 5, sh = q0 & 31; uint32_t m = inv[wd] >> sh; if (sh > 24) m |= inv[wd + 1] << (32 - sh); m8 = m & 0xffu; }
+            else m8 = ((inv[0] << (8 - p)) | ((1u << (8 - p)) - 1u)) & 0xffu;
+            lvr = m8 ? (uint32_t)__clz((int)(m8 << 24)) : 8u;  // bit 7 = base x-1
+          }
           // (2) seed bucket (a sorted superset of the k-mer's suffix-array interval)
           const int shk = 2 * (ix.seed_k - k);
           lo = seed_at(ix, kc << shk);
@@ -552,19 +551,27 @@ k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
           cnt = (int)(hi - lo < (uint64_t)(BIG_BUCKET + 1) ? hi - lo : (uint64_t)(BIG_BUCKET + 1));
         }
         if (__any_sync(0xffffffffu, cnt > BIG_BUCKET)) { slow = true; break; }
-        // (3) ext filter on the bucket entries; survivors parked in (entry, lane) order
+        // (3) ext filter on the bucket entries: reach test + EXACT left extension (ownership); survivors parked in
+        // (entry, lane) order with their left extension
         for (int j0 = 0; !slow && __any_sync(0xffffffffu, j0 < cnt); j0 += 4) {
           uint32_t e[4];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) e[t] = j0 + t < cnt ? (uint32_t)__ldg(ix.ext + lo + (uint64_t)(j0 + t)) : 0u;
+          for (int t = 0; t < 4; ++t) e[t] = j0 + t < cnt ? __ldg(ix.ext + lo + (uint64_t)(j0 + t)) : 0u;
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            const bool pass = j0 + t < cnt && ext_may_reach(e[t], rext, k, sp.L);
+            bool pass = false; uint32_t left = 0;
+            if (j0 + t < cnt) {
+              const uint32_t xo = e[t] ^ rext;
+              const uint32_t r6 = ext_right_pairs(xo & 0xfffu), lm = ext_left_pairs((xo >> 12) & 0xffffu);
+              const uint32_t lvt = e[t] >> 28, v = lvt < lvr ? lvt : lvr;
+              left = lm < v ? lm : v;                          // exact when < 8: a mismatch, or a byte nothing here can match
+              pass = left == 8 ? s > 8 : ((int)left < s && (r6 == 6 || (uint32_t)k + left + r6 >= sp.L));
+            }
             const unsigned mask = __ballot_sync(0xffffffffu, pass);
             if (!mask) continue;
             const int np = __popc(mask);
             if (nsurv + np > SURV_CAP) { slow = true; break; }
-            if (pass) w.surv[read * SURV_CAP + nsurv + __popc(mask & ((1u << lane) - 1u))] = ((uint64_t)x << 48) | (lo + (uint64_t)(j0 + t));
+            if (pass) w.surv[read * SURV_CAP + nsurv + __popc(mask & ((1u << lane) - 1u))] = ((uint64_t)x << 48) | ((uint64_t)left << 40) | (lo + (uint64_t)(j0 + t));
             nsurv += np;
           }
         }
@@ -608,8 +615,9 @@ k_mam_verify(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
     if (lane < nsv) {
       const uint64_t e = w.surv[read * SURV_CAP + lane];
       x = (int)(e >> 48);
-      c = sa_at(ix, e & 0xffffffffffffull);
-      left = match_left(T, (int64_t)c, P, x, sp.s);
+      c = sa_at(ix, e & 0xffffffffffull);
+      left = (int)((e >> 40) & 0xffu);                         // from the ext code: exact below 8 (k_mam_seed parks owners only)
+      if (left >= 8) left = match_left(T, (int64_t)c, P, x, sp.s);
       own = left < sp.s;
     }
     const unsigned om = __ballot_sync(0xffffffffu, own);

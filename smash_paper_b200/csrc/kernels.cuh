@@ -42,7 +42,7 @@ struct WorkDev {
   uint32_t *flags;             // N_FLAGS counters
   // split search (K1a/K1b): candidates that pass the seed + 4+4 filters are parked per read and verified
   // by k_mam_verify with lanes = candidates of ONE read (null => verification inside k_mam_search)
-  uint64_t *surv;              // n_reads * SURV_CAP: anchor offset << 48 | SA index
+  uint64_t *surv;              // n_reads * SURV_CAP: anchor offset << 48 | left extension (0..7 exact, 8 = at least 8) << 40 | SA index
   uint8_t *surv_cnt;           // n_reads
   uint8_t *slow;               // n_reads: 1 = k_mam_seed left the read to k_mam_search (null => k_mam_search takes every read)
   uint8_t *lc;                 // lower-cased reads with the 16-byte pads of the staging buffer: read r at seq_off[r] + 32 r + 16
@@ -79,7 +79,7 @@ struct SearchParams {
 // launchers (all asynchronous on `st`); each returns the number of kernels it launched
 int launch_uniq_build(const DevIndex &ix, uint8_t *uniq, cudaStream_t st);
 int launch_seed_build(const DevIndex &ix, void *seed, int k, int seed_w, cudaStream_t st);
-int launch_ext_build(const DevIndex &ix, int k, uint16_t *ext, cudaStream_t st);
+int launch_ext_build(const DevIndex &ix, int k, uint32_t *ext, cudaStream_t st);
 int launch_alpha(const uint8_t *text, uint64_t N, uint32_t *alpha8, cudaStream_t st);
 int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
 int launch_mam_verify(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);

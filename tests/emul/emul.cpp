@@ -25,7 +25,7 @@ struct EmulIndex {
   std::string descr;
   std::vector<uint32_t> off32;
   std::vector<uint8_t> mapbody;
-  std::vector<uint16_t> ext;
+  std::vector<uint32_t> ext;
   std::vector<uint64_t> descr8;
 };
 
@@ -92,21 +92,9 @@ void *emul_index_create(const uint8_t *text, uint64_t N, const void *sa, const v
   e->off32.push_back(acc);
   d.chrom_off32 = e->off32.data();
   {
-    // 4+4 character pre-filter codes, mirrors k_ext_build (built for k = min(seed_k, 20): the tests use min_len >= 12)
-    const int kk = d.seed_k;
+    // 8+6 character pre-filter codes (core.cuh ext_entry, what k_ext_build stores)
     e->ext.assign(N, 0);
-    for (uint64_t i = 0; i < N; ++i) {
-      const uint64_t c = sa_at(d, i);
-      uint32_t r = 0, l = 0;
-      for (int j = 0; j < 4; ++j) {
-        const uint64_t pr = c + (uint64_t)kk + (uint64_t)j;
-        const int br = pr < N ? base_code(text[pr]) : 4;
-        r = (r << 2) | (uint32_t)(br > 3 ? 0 : br);
-        const int bl = c >= (uint64_t)(4 - j) ? base_code(text[c - (uint64_t)(4 - j)]) : 4;
-        l = (l << 2) | (uint32_t)(bl > 3 ? 0 : bl);
-      }
-      e->ext[i] = (uint16_t)(r | (l << 8));
-    }
+    for (uint64_t i = 0; i < N; ++i) e->ext[i] = ext_entry(text, N, sa_at(d, i), d.seed_k);
   }
   d.ext = e->ext.data();
   if (mapbody && map_bytes) { e->mapbody.assign(mapbody, mapbody + map_bytes); d.mapbody = e->mapbody.data(); d.map_bytes = map_bytes; }
