@@ -586,102 +586,104 @@ k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
   }
 }
 
-// K1b: verification of the parked candidates.  One warp per read, lanes = its candidates: the SA
-// entries of all of them are fetched at once, then the text words left of the seed (ownership), then
-// the right extensions and the U bytes of the few that own their diagonal.  The matches join the ones
-// k_mam_search found on its exact paths, get rank-sorted by query offset and written in order.
-struct VerifySmem {
-  Match stage[WARPS][STAGE_CAP];
-  uint64_t own_c[WARPS][SURV_CAP];             // candidates that own their diagonal: suffix position,
-  uint32_t own_xl[WARPS][SURV_CAP];            // anchor offset << 16 | left extension
-};
+// K1b: verification of the parked candidates.  k_mam_seed parks only candidates that OWN their diagonal, with the
+// left extension it read off the ext code, so a read is left with a handful of them: 8 lanes per read, four reads per
+// warp.  Lane = candidate: SA entry, the right extension along the diagonal (8-byte compares of the text against the
+// lower-cased read copy in HBM), one byte of U.  The matches join the ones k_mam_search found on its exact paths, get
+// rank-sorted by query offset (copies dropped, see emit_ranked) and are written in order.
+constexpr int VG = 4;                                          // reads per warp
+struct VerifySmem { Match stage[WARPS][VG][STAGE_CAP]; };
+// emit_ranked for an 8-lane group (sl = lane & 7, the group's lanes are bits gshift..gshift+7 of a ballot); every lane of
+// the warp must call it (groups without work pass ns = 0)
+__device__ __forceinline__ int emit_ranked_group(const Match *stage, int ns, Match *dst, int cap, int sl, int gshift) {
+  static_assert(STAGE_CAP <= 64, "one 64-bit mask covers the stage");
+  uint64_t first = 0;                                          // bit e: entry e is the first with its query offset
+  for (int j = 0; __any_sync(0xffffffffu, 8 * j < ns); ++j) {
+    const int e = 8 * j + sl;
+    bool fst = false;
+    if (e < ns) {
+      fst = true;
+      const uint32_t qp = stage[e].qpos;
+      for (int f = 0; f < e; ++f) if (stage[f].qpos == qp) { fst = false; break; }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, fst);
+    first |= (uint64_t)((bal >> gshift) & 0xffu) << (8 * j);
+  }
+  for (int e = sl; e < ns; e += 8) {
+    if (!((first >> e) & 1ull)) continue;
+    const Match me = stage[e];
+    int rank = 0;
+    for (int f = 0; f < ns; ++f) rank += (((first >> f) & 1ull) && stage[f].qpos < me.qpos) ? 1 : 0;
+    if (rank < cap) dst[rank] = me;
+  }
+  return __popcll(first);
+}
 #ifndef SMASH_VERIFY_MINBLK
-#define SMASH_VERIFY_MINBLK 8
+#define SMASH_VERIFY_MINBLK 6
 #endif
 __global__ void __launch_bounds__(THREADS, SMASH_VERIFY_MINBLK)
 k_mam_verify(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
   __shared__ __align__(16) VerifySmem sm;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 3, sl = lane & 7, gshift = 8 * g;
   const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
   const uint8_t *T = ix.text;
-  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
-    const int nsv = (int)w.surv_cnt[read];
-    if (nsv == 0) continue;                                  // k_mam_search finished this read
-    const int64_t so = b.seq_off[read];
-    const int q = (int)(b.seq_off[read + 1] - so);
-    const uint8_t *P = w.lc + so + 32 * read + 16;
-    // (A) lanes = parked candidates: SA entry, ownership (left extension shorter than the stride)
-    bool own = false; uint64_t c = 0; int x = 0, left = 0;
-    if (lane < nsv) {
-      const uint64_t e = w.surv[read * SURV_CAP + lane];
-      x = (int)(e >> 48);
-      c = sa_at(ix, e & 0xffffffffffull);
-      left = (int)((e >> 40) & 0xffu);                         // from the ext code: exact below 8 (k_mam_seed parks owners only)
-      if (left >= 8) left = match_left(T, (int64_t)c, P, x, sp.s);
-      own = left < sp.s;
+  Match *stage = sm.stage[warp][g];
+  for (uint64_t r0 = ((uint64_t)blockIdx.x * WARPS + warp) * VG; r0 < b.n_reads; r0 += warps_total * VG) {
+    const uint64_t read = r0 + (uint64_t)g;
+    const int nsv = read < b.n_reads ? (int)w.surv_cnt[read] : 0;        // 0: k_mam_search finished this read (or none)
+    if (!__any_sync(0xffffffffu, nsv > 0)) continue;
+    int64_t so = 0; int q = 0; const uint8_t *P = nullptr; Match *dst = nullptr;
+    int n_e_true = 0, n_e = 0;
+    if (nsv) {
+      so = b.seq_off[read];
+      q = (int)(b.seq_off[read + 1] - so);
+      P = w.lc + so + 32 * read + 16;
+      dst = w.match_slots + slot_base(w, read);
+      n_e_true = (int)w.match_cnt[read];                     // found by k_mam_search's exact paths (already in the slots)
+      n_e = n_e_true < w.cap ? n_e_true : w.cap;
+      if (n_e > STAGE_CAP) n_e = STAGE_CAP;
+      for (int e = sl; e < n_e; e += 8) stage[e] = dst[e];
     }
-    const unsigned om = __ballot_sync(0xffffffffu, own);
-    const int n_own = __popc(om);
-    if (own) { const int pos = __popc(om & ((1u << lane) - 1u)); sm.own_c[warp][pos] = c; sm.own_xl[warp][pos] = ((uint32_t)x << 16) | (uint32_t)left; }
-    const int n_e_true = (int)w.match_cnt[read];             // found by k_mam_search's exact paths (already in the slots)
-    int n_e = n_e_true < w.cap ? n_e_true : w.cap;
-    if (n_e > STAGE_CAP) n_e = STAGE_CAP;
-    Match *dst = w.match_slots + slot_base(w, read);
-    for (int e = lane; e < n_e; e += 32) sm.stage[warp][e] = dst[e];
-    __syncwarp();
-    // (B) 4 lanes per owning candidate, 8 candidates per pass: lane t of a group compares the words
-    // t, t+4, t+8, .. of the diagonal to the right of the anchor; the group's first mismatch wins
     int n_new = 0;
-    const int g = lane >> 2, t = lane & 3;
-    for (int base = 0; base < n_own; base += 8) {
-      const bool have = base + g < n_own;
-      uint64_t cc = 0; int cx = 0, cl = 0;
-      if (have) { cc = sm.own_c[warp][base + g]; const uint32_t xl = sm.own_xl[warp][base + g]; cx = (int)(xl >> 16); cl = (int)(xl & 0xffffu); }
-      const int limit = q - cx;
-      int right = limit;                                      // stays `limit` when the read ends first
-      bool open = have;
-      for (int off = 8 * t; __any_sync(0xffffffffu, open); off += 32) {
-        int mm = 0x7fffffff;
-        if (open && off < limit) {
-          const uint64_t d = text8(T, (int64_t)cc + off) ^ read8(P, cx + off);
-          if (d) mm = off + (ctz64(d) >> 3);
-        }
-        const int o1 = __shfl_xor_sync(0xffffffffu, mm, 1); mm = o1 < mm ? o1 : mm;
-        const int o2 = __shfl_xor_sync(0xffffffffu, mm, 2); mm = o2 < mm ? o2 : mm;
-        if (open) {
-          if (mm != 0x7fffffff) { right = mm < limit ? mm : limit; open = false; }
-          else if (off - 8 * t + 32 >= limit) open = false;   // the whole group ran past the end of the read
-        }
-      }
-      // group leaders finish the candidate (candidate_check, core.cuh)
+    for (int base = 0; __any_sync(0xffffffffu, base < nsv); base += 8) {
+      const int idx = base + sl;
       Match m; int r = 0;
-      if (have && t == 0 && right >= sp.k) {
-        const uint32_t len = (uint32_t)(cl + right);
-        if (len >= sp.L && len >= 2) {
-          const uint64_t ref = cc - (uint64_t)cl;
-          const uint8_t u = ix.uniq[ref];
-          if (u == 255 && len >= 255) r = exact_start(ix, P, q, cx - cl, sp.L, &m) ? 1 : 0;
-          else if (len >= u) { m.ref = ref; m.qpos = (uint32_t)(cx - cl); m.len = len; r = 1; }
+      if (idx < nsv) {
+        const uint64_t e = w.surv[read * SURV_CAP + idx];
+        const int x = (int)(e >> 48);
+        const uint64_t c = sa_at(ix, e & 0xffffffffffull);
+        int left = (int)((e >> 40) & 0xffu);                 // from the ext code: exact below 8
+        if (left >= 8) left = match_left(T, (int64_t)c, P, x, sp.s);
+        if (left < sp.s) {                                   // this anchor owns the diagonal (candidate_check, core.cuh)
+          const int right = match_right(T, (int64_t)c, P, x, q - x);
+          const uint32_t len = (uint32_t)(left + right);
+          if (right >= sp.k && len >= sp.L && len >= 2) {
+            const uint64_t ref = c - (uint64_t)left;
+            const uint8_t u = ix.uniq[ref];
+            if (u == 255 && len >= 255) r = exact_start(ix, P, q, x - left, sp.L, &m) ? 1 : 0;
+            else if (len >= u) { m.ref = ref; m.qpos = (uint32_t)(x - left); m.len = len; r = 1; }
+          }
         }
       }
-      const unsigned pass = __ballot_sync(0xffffffffu, r > 0);
-      if (r > 0) { const int pos = n_e + n_new + __popc(pass & ((1u << lane) - 1u)); if (pos < STAGE_CAP) sm.stage[warp][pos] = m; }
+      const unsigned pass = (__ballot_sync(0xffffffffu, r > 0) >> gshift) & 0xffu;
+      if (r > 0) { const int pos = n_e + n_new + __popc(pass & ((1u << sl) - 1u)); if (pos < STAGE_CAP) stage[pos] = m; }
       n_new += __popc(pass);
     }
     __syncwarp();
     const int n_raw = n_e_true + n_new;
     const int ns = n_e + n_new < STAGE_CAP ? n_e + n_new : STAGE_CAP;
-    const int nu = emit_ranked(sm.stage[warp], ns, dst, w.cap, lane);
+    const int nu = emit_ranked_group(stage, ns, dst, w.cap, sl, gshift);
     const int n = nu + (n_raw - ns);                                    // distinct matches (+ what did not fit the stage)
     int n_out = n;
-    if (sp.mum && n <= w.cap && n <= STAGE_CAP) {
+    if (sp.mum) {                                                       // -mum: cleanMUMcand sweep on the ordered list
       __syncwarp();
-      for (int e = lane; e < nu; e += 32) sm.stage[warp][e] = dst[e];
+      const bool sweep = nsv && n <= w.cap && n <= STAGE_CAP;
+      if (sweep) for (int e = sl; e < nu; e += 8) stage[e] = dst[e];
       __syncwarp();
-      if (lane == 0) { uint16_t ord[STAGE_CAP]; n_out = mum_clean(sm.stage[warp], nu, ord, dst); }
-      n_out = __shfl_sync(0xffffffffu, n_out, 0);
+      if (sweep && sl == 0) { uint16_t ord[STAGE_CAP]; n_out = mum_clean(stage, nu, ord, dst); }
     }
-    if (lane == 0) {
+    if (nsv && sl == 0) {
       w.match_cnt[read] = (uint32_t)n_out;
       // more staged entries than the stage holds (copies of a saturated repeat family included): the dropped ones may
       // have been distinct matches, so this is always an overflow, never a silent count
@@ -758,7 +760,7 @@ int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, c
 int launch_mam_verify(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
   if (!b.n_reads) return 0;
   int nl = 0;
-  if (w.surv) { k_mam_verify<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p); ++nl; }
+  if (w.surv) { k_mam_verify<<<grid_for_warps((b.n_reads + VG - 1) / VG, SMASH_VERIFY_MINBLK), THREADS, 0, st>>>(ix, b, w, p); ++nl; }
   if (w.long_q > MAXQ_FAST) { k_mam_search_long<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p); ++nl; }
   return nl;
 }
