@@ -208,13 +208,22 @@ def run_ours(args, wl, rank, world):
     counts_t = torch.zeros(len(starts), dtype=torch.int64, device=f"cuda:{dev}")
     from smash_paper_b200 import multigpu
     backend = multigpu.ContextBackend(ctx, rank * args.steps * pairs_per_batch, torch.device("cuda", dev))
+    torch_tail = bool(os.environ.get("SMASH_TORCH_TAIL"))       # A/B: round 1's exchange in torch.distributed (multigpu.py)
+    if dist and not torch_tail:
+        # NCCL behind the C ABI (csrc/comm.cu): rank 0's unique id goes round through the job's rendezvous store
+        uid = [api.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init_rank(rank, world, uid[0])
 
     def finish():
-        """smashMEM dedupe + varbin over everything accumulated; across ranks: fingerprint all_gather, shard-edge
-        all_gather and ONE all_reduce of the per-bin counts (multigpu.py) -- exact, not per-shard."""
+        """smashMEM dedupe + varbin over everything accumulated; across ranks smash_bins_finish: hash-partitioned
+        exchange of the dupe fingerprints (two all-to-alls, resolved on the device), all-gather of the shard edges and
+        ONE ncclAllReduce of the per-bin counts -- exact, not per-shard."""
+        if dist and torch_tail:
+            return multigpu.sharded_tail_finish(backend, dist, rank, world)
         if dist:
-            c, st_ = multigpu.sharded_tail_finish(backend, dist, rank, world)
-            return c, st_
+            _, st_ = ctx.bins_finish(ordinal_base=rank << 40, counts_device_ptr=counts_t.data_ptr())
+            return counts_t, st_
         c, st_ = ctx.tail_finish(counts_t.data_ptr())
         return counts_t, st_
 
@@ -358,7 +367,7 @@ def run_ours(args, wl, rank, world):
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": args.workload_desc, "reads_per_step_per_gpu": B, "read_len": wl["read_len"],
                        "min_len": wl["min_len"], "text_len": int(n_text), "n_bins": int(len(starts)),
-                       "index": "built on GPU, replicated per GPU", "sharding": f"reads x{world} (contiguous pair ranges, index replicated); tail exact across shards: all_gather of dupe fingerprints + shard edges, 1 all_reduce of bin counts",
+                       "index": "built on GPU, replicated per GPU", "sharding": f"reads x{world} (contiguous pair ranges, index replicated); tail exact across shards inside smash_bins_finish (C ABI, NCCL): partitioned exchange of dupe fingerprints, all-gather of shard edges, 1 ncclAllReduce of bin counts",
                        "l2": "inputs (index touches, 1.7 KB/read SAM) far larger than L2; distinct batch per step",
                        "timing": "sum of per-step CUDA-event durations with the batch resident + tail_finish/allreduce; max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // max(args.steps, 1),

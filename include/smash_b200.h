@@ -245,6 +245,24 @@ int smash_tail_phase_a_verdict(smash_ctx *ctx, uint64_t ordinal_base, const void
                                smash_tail_edge *edge);
 int smash_tail_phase_b(smash_ctx *ctx, int has_prev, int64_t prev_last_pos, int64_t *counts, void *counts_device,
                        smash_tail_stats *st);
+/* ---- the same protocol behind ONE call, with NCCL moving the data (csrc/comm.cu): this is the "smash_bins_finish
+ * (includes the allreduce)" of the survey's boundary.  One communicator rank per context.
+ *  - one process per GPU: rank 0 calls smash_comm_unique_id, the host program distributes the 128 bytes (MPI, torchrun's
+ *    store, a file ..), every rank calls smash_comm_init_rank;
+ *  - one process driving n GPUs (bin/mummer -gpus n): smash_comm_init_all over its n contexts, then one host thread per
+ *    context.
+ * smash_bins_finish is collective: every rank calls it after collecting its batches.  Rank r must have mapped a
+ * contiguous range of the name-ordered read pairs and passes an ordinal_base >= the previous rank's base + pair count
+ * (r * 2^40 will do).  The first-wins duplicate rule is resolved on the device by a hash-partitioned exchange of the
+ * dupe-set fingerprints (two all-to-alls), the adjacent-duplicate rule by an all-gather of the shard edges, and the
+ * n_bins int64 counts (+ stats) are summed by a single ncclAllReduce: every rank receives the GLOBAL counts and stats.
+ * Without a communicator it is smash_tail_finish.  NCCL is bound at run time (libnccl.so.2, or SMASH_NCCL_LIB). */
+int smash_comm_unique_id(void *id128, size_t cap);
+int smash_comm_init_rank(smash_ctx *ctx, int rank, int world, const void *id128);
+int smash_comm_init_all(smash_ctx *const *ctxs, int n);
+int smash_comm_destroy(smash_ctx *ctx);
+int smash_comm_rank(const smash_ctx *ctx, int *rank, int *world);
+int smash_bins_finish(smash_ctx *ctx, uint64_t ordinal_base, int64_t *counts, void *counts_device, smash_tail_stats *st);
 /* positions.txt rows produced so far by smash_tail_finish: chromosome index (into the forward
  * sequences) and 0-based position, in output order. */
 int smash_tail_positions(smash_ctx *ctx, const int32_t **chrom, const int64_t **pos, uint64_t *n);

@@ -448,6 +448,24 @@ class Context:
                                                  C.c_void_p(counts_device_ptr) if counts_device_ptr else None, C.byref(st)))
         return counts, {k: int(getattr(st, k)) for k, _ in _TailStats._fields_}
 
+    # -- NCCL behind the ABI (csrc/comm.cu) -------------------------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        buf = C.create_string_buffer(128)
+        _check(load_library().smash_comm_unique_id(buf, C.c_size_t(128)))
+        return buf.raw
+
+    def comm_init_rank(self, rank, world, unique_id: bytes):
+        _check(load_library().smash_comm_init_rank(self.h, int(rank), int(world), C.c_char_p(unique_id)))
+
+    def bins_finish(self, ordinal_base=0, counts_device_ptr=None):
+        """Collective: global bin counts + stats on every rank (partitioned dedupe exchange + ONE ncclAllReduce)."""
+        counts = np.zeros(self.n_bins, dtype=np.int64)
+        st = _TailStats()
+        _check(load_library().smash_bins_finish(self.h, C.c_uint64(ordinal_base), _ptr(counts),
+                                                C.c_void_p(counts_device_ptr) if counts_device_ptr else None, C.byref(st)))
+        return counts, {k: int(getattr(st, k)) for k, _ in _TailStats._fields_}
+
     def tail_reserve(self, max_pairs, max_hits):
         _check(load_library().smash_tail_reserve(self.h, C.c_uint64(max_pairs), C.c_uint64(max_hits)))
 

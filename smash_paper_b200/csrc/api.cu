@@ -27,6 +27,7 @@
 #include "sabuild.cuh"
 #include "ingest_launch.cuh"
 #include "expand.h"
+#include "ctx_internal.h"
 
 using namespace smash;
 
@@ -315,6 +316,7 @@ struct smash_ctx {
   uint64_t launches = 0, io_h2d = 0, io_d2h = 0;
   int transport = 0;                                // 0: per read range, whichever is faster; 1: full SAM text over PCIe; 2: compact only
   int host_threads = 0;                             // expansion threads (0 = auto)
+  void *comm = nullptr;                              // multi-GPU state (comm.cu)
   HostPool pool;
   // transport scheduler: when the download stream and the line-building threads are expected to be free [host clock, ms],
   // the measured rate of each; a read range takes whichever way gets its lines into host memory first
@@ -844,6 +846,7 @@ extern "C" void smash_ctx_destroy(smash_ctx *c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   host_threads_stop(c);
+  smash_comm_destroy(c);
   for (int s = 0; s < SMASH_N_SLOTS; ++s) slot_release(c->slot[s]);
   tail_release(&c->tail);
   void *ptrs[] = {c->descr8, c->ext, c->text_alloc, c->sa, c->isa, c->lcp, c->lcp_m, c->uniq, c->seed, c->startpos, c->sizes,
@@ -1627,6 +1630,19 @@ static int require_idle(smash_ctx *c) {
     if (c->slot[i].busy) return fail(SMASH_ERR_STATE, "slot %d still has a batch in flight: collect it with smash_wait first", i);
   return 0;
 }
+// ---- accessors for comm.cu (ctx_internal.h)
+int ctx_fail(int code, const char *fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+  return code;
+}
+void **ctx_comm_slot(smash_ctx *c) { return &c->comm; }
+int ctx_device(const smash_ctx *c) { return c->device; }
+smash::TailState *ctx_tail(smash_ctx *c) { return &c->tail; }
+cudaStream_t ctx_stream(smash_ctx *c) { return c->slot[0].st; }
+uint64_t *ctx_launches(smash_ctx *c) { return &c->launches; }
+uint64_t ctx_n_bins(smash_ctx *c) { return c->tail.n_bins; }
+int ctx_require_idle(smash_ctx *c) { return require_idle(c); }
+
 extern "C" int smash_tail_configure(smash_ctx *c, const int64_t *bin_starts, uint64_t n_bins,
                                     const char *const *chrom_names, const int64_t *chrom_offsets,
                                     uint64_t n_chroms, int64_t hit_window, int32_t min_excess) {

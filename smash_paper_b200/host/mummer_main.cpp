@@ -19,7 +19,10 @@
 #include <iostream>
 #include <sstream>
 #include <stdexcept>
+#include <atomic>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/smash_b200.h"
@@ -32,6 +35,8 @@ struct Options {
   bool nucleotides_only = false, sam_out = false, verbose = false, nomap = false, rcref = false, fastq = false,
        sam_in = false, mappability = false, fastq_pair = false, replace_n = false;
   int threads = 2;
+  int gpus = 1;                                   // -gpus N (extension): the query file is cut into N ranges of read pairs
+  std::string bins, chromsizes, binout, binstats, mapbin;   // -bins .. (extension): fused mappability_tag + smashMEM.py + varbin.py
   std::string ref;
   std::vector<std::string> inputs;
 };
@@ -43,13 +48,18 @@ struct Options {
             << "  -samin -samout -nomap -rcref -fastq -verbose -qthreads N -mappability\n"
             << "  -minblock N -cached -normalmem (accepted for compatibility)\n"
             << "  -fastqpair [-replaceN] <ref> <mate1.fq> <mate2.fq>   (extension) the two FASTQ files of a mate pair instead of\n"
-            << "      `-samin <(fastqs_to_sam mate1.fq mate2.fq [1])`; both are parsed on the GPU\n";
+            << "      `-samin <(fastqs_to_sam mate1.fq mate2.fq [1])`; both are parsed on the GPU\n"
+            << "  -gpus N   (extension, with -samin) N GPUs, one contiguous range of read pairs each\n"
+            << "  -bins <bins.txt> -chromsizes <chrom_sizes.txt> -binout <varbin.txt> [-binstats <stats.txt>] [-mapbin <map.bin>]\n"
+            << "      (extension) the stages after mummer in smash_mapping.sh / binning.sh on the GPU(s): mappability_tag,\n"
+            << "      smashMEM.py <bam> 0 0 10000 4, the chromosome filter and varbin.py; counts of all GPUs are summed by one\n"
+            << "      NCCL allreduce\n";
   std::exit(1);
 }
 
 Options parse(int argc, char **argv) {
   Options o;
-  enum { L = 1, MUMREF, MAXMATCH, MUM, MUMCAND, N, QTHREADS, SAMOUT, VERBOSE, NOMAP, RCREF, FASTQ, SAMIN, MAPPABILITY, CACHED, NORMALMEM, MINBLOCK, FASTQPAIR, REPLACEN };
+  enum { L = 1, MUMREF, MAXMATCH, MUM, MUMCAND, N, QTHREADS, SAMOUT, VERBOSE, NOMAP, RCREF, FASTQ, SAMIN, MAPPABILITY, CACHED, NORMALMEM, MINBLOCK, FASTQPAIR, REPLACEN, GPUS, BINS, CHROMSIZES, BINOUT, BINSTATS, MAPBIN };
   static const option table[] = {
       {"l", required_argument, nullptr, L},          {"mumreference", no_argument, nullptr, MUMREF},
       {"maxmatch", no_argument, nullptr, MAXMATCH},  {"mum", no_argument, nullptr, MUM},
@@ -60,7 +70,10 @@ Options parse(int argc, char **argv) {
       {"samin", no_argument, nullptr, SAMIN},        {"mappability", no_argument, nullptr, MAPPABILITY},
       {"cached", no_argument, nullptr, CACHED},      {"normalmem", no_argument, nullptr, NORMALMEM},
       {"minblock", required_argument, nullptr, MINBLOCK}, {"fastqpair", no_argument, nullptr, FASTQPAIR},
-      {"replaceN", no_argument, nullptr, REPLACEN},  {nullptr, 0, nullptr, 0}};
+      {"replaceN", no_argument, nullptr, REPLACEN},  {"gpus", required_argument, nullptr, GPUS},
+      {"bins", required_argument, nullptr, BINS},    {"chromsizes", required_argument, nullptr, CHROMSIZES},
+      {"binout", required_argument, nullptr, BINOUT}, {"binstats", required_argument, nullptr, BINSTATS},
+      {"mapbin", required_argument, nullptr, MAPBIN}, {nullptr, 0, nullptr, 0}};
   for (;;) {
     int idx = -1;
     const int c = getopt_long_only(argc, argv, "", table, &idx);
@@ -82,6 +95,12 @@ Options parse(int argc, char **argv) {
       case SAMIN: o.sam_in = true; break;
       case MAPPABILITY: o.mappability = true; break;
       case CACHED: case NORMALMEM: case MINBLOCK: break;
+      case GPUS: o.gpus = atoi(optarg); break;
+      case BINS: o.bins = optarg; break;
+      case CHROMSIZES: o.chromsizes = optarg; break;
+      case BINOUT: o.binout = optarg; break;
+      case BINSTATS: o.binstats = optarg; break;
+      case MAPBIN: o.mapbin = optarg; break;
       default: std::cerr << "Invalid arguments." << std::endl; usage(argv[0]);
     }
   }
@@ -92,6 +111,10 @@ Options parse(int argc, char **argv) {
   if (o.replace_n && !o.fastq_pair) throw std::runtime_error("-replaceN can only be used with -fastqpair");
   if (o.nomap && !o.sam_out) throw std::runtime_error("-nomap can only be used with -sam_out");
   if (o.mappability && !o.rcref) throw std::runtime_error("-mappability requires -rcref");
+  if (o.gpus < 1) throw std::runtime_error("-gpus must be at least 1");
+  if (o.gpus > 1 && !o.sam_in) throw std::runtime_error("-gpus needs -samin (the query file is cut into ranges of SAM lines)");
+  if (!o.bins.empty() && (o.chromsizes.empty() || o.binout.empty())) throw std::runtime_error("-bins needs -chromsizes and -binout");
+  if (!o.bins.empty() && (!o.rcref || o.mode != SMASH_MODE_MAM)) throw std::runtime_error("-bins needs -rcref and the default match type");
   o.ref = argv[optind];
   for (int i = optind + 1; i < argc; ++i) o.inputs.push_back(argv[i]);
   return o;
@@ -218,6 +241,77 @@ struct QueryParser {
   }
 };
 
+// first line start at or after `approx` whose SAM flag marks a first mate (or an unpaired read): a cut there keeps
+// reads 2k and 2k+1 of every pair in one range (query.cpp:629-637 pairs by arrival)
+uint64_t pair_boundary(FILE *f, uint64_t approx, uint64_t size) {
+  if (approx == 0) return 0;
+  fseeko(f, (off_t)(approx - 1), SEEK_SET);
+  uint64_t pos = approx - 1;
+  int ch;
+  while ((ch = fgetc(f)) != EOF) { ++pos; if (ch == '\n') break; }          // to the start of the next line
+  std::string line;
+  for (;;) {
+    if (pos >= size) return size;
+    line.clear();
+    while ((ch = fgetc(f)) != EOF && ch != '\n') line.push_back((char)ch);
+    const uint64_t next = pos + line.size() + (ch == '\n' ? 1 : 0);
+    const size_t t1 = line.find('\t');
+    const unsigned flag = t1 == std::string::npos ? 0u : (unsigned)strtoul(line.c_str() + t1 + 1, nullptr, 10);
+    if (!line.empty() && line[0] != '@' && !(flag & 128)) return pos;        // first mate (64) or unpaired
+    if (ch == EOF) return size;
+    pos = next;
+  }
+}
+// str(float) of Python 3 (varbin.py:97 writes the ratio column with it): shortest digits that round-trip, fixed
+// notation for 1e-4 <= |x| < 1e16, always a fractional part
+std::string py_repr(double v) {
+  if (v != v) return "nan";
+  if (v == 1.0 / 0.0) return "inf";
+  if (v == -1.0 / 0.0) return "-inf";
+  char buf[64];
+  int p = 1;
+  for (; p <= 17; ++p) { snprintf(buf, sizeof buf, "%.*e", p - 1, v); if (strtod(buf, nullptr) == v) break; }
+  std::string m(buf);
+  const size_t epos = m.find('e');
+  const int e10 = atoi(m.c_str() + epos + 1);
+  std::string digits; bool neg = false;
+  for (size_t i = 0; i < epos; ++i) { if (m[i] == '-') neg = true; else if (m[i] != '.') digits.push_back(m[i]); }
+  std::string out = neg ? "-" : "";
+  if (e10 >= -4 && e10 < 16) {
+    if (e10 >= 0) {
+      std::string ip = digits.substr(0, std::min<size_t>(digits.size(), (size_t)e10 + 1));
+      ip.append((size_t)e10 + 1 - ip.size(), '0');
+      std::string fp = digits.size() > (size_t)e10 + 1 ? digits.substr((size_t)e10 + 1) : "0";
+      out += ip + "." + fp;
+    } else out += "0." + std::string((size_t)(-e10 - 1), '0') + digits;
+  } else {
+    out += digits.substr(0, 1);
+    if (digits.size() > 1) out += "." + digits.substr(1);
+    char eb[16]; snprintf(eb, sizeof eb, "e%c%02d", e10 < 0 ? '-' : '+', e10 < 0 ? -e10 : e10);
+    out += eb;
+  }
+  return out;
+}
+// varbin.py:95-114: rows `chrom start abs count ratio`, then the stats file
+void write_varbin(const Options &o, const std::vector<std::string> &rows, std::vector<int64_t> counts, const smash_tail_stats &st) {
+  FILE *f = fopen(o.binout.c_str(), "wb");
+  if (!f) throw std::runtime_error("could not open " + o.binout + " for writing");
+  const double per_bin = (double)st.reads_kept / (double)rows.size();
+  for (size_t i = 0; i < rows.size(); ++i) {
+    const std::string r = per_bin > 0 ? py_repr((double)counts[i] / per_bin) : std::string("nan");
+    fprintf(f, "%s\t%lld\t%s\n", rows[i].c_str(), (long long)counts[i], r.c_str());
+  }
+  fclose(f);
+  if (!o.binstats.empty()) {
+    FILE *s = fopen(o.binstats.c_str(), "wb");
+    if (!s) throw std::runtime_error("could not open " + o.binstats + " for writing");
+    std::sort(counts.begin(), counts.end());
+    fprintf(s, "TotalReads\tDupsRemoved\tReadsKept\tMedianBinCount\n%llu\t%llu\t%llu\t%lld\n", (unsigned long long)st.total_reads,
+            (unsigned long long)st.dups_removed, (unsigned long long)st.reads_kept, (long long)(counts.empty() ? 0 : counts[counts.size() / 2]));
+    fclose(s);
+  }
+}
+
 bool readable(const std::string &p) { return access(p.c_str(), R_OK) == 0; }
 
 }  // namespace
@@ -268,6 +362,37 @@ int main(int argc, char **argv) {
       smash_ctx_destroy(ctx); smash_index_close(ix);
       return 0;
     }
+    // -gpus N: one context per GPU over the same host index; -bins: map.bin + the tail's configuration on each
+    const int n_gpus = o.gpus;
+    std::vector<smash_ctx *> ctxs{ctx};
+    for (int g = 1; g < n_gpus; ++g) { smash_params pg = p; pg.device = g; smash_ctx *cg = nullptr; check(smash_ctx_create(ix, &pg, &cg)); ctxs.push_back(cg); }
+    std::vector<int64_t> bin_starts; std::vector<std::string> bin_rows;
+    if (!o.bins.empty()) {
+      std::ifstream bf(o.bins); if (!bf) throw std::runtime_error("unable to open " + o.bins);
+      std::string l;
+      while (std::getline(bf, l)) {                                  // bins.txt: chrom, start, abs start, ... (varbin.py:17-26)
+        if (l.empty()) continue;
+        std::istringstream ls(l); std::string c0, c1, c2; ls >> c0 >> c1 >> c2;
+        bin_rows.push_back(c0 + "\t" + c1 + "\t" + c2); bin_starts.push_back(strtoll(c2.c_str(), nullptr, 10));
+      }
+      std::ifstream cf(o.chromsizes); if (!cf) throw std::runtime_error("unable to open " + o.chromsizes);
+      std::vector<std::string> cnames; std::vector<int64_t> coffs;
+      while (std::getline(cf, l)) {                                  // chrom_sizes.txt: name, size, cumulative offset (varbin.py:28-36)
+        if (l.empty()) continue;
+        std::istringstream ls(l); std::string c0, c1, c2; ls >> c0 >> c1 >> c2;
+        cnames.push_back(c0); coffs.push_back(strtoll(c2.c_str(), nullptr, 10));
+      }
+      std::vector<const char *> cptr; for (auto &c : cnames) cptr.push_back(c.c_str());
+      const std::string mb = o.mapbin.empty() ? o.ref + ".bin/map.bin" : o.mapbin;
+      std::ifstream mf(mb, std::ios::binary); if (!mf) throw std::runtime_error("unable to open " + mb + " (mummer -mappability writes it)");
+      std::vector<char> body((std::istreambuf_iterator<char>(mf)), std::istreambuf_iterator<char>());
+      if (body.size() < 2) throw std::runtime_error(mb + " is empty");
+      for (smash_ctx *cg : ctxs) {
+        check(smash_ctx_load_mappability(cg, (const uint8_t *)body.data() + 2, body.size() - 2));   // 2 junk bytes (longSA.cpp:606-617)
+        check(smash_tail_configure(cg, bin_starts.data(), bin_starts.size(), cptr.data(), coffs.data(), cnames.size(), 10000, 4));
+      }
+    }
+    if (n_gpus > 1) check(smash_comm_init_all(ctxs.data(), n_gpus));
     std::vector<char> header(smash_index_sam_header(ix, nullptr, 0));
     smash_index_sam_header(ix, header.data(), header.size());
     if (o.verbose) std::cerr << "# running " << o.threads << " threads to answer queries\n# running " << o.inputs.size() << " query reader" << std::endl;
@@ -275,10 +400,16 @@ int main(int argc, char **argv) {
     // every batch becomes one chunk file, its lines sorted as OutputSorter::flush sorts a chunk (query.cpp:448-468);
     // SMASH_CHUNK_ORDER=input keeps them in input order instead
     const char *ord_env = getenv("SMASH_CHUNK_ORDER");
-    const int want_sam = SMASH_WANT_SAM | ((ord_env && !strcmp(ord_env, "input")) ? 0 : SMASH_WANT_SORTED);
-    uint64_t n_queries = 0, chunk = 0, pairs_done = 0;
+    const int want_sam = SMASH_WANT_SAM | ((ord_env && !strcmp(ord_env, "input")) ? 0 : SMASH_WANT_SORTED) | (o.bins.empty() ? 0 : SMASH_WANT_TAIL);
     const auto tq = std::chrono::steady_clock::now();
     const bool device_reader = o.sam_in && !getenv("SMASH_HOST_READER");   // -samin text is parsed on the GPU (smash_submit_text)
+    if (n_gpus > 1 && !device_reader) throw std::runtime_error("-gpus needs the device reader (-samin without SMASH_HOST_READER)");
+    std::atomic<uint64_t> total_queries{0};
+    // one GPU's share of the work: with -gpus N, GPU g takes the g-th of N byte ranges of every query file, cut at
+    // read-pair boundaries (contiguous ranges of pairs: what the sharded tail needs)
+    auto run_gpu = [&](int g) {
+    smash_ctx *ctx = ctxs[g];
+    uint64_t n_queries = 0, chunk = 0, pairs_done = 0;
     for (size_t fi = 0; fi < o.inputs.size(); ++fi) {
       if (o.fastq_pair && fi > 0) break;                            // the two inputs are ONE stream of pairs
       bool in_flight[SMASH_N_SLOTS] = {};
@@ -287,7 +418,7 @@ int main(int argc, char **argv) {
         in_flight[slot] = false;
         if (o.sam_out && r.sam_bytes) {
           mkdir("mapout", 0755);
-          const std::string fn = "mapout/mapoutb200_" + std::to_string(fi) + "." + std::to_string(++chunk) + ".txt";
+          const std::string fn = "mapout/mapoutb200_" + (n_gpus > 1 ? "g" + std::to_string(g) + "_" : std::string()) + std::to_string(fi) + "." + std::to_string(++chunk) + ".txt";
           FILE *f = fopen(fn.c_str(), "wb");
           if (!f) throw std::runtime_error("Problem opening out file");
           fwrite(header.data(), 1, header.size(), f); fwrite(r.sam, 1, r.sam_bytes, f); fclose(f);
@@ -340,13 +471,26 @@ int main(int argc, char **argv) {
         // buffer in large chunks; what a chunk leaves unconsumed (a cut line, an odd trailing read) is carried over.
         FILE *f = fopen(o.inputs[fi].c_str(), "rb");
         if (!f) throw std::runtime_error("unable to open " + o.inputs[fi]);
+        uint64_t range_begin = 0, range_end = UINT64_MAX;
+        if (n_gpus > 1) {
+          struct stat fst; if (stat(o.inputs[fi].c_str(), &fst)) throw std::runtime_error("unable to open " + o.inputs[fi]);
+          range_begin = pair_boundary(f, (uint64_t)fst.st_size / n_gpus * g, (uint64_t)fst.st_size);
+          range_end = g + 1 == n_gpus ? (uint64_t)fst.st_size : pair_boundary(f, (uint64_t)fst.st_size / n_gpus * (g + 1), (uint64_t)fst.st_size);
+          fseeko(f, (off_t)range_begin, SEEK_SET);
+        }
+        uint64_t left_in_range = range_end - range_begin;
         size_t cap = (size_t)256 << 20, len = 0;
         if (const char *e = getenv("SMASH_TEXT_CHUNK")) cap = std::max<size_t>(4096, strtoull(e, nullptr, 10));
         char *text = (char *)smash_host_alloc(cap);
         if (!text) throw std::runtime_error("out of pinned host memory");
         bool eof = false;
         while (!eof) {
-          while (len < cap && !eof) { const size_t got = fread(text + len, 1, cap - len, f); len += got; if (!got) eof = true; }
+          while (len < cap && !eof) {
+            const size_t ask = (uint64_t)(cap - len) < left_in_range ? cap - len : (size_t)left_in_range;
+            const size_t got = ask ? fread(text + len, 1, ask, f) : 0;
+            len += got; left_in_range -= got;
+            if (!got) eof = true;
+          }
           if (in_flight[slot]) drain(slot);
           smash_text t{}; smash_text_info info{};
           t.kind = SMASH_TEXT_SAM; t.flags = eof ? SMASH_TEXT_FINAL : 0; t.text[0] = text; t.n_bytes[0] = len;
@@ -382,12 +526,39 @@ int main(int argc, char **argv) {
       }
       delete qpp;
       for (int s = 0; s < SMASH_N_SLOTS; ++s) { const int k = (slot + s) % SMASH_N_SLOTS; if (in_flight[k]) drain(k); }
-      if (o.verbose) std::cerr << "# query reader for " << o.inputs[fi] << " processed " << n_queries << " sequences" << std::endl;
+      if (o.verbose && n_gpus == 1) std::cerr << "# query reader for " << o.inputs[fi] << " processed " << n_queries << " sequences" << std::endl;
     }
+    total_queries += n_queries;
+    };                                                               // run_gpu
+    // the stages after mummer (-bins): collective over the GPUs, every rank ends up with the global counts
+    std::vector<int64_t> counts(bin_starts.size());
+    smash_tail_stats tstats{};
+    auto finish_gpu = [&](int g) {
+      if (o.bins.empty()) return;
+      smash_tail_stats st_g{};
+      std::vector<int64_t> mine(bin_starts.size());
+      check(smash_bins_finish(ctxs[g], (uint64_t)g << 40, mine.data(), nullptr, &st_g));
+      if (g == 0) { counts.swap(mine); tstats = st_g; }
+    };
+    if (n_gpus == 1) { run_gpu(0); finish_gpu(0); }
+    else {
+      std::vector<std::thread> th;
+      std::vector<std::string> errs(n_gpus);
+      for (int g = 0; g < n_gpus; ++g)
+        th.emplace_back([&, g] {
+          try { run_gpu(g); } catch (const std::exception &e) { errs[g] = e.what(); }
+          try { if (errs[g].empty()) finish_gpu(g); } catch (const std::exception &e) { errs[g] = e.what(); }
+        });
+      for (auto &t : th) t.join();
+      for (auto &e : errs) if (!e.empty()) throw std::runtime_error(e);
+    }
+    const uint64_t n_queries = total_queries.load();
+    if (!o.bins.empty()) write_varbin(o, bin_rows, counts, tstats);
     if (!n_queries) std::cerr << "# no reads processed" << std::endl;
     if (o.verbose)
       std::cerr << "# ran " << n_queries << " queries in "
                 << std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - tq).count() << " seconds" << std::endl;
+    for (size_t g = 1; g < ctxs.size(); ++g) smash_ctx_destroy(ctxs[g]);
     smash_ctx_destroy(ctx); smash_index_close(ix);
     return 0;
   } catch (const std::exception &e) {

@@ -32,10 +32,12 @@ STUB = r'''
 // of the text, so a plain comparison sort gives the arrays the kernels downstream expect; tests of the index BUILDER
 // itself mean nothing under the emulation and are not run there.
 #include "sabuild.cuh"
+#include "smash_b200.h"
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
+extern "C" int smash_comm_destroy(smash_ctx *) { return 0; }      // comm.cu (NCCL) is not part of the emulation
 namespace smash {
 int build_index_device(const uint8_t *T, uint64_t N, int w, void *d_sa, void *d_isa, uint8_t *d_lcp, LcpItem **d_lcpm, uint64_t *n_m,
                        uint64_t, cudaStream_t, char *err, uint64_t *) {
@@ -100,8 +102,8 @@ def build(force=False, sanitize=False):
         out = os.path.join(GEN, f.replace(".cu", "_shim.cpp"))
         open(out, "w").write(rewrite(open(os.path.join(CSRC, f)).read()))
         srcs.append(out)
-    for f in ("compact.h", "expand.h", "expand.cpp"):                # plain host C++: compiled as it is
-        open(os.path.join(GEN, f), "w").write(open(os.path.join(CSRC, f)).read())
+    for f in ("compact.h", "expand.h", "expand.cpp", "ctx_internal.h"):     # plain host C++: compiled as it is
+        open(os.path.join(GEN, f), "w").write(open(os.path.join(CSRC, f)).read().replace('#include "../../include/smash_b200.h"', '#include "smash_b200.h"'))
     srcs.append(os.path.join(GEN, "expand.cpp"))
     stub = os.path.join(GEN, "sabuild_stub.cpp")
     open(stub, "w").write(STUB)

@@ -763,3 +763,55 @@ def test_long_reads(workdir):
         assert ctx.map_batch(reads).sam == sam
     finally:
         ctx.close(); ix.close()
+
+
+def _driver_case_tail(workdir, tag):
+    """case_tail of tests/golden on disk: ref.fa + index (built by the driver), map.bin, reads.sam, bins, chrom sizes."""
+    import gzip, shutil, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "smash_paper_b200", "bin", "mummer")
+    src = os.path.join(root, "tests", "golden", "case_tail")
+    d = os.path.join(workdir, "driver_bins_" + tag)
+    shutil.rmtree(d, ignore_errors=True)
+    os.makedirs(d)
+    fa = os.path.join(d, "ref.fa")
+    open(fa, "wb").write(gzip.open(os.path.join(src, "ref.fa.gz")).read())
+    open(os.path.join(d, "reads.sam"), "wb").write(gzip.open(os.path.join(src, "reads.sam.gz")).read())
+    shutil.copy(os.path.join(src, "bins.txt"), d); shutil.copy(os.path.join(src, "chrom_sizes.txt"), d)
+    r = subprocess.run([exe, "-rcref", fa, "dummy"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 1 and "unable to open dummy" in r.stderr
+    r = subprocess.run([exe, "-rcref", "-mappability", fa, fa + ".bin/map.bin"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(fa + ".bin/map.bin", "rb").read()[2:] == gzip.open(os.path.join(src, "map.bin.gz")).read()[2:]
+    return exe, d, fa, src
+
+
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_driver_fused_tail_equals_reference_varbin(workdir, gpus):
+    """bin/mummer -bins ..: mapout + the stages after mummer (mappability_tag, smashMEM.py, chromosome filter, varbin.py)
+    in one run.  The varbin file must be BYTE-identical to what the unmodified pipeline printed for these reads
+    (tests/golden/case_tail/varbin.txt.gz, incl. Python's repr of the ratio column); with -gpus 2 the reads are cut into
+    two ranges, each GPU maps its own, and the counts meet in smash_bins_finish (one ncclAllReduce)."""
+    import glob, gzip, subprocess
+    from smash_paper_b200 import api
+    if api.device_count() < gpus:
+        pytest.skip(f"needs {gpus} GPUs")
+    exe, d, fa, src = _driver_case_tail(workdir, str(gpus))
+    cmd = [exe, "-rcref", "-qthreads", "4", "-nomap", "-samin", "-samout", "-bins", "bins.txt", "-chromsizes", "chrom_sizes.txt",
+           "-binout", "varbin.txt", "-binstats", "stats.txt"] + (["-gpus", str(gpus)] if gpus > 1 else []) + [fa, "reads.sam"]
+    r = subprocess.run(cmd, cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(os.path.join(d, "varbin.txt"), "rb").read() == gzip.open(os.path.join(src, "varbin.txt.gz")).read()
+    stats = open(os.path.join(d, "stats.txt")).read().splitlines()
+    assert stats[0] == "TotalReads\tDupsRemoved\tReadsKept\tMedianBinCount" and len(stats[1].split("\t")) == 4
+    # the mapout of all chunk files = the reference's records for these reads (sorted multiset; chunking differs by design)
+    got = sorted(l for f in glob.glob(os.path.join(d, "mapout", "*.txt")) for l in open(f, "rb") if not l.startswith(b"@"))
+    g = load_golden_case("case_tail") if os.path.exists(os.path.join(src, "mapout_mam_l20.sam.gz")) else None
+    if g is None:
+        from smash_paper_b200 import samio, sequence
+        names, seqs = sequence.read_fasta(fa)
+        oix = O.Index.build(names, seqs)
+        exp = sorted(oix.map_batch(samio.read_sam(os.path.join(d, "reads.sam")), min_len=20, n_threads=4).splitlines(keepends=True))
+        assert got == exp
+    if gpus > 1:
+        assert len({os.path.basename(f).split("_")[1] for f in glob.glob(os.path.join(d, "mapout", "*.txt"))}) == gpus
