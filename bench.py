@@ -341,8 +341,12 @@ def run_ours(args, wl, rank, world):
         sam_per_read = sam_bytes / max(B * args.steps, 1)
         split = stage.get("verify", 0.0) > 0.0                  # split search: k_mam_search parks, k_mam_verify extends
         alg = kernel_alg_bytes(wl, n_text, n_rec_per_read, sam_per_read, split)
+        # the "search" stage timer spans k_mam_seed (lanes = anchors; nearly all of the time) + k_mam_search (exact paths of
+        # the few flagged reads); without the split search it is k_mam_search alone
+        SEARCH_KEY = "k_mam_seed+k_mam_search" if split else "k_mam_search"
+        alg[SEARCH_KEY] = alg["k_mam_search"]
         per_kernel = {}
-        for kname, skey in (("k_mam_search", "search"), ("k_mam_verify", "verify"), ("k_rec_build+k_rec_xe", "records"),
+        for kname, skey in ((SEARCH_KEY, "search"), ("k_mam_verify", "verify"), ("k_rec_build+k_rec_xe", "records"),
                             ("k_sizes", "sizes_scan"), ("k_emit_text", "emit_text"), ("k_emit_copy", "emit_copy")):
             if kname == "k_mam_verify" and not split:
                 continue
@@ -353,13 +357,21 @@ def run_ours(args, wl, rank, world):
         # DRAM traffic of that kernel from the committed ncu --set full capture of this workload (1 M reads per launch)
         traffic, traffic_src = None, None
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", f"r01_dram_traffic_{args.workload}.json")))
-            if dom in tj:
-                traffic = (tj[dom]["dram_read_bytes"] + tj[dom]["dram_write_bytes"]) * (B / 1e6)
-                traffic_src = f"profiles/r01_ncu_full_{args.workload}_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum, scaled to {B} reads/launch)"
+            import hashlib
+            tj = json.load(open(os.path.join(ROOT, "profiles", f"r02_dram_traffic_{args.workload}.json")))
+            hsh = hashlib.sha256()
+            for fn in ("kernels.cu", "core.cuh", "records.cuh", "kernels.cuh"):
+                hsh.update(open(os.path.join(ROOT, "smash_paper_b200", "csrc", fn), "rb").read())
+            parts = [k for k in dom.split("+") if k in tj]
+            if tj.get("_kernel_sources_sha256") != hsh.hexdigest():
+                traffic_src = "stale: the kernel sources changed after profiles/r02_dram_traffic_*.json was captured (field dropped)"
+            elif parts:
+                traffic = sum(tj[k]["dram_read_bytes"] + tj[k]["dram_write_bytes"] for k in parts) * (B / 1e6)
+                traffic_src = (f"profiles/r02_ncu_full_{args.workload}_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum of {' + '.join(parts)}, "
+                               f"scaled to {B} reads/launch; capture taken from these kernel sources, sha256 checked)")
         except (OSError, ValueError):
             pass
-        search_ms = per_kernel["k_mam_search"]["ms"] + (per_kernel["k_mam_verify"]["ms"] if split else 0.0)
+        search_ms = per_kernel[SEARCH_KEY]["ms"] + (per_kernel["k_mam_verify"]["ms"] if split else 0.0)
         achieved = per_kernel[dom]["achieved_gbs"]
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -531,8 +543,8 @@ def kernel_alg_bytes(wl, N, n_rec, sam_bytes, split=False):
     name = 10
     surv = anchors * true_cand                                      # candidates left after the 4+4 filter (chance hits: ~2 %)
     if split:
-        # read in + lower-cased copy out, per anchor two seed entries, per bucket entry its 2-byte ext code, parked candidates out
-        search = q + q + anchors * 2 * seed_w + cand * 2 + surv * 8
+        # read in + lower-cased copy out, per anchor two seed entries, per bucket entry its 4-byte ext code, parked candidates out
+        search = q + q + anchors * 2 * seed_w + cand * 4 + surv * 8
         # parked candidates in, their SA entry and the 8-byte text window left of the seed, the read once; per fragment
         # (the candidates that own a diagonal) its text span and one U byte; matches out
         verify = surv * (8 + w + 8) + q + (q / frag) * (frag + 1) + 16 * n_rec

@@ -1024,6 +1024,7 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
   const uint64_t n = s.n_reads;
   const bool chunked = s.n_chunks > 1;
   const int evs_at_entry = s.n_evs;
+  bool exact_csr = false;
   for (int attempt = 0;; ++attempt) {
     WorkDev w = work_of(s);
     s.n_evs = evs_at_entry;
@@ -1048,8 +1049,31 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
       if (s.compact && ((rc = s.cmp_bytes.ensure(total + 1)) || (rc = s.cmp_off.ensure(total + 2)))) return rc;
       w = work_of(s);
       nl += launch_mem_write(c->dix, s.bd, c->sp, c->prm.min_len, s.slot_off.p, s.match_slots.p, s.st);
-    } else {
+    } else if (exact_csr) {
+      // K1c: a read of this range has more matches than the anchor kernels stage (STAGE_CAP): exact per-start search with
+      // CSR slots, any number of matches per read (count pass -> slot offsets -> exact-size buffers -> write pass)
+      int rc;
+      if (s.long_q < MAXQ_FAST) s.long_q = MAXQ_FAST;
+      if ((rc = s.long_scratch.ensure((size_t)148 * 8 * 8 * (size_t)(s.long_q + P_FRONT + P_BACK + 8))) || (rc = s.slot_off.ensure(n + 2)) ||
+          (rc = s.tmp32.ensure(n + 1)))
+        return rc;
       s.csr = false;
+      w = work_of(s);
+      nl = launch_mam_exact(c->dix, s.bd, w, c->sp, s.match_cnt.p, s.st);
+      nl += launch_slot_offsets(s.match_cnt.p, n, s.tmp32.p, s.blk_sums.p, s.slot_off.p, s.st);
+      CU(cudaMemcpyAsync(s.h_small.p + 16, s.slot_off.p + n, 8, cudaMemcpyDeviceToHost, s.st));
+      CU(cudaStreamSynchronize(s.st));
+      const uint64_t total = s.h_small.p[16];
+      s.slots_total = total; s.csr = true;
+      if ((rc = s.match_slots.ensure(total + 1)) || (rc = s.item_slots.ensure(total + 1)) || (rc = s.rec_slots.ensure(total + 1)) ||
+          (rc = s.aln_scr.ensure(total + 1)) || (rc = s.ord_scr.ensure(total + 1)) || (rc = s.rec_read.ensure(total + 1)) ||
+          (rc = s.rec_bytes.ensure(total + 1)) || (rc = s.rec_off.ensure(total + 2)) || (rc = s.blk_sums2.ensure(total / 2048 + 8)))
+        return rc;
+      if (s.compact && ((rc = s.cmp_bytes.ensure(total + 1)) || (rc = s.cmp_off.ensure(total + 2)))) return rc;
+      w = work_of(s);
+      nl += launch_mam_exact(c->dix, s.bd, w, c->sp, nullptr, s.st);
+    } else {
+      if (s.csr) { s.csr = false; w = work_of(s); }           // an earlier range of this slot ran on CSR slots (K1c)
       nl = launch_mam_search(c->dix, s.bd, w, c->sp, s.st);
     }
     s.launches += nl;
@@ -1078,8 +1102,8 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
     if (fl[FLAG_LONGREAD]) return fail(SMASH_ERR_STATE, "%u long reads could not be staged", fl[FLAG_LONGREAD]);
     if (fl[FLAG_OVERFLOW]) {
       const uint32_t need = fl[FLAG_MAXCNT];
-      if (need > (uint32_t)STAGE_CAP || attempt > 3)
-        return fail(SMASH_ERR_DATA, "a read produced %u matches; this build keeps at most %d per read", need, STAGE_CAP);
+      if (exact_csr || attempt > 4) return fail(SMASH_ERR_DATA, "a read produced more than 65535 matches (%u)", need);
+      if (need > (uint32_t)STAGE_CAP) { exact_csr = true; continue; }   // rerun the range on the exact CSR path (K1c)
       s.cap = (int)need + 8 > STAGE_CAP ? STAGE_CAP : (int)need + 8;
       int rc;
       if ((rc = s.match_slots.ensure(n_full * s.cap)) || (rc = s.item_slots.ensure(n_full * s.cap)) || (rc = s.rec_slots.ensure(n_full * s.cap)) ||

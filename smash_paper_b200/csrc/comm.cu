@@ -82,7 +82,7 @@ template <class T> struct Buf {                                // growable devic
 struct CommState {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
-  Buf<uint64_t> send, recv, fp1, fp1_sorted, mins, back, verdict, small, counts;
+  Buf<uint64_t> send, recv, fp1, fp1_sorted, mins, back, verdict, small, counts, info;
   Buf<uint32_t> perm, idx, idx_sorted;
   Buf<uint8_t> sort_tmp;
   uint64_t *h_small = nullptr;                                 // pinned: counts matrix, edges, stats
@@ -160,6 +160,104 @@ int comm_attach(smash_ctx *c, ncclComm_t comm, int rank, int world) {
   return 0;
 }
 
+// ---- inputs that are not in `samtools sort -n` order -------------------------------------------------------------------
+// smashMEM.py's first-wins rule and varbin.py's adjacent-duplicate rule follow the NAME order of the pairs, and the
+// sharded protocol above relies on every shard being a contiguous run of it.  Every rank publishes {pairs, hits, name
+// bytes, pairs out of order, first name, last name}; if any shard is out of order inside, or two neighbouring shards are
+// out of order at their seam, the ranks send their pairs to rank 0 (grouped ncclSend/ncclRecv, rank order = input order)
+// and rank 0 runs the single-GPU finish, whose name sort handles any order.  The decision is taken from all-gathered data,
+// so every rank takes the same branch.
+constexpr int INFO_WORDS = 4 + 2 * TAIL_EDGE_NAME / 8;
+int gather_if_unsorted(CommState *cs, TailState *t, cudaStream_t st, uint64_t *launches, bool *gathered) {
+  const int W = cs->world, R = cs->rank;
+  int rc;
+  std::vector<uint64_t> mine(INFO_WORDS), all((size_t)INFO_WORDS * W);
+  if ((rc = tail_totals(t, mine.data(), st))) return ctx_fail(rc, "tail: %s", tail_error());
+  if ((rc = tail_edge_names(t, (uint8_t *)(mine.data() + 4), (uint8_t *)(mine.data() + 4) + TAIL_EDGE_NAME, st))) return ctx_fail(rc, "tail: %s", tail_error());
+  if ((rc = cs->info.ensure((size_t)INFO_WORDS * (W + 1)))) return rc;
+  CC(cudaMemcpyAsync(cs->info.p, mine.data(), 8 * INFO_WORDS, cudaMemcpyHostToDevice, st));
+  NC(g_nccl.AllGather(cs->info.p, cs->info.p + INFO_WORDS, INFO_WORDS, ncclUint64, cs->comm, st));
+  CC(cudaMemcpyAsync(all.data(), cs->info.p + INFO_WORDS, 8 * (size_t)INFO_WORDS * W, cudaMemcpyDeviceToHost, st));
+  CC(cudaStreamSynchronize(st));
+  bool unsorted = false;
+  const uint8_t *prev_last = nullptr;
+  for (int r = 0; r < W; ++r) {
+    const uint64_t *info = all.data() + (size_t)INFO_WORDS * r;
+    if (!info[0]) continue;
+    const uint8_t *first = (const uint8_t *)(info + 4), *last = first + TAIL_EDGE_NAME;
+    if (info[3] || first[0] == 255 || last[0] == 255) unsorted = true;       // a name too long for the slot: take the safe path
+    else if (prev_last && strnum_cmp(prev_last + 1, prev_last[0], first + 1, first[0]) > 0) unsorted = true;
+    prev_last = last;
+  }
+  *gathered = unsorted;
+  if (!unsorted) return 0;
+  // rank 0 takes the others' pairs behind its own, shard by shard
+  uint64_t add[3] = {0, 0, 0};
+  for (int r = 1; r < W; ++r) for (int k = 0; k < 3; ++k) add[k] += all[(size_t)INFO_WORDS * r + k];
+  if (R == 0 && (rc = tail_absorb_reserve(t, add[0], add[1], add[2], st))) return ctx_fail(rc, "tail: %s", tail_error());
+  NC(g_nccl.GroupStart());
+  if (R == 0) {
+    uint64_t P = all[0], H = all[1], B = all[2];
+    for (int r = 1; r < W; ++r) {
+      const uint64_t *info = all.data() + (size_t)INFO_WORDS * r;
+      const uint64_t p = info[0], h = info[1], b = info[2];
+      if (p) {
+        NC(g_nccl.Recv(t->pair_nhits.p + P, 4 * p, ncclUint8, r, cs->comm, st));
+        NC(g_nccl.Recv(t->pair_fp.p + 2 * P, 16 * p, ncclUint8, r, cs->comm, st));
+        NC(g_nccl.Recv(t->pair_hit_off.p + P, 8 * p, ncclUint8, r, cs->comm, st));
+        NC(g_nccl.Recv(t->pair_name_off.p + P + 1, 8 * p, ncclUint8, r, cs->comm, st));
+        if (h) NC(g_nccl.Recv(t->hits.p + H, 8 * h, ncclUint8, r, cs->comm, st));
+        if (b) NC(g_nccl.Recv(t->name_blob.p + B, b, ncclUint8, r, cs->comm, st));
+      }
+      P += p; H += h; B += b;
+    }
+  } else if (mine[0]) {
+    const uint64_t p = mine[0], h = mine[1], b = mine[2];
+    NC(g_nccl.Send(t->pair_nhits.p, 4 * p, ncclUint8, 0, cs->comm, st));
+    NC(g_nccl.Send(t->pair_fp.p, 16 * p, ncclUint8, 0, cs->comm, st));
+    NC(g_nccl.Send(t->pair_hit_off.p, 8 * p, ncclUint8, 0, cs->comm, st));
+    NC(g_nccl.Send(t->pair_name_off.p + 1, 8 * p, ncclUint8, 0, cs->comm, st));
+    if (h) NC(g_nccl.Send(t->hits.p, 8 * h, ncclUint8, 0, cs->comm, st));
+    if (b) NC(g_nccl.Send(t->name_blob.p, b, ncclUint8, 0, cs->comm, st));
+  }
+  NC(g_nccl.GroupEnd());
+  CC(cudaStreamSynchronize(st));
+  if (R == 0) {
+    for (int r = 1; r < W; ++r) {
+      const uint64_t *info = all.data() + (size_t)INFO_WORDS * r;
+      if ((rc = tail_absorb_commit(t, info[0], info[1], info[2], st, launches))) return ctx_fail(rc, "tail: %s", tail_error());
+    }
+  } else {
+    tail_reset(t);                                              // this rank's pairs now live on rank 0
+  }
+  return 0;
+}
+// rank 0 holds every pair: it finishes alone, the others contribute zeros to the allreduce that hands everyone the counts
+int finish_gathered(smash_ctx *c, CommState *cs, TailState *t, cudaStream_t st, uint64_t *launches, int64_t *counts, void *counts_device,
+                    smash_tail_stats *st_out) {
+  int rc;
+  const uint64_t nb = ctx_n_bins(c);
+  if ((rc = cs->counts.ensure(nb + 8))) return rc;
+  CC(cudaMemsetAsync(cs->counts.p, 0, 8 * (nb + 8), st));
+  uint64_t *h_stats = cs->h_small;
+  if (cs->rank == 0) {
+    smash_tail_stats stl{};
+    if ((rc = tail_finish(t, nullptr, (int64_t *)cs->counts.p, &stl, st, launches))) return ctx_fail(rc, "tail: %s", tail_error());
+    h_stats[0] = stl.total_reads; h_stats[1] = stl.dups_removed; h_stats[2] = stl.reads_kept; h_stats[3] = stl.n_dupe_pairs; h_stats[4] = stl.n_non_dupe_pairs; h_stats[5] = stl.n_positions;
+    CC(cudaMemcpyAsync(cs->counts.p + nb, h_stats, 48, cudaMemcpyHostToDevice, st));
+  }
+  NC(g_nccl.AllReduce(cs->counts.p, cs->counts.p, nb + 6, ncclUint64, ncclSum, cs->comm, st));
+  if (counts) CC(cudaMemcpyAsync(counts, cs->counts.p, 8 * nb, cudaMemcpyDeviceToHost, st));
+  if (counts_device) CC(cudaMemcpyAsync(counts_device, cs->counts.p, 8 * nb, cudaMemcpyDeviceToDevice, st));
+  CC(cudaMemcpyAsync(h_stats, cs->counts.p + nb, 48, cudaMemcpyDeviceToHost, st));
+  CC(cudaStreamSynchronize(st));
+  if (st_out) {
+    st_out->total_reads = h_stats[0]; st_out->dups_removed = h_stats[1]; st_out->reads_kept = h_stats[2];
+    st_out->n_dupe_pairs = h_stats[3]; st_out->n_non_dupe_pairs = h_stats[4]; st_out->n_positions = h_stats[5];
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" int smash_comm_unique_id(void *id, size_t cap) {
@@ -197,7 +295,7 @@ extern "C" int smash_comm_destroy(smash_ctx *c) {
   cudaSetDevice(ctx_device(c));
   if (cs->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(cs->comm);
   cs->send.release(); cs->recv.release(); cs->fp1.release(); cs->fp1_sorted.release(); cs->mins.release(); cs->back.release();
-  cs->verdict.release(); cs->small.release(); cs->counts.release(); cs->perm.release(); cs->idx.release(); cs->idx_sorted.release(); cs->sort_tmp.release();
+  cs->verdict.release(); cs->small.release(); cs->counts.release(); cs->info.release(); cs->perm.release(); cs->idx.release(); cs->idx_sorted.release(); cs->sort_tmp.release();
   if (cs->h_small) cudaFreeHost(cs->h_small);
   delete cs;
   *ctx_comm_slot(c) = nullptr;
@@ -226,6 +324,12 @@ extern "C" int smash_bins_finish(smash_ctx *c, uint64_t ordinal_base, int64_t *c
   CC(cudaDeviceSynchronize());
   const int W = cs->world, R = cs->rank;
   int rc;
+  // 0. are the shards, one after the other, a run of the name order (smash_mapping.sh:23)?  If not, rank 0 finishes alone.
+  {
+    bool gathered = false;
+    if ((rc = gather_if_unsorted(cs, t, st, launches, &gathered))) return rc;
+    if (gathered) return finish_gathered(c, cs, t, st, launches, counts, counts_device, st_out);
+  }
   // 1. this rank's dupe-set keys, bucketed by owner
   const uint64_t *keys = nullptr; uint64_t n = 0;
   if ((rc = tail_export_keys(t, ordinal_base, &keys, &n, st, launches))) return ctx_fail(rc, "tail: %s", tail_error());

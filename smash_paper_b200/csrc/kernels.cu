@@ -746,6 +746,59 @@ k_mam_search_long(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
   }
 }
 
+// K1c: any number of matches per read.  The anchor kernels stage at most STAGE_CAP matches of a read in shared memory; a
+// range holding a read with more (the reference has no such limit: a few-thousand-base read made of short unique pieces)
+// is redone here with the exact per-start path and CSR slots, as MEM mode does: a COUNT pass, the slot offsets, a WRITE
+// pass.  One warp per read, lanes = query starts p (32 at a time, in increasing order), so a ballot prefix writes the
+// matches in query order without any staging.  -mum: the raw matches go to the read's scratch slots and lane 0 runs the
+// cleanMUMcand sweep from there into the match slots.
+template <bool WRITE>
+__global__ void __launch_bounds__(THREADS)
+k_mam_exact(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp, uint32_t *__restrict__ cnt) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
+  uint8_t *gbuf = w.long_scratch + ((uint64_t)blockIdx.x * WARPS + warp) * (uint64_t)(w.long_q + P_FRONT + P_BACK + 8);
+  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
+    const int64_t so = b.seq_off[read];
+    const int q = (int)(b.seq_off[read + 1] - so);
+    if (q > w.long_q) {                                        // cannot happen: the host sized the scratch for the longest read
+      if (lane == 0) { atomicAdd(&w.flags[FLAG_LONGREAD], 1u); if (WRITE) w.match_cnt[read] = 0; else cnt[read] = 0; }
+      continue;
+    }
+    __syncwarp();
+    stage_read(ix, b.seq + so, q, sp.nucleotides_only, gbuf, lane);
+    __threadfence_block();
+    const uint8_t *P = gbuf + P_FRONT;
+    Match *dst = nullptr;
+    if (WRITE) dst = sp.mum ? reinterpret_cast<Match *>(w.aln_scratch + slot_base(w, read)) : w.match_slots + slot_base(w, read);
+    int n = 0;
+    for (int p0 = 0; p0 + (int)sp.L <= q; p0 += 32) {
+      const int p = p0 + lane;
+      Match m;
+      const bool ok = p + (int)sp.L <= q && exact_start(ix, P, q, p, sp.L, &m);
+      const unsigned mask = __ballot_sync(0xffffffffu, ok);
+      if (WRITE && ok) dst[n + __popc(mask & ((1u << lane) - 1u))] = m;
+      n += __popc(mask);
+    }
+    if (WRITE) {
+      __syncwarp();
+      if (lane == 0) {
+        if (sp.mum) n = mum_clean(dst, n, w.ord_scratch + slot_base(w, read), w.match_slots + slot_base(w, read));
+        w.match_cnt[read] = (uint32_t)n;
+      }
+    } else if (lane == 0) {
+      cnt[read] = (uint32_t)n;
+      if (n > 65535) atomicAdd(&w.flags[FLAG_OVERFLOW], 1u);   // 16-bit per-read record fields
+    }
+  }
+}
+int launch_mam_exact(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, uint32_t *cnt, cudaStream_t st) {
+  if (!b.n_reads) return 0;
+  if (cnt) k_mam_exact<false><<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p, cnt);
+  else k_mam_exact<true><<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p, nullptr);
+  return 1;
+}
+
 int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
   if (!b.n_reads) return 0;
   if (w.slow) {                                    // split search with the lean seed stage; k_mam_search redoes the flagged reads

@@ -83,6 +83,9 @@ int launch_ext_build(const DevIndex &ix, int k, uint32_t *ext, cudaStream_t st);
 int launch_alpha(const uint8_t *text, uint64_t N, uint32_t *alpha8, cudaStream_t st);
 int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
 int launch_mam_verify(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
+// exact per-start MAM search with CSR slots (any number of matches per read): cnt != null => count pass into cnt,
+// cnt == null => write pass (w.slot_off set; w.long_scratch sized for the longest read of the batch, w.long_q)
+int launch_mam_exact(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, uint32_t *cnt, cudaStream_t st);
 int launch_mem_count(const DevIndex &ix, const BatchDev &b, const SearchParams &p, uint32_t min_len_raw, uint32_t *cnt, cudaStream_t st);
 int launch_mem_write(const DevIndex &ix, const BatchDev &b, const SearchParams &p, uint32_t min_len_raw, const uint64_t *off,
                      Match *matches, cudaStream_t st);

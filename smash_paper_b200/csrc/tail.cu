@@ -165,29 +165,6 @@ __global__ void k_pair_write(BatchDev b, WorkDev w, PairParams pp, uint64_t n_pa
 // digit runs as numbers, leading zeros skipped, of two equal numbers the one with FEWER leading zeros is greater; other
 // bytes by value), ties broken by mate.  The pairs' names are kept, every pair is checked against its predecessor while
 // its batch is appended, and tail_finish sorts the pairs by name only if some pair was out of order.
-__host__ __device__ inline bool nm_digit(const uint8_t *s, uint64_t n, uint64_t i) { return i < n && s[i] >= '0' && s[i] <= '9'; }
-__host__ __device__ inline int strnum_cmp(const uint8_t *a, uint64_t na, const uint8_t *b, uint64_t nb) {
-  uint64_t pa = 0, pb = 0;
-  while (pa < na && pb < nb) {
-    if (nm_digit(a, na, pa) && nm_digit(b, nb, pb)) {
-      while (pa < na && a[pa] == '0') ++pa;
-      while (pb < nb && b[pb] == '0') ++pb;
-      while (nm_digit(a, na, pa) && nm_digit(b, nb, pb) && a[pa] == b[pb]) { ++pa; ++pb; }
-      if (nm_digit(a, na, pa) && nm_digit(b, nb, pb)) {
-        uint64_t i = 0;
-        while (nm_digit(a, na, pa + i) && nm_digit(b, nb, pb + i)) ++i;
-        return nm_digit(a, na, pa + i) ? 1 : nm_digit(b, nb, pb + i) ? -1 : (int)a[pa] - (int)b[pb];
-      }
-      if (nm_digit(a, na, pa)) return 1;
-      if (nm_digit(b, nb, pb)) return -1;
-      if (pa != pb) return pa < pb ? 1 : -1;
-    } else {
-      if (a[pa] != b[pb]) return (int)a[pa] - (int)b[pb];
-      ++pa; ++pb;
-    }
-  }
-  return pa < na ? 1 : pb < nb ? -1 : 0;
-}
 __global__ void k_pair_name_len(BatchDev b, uint64_t n_pairs, uint32_t *__restrict__ cnt) {
   for (uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += (uint64_t)gridDim.x * blockDim.x)
     cnt[p] = (uint32_t)(b.name_off[2 * p + 1] - b.name_off[2 * p]);
@@ -676,6 +653,80 @@ int tail_positions(TailState *t, const int32_t **chrom, const int64_t **pos, uin
     TCU(cudaMemcpy(t->h_pos_pos, t->pos_pos, 8 * m, cudaMemcpyDeviceToHost));
   }
   *chrom = t->h_pos_chrom; *pos = t->h_pos_pos; *n = m;
+  return 0;
+}
+
+// ---- several shards' pairs gathered into one tail (comm.cu).  The read-sharded protocol needs every shard to be a
+// contiguous run of the name order; when the input is not name-sorted the shards' pairs are appended to rank 0's tail in
+// rank order (= submission order of the whole input) and the single-GPU finish, with its name sort, does the rest.
+int tail_totals(TailState *t, uint64_t out[4], cudaStream_t st) {
+  uint64_t h[N_TAIL_COUNTERS] = {0, 0, 0, 0};
+  if (t->d_nhits) {
+    TCU(cudaMemcpyAsync(h, t->d_nhits, sizeof h, cudaMemcpyDeviceToHost, st));
+    TCU(cudaStreamSynchronize(st));
+  }
+  out[0] = t->n_pairs; out[1] = h[CNT_HITS]; out[2] = h[CNT_NAME_BYTES]; out[3] = h[CNT_ORDER_VIOLATIONS];
+  return 0;
+}
+int tail_edge_names(TailState *t, uint8_t *first, uint8_t *last, cudaStream_t st) {
+  memset(first, 0, TAIL_EDGE_NAME); memset(last, 0, TAIL_EDGE_NAME);
+  const uint64_t P = t->n_pairs;
+  if (!P) return 0;
+  uint64_t o[4];
+  TCU(cudaMemcpyAsync(o, t->pair_name_off.p, 16, cudaMemcpyDeviceToHost, st));
+  TCU(cudaMemcpyAsync(o + 2, t->pair_name_off.p + (P - 1), 16, cudaMemcpyDeviceToHost, st));
+  TCU(cudaStreamSynchronize(st));
+  uint8_t *dst[2] = {first, last};
+  for (int k = 0; k < 2; ++k) {
+    const uint64_t len = o[2 * k + 1] - o[2 * k];
+    if (len >= 255) { dst[k][0] = 255; continue; }
+    dst[k][0] = (uint8_t)len;
+    if (len) TCU(cudaMemcpyAsync(dst[k] + 1, t->name_blob.p + o[2 * k], len, cudaMemcpyDeviceToHost, st));
+  }
+  TCU(cudaStreamSynchronize(st));
+  return 0;
+}
+// room for `pairs`/`hits`/`name_bytes` MORE than the tail holds now (exact totals: the appends have all landed)
+int tail_absorb_reserve(TailState *t, uint64_t pairs, uint64_t hits, uint64_t name_bytes, cudaStream_t st) {
+  uint64_t cur[4];
+  int rc;
+  if ((rc = tail_totals(t, cur, st))) return rc;
+  if (!t->d_nhits) { TCU(cudaMalloc((void **)&t->d_nhits, 8 * N_TAIL_COUNTERS)); TCU(cudaMemset(t->d_nhits, 0, 8 * N_TAIL_COUNTERS)); }
+  const uint64_t P = cur[0] + pairs;
+  if ((rc = t->pair_nhits.reserve(P, cur[0], st)) || (rc = t->pair_fp.reserve(2 * P, 2 * cur[0], st)) ||
+      (rc = t->pair_hit_off.reserve(P, cur[0], st)) || (rc = t->hits.reserve(cur[1] + hits + 1, cur[1], st)) ||
+      (rc = t->pair_name_off.reserve(P + 2, cur[0] ? cur[0] + 1 : 0, st)) || (rc = t->name_blob.reserve(cur[2] + name_bytes + 1, cur[2], st)))
+    return rc;
+  if (!cur[0]) TCU(cudaMemsetAsync(t->pair_name_off.p, 0, 8, st));
+  return 0;
+}
+__global__ void k_absorb_fixup(uint64_t *__restrict__ hit_off, uint64_t *__restrict__ name_off, uint64_t from, uint64_t n, uint64_t hit_base,
+                               uint64_t name_base) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    hit_off[from + i] += hit_base;
+    name_off[from + i + 1] += name_base;                      // the shard's offsets 1..n arrived; name_off[from] is this tail's old end
+  }
+}
+__global__ void k_set_counters(uint64_t *c, uint64_t hits, uint64_t name_bytes, uint64_t violations) {
+  c[CNT_HITS] = hits; c[CNT_NAME_BYTES] = name_bytes; c[CNT_ORDER_VIOLATIONS] = violations;
+}
+// a shard's arrays have been written behind this tail's own (pair_hit_off and pair_name_off[1..pairs] still relative to
+// the shard):
+// shift them, count the shard in.  The gathered pairs are by construction not in name order: the finish sorts them.
+int tail_absorb_commit(TailState *t, uint64_t pairs, uint64_t hits, uint64_t name_bytes, cudaStream_t st, uint64_t *launches) {
+  uint64_t cur[4];
+  int rc;
+  if ((rc = tail_totals(t, cur, st))) return rc;
+  if (pairs) {
+    const int grid = (int)((pairs + 256) / 256 < 148 * 8 ? (pairs + 256) / 256 : 148 * 8);
+    k_absorb_fixup<<<grid, 256, 0, st>>>(t->pair_hit_off.p, t->pair_name_off.p, cur[0], pairs, cur[1], cur[2]);
+    ++*launches;
+  }
+  k_set_counters<<<1, 1, 0, st>>>(t->d_nhits, cur[1] + hits, cur[2] + name_bytes, cur[3] + 1);
+  ++*launches;
+  TCU(cudaStreamSynchronize(st));
+  TCU(cudaGetLastError());
+  t->n_pairs = cur[0] + pairs; t->n_hits_bound = cur[1] + hits; t->n_name_bound = cur[2] + name_bytes;
   return 0;
 }
 

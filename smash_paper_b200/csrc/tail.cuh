@@ -41,6 +41,31 @@ struct TailState {
   int32_t *h_pos_chrom = nullptr; int64_t *h_pos_pos = nullptr; size_t h_pos_cap = 0;
 };
 
+// samtools 0.1.x name order (bam_sort.c strnum_cmp), shared by the append-time order check, the name sort and comm.cu
+__host__ __device__ inline bool nm_digit(const uint8_t *s, uint64_t n, uint64_t i) { return i < n && s[i] >= '0' && s[i] <= '9'; }
+__host__ __device__ inline int strnum_cmp(const uint8_t *a, uint64_t na, const uint8_t *b, uint64_t nb) {
+  uint64_t pa = 0, pb = 0;
+  while (pa < na && pb < nb) {
+    if (nm_digit(a, na, pa) && nm_digit(b, nb, pb)) {
+      while (pa < na && a[pa] == '0') ++pa;
+      while (pb < nb && b[pb] == '0') ++pb;
+      while (nm_digit(a, na, pa) && nm_digit(b, nb, pb) && a[pa] == b[pb]) { ++pa; ++pb; }
+      if (nm_digit(a, na, pa) && nm_digit(b, nb, pb)) {
+        uint64_t i = 0;
+        while (nm_digit(a, na, pa + i) && nm_digit(b, nb, pb + i)) ++i;
+        return nm_digit(a, na, pa + i) ? 1 : nm_digit(b, nb, pb + i) ? -1 : (int)a[pa] - (int)b[pb];
+      }
+      if (nm_digit(a, na, pa)) return 1;
+      if (nm_digit(b, nb, pb)) return -1;
+      if (pa != pb) return pa < pb ? 1 : -1;
+    } else {
+      if (a[pa] != b[pb]) return (int)a[pa] - (int)b[pb];
+      ++pa; ++pb;
+    }
+  }
+  return pa < na ? 1 : pb < nb ? -1 : 0;
+}
+
 void tail_init(TailState *t);
 void tail_release(TailState *t);
 void tail_reset(TailState *t);
@@ -58,5 +83,11 @@ int tail_phase_b(TailState *t, int has_prev, int64_t prev_last_pos, int64_t *cou
 int tail_export_keys(TailState *t, uint64_t ordinal_base, const uint64_t **dev_keys, uint64_t *n, cudaStream_t st, uint64_t *launches);
 int tail_reserve(TailState *t, uint64_t pairs, uint64_t hits, cudaStream_t st);
 int tail_positions(TailState *t, const int32_t **chrom, const int64_t **pos, uint64_t *n);
+// ---- gather of several shards' pairs into one tail (comm.cu: inputs that are not in name order) ----
+constexpr int TAIL_EDGE_NAME = 256;                               // bytes per edge name slot: [0] = length (255 = too long), then the name
+int tail_totals(TailState *t, uint64_t out[4] /*pairs, kept hits, name bytes, pairs out of order*/, cudaStream_t st);
+int tail_edge_names(TailState *t, uint8_t *first, uint8_t *last, cudaStream_t st);   // host buffers of TAIL_EDGE_NAME bytes
+int tail_absorb_reserve(TailState *t, uint64_t pairs, uint64_t hits, uint64_t name_bytes, cudaStream_t st);
+int tail_absorb_commit(TailState *t, uint64_t pairs, uint64_t hits, uint64_t name_bytes, cudaStream_t st, uint64_t *launches);
 
 }  // namespace smash

@@ -765,6 +765,31 @@ def test_long_reads(workdir):
         ctx.close(); ix.close()
 
 
+@pytest.mark.parametrize("mode", ["mam", "mum"])
+def test_more_matches_per_read_than_the_stage_holds(workdir, mode):
+    """The reference keeps any number of MAMs per read.  4000-base reads made of 120..160 short unique pieces give ~100 MAMs
+    each, more than the anchor kernels stage in shared memory (64): the range is redone by the exact per-start kernel
+    with CSR slots (k_mam_exact, count + write passes) and the SAM must still equal the oracle's byte for byte; a second
+    batch of ordinary reads on the same context goes back to the anchor path."""
+    from smash_paper_b200 import api
+    d = os.path.join(workdir, "many_matches_" + mode)
+    ref, reads, fa, oix, body = make_case(d, n_pairs=12, seed=91, read_len=4000, frag_min=120, frag_max=160)
+    ix = api.Index.open(fa)
+    ctx = api.Context(ix, min_len=20, nomap=True, mode=api.MODE_MUM if mode == "mum" else api.MODE_MAM)
+    try:
+        omode = O.MUM if mode == "mum" else O.MAM
+        sam = oix.map_batch(reads, min_len=20, n_threads=4, mode=omode)
+        res = ctx.map_batch(reads, want=api.WANT_SAM | api.WANT_MATCHES)
+        assert res.sam == sam
+        per_read = np.diff(res.match_off)
+        assert per_read.max() > 64, per_read.max()
+        from smash_paper_b200 import synth
+        short = synth.make_reads(ref, 50, read_len=150, seed=5)
+        assert ctx.map_batch(short).sam == oix.map_batch(short, min_len=20, n_threads=4, mode=omode)
+    finally:
+        ctx.close(); ix.close()
+
+
 def _driver_case_tail(workdir, tag):
     """case_tail of tests/golden on disk: ref.fa + index (built by the driver), map.bin, reads.sam, bins, chrom sizes."""
     import gzip, shutil, subprocess
@@ -786,17 +811,28 @@ def _driver_case_tail(workdir, tag):
     return exe, d, fa, src
 
 
+@pytest.mark.parametrize("order", ["as_given", "name_sorted"])
 @pytest.mark.parametrize("gpus", [1, 2])
-def test_driver_fused_tail_equals_reference_varbin(workdir, gpus):
+def test_driver_fused_tail_equals_reference_varbin(workdir, gpus, order):
     """bin/mummer -bins ..: mapout + the stages after mummer (mappability_tag, smashMEM.py, chromosome filter, varbin.py)
     in one run.  The varbin file must be BYTE-identical to what the unmodified pipeline printed for these reads
     (tests/golden/case_tail/varbin.txt.gz, incl. Python's repr of the ratio column); with -gpus 2 the reads are cut into
-    two ranges, each GPU maps its own, and the counts meet in smash_bins_finish (one ncclAllReduce)."""
+    two ranges, each GPU maps its own, and the counts meet in smash_bins_finish (one ncclAllReduce).
+    The reference name-sorts the records before smashMEM.py (smash_mapping.sh:23), so its counts do not depend on the
+    order of the input: "as_given" (97 pairs out of `samtools sort -n` order: on 2 GPUs the shards are gathered on rank 0,
+    which sorts by name) and "name_sorted" (the read-sharded exchange proper) must both print the golden file."""
     import glob, gzip, subprocess
     from smash_paper_b200 import api
     if api.device_count() < gpus:
         pytest.skip(f"needs {gpus} GPUs")
-    exe, d, fa, src = _driver_case_tail(workdir, str(gpus))
+    exe, d, fa, src = _driver_case_tail(workdir, f"{gpus}_{order}")
+    if order == "name_sorted":
+        import functools
+        otail = T
+        lines = open(os.path.join(d, "reads.sam"), "rb").read().splitlines(keepends=True)
+        pairs = [(lines[i], lines[i + 1]) for i in range(0, len(lines), 2)]
+        pairs.sort(key=functools.cmp_to_key(lambda a, b: otail.strnum_cmp(a[0].split(b"\t")[0], b[0].split(b"\t")[0])))
+        open(os.path.join(d, "reads.sam"), "wb").write(b"".join(a + b for a, b in pairs))
     cmd = [exe, "-rcref", "-qthreads", "4", "-nomap", "-samin", "-samout", "-bins", "bins.txt", "-chromsizes", "chrom_sizes.txt",
            "-binout", "varbin.txt", "-binstats", "stats.txt"] + (["-gpus", str(gpus)] if gpus > 1 else []) + [fa, "reads.sam"]
     r = subprocess.run(cmd, cwd=d, capture_output=True, text=True)
