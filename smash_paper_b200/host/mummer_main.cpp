@@ -24,6 +24,7 @@
 #include <string>
 #include <thread>
 #include <vector>
+#include <zlib.h>
 
 #include "../../include/smash_b200.h"
 
@@ -47,7 +48,7 @@ struct Options {
             << "  -l N   minimum match length (20)      -n   match only a, c, g, t\n"
             << "  -samin -samout -nomap -rcref -fastq -verbose -qthreads N -mappability\n"
             << "  -minblock N -cached -normalmem (accepted for compatibility)\n"
-            << "  -fastqpair [-replaceN] <ref> <mate1.fq> <mate2.fq>   (extension) the two FASTQ files of a mate pair instead of\n"
+            << "  -fastqpair [-replaceN] <ref> <mate1.fq[.gz]> <mate2.fq[.gz]>   (extension) the two FASTQ files (plain or gzip) of a mate pair instead of\n"
             << "      `-samin <(fastqs_to_sam mate1.fq mate2.fq [1])`; both are parsed on the GPU\n"
             << "  -gpus N   (extension, with -samin) N GPUs, one contiguous range of read pairs each\n"
             << "  -bins <bins.txt> -chromsizes <chrom_sizes.txt> -binout <varbin.txt> [-binstats <stats.txt>] [-mapbin <map.bin>]\n"
@@ -429,19 +430,35 @@ int main(int argc, char **argv) {
         // fastqs_to_sam's loop (fastqs_to_sam.cpp:47-95) + the SAM reader, both on the device: the two files are
         // streamed through two pinned buffers; each call says how much of either it used and which mate the next
         // chunk starts with.
-        FILE *f[2]; char *text[2]; size_t cap[2], len[2] = {0, 0}; bool eof[2] = {false, false};
+        // The files may be gzip streams (smash_mapping.sh:19 feeds fastqs_to_sam from two `zcat`s): zlib inflates them
+        // here, one thread per mate file as the two zcat processes of the script run side by side; plain text passes
+        // through gzread unchanged.
+        gzFile f[2]; char *text[2]; size_t cap[2], len[2] = {0, 0}; bool eof[2] = {false, false};
         size_t chunk_bytes = (size_t)128 << 20;
         if (const char *e = getenv("SMASH_TEXT_CHUNK")) chunk_bytes = std::max<size_t>(4096, strtoull(e, nullptr, 10));
         for (int k = 0; k < 2; ++k) {
-          f[k] = fopen(o.inputs[k].c_str(), "rb");
+          f[k] = gzopen(o.inputs[k].c_str(), "rb");
           if (!f[k]) throw std::runtime_error("Could not open fastq file " + o.inputs[k]);      // fastqs_to_sam.cpp:35-37
+          gzbuffer(f[k], 1u << 20);
           cap[k] = chunk_bytes; text[k] = (char *)smash_host_alloc(cap[k]);
           if (!text[k]) throw std::runtime_error("out of pinned host memory");
         }
         int mate2_first = 0;
         for (;;) {
-          for (int k = 0; k < 2; ++k)
-            while (len[k] < cap[k] && !eof[k]) { const size_t got = fread(text[k] + len[k], 1, cap[k] - len[k], f[k]); len[k] += got; if (!got) eof[k] = true; }
+          {
+            bool bad[2] = {false, false};
+            auto fill = [&](int k) {
+              while (len[k] < cap[k] && !eof[k]) {
+                const int got = gzread(f[k], text[k] + len[k], (unsigned)std::min<size_t>(cap[k] - len[k], (size_t)1 << 30));
+                if (got < 0) { bad[k] = true; return; }
+                len[k] += (size_t)got; if (!got) eof[k] = true;
+              }
+            };
+            std::thread other(fill, 1);
+            fill(0);
+            other.join();
+            for (int k = 0; k < 2; ++k) if (bad[k]) throw std::runtime_error("error reading fastq file " + o.inputs[k] + " (corrupt gzip stream?)");
+          }
           const bool final = eof[0] && eof[1];
           if (in_flight[slot]) drain(slot);
           smash_text t{}; smash_text_info info{};
@@ -464,7 +481,7 @@ int main(int argc, char **argv) {
             memmove(text[k], text[k] + info.consumed[k], len[k]);
           }
         }
-        for (int k = 0; k < 2; ++k) { fclose(f[k]); smash_host_free(text[k]); }
+        for (int k = 0; k < 2; ++k) { gzclose(f[k]); smash_host_free(text[k]); }
         more = false;
       } else if (device_reader) {
         // QueryReader::run's SAM branch (query.cpp:625-648) on the device: the file is streamed through a pinned

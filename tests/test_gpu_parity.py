@@ -333,20 +333,24 @@ def test_driver_streams_sam_text_in_chunks(case, workdir):
     assert got == case["oix"].map_batch(case["reads"], min_len=20, n_threads=4)
 
 
-def test_driver_fastq_pair_matches_reference_pipeline(workdir):
+@pytest.mark.parametrize("gzipped", [False, True])
+def test_driver_fastq_pair_matches_reference_pipeline(workdir, gzipped):
     """`mummer -fastqpair -replaceN ref r1.fq r2.fq` (both FASTQ files parsed on the GPU, streamed in small chunks)
-    against what the unmodified `fastqs_to_sam r1.fq r2.fq 1 | mummer -samin` printed (tests/golden/case_ingest)."""
+    against what the unmodified `fastqs_to_sam r1.fq r2.fq 1 | mummer -samin` printed (tests/golden/case_ingest);
+    gzipped: the .fq.gz files go in as they are (smash_mapping.sh:19 puts a zcat in front of each)."""
     import shutil, subprocess, glob, gzip
     from helpers import GOLDEN, golden_lines
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = os.path.join(root, "smash_paper_b200", "bin", "mummer")
-    d = os.path.join(workdir, "driver_fastqpair")
+    d = os.path.join(workdir, "driver_fastqpair" + ("_gz" if gzipped else ""))
     shutil.rmtree(d, ignore_errors=True)
     os.makedirs(d)
-    for name, src in (("ref.fa", "case_basic/ref.fa.gz"), ("r1.fq", "case_ingest/r1.fq.gz"), ("r2.fq", "case_ingest/r2.fq.gz")):
-        open(os.path.join(d, name), "wb").write(gzip.open(os.path.join(GOLDEN, src)).read())
+    r1, r2 = ("r1.fq.gz", "r2.fq.gz") if gzipped else ("r1.fq", "r2.fq")
+    for name, src in (("ref.fa", "case_basic/ref.fa.gz"), (r1, "case_ingest/r1.fq.gz"), (r2, "case_ingest/r2.fq.gz")):
+        raw = open(os.path.join(GOLDEN, src), "rb").read()
+        open(os.path.join(d, name), "wb").write(raw if name.endswith(".gz") else gzip.decompress(raw))
     env = dict(os.environ, SMASH_TEXT_CHUNK="9000")
-    r = subprocess.run([exe, "-rcref", "-nomap", "-samout", "-fastqpair", "-replaceN", "ref.fa", "r1.fq", "r2.fq"],
+    r = subprocess.run([exe, "-rcref", "-nomap", "-samout", "-fastqpair", "-replaceN", "ref.fa", r1, r2],
                        cwd=d, env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     hdr, lines = golden_lines(os.path.join(GOLDEN, "case_ingest", "mapout_fastq.sam.gz"))

@@ -327,6 +327,14 @@ def test_driver_streaming_loops_over_fake_library(workdir, chunk):
     assert got == _dump(I.parse_fastq_pair(a, b, False))
     got = _run_driver(workdir, "fqm%d" % chunk, ["-fastqpair", "ref.fa", "r1.fq", "r2.fq"], {"r1.fq": b, "r2.fq": a}, chunk)
     assert got == _dump(I.parse_fastq_pair(b, a, False))
+    # gzip streams straight in (smash_mapping.sh:19 runs two zcat processes in front of fastqs_to_sam): one gzip member,
+    # and a multi-member stream as bgzip / Illumina's bcl2fastq write them; mate 2 stays plain text
+    import gzip
+    cut = len(a) // 3
+    members = gzip.compress(a[:cut]) + gzip.compress(a[cut:])
+    for tag, za in (("z1", gzip.compress(a)), ("zm", members)):
+        got = _run_driver(workdir, "fq%s%d" % (tag, chunk), ["-fastqpair", "ref.fa", "r1.fq.gz", "r2.fq"], {"r1.fq.gz": za, "r2.fq": b}, chunk)
+        assert got == _dump(I.parse_fastq_pair(a, b, False))
     q = gz("quirks.sam.gz")
     long_line = b"big\t77\t*\t0\t0\t*\t*\t0\t0\t" + b"A" * 9000 + b"\t" + b"I" * 9000 + b"\n"
     text = q + long_line + q
