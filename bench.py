@@ -357,13 +357,11 @@ def run_ours(args, wl, rank, world):
         # DRAM traffic of that kernel from the committed ncu --set full capture of this workload (1 M reads per launch)
         traffic, traffic_src = None, None
         try:
-            import hashlib
+            sys.path.insert(0, os.path.join(ROOT, "profiles"))
+            from kernel_hash import kernel_source_hash
             tj = json.load(open(os.path.join(ROOT, "profiles", f"r02_dram_traffic_{args.workload}.json")))
-            hsh = hashlib.sha256()
-            for fn in ("kernels.cu", "core.cuh", "records.cuh", "kernels.cuh"):
-                hsh.update(open(os.path.join(ROOT, "smash_paper_b200", "csrc", fn), "rb").read())
             parts = [k for k in dom.split("+") if k in tj]
-            if tj.get("_kernel_sources_sha256") != hsh.hexdigest():
+            if tj.get("_kernel_sources_sha256") != kernel_source_hash():
                 traffic_src = "stale: the kernel sources changed after profiles/r02_dram_traffic_*.json was captured (field dropped)"
             elif parts:
                 traffic = sum(tj[k]["dram_read_bytes"] + tj[k]["dram_write_bytes"] for k in parts) * (B / 1e6)

@@ -40,7 +40,7 @@ for r in csv.reader(open(launches)):
     d = dict(zip(h, r))
     v, u = float(d["Metric Value"].replace(",", "")), d["Metric Unit"]
     v = v / 1e6 if u in ("ns", "nsecond") else v / 1e3 if u in ("us", "usecond") else v
-    agg.setdefault(d["Kernel Name"].split("(")[0], []).append(v)
+    agg.setdefault(d["Kernel Name"].split("(")[0].split("::")[-1], []).append(v)
 with open(f"profiles/{rnd}_ncu_summary_{wl}.md", "w") as f:
     f.write(f"# {rnd} -- ncu evidence, workload {wl}\n\nCommand: `{cmd}`\n\n")
     f.write(f"* full capture (`--set full --clock-control none --import-source on`, one launch of each per-batch kernel of the timed step): raw export `{rnd}_ncu_full_{wl}_raw.csv`\n")
@@ -57,12 +57,9 @@ with open(f"profiles/{rnd}_ncu_summary_{wl}.md", "w") as f:
     tot = sum(per_batch.values())
     f.write("\nShare of the per-batch kernels: " + ", ".join(f"`{k}` {100 * v / tot:.0f} %" for k, v in per_batch.items()) + "\n")
 # the capture is only evidence for the kernels it was taken from: bench.py compares this hash with the sources it runs
-import hashlib
 import os
-root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-hsh = hashlib.sha256()
-for fn in ("kernels.cu", "core.cuh", "records.cuh", "kernels.cuh"):
-    hsh.update(open(os.path.join(root, "smash_paper_b200", "csrc", fn), "rb").read())
-traffic["_kernel_sources_sha256"] = hsh.hexdigest()
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from kernel_hash import kernel_source_hash
+traffic["_kernel_sources_sha256"] = kernel_source_hash()
 json.dump(traffic, open(f"profiles/{rnd}_dram_traffic_{wl}.json", "w"), indent=1)
 print(open(f"profiles/{rnd}_ncu_summary_{wl}.md").read())
