@@ -48,8 +48,13 @@ def parent(args):
     for variant in args.variants.split(","):
         for k in args.seed_k.split(","):
             env = dict(os.environ)
-            if variant != "default":
-                env["SMASH_B200_LIB"] = os.path.join(ROOT, "build", "variants", f"libsmash_b200_{variant}.so")
+            # "name@VAR=VALUE[@VAR2=..]": the default build with environment switches of the library (e.g. flat@SMASH_FLAT_SEED=1)
+            variant, *envs = variant.split("@")
+            for kv in envs:
+                env[kv.split("=", 1)[0]] = kv.split("=", 1)[1]
+            vlib = os.path.join(ROOT, "build", "variants", f"libsmash_b200_{variant}.so")
+            if variant != "default" and (os.path.exists(vlib) or not envs):
+                env["SMASH_B200_LIB"] = vlib
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", "--workload", args.workload, "--variant", variant,
                                 "--seed-k", k, "--l2", args.l2, "--steps", str(args.steps), "--batches", str(args.batches),
                                 "--want", args.want], env=env)

@@ -306,7 +306,7 @@ struct smash_ctx {
   SearchParams sp{};
   // index storage
   uint8_t *text_alloc = nullptr; void *sa = nullptr; void *isa = nullptr; uint8_t *lcp = nullptr;
-  LcpItem *lcp_m = nullptr; uint8_t *uniq = nullptr; void *seed = nullptr; uint32_t *ext = nullptr; uint64_t *startpos = nullptr;
+  LcpItem *lcp_m = nullptr; uint8_t *uniq = nullptr; void *seed = nullptr; uint64_t *seed_irr = nullptr; uint32_t *ext = nullptr; uint64_t *startpos = nullptr;
   uint64_t *sizes = nullptr; char *descr = nullptr; int *descr_off = nullptr; uint64_t *descr8 = nullptr; uint32_t *alpha = nullptr;
   uint8_t *mapbody = nullptr; uint32_t *chrom_off32 = nullptr; uint64_t *chrom_abs64 = nullptr;
   uint64_t n_m = 0;
@@ -465,6 +465,26 @@ static int ctx_finish(smash_ctx *c, const smash_index *ix) {
     CK(dmalloc((void **)&c->ext, 4 * N, &c->index_bytes));
     c->launches += launch_ext_build(d, c->sp.k, c->ext, st);
     d.ext = c->ext;
+    // blocked seed table (core.cuh): the 8-byte table of an index whose anchors use the full seed length is rewritten in
+    // place, so that a bucket's bounds and its candidates' ext codes share one 128-byte line.  SMASH_FLAT_SEED: A/B switch
+    if (d.seed_w == 8 && c->sp.k == d.seed_k && k >= 2 && !getenv("SMASH_FLAT_SEED")) {
+      const uint64_t n_buckets = 1ull << (2 * k), n_blocks = n_buckets >> 4;
+      unsigned long long *d_cnt = nullptr, h_cnt = 0;
+      uint64_t h_end = 0;
+      CK(dmalloc((void **)&d_cnt, 8, nullptr));
+      CUC(cudaMemsetAsync(d_cnt, 0, 8, st));
+      c->launches += launch_seed_irr_count(c->seed, n_blocks, d_cnt, st);
+      CUC(cudaMemcpyAsync(&h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+      CUC(cudaMemcpyAsync(&h_end, (const uint64_t *)c->seed + n_buckets, 8, cudaMemcpyDeviceToHost, st));
+      CUC(cudaStreamSynchronize(st));
+      CK(dmalloc((void **)&c->seed_irr, 8 * 17 * (size_t)(h_cnt + 1), &c->index_bytes));
+      CUC(cudaMemsetAsync(d_cnt, 0, 8, st));
+      c->launches += launch_seed_block(c->seed, n_blocks, c->ext, N, c->seed_irr, d_cnt, st);
+      CUC(cudaStreamSynchronize(st));
+      cudaFree(d_cnt);
+      d.seed_blocked = 1; d.seed_n = n_buckets; d.seed_end = h_end; d.seed_irr = c->seed_irr;
+      if (g_dbg) fprintf(stderr, "[smash-dbg] blocked seed table: %llu blocks of 16 buckets, %llu with a row of exact values\n", (unsigned long long)n_blocks, h_cnt);
+    }
   }
   CUC(cudaStreamSynchronize(st));
   CUC(cudaGetLastError());
@@ -849,7 +869,7 @@ extern "C" void smash_ctx_destroy(smash_ctx *c) {
   smash_comm_destroy(c);
   for (int s = 0; s < SMASH_N_SLOTS; ++s) slot_release(c->slot[s]);
   tail_release(&c->tail);
-  void *ptrs[] = {c->descr8, c->ext, c->text_alloc, c->sa, c->isa, c->lcp, c->lcp_m, c->uniq, c->seed, c->startpos, c->sizes,
+  void *ptrs[] = {c->seed_irr, c->descr8, c->ext, c->text_alloc, c->sa, c->isa, c->lcp, c->lcp_m, c->uniq, c->seed, c->startpos, c->sizes,
                   c->descr, c->descr_off, c->alpha, c->mapbody, c->chrom_off32, c->chrom_abs64};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->own_index) delete c->own_index;

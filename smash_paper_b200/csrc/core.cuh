@@ -47,6 +47,15 @@ struct DevIndex {
   const void *seed;          // S[x] = #suffixes < k-mer x (monotone, 4^k + 1 entries)
   int seed_k;
   int seed_w;                // 4 or 8 bytes per entry
+#ifndef SMASH_SEED_FIELDS_LAST
+  // Blocked form of the 8-byte seed table (seed_blocked != 0; built in place, same bytes): 16 consecutive k-mer buckets
+  // share one 128-byte line that also holds the ext codes of the block's first SEED_INLINE suffixes, so an anchor's
+  // bucket bounds AND its candidates' pre-filter codes arrive with ONE line fill from HBM instead of two (seed_block_*).
+  int seed_blocked;
+  uint64_t seed_n;           // 4^seed_k buckets
+  uint64_t seed_end;         // S[4^seed_k]
+  const uint64_t *seed_irr;  // exact S[16B .. 16B+16] of the blocks holding a bucket of >= 255 suffixes
+#endif
   const uint32_t *ext;       // per SA rank i: 2-bit codes of the 6 text chars after SA[i]+k, the 8 before SA[i], and how many of those are acgt (ext_entry)
   uint32_t alpha[8];         // bitmap of byte values present in text
   // Sequence metadata (fasta.h:24-42)
@@ -63,6 +72,15 @@ struct DevIndex {
   uint64_t map_bytes;
   const uint32_t *chrom_off32;   // per forward chromosome
   const uint64_t *chrom_abs64;   // MemSam::chromosomes (query.cpp:546-552): 64-bit running sums per forward chromosome, [n_fwd] = total ("*")
+#ifdef SMASH_SEED_FIELDS_LAST
+  // Blocked form of the 8-byte seed table (seed_blocked != 0; built in place, same bytes): 16 consecutive k-mer buckets
+  // share one 128-byte line that also holds the ext codes of the block's first SEED_INLINE suffixes, so an anchor's
+  // bucket bounds AND its candidates' pre-filter codes arrive with ONE line fill from HBM instead of two (seed_block_*).
+  int seed_blocked;
+  uint64_t seed_n;           // 4^seed_k buckets
+  uint64_t seed_end;         // S[4^seed_k]
+  const uint64_t *seed_irr;  // exact S[16B .. 16B+16] of the blocks holding a bucket of >= 255 suffixes
+#endif
 };
 
 HD uint64_t sa_at(const DevIndex &ix, uint64_t i) {
@@ -71,7 +89,36 @@ HD uint64_t sa_at(const DevIndex &ix, uint64_t i) {
 HD uint64_t isa_at(const DevIndex &ix, uint64_t i) {
   return ix.w == 4 ? (uint64_t)((const uint32_t *)ix.isa)[i] : ((const uint64_t *)ix.isa)[i];
 }
+// ---- blocked seed table.  Block B = buckets 16B .. 16B+15, one 128-byte line of 16 words:
+//   word 0        bits 0..39 S[16B] (rank of the block's first suffix), bit 63 = irregular;
+//   words 1..2    the 16 bucket sizes S[x+1]-S[x] as bytes (regular blocks: all < 255); irregular: word 1 = row in seed_irr;
+//   bytes 24..127 ext[S[16B] + j], j < SEED_INLINE: the pre-filter codes of the block's first 26 suffixes (the suffix array
+//                 is in bucket order, so these are the block's buckets' candidates; later ones stay in the flat ext array).
+// A random 3.1 Gb genome with k = 16 has 23 suffixes per block: ~96 % of the anchors find all they need in the one line.
+constexpr int SEED_INLINE = 26;
+constexpr uint64_t SEED_BASE_MASK = (1ull << 40) - 1ull;
+HD uint32_t bytesum8(uint64_t v) {                       // sum of the 8 bytes of v
+  const uint64_t m = 0x00ff00ff00ff00ffull;
+  return (uint32_t)((((v & m) + ((v >> 8) & m)) * 0x0001000100010001ull) >> 48);
+}
+// sum of the first i (0..15) count bytes of a regular block
+HD uint32_t seed_block_prefix(uint64_t c0, uint64_t c1, unsigned i) {
+  if (i < 8) return i ? bytesum8(c0 & ((1ull << (8 * i)) - 1ull)) : 0u;
+  return bytesum8(c0) + (i > 8 ? bytesum8(c1 & ((1ull << (8 * (i - 8))) - 1ull)) : 0u);
+}
+// S[x] from the blocked table: the exact paths' lookup (kept out of line: the hot loops around it must not grow)
+HDNI inline uint64_t seed_at_blocked(const DevIndex &ix, uint64_t x) {
+  if (x >= ix.seed_n) return ix.seed_end;
+  const uint64_t *blk = (const uint64_t *)ix.seed + ((x >> 4) << 4);
+  const uint64_t h = blk[0];
+  const unsigned i = (unsigned)(x & 15);
+  if (h >> 63) return ix.seed_irr[blk[1] * 17 + i];
+  return (h & SEED_BASE_MASK) + seed_block_prefix(blk[1], blk[2], i);
+}
 HD uint64_t seed_at(const DevIndex &ix, uint64_t x) {
+#ifndef SMASH_NO_BLOCKED
+  if (ix.seed_blocked) return seed_at_blocked(ix, x);
+#endif
   return ix.seed_w == 4 ? (uint64_t)((const uint32_t *)ix.seed)[x] : ((const uint64_t *)ix.seed)[x];
 }
 // vec_uchar::operator[] (longSA.h:34-39)
@@ -186,13 +233,17 @@ HD bool is_unique(const DevIndex &ix, uint64_t r, uint32_t len, uint64_t sa_inde
 // binary search over the suffix array (optionally inside the seed bucket), its uniqueness and
 // left-maximality.  Returns true and fills m when (p) is a reportable MAM.
 // (kept out of line on the device: it is the rare path and is called from three places of k_mam_search)
+// SEEDED = false: the search starts from the whole suffix array (a few more steps).  k_mam_verify, which gets here only for
+// saturated repeat families, uses that form: with the seed-table lookup compiled into its call tree ptxas schedules its
+// hot loop 20 % slower (measured, profiles/r02 A/B notes in DESIGN.md).
+template <bool SEEDED = true>
 HDNI inline bool exact_start(const DevIndex &ix, const uint8_t *P, int q, int p, uint32_t L, Match *m) {
   if (q - p < (int)L) return false;
   const uint8_t *T = ix.text;
   uint64_t lo = 0, hi = ix.N;
   int kk = ix.seed_k < (int)L ? ix.seed_k : (int)L;
   if (kk > q - p) kk = q - p;
-  if (kk > 0 && ix.seed) {
+  if (SEEDED && kk > 0 && ix.seed) {
     uint64_t code = 0; bool ok = true;
     for (int j = 0; j < kk; ++j) { int b = base_code(P[p + j]); if (b > 3) { ok = false; break; } code = (code << 2) | (uint64_t)b; }
     if (ok) {

@@ -92,6 +92,49 @@ __global__ void k_seed_build(DevIndex ix, SeedT *__restrict__ seed, int k) {
   }
 }
 
+// The 8-byte seed table rewritten IN PLACE into its blocked form (core.cuh): thread B turns S[16B .. 16B+15] into block B.
+// The only word it reads outside its own block is S[16B+16], the first word of block B+1, whose low 40 bits are S[16B+16]
+// before AND after that block's conversion (aligned 8-byte accesses do not tear), so no copy of the table is needed.
+__global__ void k_seed_irr_count(const uint64_t *__restrict__ seed, uint64_t n_blocks, unsigned long long *n_irr) {
+  for (uint64_t B = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; B < n_blocks; B += (uint64_t)gridDim.x * blockDim.x) {
+    bool irr = false;
+    for (int i = 0; i < 16; ++i) irr |= seed[16 * B + i + 1] - seed[16 * B + i] >= 255;
+    if (irr) atomicAdd(n_irr, 1ull);
+  }
+}
+__global__ void k_seed_block(uint64_t *seed, uint64_t n_blocks, const uint32_t *__restrict__ ext, uint64_t N,
+                             uint64_t *__restrict__ irr, unsigned long long *n_irr) {
+  for (uint64_t B = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; B < n_blocks; B += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t s[17];
+    for (int i = 0; i < 16; ++i) s[i] = seed[16 * B + i];
+    s[16] = *(volatile const uint64_t *)(seed + 16 * B + 16) & SEED_BASE_MASK;
+    bool irregular = false;
+    for (int i = 0; i < 16; ++i) irregular |= s[i + 1] - s[i] >= 255;
+    uint64_t wd[16];
+    wd[0] = s[0]; wd[1] = 0; wd[2] = 0;
+    if (irregular) {
+      const uint64_t row = (uint64_t)atomicAdd(n_irr, 1ull);
+      for (int i = 0; i < 17; ++i) irr[row * 17 + i] = s[i];
+      wd[0] |= 1ull << 63; wd[1] = row;
+    } else {
+      for (int i = 0; i < 8; ++i) { wd[1] |= (s[i + 1] - s[i]) << (8 * i); wd[2] |= (s[i + 9] - s[i + 8]) << (8 * i); }
+    }
+    uint32_t e[SEED_INLINE];
+    for (int j = 0; j < SEED_INLINE; ++j) e[j] = s[0] + (uint64_t)j < N ? ext[s[0] + (uint64_t)j] : 0u;
+    for (int j = 0; j < SEED_INLINE / 2; ++j) wd[3 + j] = (uint64_t)e[2 * j] | ((uint64_t)e[2 * j + 1] << 32);
+    uint4 *out = reinterpret_cast<uint4 *>(seed + 16 * B);
+    for (int j = 0; j < 8; ++j) out[j] = make_uint4((uint32_t)wd[2 * j], (uint32_t)(wd[2 * j] >> 32), (uint32_t)wd[2 * j + 1], (uint32_t)(wd[2 * j + 1] >> 32));
+  }
+}
+int launch_seed_irr_count(const void *seed, uint64_t n_blocks, unsigned long long *n_irr, cudaStream_t st) {
+  k_seed_irr_count<<<sm_count() * 8, 256, 0, st>>>((const uint64_t *)seed, n_blocks, n_irr);
+  return 1;
+}
+int launch_seed_block(void *seed, uint64_t n_blocks, const uint32_t *ext, uint64_t N, uint64_t *irr, unsigned long long *n_irr, cudaStream_t st) {
+  k_seed_block<<<sm_count() * 8, 256, 0, st>>>((uint64_t *)seed, n_blocks, ext, N, irr, n_irr);
+  return 1;
+}
+
 __global__ void k_ext_build(DevIndex ix, int k, uint32_t *__restrict__ ext) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ix.N; i += (uint64_t)gridDim.x * blockDim.x)
     ext[i] = ext_entry(ix.text, ix.N, sa_at(ix, i), k);
@@ -468,6 +511,7 @@ __device__ __forceinline__ uint64_t code_window(const uint8_t *code, int bi) {
 #ifndef SMASH_SEED_MINBLK
 #define SMASH_SEED_MINBLK 6
 #endif
+constexpr int SEED_RB = 8;                                    // consecutive reads per warp task
 __global__ void __launch_bounds__(THREADS, SMASH_SEED_MINBLK)
 k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
   __shared__ __align__(16) SeedSmem sm;
@@ -482,9 +526,41 @@ k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
   uint8_t *code = sm.code[warp];
   uint32_t *inv = sm.inv[warp];
   const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
-  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
-    const int64_t so = b.seq_off[read];
-    const int q = (int)(b.seq_off[read + 1] - so);
+  // A warp takes SEED_RB consecutive reads at a time: their offsets arrive with one coalesced load, and the first 64 words
+  // of the NEXT read are requested before the current one is worked on, so the dependent chain of a read (offset -> words
+  // -> seed line -> ext codes) starts two steps in.
+  const uint64_t n_blk = (b.n_reads + SEED_RB - 1) / SEED_RB;
+  for (uint64_t blk = (uint64_t)blockIdx.x * WARPS + warp; blk < n_blk; blk += warps_total) {
+  const uint64_t r0 = blk * SEED_RB;
+  const int nr = (int)(b.n_reads - r0 < (uint64_t)SEED_RB ? b.n_reads - r0 : (uint64_t)SEED_RB);
+  const long long m_so = lane <= nr ? (long long)b.seq_off[r0 + (uint64_t)lane] : 0ll;
+  uint32_t pw0 = 0, pw1 = 0;
+  {
+    const long long so0 = __shfl_sync(0xffffffffu, m_so, 0);
+    const int q0 = (int)(__shfl_sync(0xffffffffu, m_so, 1) - so0);
+    if (q0 <= MAXQ_FAST) {
+      const int mis0 = (int)(so0 & 3), nw0 = (mis0 + q0 + 3) >> 2;
+      const uint32_t *g0 = reinterpret_cast<const uint32_t *>(b.seq + (so0 - mis0));
+      if (lane < nw0) pw0 = __ldg(g0 + lane);
+      if (lane + 32 < nw0) pw1 = __ldg(g0 + 32 + lane);
+    }
+  }
+  for (int ri = 0; ri < nr; ++ri) {
+    const uint64_t read = r0 + (uint64_t)ri;
+    const int64_t so = (int64_t)__shfl_sync(0xffffffffu, m_so, ri);
+    const int q = (int)((int64_t)__shfl_sync(0xffffffffu, m_so, ri + 1) - so);
+    const uint32_t cw0 = pw0, cw1 = pw1;
+    if (ri + 1 < nr) {
+      const long long so1 = __shfl_sync(0xffffffffu, m_so, ri + 1);
+      const int q1 = (int)(__shfl_sync(0xffffffffu, m_so, ri + 2) - so1);
+      pw0 = 0; pw1 = 0;
+      if (q1 <= MAXQ_FAST) {
+        const int mis1 = (int)(so1 & 3), nw1 = (mis1 + q1 + 3) >> 2;
+        const uint32_t *g1 = reinterpret_cast<const uint32_t *>(b.seq + (so1 - mis1));
+        if (lane < nw1) pw0 = __ldg(g1 + lane);
+        if (lane + 32 < nw1) pw1 = __ldg(g1 + 32 + lane);
+      }
+    }
     if (q > MAXQ_FAST) {                           // k_mam_search_long takes these (the host learns the length from the flag)
       if (lane == 0) { atomicMax(&w.flags[FLAG_LONGQ], (uint32_t)q); if (q > w.long_q) w.match_cnt[read] = 0; w.surv_cnt[read] = 0; w.slow[read] = 0; }
       continue;
@@ -501,7 +577,7 @@ k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
       const int i = w0 + lane;
       unsigned nib = 0;
       if (i < nwords) {
-        const uint32_t o = lut4(sm.lut, __ldg(gw + i), 4 * i - mis, q, nib, oddbits);
+        const uint32_t o = lut4(sm.lut, w0 == 0 ? cw0 : w0 == 32 ? cw1 : __ldg(gw + i), 4 * i - mis, q, nib, oddbits);
         lw[i] = o;
         code[CODE_PAD + i] = (uint8_t)code4(o);
         if (4 * i - mis < 0 || 4 * i - mis + 3 >= q) {        // edge words: bytes outside the read can start no k-mer
@@ -527,6 +603,7 @@ k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
       for (int a0 = 0; a0 < n_anchor && !slow; a0 += 32) {
         const int a = a0 + lane, x = a * s;
         uint64_t lo = 0; int cnt = 0; uint32_t rext = 0, lvr = 0;
+        const uint32_t *inl = nullptr; int jb = 0;             // blocked seed table: the block's inline ext codes, the bucket's first entry in it
         if (a < n_anchor && !kmer_invalid(inv, x + mis, k)) {
           // (1) two windows of the 2-bit stream: bases x-8 .. x+k (8 before the k-mer + the k-mer), bases x+k .. x+k+6
           const int xb = x + mis + 4 * CODE_PAD - 8;           // stream position of base x-8
@@ -546,9 +623,27 @@ k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
           }
           // (2) seed bucket (a sorted superset of the k-mer's suffix-array interval)
           const int shk = 2 * (ix.seed_k - k);
-          lo = seed_at(ix, kc << shk);
-          const uint64_t hi = seed_at(ix, (kc + 1) << shk);
-          cnt = (int)(hi - lo < (uint64_t)(BIG_BUCKET + 1) ? hi - lo : (uint64_t)(BIG_BUCKET + 1));
+          if (ix.seed_blocked && shk == 0) {
+            // one 128-byte line: block header (rank of the block's first suffix + 16 bucket sizes) and, behind it, the
+            // ext codes of the block's first SEED_INLINE suffixes
+            const uint64_t *blk = (const uint64_t *)ix.seed + ((kc >> 4) << 4);
+            const uint4 h = __ldg(reinterpret_cast<const uint4 *>(blk));
+            const uint2 h2 = __ldg(reinterpret_cast<const uint2 *>(blk + 2));
+            const uint64_t h0 = (uint64_t)h.x | ((uint64_t)h.y << 32), c0 = (uint64_t)h.z | ((uint64_t)h.w << 32), c1 = (uint64_t)h2.x | ((uint64_t)h2.y << 32);
+            const unsigned bi = (unsigned)(kc & 15);
+            if (h0 >> 63) cnt = BIG_BUCKET + 1;                // a bucket of >= 255 suffixes in the block: exact path
+            else {
+              jb = (int)seed_block_prefix(c0, c1, bi);
+              lo = (h0 & SEED_BASE_MASK) + (uint64_t)jb;
+              const int c = (int)(((bi < 8 ? c0 : c1) >> (8 * (bi & 7))) & 0xffu);
+              cnt = c < BIG_BUCKET + 1 ? c : BIG_BUCKET + 1;
+              inl = reinterpret_cast<const uint32_t *>(blk) + 6;
+            }
+          } else {
+            lo = seed_at(ix, kc << shk);
+            const uint64_t hi = seed_at(ix, (kc + 1) << shk);
+            cnt = (int)(hi - lo < (uint64_t)(BIG_BUCKET + 1) ? hi - lo : (uint64_t)(BIG_BUCKET + 1));
+          }
         }
         if (__any_sync(0xffffffffu, cnt > BIG_BUCKET)) { slow = true; break; }
         // (3) ext filter on the bucket entries: reach test + EXACT left extension (ownership); survivors parked in
@@ -556,7 +651,8 @@ k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
         for (int j0 = 0; !slow && __any_sync(0xffffffffu, j0 < cnt); j0 += 4) {
           uint32_t e[4];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) e[t] = j0 + t < cnt ? __ldg(ix.ext + lo + (uint64_t)(j0 + t)) : 0u;
+          for (int t = 0; t < 4; ++t)
+            e[t] = j0 + t < cnt ? (inl && jb + j0 + t < SEED_INLINE ? __ldg(inl + jb + j0 + t) : __ldg(ix.ext + lo + (uint64_t)(j0 + t))) : 0u;
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             bool pass = false; uint32_t left = 0;
@@ -583,6 +679,7 @@ k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
       w.match_cnt[read] = 0;
     }
     __syncwarp();
+  }
   }
 }
 
@@ -661,7 +758,7 @@ k_mam_verify(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
           if (right >= sp.k && len >= sp.L && len >= 2) {
             const uint64_t ref = c - (uint64_t)left;
             const uint8_t u = ix.uniq[ref];
-            if (u == 255 && len >= 255) r = exact_start(ix, P, q, x - left, sp.L, &m) ? 1 : 0;
+            if (u == 255 && len >= 255) r = exact_start<false>(ix, P, q, x - left, sp.L, &m) ? 1 : 0;
             else if (len >= u) { m.ref = ref; m.qpos = (uint32_t)(x - left); m.len = len; r = 1; }
           }
         }
@@ -802,7 +899,7 @@ int launch_mam_exact(const DevIndex &ix, const BatchDev &b, const WorkDev &w, co
 int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
   if (!b.n_reads) return 0;
   if (w.slow) {                                    // split search with the lean seed stage; k_mam_search redoes the flagged reads
-    k_mam_seed<<<grid_for_warps(b.n_reads, SMASH_SEED_MINBLK), THREADS, 0, st>>>(ix, b, w, p);
+    k_mam_seed<<<grid_for_warps((b.n_reads + SEED_RB - 1) / SEED_RB, SMASH_SEED_MINBLK), THREADS, 0, st>>>(ix, b, w, p);
     k_mam_search<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p);
     return 2;
   }

@@ -80,6 +80,9 @@ struct SearchParams {
 int launch_uniq_build(const DevIndex &ix, uint8_t *uniq, cudaStream_t st);
 int launch_seed_build(const DevIndex &ix, void *seed, int k, int seed_w, cudaStream_t st);
 int launch_ext_build(const DevIndex &ix, int k, uint32_t *ext, cudaStream_t st);
+// 8-byte seed table -> blocked form, in place (core.cuh): count the blocks that need a row of exact values, then convert
+int launch_seed_irr_count(const void *seed, uint64_t n_blocks, unsigned long long *n_irr, cudaStream_t st);
+int launch_seed_block(void *seed, uint64_t n_blocks, const uint32_t *ext, uint64_t N, uint64_t *irr, unsigned long long *n_irr, cudaStream_t st);
 int launch_alpha(const uint8_t *text, uint64_t N, uint32_t *alpha8, cudaStream_t st);
 int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
 int launch_mam_verify(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);
