@@ -272,6 +272,22 @@ int smash_tail_reserve(smash_ctx *ctx, uint64_t max_pairs, uint64_t max_hits);
 /* Forget everything accumulated so far (buffers are kept). */
 int smash_tail_reset(smash_ctx *ctx);
 
+/* ---- GC normalisation of the bin counts: the head of cbs.segment01 (cbs.r:18-25) with lowess.gc (cbs.r:3-7), i.e. what
+ * binning.sh:39 computes first from varbin's counts and gc.txt:
+ *     a <- bincount + 1;  ratio <- a / mean(a[autosomes]);
+ *     lowratio <- exp(log(ratio) - approx(lowess(gc.content, log(ratio), f), xout = gc.content)$y)
+ * R's stats::lowess (clowess, iter robustness iterations, delta = 1 % of the gc range) and stats::approx (ties averaged).
+ * smash_gcnorm_create works out, on the host, everything that depends on gc.content alone (the sort, which points get a
+ * local fit and their windows, the tie groups); smash_gcnorm_run does the arithmetic on the GPU for one vector of counts
+ * (host pointer, or a device pointer such as the one smash_tail_finish / smash_bins_finish filled).  cbs.r uses f = 0.05
+ * and lowess's default iter = 3; autosome[b] != 0 for the bins of chr1..chr22 (cbs.r:13-16, 21).  ratio / lowratio: host
+ * arrays of n_bins doubles (either may be null).  Double precision throughout; results agree with R to rounding. */
+typedef struct smash_gcnorm smash_gcnorm;
+int smash_gcnorm_create(int device, const double *gc_content, const uint8_t *autosome, uint64_t n_bins, double f, int iter,
+                        smash_gcnorm **out);
+int smash_gcnorm_run(smash_gcnorm *g, const int64_t *counts, const void *counts_device, double *ratio, double *lowratio);
+void smash_gcnorm_destroy(smash_gcnorm *g);
+
 /* cudaMemcpy(cudaMemcpyDefault): lets a host language move the small exchange arrays of the multi-GPU
  * tail between library-owned device memory and its own (e.g. torch) tensors. */
 int smash_memcpy(void *dst, const void *src, size_t bytes);

@@ -141,7 +141,9 @@ def r_approx(x, y, xout):
 def gc_normalise(bincount, gc_content, chrom_names):
     """cbs.r:18-25 -> (ratio, lowratio).  chrom_names: bin.chrom column of gc.txt (chr1..chr22, chrX, chrY)."""
     a = np.asarray(bincount, dtype=np.float64) + 1.0
-    num = np.array([23 if c == "chrX" else 24 if c == "chrY" else int(c[3:]) for c in chrom_names])
+    # cbs.r:13-16: substring(chrom, 4) with X -> 23, Y -> 24; anything else non-numeric is NA under as.numeric and drops
+    # out of which(chrom.numeric < 23)
+    num = np.array([23 if c == "chrX" else 24 if c == "chrY" else int(c[3:]) if c[3:].isdigit() else 99 for c in chrom_names])
     ratio = a / np.mean(a[num < 23])
     gc = np.asarray(gc_content, dtype=np.float64)
     lx, ly = r_lowess(gc, np.log(ratio), f=0.05)

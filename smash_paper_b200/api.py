@@ -508,3 +508,33 @@ class Context:
     @property
     def stream(self):
         return load_library().smash_ctx_stream(self.h)
+
+
+class GcNorm:
+    """GC normalisation of bin counts on the GPU: cbs.r:18-25 with lowess.gc (cbs.r:3-7), `smash_gcnorm_*`.
+
+    gc_content: gc.txt's gc.content column; chrom_names: its bin.chrom column (chr1..chr22 are the autosomes whose
+    mean scales the ratio, cbs.r:13-16, 21).  run(counts) -> (ratio, lowratio); counts may be a host array or a device
+    pointer (e.g. the one Context.tail_finish / bins_finish filled)."""
+
+    def __init__(self, gc_content, chrom_names, f=0.05, iter=3, device=0):
+        gc = np.ascontiguousarray(gc_content, dtype=np.float64)
+        num = [23 if c == "chrX" else 24 if c == "chrY" else int(c[3:]) if c[3:].isdigit() else 99 for c in chrom_names]   # as.numeric -> NA: not an autosome
+        auto = np.ascontiguousarray(np.array(num) < 23, dtype=np.uint8)
+        self.n = len(gc)
+        self.h = C.c_void_p()
+        _check(load_library().smash_gcnorm_create(C.c_int(device), _ptr(gc), _ptr(auto), C.c_uint64(self.n), C.c_double(f), C.c_int(iter),
+                                                  C.byref(self.h)))
+
+    def run(self, counts=None, counts_device_ptr=None):
+        ratio = np.zeros(self.n, dtype=np.float64)
+        low = np.zeros(self.n, dtype=np.float64)
+        c = np.ascontiguousarray(counts, dtype=np.int64) if counts is not None else None
+        _check(load_library().smash_gcnorm_run(self.h, _ptr(c) if c is not None else None,
+                                               C.c_void_p(counts_device_ptr) if counts_device_ptr else None, _ptr(ratio), _ptr(low)))
+        return ratio, low
+
+    def close(self):
+        if self.h:
+            load_library().smash_gcnorm_destroy(self.h)
+            self.h = C.c_void_p()

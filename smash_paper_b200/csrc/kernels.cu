@@ -511,7 +511,6 @@ __device__ __forceinline__ uint64_t code_window(const uint8_t *code, int bi) {
 #ifndef SMASH_SEED_MINBLK
 #define SMASH_SEED_MINBLK 6
 #endif
-constexpr int SEED_RB = 8;                                    // consecutive reads per warp task
 __global__ void __launch_bounds__(THREADS, SMASH_SEED_MINBLK)
 k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
   __shared__ __align__(16) SeedSmem sm;
@@ -526,41 +525,9 @@ k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
   uint8_t *code = sm.code[warp];
   uint32_t *inv = sm.inv[warp];
   const uint64_t warps_total = (uint64_t)gridDim.x * WARPS;
-  // A warp takes SEED_RB consecutive reads at a time: their offsets arrive with one coalesced load, and the first 64 words
-  // of the NEXT read are requested before the current one is worked on, so the dependent chain of a read (offset -> words
-  // -> seed line -> ext codes) starts two steps in.
-  const uint64_t n_blk = (b.n_reads + SEED_RB - 1) / SEED_RB;
-  for (uint64_t blk = (uint64_t)blockIdx.x * WARPS + warp; blk < n_blk; blk += warps_total) {
-  const uint64_t r0 = blk * SEED_RB;
-  const int nr = (int)(b.n_reads - r0 < (uint64_t)SEED_RB ? b.n_reads - r0 : (uint64_t)SEED_RB);
-  const long long m_so = lane <= nr ? (long long)b.seq_off[r0 + (uint64_t)lane] : 0ll;
-  uint32_t pw0 = 0, pw1 = 0;
-  {
-    const long long so0 = __shfl_sync(0xffffffffu, m_so, 0);
-    const int q0 = (int)(__shfl_sync(0xffffffffu, m_so, 1) - so0);
-    if (q0 <= MAXQ_FAST) {
-      const int mis0 = (int)(so0 & 3), nw0 = (mis0 + q0 + 3) >> 2;
-      const uint32_t *g0 = reinterpret_cast<const uint32_t *>(b.seq + (so0 - mis0));
-      if (lane < nw0) pw0 = __ldg(g0 + lane);
-      if (lane + 32 < nw0) pw1 = __ldg(g0 + 32 + lane);
-    }
-  }
-  for (int ri = 0; ri < nr; ++ri) {
-    const uint64_t read = r0 + (uint64_t)ri;
-    const int64_t so = (int64_t)__shfl_sync(0xffffffffu, m_so, ri);
-    const int q = (int)((int64_t)__shfl_sync(0xffffffffu, m_so, ri + 1) - so);
-    const uint32_t cw0 = pw0, cw1 = pw1;
-    if (ri + 1 < nr) {
-      const long long so1 = __shfl_sync(0xffffffffu, m_so, ri + 1);
-      const int q1 = (int)(__shfl_sync(0xffffffffu, m_so, ri + 2) - so1);
-      pw0 = 0; pw1 = 0;
-      if (q1 <= MAXQ_FAST) {
-        const int mis1 = (int)(so1 & 3), nw1 = (mis1 + q1 + 3) >> 2;
-        const uint32_t *g1 = reinterpret_cast<const uint32_t *>(b.seq + (so1 - mis1));
-        if (lane < nw1) pw0 = __ldg(g1 + lane);
-        if (lane + 32 < nw1) pw1 = __ldg(g1 + 32 + lane);
-      }
-    }
+  for (uint64_t read = (uint64_t)blockIdx.x * WARPS + warp; read < b.n_reads; read += warps_total) {
+    const int64_t so = b.seq_off[read];
+    const int q = (int)(b.seq_off[read + 1] - so);
     if (q > MAXQ_FAST) {                           // k_mam_search_long takes these (the host learns the length from the flag)
       if (lane == 0) { atomicMax(&w.flags[FLAG_LONGQ], (uint32_t)q); if (q > w.long_q) w.match_cnt[read] = 0; w.surv_cnt[read] = 0; w.slow[read] = 0; }
       continue;
@@ -577,7 +544,7 @@ k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
       const int i = w0 + lane;
       unsigned nib = 0;
       if (i < nwords) {
-        const uint32_t o = lut4(sm.lut, w0 == 0 ? cw0 : w0 == 32 ? cw1 : __ldg(gw + i), 4 * i - mis, q, nib, oddbits);
+        const uint32_t o = lut4(sm.lut, __ldg(gw + i), 4 * i - mis, q, nib, oddbits);
         lw[i] = o;
         code[CODE_PAD + i] = (uint8_t)code4(o);
         if (4 * i - mis < 0 || 4 * i - mis + 3 >= q) {        // edge words: bytes outside the read can start no k-mer
@@ -679,7 +646,6 @@ k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
       w.match_cnt[read] = 0;
     }
     __syncwarp();
-  }
   }
 }
 
@@ -899,7 +865,7 @@ int launch_mam_exact(const DevIndex &ix, const BatchDev &b, const WorkDev &w, co
 int launch_mam_search(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
   if (!b.n_reads) return 0;
   if (w.slow) {                                    // split search with the lean seed stage; k_mam_search redoes the flagged reads
-    k_mam_seed<<<grid_for_warps((b.n_reads + SEED_RB - 1) / SEED_RB, SMASH_SEED_MINBLK), THREADS, 0, st>>>(ix, b, w, p);
+    k_mam_seed<<<grid_for_warps(b.n_reads, SMASH_SEED_MINBLK), THREADS, 0, st>>>(ix, b, w, p);
     k_mam_search<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p);
     return 2;
   }

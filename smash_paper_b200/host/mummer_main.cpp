@@ -37,7 +37,7 @@ struct Options {
        sam_in = false, mappability = false, fastq_pair = false, replace_n = false;
   int threads = 2;
   int gpus = 1;                                   // -gpus N (extension): the query file is cut into N ranges of read pairs
-  std::string bins, chromsizes, binout, binstats, mapbin;   // -bins .. (extension): fused mappability_tag + smashMEM.py + varbin.py
+  std::string bins, chromsizes, binout, binstats, mapbin, gc, gcout;   // -bins .. (extension): fused mappability_tag + smashMEM.py + varbin.py
   std::string ref;
   std::vector<std::string> inputs;
 };
@@ -54,13 +54,15 @@ struct Options {
             << "  -bins <bins.txt> -chromsizes <chrom_sizes.txt> -binout <varbin.txt> [-binstats <stats.txt>] [-mapbin <map.bin>]\n"
             << "      (extension) the stages after mummer in smash_mapping.sh / binning.sh on the GPU(s): mappability_tag,\n"
             << "      smashMEM.py <bam> 0 0 10000 4, the chromosome filter and varbin.py; counts of all GPUs are summed by one\n"
-            << "      NCCL allreduce\n";
+            << "      NCCL allreduce\n"
+            << "  -gc <gc.txt> -gcout <lowratio.txt>   (extension, with -bins) GC normalisation of the counts, the head of cbs.r\n"
+            << "      (cbs.r:18-25): rows `chrom chrompos abspos bincount ratio gc.content lowratio`\n";
   std::exit(1);
 }
 
 Options parse(int argc, char **argv) {
   Options o;
-  enum { L = 1, MUMREF, MAXMATCH, MUM, MUMCAND, N, QTHREADS, SAMOUT, VERBOSE, NOMAP, RCREF, FASTQ, SAMIN, MAPPABILITY, CACHED, NORMALMEM, MINBLOCK, FASTQPAIR, REPLACEN, GPUS, BINS, CHROMSIZES, BINOUT, BINSTATS, MAPBIN };
+  enum { L = 1, MUMREF, MAXMATCH, MUM, MUMCAND, N, QTHREADS, SAMOUT, VERBOSE, NOMAP, RCREF, FASTQ, SAMIN, MAPPABILITY, CACHED, NORMALMEM, MINBLOCK, FASTQPAIR, REPLACEN, GPUS, BINS, CHROMSIZES, BINOUT, BINSTATS, MAPBIN, GC, GCOUT };
   static const option table[] = {
       {"l", required_argument, nullptr, L},          {"mumreference", no_argument, nullptr, MUMREF},
       {"maxmatch", no_argument, nullptr, MAXMATCH},  {"mum", no_argument, nullptr, MUM},
@@ -74,7 +76,8 @@ Options parse(int argc, char **argv) {
       {"replaceN", no_argument, nullptr, REPLACEN},  {"gpus", required_argument, nullptr, GPUS},
       {"bins", required_argument, nullptr, BINS},    {"chromsizes", required_argument, nullptr, CHROMSIZES},
       {"binout", required_argument, nullptr, BINOUT}, {"binstats", required_argument, nullptr, BINSTATS},
-      {"mapbin", required_argument, nullptr, MAPBIN}, {nullptr, 0, nullptr, 0}};
+      {"mapbin", required_argument, nullptr, MAPBIN}, {"gc", required_argument, nullptr, GC},
+      {"gcout", required_argument, nullptr, GCOUT}, {nullptr, 0, nullptr, 0}};
   for (;;) {
     int idx = -1;
     const int c = getopt_long_only(argc, argv, "", table, &idx);
@@ -102,6 +105,8 @@ Options parse(int argc, char **argv) {
       case BINOUT: o.binout = optarg; break;
       case BINSTATS: o.binstats = optarg; break;
       case MAPBIN: o.mapbin = optarg; break;
+      case GC: o.gc = optarg; break;
+      case GCOUT: o.gcout = optarg; break;
       default: std::cerr << "Invalid arguments." << std::endl; usage(argv[0]);
     }
   }
@@ -115,6 +120,7 @@ Options parse(int argc, char **argv) {
   if (o.gpus < 1) throw std::runtime_error("-gpus must be at least 1");
   if (o.gpus > 1 && !o.sam_in) throw std::runtime_error("-gpus needs -samin (the query file is cut into ranges of SAM lines)");
   if (!o.bins.empty() && (o.chromsizes.empty() || o.binout.empty())) throw std::runtime_error("-bins needs -chromsizes and -binout");
+  if (o.gc.empty() != o.gcout.empty() || (!o.gc.empty() && o.bins.empty())) throw std::runtime_error("-gc and -gcout go together and need -bins");
   if (!o.bins.empty() && (!o.rcref || o.mode != SMASH_MODE_MAM)) throw std::runtime_error("-bins needs -rcref and the default match type");
   o.ref = argv[optind];
   for (int i = optind + 1; i < argc; ++i) o.inputs.push_back(argv[i]);
@@ -311,6 +317,43 @@ void write_varbin(const Options &o, const std::vector<std::string> &rows, std::v
             (unsigned long long)st.dups_removed, (unsigned long long)st.reads_kept, (long long)(counts.empty() ? 0 : counts[counts.size() / 2]));
     fclose(s);
   }
+}
+
+// cbs.r:11-25: gc.txt (header line; columns bin.chrom and gc.content) + the counts -> ratio and lowratio per bin, computed on
+// the GPU (smash_gcnorm_*).  One row per bin: varbin's three leading columns, the count, then the three doubles.
+void write_gcnorm(const Options &o, const std::vector<std::string> &rows, const std::vector<int64_t> &counts) {
+  std::ifstream in(o.gc);
+  if (!in) throw std::runtime_error("unable to open " + o.gc);
+  std::string line;
+  if (!std::getline(in, line)) throw std::runtime_error(o.gc + ": empty file");
+  int c_chrom = -1, c_gc = -1, col = 0;
+  { std::istringstream hs(line); std::string t; while (hs >> t) { if (t == "bin.chrom") c_chrom = col; if (t == "gc.content") c_gc = col; ++col; } }
+  if (c_chrom < 0 || c_gc < 0) throw std::runtime_error(o.gc + ": header needs the columns bin.chrom and gc.content (cbs.r:11-12, 23)");
+  std::vector<double> gc; std::vector<uint8_t> autosome;
+  while (std::getline(in, line)) {
+    if (line.empty()) continue;
+    std::istringstream ls(line); std::string t, chrom, g; col = 0;
+    while (ls >> t) { if (col == c_chrom) chrom = t; if (col == c_gc) g = t; ++col; }
+    if (chrom.empty() || g.empty()) throw std::runtime_error(o.gc + ": short line");
+    gc.push_back(strtod(g.c_str(), nullptr));
+    // chrom.numeric < 23 (cbs.r:13-16, 21): chr1..chr22
+    const std::string num = chrom.size() > 3 ? chrom.substr(3) : std::string();
+    char *end = nullptr; const long v = strtol(num.c_str(), &end, 10);
+    autosome.push_back((!num.empty() && *end == 0 && v < 23) ? 1 : 0);
+  }
+  if (gc.size() != counts.size()) throw std::runtime_error(o.gc + ": " + std::to_string(gc.size()) + " bins, the bin file has " + std::to_string(counts.size()));
+  smash_gcnorm *g = nullptr;
+  check(smash_gcnorm_create(0, gc.data(), autosome.data(), gc.size(), 0.05, 3, &g));
+  std::vector<double> ratio(gc.size()), low(gc.size());
+  const int rc = smash_gcnorm_run(g, counts.data(), nullptr, ratio.data(), low.data());
+  smash_gcnorm_destroy(g);
+  check(rc);
+  FILE *f = fopen(o.gcout.c_str(), "wb");
+  if (!f) throw std::runtime_error("could not open " + o.gcout + " for writing");
+  fprintf(f, "chrom\tchrompos\tabspos\tbincount\tratio\tgc.content\tlowratio\n");
+  for (size_t i = 0; i < gc.size(); ++i)
+    fprintf(f, "%s\t%lld\t%.15g\t%.15g\t%.15g\n", rows[i].c_str(), (long long)counts[i], ratio[i], gc[i], low[i]);
+  fclose(f);
 }
 
 bool readable(const std::string &p) { return access(p.c_str(), R_OK) == 0; }
@@ -571,6 +614,7 @@ int main(int argc, char **argv) {
     }
     const uint64_t n_queries = total_queries.load();
     if (!o.bins.empty()) write_varbin(o, bin_rows, counts, tstats);
+    if (!o.gc.empty()) write_gcnorm(o, bin_rows, counts);
     if (!n_queries) std::cerr << "# no reads processed" << std::endl;
     if (o.verbose)
       std::cerr << "# ran " << n_queries << " queries in "

@@ -1,7 +1,7 @@
 """tests/emul/shimlib.py -- TEST INFRASTRUCTURE ONLY.
 
 Builds tests/emul/libsmash_b200_shim.so: the product's own sources (smash_paper_b200/csrc/{api,kernels,tail,mem_search,
-ingest}.cu) compiled with g++ against tests/emul/cuda_shim/cuda_runtime.h, so that the CPU test-suite can EXECUTE the
+ingest,gcnorm}.cu) compiled with g++ against tests/emul/cuda_shim/cuda_runtime.h, so that the CPU test-suite can EXECUTE the
 kernels (blocks of OS threads, real barriers, rendezvous-based warp intrinsics) behind the same C ABI and find logic
 bugs without a GPU.  The sources are not modified: two purely syntactic rewrites are applied to temporary copies,
 
@@ -22,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "smash_paper_b200", "csrc")
 GEN = os.path.join(HERE, "_shim_src")
 SO = os.path.join(HERE, "libsmash_b200_shim.so")
-SOURCES = ["api.cu", "kernels.cu", "tail.cu", "mem_search.cu", "ingest.cu"]
+SOURCES = ["api.cu", "kernels.cu", "tail.cu", "mem_search.cu", "ingest.cu", "gcnorm.cu"]
 
 _LAUNCH = re.compile(r"(\b[A-Za-z_]\w*(?:<[^<>;(){}]*>)?)<<<")
 _EXTERN_SHARED = re.compile(r"extern\s+__shared__\s+((?:__align__\(\d+\)\s+)?)([A-Za-z_][\w ]*?)\s+(\w+)\[\];")

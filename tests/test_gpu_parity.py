@@ -855,3 +855,32 @@ def test_driver_fused_tail_equals_reference_varbin(workdir, gpus, order):
         assert got == exp
     if gpus > 1:
         assert len({os.path.basename(f).split("_")[1] for f in glob.glob(os.path.join(d, "mapout", "*.txt"))}) == gpus
+
+
+def test_driver_gc_normalisation(workdir):
+    """bin/mummer -bins .. -gc gc.txt -gcout lowratio.txt: the counts go on to the head of cbs.r (cbs.r:18-25, lowess.gc)
+    on the GPU; ratio and lowratio per bin against the oracle's restatement of R's lowess/approx (tests/test_gcnorm.py pins
+    it) on the counts the same run printed."""
+    import subprocess
+    from oracle import gcnorm as G
+    exe, d, fa, src = _driver_case_tail(workdir, "gc")
+    bins = [l.split("\t") for l in open(os.path.join(d, "bins.txt")).read().splitlines()]
+    rng = np.random.default_rng(3)
+    gc = np.round(rng.uniform(0.32, 0.6, len(bins)), 6)
+    with open(os.path.join(d, "gc.txt"), "w") as f:
+        f.write("bin.chrom\tbin.start\tbin.end\tbin.length\tgene.count\tcgi.count\tdist.telomere\tgc.content\tcviki_count\tnlaiii_count\n")
+        for b, g in zip(bins, gc):
+            f.write("%s\t%s\t0\t0\t0\t0\t0\t%.6f\t0\t0\n" % (b[0], b[1], g))
+    cmd = [exe, "-rcref", "-qthreads", "4", "-nomap", "-samin", "-samout", "-bins", "bins.txt", "-chromsizes", "chrom_sizes.txt",
+           "-binout", "varbin.txt", "-gc", "gc.txt", "-gcout", "lowratio.txt", fa, "reads.sam"]
+    r = subprocess.run(cmd, cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    counts = np.array([int(l.split("\t")[3]) for l in open(os.path.join(d, "varbin.txt")).read().splitlines()])
+    rows = [l.split("\t") for l in open(os.path.join(d, "lowratio.txt")).read().splitlines()]
+    assert rows[0] == ["chrom", "chrompos", "abspos", "bincount", "ratio", "gc.content", "lowratio"] and len(rows) == len(bins) + 1
+    assert [int(x[3]) for x in rows[1:]] == list(counts)
+    oratio, olow = G.gc_normalise(counts, gc, [b[0] for b in bins])
+    assert np.allclose([float(x[4]) for x in rows[1:]], oratio, rtol=1e-13, atol=0)
+    assert np.allclose([float(x[6]) for x in rows[1:]], olow, rtol=1e-9, atol=0)
+    r = subprocess.run(cmd[:-6] + ["-gc", "gc.txt", fa, "reads.sam"], cwd=d, capture_output=True, text=True)
+    assert r.returncode == 1 and "-gc and -gcout go together" in r.stderr
