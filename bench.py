@@ -3,6 +3,7 @@
 N B200s, next to the reference's CPU path on the box's own host cores.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config1|config2] [--impl ours|reference]
+                  [--scaling strong --total-reads 100000000]     (configs[2]: a fixed job sharded over the GPUs)
 
 One "step" = one batch of synthetic reads through the whole hot path.  Prints ONE JSON line
 (rank 0).  `value` = whole-job reads/s with the batch resident in HBM (CUDA events);
@@ -373,11 +374,11 @@ def run_ours(args, wl, rank, world):
         achieved = per_kernel[dom]["achieved_gbs"]
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": args.workload_desc, "reads_per_step_per_gpu": B, "read_len": wl["read_len"],
                        "min_len": wl["min_len"], "text_len": int(n_text), "n_bins": int(len(starts)),
-                       "index": "built on GPU, replicated per GPU", "sharding": f"reads x{world} (contiguous pair ranges, index replicated); tail exact across shards inside smash_bins_finish (C ABI, NCCL): partitioned exchange of dupe fingerprints, all-gather of shard edges, 1 ncclAllReduce of bin counts",
+                       "total_reads": int(total_reads), "index": "built on GPU, replicated per GPU", "sharding": f"reads x{world} (contiguous pair ranges, index replicated); tail exact across shards inside smash_bins_finish (C ABI, NCCL): partitioned exchange of dupe fingerprints, all-gather of shard edges, 1 ncclAllReduce of bin counts",
                        "l2": "inputs (index touches, 1.7 KB/read SAM) far larger than L2; distinct batch per step",
                        "timing": "sum of per-step CUDA-event durations with the batch resident + tail_finish/allreduce; max over ranks"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // max(args.steps, 1),
@@ -729,7 +730,14 @@ def main():
     ap.add_argument("--batch-reads", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample-pairs", type=int, default=150_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    # BASELINE.json configs[2]: a FIXED number of reads sharded over the GPUs (strong scaling); --steps is then derived
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--total-reads", type=int, default=100_000_000)
     args = ap.parse_args()
+    if args.scaling == "strong":
+        world_ = int(os.environ.get("WORLD_SIZE", 1))
+        args.steps = max(1, args.total_reads // (args.batch_reads * world_))       # batches per rank, all distinct
+        args.no_cpu_baseline = True                                                # the scaling run; the CPU arm has its own line
     wl = WORKLOADS[args.workload]
     if args.workload == "tiny":
         args.batch_reads = min(args.batch_reads, 20000)
