@@ -570,7 +570,7 @@ k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
       for (int a0 = 0; a0 < n_anchor && !slow; a0 += 32) {
         const int a = a0 + lane, x = a * s;
         uint64_t lo = 0; int cnt = 0; uint32_t rext = 0, lvr = 0;
-        const uint32_t *inl = nullptr; int jb = 0;             // blocked seed table: the block's inline ext codes, the bucket's first entry in it
+        const uint32_t *entries = ix.ext; int jb = 0;          // the bucket's ext codes (inside the seed line, or the flat table)
         if (a < n_anchor && !kmer_invalid(inv, x + mis, k)) {
           // (1) two windows of the 2-bit stream: bases x-8 .. x+k (8 before the k-mer + the k-mer), bases x+k .. x+k+6
           const int xb = x + mis + 4 * CODE_PAD - 8;           // stream position of base x-8
@@ -592,24 +592,29 @@ k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
           const int shk = 2 * (ix.seed_k - k);
           if (ix.seed_blocked && shk == 0) {
             // one 128-byte line: block header (rank of the block's first suffix + 16 bucket sizes) and, behind it, the
-            // ext codes of the block's first SEED_INLINE suffixes
-            const uint64_t *blk = (const uint64_t *)ix.seed + ((kc >> 4) << 4);
+            // ext codes of the block's first SEED_INLINE suffixes.  32-bit arithmetic throughout: the sizes are four
+            // words of four bytes, a byte sum is one __vsadu4.
+            const uint32_t *blk = reinterpret_cast<const uint32_t *>(ix.seed) + ((kc >> 4) << 5);
             const uint4 h = __ldg(reinterpret_cast<const uint4 *>(blk));
-            const uint2 h2 = __ldg(reinterpret_cast<const uint2 *>(blk + 2));
-            const uint64_t h0 = (uint64_t)h.x | ((uint64_t)h.y << 32), c0 = (uint64_t)h.z | ((uint64_t)h.w << 32), c1 = (uint64_t)h2.x | ((uint64_t)h2.y << 32);
-            const unsigned bi = (unsigned)(kc & 15);
-            if (h0 >> 63) cnt = BIG_BUCKET + 1;                // a bucket of >= 255 suffixes in the block: exact path
+            const uint2 h2 = __ldg(reinterpret_cast<const uint2 *>(blk + 4));
+            if (h.y >> 31) cnt = BIG_BUCKET + 1;               // a bucket of >= 255 suffixes in the block: exact path
             else {
-              jb = (int)seed_block_prefix(c0, c1, bi);
-              lo = (h0 & SEED_BASE_MASK) + (uint64_t)jb;
-              const int c = (int)(((bi < 8 ? c0 : c1) >> (8 * (bi & 7))) & 0xffu);
+              const unsigned bi = (unsigned)kc & 15u, wsel = bi >> 2, bsh = (bi & 3u) * 8u;
+              const uint32_t below = (1u << bsh) - 1u;          // bytes of the selected word in front of this bucket
+              const uint32_t cw = wsel == 0 ? h.z : wsel == 1 ? h.w : wsel == 2 ? h2.x : h2.y;
+              jb = (int)(__vsadu4(cw & below, 0u) + (wsel > 0 ? __vsadu4(h.z, 0u) : 0u) + (wsel > 1 ? __vsadu4(h.w, 0u) : 0u) +
+                         (wsel > 2 ? __vsadu4(h2.x, 0u) : 0u));
+              const int c = (int)((cw >> bsh) & 0xffu);
+              lo = ((uint64_t)h.x | ((uint64_t)(h.y & 0xffu) << 32)) + (uint64_t)jb;
               cnt = c < BIG_BUCKET + 1 ? c : BIG_BUCKET + 1;
-              inl = reinterpret_cast<const uint32_t *>(blk) + 6;
+              // the whole bucket inside the line (the usual case): its codes are read from there, else from the flat table
+              entries = jb + c <= SEED_INLINE ? blk + 6 + jb : ix.ext + lo;
             }
           } else {
             lo = seed_at(ix, kc << shk);
             const uint64_t hi = seed_at(ix, (kc + 1) << shk);
             cnt = (int)(hi - lo < (uint64_t)(BIG_BUCKET + 1) ? hi - lo : (uint64_t)(BIG_BUCKET + 1));
+            entries = ix.ext + lo;
           }
         }
         if (__any_sync(0xffffffffu, cnt > BIG_BUCKET)) { slow = true; break; }
@@ -618,8 +623,7 @@ k_mam_seed(DevIndex ix, BatchDev b, WorkDev w, SearchParams sp) {
         for (int j0 = 0; !slow && __any_sync(0xffffffffu, j0 < cnt); j0 += 4) {
           uint32_t e[4];
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
-            e[t] = j0 + t < cnt ? (inl && jb + j0 + t < SEED_INLINE ? __ldg(inl + jb + j0 + t) : __ldg(ix.ext + lo + (uint64_t)(j0 + t))) : 0u;
+          for (int t = 0; t < 4; ++t) e[t] = j0 + t < cnt ? __ldg(entries + j0 + t) : 0u;
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             bool pass = false; uint32_t left = 0;

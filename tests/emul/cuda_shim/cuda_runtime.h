@@ -178,6 +178,11 @@ inline int __ffs(int v) { return __builtin_ffs(v); }
 inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { return (unsigned)(((((uint64_t)hi) << 32) | lo) >> (sh & 31)); }
 inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) { return (unsigned)((((((uint64_t)hi) << 32) | lo) << (sh & 31)) >> 32); }
+inline unsigned __vsadu4(unsigned a, unsigned b) {               // sum of absolute differences of the four unsigned bytes
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) { const int x = (int)((a >> (8 * i)) & 0xffu), y = (int)((b >> (8 * i)) & 0xffu); r += (unsigned)(x > y ? x - y : y - x); }
+  return r;
+}
 inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
   const uint64_t v = ((uint64_t)b << 32) | a;
   unsigned r = 0;
