@@ -418,6 +418,17 @@ def run_ours(args, wl, rank, world):
                     raise RuntimeError(ref_files["error"])
                 out["cpu_baseline"] = cpu_baseline(args, wl, ref, ref_files, sample_pairs=args.cpu_sample_pairs, steps=1, check_ctx=ctx)
                 out["parity_check"] = out["cpu_baseline"].pop("parity_check")
+                rc = out["cpu_baseline"].pop("ref_counters", None)
+                if rc and "alg_bytes_per_read" in rc:
+                    # measured on this workload by the counting build of the reference: replaces the survey's estimate
+                    rl = out["roofline"]
+                    rl["ref_alg_bytes_per_read_estimate"] = rl["ref_alg_bytes_per_read"]
+                    rl["ref_alg_bytes_per_read"] = rc["alg_bytes_per_read"]
+                    rl["ref_alg_bytes_source"] = "measured: oracle/_ref counting build on a sample of this workload (ref_counters)"
+                    if rl.get("search_on_ref_alg_bytes_gbs"):
+                        rl["search_on_ref_alg_bytes_gbs"] *= rc["alg_bytes_per_read"] / rl["ref_alg_bytes_per_read_estimate"]
+                    rl["step_on_ref_alg_bytes_frac"] = out["value"] / world * rc["alg_bytes_per_read"] / 1e9 / rl["peak"] if rl.get("peak") else None
+                out["ref_counters"] = rc
             except Exception as e:  # noqa: BLE001 -- the baseline must never break the bench line
                 out["cpu_baseline"] = {"error": str(e)[:300]}
     if out is not None and world == 1:
@@ -635,6 +646,44 @@ def parity_check(ctx, batch, ref_lines):
     return out
 
 
+def reference_counters(wl, genome, files, n_pairs):
+    """the reference with event counters compiled in (oracle/_ref/mummer[-long]-counters, built
+    by oracle/make_counters.py from a patched scratch copy) run on a small sample of THIS workload, to measure the
+    element-granular bytes the reference algorithm touches per read:
+      B_alg = (E+S)(w+1) + K + Lk*4w + q(1+rec) + 2q
+    E edge probes, S binary-search steps (each = one SA entry of w bytes + one text byte), K LCP reads, Lk suffix links
+    (4 SA/ISA entries each), rec records per read (the XE scan of q text bytes each), 2q = bases + qualities."""
+    from oracle import oracle as O
+    fa, workdir, long_ints = files["fa"], files["workdir"], files["long_ints"]
+    exe = os.path.join(O.REF_BIN, "mummer-long-counters" if long_ints else "mummer-counters")
+    if not os.path.exists(exe):
+        raise RuntimeError("oracle/_ref/*-counters not built (oracle/make_counters.py)")
+    cores = os.cpu_count() or 2
+    b = synth.make_reads_fast(genome, n_pairs, read_len=wl["read_len"], seed=1000, first_pair=700_000_000)
+    sam = os.path.join(workdir, "counters.sam")
+    synth.write_sam(b, sam)
+    shutil.rmtree(os.path.join(workdir, "mapout"), ignore_errors=True)
+    p = subprocess.run([exe, "-rcref", "-qthreads", str(max(2, cores)), "-nomap", "-samin", "-samout", fa, sam],
+                       cwd=workdir, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    os.unlink(sam)
+    line = [ln for ln in p.stderr.decode(errors="replace").splitlines() if ln.startswith("# smash_counters")]
+    if not line:
+        raise RuntimeError("no counter line on stderr")
+    c = {k: int(v) for k, v in (kv.split("=") for kv in line[-1].split()[2:])}
+    n = c["reads"]
+    if n != 2 * n_pairs:
+        raise RuntimeError(f"counted {n} reads, sent {2 * n_pairs}")
+    rec = len(mapout_lines(workdir)) / n
+    w, q = (8 if long_ints else 4), wl["read_len"]
+    E, S, K, Lk = c["edge"] / n, c["steps"] / n, c["lcp"] / n, c["links"] / n
+    b_alg = (E + S) * (w + 1) + K + Lk * 4 * w + q * (1 + rec) + 2 * q
+    return {"reads": n, "per_read": {"edge_probes": E, "bsearch_steps": S, "lcp_reads": K, "suffix_links": Lk,
+                                     "traverse_calls": c["traverse"] / n, "matches": c["emit"] / n,
+                                     "link_expansions_failed": c["linkfail"] / n, "records": rec},
+            "w": w, "q": q, "alg_bytes_per_read": b_alg,
+            "formula": "(E+S)(w+1) + K + Lk*4w + q(1+rec) + 2q  (SURVEY 8d), counters of SURVEY App. D measured on this workload"}
+
+
 def cpu_baseline(args, wl, ref, files, sample_pairs, steps, check_ctx=None):
     """The UNMODIFIED reference (oracle/_ref/mummer[-long]) on the host cores, bounded sample per step.
     check_ctx: a GPU context on the same reference -> the first sample's mapout is kept and compared with the GPU
@@ -674,7 +723,14 @@ def cpu_baseline(args, wl, ref, files, sample_pairs, steps, check_ctx=None):
         vals.append(2 * sample_pairs / max(wall - startup, 0.1 * wall))
         log(f"reference step {s}: {2 * sample_pairs} reads wall {wall:.2f}s startup {startup:.2f}s -> {vals[-1]:.0f} reads/s")
         os.unlink(sam)
-    return {"value": float(np.mean(vals)), "unit": UNIT, "cores": cores, "kind": "reference",
+    counters = None
+    if check_ctx is not None:
+        try:
+            counters = reference_counters(wl, genome, files, n_pairs=min(sample_pairs, 25_000))
+        except Exception as e:  # noqa: BLE001
+            counters = {"error": str(e)[:300]}
+        log(f"reference counters: {counters}")
+    return {"value": float(np.mean(vals)), "unit": UNIT, "cores": cores, "kind": "reference", "ref_counters": counters,
             "sample": f"{2 * sample_pairs} reads/step x {steps} through oracle/_ref/{os.path.basename(exe)} -rcref -qthreads {max(2, cores)} "
                       f"-nomap -samin -samout; wall minus a zero-read run ({startup:.2f}s index mmap + buffer init); "
                       f"mapping+SAM only (mappability_tag/smashMEM/varbin stages not included)",

@@ -12,7 +12,12 @@ tail -c 600 gpurun_out/${TAG}_bench.err
 CMD="python bench.py --no-cpu-baseline --steps 2 --warmup 3"
 export SMASH_NO_CHUNKS=1
 $CMD > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err || { echo "plain run failed"; exit 1; }
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launch.log 2>&1; echo "launch list rc=$?"
+# launch list: the per-batch + tail kernels only (the index build alone is several thousand launches of its own)
+KL='regex:^k_(mam|rec|sizes|emit|scan|publish|pair|bump|dd|varbin|perm|export|slot|sort|add_one)'
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KL" -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launch.log 2>&1; echo "launch list rc=$?"
 K='regex:^(k_mam_seed|k_mam_search|k_mam_verify|k_rec_build|k_rec_xe|k_sizes|k_emit_text|k_emit_copy)$'
 timeout 1500 ncu --set full --clock-control none --import-source on -k "$K" -s ${SKIP:-24} -c 8 -o gpurun_out/${TAG}_prof -f $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "full rc=$?"
 tail -5 gpurun_out/${TAG}_ncu_full.log
+# BASELINE.json configs[0]: the reference's CPU-runnable case (50 Mb, 4-byte index) next to 1 GPU
+unset SMASH_NO_CHUNKS
+python bench.py --workload config1 > gpurun_out/${TAG}_bench_config1.json 2> gpurun_out/${TAG}_bench_config1.err; echo "config1 rc=$?"
