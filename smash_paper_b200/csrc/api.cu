@@ -37,6 +37,7 @@ static const bool g_dbg = getenv("SMASH_DEBUG_TIMING") != nullptr;
 static cudaEvent_t g_tl_base = nullptr;
 static const bool g_force_split = getenv("SMASH_FORCE_SPLIT_SEARCH") != nullptr;
 static const bool g_no_split = getenv("SMASH_NO_SPLIT_SEARCH") != nullptr;   // A/B switch: verification inside k_mam_search
+static const bool g_no_tail_overlap = getenv("SMASH_NO_TAIL_OVERLAP") != nullptr;   // A/B switch: tail append after the emit kernels, same stream
 static const bool g_no_chunks = getenv("SMASH_NO_CHUNKS") != nullptr;   // A/B switch for the chunked submit pipeline
 static const bool g_full_sam = getenv("SMASH_FULL_SAM_D2H") != nullptr; // A/B switch: whole SAM text over PCIe instead of the compact transport
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -235,6 +236,7 @@ struct Slot {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool owns_out = false;
   cudaStream_t st_in = nullptr, st_out = nullptr;                  // chunked submit: upload / download streams
+  cudaStream_t st_tail = nullptr; cudaEvent_t ev_tail = nullptr;   // tail append of a range next to its emit kernels
   cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_emit[MAX_CHUNKS] = {}, ev_out = nullptr;
   int n_chunks = 1; uint64_t chunk_r[MAX_CHUNKS + 1] = {}; uint64_t sam_base = 0;
   uint64_t chunk_name_bytes[MAX_CHUNKS] = {};                      // name bytes of each read range (upper bound)
@@ -248,7 +250,7 @@ struct Slot {
   BatchDev bd{};
   // work
   int cap = 0;
-  DBuf<Match> match_slots; DBuf<uint32_t> match_cnt; DBuf<Item> item_slots; DBuf<Rec> rec_slots;
+  DBuf<Match> match_slots; DBuf<Match> mem_stage; DBuf<uint32_t> match_cnt; DBuf<Item> item_slots; DBuf<Rec> rec_slots;
   DBuf<ReadSum> sums; DBuf<uint32_t> nrec; DBuf<uint64_t> rec_base; DBuf<uint32_t> rec_read; DBuf<uint32_t> rec_bytes; DBuf<uint64_t> rec_off; DBuf<uint64_t> sam_total; DBuf<uint64_t> blk_sums2; DBuf<uint64_t> blk_sums;
   DBuf<char> sam; DBuf<uint32_t> flags;
   DBuf<int64_t> csr_off; DBuf<uint64_t> csr_triples;
@@ -386,6 +388,8 @@ static int ctx_begin(const smash_params *p, smash_ctx **out, int rcref) {
     CUC(cudaEventCreate(&c->slot[s].ev0)); CUC(cudaEventCreate(&c->slot[s].ev1));
     for (int e = 0; e < N_EVS; ++e) CUC(cudaEventCreate(&c->slot[s].evs[e]));
     CUC(cudaStreamCreateWithFlags(&c->slot[s].st_in, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->slot[s].st_tail, cudaStreamNonBlocking));
+    CUC(cudaEventCreateWithFlags(&c->slot[s].ev_tail, cudaEventDisableTiming));
     if (s == 0) { CUC(cudaStreamCreateWithFlags(&c->slot[s].st_out, cudaStreamNonBlocking)); c->slot[s].owns_out = true; }
     else c->slot[s].st_out = c->slot[0].st_out;     // ONE download stream: SAM ranges cross PCIe one after another, in submit order
     for (int e = 0; e < MAX_CHUNKS; ++e) {
@@ -809,6 +813,14 @@ static void tail_turn_acquire(smash_ctx *c, Slot &s) {
   c->turn_cv.wait(lk, [&] { return c->tail_turn == s.job_seq; });
   s.turn_held = true;
 }
+static bool tail_turn_try(smash_ctx *c, Slot &s) {            // the turn, if it is this job's already (never waits)
+  if (s.turn_held) return true;
+  if (s.turn_done) return false;
+  std::lock_guard<std::mutex> lk(c->turn_mu);
+  if (c->tail_turn != s.job_seq) return false;
+  s.turn_held = true;
+  return true;
+}
 static void tail_turn_release(smash_ctx *c, Slot &s) {
   if (s.turn_done) return;
   std::unique_lock<std::mutex> lk(c->turn_mu);
@@ -834,7 +846,7 @@ static void host_threads_stop(smash_ctx *c) {
 
 static void slot_release(Slot &s) {
   s.names.release(); s.seq.release(); s.qual.release(); s.opt.release(); s.name_off.release();
-  s.seq_off.release(); s.opt_off.release(); s.read_flag.release(); s.match_slots.release();
+  s.seq_off.release(); s.opt_off.release(); s.read_flag.release(); s.match_slots.release(); s.mem_stage.release();
   s.match_cnt.release(); s.item_slots.release(); s.rec_slots.release(); s.sums.release();
   s.nrec.release(); s.rec_base.release(); s.rec_read.release(); s.rec_bytes.release(); s.rec_off.release(); s.sam_total.release(); s.blk_sums2.release(); s.blk_sums.release(); s.sam.release(); s.flags.release();
   s.csr_off.release(); s.csr_triples.release(); s.long_scratch.release(); s.slot_off.release(); s.aln_scr.release(); s.ord_scr.release(); s.tmp32.release(); s.h_sam.release(); s.h_csr_off.release();
@@ -857,6 +869,8 @@ static void slot_release(Slot &s) {
   s.cmp_bytes.release(); s.cmp_off.release();
   if (s.ev_out) cudaEventDestroy(s.ev_out);
   if (s.st_in) cudaStreamDestroy(s.st_in);
+  if (s.st_tail) cudaStreamDestroy(s.st_tail);
+  if (s.ev_tail) cudaEventDestroy(s.ev_tail);
   if (s.st_out && s.owns_out) cudaStreamDestroy(s.st_out);
   if (s.st) cudaStreamDestroy(s.st);
 }
@@ -1055,8 +1069,8 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
     if (c->prm.mode == SMASH_MODE_MEM) {
       // K2: count pass -> slot offsets (one spare slot per read) -> exact-size buffers -> write pass
       int rc;
-      if ((rc = s.slot_off.ensure(n + 2)) || (rc = s.tmp32.ensure(n + 1))) return rc;
-      nl = launch_mem_count(c->dix, s.bd, c->sp, c->prm.min_len, s.match_cnt.p, s.st);
+      if ((rc = s.slot_off.ensure(n + 2)) || (rc = s.tmp32.ensure(n + 1)) || (rc = s.mem_stage.ensure(n * MEM_STAGE + 1))) return rc;
+      nl = launch_mem_count(c->dix, s.bd, c->sp, c->prm.min_len, s.match_cnt.p, s.mem_stage.p, s.st);
       nl += launch_slot_offsets(s.match_cnt.p, n, s.tmp32.p, s.blk_sums.p, s.slot_off.p, s.st);
       CU(cudaMemcpyAsync(s.h_small.p + 16, s.slot_off.p + n, 8, cudaMemcpyDeviceToHost, s.st));
       CU(cudaStreamSynchronize(s.st));
@@ -1068,7 +1082,7 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
         return rc;
       if (s.compact && ((rc = s.cmp_bytes.ensure(total + 1)) || (rc = s.cmp_off.ensure(total + 2)))) return rc;
       w = work_of(s);
-      nl += launch_mem_write(c->dix, s.bd, c->sp, c->prm.min_len, s.slot_off.p, s.match_slots.p, s.st);
+      nl += launch_mem_write(c->dix, s.bd, c->sp, c->prm.min_len, s.slot_off.p, s.match_slots.p, s.mem_stage.p, s.match_cnt.p, s.st);
     } else if (exact_csr) {
       // K1c: a read of this range has more matches than the anchor kernels stage (STAGE_CAP): exact per-start search with
       // CSR slots, any number of matches per read (count pass -> slot offsets -> exact-size buffers -> write pass)
@@ -1137,6 +1151,17 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
     break;
   }
   const uint64_t bytes = s.h_small.p[0], recs = s.h_small.p[8];
+  // The tail append reads the records only, so it can run NEXT TO the emit kernels (small latency-bound kernels beside
+  // issue-bound ones) on the slot's side stream: everything it reads was complete at the synchronisation above.  Not with
+  // SMASH_WANT_SORTED (the sort re-orders record arrays), and only if the append turn is this batch's already (a worker
+  // never delays its emit launches waiting for an earlier batch).
+  bool tail_early = false;
+  if ((want & SMASH_WANT_TAIL) && !g_no_tail_overlap && !(want & SMASH_WANT_SORTED) && tail_turn_try(c, s)) {
+    int rc = tail_accumulate(&c->tail, c->dix, s.bd, work_of(s), recs, s.chunk_name_bytes[ch], s.st_tail, &s.launches);
+    if (rc) return fail(rc, "tail: %s", tail_error());
+    CU(cudaEventRecord(s.ev_tail, s.st_tail));
+    tail_early = true;
+  }
   const bool range_compact = (want & SMASH_WANT_SAM) && s.compact && sched_choose_compact(c, bytes, s.h_small.p[9], recs, ch);
   if (g_dbg && s.compact) fprintf(stderr, "[smash-dbg]   range %d of slot %d: %s\n", ch, (int)(&s - c->slot), range_compact ? "compact" : "full text");
   if (range_compact) {
@@ -1244,7 +1269,10 @@ static int run_range(smash_ctx *c, Slot &s, int want, bool to_host, int ch, uint
     CU(cudaMemcpyAsync(s.h_matches.p, s.csr_triples.p, 24 * mslots, cudaMemcpyDeviceToHost, s.st));
     s.io_d2h += 8 * (n + 1) + 24 * mslots;
   }
-  if (want & SMASH_WANT_TAIL) {
+  if (tail_early) {
+    CU(cudaStreamWaitEvent(s.st, s.ev_tail, 0));              // the range is done when its append is
+    MARK(5);
+  } else if (want & SMASH_WANT_TAIL) {
     tail_turn_acquire(c, s);                                  // appends happen in the order the batches were submitted
     const double tt = now_ms();
     int rc = tail_accumulate(&c->tail, c->dix, s.bd, work_of(s), recs, s.chunk_name_bytes[ch], s.st, &s.launches);

@@ -89,9 +89,11 @@ int launch_mam_verify(const DevIndex &ix, const BatchDev &b, const WorkDev &w, c
 // exact per-start MAM search with CSR slots (any number of matches per read): cnt != null => count pass into cnt,
 // cnt == null => write pass (w.slot_off set; w.long_scratch sized for the longest read of the batch, w.long_q)
 int launch_mam_exact(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, uint32_t *cnt, cudaStream_t st);
-int launch_mem_count(const DevIndex &ix, const BatchDev &b, const SearchParams &p, uint32_t min_len_raw, uint32_t *cnt, cudaStream_t st);
+constexpr int MEM_STAGE = 8;     // matches per read the MEM counting pass keeps (k_mem_search): such reads are searched once
+int launch_mem_count(const DevIndex &ix, const BatchDev &b, const SearchParams &p, uint32_t min_len_raw, uint32_t *cnt, Match *stage,
+                     cudaStream_t st);
 int launch_mem_write(const DevIndex &ix, const BatchDev &b, const SearchParams &p, uint32_t min_len_raw, const uint64_t *off,
-                     Match *matches, cudaStream_t st);
+                     Match *matches, const Match *stage, const uint32_t *cnt, cudaStream_t st);
 // slot_off = exclusive scan of (match_cnt + 1): one spare slot per read for the unmapped placeholder
 int launch_slot_offsets(const uint32_t *match_cnt, uint64_t n_reads, uint32_t *tmp, uint64_t *blk, uint64_t *slot_off, cudaStream_t st);
 int launch_records(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st);

@@ -63,10 +63,13 @@ __device__ __forceinline__ bool suffixlink(const DevIndex &ix, Ivl *v) {
   return expand_link(ix, v);
 }
 
+// WRITE: matches go to their CSR place.  !WRITE (the counting pass): the first `cap` matches of the read are kept in a
+// small per-read stage, so that a read with at most MEM_STAGE matches -- nearly all of them -- is not searched a second
+// time: the writing pass copies its staged matches to the CSR place and redoes only the reads that overflowed the stage.
 template <bool WRITE> struct Sink {
-  Match *out; uint64_t n;
+  Match *out; uint64_t n; uint64_t cap;
   __device__ __forceinline__ void emit(uint64_t ref, uint64_t qpos, uint64_t len) {
-    if (WRITE) { out[n].ref = ref; out[n].qpos = (uint32_t)qpos; out[n].len = (uint32_t)len; }
+    if (WRITE || n < cap) { out[n].ref = ref; out[n].qpos = (uint32_t)qpos; out[n].len = (uint32_t)len; }
     ++n;
   }
 };
@@ -133,27 +136,39 @@ __device__ void find_mem(const DevIndex &ix, const QueryView &P, uint64_t min_le
 template <bool WRITE>
 __global__ void __launch_bounds__(128)
 k_mem_search(DevIndex ix, BatchDev b, SearchParams sp, uint32_t min_len_raw, uint32_t *__restrict__ cnt,
-             const uint64_t *__restrict__ off, Match *__restrict__ matches) {
+             const uint64_t *__restrict__ off, Match *__restrict__ matches, Match *__restrict__ stage) {
   for (uint64_t read = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; read < b.n_reads; read += (uint64_t)gridDim.x * blockDim.x) {
     const int64_t so = b.seq_off[read];
     QueryView P{b.seq + so, (int)(b.seq_off[read + 1] - so), sp.nucleotides_only};
-    Sink<WRITE> s{WRITE ? matches + off[read] : nullptr, 0};
-    find_mem<WRITE>(ix, P, (uint64_t)min_len_raw, &s);
-    if (!WRITE) cnt[read] = (uint32_t)(s.n > 0xfffffffeull ? 0xfffffffeull : s.n);
+    if (WRITE) {
+      const uint64_t o = off[read], n = cnt[read];
+      if (stage && n <= (uint64_t)MEM_STAGE) {                       // searched already: the counting pass kept its matches
+        for (uint64_t i = 0; i < n; ++i) matches[o + i] = stage[read * MEM_STAGE + i];
+        continue;
+      }
+      Sink<WRITE> s{matches + o, 0, 0};
+      find_mem<WRITE>(ix, P, (uint64_t)min_len_raw, &s);
+    } else {
+      Sink<WRITE> s{stage ? stage + read * MEM_STAGE : nullptr, 0, stage ? (uint64_t)MEM_STAGE : 0};
+      find_mem<WRITE>(ix, P, (uint64_t)min_len_raw, &s);
+      cnt[read] = (uint32_t)(s.n > 0xfffffffeull ? 0xfffffffeull : s.n);
+    }
   }
 }
 
-int launch_mem_count(const DevIndex &ix, const BatchDev &b, const SearchParams &p, uint32_t min_len_raw, uint32_t *cnt, cudaStream_t st) {
+int launch_mem_count(const DevIndex &ix, const BatchDev &b, const SearchParams &p, uint32_t min_len_raw, uint32_t *cnt, Match *stage,
+                     cudaStream_t st) {
   if (!b.n_reads) return 0;
   const uint64_t need = (b.n_reads + 127) / 128;
-  k_mem_search<false><<<(unsigned)(need < 148 * 16 ? need : 148 * 16), 128, 0, st>>>(ix, b, p, min_len_raw, cnt, nullptr, nullptr);
+  k_mem_search<false><<<(unsigned)(need < 148 * 16 ? need : 148 * 16), 128, 0, st>>>(ix, b, p, min_len_raw, cnt, nullptr, nullptr, stage);
   return 1;
 }
 int launch_mem_write(const DevIndex &ix, const BatchDev &b, const SearchParams &p, uint32_t min_len_raw, const uint64_t *off,
-                     Match *matches, cudaStream_t st) {
+                     Match *matches, const Match *stage, const uint32_t *cnt, cudaStream_t st) {
   if (!b.n_reads) return 0;
   const uint64_t need = (b.n_reads + 127) / 128;
-  k_mem_search<true><<<(unsigned)(need < 148 * 16 ? need : 148 * 16), 128, 0, st>>>(ix, b, p, min_len_raw, nullptr, off, matches);
+  k_mem_search<true><<<(unsigned)(need < 148 * 16 ? need : 148 * 16), 128, 0, st>>>(ix, b, p, min_len_raw, const_cast<uint32_t *>(cnt), off,
+                                                                                   matches, const_cast<Match *>(stage));
   return 1;
 }
 
