@@ -406,7 +406,13 @@ def run_ours(args, wl, rank, world):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "ref_alg_bytes_per_read": wl["ref_alg_bytes_per_read"],
                          "search_on_ref_alg_bytes_gbs": B * wl["ref_alg_bytes_per_read"] / (search_ms / 1e3) / 1e9 if search_ms > 0 else None,
-                         "split_search": bool(split)},
+                         "split_search": bool(split),
+                         # the dominant kernel fetches random 128-byte lines: its memory ceiling is the random-line rate of
+                         # the GPU at the kernel's footprint, measured by profiles/microbench/random_gather.cu (committed
+                         # numbers, not re-measured here), next to which the ncu DRAM traffic of the kernel is placed
+                         "random_line_ceiling": {"gbs": 4640.0, "glines_per_s": 36.3, "valid_up_to_footprint_gb": 68,
+                                                 "source": "profiles/r02_random_gather.md",
+                                                 "traffic_frac": (traffic / (per_kernel[dom]["ms"] / 1e3) / 1e9 / 4640.0) if traffic else None}},
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "sam_bytes_per_read": sam_bytes / max(B * args.steps, 1),
             "tail": stats, "tail_finish_ms": finish_ms, "index_build_s": t_index, "mappability_build_s": t_map,

@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 TAG=${1:-r02}
 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_gputest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${TAG}_gputest.log
 tail -3 gpurun_out/${TAG}_gputest.log
-python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
+python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 tail -c 600 gpurun_out/${TAG}_bench.err
 CMD="python bench.py --no-cpu-baseline --steps 2 --warmup 3"
 export SMASH_NO_CHUNKS=1
