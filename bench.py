@@ -698,6 +698,13 @@ def cpu_baseline(args, wl, ref, files, sample_pairs, steps, check_ctx=None):
     cores = os.cpu_count() or 2
     fa, workdir, long_ints, built = files["fa"], files["workdir"], files["long_ints"], files["built"]
     exe = os.path.join(O.REF_BIN, "mummer-long" if long_ints else "mummer")
+    march = "x86-64-v3"
+    try:                                                 # closest build to the reference's -march=native that this host can run
+        cpu_flags = set(next(ln for ln in open("/proc/cpuinfo") if ln.startswith("flags")).split())
+        if {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= cpu_flags and os.path.exists(exe + "-v4"):
+            exe, march = exe + "-v4", "x86-64-v4"
+    except (OSError, StopIteration):
+        pass
     empty = os.path.join(workdir, "empty.sam")
     open(empty, "w").close()
 
@@ -739,7 +746,7 @@ def cpu_baseline(args, wl, ref, files, sample_pairs, steps, check_ctx=None):
     return {"value": float(np.mean(vals)), "unit": UNIT, "cores": cores, "kind": "reference", "ref_counters": counters,
             "sample": f"{2 * sample_pairs} reads/step x {steps} through oracle/_ref/{os.path.basename(exe)} -rcref -qthreads {max(2, cores)} "
                       f"-nomap -samin -samout; wall minus a zero-read run ({startup:.2f}s index mmap + buffer init); "
-                      f"mapping+SAM only (mappability_tag/smashMEM/varbin stages not included)",
+                      f"mapping+SAM only (mappability_tag/smashMEM/varbin stages not included); reference flags -Ofast -march={march}",
             "index": built, "per_step": vals, "parity_check": parity}
 
 
