@@ -69,7 +69,7 @@ void tail_release(TailState *t) {
   t->name_blob.release(); t->pair_name_off.release();
   for (auto &b : t->scr) b.release();
   t->exp_keys.release();
-  void *d[] = {t->bin_starts, t->chrom_off, t->batch_cnt, t->batch_off, t->blk, t->counts, t->pos_chrom, t->pos_pos, t->d_nhits};
+  void *d[] = {t->bin_starts, t->chrom_off, t->batch_cnt, t->batch_off, t->blk, t->counts, t->pos_chrom, t->pos_pos, t->d_nhits, t->bin_lut};
   for (void *p : d) if (p) cudaFree(p);
   if (t->h_pos_chrom) cudaFreeHost(t->h_pos_chrom);
   if (t->h_pos_pos) cudaFreeHost(t->h_pos_pos);
@@ -87,6 +87,28 @@ int tail_configure(TailState *t, const int64_t *bin_starts, uint64_t n_bins, con
   TCU(cudaMalloc((void **)&t->chrom_off, 8 * (n_chrom + 1)));
   TCU(cudaMalloc((void **)&t->counts, 8 * n_bins));
   TCU(cudaMemcpy(t->bin_starts, bin_starts, 8 * n_bins, cudaMemcpyHostToDevice));
+  // granule table for bin_of: lut[g] = number of starts <= g << shift, at most 2^20 granules; only for sorted,
+  // non-negative starts (anything else keeps the plain bisect, whose answer on unsorted input is what python's is)
+  if (t->bin_lut) { cudaFree(t->bin_lut); t->bin_lut = nullptr; }
+  t->lut_n = 0; t->lut_shift = 0;
+  bool sorted = n_bins > 0 && n_bins < 0xffffffffull && bin_starts[0] >= 0;
+  for (uint64_t i = 1; sorted && i < n_bins; ++i) sorted = bin_starts[i - 1] <= bin_starts[i];
+  if (sorted) {
+    const uint64_t top = (uint64_t)bin_starts[n_bins - 1];
+    int shift = 0;
+    while ((top >> shift) + 2 > (1ull << 20)) ++shift;
+    const uint64_t n = (top >> shift) + 2;
+    std::vector<uint32_t> lut(n);
+    uint64_t c = 0;
+    for (uint64_t g = 0; g < n; ++g) {
+      const uint64_t v = g << shift;
+      while (c < n_bins && (uint64_t)bin_starts[c] <= v) ++c;
+      lut[g] = (uint32_t)c;
+    }
+    TCU(cudaMalloc((void **)&t->bin_lut, 4 * n));
+    TCU(cudaMemcpy(t->bin_lut, lut.data(), 4 * n, cudaMemcpyHostToDevice));
+    t->lut_n = n; t->lut_shift = shift;
+  }
   TCU(cudaMemcpy(t->chrom_off, chrom_off, 8 * n_chrom, cudaMemcpyHostToDevice));
   t->n_bins = n_bins; t->n_chrom = n_chrom; t->hit_window = hit_window; t->min_excess = min_excess;
   t->configured = true;
@@ -391,32 +413,40 @@ __global__ void k_pair_out_write(const uint32_t *__restrict__ nhits, const uint6
   }
 }
 
-__device__ __forceinline__ uint64_t bin_of(const int64_t *__restrict__ starts, uint64_t n_bins, int64_t abspos) {
-  uint64_t lo = 0, hi = n_bins;                              // bisect.bisect (right) - 1, varbin.py:89-92
+// bisect.bisect (right) - 1 over the bin starts (varbin.py:89-92).  With the granule table of tail_configure
+// (lut[g] = number of starts <= g << shift) the search runs between lut[g] and lut[g + 1]: bins are far wider than a
+// granule, so it ends after zero to two probes instead of log2(n_bins) = 16..19 dependent loads.
+struct BinLut { const uint32_t *lut; uint64_t n; int shift; };
+__device__ __forceinline__ uint64_t bin_of(const int64_t *__restrict__ starts, uint64_t n_bins, int64_t abspos, const BinLut &bl) {
+  uint64_t lo = 0, hi = n_bins;
+  if (bl.n && abspos >= 0) {
+    const uint64_t g = (uint64_t)abspos >> bl.shift;
+    if (g + 1 < bl.n) { lo = bl.lut[g]; hi = bl.lut[g + 1]; } else lo = bl.lut[bl.n - 1];
+  }
   while (lo < hi) { uint64_t mid = (lo + hi) >> 1; if (starts[mid] <= abspos) lo = mid + 1; else hi = mid; }
   return lo ? lo - 1 : n_bins - 1;                           // python's counts[-1]
 }
 // varbin.py:56-58: a line whose position string equals the previous kept line's is a duplicate
 __global__ void k_varbin_global(const int64_t *__restrict__ f_pos, const int64_t *__restrict__ f_abs, uint64_t n,
                                 const int64_t *__restrict__ starts, uint64_t n_bins, unsigned long long *counts,
-                                unsigned long long *stats /*[3]=dups*/, int has_prev, int64_t prev_pos) {
+                                unsigned long long *stats /*[3]=dups*/, int has_prev, int64_t prev_pos, BinLut bl) {
   unsigned long long dups = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     if (i ? f_pos[i] == f_pos[i - 1] : (has_prev && f_pos[0] == prev_pos)) { ++dups; continue; }
-    atomicAdd(&counts[bin_of(starts, n_bins, f_abs[i])], 1ull);
+    atomicAdd(&counts[bin_of(starts, n_bins, f_abs[i], bl)], 1ull);
   }
   if (dups) atomicAdd(&stats[3], dups);
 }
 __global__ void k_varbin_smem(const int64_t *__restrict__ f_pos, const int64_t *__restrict__ f_abs, uint64_t n,
                               const int64_t *__restrict__ starts, uint64_t n_bins, unsigned long long *counts,
-                              unsigned long long *stats, int has_prev, int64_t prev_pos) {
+                              unsigned long long *stats, int has_prev, int64_t prev_pos, BinLut bl) {
   extern __shared__ uint32_t hist[];
   for (uint64_t k = threadIdx.x; k < n_bins; k += blockDim.x) hist[k] = 0;
   __syncthreads();
   unsigned long long dups = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
     if (i ? f_pos[i] == f_pos[i - 1] : (has_prev && f_pos[0] == prev_pos)) { ++dups; continue; }
-    atomicAdd(&hist[bin_of(starts, n_bins, f_abs[i])], 1u);
+    atomicAdd(&hist[bin_of(starts, n_bins, f_abs[i], bl)], 1u);
   }
   if (dups) atomicAdd(&stats[3], dups);
   __syncthreads();
@@ -560,15 +590,16 @@ int tail_phase_b(TailState *t, int has_prev, int64_t prev_last_pos, int64_t *cou
     TCU(cudaMemsetAsync(d_stats, 0, 32, st));
     const int64_t *f_pos = (const int64_t *)t->scr[10].p, *f_abs = (const int64_t *)t->scr[11].p;
     const size_t smem = 4 * t->n_bins;
+    const BinLut bl{t->bin_lut, t->lut_n, t->lut_shift};
     const int vgrid = (int)((n_f + 255) / 256 < 148 * 2 ? (n_f + 255) / 256 : 148 * 2);
     if (smem <= 200 * 1024 && n_f >= 16 * t->n_bins) {
       TCU(cudaFuncSetAttribute(k_varbin_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const int g = vgrid < 148 ? vgrid : 148;
       k_varbin_smem<<<g, 1024, smem, st>>>(f_pos, f_abs, n_f, t->bin_starts, t->n_bins, (unsigned long long *)t->counts,
-                                           (unsigned long long *)d_stats, has_prev, prev_last_pos);
+                                           (unsigned long long *)d_stats, has_prev, prev_last_pos, bl);
     } else {
       k_varbin_global<<<vgrid, 256, 0, st>>>(f_pos, f_abs, n_f, t->bin_starts, t->n_bins, (unsigned long long *)t->counts,
-                                             (unsigned long long *)d_stats, has_prev, prev_last_pos);
+                                             (unsigned long long *)d_stats, has_prev, prev_last_pos, bl);
     }
     *launches += 1;
     TCU(cudaMemcpyAsync(h_stats, d_stats, 32, cudaMemcpyDeviceToHost, st));

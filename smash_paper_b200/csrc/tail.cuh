@@ -16,6 +16,7 @@ struct TailState {
   bool configured = false;
   // configuration
   int64_t *bin_starts = nullptr; uint64_t n_bins = 0;
+  uint32_t *bin_lut = nullptr; uint64_t lut_n = 0; int lut_shift = 0;   // granule table of bin_of (tail.cu)
   int64_t *chrom_off = nullptr; uint64_t n_chrom = 0;   // >=0 abs offset, -1 filtered by the regex, -2 by varbin
   int64_t hit_window = 10000; int32_t min_excess = 4;
   // accumulated over batches (pair index = order of submission)

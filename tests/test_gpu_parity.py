@@ -678,6 +678,45 @@ def test_bin_resolution_sweep(case, workdir, parts):
         ctx.close(); ix.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["late_first_bin", "one_bin", "tiny_bins", "unsorted", "dense_at_the_end"])
+def test_bin_lookup_equals_bisect_on_odd_bin_tables(case, workdir, kind):
+    """varbin.py:89-92 is `bisect.bisect(starts, abspos) - 1` with python's negative index for positions before the first
+    start.  The device lookup narrows the search with a granule table (tail.cu bin_of): bin tables that stress it --
+    first bin far from 0 (counts[-1] case), one bin, thousands of bins inside one granule, bins piled up at the end, and an
+    unsorted table (plain bisect, whatever it answers) -- must count exactly like python's bisect on the same positions."""
+    from smash_paper_b200 import api
+    ix = api.Index.open(case["fa"])
+    ctx = api.Context(ix, min_len=20, nomap=True)
+    try:
+        ctx.load_mappability(case["body"])
+        sam = case["oix"].map_batch(case["reads"], min_len=20, n_threads=4)
+        exp = oracle_tail(case["oix"], case["body"], sam, case["dir"], case["fa"])
+        ci = exp["chrominfo"]
+        total = sum(int(v[1]) for v in ci.values())
+        rng = np.random.default_rng(11)
+        if kind == "late_first_bin":
+            starts = list(range(total // 3, total, 997))
+        elif kind == "one_bin":
+            starts = [total // 2]
+        elif kind == "tiny_bins":
+            starts = sorted(set([0] + [int(x) for x in rng.integers(total // 4, total // 4 + 3000, 2500)] + [total // 2]))
+        elif kind == "dense_at_the_end":
+            starts = [0, 10] + list(range(total - 5000, total, 3))
+        else:
+            starts = [int(x) for x in rng.permutation(np.arange(0, total, 1009))]
+        ctx.tail_configure(starts, list(ci.keys()), [int(v[2]) for v in ci.values()])
+        ctx.map_batch(case["reads"], want=api.WANT_TAIL)
+        counts, st = ctx.tail_finish()
+        # the restated varbin.py loop (oracle/tail.py, pinned on the reference script) on the oracle's positions list
+        want, n_total, n_dups, n_kept = T.varbin(exp["positions"], [["c", "0", str(x)] for x in starts], ci)
+        assert n_total > 500
+        assert (st["total_reads"], st["dups_removed"], st["reads_kept"]) == (n_total, n_dups, n_kept)
+        assert np.array_equal(counts, np.array(want))
+    finally:
+        ctx.close(); ix.close()
+
+
 def test_error_paths(workdir, case):
     """Errors the reference raises as paa::Error come back as SmashError with the same wording."""
     import shutil
