@@ -559,8 +559,11 @@ def kernel_alg_bytes(wl, N, n_rec, sam_bytes, split=False):
     name = 10
     surv = anchors * true_cand                                      # candidates left after the 4+4 filter (chance hits: ~2 %)
     if split:
-        # read in + lower-cased copy out, per anchor two seed entries, per bucket entry its 4-byte ext code, parked candidates out
-        search = q + q + anchors * 2 * seed_w + cand * 4 + surv * 8
+        # read in + lower-cased copy out; per anchor the bucket bounds -- two entries of the flat seed table, or, in the blocked
+        # table of the 8-byte case, the 24-byte block header the kernel loads (40-bit rank + 16 bucket sizes) --;
+        # per bucket entry its 4-byte ext code; parked candidates out
+        blocked = seed_w == 8 and k == 16
+        search = q + q + anchors * (24 if blocked else 2 * seed_w) + cand * 4 + surv * 8
         # parked candidates in, their SA entry and the 8-byte text window left of the seed, the read once; per fragment
         # (the candidates that own a diagonal) its text span and one U byte; matches out
         verify = surv * (8 + w + 8) + q + (q / frag) * (frag + 1) + 16 * n_rec
