@@ -33,6 +33,19 @@ static int sm_count() {
   }
   return g_sm_count;
 }
+// grid caps (CTAs per SM) of the thread-per-item kernels; A/B knobs of the variant builds.  k_rec_build and k_sizes have
+// very uneven items (0..10 matches per read, records of an unmapped read vs a five-fragment one): 64 CTAs per SM instead
+// of 16 lets the block scheduler even them out (records 1.140 -> 1.115 ms, sizes+scan 0.290 -> 0.245 ms, r02w A/B);
+// k_emit_text gains nothing from it (it only moves the tail append beside k_emit_copy instead).
+#ifndef SMASH_RECB_CTAS
+#define SMASH_RECB_CTAS 64
+#endif
+#ifndef SMASH_SIZES_CTAS
+#define SMASH_SIZES_CTAS 64
+#endif
+#ifndef SMASH_TEXT_CTAS
+#define SMASH_TEXT_CTAS 16
+#endif
 static int grid_for_warps(uint64_t n_items, int ctas_per_sm) {
   uint64_t need = (n_items + WARPS - 1) / WARPS;
   uint64_t cap = (uint64_t)sm_count() * (uint64_t)ctas_per_sm;
@@ -1075,7 +1088,7 @@ int launch_records(const DevIndex &ix, const BatchDev &b, const WorkDev &w, cons
   if (w.slot_off) {
     k_rec_build_big<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p);
   } else if (w.cap <= LOCAL_CAP) {
-    const uint64_t need = (b.n_reads + 127) / 128, cap = (uint64_t)sm_count() * 16;
+    const uint64_t need = (b.n_reads + 127) / 128, cap = (uint64_t)sm_count() * SMASH_RECB_CTAS;
     k_rec_build<<<(unsigned)(need < cap ? need : cap), 128, 0, st>>>(ix, b, w, p);
   } else {
     k_rec_build_serial<<<grid_for_warps(b.n_reads, 6), THREADS, 0, st>>>(ix, b, w, p);
@@ -1235,7 +1248,7 @@ int launch_publish(uint64_t *host_small, const uint64_t *sam_total, const uint64
 
 int launch_sizes_scan(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st) {
   if (!b.n_reads) return 0;
-  k_sizes<<<sm_count() * 16, 128, 0, st>>>(ix, b, w, p);
+  k_sizes<<<sm_count() * SMASH_SIZES_CTAS, 128, 0, st>>>(ix, b, w, p);
   // rec_off = exclusive scan of rec_bytes over the (device-side) record count; total -> sam_total[0]
   int n = 1 + exclusive_scan_u32_devn(w.rec_bytes, w.slots_total, w.rec_base + b.n_reads, w.blk_sums2, w.rec_off,
                                       w.sam_total, st);
@@ -1477,7 +1490,7 @@ k_emit_copy(BatchDev b, WorkDev w) {
 
 int launch_emit_text(const DevIndex &ix, const BatchDev &b, const WorkDev &w, const SearchParams &p, cudaStream_t st, uint64_t n_records) {
   if (!b.n_reads || !n_records) return 0;
-  const uint64_t need = (n_records + 127) / 128, cap = (uint64_t)sm_count() * 16;
+  const uint64_t need = (n_records + 127) / 128, cap = (uint64_t)sm_count() * SMASH_TEXT_CTAS;
   k_emit_text<<<(unsigned)(need < cap ? need : cap), 128, 0, st>>>(ix, b, w, p, n_records);
   return 1;
 }
