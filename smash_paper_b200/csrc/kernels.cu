@@ -43,6 +43,12 @@ static int sm_count() {
 #ifndef SMASH_SIZES_CTAS
 #define SMASH_SIZES_CTAS 64
 #endif
+// k_rec_xe is a persistent warp-per-read kernel: its grid must be a whole number of waves.  6 CTAs per SM are resident
+// (40 registers x 256 threads); the former grid of 8 per SM ran 1.33 waves, the last one on a third of the machine
+// (records stage 1.12 -> 0.925 ms with 6, 12 or 24 CTAs per SM, r02y A/B).
+#ifndef SMASH_XE_CTAS
+#define SMASH_XE_CTAS 6
+#endif
 #ifndef SMASH_TEXT_CTAS
 #define SMASH_TEXT_CTAS 16
 #endif
@@ -1094,7 +1100,7 @@ int launch_records(const DevIndex &ix, const BatchDev &b, const WorkDev &w, cons
     k_rec_build_serial<<<grid_for_warps(b.n_reads, 6), THREADS, 0, st>>>(ix, b, w, p);
   }
   int n = 1 + exclusive_scan_u32(w.nrec, b.n_reads, w.blk_sums, w.rec_base, st, w.rec_read);    // + flat record -> read map
-  k_rec_xe<<<grid_for_warps(b.n_reads, 8), THREADS, 0, st>>>(ix, b, w, p);
+  k_rec_xe<<<grid_for_warps(b.n_reads, SMASH_XE_CTAS), THREADS, 0, st>>>(ix, b, w, p);
   return n + 1;
 }
 
